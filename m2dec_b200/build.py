@@ -1,0 +1,61 @@
+"""Builds libm2dec_b200.so in-tree with nvcc for sm_100a (no torch involved: the library is a
+plain C-ABI shared object, see include/*.h)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libm2dec_b200.so")
+
+CPP = ["bits.cpp", "backend.cpp", "plugin.cpp", "mpeg2_front.cpp", "h264_front.cpp"]
+CU = ["session.cu", "mpeg2_recon.cu"]
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(src_list, out):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    deps = list(src_list)
+    for d in (CSRC, os.path.join(ROOT, "include")):
+        deps += [os.path.join(d, f) for f in os.listdir(d)]
+    return any(os.path.getmtime(p) > t for p in deps if os.path.isfile(p))
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in CPP + CU if os.path.exists(os.path.join(CSRC, f))]
+    if not force and not _newer(srcs, OUT):
+        return OUT
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    common = ["-O3", "-std=c++17", "-lineinfo", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+    procs = []
+    objs = []
+    for s in srcs:
+        o = os.path.join(objdir, os.path.basename(s) + ".o")
+        objs.append(o)
+        cmd = [NVCC] + ARCH + common + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(" ".join(cmd) + "\n" + out + "\n")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-fPIC", "-lpthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,49 @@
+// backend.cpp — picture hand-off from a front end to the device session / tap.
+#include "frontend.h"
+#include <stdlib.h>
+#include <stdio.h>
+
+namespace b2 {
+
+Backend::Backend() : tap_(nullptr), tap_arg_(nullptr), device_off_(false), dead_(false), cuda_device_(0), sess_(nullptr), codec_(0), width_(0), height_(0), nframes_(0) {
+	const char *e = getenv("B2_CUDA_DEVICE");
+	if (e) cuda_device_ = atoi(e);
+}
+
+Backend::~Backend() { release(); }
+
+void Backend::release() {
+	if (sess_) { b2_session_destroy(sess_); sess_ = nullptr; }
+}
+
+int Backend::configure(int codec, int width, int height, int nframes) {
+	release();
+	dead_ = false;
+	codec_ = codec; width_ = width; height_ = height; nframes_ = nframes;
+	if (device_off_) return 0;
+	int err = b2_session_create(cuda_device_, codec, width, height, nframes, &sess_);
+	if (err < 0) {
+		// There is deliberately no CPU reconstruction to fall back to.
+		fprintf(stderr, "m2dec_b200: cannot create CUDA reconstruction session: %s\n", b2_last_error());
+		sess_ = nullptr;
+		dead_ = true;
+	}
+	return err;
+}
+
+int Backend::submit(int codec, const void *picture) {
+	int err = 0;
+	if (tap_) err = tap_(tap_arg_, codec, picture);
+	if (device_off_) return err;
+	if (!sess_) return -1;
+	if (codec == B2_CODEC_MPEG2) return b2_session_submit_mpeg2(sess_, (const b2_m2_picture *)picture);
+	return -1;
+}
+
+int Backend::fetch(int idx, uint8_t *luma, uint8_t *chroma) {
+	if (device_off_) return 0;
+	if (!sess_) return -1;
+	return b2_session_download(sess_, idx, luma, chroma);
+}
+
+}  // namespace b2

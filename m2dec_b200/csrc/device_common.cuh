@@ -1,0 +1,33 @@
+// device_common.cuh — declarations shared by the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2_recon.h"
+
+namespace b2 {
+
+void set_error(const char *fmt, ...);
+#define B2_CUDA_OK(expr)                                                                    \
+	do {                                                                                    \
+		cudaError_t e__ = (expr);                                                           \
+		if (e__ != cudaSuccess) {                                                           \
+			b2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+			return -1;                                                                      \
+		}                                                                                   \
+	} while (0)
+
+// One MPEG-2 picture as the kernel sees it (all pointers are device pointers).
+struct M2Job {
+	uint8_t *dst_y, *dst_c;
+	const uint8_t *fwd_y, *fwd_c, *bwd_y, *bwd_c;
+	const b2_m2_mb *mbs;
+	const int16_t *coefs;
+	int32_t mb_w, mb_h;
+};
+
+// Launch reconstruction of n_jobs independent pictures of identical size in one grid.
+int launch_mpeg2(cudaStream_t stream, const M2Job *d_jobs, int n_jobs, int mb_w, int mb_h);
+
+__device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+}  // namespace b2

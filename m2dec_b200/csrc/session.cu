@@ -1,0 +1,186 @@
+// session.cu — device-side C ABI (include/b2_recon.h): a reconstruction session owns one
+// CUDA stream, a pool of device-resident NV12 frames and a pinned staging ring through which
+// each picture's SoA travels host -> HBM in a single asynchronous copy.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include "device_common.cuh"
+
+namespace b2 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+enum { NSLOT = 4 };
+
+struct StageSlot {
+	uint8_t *host;
+	uint8_t *dev;
+	size_t cap;
+	cudaEvent_t done;      // recorded after the kernels that read the slot
+	bool pending;
+};
+
+struct b2_session {
+	int dev, codec, width, height, nframes;
+	size_t frame_bytes;
+	cudaStream_t stream;
+	uint8_t *frames;
+	StageSlot slots[NSLOT];
+	int next_slot;
+	uint64_t launches;
+};
+
+extern "C" const char *b2_last_error(void) { return b2::g_err; }
+
+extern "C" int b2_device_count(void) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+		return -1;
+	}
+	return n;
+}
+
+extern "C" int b2_session_create(int cuda_device, int codec, int width, int height, int nframes, b2_session **out) {
+	if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || nframes <= 0) {
+		set_error("b2_session_create: bad arguments (%dx%d, %d frames)", width, height, nframes);
+		return -1;
+	}
+	int n = b2_device_count();
+	if (n <= 0) {
+		if (n == 0) set_error("no CUDA device visible");
+		return -1;
+	}
+	B2_CUDA_OK(cudaSetDevice(cuda_device));
+	b2_session *s = new b2_session();
+	memset(s, 0, sizeof(*s));
+	s->dev = cuda_device;
+	s->codec = codec;
+	s->width = width;
+	s->height = height;
+	s->nframes = nframes;
+	s->frame_bytes = (size_t)width * height * 3 / 2;
+	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	B2_CUDA_OK(cudaMalloc(&s->frames, s->frame_bytes * nframes));
+	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * nframes, s->stream));
+	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming));
+	*out = s;
+	return 0;
+}
+
+extern "C" void b2_session_destroy(b2_session *s) {
+	if (!s) return;
+	cudaSetDevice(s->dev);
+	cudaStreamSynchronize(s->stream);
+	for (int i = 0; i < NSLOT; ++i) {
+		if (s->slots[i].host) cudaFreeHost(s->slots[i].host);
+		if (s->slots[i].dev) cudaFree(s->slots[i].dev);
+		cudaEventDestroy(s->slots[i].done);
+	}
+	cudaFree(s->frames);
+	cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+// Obtain a staging slot of at least `bytes`, waiting for its previous use to drain.
+static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
+	StageSlot *sl = &s->slots[s->next_slot];
+	s->next_slot = (s->next_slot + 1) % NSLOT;
+	if (sl->pending) {
+		B2_CUDA_OK(cudaEventSynchronize(sl->done));
+		sl->pending = false;
+	}
+	if (sl->cap < bytes) {
+		if (sl->host) cudaFreeHost(sl->host);
+		if (sl->dev) cudaFree(sl->dev);
+		sl->host = sl->dev = nullptr;
+		size_t cap = bytes + bytes / 2 + 4096;
+		B2_CUDA_OK(cudaMallocHost(&sl->host, cap));
+		B2_CUDA_OK(cudaMalloc(&sl->dev, cap));
+		sl->cap = cap;
+	}
+	*out = sl;
+	return 0;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
+	if (!s || !p || s->codec != B2_CODEC_MPEG2) return -1;
+	if (p->mb_w * 16 != s->width || p->mb_h * 16 != s->height) {
+		set_error("picture %dx%d MB does not match session %dx%d", p->mb_w, p->mb_h, s->width, s->height);
+		return -1;
+	}
+	if ((unsigned)p->dst >= (unsigned)s->nframes || (unsigned)p->fwd >= (unsigned)s->nframes ||
+	    (unsigned)p->bwd >= (unsigned)s->nframes) return -1;
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	size_t off_mbs = align_up(sizeof(M2Job), 256);
+	size_t off_coef = align_up(off_mbs + sizeof(b2_m2_mb) * p->n_mbs, 256);
+	size_t total = off_coef + (size_t)p->n_blocks * 128;
+	StageSlot *sl;
+	if (acquire_slot(s, total, &sl) < 0) return -1;
+	size_t luma = (size_t)s->width * s->height;
+	M2Job job;
+	job.dst_y = s->frames + s->frame_bytes * p->dst;
+	job.dst_c = job.dst_y + luma;
+	job.fwd_y = s->frames + s->frame_bytes * p->fwd;
+	job.fwd_c = job.fwd_y + luma;
+	job.bwd_y = s->frames + s->frame_bytes * p->bwd;
+	job.bwd_c = job.bwd_y + luma;
+	job.mbs = (const b2_m2_mb *)(sl->dev + off_mbs);
+	job.coefs = (const int16_t *)(sl->dev + off_coef);
+	job.mb_w = p->mb_w;
+	job.mb_h = p->mb_h;
+	memcpy(sl->host, &job, sizeof(job));
+	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_m2_mb) * p->n_mbs);
+	if (p->n_blocks) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_blocks * 128);
+	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
+	if (launch_mpeg2(s->stream, (const M2Job *)sl->dev, 1, p->mb_w, p->mb_h) < 0) return -1;
+	s->launches++;
+	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
+	sl->pending = true;
+	return 0;
+}
+
+extern "C" int b2_session_sync(b2_session *s) {
+	if (!s) return -1;
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	B2_CUDA_OK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma) {
+	if (!s || (unsigned)idx >= (unsigned)s->nframes || !luma || !chroma) return -1;
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	size_t ls = (size_t)s->width * s->height;
+	const uint8_t *src = s->frames + s->frame_bytes * idx;
+	B2_CUDA_OK(cudaMemcpyAsync(luma, src, ls, cudaMemcpyDeviceToHost, s->stream));
+	B2_CUDA_OK(cudaMemcpyAsync(chroma, src + ls, ls / 2, cudaMemcpyDeviceToHost, s->stream));
+	B2_CUDA_OK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" int b2_session_upload(b2_session *s, int idx, const uint8_t *luma, const uint8_t *chroma) {
+	if (!s || (unsigned)idx >= (unsigned)s->nframes || !luma || !chroma) return -1;
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	size_t ls = (size_t)s->width * s->height;
+	uint8_t *dst = s->frames + s->frame_bytes * idx;
+	B2_CUDA_OK(cudaMemcpyAsync(dst, luma, ls, cudaMemcpyHostToDevice, s->stream));
+	B2_CUDA_OK(cudaMemcpyAsync(dst + ls, chroma, ls / 2, cudaMemcpyHostToDevice, s->stream));
+	B2_CUDA_OK(cudaStreamSynchronize(s->stream));
+	return 0;
+}
+
+extern "C" uint64_t b2_session_launches(const b2_session *s) { return s ? s->launches : 0; }

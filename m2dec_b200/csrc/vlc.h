@@ -1,0 +1,82 @@
+// vlc.h — variable-length-code tables written as bit strings (as printed in the standards'
+// annexes) and a two-level lookup decoder built from them at start-up.  The same string
+// tables drive the test-only bitstream writer (tools/streamgen), so a typo shows up as a
+// mismatch against the reference decoder rather than cancelling out silently... it would
+// cancel out, which is why tests/ also decode writer output with the compiled reference.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "bits.h"
+
+namespace b2 {
+
+struct VlcCode {
+	const char *bits;   // '0'/'1' characters, spaces ignored
+	int32_t value;
+};
+
+inline int vlc_parse(const char *s, uint32_t *code) {
+	int len = 0;
+	uint32_t c = 0;
+	for (; *s; ++s) {
+		if (*s == '0' || *s == '1') { c = (c << 1) | (uint32_t)(*s - '0'); ++len; }
+	}
+	*code = c;
+	return len;
+}
+
+class Vlc {
+public:
+	enum { INVALID = INT32_MIN };
+	Vlc() : l1_(0), maxlen_(0) {}
+	void build(const VlcCode *codes, int n, int l1bits) {
+		l1_ = l1bits;
+		maxlen_ = 0;
+		std::vector<uint32_t> code(n);
+		std::vector<int> len(n);
+		for (int i = 0; i < n; ++i) {
+			len[i] = vlc_parse(codes[i].bits, &code[i]);
+			if (len[i] > maxlen_) maxlen_ = len[i];
+		}
+		if (l1_ > maxlen_) l1_ = maxlen_;
+		int l2 = maxlen_ - l1_;
+		tab_.assign((size_t)1 << l1_, Entry{INVALID, 0});
+		for (int i = 0; i < n; ++i) {
+			if (len[i] <= l1_) {
+				uint32_t base = code[i] << (l1_ - len[i]);
+				for (uint32_t k = 0; k < (1u << (l1_ - len[i])); ++k)
+					tab_[base + k] = Entry{codes[i].value, (int8_t)len[i]};
+			} else {
+				uint32_t prefix = code[i] >> (len[i] - l1_);
+				if (tab_[prefix].len != -1) {
+					// open a sub-table
+					tab_[prefix] = Entry{(int32_t)tab_.size(), -1};
+					tab_.resize(tab_.size() + ((size_t)1 << l2), Entry{INVALID, 0});
+				}
+				uint32_t off = (uint32_t)tab_[prefix].value;
+				int rem = len[i] - l1_;
+				uint32_t sub = code[i] & ((1u << rem) - 1);
+				uint32_t base = sub << (l2 - rem);
+				for (uint32_t k = 0; k < (1u << (l2 - rem)); ++k)
+					tab_[off + base + k] = Entry{codes[i].value, (int8_t)len[i]};
+			}
+		}
+	}
+	// Returns the decoded value, or INVALID (no bits consumed) for an undefined code.
+	inline int32_t decode(BitReader &br) const {
+		uint32_t v = br.peek(maxlen_);
+		const Entry *e = &tab_[v >> (maxlen_ - l1_)];
+		if (e->len == -1) e = &tab_[(uint32_t)e->value + (v & ((1u << (maxlen_ - l1_)) - 1))];
+		if (e->len <= 0) return INVALID;
+		br.skip(e->len);
+		return e->value;
+	}
+	int maxlen() const { return maxlen_; }
+private:
+	struct Entry { int32_t value; int8_t len; };
+	std::vector<Entry> tab_;
+	int l1_, maxlen_;
+};
+
+}  // namespace b2
