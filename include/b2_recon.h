@@ -59,6 +59,87 @@ typedef struct {
 } b2_m2_picture;
 
 /* ------------------------------------------------------------------------------------ */
+/* H.264 (frame pictures, 4:2:0, 8 bit).  Per picture: one b2_h264_mb and one            */
+/* b2_h264_dbk per macroblock in raster order, a pool of motion-compensation records,     */
+/* and a pool of coefficient records (16 int16 each, levels BEFORE dequantisation).       */
+/* ------------------------------------------------------------------------------------ */
+
+enum { B2_H4_INTER = 0, B2_H4_I4x4 = 1, B2_H4_I8x8 = 2, B2_H4_I16x16 = 3, B2_H4_IPCM = 4 };
+enum { B2_H4_T8x8 = 0x01 };     /* b2_h264_mb.flags: transform_size_8x8_flag */
+
+/* b2_h264_mb.nz — which coefficient records exist, bit order == record order:
+ *   bit 0        Intra16x16 luma DC (16 levels, raster 4x4 of the DC matrix)
+ *   bits 1..16   luma 4x4 block k = bit-1 (k in decode order);
+ *                an 8x8-transform block i owns bits 1+4i..4+4i (64 levels, raster 8x8)
+ *   bit 17       chroma DC (one record: Cb c0..c3 then Cr c0..c3, raster 2x2)
+ *   bits 18..21  Cb AC blocks 0..3 (raster 2x2 of 4x4 blocks), bits 22..25 Cr AC
+ * I_PCM: 12 records hold the 384 raw sample bytes (256 Y, 64 Cb, 64 Cr), nz = 0xfff.
+ * Record index of bit b = coef_idx + popcount(nz & ((1 << b) - 1)).
+ * Levels are stored in raster order inside a record (position 4*y + x), i.e. the inverse
+ * zig-zag (h264.cpp:1927-1994) is already applied; dequantisation (h264.cpp:2005-2022,
+ * 964-1054) is done on the device from qp_y / qp_cb / qp_cr.                               */
+typedef struct {
+	uint8_t type;           /* B2_H4_*                                                            */
+	uint8_t flags;
+	uint8_t qp_y, qp_cb, qp_cr;  /* QPs in force when this MB's residual was dequantised (set_qp, h264.cpp:1092-1119) */
+	uint8_t intra_avail;    /* bit0 left, bit1 top, bit2 top-right, bit3 top-left: MB-level availability as used by the predictors (h264.cpp:9704-9715, constrained-intra mask 3271-3273) */
+	uint8_t i16_mode;       /* Intra16x16 prediction mode 0 V, 1 H, 2 DC, 3 plane                 */
+	uint8_t chroma_mode;    /* intra_chroma_pred_mode 0 DC, 1 H, 2 V, 3 plane                     */
+	uint32_t nz;
+	uint32_t coef_idx;      /* first coefficient record of this MB                                */
+	uint32_t mc_idx;        /* first motion-compensation record of this MB                        */
+	uint8_t mc_cnt;
+	uint8_t intra_avail_c;  /* availability mask the chroma predictor received (differs from intra_avail only for a no-residual Intra4x4 MB under constrained_intra_pred, h264.cpp:3281 vs 3292) */
+	uint8_t reserved[2];
+	uint8_t i4_modes[8];    /* Intra4x4 (16 nibbles) / Intra8x8 (4 nibbles) prediction modes, block k in nibble k */
+} b2_h264_mb;               /* 32 bytes */
+
+/* One call of mb->inter_pred (h264.h:396; 14 call sites). */
+typedef struct {
+	uint8_t pos;            /* (y4 << 2) | x4: top-left 4x4 block of the partition inside the MB  */
+	uint8_t size;           /* (h4 << 4) | w4: partition size in 4-pel units (1, 2 or 4)          */
+	int8_t ref_frame[2];    /* frame-pool index for list 0 / 1 (refs[lx][ref_idx].frame_idx, h264.cpp:6740); -1 = list unused */
+	int8_t ref_idx[2];      /* reference index (selects explicit weights)                         */
+	uint8_t reserved[2];
+	int16_t mv[2][2];       /* [list][x,y] quarter-pel                                            */
+} b2_h264_mc;               /* 16 bytes */
+
+/* b2_h264_dbk.flags */
+enum {
+	B2_DBK_LEFT_BS4 = 0x01,   /* left MB edge has bS 4 (str4_horiz, h264.h:344-348)               */
+	B2_DBK_TOP_BS4 = 0x02,    /* top MB edge has bS 4 (str4_vert)                                 */
+	B2_DBK_OFF = 0x04,        /* disable_deblocking_filter_idc == 1 for this MB's slice           */
+	B2_DBK_LEFT_EDGE = 0x08,  /* left MB edge is filtered (exists and not excluded by idc == 2)   */
+	B2_DBK_TOP_EDGE = 0x10    /* top MB edge is filtered                                          */
+};
+
+/* Deblocking input for one MB: the reference's deblock_info_t (h264.h:344-348) restated.
+ * bs_v: the four vertical edges (filtered horizontally; reference str_horiz), byte e = edge
+ * e (0 = MB edge), 2 bits per 4-line segment, top segment in the low bits: 0 none, 1..3 = bS
+ * (3 also stands for bS 4 on an MB edge when the BS4 flag is set).  bs_h likewise for the
+ * four horizontal edges, left segment in the low bits.                                      */
+typedef struct {
+	uint32_t bs_v;
+	uint32_t bs_h;
+	int8_t qp_y, qp_cb, qp_cr;   /* as the reference stores them for the filter (I_PCM: 0 and qpc - qp, h264.cpp:4749-4751) */
+	uint8_t flags;
+	int8_t alpha_off, beta_off;  /* FilterOffsetA / FilterOffsetB (= 2 * slice_*_offset_div2)          */
+	uint8_t reserved[2];
+} b2_h264_dbk;              /* 16 bytes */
+
+typedef struct {
+	int32_t mb_w, mb_h;
+	int32_t dst;               /* frame-pool index being reconstructed                                */
+	int32_t deblock;           /* != 0 if any MB of the picture has the loop filter enabled          */
+	uint32_t n_mbs, n_mcs, n_coef_recs;
+	uint32_t n_intra;          /* number of intra macroblocks (0: the intra wavefront is skipped)     */
+	const b2_h264_mb *mbs;
+	const b2_h264_dbk *dbk;
+	const b2_h264_mc *mcs;
+	const int16_t *coefs;
+} b2_h264_picture;
+
+/* ------------------------------------------------------------------------------------ */
 /* Picture tap: a hook that sees every picture the front end emits, before it is queued   */
 /* for the device.  Used by bench.py to capture SoA for kernel replay and by tests/ to    */
 /* hand the same records to the CPU oracle.  It never produces pixels itself.             */
@@ -86,6 +167,7 @@ int b2_session_create(int cuda_device, int codec, int width, int height, int nfr
 void b2_session_destroy(b2_session *s);
 /* Asynchronous: copies the picture's SoA into pinned staging, enqueues H2D + kernels.     */
 int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *pic);
+int b2_session_submit_h264(b2_session *s, const b2_h264_picture *pic);
 /* Waits for everything queued so far, then copies frame `idx` to host memory.             */
 int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma);
 int b2_session_upload(b2_session *s, int idx, const uint8_t *luma, const uint8_t *chroma);

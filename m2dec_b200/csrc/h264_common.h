@@ -1,0 +1,243 @@
+// h264_common.h — H.264 syntax-level context shared by the host front end (h264_front.cpp)
+// and the test-only bitstream writer (tools/streamgen): scan tables, the coded_block_pattern
+// mapping, and the neighbour derivations of clauses 6.4.11, 8.3.1.1, 8.4.1.3 and 9.2.1
+// (availability, Intra4x4PredMode prediction, motion-vector prediction, CAVLC nC).
+//
+// The reference keeps this state as packed per-row words inside h264d_mb_current
+// (left4x4pred/top4x4pred, left4x4coef/top4x4coef, left4x4inter/top4x4inter, h264.h:330-395)
+// and derives neighbours with hand-unrolled code (calc_mv*, h264.cpp:6669-6724, 7379-8330).
+// Here the picture keeps full-frame per-4x4 arrays, which makes every neighbour a lookup.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+namespace b2 { namespace h4 {
+
+// 4x4 luma block k (decode order) -> position inside the MB in 4-pel units
+static const uint8_t blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
+static const uint8_t blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+// raster position (y4 * 4 + x4) -> decode-order index
+static const uint8_t raster_to_blk[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+
+// zig-zag scan index -> raster position 4*y + x (frame scan, Table 8-2 / Figure 8-8)
+static const uint8_t zigzag4x4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+static const uint8_t zigzag8x8[64] = {
+	0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20,
+	13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59,
+	52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// Table 9-4: codeNum -> coded_block_pattern for [0] Intra4x4/8x8, [1] Inter (ChromaArrayType 1)
+static const uint8_t cbp_from_code[2][48] = {
+	{47, 31, 15, 0, 23, 27, 29, 30, 7, 11, 13, 14, 39, 43, 45, 46, 16, 3, 5, 10, 12, 19, 21, 26,
+	 28, 35, 37, 42, 44, 1, 2, 4, 8, 17, 18, 20, 24, 6, 9, 22, 25, 32, 33, 34, 36, 40, 38, 41},
+	{0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44,
+	 33, 34, 36, 40, 39, 43, 45, 46, 17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41}};
+
+// Table 8-15: qPI -> QPC
+static inline int chroma_qp(int qp_y, int offset) {
+	static const uint8_t tab[22] = {29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39};
+	int q = qp_y + offset;
+	if (q < 0) q = 0;
+	if (q > 51) q = 51;
+	return q < 30 ? q : tab[q - 30];
+}
+
+enum MbKind : uint8_t { MB_NONE = 0, MB_INTER, MB_SKIP, MB_I4x4, MB_I8x8, MB_I16x16, MB_IPCM };
+static inline bool kind_is_intra(uint8_t k) { return k >= MB_I4x4; }
+
+struct MbInfo {
+	uint16_t slice;     // slice number inside the picture, 0xffff = not decoded yet
+	uint8_t kind;
+	uint8_t qp_y;       // QP'Y after this MB (the predictor for the next mb_qp_delta)
+	uint8_t cbp;
+	uint8_t t8x8;
+	uint8_t chroma_mode;
+	uint8_t pad;
+};
+
+struct Neighbour {
+	bool avail;
+	int ref;            // -1: intra or list unused
+	int16_t mv[2];
+};
+
+// Per-picture neighbour context.
+class PicCtx {
+public:
+	int mb_w, mb_h, w4, h4;
+	std::vector<MbInfo> mb;
+	std::vector<uint8_t> nnz;        // [mb][24]: luma raster 0..15, Cb 16..19, Cr 20..23
+	std::vector<int8_t> ipred;       // [mb][16] raster Intra4x4/8x8PredMode (2 when not I4x4/I8x8)
+	std::vector<int16_t> mv[2];      // [(gy * w4 + gx) * 2]
+	std::vector<int8_t> ref[2];      // per 4x4: -2 not decoded, -1 intra / unused list, >= 0 refIdx
+	std::vector<int8_t> refpic[2];   // per 4x4: frame-pool index of the reference picture, -1 none
+
+	void resize(int mbw, int mbh) {
+		mb_w = mbw; mb_h = mbh; w4 = mbw * 4; h4 = mbh * 4;
+		size_t n = (size_t)mbw * mbh;
+		mb.assign(n, MbInfo());
+		nnz.assign(n * 24, 0);
+		ipred.assign(n * 16, 2);
+		for (int l = 0; l < 2; ++l) {
+			mv[l].assign(n * 16 * 2, 0);
+			ref[l].assign(n * 16, -2);
+			refpic[l].assign(n * 16, -1);
+		}
+	}
+	void begin_picture() {
+		for (auto &m : mb) { m = MbInfo(); m.slice = 0xffff; }
+		std::fill(nnz.begin(), nnz.end(), 0);
+		std::fill(ipred.begin(), ipred.end(), 2);
+		for (int l = 0; l < 2; ++l) {
+			std::fill(mv[l].begin(), mv[l].end(), 0);
+			std::fill(ref[l].begin(), ref[l].end(), -2);
+			std::fill(refpic[l].begin(), refpic[l].end(), -1);
+		}
+	}
+
+	// --- macroblock-level availability (6.4.8): same slice and already decoded --------------
+	inline bool mb_avail(int mbx, int mby, int cur_slice) const {
+		if (mbx < 0 || mby < 0 || mbx >= mb_w || mby >= mb_h) return false;
+		return mb[(size_t)mby * mb_w + mbx].slice == cur_slice;
+	}
+	// bit0 left, bit1 top, bit2 top-right, bit3 top-left
+	inline int mb_avail_mask(int mbx, int mby, int cur_slice) const {
+		return (mb_avail(mbx - 1, mby, cur_slice) ? 1 : 0) | (mb_avail(mbx, mby - 1, cur_slice) ? 2 : 0) |
+		       (mb_avail(mbx + 1, mby - 1, cur_slice) ? 4 : 0) | (mb_avail(mbx - 1, mby - 1, cur_slice) ? 8 : 0);
+	}
+
+	// --- start of a macroblock: its 16 blocks become "not yet decoded" ------------------------
+	void open_mb(int mbx, int mby, int cur_slice) {
+		MbInfo &m = mb[(size_t)mby * mb_w + mbx];
+		m.slice = (uint16_t)cur_slice;
+		for (int y = 0; y < 4; ++y)
+			for (int x = 0; x < 4; ++x) {
+				size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x;
+				ref[0][g] = ref[1][g] = -2;
+			}
+	}
+
+	// fill a w4 x h4 partition (4-pel units) of the current MB
+	void set_motion(int list, int mbx, int mby, int x4, int y4, int pw, int ph, int refidx, int pic, int mvx, int mvy) {
+		for (int y = y4; y < y4 + ph; ++y)
+			for (int x = x4; x < x4 + pw; ++x) {
+				size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x;
+				ref[list][g] = (int8_t)refidx;
+				refpic[list][g] = (int8_t)pic;
+				mv[list][g * 2] = (int16_t)mvx;
+				mv[list][g * 2 + 1] = (int16_t)mvy;
+			}
+	}
+	void set_intra_motion(int mbx, int mby) {
+		for (int l = 0; l < 2; ++l) set_motion(l, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
+	}
+
+	// neighbouring 4x4 block at global 4-pel coordinates (gx, gy)
+	inline Neighbour nb(int list, int gx, int gy, int cur_slice) const {
+		Neighbour n = {false, -1, {0, 0}};
+		if (gx < 0 || gy < 0 || gx >= w4 || gy >= h4) return n;
+		if (mb[(size_t)(gy >> 2) * mb_w + (gx >> 2)].slice != cur_slice) return n;
+		size_t g = (size_t)gy * w4 + gx;
+		int r = ref[list][g];
+		if (r == -2) return n;
+		n.avail = true;
+		n.ref = r;
+		if (r >= 0) { n.mv[0] = mv[list][g * 2]; n.mv[1] = mv[list][g * 2 + 1]; }
+		return n;
+	}
+
+	static inline int median3(int a, int b, int c) {
+		int mx = a > b ? a : b, mn = a < b ? a : b;
+		return c > mx ? mx : (c < mn ? mn : c);
+	}
+
+	// 8.4.1.3: motion vector prediction for a partition at (x4, y4) of size pw x ph (4-pel units)
+	// shape: 0 generic/median, 1 = 16x8 partition (part = 0 top, 1 bottom), 2 = 8x16 (0 left, 1 right)
+	void predict_mv(int list, int mbx, int mby, int x4, int y4, int pw, int refidx, int cur_slice,
+	                int shape, int part, int16_t out[2]) const {
+		int gx = mbx * 4 + x4, gy = mby * 4 + y4;
+		Neighbour a = nb(list, gx - 1, gy, cur_slice);
+		Neighbour b = nb(list, gx, gy - 1, cur_slice);
+		Neighbour c = nb(list, gx + pw, gy - 1, cur_slice);
+		if (!c.avail) c = nb(list, gx - 1, gy - 1, cur_slice);
+		if (shape == 1) {
+			if (part == 0 && b.avail && b.ref == refidx) { out[0] = b.mv[0]; out[1] = b.mv[1]; return; }
+			if (part == 1 && a.avail && a.ref == refidx) { out[0] = a.mv[0]; out[1] = a.mv[1]; return; }
+		} else if (shape == 2) {
+			if (part == 0 && a.avail && a.ref == refidx) { out[0] = a.mv[0]; out[1] = a.mv[1]; return; }
+			if (part == 1 && c.avail && c.ref == refidx) { out[0] = c.mv[0]; out[1] = c.mv[1]; return; }
+		}
+		if (!b.avail && !c.avail && a.avail) { b = a; c = a; }
+		int ma = a.avail && a.ref == refidx, mb_ = b.avail && b.ref == refidx, mc = c.avail && c.ref == refidx;
+		if (ma + mb_ + mc == 1) {
+			const Neighbour &s = ma ? a : (mb_ ? b : c);
+			out[0] = s.mv[0]; out[1] = s.mv[1];
+			return;
+		}
+		out[0] = (int16_t)median3(a.mv[0], b.mv[0], c.mv[0]);
+		out[1] = (int16_t)median3(a.mv[1], b.mv[1], c.mv[1]);
+	}
+
+	// 8.4.1.1: P_Skip motion vector
+	void pskip_mv(int mbx, int mby, int cur_slice, int16_t out[2]) const {
+		int gx = mbx * 4, gy = mby * 4;
+		Neighbour a = nb(0, gx - 1, gy, cur_slice);
+		Neighbour b = nb(0, gx, gy - 1, cur_slice);
+		out[0] = out[1] = 0;
+		if (!a.avail || !b.avail) return;
+		if (a.ref == 0 && a.mv[0] == 0 && a.mv[1] == 0) return;
+		if (b.ref == 0 && b.mv[0] == 0 && b.mv[1] == 0) return;
+		predict_mv(0, mbx, mby, 0, 0, 4, 0, cur_slice, 0, 0, out);
+	}
+
+	// 9.2.1: nC for the block at (x, y) in units of blocks; plane 0 luma (4x4 grid), 1 Cb, 2 Cr (2x2 grid)
+	int cavlc_nc(int mbx, int mby, int plane, int x, int y, int cur_slice) const {
+		int dim = plane ? 2 : 4, base = plane ? 12 + plane * 4 : 0;
+		int na = -1, nb_ = -1;
+		if (x > 0) na = nnz[((size_t)mby * mb_w + mbx) * 24 + base + y * dim + x - 1];
+		else if (mb_avail(mbx - 1, mby, cur_slice)) na = nnz[((size_t)mby * mb_w + mbx - 1) * 24 + base + y * dim + dim - 1];
+		if (y > 0) nb_ = nnz[((size_t)mby * mb_w + mbx) * 24 + base + (y - 1) * dim + x];
+		else if (mb_avail(mbx, mby - 1, cur_slice)) nb_ = nnz[((size_t)(mby - 1) * mb_w + mbx) * 24 + base + (dim - 1) * dim + x];
+		if (na >= 0 && nb_ >= 0) return (na + nb_ + 1) >> 1;
+		if (na >= 0) return na;
+		if (nb_ >= 0) return nb_;
+		return 0;
+	}
+	inline uint8_t *nnz_of(int mbx, int mby) { return &nnz[((size_t)mby * mb_w + mbx) * 24]; }
+	inline int8_t *ipred_of(int mbx, int mby) { return &ipred[((size_t)mby * mb_w + mbx) * 16]; }
+	inline MbInfo &info(int mbx, int mby) { return mb[(size_t)mby * mb_w + mbx]; }
+	inline const MbInfo &info(int mbx, int mby) const { return mb[(size_t)mby * mb_w + mbx]; }
+
+	// 8.3.1.1: predIntra4x4PredMode for the 4x4 block at raster (x4, y4) of the current MB.
+	// constrained: constrained_intra_pred_flag (inter neighbours then count as unavailable).
+	int predict_ipred(int mbx, int mby, int x4, int y4, int cur_slice, bool constrained) const {
+		int m[2];
+		for (int k = 0; k < 2; ++k) {
+			int nx = x4 - (k == 0), ny = y4 - (k == 1);
+			int nmbx = mbx, nmby = mby;
+			if (nx < 0) { nx = 3; nmbx--; }
+			if (ny < 0) { ny = 3; nmby--; }
+			if (nmbx != mbx || nmby != mby) {
+				if (!mb_avail(nmbx, nmby, cur_slice)) return 2;
+				const MbInfo &o = info(nmbx, nmby);
+				if (!kind_is_intra(o.kind) && constrained) return 2;
+				m[k] = (o.kind == MB_I4x4 || o.kind == MB_I8x8) ? ipred[((size_t)nmby * mb_w + nmbx) * 16 + ny * 4 + nx] : 2;
+			} else {
+				m[k] = ipred[((size_t)mby * mb_w + mbx) * 16 + ny * 4 + nx];
+			}
+		}
+		return m[0] < m[1] ? m[0] : m[1];
+	}
+};
+
+// Reference picture marking + list construction state (clauses 8.2.4, 8.2.5), shared so the
+// writer can produce streams whose lists it knows.
+struct RefPic {
+	int frame_idx;     // frame-pool index
+	int frame_num;     // FrameNum
+	int long_idx;      // LongTermFrameIdx, -1 when short term
+	int poc;
+};
+
+}}  // namespace b2::h4

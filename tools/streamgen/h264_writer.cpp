@@ -1,0 +1,539 @@
+// h264_writer.cpp — TEST-ONLY H.264 elementary-stream writer (not an encoder: it does not look
+// at pictures).  It draws random but *valid* syntax — macroblock types, partitions, motion
+// vectors, intra modes, coefficient levels, QP changes, slices — and entropy-codes it with
+// CAVLC, so that every reconstruction path of a decoder is exercised with known-legal input.
+// Streams stay inside the region where the reference decoder is well defined (SURVEY.md §8a
+// hazards 1, 2, 5, 10): bounded residual amplitude, beta_offset >= alpha_offset,
+// seq_parameter_set_id 0, disable_deblocking_filter_idc in {0, 1}.
+//
+// Neighbour-dependent syntax (mvd, prev_intra4x4_pred_mode, coeff_token nC, P_Skip motion)
+// uses the same context class as the decoder front end (m2dec_b200/csrc/h264_common.h); that
+// a shared mistake cannot hide is guaranteed by decoding every stream with the compiled
+// reference (tests/, oracle/_ref).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "bitwriter.h"
+#include "h264_cavlc_tables.h"
+#include "h264_common.h"
+#include "streamgen.h"
+
+using namespace b2::h4;
+namespace h4t = b2::h4t;
+
+namespace sg {
+namespace {
+
+struct Enc {
+	VlcEnc coeff_token[5], total_zeros[15], total_zeros_cdc[3], run_before[7];
+	uint8_t code_from_cbp[2][48];
+	Enc() {
+		for (int i = 0; i < 5; ++i) coeff_token[i].build(h4t::coeff_token_tabs[i].codes, h4t::coeff_token_tabs[i].n);
+		for (int i = 0; i < 15; ++i) total_zeros[i].build(h4t::total_zeros_tabs[i].codes, h4t::total_zeros_tabs[i].n);
+		for (int i = 0; i < 3; ++i) total_zeros_cdc[i].build(h4t::total_zeros_cdc_tabs[i].codes, h4t::total_zeros_cdc_tabs[i].n);
+		for (int i = 0; i < 7; ++i) run_before[i].build(h4t::run_before_tabs[i].codes, h4t::run_before_tabs[i].n);
+		for (int t = 0; t < 2; ++t)
+			for (int c = 0; c < 48; ++c) code_from_cbp[t][cbp_from_code[t][c]] = (uint8_t)c;
+	}
+};
+
+// dequantisation scale of position (x, y) of a 4x4 block (flat matrices)
+int level_scale(int qp, int x, int y) {
+	static const int na[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+	int cls = ((x & 1) == 0 && (y & 1) == 0) ? 0 : (((x & 1) && (y & 1)) ? 1 : 2);
+	return na[qp % 6][cls] << (qp / 6);
+}
+
+class Writer {
+public:
+	Writer(const H264Opts &o) : o_(o), rng_((uint64_t)o.seed) {
+		ctx_.resize(o.mbw, o.mbh);
+	}
+
+	std::vector<uint8_t> run() {
+		write_sps();
+		write_pps();
+		int frame_num = 0, since_idr = 0;
+		for (int f = 0; f < o_.frames; ++f) {
+			bool idr = (f % o_.gop) == 0;
+			if (idr) { frame_num = 0; since_idr = 0; idr_id_ = (idr_id_ + 1) & 0xff; }
+			picture(idr, frame_num, since_idr);
+			frame_num = (frame_num + 1) & 15;
+			since_idr++;
+		}
+		return out_;
+	}
+
+private:
+	// ---- NAL ------------------------------------------------------------------------------------
+	void emit_nal(int ref_idc, int type, BitWriter &bw) {
+		static const uint8_t sc[4] = {0, 0, 0, 1};
+		out_.insert(out_.end(), sc, sc + 4);
+		out_.push_back((uint8_t)((ref_idc << 5) | type));
+		int zeros = 0;
+		for (uint8_t b : bw.bytes()) {
+			if (zeros >= 2 && b <= 3) { out_.push_back(3); zeros = 0; }
+			out_.push_back(b);
+			zeros = b ? 0 : zeros + 1;
+		}
+	}
+
+	void write_sps() {
+		BitWriter bw;
+		bw.put(o_.profile, 8);
+		bw.put(0, 8);
+		bw.put(40, 8);               // level 4.0
+		bw.ue(0);                    // seq_parameter_set_id (hazard 10: must be 0)
+		bw.ue(0);                    // log2_max_frame_num_minus4
+		bw.ue(2);                    // pic_order_cnt_type
+		bw.ue(o_.refs);              // num_ref_frames
+		bw.put1(0);                  // gaps_in_frame_num_value_allowed_flag
+		bw.ue(o_.mbw - 1);
+		bw.ue(o_.mbh - 1);
+		bw.put1(1);                  // frame_mbs_only_flag
+		bw.put1(1);                  // direct_8x8_inference_flag
+		if (o_.crop_bottom || o_.crop_right) {
+			bw.put1(1);
+			bw.ue(0); bw.ue(o_.crop_right / 2); bw.ue(0); bw.ue(o_.crop_bottom / 2);
+		} else {
+			bw.put1(0);
+		}
+		bw.put1(0);                  // vui_parameters_present_flag
+		bw.rbsp_trailing();
+		emit_nal(3, 7, bw);
+	}
+
+	void write_pps() {
+		BitWriter bw;
+		bw.ue(0); bw.ue(0);
+		bw.put1(0);                  // entropy_coding_mode_flag: CAVLC
+		bw.put1(0);
+		bw.ue(0);                    // num_slice_groups_minus1
+		bw.ue(o_.refs - 1);          // num_ref_idx_l0_default_active_minus1
+		bw.ue(0);
+		bw.put1(0);                  // weighted_pred_flag
+		bw.put(0, 2);
+		bw.se(o_.qp - 26);           // pic_init_qp_minus26
+		bw.se(0);
+		bw.se(o_.chroma_qp_offset);
+		bw.put1(1);                  // deblocking_filter_control_present_flag
+		bw.put1(o_.constrained_intra);
+		bw.put1(0);
+		bw.rbsp_trailing();
+		emit_nal(3, 8, bw);
+	}
+
+	// ---- picture / slice ---------------------------------------------------------------------------
+	void picture(bool idr, int frame_num, int since_idr) {
+		ctx_.begin_picture();
+		int total = o_.mbw * o_.mbh;
+		int nslices = o_.slices < 1 ? 1 : o_.slices;
+		int per = (total + nslices - 1) / nslices;
+		qp_ = o_.qp;
+		for (int s = 0, first = 0; first < total; ++s, first += per) {
+			int last = first + per < total ? first + per : total;
+			slice_num_ = s;
+			nref_ = idr ? 0 : (since_idr < o_.refs ? since_idr : o_.refs);
+			BitWriter bw;
+			bw.ue(first);
+			bw.ue(idr ? 7 : 5);      // slice_type: all slices of the picture are I / P
+			bw.ue(0);                // pic_parameter_set_id
+			bw.put(frame_num, 4);
+			if (idr) bw.ue(idr_id_);
+			if (!idr) {
+				bool override_flag = nref_ != o_.refs;
+				bw.put1(override_flag);
+				if (override_flag) bw.ue(nref_ - 1);
+				bw.put1(0);          // ref_pic_list_modification_flag_l0
+			}
+			if (idr) { bw.put1(0); bw.put1(0); }   // no_output_of_prior_pics, long_term_reference_flag
+			else bw.put1(0);                        // adaptive_ref_pic_marking_mode_flag
+			int slice_qp = o_.qp + (o_.vary_qp ? rng_.range(-2, 2) : 0);
+			bw.se(slice_qp - o_.qp);
+			qp_ = slice_qp;
+			int idc = o_.deblock ? ((o_.deblock == 2 && (s & 1)) ? 1 : 0) : 1;
+			bw.ue(idc);
+			if (idc != 1) { bw.se(o_.alpha_div2); bw.se(o_.beta_div2); }
+			slice_data(bw, idr, first, last);
+			bw.rbsp_trailing();
+			emit_nal(idr ? 3 : 2, idr ? 5 : 1, bw);
+		}
+	}
+
+	void slice_data(BitWriter &bw, bool idr, int first, int last) {
+		int skip_run = 0;
+		for (int addr = first; addr < last; ++addr) {
+			int mbx = addr % o_.mbw, mby = addr / o_.mbw;
+			ctx_.open_mb(mbx, mby, slice_num_);
+			if (!idr && rng_.chance(o_.skip_pct)) {
+				int16_t mv[2];
+				ctx_.pskip_mv(mbx, mby, slice_num_, mv);
+				ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, 0, mv[0], mv[1]);
+				ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
+				MbInfo &info = ctx_.info(mbx, mby);
+				info.kind = MB_SKIP;
+				memset(ctx_.nnz_of(mbx, mby), 0, 24);
+				skip_run++;
+				continue;
+			}
+			if (!idr) { bw.ue(skip_run); skip_run = 0; }
+			if (idr || rng_.chance(o_.intra_pct)) intra_mb(bw, mbx, mby, idr);
+			else inter_mb(bw, mbx, mby);
+		}
+		if (!idr && skip_run) bw.ue(skip_run);
+	}
+
+	// ---- residual generation / coding ---------------------------------------------------------------
+	// Draw up to `maxc` coefficients in scan order for a 4x4 block whose dequantised L1 amplitude
+	// (sum |level| * scale / 64) must stay below *budget; returns the number of non-zero levels.
+	int draw_block(int16_t *lv, int maxc, int first_scan, int qp, int *budget) {
+		memset(lv, 0, sizeof(int16_t) * 16);
+		int n = 1 + (int)(rng_.next() % 4);
+		if (rng_.chance(8)) n = rng_.range(5, maxc);
+		int cnt = 0;
+		for (int i = 0; i < n; ++i) {
+			int pos = rng_.chance(70) ? rng_.range(0, maxc > 6 ? 5 : maxc - 1) : rng_.range(0, maxc - 1);
+			if (lv[pos]) continue;
+			int mag = rng_.chance(75) ? 1 : rng_.range(2, o_.max_level);
+			if (rng_.chance(1) && o_.big_levels) mag = rng_.range(16, 300);
+			int r = zigzag4x4[pos + first_scan];
+			int cost = (mag * level_scale(qp, r & 3, r >> 2) + 63) / 64 + 1;
+			if (cost > *budget) {
+				mag = 1;
+				cost = (level_scale(qp, r & 3, r >> 2) + 63) / 64 + 1;
+				if (cost > *budget) continue;
+			}
+			*budget -= cost;
+			lv[pos] = (int16_t)(rng_.chance(50) ? mag : -mag);
+			cnt++;
+		}
+		return cnt;
+	}
+
+	// 9.2 encode one block; lv[] in scan order, maxc = 4, 15 or 16
+	int code_block(BitWriter &bw, const int16_t *lv, int maxc, int nc) {
+		int idx[16], total = 0;
+		for (int i = 0; i < maxc; ++i) if (lv[i]) idx[total++] = i;
+		int t1 = 0;
+		for (int k = total - 1; k >= 0 && t1 < 3; --k) {
+			if (lv[idx[k]] == 1 || lv[idx[k]] == -1) t1++;
+			else break;
+		}
+		const VlcEnc &ct = nc < 0 ? enc_.coeff_token[4] : (nc < 2 ? enc_.coeff_token[0] : (nc < 4 ? enc_.coeff_token[1] : (nc < 8 ? enc_.coeff_token[2] : enc_.coeff_token[3])));
+		ct.put(bw, total * 4 + t1);
+		if (!total) return 0;
+		for (int k = 0; k < t1; ++k) bw.put1(lv[idx[total - 1 - k]] < 0);
+		int sl = (total > 10 && t1 < 3) ? 1 : 0;
+		for (int k = t1; k < total; ++k) {
+			int level = lv[idx[total - 1 - k]];
+			int code = level > 0 ? 2 * level - 2 : -2 * level - 1;
+			if (k == t1 && t1 < 3) code -= 2;
+			if (sl == 0) {
+				if (code < 14) { bw.put(0, code); bw.put1(1); }
+				else if (code < 30) { bw.put(0, 14); bw.put1(1); bw.put(code - 14, 4); }
+				else { bw.put(0, 15); bw.put1(1); bw.put(code - 30, 12); }
+			} else {
+				if (code < (15 << sl)) { bw.put(0, code >> sl); bw.put1(1); bw.put(code & ((1 << sl) - 1), sl); }
+				else { bw.put(0, 15); bw.put1(1); bw.put(code - (15 << sl), 12); }
+			}
+			if (sl == 0) sl = 1;
+			int a = level < 0 ? -level : level;
+			if (sl < 6 && a > (3 << (sl - 1))) sl++;
+		}
+		int zeros = idx[total - 1] + 1 - total;
+		if (total < maxc) (maxc == 4 ? enc_.total_zeros_cdc[total - 1] : enc_.total_zeros[total - 1]).put(bw, zeros);
+		int left = zeros;
+		for (int k = total - 1; k > 0 && left > 0; --k) {
+			int run = idx[k] - idx[k - 1] - 1;
+			enc_.run_before[(left > 7 ? 7 : left) - 1].put(bw, run);
+			left -= run;
+		}
+		return total;
+	}
+
+	struct Residual {
+		int16_t luma_dc[16];
+		int16_t luma[16][16];
+		bool luma_coded[16];
+		int16_t cdc[2][4];
+		int16_t cac[2][4][16];
+		bool cac_coded[2][4];
+		int cbp;
+	};
+
+	// decide the residual of one MB (after QP is final); i16 selects the Intra16x16 layout
+	void draw_residual(Residual &r, int qp, int qpc0, int qpc1, bool i16) {
+		memset(&r, 0, sizeof(r));
+		int budget = o_.amp_budget;
+		int cbp = 0;
+		if (i16) {
+			if (rng_.chance(70)) {
+				int n = rng_.range(1, 4);
+				for (int i = 0; i < n; ++i) {
+					// Hadamard of the DC matrix spreads every level to all 16 blocks: |f| <= sum |c|
+					int cost = (2 * level_scale(qp, 0, 0) / 4 + 63) / 64 + 1;
+					if (cost > budget) break;
+					budget -= cost;
+					r.luma_dc[rng_.range(0, 15)] = (int16_t)(rng_.chance(50) ? rng_.range(1, 2) : -rng_.range(1, 2));
+				}
+			}
+			if (rng_.chance(50)) {
+				cbp |= 15;
+				for (int k = 0; k < 16; ++k)
+					if (rng_.chance(o_.coded_pct)) { int b = budget; r.luma_coded[k] = draw_block(r.luma[k], 15, 1, qp, &b) > 0; }
+			}
+		} else {
+			for (int q = 0; q < 4; ++q) {
+				if (!rng_.chance(o_.coded_pct * 2 > 100 ? 100 : o_.coded_pct * 2)) continue;
+				bool any = false;
+				for (int s = 0; s < 4; ++s) {
+					int k = q * 4 + s;
+					if (rng_.chance(50)) { int b = budget; r.luma_coded[k] = draw_block(r.luma[k], 16, 0, qp, &b) > 0; any |= r.luma_coded[k]; }
+				}
+				if (any) cbp |= 1 << q;
+			}
+		}
+		int cmode = rng_.chance(o_.coded_pct) ? rng_.range(1, 2) : 0;
+		if (cmode) {
+			bool any_dc = false, any_ac = false;
+			for (int c = 0; c < 2; ++c) {
+				int q = c ? qpc1 : qpc0;
+				int b = o_.amp_budget;
+				int n = rng_.range(0, 3);
+				for (int i = 0; i < n; ++i) {
+					int cost = (2 * level_scale(q, 0, 0) / 2 + 63) / 64 + 1;
+					if (cost > b) break;
+					b -= cost;
+					r.cdc[c][rng_.range(0, 3)] = (int16_t)(rng_.chance(50) ? rng_.range(1, 2) : -rng_.range(1, 2));
+					any_dc = true;
+				}
+				if (cmode == 2)
+					for (int k = 0; k < 4; ++k)
+						if (rng_.chance(50)) { int bb = b; r.cac_coded[c][k] = draw_block(r.cac[c][k], 15, 1, q, &bb) > 0; any_ac |= r.cac_coded[c][k]; }
+			}
+			if (cmode == 2 && !any_ac) cmode = 1;
+			if (cmode == 1 && !any_dc) cmode = 0;
+			if (!cmode) { memset(r.cdc, 0, sizeof(r.cdc)); memset(r.cac_coded, 0, sizeof(r.cac_coded)); }
+		}
+		r.cbp = cbp | (cmode << 4);
+	}
+
+	void code_luma(BitWriter &bw, const Residual &r, int mbx, int mby, bool i16) {
+		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
+		static const int16_t zero[16] = {0};
+		for (int k = 0; k < 16; ++k) {
+			int x4 = blk_x[k], y4 = blk_y[k];
+			if (!(r.cbp & (1 << (k >> 2)))) { nnz[y4 * 4 + x4] = 0; continue; }
+			int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
+			nnz[y4 * 4 + x4] = (uint8_t)code_block(bw, r.luma_coded[k] ? r.luma[k] : zero, i16 ? 15 : 16, nc);
+		}
+	}
+
+	void code_chroma(BitWriter &bw, const Residual &r, int mbx, int mby) {
+		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
+		memset(nnz + 16, 0, 8);
+		int cm = r.cbp >> 4;
+		if (!cm) return;
+		static const int16_t zero[16] = {0};
+		for (int c = 0; c < 2; ++c) code_block(bw, r.cdc[c], 4, -1);
+		if (cm & 2)
+			for (int c = 0; c < 2; ++c)
+				for (int b = 0; b < 4; ++b) {
+					int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, b & 1, b >> 1, slice_num_);
+					nnz[16 + c * 4 + b] = (uint8_t)code_block(bw, r.cac_coded[c][b] ? r.cac[c][b] : zero, 15, nc);
+				}
+	}
+
+	int draw_qp_delta() {
+		if (!o_.vary_qp || !rng_.chance(15)) return 0;
+		int d = rng_.range(-2, 2);
+		if (qp_ + d < o_.qp - 4 || qp_ + d > o_.qp + 4) d = 0;
+		return d;
+	}
+
+	// ---- intra ------------------------------------------------------------------------------------------
+	int pick(const int *cands, int n) { return cands[rng_.range(0, n - 1)]; }
+
+	void intra_mb(BitWriter &bw, int mbx, int mby, bool islice) {
+		int avail = ctx_.mb_avail_mask(mbx, mby, slice_num_);
+		if (o_.constrained_intra) {
+			static const int dx[4] = {-1, 0, 1, -1}, dy[4] = {0, -1, -1, -1};
+			for (int b = 0; b < 4; ++b)
+				if ((avail >> b) & 1)
+					if (!kind_is_intra(ctx_.info(mbx + dx[b], mby + dy[b]).kind)) avail &= ~(1 << b);
+		}
+		bool L = avail & 1, T = avail & 2, TL = avail & 8;
+		MbInfo &info = ctx_.info(mbx, mby);
+		ctx_.set_intra_motion(mbx, mby);
+		int8_t *ip = ctx_.ipred_of(mbx, mby);
+		int ofs = islice ? 0 : 5;
+		// chroma mode candidates
+		int cc[4], ncc = 0;
+		cc[ncc++] = 0;
+		if (L) cc[ncc++] = 1;
+		if (T) cc[ncc++] = 2;
+		if (L && T && TL) cc[ncc++] = 3;
+		int chroma_mode = pick(cc, ncc);
+		int r100 = rng_.range(0, 99);
+		if (r100 < o_.ipcm_pct) {
+			bw.ue(ofs + 25);
+			bw.align_zero();
+			for (int i = 0; i < 384; ++i) bw.put((uint32_t)rng_.range(0, 255), 8);
+			info.kind = MB_IPCM;
+			memset(ctx_.nnz_of(mbx, mby), 16, 24);
+			memset(ip, 2, 16);
+			return;
+		}
+		Residual r;
+		if (r100 < 55) {   // Intra4x4
+			info.kind = MB_I4x4;
+			bw.ue(ofs + 0);
+			for (int k = 0; k < 16; ++k) {
+				int x4 = blk_x[k], y4 = blk_y[k];
+				bool l = x4 > 0 || L, t = y4 > 0 || T;
+				bool tl = (x4 > 0 && y4 > 0) || (x4 == 0 && y4 > 0 && L) || (y4 == 0 && x4 > 0 && T) || (x4 == 0 && y4 == 0 && TL);
+				int cand[9], n = 0;
+				cand[n++] = 2;
+				if (t) { cand[n++] = 0; cand[n++] = 3; cand[n++] = 7; }
+				if (l) { cand[n++] = 1; cand[n++] = 8; }
+				if (l && t && tl) { cand[n++] = 4; cand[n++] = 5; cand[n++] = 6; }
+				int mode = pick(cand, n);
+				int pred = ctx_.predict_ipred(mbx, mby, x4, y4, slice_num_, o_.constrained_intra != 0);
+				if (rng_.chance(30)) mode = pred;       // pred is always legal here: it is DC or a neighbour's legal choice... not necessarily
+				// a neighbour's mode may need samples this block lacks; fall back to DC then
+				bool ok = false;
+				for (int i = 0; i < n; ++i) ok |= cand[i] == mode;
+				if (!ok) mode = 2;
+				if (mode == pred) bw.put1(1);
+				else { bw.put1(0); bw.put(mode < pred ? mode : mode - 1, 3); }
+				ip[y4 * 4 + x4] = (int8_t)mode;
+			}
+			bw.ue(chroma_mode);
+			int qd = draw_qp_delta();
+			int qp = qp_ + qd;
+			draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false);
+			bw.ue(enc_.code_from_cbp[0][r.cbp]);
+			if (r.cbp) { bw.se(qd); qp_ = qp; }
+			code_luma(bw, r, mbx, mby, false);
+		} else {           // Intra16x16
+			info.kind = MB_I16x16;
+			memset(ip, 2, 16);
+			int cand[4], n = 0;
+			cand[n++] = 2;
+			if (T) cand[n++] = 0;
+			if (L) cand[n++] = 1;
+			if (L && T && TL) cand[n++] = 3;
+			int mode = pick(cand, n);
+			int qd = draw_qp_delta();
+			int qp = qp_ + qd;
+			draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), true);
+			int cl = (r.cbp & 15) ? 1 : 0, cchroma = r.cbp >> 4;
+			bw.ue(ofs + 1 + mode + cchroma * 4 + cl * 12);
+			bw.ue(chroma_mode);
+			bw.se(qd);
+			qp_ = qp;
+			int nc = ctx_.cavlc_nc(mbx, mby, 0, 0, 0, slice_num_);
+			code_block(bw, r.luma_dc, 16, nc);
+			code_luma(bw, r, mbx, mby, true);
+		}
+		code_chroma(bw, r, mbx, mby);
+	}
+
+	// ---- inter -------------------------------------------------------------------------------------------
+	void draw_mv(int mbx, int mby, const int16_t pred[2], int out[2]) {
+		int mode = rng_.range(0, 99);
+		if (mode < 25) { out[0] = pred[0]; out[1] = pred[1]; }
+		else if (mode < 85) {
+			out[0] = pred[0] + rng_.range(-o_.mv_step, o_.mv_step);
+			out[1] = pred[1] + rng_.range(-o_.mv_step, o_.mv_step);
+		} else {
+			out[0] = rng_.range(-o_.mv_range, o_.mv_range);
+			out[1] = rng_.range(-o_.mv_range, o_.mv_range);
+		}
+		// keep the block within `mv_out` pixels of the picture so that edge replication is
+		// exercised but vectors stay inside level limits
+		int px = mbx * 16 * 4, py = mby * 16 * 4;
+		int lim = o_.mv_out * 4;
+		int minx = -px - lim, maxx = (o_.mbw * 16 * 4 - px - 16 * 4) + lim;
+		int miny = -py - lim, maxy = (o_.mbh * 16 * 4 - py - 16 * 4) + lim;
+		if (out[0] < minx) out[0] = minx;
+		if (out[0] > maxx) out[0] = maxx;
+		if (out[1] < miny) out[1] = miny;
+		if (out[1] > maxy) out[1] = maxy;
+	}
+
+	void inter_mb(BitWriter &bw, int mbx, int mby) {
+		MbInfo &info = ctx_.info(mbx, mby);
+		info.kind = MB_INTER;
+		memset(ctx_.ipred_of(mbx, mby), 2, 16);
+		ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
+		struct Part { int x4, y4, pw, ph, ref, shape, part; };
+		std::vector<Part> parts;
+		int t = rng_.range(0, 99);
+		int mb_type, sub[4] = {0, 0, 0, 0}, refs[4];
+		for (int i = 0; i < 4; ++i) refs[i] = nref_ > 1 ? rng_.range(0, nref_ - 1) : 0;
+		if (t < 40) { mb_type = 0; parts.push_back({0, 0, 4, 4, refs[0], 0, 0}); }
+		else if (t < 55) { mb_type = 1; parts.push_back({0, 0, 4, 2, refs[0], 1, 0}); parts.push_back({0, 2, 4, 2, refs[1], 1, 1}); }
+		else if (t < 70) { mb_type = 2; parts.push_back({0, 0, 2, 4, refs[0], 2, 0}); parts.push_back({2, 0, 2, 4, refs[1], 2, 1}); }
+		else {
+			mb_type = (nref_ > 1 || rng_.chance(50)) ? 3 : 4;   // P_8x8 / P_8x8ref0
+			if (mb_type == 4) for (int i = 0; i < 4; ++i) refs[i] = 0;
+			for (int i = 0; i < 4; ++i) {
+				sub[i] = rng_.range(0, 3);
+				int bx = (i & 1) * 2, by = (i >> 1) * 2;
+				switch (sub[i]) {
+				case 0: parts.push_back({bx, by, 2, 2, refs[i], 0, 0}); break;
+				case 1: parts.push_back({bx, by, 2, 1, refs[i], 0, 0}); parts.push_back({bx, by + 1, 2, 1, refs[i], 0, 0}); break;
+				case 2: parts.push_back({bx, by, 1, 2, refs[i], 0, 0}); parts.push_back({bx + 1, by, 1, 2, refs[i], 0, 0}); break;
+				default: for (int s = 0; s < 4; ++s) parts.push_back({bx + (s & 1), by + (s >> 1), 1, 1, refs[i], 0, 0}); break;
+				}
+			}
+		}
+		bw.ue(mb_type);
+		auto put_ref = [&](int r) {
+			if (nref_ <= 1) return;
+			if (nref_ == 2) bw.put1(r ^ 1); else bw.ue(r);
+		};
+		if (mb_type == 0) put_ref(refs[0]);
+		else if (mb_type == 1 || mb_type == 2) { put_ref(refs[0]); put_ref(refs[1]); }
+		else {
+			for (int i = 0; i < 4; ++i) bw.ue(sub[i]);
+			if (mb_type == 3) for (int i = 0; i < 4; ++i) put_ref(refs[i]);
+		}
+		for (const Part &p : parts) {
+			int16_t pred[2];
+			ctx_.predict_mv(0, mbx, mby, p.x4, p.y4, p.pw, p.ref, slice_num_, p.shape, p.part, pred);
+			int mv[2];
+			draw_mv(mbx, mby, pred, mv);
+			bw.se(mv[0] - pred[0]);
+			bw.se(mv[1] - pred[1]);
+			ctx_.set_motion(0, mbx, mby, p.x4, p.y4, p.pw, p.ph, p.ref, p.ref, mv[0], mv[1]);
+		}
+		Residual r;
+		int qd = draw_qp_delta();
+		int qp = qp_ + qd;
+		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false);
+		bw.ue(enc_.code_from_cbp[1][r.cbp]);
+		if (r.cbp) { bw.se(qd); qp_ = qp; }
+		code_luma(bw, r, mbx, mby, false);
+		code_chroma(bw, r, mbx, mby);
+	}
+
+	H264Opts o_;
+	Rng rng_;
+	Enc enc_;
+	PicCtx ctx_;
+	std::vector<uint8_t> out_;
+	int slice_num_ = 0, nref_ = 0, qp_ = 26, idr_id_ = 0;
+};
+
+}  // namespace
+
+std::vector<uint8_t> write_h264(const H264Opts &o) {
+	Writer w(o);
+	return w.run();
+}
+
+}  // namespace sg

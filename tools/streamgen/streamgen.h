@@ -1,0 +1,41 @@
+// streamgen.h — options of the test-only bitstream writers.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace sg {
+
+struct H264Opts {
+	int mbw = 8, mbh = 6, frames = 8, seed = 1;
+	int profile = 66;          // Baseline
+	int gop = 1000;            // IDR period in frames
+	int refs = 1;              // num_ref_frames (and default active count)
+	int qp = 28;
+	int chroma_qp_offset = 0;
+	int vary_qp = 1;           // slice_qp_delta / mb_qp_delta within +-4 of qp
+	int deblock = 1;           // 0: filter off (idc 1); 1: on (idc 0); 2: off in odd slices
+	int alpha_div2 = 0, beta_div2 = 0;   // keep beta >= alpha (hazard 5)
+	int slices = 1;
+	int intra_pct = 10, skip_pct = 15, ipcm_pct = 1, coded_pct = 25;
+	int max_level = 3, big_levels = 0;
+	int amp_budget = 200;      // bound on the L1 amplitude of a block's residual (hazards 1, 2)
+	int mv_step = 6, mv_range = 96, mv_out = 24;   // quarter-pel step / range, pixels allowed outside
+	int crop_bottom = 0, crop_right = 0;
+	int constrained_intra = 0;
+};
+
+struct Mpeg2Opts {
+	int mbw = 8, mbh = 6, frames = 9, seed = 1;
+	int gop = 12, bframes = 2;
+	int qscale = 6;
+	int intra_pct = 8, skip_pct = 10, coded_pct = 40;
+	int field = 0;             // 1: frame pictures with field prediction / field DCT allowed
+	int intra_vlc = 0, alt_scan = 0, q_scale_type = 0, dc_precision = 0;
+	int mv_range = 24;         // half-pel
+	int width = 0, height = 0; // 0: mbw*16 x mbh*16
+};
+
+std::vector<uint8_t> write_h264(const H264Opts &o);
+std::vector<uint8_t> write_mpeg2(const Mpeg2Opts &o);
+
+}  // namespace sg
