@@ -65,7 +65,7 @@ struct Neighbour {
 // Per-picture neighbour context.
 class PicCtx {
 public:
-	int mb_w, mb_h, w4, h4;
+	int mb_w = 0, mb_h = 0, w4 = 0, h4 = 0;
 	std::vector<MbInfo> mb;
 	std::vector<uint8_t> nnz;        // [mb][24]: luma raster 0..15, Cb 16..19, Cr 20..23
 	std::vector<int8_t> ipred;       // [mb][16] raster Intra4x4/8x8PredMode (2 when not I4x4/I8x8)

@@ -169,6 +169,14 @@ public:
 		prev_mmco5_ = false;
 		mb_w_ = mb_h_ = 0;
 		unsupported_ = false;
+		memset(&hdr_, 0, sizeof(hdr_));
+		nal_ref_idc_ = nal_type_ = 0;
+		cur_poc_ = 0;
+		mb_addr_ = slice_num_ = 0;
+		qp_ = 26;
+		n_intra_ = 0;
+		any_deblock_ = false;
+		stop_bit_pos_ = total_bits_ = 0;
 	}
 
 	// ---- m2d_func_table_t entry points (h264.cpp:505-525, 647-659, 663-693, 817-867) --------

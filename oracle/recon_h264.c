@@ -1,0 +1,495 @@
+/* recon_h264.c — ORACLE (test infrastructure, never shipped or called by the product).
+ *
+ * CPU restatement of the reference's H.264 picture reconstruction, driven by the same
+ * per-picture SoA records (include/b2_recon.h) that the CUDA kernels consume.  Macroblocks
+ * are reconstructed in raster order exactly in the reference's order of operations
+ * (prediction, then residual, block by block for Intra4x4), then the whole picture is
+ * deblocked MB by MB in raster order (left edge, inner vertical edges, top edge, inner
+ * horizontal edges), as deblock_pb does.
+ *
+ * Follows (reference, /root/reference/src/lib/h264.cpp unless noted):
+ *   964-1054   qp_matrix (flat dequantisation tables)          2005-2022  coeff_writeback
+ *   2113-2269  4x4 inverse transform + add (SSE2 path = exact clip), chroma variant, DC-only
+ *   4309-4365  intra16x16_dc_transform ((x+2)>>2)              4387-4404  intra_chroma_dc_transform (>>1)
+ *   2510-2997  Intra4x4 predictors                              3042, 2537, 2510, 4224-4304  Intra16x16
+ *   4561-4705  chroma predictors (NV12)                         4736-4761  I_PCM
+ *   3121-3254, 4407-4552, 2374-2461  per-MB drivers (block order, DC-only vs AC paths)
+ *   5381-6406  luma 6-tap quarter-pel (incl. UMV edge replication 5932-6116)
+ *   4859-5330  chroma eighth-pel bilinear
+ *   6726-6749  inter_pred_basic
+ *   10253-10663 deblock_pb and the edge filters; tables h264vld.h:4536-4627
+ *   m2d.h:286-341 DC-only packed add (equals a clipped add for |dc| <= 255, the only range
+ *   the test streams use — SURVEY.md hazard 2)
+ *
+ * Parity pin: tests/test_h264_* compare this file's output, frame by frame, with the MD5
+ * lines of the compiled reference (oracle/_ref/h264dec -O) on writer-generated streams.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b2_recon.h"
+
+static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static const uint8_t blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
+static const uint8_t blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+
+/* ---- dequantisation (qp_matrix, h264.cpp:964-995) ------------------------------------------ */
+static int level_scale4(int qp, int pos)
+{
+	static const int8_t na[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+	int x = pos & 3, y = pos >> 2;
+	int cls = (!(x & 1) && !(y & 1)) ? 0 : ((x & 1) && (y & 1)) ? 1 : 2;
+	return na[qp % 6][cls] << (qp / 6);
+}
+
+/* 4x4 inverse transform of dequantised coefficients c[4*y+x], +32 on DC, >>6 (h264.cpp:2145-2197) */
+static void idct4x4(const int *c, int *res)
+{
+	int t[16];
+	for (int y = 0; y < 4; ++y) {          /* horizontal first, as the reference and 8.5.12.2 */
+		int d0 = c[4 * y], d1 = c[4 * y + 1], d2 = c[4 * y + 2], d3 = c[4 * y + 3];
+		int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+		t[4 * y] = e0 + e3; t[4 * y + 1] = e1 + e2; t[4 * y + 2] = e1 - e2; t[4 * y + 3] = e0 - e3;
+	}
+	for (int x = 0; x < 4; ++x) {
+		int d0 = t[x], d1 = t[4 + x], d2 = t[8 + x], d3 = t[12 + x];
+		int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+		res[x] = (e0 + e3) >> 6; res[4 + x] = (e1 + e2) >> 6; res[8 + x] = (e1 - e2) >> 6; res[12 + x] = (e0 - e3) >> 6;
+	}
+}
+
+/* residual add of one 4x4 block; step = 1 luma, 2 NV12 chroma.  lv = levels (raster) or NULL,
+ * dc_override: use *dc (already dequantised/transformed DC) in place of the level at position 0 */
+static void add_block4x4(uint8_t *dst, int stride, int step, const int16_t *lv, int qp, const int *dc)
+{
+	int c[16], res[16];
+	for (int i = 0; i < 16; ++i) c[i] = lv ? lv[i] * level_scale4(qp, i) : 0;
+	if (dc) c[0] = *dc;
+	c[0] += 32;
+	idct4x4(c, res);
+	for (int y = 0; y < 4; ++y)
+		for (int x = 0; x < 4; ++x) {
+			uint8_t *p = dst + y * stride + x * step;
+			*p = (uint8_t)clip255(*p + res[4 * y + x]);
+		}
+}
+
+/* ---- intra prediction -------------------------------------------------------------------------- */
+/* Intra4x4 (8.3.1.2; h264.cpp:2510-2985).  avail: bit0 left, bit1 top, bit2 top-right */
+static void pred4x4(uint8_t *d, int s, int mode, int avail)
+{
+	int t[9], l[5];   /* t[0] = p[-1,-1], t[1..8] = p[0..7,-1]; l[0] = p[-1,-1], l[1..4] = p[-1,0..3] */
+	uint8_t pr[16];
+	for (int i = 0; i < 9; ++i) t[i] = 128;
+	for (int i = 0; i < 5; ++i) l[i] = 128;
+	if (avail & 2) {
+		for (int i = 0; i < 4; ++i) t[1 + i] = d[-s + i];
+		for (int i = 4; i < 8; ++i) t[1 + i] = (avail & 4) ? d[-s + i] : d[-s + 3];
+	}
+	if (avail & 1) for (int i = 0; i < 4; ++i) l[1 + i] = d[i * s - 1];
+	if ((avail & 3) == 3) t[0] = l[0] = d[-s - 1];
+#define T(i) t[(i) + 1]
+#define L(i) l[(i) + 1]
+	for (int y = 0; y < 4; ++y)
+		for (int x = 0; x < 4; ++x) {
+			int v;
+			switch (mode) {
+			case 0: v = T(x); break;
+			case 1: v = L(y); break;
+			case 2:
+				if ((avail & 3) == 3) v = (T(0) + T(1) + T(2) + T(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
+				else if (avail & 1) v = (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
+				else if (avail & 2) v = (T(0) + T(1) + T(2) + T(3) + 2) >> 2;
+				else v = 128;
+				break;
+			case 3:
+				v = (x == 3 && y == 3) ? (T(6) + 3 * T(7) + 2) >> 2 : (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
+				break;
+			case 4:
+				if (x > y) v = (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
+				else if (x < y) v = (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+				else v = (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
+				break;
+			case 5: {
+				int z = 2 * x - y;
+				if (z >= 0 && !(z & 1)) v = (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
+				else if (z >= 0) v = (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
+				else if (z == -1) v = (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+				else v = (L(y - 1) + 2 * L(y - 2) + L(y - 3) + 2) >> 2;
+				break;
+			}
+			case 6: {
+				int z = 2 * y - x;
+				if (z >= 0 && !(z & 1)) v = (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
+				else if (z >= 0) v = (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
+				else if (z == -1) v = (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+				else v = (T(x - 1) + 2 * T(x - 2) + T(x - 3) + 2) >> 2;
+				break;
+			}
+			case 7:
+				if (!(y & 1)) v = (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
+				else v = (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
+				break;
+			default: {
+				int z = x + 2 * y;
+				if (z > 5) v = L(3);
+				else if (z == 5) v = (L(2) + 3 * L(3) + 2) >> 2;
+				else if (!(z & 1)) v = (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
+				else v = (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2;
+				break;
+			}
+			}
+			pr[4 * y + x] = (uint8_t)v;
+		}
+#undef T
+#undef L
+	for (int y = 0; y < 4; ++y) memcpy(d + y * s, pr + 4 * y, 4);
+}
+
+/* per-block availability from the MB-level mask (h264.cpp:3132-3225) */
+static int blk_avail(int k, int a)
+{
+	int x = blk_x[k], y = blk_y[k];
+	int left = x > 0 || (a & 1), top = y > 0 || (a & 2), tr;
+	if (y == 0) tr = x < 3 ? (a & 2) != 0 : (a & 4) != 0;
+	else if (x == 3) tr = 0;
+	else {
+		static const uint8_t r2b[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+		tr = r2b[(y - 1) * 4 + x + 1] < k;
+	}
+	return (left ? 1 : 0) | (top ? 2 : 0) | (tr ? 4 : 0);
+}
+
+/* Intra16x16 (8.3.3) */
+static void pred16x16(uint8_t *d, int s, int mode, int avail)
+{
+	if (mode == 0) {
+		for (int y = 0; y < 16; ++y) memcpy(d + y * s, d - s, 16);
+	} else if (mode == 1) {
+		for (int y = 0; y < 16; ++y) memset(d + y * s, d[y * s - 1], 16);
+	} else if (mode == 2) {
+		int sum = 0, v;
+		if (avail & 1) for (int i = 0; i < 16; ++i) sum += d[i * s - 1];
+		if (avail & 2) for (int i = 0; i < 16; ++i) sum += d[-s + i];
+		if ((avail & 3) == 3) v = (sum + 16) >> 5;
+		else if (avail & 3) v = (sum + 8) >> 4;
+		else v = 128;
+		for (int y = 0; y < 16; ++y) memset(d + y * s, v, 16);
+	} else {
+		int H = 0, V = 0;
+		for (int i = 0; i < 8; ++i) {
+			H += (i + 1) * (d[-s + 8 + i] - d[-s + 6 - i]);
+			V += (i + 1) * (d[(8 + i) * s - 1] - d[(6 - i) * s - 1]);
+		}
+		int a = 16 * (d[15 * s - 1] + d[-s + 15]), b = (5 * H + 32) >> 6, c = (5 * V + 32) >> 6;
+		uint8_t tmp[256];
+		for (int y = 0; y < 16; ++y)
+			for (int x = 0; x < 16; ++x) tmp[16 * y + x] = (uint8_t)clip255((a + b * (x - 7) + c * (y - 7) + 16) >> 5);
+		for (int y = 0; y < 16; ++y) memcpy(d + y * s, tmp + 16 * y, 16);
+	}
+}
+
+/* chroma 8x8 of one component inside the NV12 plane (8.3.4); d points at the component's first byte */
+static void pred_chroma(uint8_t *d, int s, int mode, int avail)
+{
+	uint8_t tmp[64];
+	if (mode == 0) {
+		for (int by = 0; by < 2; ++by)
+			for (int bx = 0; bx < 2; ++bx) {
+				int st = 0, sl = 0, v;
+				for (int i = 0; i < 4; ++i) {
+					if (avail & 2) st += d[-s + (bx * 4 + i) * 2];
+					if (avail & 1) sl += d[(by * 4 + i) * s - 2];
+				}
+				int has_t = (avail & 2) != 0, has_l = (avail & 1) != 0;
+				if (bx == 0 && by == 0) v = (has_t && has_l) ? (st + sl + 4) >> 3 : has_l ? (sl + 2) >> 2 : has_t ? (st + 2) >> 2 : 128;
+				else if (bx == 1 && by == 0) v = has_t ? (st + 2) >> 2 : has_l ? (sl + 2) >> 2 : 128;
+				else if (bx == 0 && by == 1) v = has_l ? (sl + 2) >> 2 : has_t ? (st + 2) >> 2 : 128;
+				else v = (has_t && has_l) ? (st + sl + 4) >> 3 : has_l ? (sl + 2) >> 2 : has_t ? (st + 2) >> 2 : 128;
+				for (int y = 0; y < 4; ++y)
+					for (int x = 0; x < 4; ++x) tmp[(by * 4 + y) * 8 + bx * 4 + x] = (uint8_t)v;
+			}
+	} else if (mode == 1) {
+		for (int y = 0; y < 8; ++y) memset(tmp + 8 * y, d[y * s - 2], 8);
+	} else if (mode == 2) {
+		for (int y = 0; y < 8; ++y)
+			for (int x = 0; x < 8; ++x) tmp[8 * y + x] = d[-s + 2 * x];
+	} else {
+		int H = 0, V = 0;
+		for (int i = 0; i < 4; ++i) {
+			H += (i + 1) * (d[-s + (4 + i) * 2] - d[-s + (2 - i) * 2]);
+			V += (i + 1) * (d[(4 + i) * s - 2] - d[(2 - i) * s - 2]);
+		}
+		int a = 16 * (d[7 * s - 2] + d[-s + 14]), b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
+		for (int y = 0; y < 8; ++y)
+			for (int x = 0; x < 8; ++x) tmp[8 * y + x] = (uint8_t)clip255((a + b * (x - 3) + c * (y - 3) + 16) >> 5);
+	}
+	for (int y = 0; y < 8; ++y)
+		for (int x = 0; x < 8; ++x) d[y * s + 2 * x] = tmp[8 * y + x];
+}
+
+/* ---- inter prediction ------------------------------------------------------------------------------ */
+static inline int ref_px(const uint8_t *p, int W, int H, int x, int y)
+{
+	/* edge replication (inter_pred_luma_umv / fill_rect_umv_luma, h264.cpp:5932-6116) */
+	return p[clip3(0, H - 1, y) * W + clip3(0, W - 1, x)];
+}
+
+static int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+/* one luma sample at integer position (x, y) + quarter-pel fraction (fx, fy) (8.4.2.2.1) */
+static int luma_sample(const uint8_t *p, int W, int H, int x, int y, int fx, int fy)
+{
+#define P(dx, dy) ref_px(p, W, H, x + (dx), y + (dy))
+#define HB(dx, dy) tap6(P((dx) - 2, dy), P((dx) - 1, dy), P(dx, dy), P((dx) + 1, dy), P((dx) + 2, dy), P((dx) + 3, dy))   /* b1 at (dx+1/2, dy) */
+#define VH(dx, dy) tap6(P(dx, (dy) - 2), P(dx, (dy) - 1), P(dx, dy), P(dx, (dy) + 1), P(dx, (dy) + 2), P(dx, (dy) + 3))   /* h1 at (dx, dy+1/2) */
+	if (!fx && !fy) return P(0, 0);
+	int G = P(0, 0);
+	int b = clip255((HB(0, 0) + 16) >> 5);
+	int h = clip255((VH(0, 0) + 16) >> 5);
+	if (fy == 0) return fx == 2 ? b : (fx == 1 ? (G + b + 1) >> 1 : (P(1, 0) + b + 1) >> 1);
+	if (fx == 0) return fy == 2 ? h : (fy == 1 ? (G + h + 1) >> 1 : (P(0, 1) + h + 1) >> 1);
+	/* j: 6-tap over the unrounded horizontal intermediates */
+	int j = clip255((tap6(HB(0, -2), HB(0, -1), HB(0, 0), HB(0, 1), HB(0, 2), HB(0, 3)) + 512) >> 10);
+	int s = clip255((HB(0, 1) + 16) >> 5);     /* half-pel below b */
+	int m = clip255((VH(1, 0) + 16) >> 5);     /* half-pel right of h */
+	if (fx == 2 && fy == 2) return j;
+	if (fx == 2) return fy == 1 ? (b + j + 1) >> 1 : (s + j + 1) >> 1;        /* f, q */
+	if (fy == 2) return fx == 1 ? (h + j + 1) >> 1 : (m + j + 1) >> 1;        /* i, k */
+	/* diagonal quarter positions e, g, p, r */
+	if (fx == 1 && fy == 1) return (b + h + 1) >> 1;
+	if (fx == 3 && fy == 1) return (b + m + 1) >> 1;
+	if (fx == 1 && fy == 3) return (h + s + 1) >> 1;
+	return (s + m + 1) >> 1;
+#undef P
+#undef HB
+#undef VH
+}
+
+static void inter_pred(const b2_h264_picture *p, const b2_h264_mc *r, int mbx, int mby, uint8_t *const *luma,
+                       uint8_t *const *chroma)
+{
+	int W = p->mb_w * 16, H = p->mb_h * 16;
+	int x0 = mbx * 16 + (r->pos & 3) * 4, y0 = mby * 16 + (r->pos >> 2) * 4;
+	int w = (r->size & 15) * 4, h = (r->size >> 4) * 4;
+	const uint8_t *ry = luma[r->ref_frame[0]], *rc = chroma[r->ref_frame[0]];
+	uint8_t *dy = luma[p->dst], *dc = chroma[p->dst];
+	int mvx = r->mv[0][0], mvy = r->mv[0][1];
+	for (int y = 0; y < h; ++y)
+		for (int x = 0; x < w; ++x)
+			dy[(y0 + y) * W + x0 + x] = (uint8_t)luma_sample(ry, W, H, x0 + x + (mvx >> 2), y0 + y + (mvy >> 2), mvx & 3, mvy & 3);
+	/* chroma (8.4.2.2.2; h264.cpp:5267-5296): eighth-pel bilinear on each component */
+	int cw = W / 2, ch = H / 2, fx = mvx & 7, fy = mvy & 7;
+	for (int y = 0; y < h / 2; ++y)
+		for (int x = 0; x < w / 2; ++x)
+			for (int c = 0; c < 2; ++c) {
+				int cx = x0 / 2 + x + (mvx >> 3), cy = y0 / 2 + y + (mvy >> 3);
+#define C(dx, dy) rc[clip3(0, ch - 1, cy + (dy)) * W + clip3(0, cw - 1, cx + (dx)) * 2 + c]
+				int v = ((8 - fx) * (8 - fy) * C(0, 0) + fx * (8 - fy) * C(1, 0) + (8 - fx) * fy * C(0, 1) + fx * fy * C(1, 1) + 32) >> 6;
+#undef C
+				dc[(y0 / 2 + y) * W + (x0 / 2 + x) * 2 + c] = (uint8_t)v;
+			}
+}
+
+/* ---- one macroblock ------------------------------------------------------------------------------------ */
+static const int16_t *rec_of(const b2_h264_picture *p, const b2_h264_mb *m, int bit)
+{
+	if (!(m->nz & (1u << bit))) return 0;
+	return p->coefs + ((size_t)m->coef_idx + __builtin_popcount(m->nz & ((1u << bit) - 1))) * 16;
+}
+
+static void chroma_residual(const b2_h264_picture *p, const b2_h264_mb *m, uint8_t *dc, int W)
+{
+	const int16_t *cdc = rec_of(p, m, 17);
+	for (int c = 0; c < 2; ++c) {
+		int qp = c ? m->qp_cr : m->qp_cb;
+		int f[4] = {0, 0, 0, 0}, dcv[4];
+		if (cdc) for (int i = 0; i < 4; ++i) f[i] = cdc[c * 4 + i] * level_scale4(qp, 0);
+		/* intra_chroma_dc_transform (h264.cpp:4387-4404): 2x2 Hadamard, >> 1 */
+		dcv[0] = (f[0] + f[1] + f[2] + f[3]) >> 1;
+		dcv[1] = (f[0] - f[1] + f[2] - f[3]) >> 1;
+		dcv[2] = (f[0] + f[1] - f[2] - f[3]) >> 1;
+		dcv[3] = (f[0] - f[1] - f[2] + f[3]) >> 1;
+		for (int b = 0; b < 4; ++b) {
+			const int16_t *ac = rec_of(p, m, 18 + c * 4 + b);
+			if (!ac && !dcv[b]) continue;
+			add_block4x4(dc + (b >> 1) * 4 * W + (b & 1) * 8 + c, W, 2, ac, qp, &dcv[b]);
+		}
+	}
+}
+
+static void recon_mb(const b2_h264_picture *p, int mbx, int mby, uint8_t *const *luma, uint8_t *const *chroma)
+{
+	const b2_h264_mb *m = &p->mbs[mby * p->mb_w + mbx];
+	int W = p->mb_w * 16;
+	uint8_t *dy = luma[p->dst] + mby * 16 * W + mbx * 16;
+	uint8_t *dc = chroma[p->dst] + mby * 8 * W + mbx * 16;
+	if (m->type == B2_H4_IPCM) {
+		const uint8_t *src = (const uint8_t *)(p->coefs + (size_t)m->coef_idx * 16);
+		for (int y = 0; y < 16; ++y) memcpy(dy + y * W, src + 16 * y, 16);
+		for (int c = 0; c < 2; ++c)
+			for (int y = 0; y < 8; ++y)
+				for (int x = 0; x < 8; ++x) dc[y * W + 2 * x + c] = src[256 + c * 64 + 8 * y + x];
+		return;
+	}
+	if (m->type == B2_H4_INTER) {
+		for (int i = 0; i < m->mc_cnt; ++i) inter_pred(p, &p->mcs[m->mc_idx + i], mbx, mby, luma, chroma);
+		for (int k = 0; k < 16; ++k) {
+			const int16_t *lv = rec_of(p, m, 1 + k);
+			if (lv) add_block4x4(dy + blk_y[k] * 4 * W + blk_x[k] * 4, W, 1, lv, m->qp_y, 0);
+		}
+		chroma_residual(p, m, dc, W);
+		return;
+	}
+	if (m->type == B2_H4_I4x4) {
+		for (int k = 0; k < 16; ++k) {
+			uint8_t *d = dy + blk_y[k] * 4 * W + blk_x[k] * 4;
+			int mode = (m->i4_modes[k >> 1] >> ((k & 1) * 4)) & 15;
+			pred4x4(d, W, mode, blk_avail(k, m->intra_avail));
+			const int16_t *lv = rec_of(p, m, 1 + k);
+			if (lv) add_block4x4(d, W, 1, lv, m->qp_y, 0);
+		}
+	} else {   /* Intra16x16 (h264.cpp:4407-4552) */
+		pred16x16(dy, W, m->i16_mode, m->intra_avail);
+		const int16_t *dcl = rec_of(p, m, 0);
+		int dcv[16];
+		memset(dcv, 0, sizeof(dcv));
+		if (dcl) {
+			/* intra16x16_dc_transform (h264.cpp:4309-4365): 4x4 Hadamard of dequantised DCs, (x+2)>>2 */
+			int f[16], t[16];
+			for (int i = 0; i < 16; ++i) f[i] = dcl[i] * level_scale4(m->qp_y, 0);
+			for (int y = 0; y < 4; ++y) {
+				int a = f[4 * y], b = f[4 * y + 1], c = f[4 * y + 2], d = f[4 * y + 3];
+				t[4 * y] = a + b + c + d; t[4 * y + 1] = a + b - c - d; t[4 * y + 2] = a - b - c + d; t[4 * y + 3] = a - b + c - d;
+			}
+			for (int x = 0; x < 4; ++x) {
+				int a = t[x], b = t[4 + x], c = t[8 + x], d = t[12 + x];
+				f[x] = a + b + c + d; f[4 + x] = a + b - c - d; f[8 + x] = a - b - c + d; f[12 + x] = a - b + c - d;
+			}
+			for (int k = 0; k < 16; ++k) dcv[k] = (f[blk_y[k] * 4 + blk_x[k]] + 2) >> 2;
+		}
+		for (int k = 0; k < 16; ++k) {
+			const int16_t *lv = rec_of(p, m, 1 + k);
+			if (!lv && !dcv[k]) continue;
+			add_block4x4(dy + blk_y[k] * 4 * W + blk_x[k] * 4, W, 1, lv, m->qp_y, &dcv[k]);
+		}
+	}
+	pred_chroma(dc, W, m->chroma_mode, m->intra_avail_c);
+	pred_chroma(dc + 1, W, m->chroma_mode, m->intra_avail_c);
+	chroma_residual(p, m, dc, W);
+}
+
+/* ---- deblocking (8.7; h264.cpp:10253-10663) ------------------------------------------------------------- */
+static const uint8_t alpha_tab[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20,
+	22, 25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
+static const uint8_t beta_tab[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8,
+	9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
+static const uint8_t tc0_tab[52][3] = {
+	{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
+	{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 1},
+	{0, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 2, 3}, {1, 2, 3},
+	{2, 2, 3}, {2, 2, 4}, {2, 3, 4}, {2, 3, 4}, {3, 3, 5}, {3, 4, 6}, {3, 4, 6}, {4, 5, 7}, {4, 5, 8}, {4, 6, 9}, {5, 7, 10},
+	{6, 8, 11}, {6, 8, 13}, {7, 10, 14}, {8, 11, 16}, {9, 12, 18}, {10, 13, 20}, {11, 15, 23}, {13, 17, 25}};
+
+/* filter one line of samples across an edge; px points at q0, `st` is the step across the edge */
+static void filter_line(uint8_t *px, int st, int bs, int alpha, int beta, int tc0, int luma)
+{
+	int p0 = px[-st], p1 = px[-2 * st], q0 = px[0], q1 = px[st];
+	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+	if (bs == 4) {
+		if (luma) {
+			int p2 = px[-3 * st], q2 = px[2 * st];
+			int strong = abs(p0 - q0) < (alpha >> 2) + 2;
+			if (strong && abs(p2 - p0) < beta) {
+				int p3 = px[-4 * st];
+				px[-st] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+				px[-2 * st] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+				px[-3 * st] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+			} else {
+				px[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+			}
+			if (strong && abs(q2 - q0) < beta) {
+				int q3 = px[3 * st];
+				px[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+				px[st] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+				px[2 * st] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+			} else {
+				px[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+			}
+		} else {
+			px[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+			px[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+		}
+		return;
+	}
+	int tc = tc0;
+	if (luma) {
+		int p2 = px[-3 * st], q2 = px[2 * st];
+		int ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
+		tc = tc0 + ap + aq;
+		if (ap) px[-2 * st] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1));
+		if (aq) px[st] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1));
+	} else {
+		tc = tc0 + 1;
+	}
+	int delta = clip3(-tc, tc, ((q0 - p0) * 4 + (p1 - q1) + 4) >> 3);
+	px[-st] = (uint8_t)clip255(p0 + delta);
+	px[0] = (uint8_t)clip255(q0 - delta);
+}
+
+/* one edge of 16 luma lines or 8 chroma lines; bs4: whole edge has bS 4; bits: 4 x 2-bit strengths */
+static void filter_edge(uint8_t *px, int across, int along, int bits, int bs4, int qp, int aoff, int boff, int luma)
+{
+	int ia = clip3(0, 51, qp + aoff), ib = clip3(0, 51, qp + boff);
+	int alpha = alpha_tab[ia], beta = beta_tab[ib];
+	if (!alpha) return;
+	int n = luma ? 16 : 8;
+	for (int i = 0; i < n; ++i) {
+		int seg = luma ? i >> 2 : i >> 1;
+		int bs = (bits >> (seg * 2)) & 3;
+		if (!bs) continue;
+		if (bs4) bs = 4;
+		filter_line(px + i * along, across, bs, alpha, beta, bs < 4 ? tc0_tab[ia][bs - 1] : 0, luma);
+	}
+}
+
+static void deblock_mb(const b2_h264_picture *p, int mbx, int mby, uint8_t *luma, uint8_t *chroma)
+{
+	const b2_h264_dbk *d = &p->dbk[mby * p->mb_w + mbx];
+	if (d->flags & B2_DBK_OFF) return;
+	int W = p->mb_w * 16;
+	uint8_t *y = luma + mby * 16 * W + mbx * 16, *c = chroma + mby * 8 * W + mbx * 16;
+	int a = d->alpha_off, b = d->beta_off;
+	for (int dir = 0; dir < 2; ++dir) {          /* 0: vertical edges (filter horizontally), 1: horizontal edges */
+		uint32_t bits = dir ? d->bs_h : d->bs_v;
+		int edge_ok = d->flags & (dir ? B2_DBK_TOP_EDGE : B2_DBK_LEFT_EDGE);
+		int bs4 = (d->flags & (dir ? B2_DBK_TOP_BS4 : B2_DBK_LEFT_BS4)) != 0;
+		const b2_h264_dbk *n = dir ? d - p->mb_w : d - 1;
+		for (int e = 0; e < 4; ++e) {
+			int eb = (bits >> (8 * e)) & 255;
+			if (!eb || (e == 0 && !edge_ok)) continue;
+			int qpy = e ? d->qp_y : (d->qp_y + n->qp_y + 1) >> 1;
+			uint8_t *py = dir ? y + e * 4 * W : y + e * 4;
+			filter_edge(py, dir ? W : 1, dir ? 1 : W, eb, e == 0 && bs4, qpy, a, b, 1);
+			if (e & 1) continue;                 /* chroma: luma edges 0 and 2 only */
+			for (int k = 0; k < 2; ++k) {
+				int qc = k ? d->qp_cr : d->qp_cb, qn = k ? n->qp_cr : n->qp_cb;
+				int qpc = e ? qc : (qc + qn + 1) >> 1;
+				uint8_t *pc = dir ? c + (e / 2) * 4 * W + k : c + (e / 2) * 8 + k;
+				filter_edge(pc, dir ? W : 2, dir ? 2 : W, eb, e == 0 && bs4, qpc, a, b, 0);
+			}
+		}
+	}
+}
+
+int oracle_h264_picture(const b2_h264_picture *p, uint8_t *const *luma, uint8_t *const *chroma)
+{
+	for (int mby = 0; mby < p->mb_h; ++mby)
+		for (int mbx = 0; mbx < p->mb_w; ++mbx) recon_mb(p, mbx, mby, luma, chroma);
+	if (p->deblock)
+		for (int mby = 0; mby < p->mb_h; ++mby)
+			for (int mbx = 0; mbx < p->mb_w; ++mbx) deblock_mb(p, mbx, mby, luma[p->dst], chroma[p->dst]);
+	return 0;
+}
