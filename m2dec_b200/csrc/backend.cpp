@@ -37,6 +37,7 @@ int Backend::submit(int codec, const void *picture) {
 	if (device_off_) return err;
 	if (!sess_) return -1;
 	if (codec == B2_CODEC_MPEG2) return b2_session_submit_mpeg2(sess_, (const b2_m2_picture *)picture);
+	if (codec == B2_CODEC_H264) return b2_session_submit_h264(sess_, (const b2_h264_picture *)picture);
 	return -1;
 }
 

@@ -28,6 +28,20 @@ struct M2Job {
 // Launch reconstruction of n_jobs independent pictures of identical size in one grid.
 int launch_mpeg2(cudaStream_t stream, const M2Job *d_jobs, int n_jobs, int mb_w, int mb_h);
 
+// One H.264 picture as the kernels see it (device pointers).  Frames of the pool are addressed
+// as frames + idx * frame_bytes (luma) and + W*H (NV12 chroma).
+struct H4Job {
+	uint8_t *frames;
+	size_t frame_bytes;
+	const b2_h264_mb *mbs;
+	const b2_h264_dbk *dbk;
+	const b2_h264_mc *mcs;
+	const int16_t *coefs;
+	int32_t dst, mb_w, mb_h, reserved;
+};
+int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
+                bool deblock, uint64_t *launches);
+
 __device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 }  // namespace b2

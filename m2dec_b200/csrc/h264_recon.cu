@@ -1,0 +1,649 @@
+// h264_recon.cu — K1..K4: H.264 picture reconstruction on sm_100a.
+//
+//   h264_inter_kernel   K2+K1  motion compensation (luma 6-tap quarter-pel, chroma eighth-pel
+//                              bilinear, edge replication by coordinate clamp) fused with
+//                              dequantisation + 4x4 inverse transform + residual add/clip for
+//                              every inter macroblock; each output byte is written once.
+//   h264_intra_kernel   K3+K1  intra 4x4 / 16x16 / chroma prediction + residual, and I_PCM, as
+//                              an MB-diagonal wavefront (slope 2: left, top, top-right deps).
+//   h264_deblock_kernel K4     in-loop filter from the per-MB strength records, same wavefront.
+//
+// Arithmetic restated from the reference (src/lib/h264.cpp): dequant tables 964-1054 and
+// coeff_writeback 2005-2022; 4x4 transform 2145-2269; DC transforms 4309-4404; intra
+// predictors 2510-2997, 4224-4304, 4561-4705; I_PCM 4736-4761; luma MC 5381-6406 (UMV
+// 5932-6116); chroma MC 4859-5330; deblock 10253-10663 with tables h264vld.h:4536-4627.
+// HBM-bound integer/byte work: no tensor cores.
+#include "device_common.cuh"
+
+namespace b2 {
+namespace {
+
+__constant__ uint8_t c_blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
+__constant__ uint8_t c_blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+__constant__ uint8_t c_r2b[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+__constant__ uint8_t c_norm_adjust[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+__constant__ uint8_t c_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20,
+	22, 25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
+__constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8,
+	9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
+__constant__ uint8_t c_tc0[52][3] = {
+	{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
+	{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 1},
+	{0, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 2, 3}, {1, 2, 3},
+	{2, 2, 3}, {2, 2, 4}, {2, 3, 4}, {2, 3, 4}, {3, 3, 5}, {3, 4, 6}, {3, 4, 6}, {4, 5, 7}, {4, 5, 8}, {4, 6, 9}, {5, 7, 10},
+	{6, 8, 11}, {6, 8, 13}, {7, 10, 14}, {8, 11, 16}, {9, 12, 18}, {10, 13, 20}, {11, 15, 23}, {13, 17, 25}};
+
+__device__ __forceinline__ int level_scale4(int qp, int pos) {
+	int x = pos & 3, y = pos >> 2;
+	int cls = (!(x & 1) && !(y & 1)) ? 0 : (((x & 1) && (y & 1)) ? 1 : 2);
+	return (int)c_norm_adjust[qp % 6][cls] << (qp / 6);
+}
+
+__device__ __forceinline__ const int16_t *rec_of(const H4Job &job, const b2_h264_mb &m, int bit) {
+	return job.coefs + ((size_t)m.coef_idx + __popc(m.nz & ((1u << bit) - 1))) * 16;
+}
+
+// 4x4 inverse transform of dequantised coefficients (DC already carries +32); res = value >> 6
+__device__ __forceinline__ void idct4x4(int *c, int16_t *res) {
+#pragma unroll
+	for (int y = 0; y < 4; ++y) {
+		int d0 = c[4 * y], d1 = c[4 * y + 1], d2 = c[4 * y + 2], d3 = c[4 * y + 3];
+		int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+		c[4 * y] = e0 + e3; c[4 * y + 1] = e1 + e2; c[4 * y + 2] = e1 - e2; c[4 * y + 3] = e0 - e3;
+	}
+#pragma unroll
+	for (int x = 0; x < 4; ++x) {
+		int d0 = c[x], d1 = c[4 + x], d2 = c[8 + x], d3 = c[12 + x];
+		int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+		res[x] = (int16_t)((e0 + e3) >> 6); res[4 + x] = (int16_t)((e1 + e2) >> 6);
+		res[8 + x] = (int16_t)((e1 - e2) >> 6); res[12 + x] = (int16_t)((e0 - e3) >> 6);
+	}
+}
+
+// Residual of block `b` of a macroblock (0..15 luma in decode order, 16..19 Cb, 20..23 Cr) into
+// res[16] (raster 4x4).  Returns false (res untouched) when the block has no residual at all.
+__device__ bool block_residual(const H4Job &job, const b2_h264_mb &m, int b, int16_t *res) {
+	int c[16];
+	bool has_ac;
+	int dc = 0;
+	bool has_dc = false;
+	int qp;
+	const int16_t *lv;
+	if (b < 16) {
+		qp = m.qp_y;
+		has_ac = (m.nz >> (1 + b)) & 1;
+		lv = rec_of(job, m, 1 + b);
+		if (m.type == B2_H4_I16x16 && (m.nz & 1)) {
+			// intra16x16_dc_transform: 4x4 Hadamard of the dequantised DC levels, (x + 2) >> 2
+			const int16_t *dl = rec_of(job, m, 0);
+			int f[16];
+			int ls = level_scale4(qp, 0);
+#pragma unroll
+			for (int i = 0; i < 16; ++i) f[i] = dl[i] * ls;
+#pragma unroll
+			for (int y = 0; y < 4; ++y) {
+				int a0 = f[4 * y], a1 = f[4 * y + 1], a2 = f[4 * y + 2], a3 = f[4 * y + 3];
+				f[4 * y] = a0 + a1 + a2 + a3; f[4 * y + 1] = a0 + a1 - a2 - a3;
+				f[4 * y + 2] = a0 - a1 - a2 + a3; f[4 * y + 3] = a0 - a1 + a2 - a3;
+			}
+			int bx = c_blk_x[b], by = c_blk_y[b];
+			int a0 = f[bx], a1 = f[4 + bx], a2 = f[8 + bx], a3 = f[12 + bx];
+			int v = by == 0 ? a0 + a1 + a2 + a3 : (by == 1 ? a0 + a1 - a2 - a3 : (by == 2 ? a0 - a1 - a2 + a3 : a0 - a1 + a2 - a3));
+			dc = (v + 2) >> 2;
+			has_dc = true;
+		}
+	} else {
+		int comp = (b - 16) >> 2, k = (b - 16) & 3;
+		qp = comp ? m.qp_cr : m.qp_cb;
+		has_ac = (m.nz >> (2 + b)) & 1;
+		lv = rec_of(job, m, 2 + b);
+		if (m.nz & (1u << 17)) {
+			// intra_chroma_dc_transform: 2x2 Hadamard of the dequantised DC levels, >> 1
+			const int16_t *dl = rec_of(job, m, 17) + comp * 4;
+			int ls = level_scale4(qp, 0);
+			int f0 = dl[0] * ls, f1 = dl[1] * ls, f2 = dl[2] * ls, f3 = dl[3] * ls;
+			int v = k == 0 ? f0 + f1 + f2 + f3 : (k == 1 ? f0 - f1 + f2 - f3 : (k == 2 ? f0 + f1 - f2 - f3 : f0 - f1 - f2 + f3));
+			dc = v >> 1;
+			has_dc = true;
+		}
+	}
+	if (!has_ac && !(has_dc && dc != 0)) return false;
+	if (has_ac) {
+		int4 r0 = __ldg(reinterpret_cast<const int4 *>(lv)), r1 = __ldg(reinterpret_cast<const int4 *>(lv) + 1);
+		int16_t l[16];
+		*reinterpret_cast<int4 *>(l) = r0;
+		*reinterpret_cast<int4 *>(l + 8) = r1;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) c[i] = l[i] * level_scale4(qp, i);
+	} else {
+#pragma unroll
+		for (int i = 0; i < 16; ++i) c[i] = 0;
+	}
+	if (has_dc) c[0] = dc;
+	c[0] += 32;
+	idct4x4(c, res);
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inter prediction
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+// Four horizontally adjacent luma samples at integer position (x..x+3, y) + fraction (fx, fy).
+// Loads the (up to) 6 x 9 reference window once, with edge replication by clamping.
+__device__ void luma_quad(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int out[4]) {
+	const int r0 = fy ? -2 : 0, r1 = fy ? 3 : 0;
+	const int c0 = fx ? -2 : 0, c1 = fx ? 6 : 3;
+	// horizontal half-pel intermediates (unrounded) for the rows that are needed
+	int hb[6][4];       // b1 for rows -2..3 at columns 0..3
+	int px[6][5];       // integer samples rows -2..3, columns 0..4
+	int vh[5];          // h1 (vertical, unrounded) at columns 0..4, row 0
+#pragma unroll
+	for (int r = 0; r < 6; ++r) {
+		int ry = r - 2;
+		if (ry < r0 || ry > r1) continue;
+		int yy = min(max(y + ry, 0), H - 1);
+		const uint8_t *row = ref + (size_t)yy * W;
+		int v[9];
+#pragma unroll
+		for (int c = 0; c < 9; ++c) {
+			int cx = c - 2;
+			v[c] = (cx >= c0 && cx <= c1) ? (int)__ldg(row + min(max(x + cx, 0), W - 1)) : 0;
+		}
+#pragma unroll
+		for (int i = 0; i < 5; ++i) px[r][i] = v[i + 2];
+		if (fx) {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) hb[r][i] = tap6(v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5]);
+		}
+	}
+	if (fy) {
+#pragma unroll
+		for (int i = 0; i < 5; ++i) vh[i] = tap6(px[0][i], px[1][i], px[2][i], px[3][i], px[4][i], px[5][i]);
+	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		int G = px[2][i];
+		int v;
+		if (!fx && !fy) {
+			v = G;
+		} else if (!fy) {
+			int b = clip255((hb[2][i] + 16) >> 5);
+			v = fx == 2 ? b : ((fx == 1 ? G : px[2][i + 1]) + b + 1) >> 1;
+		} else if (!fx) {
+			int h = clip255((vh[i] + 16) >> 5);
+			v = fy == 2 ? h : ((fy == 1 ? G : px[3][i]) + h + 1) >> 1;
+		} else {
+			int b = clip255((hb[2][i] + 16) >> 5);
+			int s = clip255((hb[3][i] + 16) >> 5);
+			int h = clip255((vh[i] + 16) >> 5);
+			int m = clip255((vh[i + 1] + 16) >> 5);
+			int j = clip255((tap6(hb[0][i], hb[1][i], hb[2][i], hb[3][i], hb[4][i], hb[5][i]) + 512) >> 10);
+			if (fx == 2 && fy == 2) v = j;
+			else if (fx == 2) v = ((fy == 1 ? b : s) + j + 1) >> 1;
+			else if (fy == 2) v = ((fx == 1 ? h : m) + j + 1) >> 1;
+			else v = ((fy == 1 ? b : s) + (fx == 1 ? h : m) + 1) >> 1;
+		}
+		out[i] = v;
+	}
+}
+
+// Four adjacent NV12 chroma bytes (Cb Cr Cb Cr) starting at byte xb (even) of chroma row y.
+__device__ void chroma_quad(const uint8_t *__restrict__ ref, int W, int CH, int xb, int y, int mvx, int mvy, int out[4]) {
+	int fx = mvx & 7, fy = mvy & 7;
+	int cw = W >> 1;
+	int cy0 = min(max(y + (mvy >> 3), 0), CH - 1), cy1 = min(max(y + (mvy >> 3) + 1, 0), CH - 1);
+	const uint8_t *r0 = ref + (size_t)cy0 * W, *r1 = ref + (size_t)cy1 * W;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		int comp = i & 1;
+		int cx = (xb >> 1) + (i >> 1) + (mvx >> 3);
+		int x0 = min(max(cx, 0), cw - 1) * 2 + comp, x1 = min(max(cx + 1, 0), cw - 1) * 2 + comp;
+		int A = __ldg(r0 + x0), B = __ldg(r0 + x1), C = __ldg(r1 + x0), D = __ldg(r1 + x1);
+		out[i] = ((8 - fx) * (8 - fy) * A + fx * (8 - fy) * B + (8 - fx) * fy * C + fx * fy * D + 32) >> 6;
+	}
+}
+
+constexpr int INTER_TPM = 96;    // threads per MB: 64 luma words + 32 chroma words
+constexpr int INTER_MBS = 2;     // MBs per CTA
+
+__global__ void __launch_bounds__(INTER_TPM * INTER_MBS)
+h264_inter_kernel(const H4Job *__restrict__ jobs) {
+	__shared__ __align__(16) int16_t s_res[INTER_MBS][24][16];
+	__shared__ uint32_t s_has[INTER_MBS];
+	__shared__ b2_h264_mc s_mc[INTER_MBS][16];
+	__shared__ uint8_t s_map[INTER_MBS][16];
+
+	const H4Job job = jobs[blockIdx.z];
+	const int lm = threadIdx.x / INTER_TPM, t = threadIdx.x % INTER_TPM;
+	const int mbx = blockIdx.x * INTER_MBS + lm, mby = blockIdx.y;
+	const bool live = mbx < job.mb_w;
+	b2_h264_mb m;
+	m.type = 255;
+	if (live) m = job.mbs[(size_t)mby * job.mb_w + mbx];
+	const bool inter = live && m.type == B2_H4_INTER;
+	if (t == 0) s_has[lm] = 0;
+	__syncthreads();
+	if (inter) {
+		if (t < 24) {
+			if (block_residual(job, m, t, s_res[lm][t])) atomicOr(&s_has[lm], 1u << t);
+		} else if (t >= 32 && t < 32 + m.mc_cnt) {
+			int r = t - 32;
+			b2_h264_mc mc = job.mcs[m.mc_idx + r];
+			s_mc[lm][r] = mc;
+			int x4 = mc.pos & 3, y4 = mc.pos >> 2, pw = mc.size & 15, ph = mc.size >> 4;
+			for (int y = y4; y < y4 + ph; ++y)
+				for (int x = x4; x < x4 + pw; ++x) s_map[lm][y * 4 + x] = (uint8_t)r;
+		}
+	}
+	__syncthreads();
+	if (!inter) return;
+
+	const int W = job.mb_w * 16, H = job.mb_h * 16;
+	const size_t luma_size = (size_t)W * H;
+	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
+	uint8_t *dst_c = dst_y + luma_size;
+	int px[4];
+	if (t < 64) {
+		const int row = t >> 2, xq = t & 3;                 // luma word: row 0..15, 4-pixel column 0..3
+		const b2_h264_mc &mc = s_mc[lm][s_map[lm][(row >> 2) * 4 + xq]];
+		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0];
+		int mvx = mc.mv[0][0], mvy = mc.mv[0][1];
+		luma_quad(ref, W, H, mbx * 16 + xq * 4 + (mvx >> 2), mby * 16 + row + (mvy >> 2), mvx & 3, mvy & 3, px);
+		const int b = c_r2b[(row >> 2) * 4 + xq];
+		if ((s_has[lm] >> b) & 1) {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) px[i] = clip255(px[i] + s_res[lm][b][(row & 3) * 4 + i]);
+		}
+		uint32_t w = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
+		*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + row) * W + mbx * 16 + xq * 4) = w;
+	} else {
+		const int w_ = t - 64;
+		const int row = w_ >> 2, xq = w_ & 3;               // chroma word: row 0..7, bytes xq*4..xq*4+3
+		// chroma sample (cx, cy) belongs to luma 4x4 block (cx >> 1, cy >> 1)
+		const b2_h264_mc &mc = s_mc[lm][s_map[lm][(row >> 1) * 4 + xq]];
+		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0] + luma_size;
+		chroma_quad(ref, W, H >> 1, mbx * 16 + xq * 4, mby * 8 + row, mc.mv[0][0], mc.mv[0][1], px);
+		// bytes 0,2 -> Cb samples 2*xq, 2*xq+1; bytes 1,3 -> Cr
+		const int cb = 16 + (row >> 2) * 2 + (xq >> 1), cr = cb + 4;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			int blk = (i & 1) ? cr : cb;
+			int sx = ((xq & 1) * 2 + (i >> 1));
+			if ((s_has[lm] >> blk) & 1) px[i] = clip255(px[i] + s_res[lm][blk][(row & 3) * 4 + sx]);
+		}
+		uint32_t w = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
+		*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + row) * W + mbx * 16 + xq * 4) = w;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// intra wavefront: one warp per macroblock of the diagonal x + 2y = d
+// ------------------------------------------------------------------------------------------------
+struct IntraTile {
+	uint8_t y[17][24];      // row 0 = samples above (col 0 = top-left, cols 1..16 above, 17..20 above-right); col 0 = left
+	uint8_t c[2][9][12];    // per component: row 0 above (col 0 top-left), col 0 left
+	int16_t res[24][16];
+	uint32_t has;
+};
+
+__device__ __forceinline__ int blk_avail(int k, int a) {
+	int x = c_blk_x[k], y = c_blk_y[k];
+	int left = x > 0 || (a & 1), top = y > 0 || (a & 2), tr;
+	if (y == 0) tr = x < 3 ? (a & 2) != 0 : (a & 4) != 0;
+	else if (x == 3) tr = 0;
+	else tr = c_r2b[(y - 1) * 4 + x + 1] < k;
+	return (left ? 1 : 0) | (top ? 2 : 0) | (tr ? 4 : 0);
+}
+
+// one sample of Intra4x4 prediction; T(i) = p[i,-1] (i = -1..7), L(i) = p[-1,i] (i = -1..3)
+__device__ int pred4x4_sample(const IntraTile &tl, int bx, int by, int mode, int avail, int x, int y) {
+	const uint8_t *top = &tl.y[by * 4][bx * 4 + 1];      // top[i] = p[i,-1], top[-1] = p[-1,-1]
+#define T(i) ((avail & 4) || (i) < 4 ? (int)top[(i)] : (int)top[3])
+#define L(i) ((int)tl.y[by * 4 + 1 + (i)][bx * 4])
+	switch (mode) {
+	case 0: return T(x);
+	case 1: return L(y);
+	case 2:
+		if ((avail & 3) == 3) return (T(0) + T(1) + T(2) + T(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
+		if (avail & 1) return (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
+		if (avail & 2) return (T(0) + T(1) + T(2) + T(3) + 2) >> 2;
+		return 128;
+	case 3:
+		return (x == 3 && y == 3) ? (T(6) + 3 * T(7) + 2) >> 2 : (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
+	case 4:
+		if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
+		if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+		return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
+	case 5: {
+		int z = 2 * x - y;
+		if (z >= 0 && !(z & 1)) return (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
+		if (z >= 0) return (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
+		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+		return (L(y - 1) + 2 * L(y - 2) + L(y - 3) + 2) >> 2;
+	}
+	case 6: {
+		int z = 2 * y - x;
+		if (z >= 0 && !(z & 1)) return (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
+		if (z >= 0) return (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
+		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+		return (T(x - 1) + 2 * T(x - 2) + T(x - 3) + 2) >> 2;
+	}
+	case 7:
+		if (!(y & 1)) return (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
+		return (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
+	default: {
+		int z = x + 2 * y;
+		if (z > 5) return L(3);
+		if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
+		if (!(z & 1)) return (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
+		return (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2;
+	}
+	}
+#undef T
+#undef L
+}
+
+constexpr int INTRA_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * INTRA_WARPS)
+h264_intra_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_job) {
+	__shared__ IntraTile s_tile[INTRA_WARPS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int item = blockIdx.x * INTRA_WARPS + warp;
+	if (item >= n_jobs * per_job) return;
+	const H4Job job = jobs[item / per_job];
+	// MBs of the diagonal: y from y_lo upwards, x = diag - 2y
+	const int y_lo = max(0, (diag - (job.mb_w - 1) + 1) >> 1);
+	const int mby = y_lo + item % per_job;
+	const int mbx = diag - 2 * mby;
+	if (mby >= job.mb_h || mbx < 0 || mbx >= job.mb_w) return;
+	const b2_h264_mb m = job.mbs[(size_t)mby * job.mb_w + mbx];
+	if (m.type == B2_H4_INTER) return;
+	IntraTile &tl = s_tile[warp];
+	const int W = job.mb_w * 16, H = job.mb_h * 16;
+	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
+	uint8_t *fc = fy + (size_t)W * H;
+	uint8_t *py = fy + (size_t)mby * 16 * W + mbx * 16;
+	uint8_t *pc = fc + (size_t)mby * 8 * W + mbx * 16;
+
+	if (m.type == B2_H4_IPCM) {
+		const uint8_t *src = reinterpret_cast<const uint8_t *>(job.coefs + (size_t)m.coef_idx * 16);
+		for (int i = lane; i < 64; i += 32) {          // 64 luma words
+			int row = i >> 2, xq = i & 3;
+			*reinterpret_cast<uint32_t *>(py + (size_t)row * W + xq * 4) = *reinterpret_cast<const uint32_t *>(src + row * 16 + xq * 4);
+		}
+		for (int i = lane; i < 128; i += 32) {         // 128 chroma bytes
+			int row = i >> 4, xb = i & 15;
+			pc[(size_t)row * W + xb] = src[256 + (xb & 1) * 64 + row * 8 + (xb >> 1)];
+		}
+		return;
+	}
+
+	// ---- neighbours into the tile ------------------------------------------------------------
+	const int a = m.intra_avail | m.intra_avail_c;
+	if (lane < 21) {            // above row: x = -1 .. 19
+		int x = lane - 1;
+		bool ok = (a & 2) && !(x < 0 && mbx == 0) && !(x >= 16 && mbx == job.mb_w - 1);
+		tl.y[0][lane] = (ok && mby > 0) ? py[-(ptrdiff_t)W + x] : 128;
+	}
+	if (lane < 16) tl.y[1 + lane][0] = ((a & 1) && mbx > 0) ? py[(size_t)lane * W - 1] : 128;
+	if (lane < 18) {            // chroma above: byte x = -2 .. 15
+		int xb = lane - 2;
+		bool ok = (a & 2) && mby > 0 && !(xb < 0 && mbx == 0);
+		tl.c[xb & 1][0][(xb + 2) >> 1] = ok ? pc[-(ptrdiff_t)W + xb] : 128;
+	}
+	if (lane < 16) {            // chroma left: rows 0..7, two components
+		int row = lane >> 1, comp = lane & 1;
+		tl.c[comp][1 + row][0] = ((a & 1) && mbx > 0) ? pc[(size_t)row * W - 2 + comp] : 128;
+	}
+	if (lane == 0) tl.has = 0;
+	__syncwarp();
+	if (lane < 24) {
+		if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
+	}
+	__syncwarp();
+
+	// ---- luma -----------------------------------------------------------------------------------
+	if (m.type == B2_H4_I4x4) {
+		for (int k = 0; k < 16; ++k) {
+			const int bx = c_blk_x[k], by = c_blk_y[k];
+			if (lane < 16) {
+				int x = lane & 3, y = lane >> 2;
+				int mode = (m.i4_modes[k >> 1] >> ((k & 1) * 4)) & 15;
+				int v = pred4x4_sample(tl, bx, by, mode, blk_avail(k, m.intra_avail), x, y);
+				if ((tl.has >> k) & 1) v = clip255(v + tl.res[k][y * 4 + x]);
+				tl.y[by * 4 + 1 + y][bx * 4 + 1 + x] = (uint8_t)v;
+			}
+			__syncwarp();
+		}
+	} else {
+		const int av = m.intra_avail;
+		int dcv = 128, pa = 0, pb = 0, pcn = 0;
+		if (m.i16_mode == 2) {
+			int sum = 0;
+			if (av & 1) for (int i = 0; i < 16; ++i) sum += tl.y[1 + i][0];
+			if (av & 2) for (int i = 0; i < 16; ++i) sum += tl.y[0][1 + i];
+			dcv = (av & 3) == 3 ? (sum + 16) >> 5 : ((av & 3) ? (sum + 8) >> 4 : 128);
+		} else if (m.i16_mode == 3) {
+			int Hh = 0, Vv = 0;
+			for (int i = 0; i < 8; ++i) {
+				Hh += (i + 1) * ((int)tl.y[0][1 + 8 + i] - (int)tl.y[0][1 + 6 - i]);
+				Vv += (i + 1) * ((int)tl.y[1 + 8 + i][0] - (int)tl.y[1 + 6 - i][0]);
+			}
+			pa = 16 * ((int)tl.y[16][0] + (int)tl.y[0][16]);
+			pb = (5 * Hh + 32) >> 6;
+			pcn = (5 * Vv + 32) >> 6;
+		}
+		__syncwarp();
+		for (int i = lane; i < 256; i += 32) {
+			int x = i & 15, y = i >> 4;
+			int v;
+			switch (m.i16_mode) {
+			case 0: v = tl.y[0][1 + x]; break;
+			case 1: v = tl.y[1 + y][0]; break;
+			case 2: v = dcv; break;
+			default: v = clip255((pa + pb * (x - 7) + pcn * (y - 7) + 16) >> 5); break;
+			}
+			int k = c_r2b[(y >> 2) * 4 + (x >> 2)];
+			if ((tl.has >> k) & 1) v = clip255(v + tl.res[k][(y & 3) * 4 + (x & 3)]);
+			// rows/columns read by the predictors above are row 0 / column 0 only: safe to overwrite
+			tl.y[1 + y][1 + x] = (uint8_t)v;
+		}
+	}
+	// ---- chroma -----------------------------------------------------------------------------------
+	{
+		const int av = m.intra_avail_c;
+		for (int i = lane; i < 128; i += 32) {
+			int comp = i >> 6, x = i & 7, y = (i >> 3) & 7;
+			const uint8_t (*c)[12] = tl.c[comp];
+			int v;
+			if (m.chroma_mode == 0) {
+				int bx = x >> 2, by = y >> 2;
+				int st = 0, sl = 0;
+				for (int j = 0; j < 4; ++j) { st += c[0][1 + bx * 4 + j]; sl += c[1 + by * 4 + j][0]; }
+				bool ht = av & 2, hl = av & 1;
+				if (bx == by) v = (ht && hl) ? (st + sl + 4) >> 3 : (hl ? (sl + 2) >> 2 : (ht ? (st + 2) >> 2 : 128));
+				else if (bx == 1) v = ht ? (st + 2) >> 2 : (hl ? (sl + 2) >> 2 : 128);
+				else v = hl ? (sl + 2) >> 2 : (ht ? (st + 2) >> 2 : 128);
+			} else if (m.chroma_mode == 1) {
+				v = c[1 + y][0];
+			} else if (m.chroma_mode == 2) {
+				v = c[0][1 + x];
+			} else {
+				int Hh = 0, Vv = 0;
+				for (int j = 0; j < 4; ++j) {
+					Hh += (j + 1) * ((int)c[0][1 + 4 + j] - (int)c[0][1 + 2 - j]);
+					Vv += (j + 1) * ((int)c[1 + 4 + j][0] - (int)c[1 + 2 - j][0]);
+				}
+				int pa = 16 * ((int)c[8][0] + (int)c[0][8]), pb = (34 * Hh + 32) >> 6, pcn = (34 * Vv + 32) >> 6;
+				v = clip255((pa + pb * (x - 3) + pcn * (y - 3) + 16) >> 5);
+			}
+			int blk = 16 + comp * 4 + (y >> 2) * 2 + (x >> 2);
+			if ((tl.has >> blk) & 1) v = clip255(v + tl.res[blk][(y & 3) * 4 + (x & 3)]);
+			pc[(size_t)y * W + 2 * x + comp] = (uint8_t)v;
+		}
+	}
+	__syncwarp();
+	for (int i = lane; i < 64; i += 32) {
+		int row = i >> 2, xq = i & 3;
+		const uint8_t *s = &tl.y[1 + row][1 + xq * 4];
+		uint32_t w = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+		*reinterpret_cast<uint32_t *>(py + (size_t)row * W + xq * 4) = w;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// deblocking wavefront: one warp per macroblock of the diagonal
+// ------------------------------------------------------------------------------------------------
+// filter one line across an edge; p = pointer to q0, st = step across the edge
+__device__ void filter_line(uint8_t *px, ptrdiff_t st, int bs, int alpha, int beta, int tc0, bool luma) {
+	int p0 = px[-st], p1 = px[-2 * st], q0 = px[0], q1 = px[st];
+	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+	if (bs == 4) {
+		if (luma) {
+			int p2 = px[-3 * st], q2 = px[2 * st];
+			bool strong = abs(p0 - q0) < (alpha >> 2) + 2;
+			if (strong && abs(p2 - p0) < beta) {
+				int p3 = px[-4 * st];
+				px[-st] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+				px[-2 * st] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+				px[-3 * st] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+			} else {
+				px[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+			}
+			if (strong && abs(q2 - q0) < beta) {
+				int q3 = px[3 * st];
+				px[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+				px[st] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+				px[2 * st] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+			} else {
+				px[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+			}
+		} else {
+			px[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+			px[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+		}
+		return;
+	}
+	int tc;
+	if (luma) {
+		int p2 = px[-3 * st], q2 = px[2 * st];
+		int ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
+		tc = tc0 + ap + aq;
+		if (ap) px[-2 * st] = (uint8_t)(p1 + min(max((p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1, -tc0), tc0));
+		if (aq) px[st] = (uint8_t)(q1 + min(max((q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1, -tc0), tc0));
+	} else {
+		tc = tc0 + 1;
+	}
+	int delta = min(max(((q0 - p0) * 4 + (p1 - q1) + 4) >> 3, -tc), tc);
+	px[-st] = (uint8_t)clip255(p0 + delta);
+	px[0] = (uint8_t)clip255(q0 - delta);
+}
+
+constexpr int DBK_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * DBK_WARPS)
+h264_deblock_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_job) {
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int item = blockIdx.x * DBK_WARPS + warp;
+	if (item >= n_jobs * per_job) return;
+	const H4Job job = jobs[item / per_job];
+	const int y_lo = max(0, (diag - (job.mb_w - 1) + 1) >> 1);
+	const int mby = y_lo + item % per_job;
+	const int mbx = diag - 2 * mby;
+	if (mby >= job.mb_h || mbx < 0 || mbx >= job.mb_w) return;
+	const b2_h264_dbk *dp = &job.dbk[(size_t)mby * job.mb_w + mbx];
+	const b2_h264_dbk d = *dp;
+	if (d.flags & B2_DBK_OFF) return;
+	const int W = job.mb_w * 16, H = job.mb_h * 16;
+	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
+	uint8_t *fc = fy + (size_t)W * H;
+	uint8_t *py = fy + (size_t)mby * 16 * W + mbx * 16;
+	uint8_t *pc = fc + (size_t)mby * 8 * W + mbx * 16;
+	const bool is_luma = lane < 16;
+	const int li = lane & 15;                 // line index: luma line 0..15, or chroma (line 0..7, comp)
+#pragma unroll 1
+	for (int dir = 0; dir < 2; ++dir) {
+		const uint32_t bits = dir ? d.bs_h : d.bs_v;
+		const bool edge_ok = d.flags & (dir ? B2_DBK_TOP_EDGE : B2_DBK_LEFT_EDGE);
+		const bool bs4 = d.flags & (dir ? B2_DBK_TOP_BS4 : B2_DBK_LEFT_BS4);
+		int nqy = 0, nqb = 0, nqr = 0;
+		if (edge_ok) {
+			const b2_h264_dbk *n = dir ? dp - job.mb_w : dp - 1;
+			nqy = n->qp_y; nqb = n->qp_cb; nqr = n->qp_cr;
+		}
+#pragma unroll 1
+		for (int e = 0; e < 4; ++e) {
+			const int eb = (bits >> (8 * e)) & 255;
+			if (!eb || (e == 0 && !edge_ok)) continue;
+			if (is_luma) {
+				int seg = li >> 2;
+				int bs = (eb >> (seg * 2)) & 3;
+				if (bs) {
+					if (e == 0 && bs4) bs = 4;
+					int qp = e ? d.qp_y : (d.qp_y + nqy + 1) >> 1;
+					int ia = min(max(qp + d.alpha_off, 0), 51), ib = min(max(qp + d.beta_off, 0), 51);
+					int alpha = c_alpha[ia], beta = c_beta[ib];
+					if (alpha) {
+						uint8_t *p = dir ? py + (size_t)e * 4 * W + li : py + (size_t)li * W + e * 4;
+						filter_line(p, dir ? (ptrdiff_t)W : 1, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, true);
+					}
+				}
+			} else if (!(e & 1)) {
+				// chroma: lines 0..7 per component.  dir 0: li = row * 2 + comp; dir 1: li = byte column
+				int line = dir ? li >> 1 : li >> 1, comp = li & 1;
+				int seg = line >> 1;
+				int bs = (eb >> (seg * 2)) & 3;
+				if (bs) {
+					if (e == 0 && bs4) bs = 4;
+					int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr : nqb;
+					int qp = e ? qc : (qc + qn + 1) >> 1;
+					int ia = min(max(qp + d.alpha_off, 0), 51), ib = min(max(qp + d.beta_off, 0), 51);
+					int alpha = c_alpha[ia], beta = c_beta[ib];
+					if (alpha) {
+						uint8_t *p = dir ? pc + (size_t)(e / 2) * 4 * W + line * 2 + comp : pc + (size_t)line * W + (e / 2) * 8 + comp;
+						filter_line(p, dir ? (ptrdiff_t)W : 2, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, false);
+					}
+				}
+			}
+			__syncwarp();
+		}
+		__syncwarp();
+	}
+	(void)H;
+}
+
+}  // namespace
+
+static inline int diag_count(int mb_w, int mb_h) { return mb_w + 2 * (mb_h - 1); }
+// upper bound on MBs per diagonal
+static inline int diag_width(int mb_w, int mb_h) { int a = (mb_w + 1) / 2; return a < mb_h ? a : mb_h; }
+
+int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
+                bool deblock, uint64_t *launches) {
+	if (n_jobs <= 0) return 0;
+	if (any_inter) {
+		dim3 grid((mb_w + INTER_MBS - 1) / INTER_MBS, mb_h, n_jobs);
+		h264_inter_kernel<<<grid, INTER_TPM * INTER_MBS, 0, stream>>>(d_jobs);
+		if (launches) ++*launches;
+	}
+	const int nd = diag_count(mb_w, mb_h), per = diag_width(mb_w, mb_h);
+	if (any_intra) {
+		int items = per * n_jobs;
+		for (int d = 0; d < nd; ++d)
+			h264_intra_kernel<<<(items + INTRA_WARPS - 1) / INTRA_WARPS, 32 * INTRA_WARPS, 0, stream>>>(d_jobs, n_jobs, d, per);
+		if (launches) *launches += nd;
+	}
+	if (deblock) {
+		int items = per * n_jobs;
+		for (int d = 0; d < nd; ++d)
+			h264_deblock_kernel<<<(items + DBK_WARPS - 1) / DBK_WARPS, 32 * DBK_WARPS, 0, stream>>>(d_jobs, n_jobs, d, per);
+		if (launches) *launches += nd;
+	}
+	B2_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+}  // namespace b2

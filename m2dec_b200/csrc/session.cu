@@ -154,6 +154,50 @@ extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 	return 0;
 }
 
+extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
+	if (!s || !p || s->codec != B2_CODEC_H264) return -1;
+	if (p->mb_w * 16 != s->width || p->mb_h * 16 != s->height) {
+		set_error("picture %dx%d MB does not match session %dx%d", p->mb_w, p->mb_h, s->width, s->height);
+		return -1;
+	}
+	if ((unsigned)p->dst >= (unsigned)s->nframes) return -1;
+	for (uint32_t i = 0; i < p->n_mcs; ++i)
+		if ((unsigned)p->mcs[i].ref_frame[0] >= (unsigned)s->nframes) {
+			set_error("motion record %u references frame %d outside the pool", i, p->mcs[i].ref_frame[0]);
+			return -1;
+		}
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	size_t off_mbs = align_up(sizeof(H4Job), 256);
+	size_t off_dbk = align_up(off_mbs + sizeof(b2_h264_mb) * p->n_mbs, 256);
+	size_t off_mcs = align_up(off_dbk + sizeof(b2_h264_dbk) * p->n_mbs, 256);
+	size_t off_coef = align_up(off_mcs + sizeof(b2_h264_mc) * p->n_mcs, 256);
+	size_t total = off_coef + (size_t)p->n_coef_recs * 32;
+	StageSlot *sl;
+	if (acquire_slot(s, total, &sl) < 0) return -1;
+	H4Job job;
+	memset(&job, 0, sizeof(job));
+	job.frames = s->frames;
+	job.frame_bytes = s->frame_bytes;
+	job.mbs = (const b2_h264_mb *)(sl->dev + off_mbs);
+	job.dbk = (const b2_h264_dbk *)(sl->dev + off_dbk);
+	job.mcs = (const b2_h264_mc *)(sl->dev + off_mcs);
+	job.coefs = (const int16_t *)(sl->dev + off_coef);
+	job.dst = p->dst;
+	job.mb_w = p->mb_w;
+	job.mb_h = p->mb_h;
+	memcpy(sl->host, &job, sizeof(job));
+	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
+	memcpy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
+	if (p->n_mcs) memcpy(sl->host + off_mcs, p->mcs, sizeof(b2_h264_mc) * p->n_mcs);
+	if (p->n_coef_recs) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
+	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
+	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs, p->n_intra > 0,
+	                p->deblock != 0, &s->launches) < 0) return -1;
+	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
+	sl->pending = true;
+	return 0;
+}
+
 extern "C" int b2_session_sync(b2_session *s) {
 	if (!s) return -1;
 	B2_CUDA_OK(cudaSetDevice(s->dev));

@@ -1,0 +1,48 @@
+"""Named test streams: writer arguments (tools/streamgen) for each parity case."""
+import os
+import subprocess
+
+import util
+
+STREAMGEN = os.path.join(util.ROOT, "tools", "_bin", "streamgen")
+
+# name -> (codec, args).  Small enough for the CPU oracle / reference to finish in seconds.
+H264_CASES = {
+    "h264_basic": "mbw=8 mbh=6 frames=6 seed=1",
+    "h264_nodeblock": "mbw=8 mbh=6 frames=6 seed=2 deblock=0",
+    "h264_refs3": "mbw=11 mbh=9 frames=12 seed=3 refs=3",
+    "h264_gop7": "mbw=11 mbh=9 frames=20 seed=4 refs=2 gop=7",
+    "h264_slices3": "mbw=10 mbh=7 frames=8 seed=5 slices=3",
+    "h264_slices_dbk_mix": "mbw=10 mbh=7 frames=8 seed=6 slices=4 deblock=2",
+    "h264_intra_ipcm": "mbw=6 mbh=5 frames=10 seed=7 intra_pct=50 ipcm_pct=10",
+    "h264_skippy": "mbw=6 mbh=5 frames=10 seed=8 skip_pct=60",
+    "h264_qp20_dense": "mbw=9 mbh=5 frames=8 seed=9 qp=20 coded_pct=60",
+    "h264_qp36_ab": "mbw=9 mbh=5 frames=8 seed=10 qp=36 alpha_div2=-2 beta_div2=1",
+    "h264_qp40_cqp": "mbw=9 mbh=5 frames=8 seed=11 qp=40 alpha_div2=3 beta_div2=4 chroma_qp_offset=4",
+    "h264_umv": "mbw=9 mbh=5 frames=8 seed=12 qp=30 chroma_qp_offset=-6 mv_range=300 mv_out=60",
+    "h264_big": "mbw=20 mbh=12 frames=24 seed=13 refs=4 gop=20 slices=2",
+    "h264_crop": "mbw=5 mbh=4 frames=6 seed=14 crop_bottom=8 crop_right=6",
+    "h264_long": "mbw=8 mbh=8 frames=40 seed=15 refs=2",
+    "h264_biglevels": "mbw=8 mbh=6 frames=6 seed=16 qp=12 big_levels=1 coded_pct=50",
+    "h264_constrained": "mbw=8 mbh=6 frames=8 seed=17 constrained_intra=1 intra_pct=30",
+    "h264_2x2": "mbw=2 mbh=2 frames=6 seed=21",
+    "h264_2x3_slices": "mbw=2 mbh=3 frames=6 seed=25 slices=2",
+}
+# Pictures one macroblock wide or high: the compiled reference disagrees with ffmpeg there (its
+# own bug), our decode agrees with ffmpeg.  Used for CUDA-vs-oracle (and ffmpeg luma) only.
+H264_REFERENCE_DEVIATES = {
+    "h264_1mb": "mbw=1 mbh=1 frames=5 seed=18",
+    "h264_row": "mbw=7 mbh=1 frames=5 seed=19",
+    "h264_col": "mbw=1 mbh=7 frames=5 seed=20 slices=2",
+}
+# committed under tests/golden/ together with the reference's MD5 lines
+H264_GOLDEN = ["h264_basic", "h264_refs3", "h264_slices_dbk_mix", "h264_intra_ipcm", "h264_qp40_cqp", "h264_umv", "h264_constrained"]
+
+MPEG2_CASES = {
+}
+
+
+def generate(codec, args):
+    """Run the test-only writer; returns the elementary stream bytes."""
+    out = subprocess.run([STREAMGEN, codec, *args.split()], stdout=subprocess.PIPE, check=True)
+    return out.stdout

@@ -1,0 +1,100 @@
+"""H.264 path.  CPU tests: product parse + CPU oracle vs the reference (committed golden MD5s,
+and the compiled reference itself where oracle/_ref exists).  GPU tests: product parse + CUDA
+reconstruction through the plugin table vs the same."""
+import os
+
+import pytest
+
+import streams
+import util
+
+
+def _golden(name):
+    data = open(os.path.join(util.GOLDEN, name + ".264"), "rb").read()
+    md5 = open(os.path.join(util.GOLDEN, name + ".md5")).read().split()
+    return data, md5
+
+
+@pytest.mark.parametrize("name", streams.H264_GOLDEN)
+def test_writer_is_deterministic(name):
+    data, _ = _golden(name)
+    assert streams.generate("h264", streams.H264_CASES[name]) == data
+
+
+@pytest.mark.parametrize("name", streams.H264_GOLDEN)
+def test_oracle_matches_golden(name):
+    data, golden = _golden(name)
+    assert util.oracle_md5("h264", data) == golden
+
+
+@pytest.mark.parametrize("name", sorted(streams.H264_CASES))
+def test_oracle_matches_compiled_reference(name):
+    if not util.have_ref():
+        pytest.skip("oracle/_ref not built")
+    data = streams.generate("h264", streams.H264_CASES[name])
+    ref = util.ref_md5(data, "264")
+    assert len(ref) > 0
+    assert util.oracle_md5("h264", data) == ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", streams.H264_GOLDEN)
+def test_cuda_matches_golden(name):
+    import m2dec_b200
+    data, golden = _golden(name)
+    assert m2dec_b200.decode_file("h264", data) == golden
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(streams.H264_CASES))
+def test_cuda_matches_oracle_and_reference(name):
+    import m2dec_b200
+    data = streams.generate("h264", streams.H264_CASES[name])
+    gpu = m2dec_b200.decode_file("h264", data)
+    assert gpu == util.oracle_md5("h264", data)
+    if util.have_ref():
+        assert gpu == util.ref_md5(data, "264")
+
+
+def _ffmpeg_luma(data, w, h, n):
+    """Luma planes from OpenCV's bundled ffmpeg H.264 decoder (an independent implementation)."""
+    import tempfile
+    import cv2
+    import numpy as np
+    with tempfile.NamedTemporaryFile(suffix=".264") as f:
+        f.write(data)
+        f.flush()
+        cap = cv2.VideoCapture(f.name)
+        cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+        out = []
+        for _ in range(n):
+            ok, frm = cap.read()
+            if not ok:
+                break
+            out.append(np.asarray(frm).reshape(-1, w)[:h].copy())
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(streams.H264_REFERENCE_DEVIATES))
+def test_degenerate_sizes_match_ffmpeg(name):
+    cv2 = pytest.importorskip("cv2")  # noqa: F841
+    import m2dec_b200
+    args = streams.H264_REFERENCE_DEVIATES[name]
+    kv = dict(a.split("=") for a in args.split())
+    w, h = int(kv["mbw"]) * 16, int(kv["mbh"]) * 16
+    data = streams.generate("h264", args)
+    ours = []
+    m2dec_b200.decode_file("h264", data, post=lambda f: ours.append(m2dec_b200.crop_frame(f)[0].copy()),
+                           tap=util.oracle_tap, device_off=True)
+    theirs = _ffmpeg_luma(data, w, h, len(ours))
+    assert len(theirs) == len(ours) > 0
+    for a, b in zip(ours, theirs):
+        assert (a == b).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(streams.H264_REFERENCE_DEVIATES))
+def test_cuda_matches_oracle_degenerate(name):
+    import m2dec_b200
+    data = streams.generate("h264", streams.H264_REFERENCE_DEVIATES[name])
+    assert m2dec_b200.decode_file("h264", data) == util.oracle_md5("h264", data)
