@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of m2dec-b200.
+
+Metric (BASELINE.json): 1080p frames/sec/GPU, every frame bit-exact against the reference
+decoder, on the H.264 Baseline CAVLC I/P 1920x1080 workload (BASELINE.json configs[1]):
+`lanes` independent synthetic streams per GPU from the committed test-only writer.
+
+  value  kernel replay: every picture's SoA resident in HBM, one batched launch per kernel and
+         step (picture #t of all lanes); device-timed with CUDA events on the launching stream.
+  e2e    the same metric through the reference-facing plugin table (m2d_func_table_t) with
+         HOST buffers: elementary streams in host memory -> host parse -> H2D of the SoA ->
+         kernels -> D2H of every output frame, timed end to end.
+  roofline      dominant kernel: algorithmic bytes / its device time.
+  cpu_baseline  the compiled reference CLI (oracle/_ref/h264dec, decode only) on the host cores.
+
+`--impl reference` times the reference's own CPU decoder on the same streams, all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STREAMGEN = os.path.join(ROOT, "tools", "_bin", "streamgen")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "h264dec")
+METRIC = "1080p frames/sec (H.264 Baseline CAVLC I/P, bit-exact MD5 vs reference)"
+UNIT = "frames/s"
+MBW, MBH = 120, 68                      # 1920x1088 coded, 1920x1080 displayed
+FRAME_BYTES = MBW * 16 * MBH * 16 * 3 // 2
+
+
+def workload_args(seed, frames):
+    # SURVEY.md 8d "C2": IDR + P, 1 reference, all P partition sizes, ~10 % intra, qp ~ 28,
+    # deblocking on, alpha = beta = 0, bounded levels (hazards 1-2)
+    return ("mbw=%d mbh=%d frames=%d seed=%d crop_bottom=8 gop=1000 refs=1 qp=28 intra_pct=10 skip_pct=15 "
+            "coded_pct=25 deblock=1" % (MBW, MBH, frames, seed)).split()
+
+
+def make_stream(seed, frames):
+    return subprocess.run([STREAMGEN, "h264", *workload_args(seed, frames)], stdout=subprocess.PIPE, check=True).stdout
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.path = gpu, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(delete=False, suffix=".csv")
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference_cli(paths, procs, md5=False):
+    """Decode every file in `paths` with the compiled reference, `procs` processes at a time.
+    Returns wall seconds."""
+    t0 = time.perf_counter()
+    running = []
+    todo = list(paths)
+    while todo or running:
+        while todo and len(running) < procs:
+            p = todo.pop()
+            args = [REF_BIN] + (["-O"] if md5 else []) + [p]
+            running.append(subprocess.Popen(args, cwd=os.path.dirname(p), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        running = [r for r in running if r.poll() is None]
+        if running and (len(running) >= procs or not todo):
+            time.sleep(0.002)
+    return time.perf_counter() - t0
+
+
+def write_streams(streams, d):
+    paths = []
+    for i, s in enumerate(streams):
+        p = os.path.join(d, "s%03d.264" % i)
+        with open(p, "wb") as f:
+            f.write(s)
+        paths.append(p)
+    return paths
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lanes", type=int, default=64, help="independent 1080p streams per GPU")
+    ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
+    ap.add_argument("--e2e-streams", type=int, default=16)
+    ap.add_argument("--verify-lanes", type=int, default=8, help="lanes whose every frame is MD5-checked against the reference")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    workload = "h264_baseline_cavlc_1080p_ip"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        procs = max(1, min(ncores, a.lanes))
+        streams = [make_stream(100 + i, a.frames) for i in range(procs)]
+        with tempfile.TemporaryDirectory() as d:
+            paths = write_streams(streams, d)
+            for _ in range(a.warmup):
+                run_reference_cli(paths, procs)
+            t = 0.0
+            for _ in range(a.steps):
+                t += run_reference_cli(paths, procs)
+        frames = procs * a.frames * a.steps
+        v = frames / t
+        sample = "%d streams x %d frames per step, %d processes of the compiled reference CLI (decode only)" % (procs, a.frames, procs)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000 * t / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    import numpy as np
+    import torch
+    import m2dec_b200
+    from m2dec_b200 import _native as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the reconstruction path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+
+    # ---- build the workload: parse on the host once, make every picture resident in HBM ------
+    t_prep = time.perf_counter()
+    seeds = [100 + rank * 1000 + i for i in range(a.lanes)]
+    streams = [make_stream(s, a.frames) for s in seeds]
+    rp = m2dec_b200.Replay("h264", MBW * 16, MBH * 16, a.lanes, pool_frames=18, cuda_device=local)
+    for lane, s in enumerate(streams):
+        n = rp.load_stream(lane, s)
+        assert n == a.frames, (n, a.frames)
+    t_prep = time.perf_counter() - t_prep
+
+    # ---- parity (untimed): every frame of the first lanes against the compiled reference -----
+    rp.run()
+    rp.sync()
+    verified, verify_kind = 0, "none"
+    nver = min(a.verify_lanes, a.lanes)
+    with tempfile.TemporaryDirectory() as d:
+        if os.path.exists(REF_BIN) and nver:
+            paths = write_streams(streams[:nver], d)
+            run_reference_cli(paths, min(ncores, nver), md5=True)
+            verify_kind = "compiled reference (oracle/_ref/h264dec -O)"
+            import hashlib
+            for lane in range(nver):
+                golden = open(os.path.join(d, "s%03d.out" % lane), "rb").read().split()
+                assert len(golden) == a.frames, (len(golden), a.frames)
+                for t, idx in enumerate(rp.outputs[lane]):
+                    y, c = rp.download(lane, idx)
+                    h = hashlib.md5()
+                    h.update(np.ascontiguousarray(y[:1080]).tobytes())
+                    h.update(np.ascontiguousarray(c[:540]).tobytes())
+                    if h.hexdigest().encode() != golden[t]:
+                        raise SystemExit("bench.py: MD5 mismatch lane %d picture %d" % (lane, t))
+                    verified += 1
+
+    # ---- timed region: K steps, one step = all lanes x frames ---------------------------------
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        rp.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        rp.run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kernel_ms = [0.0, 0.0, 0.0]
+    rp.mark(0)
+    for _ in range(a.steps):
+        rp.run(timed=True)
+    rp.mark(1)
+    rp.sync()
+    barrier()
+    total_ms = rp.elapsed_ms()
+    st = rp.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel device time of the last timed step (events between the phases of every sub-step)
+    kernel_ms = [st.kernel_ms[i] for i in range(3)]
+    if dist is not None:
+        tt = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    frames_per_step = a.lanes * a.frames
+    value = world * frames_per_step * a.steps / (total_ms / 1000.0)
+
+    # ---- end to end through the plugin table with host buffers --------------------------------
+    ne = min(a.e2e_streams, a.lanes)
+    threads_n = max(1, min(ne, ncores))
+    counts = [None] * ne
+    frames_out = [0] * ne
+
+    def decode_one(i):
+        n = [0]
+        dec = m2dec_b200.M2Decoder("h264", streams[i], cuda_device=local)
+        try:
+            dec.run(lambda frm: n.__setitem__(0, n[0] + 1))
+            c = (L.C.c_uint64 * 3)()
+            L.lib.b2_context_stats(dec.ctx, L.C.byref(c))
+            counts[i] = [int(c[0]), int(c[1]), int(c[2])]
+        finally:
+            dec.close()
+        frames_out[i] = n[0]
+
+    decode_one(0)    # warm-up: CUDA context, pinned staging
+    barrier()
+    t0 = time.perf_counter()
+    work = list(range(ne))
+    lock = threading.Lock()
+
+    def worker():
+        while True:
+            with lock:
+                if not work:
+                    return
+                i = work.pop()
+            decode_one(i)
+
+    ths = [threading.Thread(target=worker) for _ in range(threads_n)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_frames = sum(frames_out)
+    e2e_value = world * e2e_frames / e2e_s
+    h2d = sum(c[0] for c in counts)
+    d2h = sum(c[1] for c in counts)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peak, peak_src = peaks()
+    names = ["h264_inter_kernel", "h264_intra_kernel", "h264_deblock_kernel"]
+    dom = max(range(3), key=lambda i: kernel_ms[i])
+    alg = [int(st.alg_bytes[i]) for i in range(3)]
+    achieved = alg[dom] / (kernel_ms[dom] / 1000.0) / 1e9 if kernel_ms[dom] > 0 else 0.0
+    whole = sum(alg) / (st.total_ms / 1000.0) / 1e9 if st.total_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "per_kernel": {names[i]: {"ms_per_step": kernel_ms[i], "alg_bytes_per_step": alg[i],
+                                          "GBps": (alg[i] / (kernel_ms[i] / 1000.0) / 1e9 if kernel_ms[i] > 0 else None)}
+                               for i in range(3)},
+                "whole_step": {"alg_bytes": sum(alg), "ms": st.total_ms, "GBps": whole, "frac": whole / peak}}
+
+    # ---- CPU baseline: compiled reference on a bounded sample (about 10-30 s of CPU work) -----
+    cpu = None
+    if os.path.exists(REF_BIN):
+        procs = max(1, min(ncores, a.lanes, 32))
+        with tempfile.TemporaryDirectory() as d:
+            paths = write_streams(streams[:procs], d)
+            run_reference_cli(paths[:1], 1)
+            tcpu = run_reference_cli(paths, procs)
+        cpu = {"value": procs * a.frames / tcpu, "unit": UNIT, "cores": procs, "kind": "reference",
+               "sample": "%d of the workload's streams x %d frames, one reference CLI process per stream (decode only), %d host cores present"
+                         % (procs, a.frames, ncores)}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload, "lanes_per_gpu": a.lanes, "frames_per_lane": a.frames,
+                   "frames_per_step": frames_per_step, "coded_size": "1920x1088", "display_size": "1920x1080",
+                   "l2_policy": "inputs larger than L2 (%.0f MB of pictures written per step)" % (frames_per_step * FRAME_BYTES / 1e6),
+                   "parity": "%d frames MD5-checked against %s before timing" % (verified, verify_kind),
+                   "partitioning": "independent streams per GPU, no collective", "host_prep_s": t_prep},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "streams": ne, "frames": e2e_frames, "host_threads": threads_n, "seconds": e2e_s,
+                "path": "m2d_func_table_t (h264d_gpu_func): host ES -> parse -> H2D SoA -> kernels -> D2H every output frame"},
+        "gpu_launches": int(st.launches) * a.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -175,6 +175,47 @@ int b2_session_sync(b2_session *s);
 /* Number of kernel launches issued by this session so far.                                */
 uint64_t b2_session_launches(const b2_session *s);
 
+/* Host<->device traffic of a session so far: bytes[0] = H2D, bytes[1] = D2H.                 */
+int b2_session_traffic(const b2_session *s, uint64_t bytes[2]);
+/* Same, for the session owned by a decoder context (0 when the context is parse-only);
+ * counts[2] = kernel launches.                                                              */
+int b2_context_stats(void *ctx, uint64_t counts[3]);
+
+/* ------------------------------------------------------------------------------------ */
+/* Kernel replay: `lanes` independent streams (one frame pool each) whose pictures are    */
+/* uploaded once and stay resident in HBM; one run reconstructs picture #t of every lane   */
+/* in a single batched launch per kernel, for t = 0 .. steps-1.  This is the throughput    */
+/* path (bench.py `value`, roofline): no host work and no PCIe traffic inside a run.       */
+/* ------------------------------------------------------------------------------------ */
+typedef struct b2_replay b2_replay;
+
+typedef struct {
+	uint64_t pictures;        /* pictures reconstructed per run                                  */
+	uint64_t launches;        /* kernel launches per run                                         */
+	/* algorithmic bytes per run, split by kernel: [0] prediction+residual of   */
+	/* inter MBs (MPEG-2: the whole fused kernel), [1] intra wavefront, [2] deblock wavefront   */
+	uint64_t alg_bytes[3];
+	/* device time of the last timed run per kernel, milliseconds (CUDA events on the replay   */
+	/* stream), and of the whole run                                                           */
+	float kernel_ms[3];
+	float total_ms;
+} b2_replay_stats;
+
+int b2_replay_create(int cuda_device, int codec, int width, int height, int lanes, int pool_frames, b2_replay **out);
+void b2_replay_destroy(b2_replay *r);
+/* Append a picture to a lane's sequence (SoA copied to the device now, untimed).            */
+int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture *pic);
+int b2_replay_add_mpeg2(b2_replay *r, int lane, const b2_m2_picture *pic);
+/* Enqueue one full run on the replay stream; with timed != 0 per-kernel events are recorded. */
+int b2_replay_run(b2_replay *r, int timed);
+int b2_replay_sync(b2_replay *r);
+/* Record a CUDA event on the replay stream (which = 0 begin, 1 end) / read the elapsed device
+ * time between the two after a sync: brackets any number of runs for whole-job timing.       */
+int b2_replay_mark(b2_replay *r, int which);
+int b2_replay_elapsed_ms(b2_replay *r, float *ms);
+int b2_replay_get_stats(b2_replay *r, b2_replay_stats *out);
+int b2_replay_download(b2_replay *r, int lane, int idx, uint8_t *luma, uint8_t *chroma);
+
 #ifdef __cplusplus
 }
 #endif

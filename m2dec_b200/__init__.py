@@ -9,5 +9,6 @@ There is no CPU reconstruction in here: if the library is missing, importing fai
 """
 from ._native import lib, LIB_PATH, FrameT, InfoT, FuncTable, M2Picture, M2MB  # noqa: F401
 from .decoder import M2Decoder, decode_file, frame_md5, crop_frame  # noqa: F401
+from .replay import Replay  # noqa: F401
 
 __all__ = ["lib", "LIB_PATH", "M2Decoder", "decode_file", "frame_md5", "crop_frame"]

@@ -69,3 +69,22 @@ lib.b2_context_set_device.argtypes = [C.c_void_p, C.c_int]
 lib.b2_context_release.argtypes = [C.c_void_p]
 lib.b2_device_count.restype = C.c_int
 lib.b2_last_error.restype = C.c_char_p
+
+
+class ReplayStats(C.Structure):     # b2_replay_stats
+    _fields_ = [("pictures", C.c_uint64), ("launches", C.c_uint64), ("alg_bytes", C.c_uint64 * 3),
+                ("kernel_ms", C.c_float * 3), ("total_ms", C.c_float)]
+
+
+lib.b2_replay_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+lib.b2_replay_destroy.argtypes = [C.c_void_p]
+lib.b2_replay_destroy.restype = None
+lib.b2_replay_add_h264.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.b2_replay_add_mpeg2.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.b2_replay_run.argtypes = [C.c_void_p, C.c_int]
+lib.b2_replay_sync.argtypes = [C.c_void_p]
+lib.b2_replay_get_stats.argtypes = [C.c_void_p, C.POINTER(ReplayStats)]
+lib.b2_replay_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.b2_context_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3)]
+lib.b2_replay_mark.argtypes = [C.c_void_p, C.c_int]
+lib.b2_replay_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]

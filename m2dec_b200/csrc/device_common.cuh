@@ -39,6 +39,8 @@ struct H4Job {
 	const int16_t *coefs;
 	int32_t dst, mb_w, mb_h, reserved;
 };
+// phase: 0 inter (MC + residual), 1 intra wavefront, 2 deblock wavefront
+int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint64_t *launches);
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
                 bool deblock, uint64_t *launches);
 

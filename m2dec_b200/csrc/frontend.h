@@ -41,6 +41,7 @@ public:
 	int fetch(int idx, uint8_t *luma, uint8_t *chroma);
 	void release();
 	bool device_off() const { return device_off_; }
+	const b2_session *session() const { return sess_; }
 	// true once a CUDA session could not be created: the decoder then refuses to go on
 	bool dead() const { return dead_; }
 private:

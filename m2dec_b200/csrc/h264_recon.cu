@@ -621,28 +621,32 @@ static inline int diag_count(int mb_w, int mb_h) { return mb_w + 2 * (mb_h - 1);
 // upper bound on MBs per diagonal
 static inline int diag_width(int mb_w, int mb_h) { int a = (mb_w + 1) / 2; return a < mb_h ? a : mb_h; }
 
-int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
-                bool deblock, uint64_t *launches) {
+int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint64_t *launches) {
 	if (n_jobs <= 0) return 0;
-	if (any_inter) {
+	const int nd = diag_count(mb_w, mb_h), per = diag_width(mb_w, mb_h);
+	const int items = per * n_jobs;
+	if (phase == 0) {
 		dim3 grid((mb_w + INTER_MBS - 1) / INTER_MBS, mb_h, n_jobs);
 		h264_inter_kernel<<<grid, INTER_TPM * INTER_MBS, 0, stream>>>(d_jobs);
 		if (launches) ++*launches;
-	}
-	const int nd = diag_count(mb_w, mb_h), per = diag_width(mb_w, mb_h);
-	if (any_intra) {
-		int items = per * n_jobs;
+	} else if (phase == 1) {
 		for (int d = 0; d < nd; ++d)
 			h264_intra_kernel<<<(items + INTRA_WARPS - 1) / INTRA_WARPS, 32 * INTRA_WARPS, 0, stream>>>(d_jobs, n_jobs, d, per);
 		if (launches) *launches += nd;
-	}
-	if (deblock) {
-		int items = per * n_jobs;
+	} else {
 		for (int d = 0; d < nd; ++d)
 			h264_deblock_kernel<<<(items + DBK_WARPS - 1) / DBK_WARPS, 32 * DBK_WARPS, 0, stream>>>(d_jobs, n_jobs, d, per);
 		if (launches) *launches += nd;
 	}
 	B2_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
+                bool deblock, uint64_t *launches) {
+	if (any_inter && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, launches) < 0) return -1;
+	if (any_intra && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, launches) < 0) return -1;
+	if (deblock && launch_h264_phase(stream, 2, d_jobs, n_jobs, mb_w, mb_h, launches) < 0) return -1;
 	return 0;
 }
 

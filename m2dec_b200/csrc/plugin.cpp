@@ -40,3 +40,14 @@ extern "C" int b2_context_release(void *ctx) {
 	b->magic = 0;
 	return 0;
 }
+
+extern "C" int b2_context_stats(void *ctx, uint64_t counts[3]) {
+	b2::Backend *be = b2::backend_of(ctx);
+	if (!be || !counts) return -1;
+	counts[0] = counts[1] = counts[2] = 0;
+	if (be->session()) {
+		b2_session_traffic(be->session(), counts);
+		counts[2] = b2_session_launches(be->session());
+	}
+	return 0;
+}

@@ -39,6 +39,7 @@ struct b2_session {
 	StageSlot slots[NSLOT];
 	int next_slot;
 	uint64_t launches;
+	uint64_t h2d_bytes, d2h_bytes;
 };
 
 extern "C" const char *b2_last_error(void) { return b2::g_err; }
@@ -147,6 +148,7 @@ extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_m2_mb) * p->n_mbs);
 	if (p->n_blocks) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_blocks * 128);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
+	s->h2d_bytes += total;
 	if (launch_mpeg2(s->stream, (const M2Job *)sl->dev, 1, p->mb_w, p->mb_h) < 0) return -1;
 	s->launches++;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
@@ -191,6 +193,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (p->n_mcs) memcpy(sl->host + off_mcs, p->mcs, sizeof(b2_h264_mc) * p->n_mcs);
 	if (p->n_coef_recs) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
+	s->h2d_bytes += total;
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs, p->n_intra > 0,
 	                p->deblock != 0, &s->launches) < 0) return -1;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
@@ -212,6 +215,7 @@ extern "C" int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_
 	const uint8_t *src = s->frames + s->frame_bytes * idx;
 	B2_CUDA_OK(cudaMemcpyAsync(luma, src, ls, cudaMemcpyDeviceToHost, s->stream));
 	B2_CUDA_OK(cudaMemcpyAsync(chroma, src + ls, ls / 2, cudaMemcpyDeviceToHost, s->stream));
+	s->d2h_bytes += ls + ls / 2;
 	B2_CUDA_OK(cudaStreamSynchronize(s->stream));
 	return 0;
 }
@@ -228,3 +232,10 @@ extern "C" int b2_session_upload(b2_session *s, int idx, const uint8_t *luma, co
 }
 
 extern "C" uint64_t b2_session_launches(const b2_session *s) { return s ? s->launches : 0; }
+
+extern "C" int b2_session_traffic(const b2_session *s, uint64_t bytes[2]) {
+	if (!s || !bytes) return -1;
+	bytes[0] = s->h2d_bytes;
+	bytes[1] = s->d2h_bytes;
+	return 0;
+}
