@@ -205,76 +205,213 @@ __device__ void chroma_quad(const uint8_t *__restrict__ ref, int W, int CH, int 
 	}
 }
 
-constexpr int INTER_TPM = 96;    // threads per MB: 64 luma words + 32 chroma words
-constexpr int INTER_MBS = 2;     // MBs per CTA
+// ---- inter kernel: one thread per 4x4 luma block (plus its 2x2 Cb / Cr samples) ---------------------
+// Each thread keeps the 9 x 12-byte reference window of its block packed in registers (three
+// aligned 32-bit loads per row + funnel shift), filters it, runs the block's own inverse transform
+// in registers and writes four luma words and two NV12 chroma words.  A half-warp is one macroblock;
+// the only exchange between threads is the chroma residual (8 blocks per MB) through shared memory.
+constexpr int INTER_THREADS = 128;                   // 8 macroblocks per CTA
+constexpr int INTER_MBS = INTER_THREADS / 16;
 
-__global__ void __launch_bounds__(INTER_TPM * INTER_MBS)
-h264_inter_kernel(const H4Job *__restrict__ jobs) {
-	__shared__ __align__(16) int16_t s_res[INTER_MBS][24][16];
-	__shared__ uint32_t s_has[INTER_MBS];
-	__shared__ b2_h264_mc s_mc[INTER_MBS][16];
-	__shared__ uint8_t s_map[INTER_MBS][16];
+// 12 bytes starting at (possibly unaligned) address p, as three little-endian words
+__device__ __forceinline__ void load12(const uint8_t *__restrict__ p, uint32_t out[3]) {
+	const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+	unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+	uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = sh ? __ldg(a + 3) : 0;
+	out[0] = __funnelshift_r(w0, w1, sh);
+	out[1] = __funnelshift_r(w1, w2, sh);
+	out[2] = __funnelshift_r(w2, w3, sh);
+}
+__device__ __forceinline__ int byte_of(const uint32_t w[3], int i) { return (w[i >> 2] >> ((i & 3) * 8)) & 255; }
 
-	const H4Job job = jobs[blockIdx.z];
-	const int lm = threadIdx.x / INTER_TPM, t = threadIdx.x % INTER_TPM;
-	const int mbx = blockIdx.x * INTER_MBS + lm, mby = blockIdx.y;
-	const bool live = mbx < job.mb_w;
-	b2_h264_mb m;
-	m.type = 255;
-	if (live) m = job.mbs[(size_t)mby * job.mb_w + mbx];
-	const bool inter = live && m.type == B2_H4_INTER;
-	if (t == 0) s_has[lm] = 0;
-	__syncthreads();
-	if (inter) {
-		if (t < 24) {
-			if (block_residual(job, m, t, s_res[lm][t])) atomicOr(&s_has[lm], 1u << t);
-		} else if (t >= 32 && t < 32 + m.mc_cnt) {
-			int r = t - 32;
-			b2_h264_mc mc = job.mcs[m.mc_idx + r];
-			s_mc[lm][r] = mc;
-			int x4 = mc.pos & 3, y4 = mc.pos >> 2, pw = mc.size & 15, ph = mc.size >> 4;
-			for (int y = y4; y < y4 + ph; ++y)
-				for (int x = x4; x < x4 + pw; ++x) s_map[lm][y * 4 + x] = (uint8_t)r;
+// window row: bytes for columns x-2 .. x+9 of reference row y (clamped to the picture)
+__device__ __forceinline__ void window_row(const uint8_t *__restrict__ ref, int W, int H, int x, int y, bool inside, uint32_t out[3]) {
+	int yy = min(max(y, 0), H - 1);
+	const uint8_t *row = ref + (size_t)yy * W;
+	if (inside) {
+		load12(row + x - 2, out);
+	} else {
+		out[0] = out[1] = out[2] = 0;
+#pragma unroll
+		for (int i = 0; i < 12; ++i) out[i >> 2] |= (uint32_t)__ldg(row + min(max(x - 2 + i, 0), W - 1)) << ((i & 3) * 8);
+	}
+}
+
+// 4x4 luma prediction at integer position (x, y) + quarter-pel fraction (fx, fy); out[4*r + c]
+__device__ void luma_block4x4(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int out[16]) {
+	// three aligned words per row are read, i.e. up to column x + 9 + 3
+	const bool inside = x >= 2 && x + 13 <= W && y >= 2 && y + 6 < H;
+	uint32_t pk[9][3];
+#pragma unroll
+	for (int r = 0; r < 9; ++r) {
+		bool need = fy ? true : (r >= 2 && r <= 5);
+		if (need) window_row(ref, W, H, x, y + r - 2, inside, pk[r]);
+		else pk[r][0] = pk[r][1] = pk[r][2] = 0;
+	}
+#define PX(r, c) byte_of(pk[(r) + 2], (c) + 2)                    /* sample at row y + r, column x + c */
+#define HB(r, c) tap6(PX(r, (c) - 2), PX(r, (c) - 1), PX(r, c), PX(r, (c) + 1), PX(r, (c) + 2), PX(r, (c) + 3))
+#define VH(r, c) tap6(PX((r) - 2, c), PX((r) - 1, c), PX(r, c), PX((r) + 1, c), PX((r) + 2, c), PX((r) + 3, c))
+	if (!fx && !fy) {
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+#pragma unroll
+			for (int c = 0; c < 4; ++c) out[4 * r + c] = PX(r, c);
+	} else if (!fy) {
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				int b = clip255((HB(r, c) + 16) >> 5);
+				out[4 * r + c] = fx == 2 ? b : ((fx == 1 ? PX(r, c) : PX(r, c + 1)) + b + 1) >> 1;
+			}
+	} else if (!fx) {
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				int h = clip255((VH(r, c) + 16) >> 5);
+				out[4 * r + c] = fy == 2 ? h : ((fy == 1 ? PX(r, c) : PX(r + 1, c)) + h + 1) >> 1;
+			}
+	} else {
+		// unrounded horizontal intermediates for rows -2..6, columns 0..3
+		int hb[9][4];
+#pragma unroll
+		for (int r = 0; r < 9; ++r)
+#pragma unroll
+			for (int c = 0; c < 4; ++c) hb[r][c] = HB(r - 2, c);
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				int v;
+				if (fx == 2 || fy == 2) {
+					int j = clip255((tap6(hb[r][c], hb[r + 1][c], hb[r + 2][c], hb[r + 3][c], hb[r + 4][c], hb[r + 5][c]) + 512) >> 10);
+					if (fx == 2 && fy == 2) v = j;
+					else if (fx == 2) v = (clip255((hb[r + 2 + (fy == 3)][c] + 16) >> 5) + j + 1) >> 1;
+					else v = (clip255((VH(r, c + (fx == 3)) + 16) >> 5) + j + 1) >> 1;
+				} else {
+					int bs = clip255((hb[r + 2 + (fy == 3)][c] + 16) >> 5);
+					int hm = clip255((VH(r, c + (fx == 3)) + 16) >> 5);
+					v = (bs + hm + 1) >> 1;
+				}
+				out[4 * r + c] = v;
+			}
+	}
+#undef PX
+#undef HB
+#undef VH
+}
+
+// 2x2 chroma samples of both components at chroma position (cx, cy): out[row][0..3] = Cb Cr Cb Cr
+__device__ void chroma_block2x2(const uint8_t *__restrict__ refc, int W, int CH, int cx, int cy, int mvx, int mvy, int out[2][4]) {
+	const int fx = mvx & 7, fy = mvy & 7, cw = W >> 1;
+	const int x0 = cx + (mvx >> 3), y0 = cy + (mvy >> 3);
+	const bool inside = x0 >= 0 && x0 + 3 < cw && y0 >= 0 && y0 + 2 < CH;     // +3: the pair of words read
+	int s[3][3][2];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		int yy = min(max(y0 + r, 0), CH - 1);
+		const uint8_t *row = refc + (size_t)yy * W;
+		if (inside) {
+			const uint8_t *p = row + x0 * 2;
+			const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+			unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+			uint32_t w0 = __ldg(a), w1 = __ldg(a + 1);
+			uint32_t lo = __funnelshift_r(w0, w1, sh), hi = w1 >> sh;
+			s[r][0][0] = lo & 255; s[r][0][1] = (lo >> 8) & 255; s[r][1][0] = (lo >> 16) & 255; s[r][1][1] = lo >> 24;
+			s[r][2][0] = hi & 255; s[r][2][1] = (hi >> 8) & 255;
+		} else {
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				int xx = min(max(x0 + c, 0), cw - 1) * 2;
+				s[r][c][0] = __ldg(row + xx);
+				s[r][c][1] = __ldg(row + xx + 1);
+			}
 		}
 	}
-	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < 2; ++r)
+#pragma unroll
+		for (int c = 0; c < 2; ++c)
+#pragma unroll
+			for (int k = 0; k < 2; ++k)
+				out[r][c * 2 + k] = ((8 - fx) * (8 - fy) * s[r][c][k] + fx * (8 - fy) * s[r][c + 1][k] +
+				                     (8 - fx) * fy * s[r + 1][c][k] + fx * fy * s[r + 1][c + 1][k] + 32) >> 6;
+}
+
+__global__ void __launch_bounds__(INTER_THREADS)
+h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
+	__shared__ __align__(16) int16_t s_cres[INTER_MBS][8][16];
+	const H4Job job = jobs[blockIdx.y];
+	const int slot = threadIdx.x >> 4, t = threadIdx.x & 15;
+	const int mb = blockIdx.x * INTER_MBS + slot;
+	const bool live = mb < n_mbs;
+	b2_h264_mb m;
+	m.type = 255;
+	m.nz = 0;
+	m.mc_cnt = 0;
+	if (live) m = job.mbs[mb];
+	const bool inter = live && m.type == B2_H4_INTER;
+	const int mbx = live ? mb % job.mb_w : 0, mby = live ? mb / job.mb_w : 0;
+	const int x4 = t & 3, y4 = t >> 2;
+
+	// chroma residual blocks: thread t < 8 of the half-warp owns block (comp = t >> 2, blk = t & 3)
+	bool c_has = false;
+	if (inter && t < 8 && (m.nz >> 17)) c_has = block_residual(job, m, 16 + t, s_cres[slot][t]);
+	const unsigned chroma_mask = __ballot_sync(0xffffffffu, c_has) >> ((threadIdx.x & 16) ? 16 : 0);
+	__syncwarp();
 	if (!inter) return;
 
+	// the motion record covering this 4x4 block
+	b2_h264_mc mc;
+	for (int i = 0; i < m.mc_cnt; ++i) {
+		int4 raw = __ldg(reinterpret_cast<const int4 *>(job.mcs + m.mc_idx + i));
+		mc = *reinterpret_cast<b2_h264_mc *>(&raw);
+		int px0 = mc.pos & 3, py0 = mc.pos >> 2;
+		if (x4 >= px0 && x4 < px0 + (mc.size & 15) && y4 >= py0 && y4 < py0 + (mc.size >> 4)) break;
+	}
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
 	const size_t luma_size = (size_t)W * H;
+	const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0];
 	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
 	uint8_t *dst_c = dst_y + luma_size;
-	int px[4];
-	if (t < 64) {
-		const int row = t >> 2, xq = t & 3;                 // luma word: row 0..15, 4-pixel column 0..3
-		const b2_h264_mc &mc = s_mc[lm][s_map[lm][(row >> 2) * 4 + xq]];
-		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0];
-		int mvx = mc.mv[0][0], mvy = mc.mv[0][1];
-		luma_quad(ref, W, H, mbx * 16 + xq * 4 + (mvx >> 2), mby * 16 + row + (mvy >> 2), mvx & 3, mvy & 3, px);
-		const int b = c_r2b[(row >> 2) * 4 + xq];
-		if ((s_has[lm] >> b) & 1) {
+	const int mvx = mc.mv[0][0], mvy = mc.mv[0][1];
+
+	int px[16];
+	luma_block4x4(ref, W, H, mbx * 16 + x4 * 4 + (mvx >> 2), mby * 16 + y4 * 4 + (mvy >> 2), mvx & 3, mvy & 3, px);
+	const int b = c_r2b[t];
+	if ((m.nz >> (1 + b)) & 1) {
+		int16_t res[16];
+		if (block_residual(job, m, b, res)) {
 #pragma unroll
-			for (int i = 0; i < 4; ++i) px[i] = clip255(px[i] + s_res[lm][b][(row & 3) * 4 + i]);
+			for (int i = 0; i < 16; ++i) px[i] = clip255(px[i] + res[i]);
 		}
-		uint32_t w = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
-		*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + row) * W + mbx * 16 + xq * 4) = w;
-	} else {
-		const int w_ = t - 64;
-		const int row = w_ >> 2, xq = w_ & 3;               // chroma word: row 0..7, bytes xq*4..xq*4+3
-		// chroma sample (cx, cy) belongs to luma 4x4 block (cx >> 1, cy >> 1)
-		const b2_h264_mc &mc = s_mc[lm][s_map[lm][(row >> 1) * 4 + xq]];
-		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0] + luma_size;
-		chroma_quad(ref, W, H >> 1, mbx * 16 + xq * 4, mby * 8 + row, mc.mv[0][0], mc.mv[0][1], px);
-		// bytes 0,2 -> Cb samples 2*xq, 2*xq+1; bytes 1,3 -> Cr
-		const int cb = 16 + (row >> 2) * 2 + (xq >> 1), cr = cb + 4;
+	}
 #pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			int blk = (i & 1) ? cr : cb;
-			int sx = ((xq & 1) * 2 + (i >> 1));
-			if ((s_has[lm] >> blk) & 1) px[i] = clip255(px[i] + s_res[lm][blk][(row & 3) * 4 + sx]);
+	for (int r = 0; r < 4; ++r) {
+		uint32_t w = (uint32_t)px[4 * r] | ((uint32_t)px[4 * r + 1] << 8) | ((uint32_t)px[4 * r + 2] << 16) | ((uint32_t)px[4 * r + 3] << 24);
+		*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + y4 * 4 + r) * W + mbx * 16 + x4 * 4) = w;
+	}
+
+	int cp[2][4];
+	chroma_block2x2(ref + luma_size, W, H >> 1, mbx * 8 + x4 * 2, mby * 8 + y4 * 2, mvx, mvy, cp);
+	// chroma 4x4 block of this thread's samples: (x4 >> 1, y4 >> 1); position inside: ((x4 & 1) * 2, (y4 & 1) * 2)
+	const int cblk = (y4 >> 1) * 2 + (x4 >> 1);
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		if ((chroma_mask >> (k * 4 + cblk)) & 1) {
+			const int16_t *res = s_cres[slot][k * 4 + cblk];
+#pragma unroll
+			for (int r = 0; r < 2; ++r)
+#pragma unroll
+				for (int c = 0; c < 2; ++c)
+					cp[r][c * 2 + k] = clip255(cp[r][c * 2 + k] + res[((y4 & 1) * 2 + r) * 4 + (x4 & 1) * 2 + c]);
 		}
-		uint32_t w = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
-		*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + row) * W + mbx * 16 + xq * 4) = w;
+	}
+#pragma unroll
+	for (int r = 0; r < 2; ++r) {
+		uint32_t w = (uint32_t)cp[r][0] | ((uint32_t)cp[r][1] << 8) | ((uint32_t)cp[r][2] << 16) | ((uint32_t)cp[r][3] << 24);
+		*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + y4 * 2 + r) * W + mbx * 16 + x4 * 4) = w;
 	}
 }
 
@@ -345,23 +482,10 @@ __device__ int pred4x4_sample(const IntraTile &tl, int bx, int by, int mode, int
 #undef L
 }
 
-constexpr int INTRA_WARPS = 4;
-
-__global__ void __launch_bounds__(32 * INTRA_WARPS)
-h264_intra_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_job) {
-	__shared__ IntraTile s_tile[INTRA_WARPS];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int item = blockIdx.x * INTRA_WARPS + warp;
-	if (item >= n_jobs * per_job) return;
-	const H4Job job = jobs[item / per_job];
-	// MBs of the diagonal: y from y_lo upwards, x = diag - 2y
-	const int y_lo = max(0, (diag - (job.mb_w - 1) + 1) >> 1);
-	const int mby = y_lo + item % per_job;
-	const int mbx = diag - 2 * mby;
-	if (mby >= job.mb_h || mbx < 0 || mbx >= job.mb_w) return;
-	const b2_h264_mb m = job.mbs[(size_t)mby * job.mb_w + mbx];
-	if (m.type == B2_H4_INTER) return;
-	IntraTile &tl = s_tile[warp];
+// Reconstruct one intra macroblock with one warp.  Pixels produced by other warps (rows above)
+// are read through L2 (__ldcg) and results are written through to L2 (__stcg): the wavefront
+// kernel orders warps with progress flags, and L1 is not coherent between SMs.
+__device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby, IntraTile &tl, int lane) {
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
 	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
 	uint8_t *fc = fy + (size_t)W * H;
@@ -372,11 +496,11 @@ h264_intra_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_
 		const uint8_t *src = reinterpret_cast<const uint8_t *>(job.coefs + (size_t)m.coef_idx * 16);
 		for (int i = lane; i < 64; i += 32) {          // 64 luma words
 			int row = i >> 2, xq = i & 3;
-			*reinterpret_cast<uint32_t *>(py + (size_t)row * W + xq * 4) = *reinterpret_cast<const uint32_t *>(src + row * 16 + xq * 4);
+			__stcg(reinterpret_cast<uint32_t *>(py + (size_t)row * W + xq * 4), *reinterpret_cast<const uint32_t *>(src + row * 16 + xq * 4));
 		}
 		for (int i = lane; i < 128; i += 32) {         // 128 chroma bytes
 			int row = i >> 4, xb = i & 15;
-			pc[(size_t)row * W + xb] = src[256 + (xb & 1) * 64 + row * 8 + (xb >> 1)];
+			__stcg(pc + (size_t)row * W + xb, src[256 + (xb & 1) * 64 + row * 8 + (xb >> 1)]);
 		}
 		return;
 	}
@@ -386,17 +510,17 @@ h264_intra_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_
 	if (lane < 21) {            // above row: x = -1 .. 19
 		int x = lane - 1;
 		bool ok = (a & 2) && !(x < 0 && mbx == 0) && !(x >= 16 && mbx == job.mb_w - 1);
-		tl.y[0][lane] = (ok && mby > 0) ? py[-(ptrdiff_t)W + x] : 128;
+		tl.y[0][lane] = (ok && mby > 0) ? __ldcg(py - (ptrdiff_t)W + x) : 128;
 	}
-	if (lane < 16) tl.y[1 + lane][0] = ((a & 1) && mbx > 0) ? py[(size_t)lane * W - 1] : 128;
+	if (lane < 16) tl.y[1 + lane][0] = ((a & 1) && mbx > 0) ? __ldcg(py + (size_t)lane * W - 1) : 128;
 	if (lane < 18) {            // chroma above: byte x = -2 .. 15
 		int xb = lane - 2;
 		bool ok = (a & 2) && mby > 0 && !(xb < 0 && mbx == 0);
-		tl.c[xb & 1][0][(xb + 2) >> 1] = ok ? pc[-(ptrdiff_t)W + xb] : 128;
+		tl.c[xb & 1][0][(xb + 2) >> 1] = ok ? __ldcg(pc - (ptrdiff_t)W + xb) : 128;
 	}
 	if (lane < 16) {            // chroma left: rows 0..7, two components
 		int row = lane >> 1, comp = lane & 1;
-		tl.c[comp][1 + row][0] = ((a & 1) && mbx > 0) ? pc[(size_t)row * W - 2 + comp] : 128;
+		tl.c[comp][1 + row][0] = ((a & 1) && mbx > 0) ? __ldcg(pc + (size_t)row * W - 2 + comp) : 128;
 	}
 	if (lane == 0) tl.has = 0;
 	__syncwarp();
@@ -482,7 +606,7 @@ h264_intra_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_
 			}
 			int blk = 16 + comp * 4 + (y >> 2) * 2 + (x >> 2);
 			if ((tl.has >> blk) & 1) v = clip255(v + tl.res[blk][(y & 3) * 4 + (x & 3)]);
-			pc[(size_t)y * W + 2 * x + comp] = (uint8_t)v;
+			__stcg(pc + (size_t)y * W + 2 * x + comp, (uint8_t)v);
 		}
 	}
 	__syncwarp();
@@ -490,7 +614,7 @@ h264_intra_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_
 		int row = i >> 2, xq = i & 3;
 		const uint8_t *s = &tl.y[1 + row][1 + xq * 4];
 		uint32_t w = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
-		*reinterpret_cast<uint32_t *>(py + (size_t)row * W + xq * 4) = w;
+		__stcg(reinterpret_cast<uint32_t *>(py + (size_t)row * W + xq * 4), w);
 	}
 }
 
@@ -542,28 +666,44 @@ __device__ void filter_line(uint8_t *px, ptrdiff_t st, int bs, int alpha, int be
 	px[0] = (uint8_t)clip255(q0 - delta);
 }
 
-constexpr int DBK_WARPS = 4;
+// Deblock one macroblock with one warp.  The MB, 4 columns to its left and 4 (luma) / 2 (chroma)
+// rows above it are staged in shared memory with L2 loads, filtered there (lanes 0..15: one luma
+// line each, lanes 16..31: one chroma line each), and written back through to L2.
+struct DbkTile {
+	uint8_t y[20][36];      // rows -4..15 at index r+4, columns -4..15 at index c+4; 36-byte pitch avoids bank conflicts
+	uint8_t c[10][36];      // chroma rows -2..7 at index r+2, byte columns -4..15 at index c+4
+};
 
-__global__ void __launch_bounds__(32 * DBK_WARPS)
-h264_deblock_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int per_job) {
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int item = blockIdx.x * DBK_WARPS + warp;
-	if (item >= n_jobs * per_job) return;
-	const H4Job job = jobs[item / per_job];
-	const int y_lo = max(0, (diag - (job.mb_w - 1) + 1) >> 1);
-	const int mby = y_lo + item % per_job;
-	const int mbx = diag - 2 * mby;
-	if (mby >= job.mb_h || mbx < 0 || mbx >= job.mb_w) return;
-	const b2_h264_dbk *dp = &job.dbk[(size_t)mby * job.mb_w + mbx];
+__device__ void deblock_mb(const H4Job &job, const b2_h264_dbk *dp, int mbx, int mby, DbkTile &tl, int lane) {
 	const b2_h264_dbk d = *dp;
-	if (d.flags & B2_DBK_OFF) return;
+	if ((d.flags & B2_DBK_OFF) || !(d.bs_v | d.bs_h)) return;
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
 	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
-	uint8_t *fc = fy + (size_t)W * H;
 	uint8_t *py = fy + (size_t)mby * 16 * W + mbx * 16;
-	uint8_t *pc = fc + (size_t)mby * 8 * W + mbx * 16;
+	uint8_t *pc = fy + (size_t)W * H + (size_t)mby * 8 * W + mbx * 16;
+	// ---- stage ----------------------------------------------------------------------------------
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		int i = lane + 32 * k;
+		if (i < 100) {
+			int r = i / 5 - 4, w = i % 5;
+			if ((r >= 0 || mby > 0) && (w > 0 || mbx > 0))
+				*reinterpret_cast<uint32_t *>(&tl.y[r + 4][w * 4]) = __ldcg(reinterpret_cast<const uint32_t *>(py + (ptrdiff_t)r * W + (w - 1) * 4));
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		int i = lane + 32 * k;
+		if (i < 50) {
+			int r = i / 5 - 2, w = i % 5;
+			if ((r >= 0 || mby > 0) && (w > 0 || mbx > 0))
+				*reinterpret_cast<uint32_t *>(&tl.c[r + 2][w * 4]) = __ldcg(reinterpret_cast<const uint32_t *>(pc + (ptrdiff_t)r * W + (w - 1) * 4));
+		}
+	}
+	__syncwarp();
+	// ---- filter ---------------------------------------------------------------------------------
 	const bool is_luma = lane < 16;
-	const int li = lane & 15;                 // line index: luma line 0..15, or chroma (line 0..7, comp)
+	const int li = lane & 15;
 #pragma unroll 1
 	for (int dir = 0; dir < 2; ++dir) {
 		const uint32_t bits = dir ? d.bs_h : d.bs_v;
@@ -579,23 +719,21 @@ h264_deblock_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int pe
 			const int eb = (bits >> (8 * e)) & 255;
 			if (!eb || (e == 0 && !edge_ok)) continue;
 			if (is_luma) {
-				int seg = li >> 2;
-				int bs = (eb >> (seg * 2)) & 3;
+				int bs = (eb >> ((li >> 2) * 2)) & 3;
 				if (bs) {
 					if (e == 0 && bs4) bs = 4;
 					int qp = e ? d.qp_y : (d.qp_y + nqy + 1) >> 1;
 					int ia = min(max(qp + d.alpha_off, 0), 51), ib = min(max(qp + d.beta_off, 0), 51);
 					int alpha = c_alpha[ia], beta = c_beta[ib];
 					if (alpha) {
-						uint8_t *p = dir ? py + (size_t)e * 4 * W + li : py + (size_t)li * W + e * 4;
-						filter_line(p, dir ? (ptrdiff_t)W : 1, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, true);
+						uint8_t *p = dir ? &tl.y[4 + e * 4][4 + li] : &tl.y[4 + li][4 + e * 4];
+						filter_line(p, dir ? 36 : 1, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, true);
 					}
 				}
 			} else if (!(e & 1)) {
-				// chroma: lines 0..7 per component.  dir 0: li = row * 2 + comp; dir 1: li = byte column
-				int line = dir ? li >> 1 : li >> 1, comp = li & 1;
-				int seg = line >> 1;
-				int bs = (eb >> (seg * 2)) & 3;
+				// chroma: dir 0: li = row * 2 + comp (8 rows x 2 components); dir 1: li = byte column
+				int line = li >> 1, comp = li & 1;
+				int bs = (eb >> ((line >> 1) * 2)) & 3;
 				if (bs) {
 					if (e == 0 && bs4) bs = 4;
 					int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr : nqb;
@@ -603,40 +741,163 @@ h264_deblock_kernel(const H4Job *__restrict__ jobs, int n_jobs, int diag, int pe
 					int ia = min(max(qp + d.alpha_off, 0), 51), ib = min(max(qp + d.beta_off, 0), 51);
 					int alpha = c_alpha[ia], beta = c_beta[ib];
 					if (alpha) {
-						uint8_t *p = dir ? pc + (size_t)(e / 2) * 4 * W + line * 2 + comp : pc + (size_t)line * W + (e / 2) * 8 + comp;
-						filter_line(p, dir ? (ptrdiff_t)W : 2, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, false);
+						uint8_t *p = dir ? &tl.c[2 + (e / 2) * 4][4 + li] : &tl.c[2 + line][4 + (e / 2) * 8 + comp];
+						filter_line(p, dir ? 36 : 2, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, false);
 					}
 				}
 			}
 			__syncwarp();
 		}
-		__syncwarp();
 	}
-	(void)H;
+	__syncwarp();
+	// ---- write back (rows -3..15 x columns -4..15; only bytes this MB may own or has ordered access to)
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		int i = lane + 32 * k;
+		if (i < 100) {
+			int r = i / 5 - 4, w = i % 5;
+			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (r >= -3 && w > 0 && mby > 0);
+			if (ok) __stcg(reinterpret_cast<uint32_t *>(py + (ptrdiff_t)r * W + (w - 1) * 4), *reinterpret_cast<const uint32_t *>(&tl.y[r + 4][w * 4]));
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		int i = lane + 32 * k;
+		if (i < 50) {
+			int r = i / 5 - 2, w = i % 5;
+			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (w > 0 && mby > 0);
+			if (ok) __stcg(reinterpret_cast<uint32_t *>(pc + (ptrdiff_t)r * W + (w - 1) * 4), *reinterpret_cast<const uint32_t *>(&tl.c[r + 2][w * 4]));
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent wavefront: a warp owns one MB row of one picture and walks it left to right, staying
+// two macroblocks behind the row above (left / top / top-right dependencies).  Rows are handed out
+// through a ticket counter in (row, job) order, so the warp a row waits for always holds an earlier
+// ticket and is already running: no deadlock whatever the CTA scheduling order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int *p) {
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int WAVE_WARPS = 8;
+
+template <int PHASE>   // 1 intra, 2 deblock
+__global__ void __launch_bounds__(32 * WAVE_WARPS)
+h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
+	__shared__ union { IntraTile intra; DbkTile dbk; } s_tile[WAVE_WARPS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int *ticket = sync_area;
+	int *progress = sync_area + 32;           // [n_jobs][mb_h]: macroblocks of the row that are final
+	const int total = n_jobs * mb_h;
+	for (;;) {
+		int t = 0;
+		if (lane == 0) t = atomicAdd(ticket, 1);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= total) return;
+		const int j = t % n_jobs, mby = t / n_jobs;
+		const H4Job job = jobs[j];
+		int *my = progress + (size_t)j * mb_h + mby;
+		const int *above = my - 1;
+		int seen = 0;                          // progress of the row above known so far
+		for (int x0 = 0; x0 < mb_w; x0 += 32) {
+			// which of the next 32 macroblocks need work in this phase
+			int mbx = x0 + lane;
+			bool need = false;
+			if (mbx < mb_w) {
+				if (PHASE == 1) need = job.mbs[(size_t)mby * mb_w + mbx].type != B2_H4_INTER;
+				else {
+					const b2_h264_dbk *d = &job.dbk[(size_t)mby * mb_w + mbx];
+					need = !(d->flags & B2_DBK_OFF) && (d->bs_v | d->bs_h);
+				}
+			}
+			unsigned todo = __ballot_sync(0xffffffffu, need);
+			int done_to = x0;                  // macroblocks < done_to are final
+			while (todo) {
+				int k = __ffs(todo) - 1;
+				todo &= todo - 1;
+				int x = x0 + k;
+				if (x > done_to) {             // publish the stretch that needed nothing
+					__syncwarp();
+					if (lane == 0) st_release(my, x);
+				}
+				if (mby > 0) {
+					int want = min(x + 2, mb_w);
+					if (seen < want) {
+						if (lane == 0) {
+							while ((seen = ld_acquire(above)) < want) __nanosleep(64);
+						}
+						seen = __shfl_sync(0xffffffffu, seen, 0);
+					}
+				}
+				if (PHASE == 1) {
+					const b2_h264_mb m = job.mbs[(size_t)mby * mb_w + x];
+					intra_mb(job, m, x, mby, s_tile[warp].intra, lane);
+				} else {
+					deblock_mb(job, &job.dbk[(size_t)mby * mb_w + x], x, mby, s_tile[warp].dbk, lane);
+				}
+				__threadfence();
+				__syncwarp();
+				done_to = x + 1;
+				if (lane == 0) st_release(my, done_to);
+			}
+			int end = min(x0 + 32, mb_w);
+			if (done_to < end) {
+				// the rest of the chunk needs no work here, but the row above must still have produced
+				// what *later phases of this row's neighbours* rely on?  No: progress only orders work of
+				// this phase, and a macroblock without work has nothing to wait for.
+				__syncwarp();
+				if (lane == 0) st_release(my, end);
+			}
+		}
+	}
 }
 
 }  // namespace
 
-static inline int diag_count(int mb_w, int mb_h) { return mb_w + 2 * (mb_h - 1); }
-// upper bound on MBs per diagonal
-static inline int diag_width(int mb_w, int mb_h) { int a = (mb_w + 1) / 2; return a < mb_h ? a : mb_h; }
+static int *g_sync_area[16] = {nullptr};      // per device: ticket + progress flags
+static size_t g_sync_cap[16] = {0};
+
+static int wave_sync_area(int n_jobs, int mb_h, int **out, size_t *bytes) {
+	int dev = 0;
+	B2_CUDA_OK(cudaGetDevice(&dev));
+	size_t need = (32 + (size_t)n_jobs * mb_h) * sizeof(int);
+	if (dev < 0 || dev >= 16) return -1;
+	if (g_sync_cap[dev] < need) {
+		if (g_sync_area[dev]) cudaFree(g_sync_area[dev]);
+		B2_CUDA_OK(cudaMalloc(&g_sync_area[dev], need * 2));
+		g_sync_cap[dev] = need * 2;
+	}
+	*out = g_sync_area[dev];
+	*bytes = need;
+	return 0;
+}
 
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint64_t *launches) {
 	if (n_jobs <= 0) return 0;
-	const int nd = diag_count(mb_w, mb_h), per = diag_width(mb_w, mb_h);
-	const int items = per * n_jobs;
 	if (phase == 0) {
-		dim3 grid((mb_w + INTER_MBS - 1) / INTER_MBS, mb_h, n_jobs);
-		h264_inter_kernel<<<grid, INTER_TPM * INTER_MBS, 0, stream>>>(d_jobs);
+		const int n_mbs = mb_w * mb_h;
+		dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
+		h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
 		if (launches) ++*launches;
-	} else if (phase == 1) {
-		for (int d = 0; d < nd; ++d)
-			h264_intra_kernel<<<(items + INTRA_WARPS - 1) / INTRA_WARPS, 32 * INTRA_WARPS, 0, stream>>>(d_jobs, n_jobs, d, per);
-		if (launches) *launches += nd;
 	} else {
-		for (int d = 0; d < nd; ++d)
-			h264_deblock_kernel<<<(items + DBK_WARPS - 1) / DBK_WARPS, 32 * DBK_WARPS, 0, stream>>>(d_jobs, n_jobs, d, per);
-		if (launches) *launches += nd;
+		int *area;
+		size_t bytes;
+		if (wave_sync_area(n_jobs, mb_h, &area, &bytes) < 0) return -1;
+		B2_CUDA_OK(cudaMemsetAsync(area, 0, bytes, stream));
+		int rows = n_jobs * mb_h;
+		int ctas = (rows + WAVE_WARPS - 1) / WAVE_WARPS;
+		int cap = 148 * 6;
+		if (ctas > cap) ctas = cap;
+		if (phase == 1) h264_wave_kernel<1><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+		else h264_wave_kernel<2><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+		if (launches) ++*launches;
 	}
 	B2_CUDA_OK(cudaGetLastError());
 	return 0;
