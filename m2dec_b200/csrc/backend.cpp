@@ -36,15 +36,19 @@ int Backend::submit(int codec, const void *picture) {
 	if (tap_) err = tap_(tap_arg_, codec, picture);
 	if (device_off_) return err;
 	if (!sess_) return -1;
-	if (codec == B2_CODEC_MPEG2) return b2_session_submit_mpeg2(sess_, (const b2_m2_picture *)picture);
-	if (codec == B2_CODEC_H264) return b2_session_submit_h264(sess_, (const b2_h264_picture *)picture);
-	return -1;
+	int r = -1;
+	if (codec == B2_CODEC_MPEG2) r = b2_session_submit_mpeg2(sess_, (const b2_m2_picture *)picture);
+	else if (codec == B2_CODEC_H264) r = b2_session_submit_h264(sess_, (const b2_h264_picture *)picture);
+	if (r < 0) fprintf(stderr, "m2dec_b200: submit failed: %s\n", b2_last_error());
+	return r;
 }
 
 int Backend::fetch(int idx, uint8_t *luma, uint8_t *chroma) {
 	if (device_off_) return 0;
 	if (!sess_) return -1;
-	return b2_session_download(sess_, idx, luma, chroma);
+	int r = b2_session_download(sess_, idx, luma, chroma);
+	if (r < 0) fprintf(stderr, "m2dec_b200: frame download failed: %s\n", b2_last_error());
+	return r;
 }
 
 }  // namespace b2

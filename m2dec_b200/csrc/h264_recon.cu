@@ -205,213 +205,355 @@ __device__ void chroma_quad(const uint8_t *__restrict__ ref, int W, int CH, int 
 	}
 }
 
-// ---- inter kernel: one thread per 4x4 luma block (plus its 2x2 Cb / Cr samples) ---------------------
-// Each thread keeps the 9 x 12-byte reference window of its block packed in registers (three
-// aligned 32-bit loads per row + funnel shift), filters it, runs the block's own inverse transform
-// in registers and writes four luma words and two NV12 chroma words.  A half-warp is one macroblock;
-// the only exchange between threads is the chroma residual (8 blocks per MB) through shared memory.
-constexpr int INTER_THREADS = 128;                   // 8 macroblocks per CTA
-constexpr int INTER_MBS = INTER_THREADS / 16;
-
-// 12 bytes starting at (possibly unaligned) address p, as three little-endian words
-__device__ __forceinline__ void load12(const uint8_t *__restrict__ p, uint32_t out[3]) {
-	const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-	unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-	uint32_t w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2), w3 = sh ? __ldg(a + 3) : 0;
-	out[0] = __funnelshift_r(w0, w1, sh);
-	out[1] = __funnelshift_r(w1, w2, sh);
-	out[2] = __funnelshift_r(w2, w3, sh);
-}
+// ---- inter kernel ----------------------------------------------------------------------------------
+// Work item = one 4x4 luma block of an inter macroblock plus its 2x2 Cb and Cr samples.  A CTA takes
+// 32 consecutive macroblocks (512 items), and
+//   A. classifies every item by the interpolation it needs (copy / horizontal / vertical /
+//      diagonal / centre column / centre row) and counting-sorts the items by class in shared
+//      memory, so that warps run one interpolation path instead of diverging over six;
+//   B. compacts the coded 4x4 blocks (luma + chroma) and runs their dequantisation + inverse
+//      transform, one block per thread, into shared memory;
+//   C. per item: reference window in packed registers (aligned 32-bit loads + funnel shift), the
+//      6-tap filter as dp4a dot products (horizontal) / packed 16-bit lanes (vertical), residual add,
+//      clip, four luma word stores; chroma eighth-pel bilinear in packed 16-bit lanes, two word stores.
+// Every output byte of an inter macroblock is written exactly once.
 __device__ __forceinline__ int byte_of(const uint32_t w[3], int i) { return (w[i >> 2] >> ((i & 3) * 8)) & 255; }
+constexpr int INTER_MBS = 32;
+constexpr int INTER_THREADS = INTER_MBS * 16;
+constexpr int N_CLASS = 6;
 
-// window row: bytes for columns x-2 .. x+9 of reference row y (clamped to the picture)
-__device__ __forceinline__ void window_row(const uint8_t *__restrict__ ref, int W, int H, int x, int y, bool inside, uint32_t out[3]) {
-	int yy = min(max(y, 0), H - 1);
-	const uint8_t *row = ref + (size_t)yy * W;
-	if (inside) {
-		load12(row + x - 2, out);
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+	int d;
+	asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+#define PACK4(a, b, c, d) ((uint32_t)((a) & 255) | ((uint32_t)((b) & 255) << 8) | ((uint32_t)((c) & 255) << 16) | ((uint32_t)((d) & 255) << 24))
+
+// (1,-5,20,20,-5,1) across window bytes c..c+5 for output columns c = 0..3 of a 12-byte window
+__device__ __forceinline__ void hfilter4(const uint32_t pk[3], int out[4]) {
+	out[0] = dp4a_us(pk[0], PACK4(1, -5, 20, 20), dp4a_us(pk[1], PACK4(-5, 1, 0, 0), 0));
+	out[1] = dp4a_us(pk[0], PACK4(0, 1, -5, 20), dp4a_us(pk[1], PACK4(20, -5, 1, 0), 0));
+	out[2] = dp4a_us(pk[0], PACK4(0, 0, 1, -5), dp4a_us(pk[1], PACK4(20, 20, -5, 1), 0));
+	out[3] = dp4a_us(pk[0], PACK4(0, 0, 0, 1), dp4a_us(pk[1], PACK4(-5, 20, 20, -5), dp4a_us(pk[2], PACK4(1, 0, 0, 0), 0)));
+}
+
+// n bytes (n <= 12) starting at column x of a reference row, as little-endian words; columns are
+// clamped to the picture (edge replication) on the slow path
+__device__ __forceinline__ void load_row(const uint8_t *__restrict__ row, int W, int x, bool fast, int nwords, uint32_t out[3]) {
+	if (fast) {
+		const uint8_t *p = row + x;
+		const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+		unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+		uint32_t w0 = __ldg(a), w1 = __ldg(a + 1);
+		out[0] = __funnelshift_r(w0, w1, sh);
+		if (nwords > 1) {
+			uint32_t w2 = __ldg(a + 2);
+			out[1] = __funnelshift_r(w1, w2, sh);
+			if (nwords > 2) out[2] = __funnelshift_r(w2, __ldg(a + 3), sh);
+		}
 	} else {
 		out[0] = out[1] = out[2] = 0;
-#pragma unroll
-		for (int i = 0; i < 12; ++i) out[i >> 2] |= (uint32_t)__ldg(row + min(max(x - 2 + i, 0), W - 1)) << ((i & 3) * 8);
+		for (int i = 0; i < nwords * 4; ++i) out[i >> 2] |= (uint32_t)__ldg(row + min(max(x + i, 0), W - 1)) << ((i & 3) * 8);
 	}
 }
 
-// 4x4 luma prediction at integer position (x, y) + quarter-pel fraction (fx, fy); out[4*r + c]
-__device__ void luma_block4x4(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int out[16]) {
-	// three aligned words per row are read, i.e. up to column x + 9 + 3
-	const bool inside = x >= 2 && x + 13 <= W && y >= 2 && y + 6 < H;
-	uint32_t pk[9][3];
-#pragma unroll
-	for (int r = 0; r < 9; ++r) {
-		bool need = fy ? true : (r >= 2 && r <= 5);
-		if (need) window_row(ref, W, H, x, y + r - 2, inside, pk[r]);
-		else pk[r][0] = pk[r][1] = pk[r][2] = 0;
-	}
-#define PX(r, c) byte_of(pk[(r) + 2], (c) + 2)                    /* sample at row y + r, column x + c */
-#define HB(r, c) tap6(PX(r, (c) - 2), PX(r, (c) - 1), PX(r, c), PX(r, (c) + 1), PX(r, (c) + 2), PX(r, (c) + 3))
-#define VH(r, c) tap6(PX((r) - 2, c), PX((r) - 1, c), PX(r, c), PX((r) + 1, c), PX((r) + 2, c), PX((r) + 3, c))
-	if (!fx && !fy) {
-#pragma unroll
-		for (int r = 0; r < 4; ++r)
-#pragma unroll
-			for (int c = 0; c < 4; ++c) out[4 * r + c] = PX(r, c);
-	} else if (!fy) {
-#pragma unroll
-		for (int r = 0; r < 4; ++r)
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				int b = clip255((HB(r, c) + 16) >> 5);
-				out[4 * r + c] = fx == 2 ? b : ((fx == 1 ? PX(r, c) : PX(r, c + 1)) + b + 1) >> 1;
-			}
-	} else if (!fx) {
-#pragma unroll
-		for (int r = 0; r < 4; ++r)
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				int h = clip255((VH(r, c) + 16) >> 5);
-				out[4 * r + c] = fy == 2 ? h : ((fy == 1 ? PX(r, c) : PX(r + 1, c)) + h + 1) >> 1;
-			}
-	} else {
-		// unrounded horizontal intermediates for rows -2..6, columns 0..3
-		int hb[9][4];
-#pragma unroll
-		for (int r = 0; r < 9; ++r)
-#pragma unroll
-			for (int c = 0; c < 4; ++c) hb[r][c] = HB(r - 2, c);
-#pragma unroll
-		for (int r = 0; r < 4; ++r)
-#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				int v;
-				if (fx == 2 || fy == 2) {
-					int j = clip255((tap6(hb[r][c], hb[r + 1][c], hb[r + 2][c], hb[r + 3][c], hb[r + 4][c], hb[r + 5][c]) + 512) >> 10);
-					if (fx == 2 && fy == 2) v = j;
-					else if (fx == 2) v = (clip255((hb[r + 2 + (fy == 3)][c] + 16) >> 5) + j + 1) >> 1;
-					else v = (clip255((VH(r, c + (fx == 3)) + 16) >> 5) + j + 1) >> 1;
-				} else {
-					int bs = clip255((hb[r + 2 + (fy == 3)][c] + 16) >> 5);
-					int hm = clip255((VH(r, c + (fx == 3)) + 16) >> 5);
-					v = (bs + hm + 1) >> 1;
-				}
-				out[4 * r + c] = v;
-			}
-	}
-#undef PX
-#undef HB
-#undef VH
-}
+__device__ __forceinline__ int avg2(int a, int b) { return (a + b + 1) >> 1; }
 
-// 2x2 chroma samples of both components at chroma position (cx, cy): out[row][0..3] = Cb Cr Cb Cr
-__device__ void chroma_block2x2(const uint8_t *__restrict__ refc, int W, int CH, int cx, int cy, int mvx, int mvy, int out[2][4]) {
-	const int fx = mvx & 7, fy = mvy & 7, cw = W >> 1;
-	const int x0 = cx + (mvx >> 3), y0 = cy + (mvy >> 3);
-	const bool inside = x0 >= 0 && x0 + 3 < cw && y0 >= 0 && y0 + 2 < CH;     // +3: the pair of words read
-	int s[3][3][2];
+// vertical 6-tap on two packed 16-bit lanes; result lanes carry a +2560 bias
+__device__ __forceinline__ uint32_t vtap_packed(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
+	return (a + f) + 20u * (c + d) + 0x0A000A00u - 5u * (b + e);
+}
+__device__ __forceinline__ int vfinish(uint32_t lane16) { return clip255(((int)lane16 - 2560 + 16) >> 5); }
+
+// vertical half-sample values h(r, c) = clip((tap6 + 16) >> 5) for rows 0..3, columns 0..3 of the words R[0..8]
+// (R[k] = four bytes of reference row y - 2 + k)
+__device__ __forceinline__ void vhalf4x4(const uint32_t R[9], int out[16]) {
+	uint32_t E[9], O[9];
 #pragma unroll
-	for (int r = 0; r < 3; ++r) {
-		int yy = min(max(y0 + r, 0), CH - 1);
-		const uint8_t *row = refc + (size_t)yy * W;
-		if (inside) {
-			const uint8_t *p = row + x0 * 2;
-			const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-			unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-			uint32_t w0 = __ldg(a), w1 = __ldg(a + 1);
-			uint32_t lo = __funnelshift_r(w0, w1, sh), hi = w1 >> sh;
-			s[r][0][0] = lo & 255; s[r][0][1] = (lo >> 8) & 255; s[r][1][0] = (lo >> 16) & 255; s[r][1][1] = lo >> 24;
-			s[r][2][0] = hi & 255; s[r][2][1] = (hi >> 8) & 255;
-		} else {
+	for (int k = 0; k < 9; ++k) { E[k] = R[k] & 0x00FF00FFu; O[k] = (R[k] >> 8) & 0x00FF00FFu; }
 #pragma unroll
-			for (int c = 0; c < 3; ++c) {
-				int xx = min(max(x0 + c, 0), cw - 1) * 2;
-				s[r][c][0] = __ldg(row + xx);
-				s[r][c][1] = __ldg(row + xx + 1);
-			}
-		}
+	for (int r = 0; r < 4; ++r) {
+		uint32_t te = vtap_packed(E[r], E[r + 1], E[r + 2], E[r + 3], E[r + 4], E[r + 5]);
+		uint32_t to = vtap_packed(O[r], O[r + 1], O[r + 2], O[r + 3], O[r + 4], O[r + 5]);
+		out[4 * r + 0] = vfinish(te & 0xFFFFu);
+		out[4 * r + 1] = vfinish(to & 0xFFFFu);
+		out[4 * r + 2] = vfinish(te >> 16);
+		out[4 * r + 3] = vfinish(to >> 16);
 	}
-#pragma unroll
-	for (int r = 0; r < 2; ++r)
-#pragma unroll
-		for (int c = 0; c < 2; ++c)
-#pragma unroll
-			for (int k = 0; k < 2; ++k)
-				out[r][c * 2 + k] = ((8 - fx) * (8 - fy) * s[r][c][k] + fx * (8 - fy) * s[r][c + 1][k] +
-				                     (8 - fx) * fy * s[r + 1][c][k] + fx * fy * s[r + 1][c + 1][k] + 32) >> 6;
 }
 
 __global__ void __launch_bounds__(INTER_THREADS)
 h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
-	__shared__ __align__(16) int16_t s_cres[INTER_MBS][8][16];
+	__shared__ __align__(16) int16_t s_res[INTER_MBS][24][16];
+	__shared__ uint32_t s_has[INTER_MBS];
+	__shared__ uint16_t s_items[INTER_THREADS];
+	__shared__ uint16_t s_coded[INTER_MBS * 24];
+	__shared__ uint8_t s_mcsel[INTER_THREADS];
+	__shared__ int s_wcnt[N_CLASS][INTER_THREADS / 32];
+	__shared__ int s_cbase[N_CLASS + 1];
+	__shared__ int s_ccnt[2 * (INTER_THREADS / 32) + 1];
+
 	const H4Job job = jobs[blockIdx.y];
-	const int slot = threadIdx.x >> 4, t = threadIdx.x & 15;
-	const int mb = blockIdx.x * INTER_MBS + slot;
-	const bool live = mb < n_mbs;
-	b2_h264_mb m;
-	m.type = 255;
-	m.nz = 0;
-	m.mc_cnt = 0;
-	if (live) m = job.mbs[mb];
-	const bool inter = live && m.type == B2_H4_INTER;
-	const int mbx = live ? mb % job.mb_w : 0, mby = live ? mb / job.mb_w : 0;
-	const int x4 = t & 3, y4 = t >> 2;
-
-	// chroma residual blocks: thread t < 8 of the half-warp owns block (comp = t >> 2, blk = t & 3)
-	bool c_has = false;
-	if (inter && t < 8 && (m.nz >> 17)) c_has = block_residual(job, m, 16 + t, s_cres[slot][t]);
-	const unsigned chroma_mask = __ballot_sync(0xffffffffu, c_has) >> ((threadIdx.x & 16) ? 16 : 0);
-	__syncwarp();
-	if (!inter) return;
-
-	// the motion record covering this 4x4 block
-	b2_h264_mc mc;
-	for (int i = 0; i < m.mc_cnt; ++i) {
-		int4 raw = __ldg(reinterpret_cast<const int4 *>(job.mcs + m.mc_idx + i));
-		mc = *reinterpret_cast<b2_h264_mc *>(&raw);
-		int px0 = mc.pos & 3, py0 = mc.pos >> 2;
-		if (x4 >= px0 && x4 < px0 + (mc.size & 15) && y4 >= py0 && y4 < py0 + (mc.size >> 4)) break;
-	}
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int mb0 = blockIdx.x * INTER_MBS;
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
 	const size_t luma_size = (size_t)W * H;
+
+	// ---- A. classify + counting sort -------------------------------------------------------------
+	int cls = 7;
+	{
+		const int mb = mb0 + (tid >> 4);
+		if (tid < INTER_MBS) s_has[tid] = 0;
+		if (mb < n_mbs) {
+			const b2_h264_mb *mp = job.mbs + mb;
+			if (mp->type == B2_H4_INTER) {
+				const int x4 = tid & 3, y4 = (tid >> 2) & 3;
+				const int cnt = mp->mc_cnt;
+				const b2_h264_mc *rec = job.mcs + mp->mc_idx;
+				int sel = 0, mvx = 0, mvy = 0;
+				for (int i = 0; i < cnt; ++i) {
+					int4 raw = __ldg(reinterpret_cast<const int4 *>(rec + i));
+					const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);
+					int px0 = mc.pos & 3, py0 = mc.pos >> 2;
+					if (x4 >= px0 && x4 < px0 + (mc.size & 15) && y4 >= py0 && y4 < py0 + (mc.size >> 4)) {
+						sel = i; mvx = mc.mv[0][0]; mvy = mc.mv[0][1];
+						break;
+					}
+				}
+				s_mcsel[tid] = (uint8_t)sel;
+				const int fx = mvx & 3, fy = mvy & 3;
+				if (!fx && !fy) cls = 0;
+				else if (!fy) cls = 1;
+				else if (!fx) cls = 2;
+				else if (fx == 2) cls = 4;          // b / s with j, or j alone
+				else if (fy == 2) cls = 5;          // h / m with j
+				else cls = 3;                       // b / s with h / m
+			}
+		}
+	}
+	int rank = 0;
+#pragma unroll
+	for (int c = 0; c < N_CLASS; ++c) {
+		unsigned mask = __ballot_sync(0xffffffffu, cls == c);
+		if (cls == c) rank = __popc(mask & ((1u << lane) - 1));
+		if (lane == 0) s_wcnt[c][warp] = __popc(mask);
+	}
+	// ---- B. list of coded 4x4 blocks (luma 0..15, Cb 16..19, Cr 20..23) --------------------------
+	int coded_rank[2];
+	bool coded[2];
+#pragma unroll
+	for (int rnd = 0; rnd < 2; ++rnd) {
+		int j = tid + rnd * INTER_THREADS;
+		bool c = false;
+		if (j < INTER_MBS * 24) {
+			int mb = mb0 + j / 24, bk = j % 24;
+			if (mb < n_mbs) {
+				const b2_h264_mb *mp = job.mbs + mb;
+				if (mp->type == B2_H4_INTER) {
+					uint32_t nz = mp->nz;
+					c = bk < 16 ? (nz >> (1 + bk)) & 1 : (((nz >> (2 + bk)) & 1) || ((nz >> 17) & 1));
+				}
+			}
+		}
+		unsigned mask = __ballot_sync(0xffffffffu, c);
+		coded[rnd] = c;
+		coded_rank[rnd] = __popc(mask & ((1u << lane) - 1));
+		if (lane == 0) s_ccnt[warp + rnd * (INTER_THREADS / 32)] = __popc(mask);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		int acc = 0;
+		for (int c = 0; c < N_CLASS; ++c) {
+			s_cbase[c] = acc;
+			for (int w = 0; w < INTER_THREADS / 32; ++w) { int n = s_wcnt[c][w]; s_wcnt[c][w] = acc; acc += n; }
+		}
+		s_cbase[N_CLASS] = acc;
+	} else if (tid == 32) {
+		int acc = 0;
+		const int nw = 2 * (INTER_THREADS / 32);
+		for (int w = 0; w < nw; ++w) { int n = s_ccnt[w]; s_ccnt[w] = acc; acc += n; }
+		s_ccnt[nw] = acc;
+	}
+	__syncthreads();
+	if (cls < N_CLASS) s_items[s_wcnt[cls][warp] + rank] = (uint16_t)tid;
+#pragma unroll
+	for (int rnd = 0; rnd < 2; ++rnd)
+		if (coded[rnd]) s_coded[s_ccnt[warp + rnd * (INTER_THREADS / 32)] + coded_rank[rnd]] = (uint16_t)(tid + rnd * INTER_THREADS);
+	__syncthreads();
+	// ---- residuals of the coded blocks -------------------------------------------------------------
+	const int n_coded = s_ccnt[2 * (INTER_THREADS / 32)];
+	for (int k = tid; k < n_coded; k += INTER_THREADS) {
+		int j = s_coded[k];
+		int slot = j / 24, bk = j % 24;
+		const b2_h264_mb m = job.mbs[mb0 + slot];
+		if (block_residual(job, m, bk, s_res[slot][bk])) atomicOr(&s_has[slot], 1u << bk);
+	}
+	__syncthreads();
+
+	// ---- C. one item per thread, in class order ------------------------------------------------------
+	const int n_items = s_cbase[N_CLASS];
+	if (tid >= n_items) return;
+	const int item = s_items[tid];
+	int c = 0;
+#pragma unroll
+	for (int k = 1; k < N_CLASS; ++k) c += tid >= s_cbase[k];
+	const int slot = item >> 4, x4 = item & 3, y4 = (item >> 2) & 3;
+	const int mb = mb0 + slot;
+	const int mbx = mb % job.mb_w, mby = mb / job.mb_w;
+	const b2_h264_mb *mp = job.mbs + mb;
+	int4 raw = __ldg(reinterpret_cast<const int4 *>(job.mcs + mp->mc_idx + s_mcsel[item]));
+	const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);
 	const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0];
 	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
 	uint8_t *dst_c = dst_y + luma_size;
 	const int mvx = mc.mv[0][0], mvy = mc.mv[0][1];
+	const int fx = mvx & 3, fy = mvy & 3;
+	const int x = mbx * 16 + x4 * 4 + (mvx >> 2), y = mby * 16 + y4 * 4 + (mvy >> 2);
+	const bool fast = x >= 3 && x + 14 <= W;      // every aligned word touched lies inside the row
+	const uint32_t has = s_has[slot];
 
 	int px[16];
-	luma_block4x4(ref, W, H, mbx * 16 + x4 * 4 + (mvx >> 2), mby * 16 + y4 * 4 + (mvy >> 2), mvx & 3, mvy & 3, px);
-	const int b = c_r2b[t];
-	if ((m.nz >> (1 + b)) & 1) {
-		int16_t res[16];
-		if (block_residual(job, m, b, res)) {
+	if (c == 0) {
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			uint32_t w[3];
+			load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x, fast, 1, w);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) px[4 * r + i] = (w[0] >> (8 * i)) & 255;
+		}
+	} else if (c == 1) {
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			uint32_t w[3];
+			int hb[4];
+			load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x - 2, fast, 3, w);
+			hfilter4(w, hb);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				int b = clip255((hb[i] + 16) >> 5);
+				int g = fx == 1 ? byte_of(w, i + 2) : byte_of(w, i + 3);
+				px[4 * r + i] = fx == 2 ? b : avg2(g, b);
+			}
+		}
+	} else if (c == 2) {
+		uint32_t R[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) {
+			uint32_t w[3];
+			load_row(ref + (size_t)min(max(y + k - 2, 0), H - 1) * W, W, x, fast, 1, w);
+			R[k] = w[0];
+		}
+		vhalf4x4(R, px);
+		if (fy != 2) {
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				uint32_t g = fy == 1 ? R[r + 2] : R[r + 3];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2((g >> (8 * i)) & 255, px[4 * r + i]);
+			}
+		}
+	} else if (c == 3) {
+		// quarter positions e, g, p, r: average of a horizontal (b / s) and a vertical (h / m) half sample
+		uint32_t R[9];
+		const int xo = fx == 3 ? 1 : 0, yo = fy == 3 ? 1 : 0;
+#pragma unroll
+		for (int k = 0; k < 9; ++k) {
+			uint32_t w[3];
+			load_row(ref + (size_t)min(max(y + k - 2, 0), H - 1) * W, W, x + xo, fast, 1, w);
+			R[k] = w[0];
+		}
+		vhalf4x4(R, px);
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			uint32_t w[3];
+			int hb[4];
+			load_row(ref + (size_t)min(max(y + r + yo, 0), H - 1) * W, W, x - 2, fast, 3, w);
+			hfilter4(w, hb);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2(clip255((hb[i] + 16) >> 5), px[4 * r + i]);
+		}
+	} else {
+		// centre column (fx == 2) or centre row (fy == 2): j from the unrounded horizontal intermediates
+		int hb[9][4];
+		uint32_t G[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) {
+			uint32_t w[3];
+			load_row(ref + (size_t)min(max(y + k - 2, 0), H - 1) * W, W, x - 2, fast, 3, w);
+			hfilter4(w, hb[k]);
+			// bytes of columns 0..3 (fx == 1) or 1..4 (fx == 3) for the vertical half samples of class 5
+			G[k] = fx == 3 ? __funnelshift_r(w[0], w[1], 24) : __funnelshift_r(w[0], w[1], 16);
+		}
+		int vh[16];
+		if (c == 5) vhalf4x4(G, vh);
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				int j1 = (hb[r][i] + hb[r + 5][i]) - 5 * (hb[r + 1][i] + hb[r + 4][i]) + 20 * (hb[r + 2][i] + hb[r + 3][i]);
+				int j = clip255((j1 + 512) >> 10);
+				int v;
+				if (c == 5) v = avg2(vh[4 * r + i], j);
+				else if (fy == 2) v = j;
+				else v = avg2(clip255(((fy == 1 ? hb[r + 2][i] : hb[r + 3][i]) + 16) >> 5), j);
+				px[4 * r + i] = v;
+			}
+	}
+	{
+		const int b = c_r2b[y4 * 4 + x4];
+		if ((has >> b) & 1) {
+			const int16_t *res = s_res[slot][b];
 #pragma unroll
 			for (int i = 0; i < 16; ++i) px[i] = clip255(px[i] + res[i]);
 		}
-	}
 #pragma unroll
-	for (int r = 0; r < 4; ++r) {
-		uint32_t w = (uint32_t)px[4 * r] | ((uint32_t)px[4 * r + 1] << 8) | ((uint32_t)px[4 * r + 2] << 16) | ((uint32_t)px[4 * r + 3] << 24);
-		*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + y4 * 4 + r) * W + mbx * 16 + x4 * 4) = w;
-	}
-
-	int cp[2][4];
-	chroma_block2x2(ref + luma_size, W, H >> 1, mbx * 8 + x4 * 2, mby * 8 + y4 * 2, mvx, mvy, cp);
-	// chroma 4x4 block of this thread's samples: (x4 >> 1, y4 >> 1); position inside: ((x4 & 1) * 2, (y4 & 1) * 2)
-	const int cblk = (y4 >> 1) * 2 + (x4 >> 1);
-#pragma unroll
-	for (int k = 0; k < 2; ++k) {
-		if ((chroma_mask >> (k * 4 + cblk)) & 1) {
-			const int16_t *res = s_cres[slot][k * 4 + cblk];
-#pragma unroll
-			for (int r = 0; r < 2; ++r)
-#pragma unroll
-				for (int c = 0; c < 2; ++c)
-					cp[r][c * 2 + k] = clip255(cp[r][c * 2 + k] + res[((y4 & 1) * 2 + r) * 4 + (x4 & 1) * 2 + c]);
+		for (int r = 0; r < 4; ++r) {
+			uint32_t w = (uint32_t)px[4 * r] | ((uint32_t)px[4 * r + 1] << 8) | ((uint32_t)px[4 * r + 2] << 16) | ((uint32_t)px[4 * r + 3] << 24);
+			*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + y4 * 4 + r) * W + mbx * 16 + x4 * 4) = w;
 		}
 	}
+
+	// ---- chroma: 2x2 samples of Cb and Cr, eighth-pel bilinear in packed 16-bit lanes -----------------
+	{
+		const uint8_t *refc = ref + luma_size;
+		const int CH = H >> 1, cw = W >> 1;
+		const int cfx = mvx & 7, cfy = mvy & 7;
+		const int cx = mbx * 8 + x4 * 2 + (mvx >> 3), cy = mby * 8 + y4 * 2 + (mvy >> 3);
+		const bool cfast = cx >= 2 && cx + 6 <= cw;
+		uint32_t hrow[3][2];        // per row: horizontally interpolated (Cb0, Cb1) and (Cr0, Cr1), 16-bit lanes, scale 8
 #pragma unroll
-	for (int r = 0; r < 2; ++r) {
-		uint32_t w = (uint32_t)cp[r][0] | ((uint32_t)cp[r][1] << 8) | ((uint32_t)cp[r][2] << 16) | ((uint32_t)cp[r][3] << 24);
-		*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + y4 * 2 + r) * W + mbx * 16 + x4 * 4) = w;
+		for (int r = 0; r < 3; ++r) {
+			const uint8_t *row = refc + (size_t)min(max(cy + r, 0), CH - 1) * W;
+			uint32_t a, bq;     // a = samples 0,1 (Cb0 Cr0 Cb1 Cr1), bq = samples 1,2
+			if (cfast) {
+				uint32_t w[3];
+				load_row(row, W, cx * 2, true, 2, w);
+				a = w[0];
+				bq = __funnelshift_r(w[0], w[1], 16);
+			} else {
+				int x0 = min(max(cx, 0), cw - 1) * 2, x1 = min(max(cx + 1, 0), cw - 1) * 2, x2 = min(max(cx + 2, 0), cw - 1) * 2;
+				uint32_t s0 = __ldg(row + x0) | (__ldg(row + x0 + 1) << 8), s1 = __ldg(row + x1) | (__ldg(row + x1 + 1) << 8),
+				         s2 = __ldg(row + x2) | (__ldg(row + x2 + 1) << 8);
+				a = s0 | (s1 << 16);
+				bq = s1 | (s2 << 16);
+			}
+			uint32_t a_cb = a & 0x00FF00FFu, a_cr = (a >> 8) & 0x00FF00FFu;
+			uint32_t b_cb = bq & 0x00FF00FFu, b_cr = (bq >> 8) & 0x00FF00FFu;
+			hrow[r][0] = (uint32_t)(8 - cfx) * a_cb + (uint32_t)cfx * b_cb;
+			hrow[r][1] = (uint32_t)(8 - cfx) * a_cr + (uint32_t)cfx * b_cr;
+		}
+		const int cblk = (y4 >> 1) * 2 + (x4 >> 1);
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			uint32_t vcb = ((uint32_t)(8 - cfy) * hrow[r][0] + (uint32_t)cfy * hrow[r + 1][0] + 0x00200020u) >> 6;
+			uint32_t vcr = ((uint32_t)(8 - cfy) * hrow[r][1] + (uint32_t)cfy * hrow[r + 1][1] + 0x00200020u) >> 6;
+			int cb0 = vcb & 0x3FF, cb1 = (vcb >> 16) & 0x3FF, cr0 = vcr & 0x3FF, cr1 = (vcr >> 16) & 0x3FF;
+			const int ro = ((y4 & 1) * 2 + r) * 4 + (x4 & 1) * 2;
+			if ((has >> (16 + cblk)) & 1) { cb0 = clip255(cb0 + s_res[slot][16 + cblk][ro]); cb1 = clip255(cb1 + s_res[slot][16 + cblk][ro + 1]); }
+			if ((has >> (20 + cblk)) & 1) { cr0 = clip255(cr0 + s_res[slot][20 + cblk][ro]); cr1 = clip255(cr1 + s_res[slot][20 + cblk][ro + 1]); }
+			uint32_t w = (uint32_t)cb0 | ((uint32_t)cr0 << 8) | ((uint32_t)cb1 << 16) | ((uint32_t)cr1 << 24);
+			*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + y4 * 2 + r) * W + mbx * 16 + x4 * 4) = w;
+		}
 	}
 }
 
