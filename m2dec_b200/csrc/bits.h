@@ -9,6 +9,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 #include <vector>
 #include "m2d_plugin.h"
 
@@ -102,6 +103,15 @@ public:
 	}
 private:
 	inline void fill() {
+		if (n_ <= 32 && p_ + 4 <= end_) {
+			// common case: four bytes at once
+			uint32_t v;
+			memcpy(&v, p_, 4);
+			cache_ |= (uint64_t)__builtin_bswap32(v) << (32 - n_);
+			p_ += 4;
+			n_ += 32;
+			return;
+		}
 		while (n_ <= 56) {
 			uint64_t b = 0;
 			if (p_ < end_) b = *p_++; else fake_++;   // past the unit: feed zeros, count them

@@ -625,7 +625,7 @@ private:
 		mbs_.assign(n, b2_h264_mb());
 		dbk_.assign(n, b2_h264_dbk());
 		mcs_.clear();
-		coefs_.clear();
+		coef_used_ = 0;
 		n_intra_ = 0;
 		any_deblock_ = false;
 		slice_num_ = -1;
@@ -644,7 +644,7 @@ private:
 		p.deblock = any_deblock_;
 		p.n_mbs = (uint32_t)mbs_.size();
 		p.n_mcs = (uint32_t)mcs_.size();
-		p.n_coef_recs = (uint32_t)(coefs_.size() / 16);
+		p.n_coef_recs = (uint32_t)(coef_used_ / 16);
 		p.n_intra = n_intra_;
 		p.mbs = mbs_.data();
 		p.dbk = dbk_.data();
@@ -757,7 +757,7 @@ private:
 		ctx_.open_mb(mbx, mby, slice_num_);
 		b2_h264_mb &m = mbs_[(size_t)mby * mb_w_ + mbx];
 		memset(&m, 0, sizeof(m));
-		m.coef_idx = (uint32_t)(coefs_.size() / 16);
+		m.coef_idx = (uint32_t)(coef_used_ / 16);
 		m.mc_idx = (uint32_t)mcs_.size();
 	}
 
@@ -807,11 +807,16 @@ private:
 		m.qp_cr = (uint8_t)chroma_qp(qp_, pps.chroma_qp_offset[1]);
 	}
 
+	// coefficient pool: grows geometrically, records are handed out zeroed
 	int16_t *new_record() {
-		size_t n = coefs_.size();
-		coefs_.resize(n + 16, 0);
-		return &coefs_[n];
+		if (coef_used_ + 16 > coefs_.size()) coefs_.resize(coefs_.size() * 2 + 65536);
+		int16_t *r = &coefs_[coef_used_];
+		coef_used_ += 16;
+		memset(r, 0, 32);
+		return r;
 	}
+	// give the last record back (nothing was coded in it)
+	inline void drop_record() { coef_used_ -= 16; }
 
 	// residual_block_cavlc (7.3.5.3.2 / 9.2): returns total_coeff; levels go to out[scan[...]]
 	int residual_block(int nc, int max_coeff, int16_t *out, const uint8_t *scan, int scan_ofs) {
@@ -876,14 +881,11 @@ private:
 			int x4 = blk_x[k], y4 = blk_y[k];
 			if (!(cbp & (1 << (k >> 2)))) { nnz[y4 * 4 + x4] = 0; continue; }
 			int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
-			int16_t tmp[16];
-			memset(tmp, 0, sizeof(tmp));
-			int total = i16 ? residual_block(nc, 15, tmp, zigzag4x4, 1) : residual_block(nc, 16, tmp, zigzag4x4, 0);
+			int16_t *rec = new_record();
+			int total = i16 ? residual_block(nc, 15, rec, zigzag4x4, 1) : residual_block(nc, 16, rec, zigzag4x4, 0);
 			nnz[y4 * 4 + x4] = (uint8_t)total;
-			if (total) {
-				memcpy(new_record(), tmp, sizeof(tmp));
-				m.nz |= 1u << (1 + k);
-			}
+			if (total) m.nz |= 1u << (1 + k);
+			else drop_record();
 		}
 	}
 
@@ -905,14 +907,11 @@ private:
 				for (int b = 0; b < 4; ++b) {
 					int x = b & 1, y = b >> 1;
 					int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, x, y, slice_num_);
-					int16_t tmp[16];
-					memset(tmp, 0, sizeof(tmp));
-					int total = residual_block(nc, 15, tmp, zigzag4x4, 1);
+					int16_t *rec = new_record();
+					int total = residual_block(nc, 15, rec, zigzag4x4, 1);
 					nnz[16 + c * 4 + b] = (uint8_t)total;
-					if (total) {
-						memcpy(new_record(), tmp, sizeof(tmp));
-						m.nz |= 1u << (18 + c * 4 + b);
-					}
+					if (total) m.nz |= 1u << (18 + c * 4 + b);
+					else drop_record();
 				}
 		}
 	}
@@ -1091,19 +1090,19 @@ private:
 	}
 
 	// ---- deblocking strengths (8.7.2.1) for the MB just parsed ------------------------------------
-	int bs_between(int gx0, int gy0, int gx1, int gy1, bool p_intra, bool q_intra, bool mb_edge,
-	               const uint8_t *nnz_p, int np, const uint8_t *nnz_q, int nq) const {
-		if (p_intra || q_intra) return mb_edge ? 4 : 3;
-		if (nnz_p[np] || nnz_q[nq]) return 2;
-		size_t g0 = (size_t)gy0 * ctx_.w4 + gx0, g1 = (size_t)gy1 * ctx_.w4 + gx1;
+	// bS of an inter/inter 4x4 block pair: 2 if either block has coefficients, else 1 if the
+	// reference pictures differ or a motion vector component differs by >= 4 quarter samples
+	inline int bs_inter(size_t g0, size_t g1, bool nz0, bool nz1) const {
+		if (nz0 | nz1) return 2;
 		if (ctx_.refpic[0][g0] != ctx_.refpic[0][g1]) return 1;
-		int dx = ctx_.mv[0][g0 * 2] - ctx_.mv[0][g1 * 2], dy = ctx_.mv[0][g0 * 2 + 1] - ctx_.mv[0][g1 * 2 + 1];
-		if (dx < 0) dx = -dx;
-		if (dy < 0) dy = -dy;
-		return (dx >= 4 || dy >= 4) ? 1 : 0;
+		const int16_t *a = &ctx_.mv[0][g0 * 2], *b = &ctx_.mv[0][g1 * 2];
+		return ((unsigned)(a[0] - b[0] + 3) > 6u || (unsigned)(a[1] - b[1] + 3) > 6u) ? 1 : 0;
 	}
 
 	void finish_mb(int mbx, int mby, const Pps &pps, int dbk_qp) {
+#ifdef NO_FINISH
+		return;
+#endif
 		const SliceHeader &h = hdr_;
 		b2_h264_dbk &d = dbk_[(size_t)mby * mb_w_ + mbx];
 		memset(&d, 0, sizeof(d));
@@ -1126,36 +1125,60 @@ private:
 		bool left_ok = mbx > 0 && (h.disable_deblock == 0 || ctx_.mb_avail(mbx - 1, mby, slice_num_));
 		bool top_ok = mby > 0 && (h.disable_deblock == 0 || ctx_.mb_avail(mbx, mby - 1, slice_num_));
 		uint32_t bsv = 0, bsh = 0;
-		for (int e = 0; e < 4; ++e) {
-			for (int s = 0; s < 4; ++s) {
-				// vertical edge e, segment s: q = block (e, s), p = block (e-1, s)
-				int bs = 0;
-				if (e == 0) {
-					if (left_ok) {
-						const MbInfo &o = ctx_.info(mbx - 1, mby);
-						bs = bs_between(mbx * 4 - 1, mby * 4 + s, mbx * 4, mby * 4 + s, kind_is_intra(o.kind), intra, true,
-						                ctx_.nnz_of(mbx - 1, mby), s * 4 + 3, nnz, s * 4);
+		if (intra) {
+			// inner edges bS 3; MB edges bS 4 (flagged, stored as 3)
+			bsv = bsh = 0xffffff00u;
+			if (left_ok) { bsv |= 0xff; d.flags |= B2_DBK_LEFT_BS4; }
+			if (top_ok) { bsh |= 0xff; d.flags |= B2_DBK_TOP_BS4; }
+		} else {
+			const size_t w4 = (size_t)ctx_.w4;
+			const size_t g00 = (size_t)mby * 4 * w4 + (size_t)mbx * 4;
+			unsigned nzm = 0;
+			for (int i = 0; i < 16; ++i) nzm |= (unsigned)(nnz[i] != 0) << i;
+			if (mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt == 1) {
+				// one partition: no motion discontinuity inside the macroblock
+				for (int e = 1; e < 4; ++e)
+					for (int sg = 0; sg < 4; ++sg) {
+						bsv |= (uint32_t)((((nzm >> (sg * 4 + e - 1)) | (nzm >> (sg * 4 + e))) & 1) * 2) << (e * 8 + sg * 2);
+						bsh |= (uint32_t)((((nzm >> ((e - 1) * 4 + sg)) | (nzm >> (e * 4 + sg))) & 1) * 2) << (e * 8 + sg * 2);
 					}
-				} else {
-					bs = bs_between(mbx * 4 + e - 1, mby * 4 + s, mbx * 4 + e, mby * 4 + s, intra, intra, false,
-					                nnz, s * 4 + e - 1, nnz, s * 4 + e);
-				}
-				if (bs == 4) { d.flags |= B2_DBK_LEFT_BS4; bs = 3; }
-				bsv |= (uint32_t)bs << (e * 8 + s * 2);
-				// horizontal edge e, segment s: q = block (s, e), p = block (s, e-1)
-				bs = 0;
-				if (e == 0) {
-					if (top_ok) {
-						const MbInfo &o = ctx_.info(mbx, mby - 1);
-						bs = bs_between(mbx * 4 + s, mby * 4 - 1, mbx * 4 + s, mby * 4, kind_is_intra(o.kind), intra, true,
-						                ctx_.nnz_of(mbx, mby - 1), 12 + s, nnz, s);
+			} else {
+				// local copy of the macroblock's motion (raster 4x4) keeps the 48 comparisons cheap
+				int16_t mvx[16], mvy[16];
+				int8_t rp[16];
+				for (int yy = 0; yy < 4; ++yy)
+					for (int xx = 0; xx < 4; ++xx) {
+						size_t g = g00 + yy * w4 + xx;
+						mvx[yy * 4 + xx] = ctx_.mv[0][g * 2];
+						mvy[yy * 4 + xx] = ctx_.mv[0][g * 2 + 1];
+						rp[yy * 4 + xx] = ctx_.refpic[0][g];
 					}
-				} else {
-					bs = bs_between(mbx * 4 + s, mby * 4 + e - 1, mbx * 4 + s, mby * 4 + e, intra, intra, false,
-					                nnz, (e - 1) * 4 + s, nnz, e * 4 + s);
+				auto pair = [&](int i0, int i1) -> uint32_t {
+					if (((nzm >> i0) | (nzm >> i1)) & 1) return 2;
+					if (rp[i0] != rp[i1]) return 1;
+					return ((unsigned)(mvx[i0] - mvx[i1] + 3) > 6u || (unsigned)(mvy[i0] - mvy[i1] + 3) > 6u) ? 1 : 0;
+				};
+				for (int e = 1; e < 4; ++e)
+					for (int sg = 0; sg < 4; ++sg) {
+						bsv |= pair(sg * 4 + e - 1, sg * 4 + e) << (e * 8 + sg * 2);
+						bsh |= pair((e - 1) * 4 + sg, e * 4 + sg) << (e * 8 + sg * 2);
+					}
+			}
+			if (left_ok) {
+				if (kind_is_intra(ctx_.info(mbx - 1, mby).kind)) { bsv |= 0xff; d.flags |= B2_DBK_LEFT_BS4; }
+				else {
+					const uint8_t *ln = ctx_.nnz_of(mbx - 1, mby);
+					for (int sg = 0; sg < 4; ++sg)
+						bsv |= (uint32_t)bs_inter(g00 + sg * w4 - 1, g00 + sg * w4, ln[sg * 4 + 3] != 0, nnz[sg * 4] != 0) << (sg * 2);
 				}
-				if (bs == 4) { d.flags |= B2_DBK_TOP_BS4; bs = 3; }
-				bsh |= (uint32_t)bs << (e * 8 + s * 2);
+			}
+			if (top_ok) {
+				if (kind_is_intra(ctx_.info(mbx, mby - 1).kind)) { bsh |= 0xff; d.flags |= B2_DBK_TOP_BS4; }
+				else {
+					const uint8_t *tn = ctx_.nnz_of(mbx, mby - 1);
+					for (int sg = 0; sg < 4; ++sg)
+						bsh |= (uint32_t)bs_inter(g00 - w4 + sg, g00 + sg, tn[12 + sg] != 0, nnz[sg] != 0) << (sg * 2);
+				}
 			}
 		}
 		d.bs_v = bsv;
@@ -1195,6 +1218,7 @@ private:
 	std::vector<b2_h264_dbk> dbk_;
 	std::vector<b2_h264_mc> mcs_;
 	std::vector<int16_t> coefs_;
+	size_t coef_used_ = 0;
 	uint32_t n_intra_;
 	bool any_deblock_;
 };

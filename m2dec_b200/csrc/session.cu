@@ -34,8 +34,10 @@ struct StageSlot {
 struct b2_session {
 	int dev, codec, width, height, nframes;
 	size_t frame_bytes;
-	cudaStream_t stream;
+	cudaStream_t stream, copy_stream;
 	uint8_t *frames;
+	cudaEvent_t frame_done[64];     // recorded after the kernels that write frame i
+	bool frame_written[64];
 	StageSlot slots[NSLOT];
 	int next_slot;
 	uint64_t launches;
@@ -73,7 +75,10 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	s->height = height;
 	s->nframes = nframes;
 	s->frame_bytes = (size_t)width * height * 3 / 2;
+	if (nframes > 64) { set_error("b2_session_create: at most 64 frames"); delete s; return -1; }
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < nframes; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
 	B2_CUDA_OK(cudaMalloc(&s->frames, s->frame_bytes * nframes));
 	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * nframes, s->stream));
 	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming));
@@ -90,7 +95,10 @@ extern "C" void b2_session_destroy(b2_session *s) {
 		if (s->slots[i].dev) cudaFree(s->slots[i].dev);
 		cudaEventDestroy(s->slots[i].done);
 	}
+	for (int i = 0; i < s->nframes; ++i) cudaEventDestroy(s->frame_done[i]);
 	cudaFree(s->frames);
+	cudaStreamSynchronize(s->copy_stream);
+	cudaStreamDestroy(s->copy_stream);
 	cudaStreamDestroy(s->stream);
 	delete s;
 }
@@ -152,6 +160,8 @@ extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 	if (launch_mpeg2(s->stream, (const M2Job *)sl->dev, 1, p->mb_w, p->mb_h) < 0) return -1;
 	s->launches++;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
+	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
+	s->frame_written[p->dst] = true;
 	sl->pending = true;
 	return 0;
 }
@@ -197,6 +207,8 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs, p->n_intra > 0,
 	                p->deblock != 0, &s->launches) < 0) return -1;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
+	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
+	s->frame_written[p->dst] = true;
 	sl->pending = true;
 	return 0;
 }
@@ -213,10 +225,13 @@ extern "C" int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_
 	B2_CUDA_OK(cudaSetDevice(s->dev));
 	size_t ls = (size_t)s->width * s->height;
 	const uint8_t *src = s->frames + s->frame_bytes * idx;
-	B2_CUDA_OK(cudaMemcpyAsync(luma, src, ls, cudaMemcpyDeviceToHost, s->stream));
-	B2_CUDA_OK(cudaMemcpyAsync(chroma, src + ls, ls / 2, cudaMemcpyDeviceToHost, s->stream));
+	// wait for the picture that last wrote this frame only, not for pictures queued behind it:
+	// the host keeps parsing ahead while earlier frames are copied out
+	if (s->frame_written[idx]) B2_CUDA_OK(cudaStreamWaitEvent(s->copy_stream, s->frame_done[idx], 0));
+	B2_CUDA_OK(cudaMemcpyAsync(luma, src, ls, cudaMemcpyDeviceToHost, s->copy_stream));
+	B2_CUDA_OK(cudaMemcpyAsync(chroma, src + ls, ls / 2, cudaMemcpyDeviceToHost, s->copy_stream));
 	s->d2h_bytes += ls + ls / 2;
-	B2_CUDA_OK(cudaStreamSynchronize(s->stream));
+	B2_CUDA_OK(cudaStreamSynchronize(s->copy_stream));
 	return 0;
 }
 
