@@ -197,6 +197,7 @@ def main():
     rp.run()
     rp.sync()
     verified, verify_kind = 0, "none"
+    goldens = {}
     nver = min(a.verify_lanes, a.lanes)
     with tempfile.TemporaryDirectory() as d:
         if os.path.exists(REF_BIN) and nver:
@@ -207,6 +208,7 @@ def main():
             for lane in range(nver):
                 golden = open(os.path.join(d, "s%03d.out" % lane), "rb").read().split()
                 assert len(golden) == a.frames, (len(golden), a.frames)
+                goldens[lane] = [g.decode() for g in golden]
                 for t, idx in enumerate(rp.outputs[lane]):
                     y, c = rp.download(lane, idx)
                     h = hashlib.md5()
@@ -254,37 +256,53 @@ def main():
     counts = [None] * ne
     frames_out = [0] * ne
 
-    def decode_one(i):
+    e2e_checked = [0]
+
+    def decode_one(i, check=False):
         n = [0]
+        md5s = []
+
+        def post(frm):
+            n[0] += 1
+            if check:
+                md5s.append(m2dec_b200.frame_md5(frm))
+
         dec = m2dec_b200.M2Decoder("h264", streams[i], cuda_device=local)
         try:
-            dec.run(lambda frm: n.__setitem__(0, n[0] + 1))
+            dec.run(post)
             c = (L.C.c_uint64 * 3)()
             L.lib.b2_context_stats(dec.ctx, L.C.byref(c))
             counts[i] = [int(c[0]), int(c[1]), int(c[2])]
         finally:
             dec.close()
         frames_out[i] = n[0]
+        if check:
+            if md5s != goldens[i]:
+                raise SystemExit("bench.py: e2e MD5 mismatch on stream %d" % i)
+            e2e_checked[0] += len(md5s)
 
-    decode_one(0)    # warm-up: CUDA context, pinned staging
+    def run_pool(check=False):
+        work = list(range(ne))
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    if not work:
+                        return
+                    i = work.pop()
+                decode_one(i, check and i in goldens)
+
+        ths = [threading.Thread(target=worker) for _ in range(threads_n)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    run_pool(check=True)   # warm-up (untimed): CUDA context, buffer cache; output MD5-checked against the reference
     barrier()
     t0 = time.perf_counter()
-    work = list(range(ne))
-    lock = threading.Lock()
-
-    def worker():
-        while True:
-            with lock:
-                if not work:
-                    return
-                i = work.pop()
-            decode_one(i)
-
-    ths = [threading.Thread(target=worker) for _ in range(threads_n)]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
+    run_pool()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -337,7 +355,7 @@ def main():
                    "parity": "%d frames MD5-checked against %s before timing" % (verified, verify_kind),
                    "partitioning": "independent streams per GPU, no collective", "host_prep_s": t_prep},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "streams": ne, "frames": e2e_frames, "host_threads": threads_n, "seconds": e2e_s,
+                "streams": ne, "frames": e2e_frames, "md5_checked_frames": e2e_checked[0], "host_threads": threads_n, "seconds": e2e_s,
                 "path": "m2d_func_table_t (h264d_gpu_func): host ES -> parse -> H2D SoA -> kernels -> D2H every output frame"},
         "gpu_launches": int(st.launches) * a.steps,
         "roofline": roofline,

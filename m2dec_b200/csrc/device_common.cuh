@@ -40,9 +40,10 @@ struct H4Job {
 	int32_t dst, mb_w, mb_h, reserved;
 };
 // phase: 0 inter (MC + residual), 1 intra wavefront, 2 deblock wavefront
-int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint64_t *launches);
+size_t h264_sync_bytes(int n_jobs, int mb_h);
+int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches);
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
-                bool deblock, uint64_t *launches);
+                bool deblock, int *sync_area, uint64_t *launches);
 
 __device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 

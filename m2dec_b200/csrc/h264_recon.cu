@@ -808,106 +808,191 @@ __device__ void filter_line(uint8_t *px, ptrdiff_t st, int bs, int alpha, int be
 	px[0] = (uint8_t)clip255(q0 - delta);
 }
 
-// Deblock one macroblock with one warp.  The MB, 4 columns to its left and 4 (luma) / 2 (chroma)
-// rows above it are staged in shared memory with L2 loads, filtered there (lanes 0..15: one luma
-// line each, lanes 16..31: one chroma line each), and written back through to L2.
+// Deblock one macroblock with one warp, in two register passes.
+//   V pass (vertical edges): lane l < 16 holds luma row l (columns -4..15) unpacked in registers,
+//   lanes 16..23 hold the eight chroma rows (byte columns -4..15); the four edges of the row are
+//   filtered in registers, then the row is parked in the shared-memory tile.  Lanes 24..29 bring in
+//   the rows above the macroblock.
+//   H pass (horizontal edges): lane c < 16 holds luma column c (rows -4..15), lanes 16..31 hold the
+//   chroma byte columns (rows -2..7); same filtering down the column, written back to the tile.
+//   The tile is then stored with 32-bit L2 stores.  Pixels of other warps are read through L2.
 struct DbkTile {
-	uint8_t y[20][36];      // rows -4..15 at index r+4, columns -4..15 at index c+4; 36-byte pitch avoids bank conflicts
+	uint8_t y[20][36];      // rows -4..15 at index r+4, columns -4..15 at index c+4; 36-byte pitch: conflict-free columns
 	uint8_t c[10][36];      // chroma rows -2..7 at index r+2, byte columns -4..15 at index c+4
 };
 
+// filter across the edge in front of v[q]: p3..p0 = v[q-4..q-1], q0..q3 = v[q..q+3], stride `st` entries
+template <int ST>
+__device__ __forceinline__ void filter_regs(int *v, int q, int bs, int alpha, int beta, int tc0, bool luma) {
+	int p0 = v[q - ST], p1 = v[q - 2 * ST], q0 = v[q], q1 = v[q + ST];
+	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+	if (bs == 4) {
+		if (luma) {
+			int p2 = v[q - 3 * ST], q2 = v[q + 2 * ST];
+			bool strong = abs(p0 - q0) < (alpha >> 2) + 2;
+			if (strong && abs(p2 - p0) < beta) {
+				int p3 = v[q - 4 * ST];
+				v[q - ST] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+				v[q - 2 * ST] = (p2 + p1 + p0 + q0 + 2) >> 2;
+				v[q - 3 * ST] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+			} else {
+				v[q - ST] = (2 * p1 + p0 + q1 + 2) >> 2;
+			}
+			if (strong && abs(q2 - q0) < beta) {
+				int q3 = v[q + 3 * ST];
+				v[q] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+				v[q + ST] = (p0 + q0 + q1 + q2 + 2) >> 2;
+				v[q + 2 * ST] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+			} else {
+				v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
+			}
+		} else {
+			v[q - ST] = (2 * p1 + p0 + q1 + 2) >> 2;
+			v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
+		}
+		return;
+	}
+	int tc;
+	if (luma) {
+		int p2 = v[q - 3 * ST], q2 = v[q + 2 * ST];
+		int ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
+		tc = tc0 + ap + aq;
+		if (ap) v[q - 2 * ST] = p1 + min(max((p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1, -tc0), tc0);
+		if (aq) v[q + ST] = q1 + min(max((q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1, -tc0), tc0);
+	} else {
+		tc = tc0 + 1;
+	}
+	int delta = min(max(((q0 - p0) * 4 + (p1 - q1) + 4) >> 3, -tc), tc);
+	v[q - ST] = clip255(p0 + delta);
+	v[q] = clip255(q0 - delta);
+}
+
+struct EdgeParams { int alpha, beta, ia; };
+__device__ __forceinline__ EdgeParams edge_params(int qp, int aoff, int boff) {
+	EdgeParams e;
+	e.ia = min(max(qp + aoff, 0), 51);
+	int ib = min(max(qp + boff, 0), 51);
+	e.alpha = c_alpha[e.ia];
+	e.beta = c_beta[ib];
+	return e;
+}
+
 __device__ void deblock_mb(const H4Job &job, const b2_h264_dbk *dp, int mbx, int mby, DbkTile &tl, int lane) {
 	const b2_h264_dbk d = *dp;
-	if ((d.flags & B2_DBK_OFF) || !(d.bs_v | d.bs_h)) return;
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
 	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
 	uint8_t *py = fy + (size_t)mby * 16 * W + mbx * 16;
 	uint8_t *pc = fy + (size_t)W * H + (size_t)mby * 8 * W + mbx * 16;
-	// ---- stage ----------------------------------------------------------------------------------
+	const bool left_ok = d.flags & B2_DBK_LEFT_EDGE, top_ok = d.flags & B2_DBK_TOP_EDGE;
+	int nqy[2] = {0, 0}, nqb[2] = {0, 0}, nqr[2] = {0, 0};
+	if (left_ok) { const b2_h264_dbk *n = dp - 1; nqy[0] = n->qp_y; nqb[0] = n->qp_cb; nqr[0] = n->qp_cr; }
+	if (top_ok) { const b2_h264_dbk *n = dp - job.mb_w; nqy[1] = n->qp_y; nqb[1] = n->qp_cb; nqr[1] = n->qp_cr; }
+
+	// ---- V pass ---------------------------------------------------------------------------------
+	if (lane < 24) {
+		const bool luma = lane < 16;
+		const int row = luma ? lane : lane - 16;
+		const uint8_t *src = luma ? py + (size_t)row * W : pc + (size_t)row * W;
+		uint32_t w[5];
+		w[0] = mbx > 0 ? __ldcg(reinterpret_cast<const uint32_t *>(src - 4)) : 0;
 #pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		int i = lane + 32 * k;
-		if (i < 100) {
-			int r = i / 5 - 4, w = i % 5;
-			if ((r >= 0 || mby > 0) && (w > 0 || mbx > 0))
-				*reinterpret_cast<uint32_t *>(&tl.y[r + 4][w * 4]) = __ldcg(reinterpret_cast<const uint32_t *>(py + (ptrdiff_t)r * W + (w - 1) * 4));
-		}
-	}
+		for (int k = 1; k < 5; ++k) w[k] = __ldcg(reinterpret_cast<const uint32_t *>(src + (k - 1) * 4));
+		int v[20];
 #pragma unroll
-	for (int k = 0; k < 2; ++k) {
-		int i = lane + 32 * k;
-		if (i < 50) {
-			int r = i / 5 - 2, w = i % 5;
-			if ((r >= 0 || mby > 0) && (w > 0 || mbx > 0))
-				*reinterpret_cast<uint32_t *>(&tl.c[r + 2][w * 4]) = __ldcg(reinterpret_cast<const uint32_t *>(pc + (ptrdiff_t)r * W + (w - 1) * 4));
-		}
-	}
-	__syncwarp();
-	// ---- filter ---------------------------------------------------------------------------------
-	const bool is_luma = lane < 16;
-	const int li = lane & 15;
-#pragma unroll 1
-	for (int dir = 0; dir < 2; ++dir) {
-		const uint32_t bits = dir ? d.bs_h : d.bs_v;
-		const bool edge_ok = d.flags & (dir ? B2_DBK_TOP_EDGE : B2_DBK_LEFT_EDGE);
-		const bool bs4 = d.flags & (dir ? B2_DBK_TOP_BS4 : B2_DBK_LEFT_BS4);
-		int nqy = 0, nqb = 0, nqr = 0;
-		if (edge_ok) {
-			const b2_h264_dbk *n = dir ? dp - job.mb_w : dp - 1;
-			nqy = n->qp_y; nqb = n->qp_cb; nqr = n->qp_cr;
-		}
-#pragma unroll 1
-		for (int e = 0; e < 4; ++e) {
-			const int eb = (bits >> (8 * e)) & 255;
-			if (!eb || (e == 0 && !edge_ok)) continue;
-			if (is_luma) {
-				int bs = (eb >> ((li >> 2) * 2)) & 3;
-				if (bs) {
-					if (e == 0 && bs4) bs = 4;
-					int qp = e ? d.qp_y : (d.qp_y + nqy + 1) >> 1;
-					int ia = min(max(qp + d.alpha_off, 0), 51), ib = min(max(qp + d.beta_off, 0), 51);
-					int alpha = c_alpha[ia], beta = c_beta[ib];
-					if (alpha) {
-						uint8_t *p = dir ? &tl.y[4 + e * 4][4 + li] : &tl.y[4 + li][4 + e * 4];
-						filter_line(p, dir ? 36 : 1, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, true);
-					}
-				}
-			} else if (!(e & 1)) {
-				// chroma: dir 0: li = row * 2 + comp (8 rows x 2 components); dir 1: li = byte column
-				int line = li >> 1, comp = li & 1;
-				int bs = (eb >> ((line >> 1) * 2)) & 3;
-				if (bs) {
-					if (e == 0 && bs4) bs = 4;
-					int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr : nqb;
-					int qp = e ? qc : (qc + qn + 1) >> 1;
-					int ia = min(max(qp + d.alpha_off, 0), 51), ib = min(max(qp + d.beta_off, 0), 51);
-					int alpha = c_alpha[ia], beta = c_beta[ib];
-					if (alpha) {
-						uint8_t *p = dir ? &tl.c[2 + (e / 2) * 4][4 + li] : &tl.c[2 + line][4 + (e / 2) * 8 + comp];
-						filter_line(p, dir ? 36 : 2, bs, alpha, beta, bs < 4 ? c_tc0[ia][bs - 1] : 0, false);
-					}
+		for (int i = 0; i < 20; ++i) v[i] = (w[i >> 2] >> ((i & 3) * 8)) & 255;
+		if (luma) {
+			const int seg = row >> 2;
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				int bs = (d.bs_v >> (8 * e + 2 * seg)) & 3;
+				if (!bs || (e == 0 && !left_ok)) continue;
+				if (e == 0 && (d.flags & B2_DBK_LEFT_BS4)) bs = 4;
+				EdgeParams ep = edge_params(e ? d.qp_y : (d.qp_y + nqy[0] + 1) >> 1, d.alpha_off, d.beta_off);
+				if (ep.alpha) filter_regs<1>(v, 4 + 4 * e, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, true);
+			}
+		} else {
+			const int seg = row >> 1;
+#pragma unroll
+			for (int e = 0; e < 4; e += 2) {
+				int bs = (d.bs_v >> (8 * e + 2 * seg)) & 3;
+				if (!bs || (e == 0 && !left_ok)) continue;
+				if (e == 0 && (d.flags & B2_DBK_LEFT_BS4)) bs = 4;
+#pragma unroll
+				for (int comp = 0; comp < 2; ++comp) {
+					int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr[0] : nqb[0];
+					EdgeParams ep = edge_params(e ? qc : (qc + qn + 1) >> 1, d.alpha_off, d.beta_off);
+					if (ep.alpha) filter_regs<2>(v, 4 + 4 * e + comp, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, false);
 				}
 			}
-			__syncwarp();
 		}
+		uint32_t *dstw = reinterpret_cast<uint32_t *>(luma ? &tl.y[4 + row][0] : &tl.c[2 + row][0]);
+#pragma unroll
+		for (int k = 0; k < 5; ++k)
+			dstw[k] = (uint32_t)v[4 * k] | ((uint32_t)v[4 * k + 1] << 8) | ((uint32_t)v[4 * k + 2] << 16) | ((uint32_t)v[4 * k + 3] << 24);
+	} else if (lane < 30 && mby > 0) {
+		// rows above: luma -4..-1 (lanes 24..27), chroma -2..-1 (lanes 28, 29); columns 0..15 only
+		const bool luma = lane < 28;
+		const int r = luma ? lane - 28 : lane - 30;          // -4..-1 / -2..-1
+		const uint8_t *src = luma ? py + (ptrdiff_t)r * W : pc + (ptrdiff_t)r * W;
+		uint32_t *dstw = reinterpret_cast<uint32_t *>(luma ? &tl.y[4 + r][0] : &tl.c[2 + r][0]);
+#pragma unroll
+		for (int k = 1; k < 5; ++k) dstw[k] = __ldcg(reinterpret_cast<const uint32_t *>(src + (k - 1) * 4));
 	}
 	__syncwarp();
-	// ---- write back (rows -3..15 x columns -4..15; only bytes this MB may own or has ordered access to)
+	// ---- H pass ---------------------------------------------------------------------------------
+	if (d.bs_h) {
+		const bool luma = lane < 16;
+		const int col = lane & 15;
+		if (luma) {
+			int v[20];
 #pragma unroll
-	for (int k = 0; k < 4; ++k) {
+			for (int i = 0; i < 20; ++i) v[i] = tl.y[i][4 + col];
+			const int seg = col >> 2;
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				int bs = (d.bs_h >> (8 * e + 2 * seg)) & 3;
+				if (!bs || (e == 0 && !top_ok)) continue;
+				if (e == 0 && (d.flags & B2_DBK_TOP_BS4)) bs = 4;
+				EdgeParams ep = edge_params(e ? d.qp_y : (d.qp_y + nqy[1] + 1) >> 1, d.alpha_off, d.beta_off);
+				if (ep.alpha) filter_regs<1>(v, 4 + 4 * e, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, true);
+			}
+#pragma unroll
+			for (int i = 1; i < 20; ++i) tl.y[i][4 + col] = (uint8_t)v[i];
+		} else {
+			int v[10];
+#pragma unroll
+			for (int i = 0; i < 10; ++i) v[i] = tl.c[i][4 + col];
+			const int seg = col >> 2, comp = col & 1;
+#pragma unroll
+			for (int e = 0; e < 4; e += 2) {
+				int bs = (d.bs_h >> (8 * e + 2 * seg)) & 3;
+				if (!bs || (e == 0 && !top_ok)) continue;
+				if (e == 0 && (d.flags & B2_DBK_TOP_BS4)) bs = 4;
+				int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr[1] : nqb[1];
+				EdgeParams ep = edge_params(e ? qc : (qc + qn + 1) >> 1, d.alpha_off, d.beta_off);
+				if (ep.alpha) filter_regs<1>(v, 2 + 2 * e, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, false);
+			}
+#pragma unroll
+			for (int i = 1; i < 10; ++i) tl.c[i][4 + col] = (uint8_t)v[i];
+		}
+		__syncwarp();
+	}
+	// ---- store: luma rows -3..15, chroma rows -1..7; word 0 (columns -4..-1) only when a left MB exists
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
 		int i = lane + 32 * k;
-		if (i < 100) {
-			int r = i / 5 - 4, w = i % 5;
-			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (r >= -3 && w > 0 && mby > 0);
+		if (i < 95) {
+			int r = i / 5 - 3, w = i % 5;
+			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (w > 0 && top_ok);
 			if (ok) __stcg(reinterpret_cast<uint32_t *>(py + (ptrdiff_t)r * W + (w - 1) * 4), *reinterpret_cast<const uint32_t *>(&tl.y[r + 4][w * 4]));
 		}
 	}
 #pragma unroll
 	for (int k = 0; k < 2; ++k) {
 		int i = lane + 32 * k;
-		if (i < 50) {
-			int r = i / 5 - 2, w = i % 5;
-			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (w > 0 && mby > 0);
+		if (i < 45) {
+			int r = i / 5 - 1, w = i % 5;
+			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (w > 0 && top_ok);
 			if (ok) __stcg(reinterpret_cast<uint32_t *>(pc + (ptrdiff_t)r * W + (w - 1) * 4), *reinterpret_cast<const uint32_t *>(&tl.c[r + 2][w * 4]));
 		}
 	}
@@ -984,7 +1069,6 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 				} else {
 					deblock_mb(job, &job.dbk[(size_t)mby * mb_w + x], x, mby, s_tile[warp].dbk, lane);
 				}
-				__threadfence();
 				__syncwarp();
 				done_to = x + 1;
 				if (lane == 0) st_release(my, done_to);
@@ -1003,25 +1087,11 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 
 }  // namespace
 
-static int *g_sync_area[16] = {nullptr};      // per device: ticket + progress flags
-static size_t g_sync_cap[16] = {0};
+// bytes of scratch (ticket counter + per-row progress flags) the wavefront kernels need; the
+// caller owns one such area per CUDA stream, since kernels of different streams run concurrently
+size_t h264_sync_bytes(int n_jobs, int mb_h) { return (32 + (size_t)n_jobs * mb_h) * sizeof(int); }
 
-static int wave_sync_area(int n_jobs, int mb_h, int **out, size_t *bytes) {
-	int dev = 0;
-	B2_CUDA_OK(cudaGetDevice(&dev));
-	size_t need = (32 + (size_t)n_jobs * mb_h) * sizeof(int);
-	if (dev < 0 || dev >= 16) return -1;
-	if (g_sync_cap[dev] < need) {
-		if (g_sync_area[dev]) cudaFree(g_sync_area[dev]);
-		B2_CUDA_OK(cudaMalloc(&g_sync_area[dev], need * 2));
-		g_sync_cap[dev] = need * 2;
-	}
-	*out = g_sync_area[dev];
-	*bytes = need;
-	return 0;
-}
-
-int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint64_t *launches) {
+int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches) {
 	if (n_jobs <= 0) return 0;
 	if (phase == 0) {
 		const int n_mbs = mb_w * mb_h;
@@ -1029,10 +1099,8 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
 		if (launches) ++*launches;
 	} else {
-		int *area;
-		size_t bytes;
-		if (wave_sync_area(n_jobs, mb_h, &area, &bytes) < 0) return -1;
-		B2_CUDA_OK(cudaMemsetAsync(area, 0, bytes, stream));
+		int *area = sync_area;
+		B2_CUDA_OK(cudaMemsetAsync(area, 0, h264_sync_bytes(n_jobs, mb_h), stream));
 		int rows = n_jobs * mb_h;
 		int ctas = (rows + WAVE_WARPS - 1) / WAVE_WARPS;
 		int cap = 148 * 6;
@@ -1046,10 +1114,10 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 }
 
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
-                bool deblock, uint64_t *launches) {
-	if (any_inter && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, launches) < 0) return -1;
-	if (any_intra && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, launches) < 0) return -1;
-	if (deblock && launch_h264_phase(stream, 2, d_jobs, n_jobs, mb_w, mb_h, launches) < 0) return -1;
+                bool deblock, int *sync_area, uint64_t *launches) {
+	if (any_inter && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
+	if (any_intra && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
+	if (deblock && launch_h264_phase(stream, 2, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	return 0;
 }
 

@@ -23,6 +23,7 @@ struct b2_replay {
 	int dev, codec, width, height, lanes, pool;
 	size_t frame_bytes;
 	uint8_t *frames;
+	int *sync_area;
 	cudaStream_t stream;
 	std::vector<Blob> blobs;
 	std::vector<int> lane_len;
@@ -53,6 +54,7 @@ extern "C" int b2_replay_create(int cuda_device, int codec, int width, int heigh
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaMalloc(&r->frames, r->frame_bytes * pool_frames * lanes));
 	B2_CUDA_OK(cudaMemset(r->frames, 0, r->frame_bytes * pool_frames * lanes));
+	B2_CUDA_OK(cudaMalloc(&r->sync_area, h264_sync_bytes(lanes, height / 16)));
 	B2_CUDA_OK(cudaEventCreate(&r->ev_begin));
 	B2_CUDA_OK(cudaEventCreate(&r->ev_end));
 	B2_CUDA_OK(cudaEventCreate(&r->ev_mark[0]));
@@ -71,6 +73,7 @@ extern "C" void b2_replay_destroy(b2_replay *r) {
 	cudaEventDestroy(r->ev_begin);
 	cudaEventDestroy(r->ev_end);
 	cudaFree(r->frames);
+	cudaFree(r->sync_area);
 	cudaStreamDestroy(r->stream);
 	delete r;
 }
@@ -203,11 +206,11 @@ extern "C" int b2_replay_run(b2_replay *r, int timed) {
 		const H4Job *jobs = (const H4Job *)s.d_jobs;
 		int n = (int)s.h4.size();
 		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 0], r->stream));
-		if (s.any_inter && launch_h264_phase(r->stream, 0, jobs, n, mb_w, mb_h, &launches) < 0) return -1;
+		if (s.any_inter && launch_h264_phase(r->stream, 0, jobs, n, mb_w, mb_h, r->sync_area, &launches) < 0) return -1;
 		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 1], r->stream));
-		if (s.any_intra && launch_h264_phase(r->stream, 1, jobs, n, mb_w, mb_h, &launches) < 0) return -1;
+		if (s.any_intra && launch_h264_phase(r->stream, 1, jobs, n, mb_w, mb_h, r->sync_area, &launches) < 0) return -1;
 		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 2], r->stream));
-		if (s.deblock && launch_h264_phase(r->stream, 2, jobs, n, mb_w, mb_h, &launches) < 0) return -1;
+		if (s.deblock && launch_h264_phase(r->stream, 2, jobs, n, mb_w, mb_h, r->sync_area, &launches) < 0) return -1;
 		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 3], r->stream));
 	}
 	B2_CUDA_OK(cudaEventRecord(r->ev_end, r->stream));

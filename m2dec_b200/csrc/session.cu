@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <vector>
 #include "device_common.cuh"
 
 namespace b2 {
@@ -23,19 +24,58 @@ using namespace b2;
 
 enum { NSLOT = 4 };
 
+// Process-wide free lists: cudaMalloc / cudaMallocHost / cudaFree synchronise the whole device, so a
+// server that opens and closes streams all the time must not call them per stream.
+namespace {
+struct CachedBuf { int dev; bool pinned; size_t bytes; void *ptr; };
+std::mutex g_cache_mu;
+std::vector<CachedBuf> g_cache;
+
+// sizes are rounded up to 1 MiB buckets so that buffers of closed streams fit the next ones
+int cache_get(int dev, bool pinned, size_t bytes, void **out, size_t *actual = nullptr) {
+	bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+	if (actual) *actual = bytes;
+	{
+		std::lock_guard<std::mutex> lk(g_cache_mu);
+		size_t best = (size_t)-1;
+		for (size_t i = 0; i < g_cache.size(); ++i) {
+			const CachedBuf &c = g_cache[i];
+			if (c.dev == dev && c.pinned == pinned && c.bytes >= bytes && c.bytes <= bytes * 2 &&
+			    (best == (size_t)-1 || c.bytes < g_cache[best].bytes)) best = i;
+		}
+		if (best != (size_t)-1) {
+			*out = g_cache[best].ptr;
+			if (actual) *actual = g_cache[best].bytes;
+			g_cache.erase(g_cache.begin() + best);
+			return 0;
+		}
+	}
+	if (pinned) B2_CUDA_OK(cudaMallocHost(out, bytes));
+	else B2_CUDA_OK(cudaMalloc(out, bytes));
+	return 0;
+}
+size_t g_sizes_dummy = 0;
+void cache_put(int dev, bool pinned, size_t bytes, void *ptr) {
+	if (!ptr) return;
+	std::lock_guard<std::mutex> lk(g_cache_mu);
+	g_cache.push_back(CachedBuf{dev, pinned, bytes, ptr});
+}
+}  // namespace
+
 struct StageSlot {
 	uint8_t *host;
 	uint8_t *dev;
-	size_t cap;
+	size_t cap, cap_host, cap_dev;
 	cudaEvent_t done;      // recorded after the kernels that read the slot
 	bool pending;
 };
 
 struct b2_session {
 	int dev, codec, width, height, nframes;
-	size_t frame_bytes;
+	size_t frame_bytes, frames_alloc, sync_alloc;
 	cudaStream_t stream, copy_stream;
 	uint8_t *frames;
+	int *sync_area;                 // wavefront ticket / progress flags of this stream
 	cudaEvent_t frame_done[64];     // recorded after the kernels that write frame i
 	bool frame_written[64];
 	StageSlot slots[NSLOT];
@@ -79,8 +119,9 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < nframes; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
-	B2_CUDA_OK(cudaMalloc(&s->frames, s->frame_bytes * nframes));
+	if (cache_get(cuda_device, false, s->frame_bytes * nframes, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
 	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * nframes, s->stream));
+	if (cache_get(cuda_device, false, h264_sync_bytes(1, height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
 	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming));
 	*out = s;
 	return 0;
@@ -91,13 +132,14 @@ extern "C" void b2_session_destroy(b2_session *s) {
 	cudaSetDevice(s->dev);
 	cudaStreamSynchronize(s->stream);
 	for (int i = 0; i < NSLOT; ++i) {
-		if (s->slots[i].host) cudaFreeHost(s->slots[i].host);
-		if (s->slots[i].dev) cudaFree(s->slots[i].dev);
+		cache_put(s->dev, true, s->slots[i].cap_host, s->slots[i].host);
+		cache_put(s->dev, false, s->slots[i].cap_dev, s->slots[i].dev);
 		cudaEventDestroy(s->slots[i].done);
 	}
 	for (int i = 0; i < s->nframes; ++i) cudaEventDestroy(s->frame_done[i]);
-	cudaFree(s->frames);
 	cudaStreamSynchronize(s->copy_stream);
+	cache_put(s->dev, false, s->frames_alloc, s->frames);
+	cache_put(s->dev, false, s->sync_alloc, s->sync_area);
 	cudaStreamDestroy(s->copy_stream);
 	cudaStreamDestroy(s->stream);
 	delete s;
@@ -112,13 +154,18 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 		sl->pending = false;
 	}
 	if (sl->cap < bytes) {
-		if (sl->host) cudaFreeHost(sl->host);
-		if (sl->dev) cudaFree(sl->dev);
+		cache_put(s->dev, true, sl->cap_host, sl->host);
+		cache_put(s->dev, false, sl->cap_dev, sl->dev);
 		sl->host = sl->dev = nullptr;
-		size_t cap = bytes + bytes / 2 + 4096;
-		B2_CUDA_OK(cudaMallocHost(&sl->host, cap));
-		B2_CUDA_OK(cudaMalloc(&sl->dev, cap));
-		sl->cap = cap;
+		sl->cap = 0;
+		// sized for a dense picture of this geometry so that it rarely has to grow
+		size_t cap = bytes + bytes / 2 + 4096, typical = (size_t)s->width * s->height * 3 / 2, got_h = 0, got_d = 0;
+		if (cap < typical) cap = typical;
+		if (cache_get(s->dev, true, cap, (void **)&sl->host, &got_h) < 0) return -1;
+		if (cache_get(s->dev, false, cap, (void **)&sl->dev, &got_d) < 0) return -1;
+		sl->cap_host = got_h;
+		sl->cap_dev = got_d;
+		sl->cap = got_h < got_d ? got_h : got_d;
 	}
 	*out = sl;
 	return 0;
@@ -205,7 +252,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs, p->n_intra > 0,
-	                p->deblock != 0, &s->launches) < 0) return -1;
+	                p->deblock != 0, s->sync_area, &s->launches) < 0) return -1;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
 	s->frame_written[p->dst] = true;

@@ -28,6 +28,7 @@ class Frames:
     NV12 chroma W*H/2."""
 
     def __init__(self, width, height, num, second_len):
+        self.width, self.height = width, height
         self.luma_len = width * height
         self.luma = [_align16(np.zeros(self.luma_len + 15, np.uint8)) for _ in range(num)]
         self.chroma = [_align16(np.zeros(self.luma_len // 2 + 15, np.uint8)) for _ in range(num)]
@@ -40,6 +41,27 @@ class Frames:
 
     def sufficient(self, num, luma_len, second_len):
         return num <= self.num and luma_len <= self.luma_len and second_len <= len(self.second)
+
+
+# Frame buffers belong to the application (reference frames.h); an application that decodes many
+# streams reuses them instead of paying page faults for fresh ones on every stream.
+_frames_pool = {}
+_frames_lock = __import__("threading").Lock()
+
+
+def _frames_acquire(width, height, num, second_len):
+    key = (width, height, num)
+    with _frames_lock:
+        lst = _frames_pool.get(key)
+        if lst:
+            return lst.pop()
+    return Frames(width, height, num, second_len)
+
+
+def _frames_release(fr):
+    key = (int(fr.width), int(fr.height), int(fr.num))
+    with _frames_lock:
+        _frames_pool.setdefault(key, []).append(fr)
 
 
 def crop_frame(frm):
@@ -92,6 +114,9 @@ class M2Decoder:
         if self.ctx:
             L.lib.b2_context_release(self.ctx)
             self.ctx = None
+            if self.frames is not None:
+                _frames_release(self.frames)
+                self.frames = None
 
     def __del__(self):
         try:
@@ -120,7 +145,7 @@ class M2Decoder:
         bufnum = min(bufnum, H264D_MAX_FRAME_NUM if self.codec == MODE_H264 else MAX_FRAME_NUM)
         if self.frames is not None and self.frames.sufficient(bufnum, width * height, info.additional_size):
             return 0
-        self.frames = Frames(width, height, bufnum, info.additional_size)
+        self.frames = _frames_acquire(width, height, bufnum, info.additional_size)
         self.info = info
         r = self.func.set_frames(self.ctx, bufnum, self.frames.array,
                                  self.frames.second.ctypes.data, info.additional_size)

@@ -98,3 +98,27 @@ def test_cuda_matches_oracle_degenerate(name):
     import m2dec_b200
     data = streams.generate("h264", streams.H264_REFERENCE_DEVIATES[name])
     assert m2dec_b200.decode_file("h264", data) == util.oracle_md5("h264", data)
+
+
+@pytest.mark.gpu
+def test_cuda_concurrent_streams():
+    """Many decoder contexts on host threads at once (one CUDA stream each): every stream must
+    still be bit-exact."""
+    import threading
+    import m2dec_b200
+    names = sorted(streams.H264_CASES)
+    data = {n: streams.generate("h264", streams.H264_CASES[n]) for n in names}
+    want = {n: util.oracle_md5("h264", data[n]) for n in names}
+    got = {}
+
+    def work(n):
+        got[n] = m2dec_b200.decode_file("h264", data[n])
+
+    for _ in range(2):
+        ths = [threading.Thread(target=work, args=(n,)) for n in names]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        for n in names:
+            assert got[n] == want[n], n
