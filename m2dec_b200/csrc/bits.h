@@ -64,11 +64,12 @@ public:
 		return v;
 	}
 	inline uint32_t ue() {
-		int zeros = 0;
-		while (get1() == 0) {
-			if (++zeros > 31) return 0;
-		}
-		return zeros ? ((1u << zeros) - 1 + get(zeros)) : 0;
+		uint32_t look = peek(32);
+		if (look & 0x80000000u) { skip(1); return 0; }
+		if (!look) { skip(32); return 0; }
+		int zeros = __builtin_clz(look);
+		skip(zeros + 1);
+		return (1u << zeros) - 1 + get(zeros);
 	}
 	inline int32_t se() {
 		uint32_t k = ue();

@@ -108,36 +108,59 @@ public:
 	}
 
 	// --- start of a macroblock: its 16 blocks become "not yet decoded" ------------------------
+	// Also caches what every neighbour derivation of this macroblock needs (availability of the
+	// four neighbouring MBs, pointers to their coefficient counts).
+	struct Env {
+		int mbx, mby;
+		bool availL, availT, availTR, availTL;
+		const uint8_t *nnz_left, *nnz_top;
+		uint8_t *nnz_cur;
+	} env;
+
 	void open_mb(int mbx, int mby, int cur_slice) {
 		MbInfo &m = mb[(size_t)mby * mb_w + mbx];
 		m.slice = (uint16_t)cur_slice;
-		for (int y = 0; y < 4; ++y)
-			for (int x = 0; x < 4; ++x) {
-				size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x;
-				ref[0][g] = ref[1][g] = -2;
-			}
+		for (int y = 0; y < 4; ++y) {
+			size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4;
+			memset(&ref[0][g], -2, 4);
+			memset(&ref[1][g], -2, 4);
+		}
+		env.mbx = mbx;
+		env.mby = mby;
+		env.availL = mb_avail(mbx - 1, mby, cur_slice);
+		env.availT = mb_avail(mbx, mby - 1, cur_slice);
+		env.availTR = mb_avail(mbx + 1, mby - 1, cur_slice);
+		env.availTL = mb_avail(mbx - 1, mby - 1, cur_slice);
+		env.nnz_cur = &nnz[((size_t)mby * mb_w + mbx) * 24];
+		env.nnz_left = env.availL ? env.nnz_cur - 24 : nullptr;
+		env.nnz_top = env.availT ? env.nnz_cur - (size_t)mb_w * 24 : nullptr;
 	}
 
 	// fill a w4 x h4 partition (4-pel units) of the current MB
 	void set_motion(int list, int mbx, int mby, int x4, int y4, int pw, int ph, int refidx, int pic, int mvx, int mvy) {
-		for (int y = y4; y < y4 + ph; ++y)
-			for (int x = x4; x < x4 + pw; ++x) {
-				size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x;
-				ref[list][g] = (int8_t)refidx;
-				refpic[list][g] = (int8_t)pic;
-				mv[list][g * 2] = (int16_t)mvx;
-				mv[list][g * 2 + 1] = (int16_t)mvy;
-			}
+		const uint32_t packed = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+		for (int y = y4; y < y4 + ph; ++y) {
+			size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x4;
+			memset(&ref[list][g], refidx, pw);
+			memset(&refpic[list][g], pic, pw);
+			uint32_t *m = reinterpret_cast<uint32_t *>(&mv[list][g * 2]);
+			for (int x = 0; x < pw; ++x) m[x] = packed;
+		}
 	}
 	void set_intra_motion(int mbx, int mby) {
 		for (int l = 0; l < 2; ++l) set_motion(l, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
 	}
 
 	// neighbouring 4x4 block at global 4-pel coordinates (gx, gy)
-	inline Neighbour nb(int list, int gx, int gy, int cur_slice) const {
+	inline Neighbour nb(int list, int gx, int gy, int /*cur_slice*/) const {
 		Neighbour n = {false, -1, {0, 0}};
-		if (gx < 0 || gy < 0 || gx >= w4 || gy >= h4) return n;
-		if (mb[(size_t)(gy >> 2) * mb_w + (gx >> 2)].slice != cur_slice) return n;
+		// (gx, gy) lies in the current macroblock or in one of its four causal neighbours
+		const int rx = (gx >> 2) - env.mbx, ry = (gy >> 2) - env.mby;
+		bool ok;
+		if (ry == 0) ok = rx == 0 || (rx < 0 && env.availL);
+		else if (ry < 0) ok = rx == 0 ? env.availT : (rx < 0 ? env.availTL : env.availTR);
+		else ok = false;
+		if (!ok) return n;
 		size_t g = (size_t)gy * w4 + gx;
 		int r = ref[list][g];
 		if (r == -2) return n;
@@ -192,13 +215,13 @@ public:
 	}
 
 	// 9.2.1: nC for the block at (x, y) in units of blocks; plane 0 luma (4x4 grid), 1 Cb, 2 Cr (2x2 grid)
-	int cavlc_nc(int mbx, int mby, int plane, int x, int y, int cur_slice) const {
-		int dim = plane ? 2 : 4, base = plane ? 12 + plane * 4 : 0;
+	inline int cavlc_nc(int /*mbx*/, int /*mby*/, int plane, int x, int y, int /*cur_slice*/) const {
+		const int dim = plane ? 2 : 4, base = plane ? 12 + plane * 4 : 0;
 		int na = -1, nb_ = -1;
-		if (x > 0) na = nnz[((size_t)mby * mb_w + mbx) * 24 + base + y * dim + x - 1];
-		else if (mb_avail(mbx - 1, mby, cur_slice)) na = nnz[((size_t)mby * mb_w + mbx - 1) * 24 + base + y * dim + dim - 1];
-		if (y > 0) nb_ = nnz[((size_t)mby * mb_w + mbx) * 24 + base + (y - 1) * dim + x];
-		else if (mb_avail(mbx, mby - 1, cur_slice)) nb_ = nnz[((size_t)(mby - 1) * mb_w + mbx) * 24 + base + (dim - 1) * dim + x];
+		if (x > 0) na = env.nnz_cur[base + y * dim + x - 1];
+		else if (env.nnz_left) na = env.nnz_left[base + y * dim + dim - 1];
+		if (y > 0) nb_ = env.nnz_cur[base + (y - 1) * dim + x];
+		else if (env.nnz_top) nb_ = env.nnz_top[base + (dim - 1) * dim + x];
 		if (na >= 0 && nb_ >= 0) return (na + nb_ + 1) >> 1;
 		if (na >= 0) return na;
 		if (nb_ >= 0) return nb_;

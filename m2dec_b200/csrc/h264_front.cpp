@@ -789,7 +789,6 @@ private:
 		int16_t mv[2];
 		ctx_.pskip_mv(mbx, mby, slice_num_, mv);
 		ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, ref_frame_of(0), mv[0], mv[1]);
-		ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
 		m.type = B2_H4_INTER;
 		set_mb_qp(m, pps);
 		emit_mc(m, 0, 0, 4, 4, 0, mv[0], mv[1]);
@@ -822,6 +821,7 @@ private:
 	int residual_block(int nc, int max_coeff, int16_t *out, const uint8_t *scan, int scan_ofs) {
 		const H264Tables &t = tables();
 		const Vlc &ct = nc < 0 ? t.coeff_token[4] : (nc < 2 ? t.coeff_token[0] : (nc < 4 ? t.coeff_token[1] : (nc < 8 ? t.coeff_token[2] : t.coeff_token[3])));
+		if (nc >= 0 && nc < 2 && br_.peek(1)) { br_.skip(1); return 0; }
 		int tok = ct.decode(br_);
 		if (tok == Vlc::INVALID) throw BitError();
 		int total = tok >> 2, t1 = tok & 3;
@@ -831,10 +831,11 @@ private:
 		for (int i = 0; i < t1; ++i) level[i] = br_.get1() ? -1 : 1;
 		int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
 		for (int i = t1; i < total; ++i) {
-			int prefix = 0;
-			while (br_.get1() == 0) {
-				if (++prefix > 32) throw BitError();
-			}
+			// level_prefix: count leading zeros, then the terminating one
+			uint32_t look = br_.peek(32);
+			if (!look) throw BitError();
+			int prefix = __builtin_clz(look);
+			br_.skip(prefix + 1);
 			int code = (prefix < 15 ? prefix : 15) << suffix_len;
 			int size = suffix_len;
 			if (prefix == 14 && suffix_len == 0) size = 4;
@@ -1031,7 +1032,6 @@ private:
 		m.type = B2_H4_INTER;
 		info.kind = MB_INTER;
 		memset(ctx_.ipred_of(mbx, mby), 2, 16);
-		ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
 		int nref = h.num_ref_idx_active[0];
 		auto read_ref = [&]() -> int {
 			if (nref <= 1) return 0;

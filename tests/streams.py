@@ -39,7 +39,17 @@ H264_REFERENCE_DEVIATES = {
 H264_GOLDEN = ["h264_basic", "h264_refs3", "h264_slices_dbk_mix", "h264_intra_ipcm", "h264_qp40_cqp", "h264_umv", "h264_constrained"]
 
 MPEG2_CASES = {
+    "mpeg2_ipb": "mbw=8 mbh=6 frames=7 seed=1",
+    "mpeg2_ip": "mbw=8 mbh=6 frames=10 seed=2 bframes=0",
+    "mpeg2_field": "mbw=10 mbh=7 frames=13 seed=3 field=1",
+    "mpeg2_b15_altscan": "mbw=6 mbh=5 frames=9 seed=4 intra_vlc=1 alt_scan=1",
+    "mpeg2_nonlinear_q": "mbw=6 mbh=5 frames=9 seed=5 q_scale_type=1 dc_precision=2 qscale=10",
+    "mpeg2_720x480": "mbw=45 mbh=30 frames=7 seed=6",
+    "mpeg2_b3_field_intra": "mbw=9 mbh=6 frames=12 seed=7 bframes=3 gop=6 field=1 intra_pct=30 skip_pct=30",
+    "mpeg2_crop": "mbw=8 mbh=6 frames=7 seed=8 width=120 height=90",
+    "mpeg2_2x2": "mbw=2 mbh=2 frames=7 seed=9",
 }
+MPEG2_GOLDEN = ["mpeg2_ipb", "mpeg2_field", "mpeg2_b15_altscan", "mpeg2_b3_field_intra", "mpeg2_crop"]
 
 
 def generate(codec, args):

@@ -122,3 +122,13 @@ def test_cuda_concurrent_streams():
             t.join()
         for n in names:
             assert got[n] == want[n], n
+
+
+@pytest.mark.gpu
+def test_cuda_1080p_baseline():
+    """BASELINE config 2: H.264 Baseline CAVLC 1920x1080 (coded 1920x1088, crop 8) I/P."""
+    import m2dec_b200
+    data = streams.generate("h264", "mbw=120 mbh=68 frames=6 seed=41 crop_bottom=8 refs=2")
+    gpu = m2dec_b200.decode_file("h264", data)
+    want = util.ref_md5(data, "264") if util.have_ref() else util.oracle_md5("h264", data)
+    assert len(gpu) == 6 and gpu == want
