@@ -94,15 +94,23 @@ typedef struct {
 	uint8_t i4_modes[8];    /* Intra4x4 (16 nibbles) / Intra8x8 (4 nibbles) prediction modes, block k in nibble k */
 } b2_h264_mb;               /* 32 bytes */
 
-/* One call of mb->inter_pred (h264.h:396; 14 call sites). */
+/* One call of mb->inter_pred (h264.h:396; 14 call sites), with the
+ * weighted-prediction parameters the call would have looked up resolved by the host
+ * (inter_pred_weighted1 / _weighted2, h264.cpp:6979-6999, 7101-7117):
+ *   one list : pred = ((p * w + 2^(logWD-1)) >> logWD) + o        (logWD = 0: p * w + o)
+ *   two lists: pred = ((p0*w0 + p1*w1 + 2^logWD) >> (logWD+1)) + ((o0 + o1 + 1) >> 1)
+ * Default prediction is w = 1, o = 0, logWD = 0; implicit bi-prediction is w0 + w1 = 64, logWD = 5.  */
 typedef struct {
 	uint8_t pos;            /* (y4 << 2) | x4: top-left 4x4 block of the partition inside the MB  */
 	uint8_t size;           /* (h4 << 4) | w4: partition size in 4-pel units (1, 2 or 4)          */
 	int8_t ref_frame[2];    /* frame-pool index for list 0 / 1 (refs[lx][ref_idx].frame_idx, h264.cpp:6740); -1 = list unused */
-	int8_t ref_idx[2];      /* reference index (selects explicit weights)                         */
-	uint8_t reserved[2];
+	int8_t ref_idx[2];      /* reference index per list (-1 unused)                               */
+	uint8_t log2wd_y, log2wd_c;
 	int16_t mv[2][2];       /* [list][x,y] quarter-pel                                            */
-} b2_h264_mc;               /* 16 bytes */
+	int8_t w[2][3];         /* [list][Y, Cb, Cr] weight                                           */
+	int8_t o[2][3];         /* [list][Y, Cb, Cr] offset                                           */
+	uint8_t reserved[4];
+} b2_h264_mc;               /* 32 bytes */
 
 /* b2_h264_dbk.flags */
 enum {

@@ -62,6 +62,31 @@ struct Neighbour {
 	int16_t mv[2];
 };
 
+// Reference picture marking + list construction state (clauses 8.2.4, 8.2.5), shared so the
+// writer can produce streams whose lists it knows.
+struct RefPic {
+	int frame_idx;     // frame-pool index
+	int frame_num;     // FrameNum
+	int long_idx;      // LongTermFrameIdx, -1 when short term
+	int poc;
+};
+
+// Motion of a decoded reference picture as direct prediction needs it (co-located picture, 8.4.1.2.1)
+struct ColBlk {
+	int8_t ref;        // reference index of the list the block used (list 0 preferred), -1 = intra
+	int8_t pad;
+	int16_t mv[2];
+	int32_t refpoc;    // POC of the picture that vector points to
+};
+struct ColPic {
+	std::vector<ColBlk> b;
+};
+// result of direct prediction for one macroblock, per 4x4 block in raster order
+struct DirectOut {
+	int ref[16][2];
+	int mv[16][2][2];
+};
+
 // Per-picture neighbour context.
 class PicCtx {
 public:
@@ -232,6 +257,92 @@ public:
 	inline MbInfo &info(int mbx, int mby) { return mb[(size_t)mby * mb_w + mbx]; }
 	inline const MbInfo &info(int mbx, int mby) const { return mb[(size_t)mby * mb_w + mbx]; }
 
+	// snapshot of this picture's motion, taken when it becomes a reference picture
+	template <class F>
+	void store_col(ColPic &c, F poc_of_frame) const {
+		c.b.resize((size_t)w4 * h4);
+		for (size_t g = 0; g < c.b.size(); ++g) {
+			ColBlk &o = c.b[g];
+			int l = ref[0][g] >= 0 ? 0 : (ref[1][g] >= 0 ? 1 : -1);
+			o.pad = 0;
+			if (l < 0) { o.ref = -1; o.mv[0] = o.mv[1] = 0; o.refpoc = 0; continue; }
+			o.ref = ref[l][g];
+			o.mv[0] = mv[l][g * 2];
+			o.mv[1] = mv[l][g * 2 + 1];
+			o.refpoc = poc_of_frame(refpic[l][g]);
+		}
+	}
+
+	static inline int min_positive(int a, int b) { return (a >= 0 && b >= 0) ? (a < b ? a : b) : (a > b ? a : b); }
+
+	// 8.4.1.2.2: spatial direct prediction of the whole macroblock (open_mb must have been called)
+	void direct_spatial(int mbx, int mby, int cur_slice, const ColPic *col, bool col_short_term, bool inference8x8,
+	                    DirectOut &out) const {
+		const int gx = mbx * 4, gy = mby * 4;
+		int refs[2];
+		int16_t mvp[2][2] = {{0, 0}, {0, 0}};
+		for (int l = 0; l < 2; ++l) {
+			Neighbour a = nb(l, gx - 1, gy, cur_slice), b = nb(l, gx, gy - 1, cur_slice), c = nb(l, gx + 4, gy - 1, cur_slice);
+			if (!c.avail) c = nb(l, gx - 1, gy - 1, cur_slice);
+			refs[l] = min_positive(a.avail ? a.ref : -1, min_positive(b.avail ? b.ref : -1, c.avail ? c.ref : -1));
+		}
+		bool zero = false;
+		if (refs[0] < 0 && refs[1] < 0) { refs[0] = refs[1] = 0; zero = true; }
+		else
+			for (int l = 0; l < 2; ++l)
+				if (refs[l] >= 0) predict_mv(l, mbx, mby, 0, 0, 4, refs[l], cur_slice, 0, 0, mvp[l]);
+		for (int y = 0; y < 4; ++y)
+			for (int x = 0; x < 4; ++x) {
+				int cx = inference8x8 ? (x >> 1) * 3 : x, cy = inference8x8 ? (y >> 1) * 3 : y;
+				bool col_zero = false;
+				if (col && col_short_term && !col->b.empty()) {
+					const ColBlk &cb = col->b[(size_t)(gy + cy) * w4 + gx + cx];
+					col_zero = cb.ref == 0 && cb.mv[0] >= -1 && cb.mv[0] <= 1 && cb.mv[1] >= -1 && cb.mv[1] <= 1;
+				}
+				for (int l = 0; l < 2; ++l) {
+					out.ref[y * 4 + x][l] = refs[l];
+					bool z = zero || refs[l] < 0 || (refs[l] == 0 && col_zero);
+					out.mv[y * 4 + x][l][0] = z ? 0 : mvp[l][0];
+					out.mv[y * 4 + x][l][1] = z ? 0 : mvp[l][1];
+				}
+			}
+	}
+
+	// 8.4.1.2.3: temporal direct prediction
+	void direct_temporal(int mbx, int mby, const ColPic *col, bool inference8x8, const RefPic *l0, int n0, const RefPic *l1,
+	                     int cur_poc, DirectOut &out) const {
+		const int gx = mbx * 4, gy = mby * 4;
+		for (int y = 0; y < 4; ++y)
+			for (int x = 0; x < 4; ++x) {
+				int cx = inference8x8 ? (x >> 1) * 3 : x, cy = inference8x8 ? (y >> 1) * 3 : y;
+				int i = y * 4 + x;
+				out.ref[i][0] = 0; out.ref[i][1] = 0;
+				out.mv[i][0][0] = out.mv[i][0][1] = out.mv[i][1][0] = out.mv[i][1][1] = 0;
+				if (!col || col->b.empty()) continue;
+				const ColBlk &cb = col->b[(size_t)(gy + cy) * w4 + gx + cx];
+				if (cb.ref < 0) continue;
+				int r0 = 0;
+				for (int k = 0; k < n0; ++k)
+					if (l0[k].frame_idx >= 0 && l0[k].poc == cb.refpoc) { r0 = k; break; }
+				out.ref[i][0] = r0;
+				int td = l1[0].poc - l0[r0].poc, tb = cur_poc - l0[r0].poc;
+				td = td < -128 ? -128 : (td > 127 ? 127 : td);
+				tb = tb < -128 ? -128 : (tb > 127 ? 127 : tb);
+				if (l0[r0].long_idx >= 0 || td == 0) {
+					out.mv[i][0][0] = cb.mv[0]; out.mv[i][0][1] = cb.mv[1];
+				} else {
+					int tx = (16384 + (td < 0 ? -td : td) / 2) / td;
+					int dsf = (tb * tx + 32) >> 6;
+					dsf = dsf < -1024 ? -1024 : (dsf > 1023 ? 1023 : dsf);
+					for (int k = 0; k < 2; ++k) {
+						int m0 = (dsf * cb.mv[k] + 128) >> 8;
+						out.mv[i][0][k] = m0;
+						out.mv[i][1][k] = m0 - cb.mv[k];
+					}
+				}
+			}
+	}
+
 	// 8.3.1.1: predIntra4x4PredMode for the 4x4 block at raster (x4, y4) of the current MB.
 	// constrained: constrained_intra_pred_flag (inter neighbours then count as unavailable).
 	int predict_ipred(int mbx, int mby, int x4, int y4, int cur_slice, bool constrained) const {
@@ -254,13 +365,5 @@ public:
 	}
 };
 
-// Reference picture marking + list construction state (clauses 8.2.4, 8.2.5), shared so the
-// writer can produce streams whose lists it knows.
-struct RefPic {
-	int frame_idx;     // frame-pool index
-	int frame_num;     // FrameNum
-	int long_idx;      // LongTermFrameIdx, -1 when short term
-	int poc;
-};
 
 }}  // namespace b2::h4

@@ -135,6 +135,7 @@ struct SliceHeader {
 	int nal_ref_idc;
 	int poc;
 	int num_ref_idx_active[2];
+	bool direct_spatial;
 	int qp;
 	int disable_deblock, alpha_off, beta_off;
 	// dec_ref_pic_marking
@@ -434,8 +435,8 @@ private:
 		const Pps &pps = pps_[pps_id];
 		const Sps &sps = sps_[pps.sps_id];
 		if (!sps.valid) return -1;
-		if (pps.cabac || st == SLICE_B || pps.transform_8x8 || !sps.frame_mbs_only) {
-			fprintf(stderr, "m2dec_b200: H.264 feature outside this revision (CABAC / B slices / 8x8 transform / interlace)\n");
+		if (pps.cabac || pps.transform_8x8 || !sps.frame_mbs_only) {
+			fprintf(stderr, "m2dec_b200: H.264 feature outside this revision (CABAC / 8x8 transform / interlace)\n");
 			unsupported_ = true;
 			return -3;
 		}
@@ -465,15 +466,18 @@ private:
 		if (pps.redundant_pic_cnt) br_.ue();
 		h.num_ref_idx_active[0] = pps.num_ref_idx_active[0];
 		h.num_ref_idx_active[1] = pps.num_ref_idx_active[1];
-		if (st == SLICE_P) {
-			if (br_.get1()) h.num_ref_idx_active[0] = br_.ue() + 1;
-			if (h.num_ref_idx_active[0] > 32) return -1;
-			build_list_p(sps, h);
-			if (pps.weighted_pred) {
-				fprintf(stderr, "m2dec_b200: weighted prediction is outside this revision\n");
-				unsupported_ = true;
-				return -3;
+		h.direct_spatial = true;
+		wt_.mode = 0;
+		if (st == SLICE_B) h.direct_spatial = br_.get1() != 0;
+		if (st != SLICE_I) {
+			if (br_.get1()) {
+				h.num_ref_idx_active[0] = br_.ue() + 1;
+				if (st == SLICE_B) h.num_ref_idx_active[1] = br_.ue() + 1;
 			}
+			if (h.num_ref_idx_active[0] > 32 || h.num_ref_idx_active[1] > 32) return -1;
+			build_lists(sps, h, st == SLICE_B);
+			if ((st == SLICE_P && pps.weighted_pred) || (st == SLICE_B && pps.weighted_bipred_idc == 1)) pred_weight_table(h, st == SLICE_B);
+			else if (st == SLICE_B && pps.weighted_bipred_idc == 2) wt_.mode = 2;
 		}
 		h.adaptive_marking = false;
 		h.long_term_reference_flag = false;
@@ -512,6 +516,8 @@ private:
 		}
 		if (br_.overrun()) throw BitError();
 		slice_num_++;
+		bslice_ = st == SLICE_B;
+		direct_8x8_inference_ = sps.direct_8x8_inference != 0;
 		slice_data(sps, pps);
 		// picture end (h264.cpp:11022-11050)
 		if (mb_addr_ >= mb_w_ * mb_h_) {
@@ -558,51 +564,99 @@ private:
 		}
 	}
 
-	// initial P list (8.2.4.2.1) + modification (8.2.4.3), restricted to short-term pictures and
-	// long-term pictures addressed by LongTermPicNum
-	void build_list_p(const Sps &sps, SliceHeader &h) {
-		int max_fn = 1 << sps.log2_max_frame_num;
+	// initial lists (8.2.4.2.1 P, 8.2.4.2.3 B) + modification (8.2.4.3)
+	void build_lists(const Sps &sps, SliceHeader &h, bool bslice) {
+		const int max_fn = 1 << sps.log2_max_frame_num;
 		std::vector<RefPic> st, lt;
 		for (const RefPic &r : refs_) (r.long_idx < 0 ? st : lt).push_back(r);
 		auto picnum = [&](const RefPic &r) { return r.frame_num > h.frame_num ? r.frame_num - max_fn : r.frame_num; };
-		std::sort(st.begin(), st.end(), [&](const RefPic &a, const RefPic &b) { return picnum(a) > picnum(b); });
 		std::sort(lt.begin(), lt.end(), [](const RefPic &a, const RefPic &b) { return a.long_idx < b.long_idx; });
-		std::vector<RefPic> list(st);
-		list.insert(list.end(), lt.begin(), lt.end());
-		int n = h.num_ref_idx_active[0];
-		RefPic none = {-1, -1, -1, 0};
-		if ((int)list.size() > n) list.resize(n);
-		while ((int)list.size() < n) list.push_back(list.empty() ? none : none);
-		if (br_.get1()) {   // ref_pic_list_modification_flag_l0
-			int pred = h.frame_num, idx = 0;
-			for (;;) {
-				unsigned op = br_.ue();
-				if (op == 3) break;
-				if (op > 3 || idx >= n) throw BitError();
-				unsigned v = br_.ue();
-				RefPic target = none;
-				if (op < 2) {
-					int d = (int)v + 1;
-					pred = op == 0 ? pred - d : pred + d;
-					if (pred < 0) pred += max_fn;
-					if (pred >= max_fn) pred -= max_fn;
-					int pn = pred > h.frame_num ? pred - max_fn : pred;
-					for (const RefPic &r : st) if (picnum(r) == pn) target = r;
-				} else {
-					for (const RefPic &r : lt) if (r.long_idx == (int)v) target = r;
-				}
-				list.insert(list.begin() + idx, target);
-				idx++;
-				int w = idx;
-				for (int k = idx; k < (int)list.size(); ++k) {
-					bool same = list[k].frame_idx == target.frame_idx && target.frame_idx >= 0;
-					if (!same) list[w++] = list[k];
-				}
-				list.resize(w);
-				list.resize(n, none);
+		const RefPic none = {-1, -1, -1, 0};
+		for (int lx = 0; lx < (bslice ? 2 : 1); ++lx) {
+			std::vector<RefPic> list;
+			if (!bslice) {
+				list = st;
+				std::sort(list.begin(), list.end(), [&](const RefPic &a, const RefPic &b) { return picnum(a) > picnum(b); });
+			} else {
+				std::vector<RefPic> before, after;
+				for (const RefPic &r : st) (r.poc < cur_poc_ ? before : after).push_back(r);
+				std::sort(before.begin(), before.end(), [](const RefPic &a, const RefPic &b) { return a.poc > b.poc; });
+				std::sort(after.begin(), after.end(), [](const RefPic &a, const RefPic &b) { return a.poc < b.poc; });
+				if (lx == 0) { list = before; list.insert(list.end(), after.begin(), after.end()); }
+				else { list = after; list.insert(list.end(), before.begin(), before.end()); }
 			}
+			list.insert(list.end(), lt.begin(), lt.end());
+			if (lx == 1 && list.size() > 1 && init0_.size() == list.size()) {
+				// identical initial lists: the first two entries of list 1 are switched (8.2.4.2.3)
+				bool same = true;
+				for (size_t i = 0; i < list.size(); ++i) same &= init0_[i].frame_idx == list[i].frame_idx;
+				if (same) std::swap(list[0], list[1]);
+			}
+			if (lx == 0) init0_ = list;
+			const int n = h.num_ref_idx_active[lx];
+			if ((int)list.size() > n) list.resize(n);
+			list.resize(n, none);
+			if (br_.get1()) {   // ref_pic_list_modification_flag_lX
+				int pred = h.frame_num, idx = 0;
+				for (;;) {
+					unsigned op = br_.ue();
+					if (op == 3) break;
+					if (op > 3 || idx >= n) throw BitError();
+					unsigned v = br_.ue();
+					RefPic target = none;
+					if (op < 2) {
+						int d = (int)v + 1;
+						pred = op == 0 ? pred - d : pred + d;
+						if (pred < 0) pred += max_fn;
+						if (pred >= max_fn) pred -= max_fn;
+						int pn = pred > h.frame_num ? pred - max_fn : pred;
+						for (const RefPic &r : st) if (picnum(r) == pn) target = r;
+					} else {
+						for (const RefPic &r : lt) if (r.long_idx == (int)v) target = r;
+					}
+					list.insert(list.begin() + idx, target);
+					idx++;
+					int w = idx;
+					for (int k = idx; k < (int)list.size(); ++k) {
+						bool same = list[k].frame_idx == target.frame_idx && target.frame_idx >= 0;
+						if (!same) list[w++] = list[k];
+					}
+					list.resize(w);
+					list.resize(n, none);
+				}
+			}
+			list_[lx] = list;
 		}
-		list0_ = list;
+		if (!bslice) list_[1].clear();
+	}
+
+	// pred_weight_table (7.3.3.2; reference h264.cpp:1668-1695): weights are int8 in the reference too
+	void pred_weight_table(SliceHeader &h, bool bslice) {
+		wt_.mode = 1;
+		wt_.denom[0] = (int)br_.ue();
+		wt_.denom[1] = (int)br_.ue();
+		if (wt_.denom[0] > 7 || wt_.denom[1] > 7) throw BitError();
+		for (int lx = 0; lx < (bslice ? 2 : 1); ++lx)
+			for (int i = 0; i < h.num_ref_idx_active[lx]; ++i) {
+				int8_t *w = wt_.w[lx][i], *o = wt_.o[lx][i];
+				if (br_.get1()) { w[0] = (int8_t)br_.se(); o[0] = (int8_t)br_.se(); }
+				else { w[0] = (int8_t)(1 << wt_.denom[0]); o[0] = 0; }
+				if (br_.get1()) {
+					for (int c = 1; c < 3; ++c) { w[c] = (int8_t)br_.se(); o[c] = (int8_t)br_.se(); }
+				} else {
+					w[1] = w[2] = (int8_t)(1 << wt_.denom[1]);
+					o[1] = o[2] = 0;
+				}
+			}
+	}
+
+	static int dist_scale_factor(int poc0, int poc1, int cur) {
+		if (poc1 == poc0) return 256;
+		int td = poc1 - poc0, tb = cur - poc0;
+		td = td < -128 ? -128 : (td > 127 ? 127 : td);
+		tb = tb < -128 ? -128 : (tb > 127 ? 127 : tb);
+		int tx = (16384 + abs(td / 2)) / td;
+		return (tb * tx + 32) >> 6;
 	}
 
 	// ---- picture begin / end ------------------------------------------------------------------
@@ -655,6 +709,7 @@ private:
 		// reference marking (8.2.5) and DPB insertion (h264.cpp:10840-10873, 11036-11045)
 		int max_fn = 1 << sps.log2_max_frame_num;
 		bool mmco5 = false;
+		if (h.nal_ref_idc) ctx_.store_col(col_[cur_frame_], [&](int f) { return f >= 0 ? (int)frames_[f].cnt : 0; });
 		if (h.nal_ref_idc) {
 			if (h.idr) {
 				refs_.clear();
@@ -761,43 +816,112 @@ private:
 		m.mc_idx = (uint32_t)mcs_.size();
 	}
 
-	void emit_mc(b2_h264_mb &m, int x4, int y4, int pw, int ph, int refidx, int mvx, int mvy) {
+	int ref_frame_of(int lx, int refidx) const {
+		if (refidx < 0 || refidx >= (int)list_[lx].size()) return -1;
+		return list_[lx][refidx].frame_idx;
+	}
+
+	// one mb->inter_pred call: ref[lx] < 0 = list unused
+	void emit_mc(b2_h264_mb &m, int x4, int y4, int pw, int ph, const int ref[2], const int mv[2][2]) {
 		b2_h264_mc r;
 		memset(&r, 0, sizeof(r));
 		r.pos = (uint8_t)((y4 << 2) | x4);
 		r.size = (uint8_t)((ph << 4) | pw);
-		const RefPic &rp = list0_[refidx < (int)list0_.size() ? refidx : 0];
-		r.ref_frame[0] = (int8_t)(rp.frame_idx < 0 ? cur_frame_ : rp.frame_idx);
-		r.ref_frame[1] = -1;
-		r.ref_idx[0] = (int8_t)refidx;
-		r.ref_idx[1] = -1;
-		r.mv[0][0] = (int16_t)mvx;
-		r.mv[0][1] = (int16_t)mvy;
+		for (int lx = 0; lx < 2; ++lx) {
+			r.ref_idx[lx] = (int8_t)ref[lx];
+			r.ref_frame[lx] = -1;
+			for (int c = 0; c < 3; ++c) { r.w[lx][c] = 1; r.o[lx][c] = 0; }
+			if (ref[lx] < 0) continue;
+			int f = ref_frame_of(lx, ref[lx]);
+			r.ref_frame[lx] = (int8_t)(f < 0 ? cur_frame_ : f);
+			r.mv[lx][0] = (int16_t)mv[lx][0];
+			r.mv[lx][1] = (int16_t)mv[lx][1];
+		}
+		const bool bi = ref[0] >= 0 && ref[1] >= 0;
+		if (wt_.mode == 1) {
+			r.log2wd_y = (uint8_t)wt_.denom[0];
+			r.log2wd_c = (uint8_t)wt_.denom[1];
+			for (int lx = 0; lx < 2; ++lx)
+				if (ref[lx] >= 0)
+					for (int c = 0; c < 3; ++c) { r.w[lx][c] = wt_.w[lx][ref[lx] & 31][c]; r.o[lx][c] = wt_.o[lx][ref[lx] & 31][c]; }
+		} else if (wt_.mode == 2 && bi) {
+			// implicit weights (8.4.2.3.1; pred_weight_type2, h264.cpp:7001-7025)
+			const RefPic &r0 = list_[0][ref[0]], &r1 = list_[1][ref[1]];
+			int w0 = 32, w1 = 32;
+			if (r0.poc != r1.poc && r0.long_idx < 0 && r1.long_idx < 0 && r0.frame_idx >= 0 && r1.frame_idx >= 0) {
+				int t = dist_scale_factor(r0.poc, r1.poc, cur_poc_) >> 2;
+				if (t >= -64 && t <= 128) { w1 = t; w0 = 64 - t; }
+			}
+			r.log2wd_y = r.log2wd_c = 5;
+			for (int c = 0; c < 3; ++c) { r.w[0][c] = (int8_t)w0; r.w[1][c] = (int8_t)w1; }
+		}
 		mcs_.push_back(r);
 		m.mc_cnt++;
 	}
-
-	int ref_frame_of(int refidx) const {
-		if (refidx < 0 || refidx >= (int)list0_.size()) return -1;
-		return list0_[refidx].frame_idx;
+	void emit_mc_p(b2_h264_mb &m, int x4, int y4, int pw, int ph, int refidx, int mvx, int mvy) {
+		const int ref[2] = {refidx, -1};
+		const int mv[2][2] = {{mvx, mvy}, {0, 0}};
+		emit_mc(m, x4, y4, pw, ph, ref, mv);
 	}
 
 	void skip_mb(const Pps &pps) {
 		int mbx = mb_addr_ % mb_w_, mby = mb_addr_ / mb_w_;
 		open_mb(mbx, mby);
 		b2_h264_mb &m = mbs_[mb_addr_];
-		int16_t mv[2];
-		ctx_.pskip_mv(mbx, mby, slice_num_, mv);
-		ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, ref_frame_of(0), mv[0], mv[1]);
 		m.type = B2_H4_INTER;
 		set_mb_qp(m, pps);
-		emit_mc(m, 0, 0, 4, 4, 0, mv[0], mv[1]);
+		if (hdr_.type == SLICE_B) {
+			DirectOut d;
+			derive_direct(mbx, mby, d);
+			apply_direct(m, mbx, mby, d, 0xf);
+		} else {
+			int16_t mv[2];
+			ctx_.pskip_mv(mbx, mby, slice_num_, mv);
+			ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, ref_frame_of(0, 0), mv[0], mv[1]);
+			emit_mc_p(m, 0, 0, 4, 4, 0, mv[0], mv[1]);
+		}
 		MbInfo &info = ctx_.info(mbx, mby);
 		info.kind = MB_SKIP;
 		info.qp_y = (uint8_t)qp_;
 		info.cbp = 0;
 		memset(ctx_.nnz_of(mbx, mby), 0, 24);
 		finish_mb(mbx, mby, pps, qp_);
+	}
+
+	// ---- direct prediction (B_Skip, B_Direct_16x16, direct 8x8 sub-macroblocks) ------------------
+	void derive_direct(int mbx, int mby, DirectOut &d) {
+		const RefPic &c1 = list_[1].empty() ? RefPic{-1, -1, -1, 0} : list_[1][0];
+		const ColPic *col = c1.frame_idx >= 0 ? &col_[c1.frame_idx] : nullptr;
+		if (hdr_.direct_spatial) ctx_.direct_spatial(mbx, mby, slice_num_, col, c1.long_idx < 0, direct_8x8_inference_, d);
+		else ctx_.direct_temporal(mbx, mby, col, direct_8x8_inference_, list_[0].data(), (int)list_[0].size(), list_[1].data(), cur_poc_, d);
+	}
+
+	// store the motion of the direct-predicted 8x8 quadrants in `quads` and emit their MC records
+	void apply_direct(b2_h264_mb &m, int mbx, int mby, const DirectOut &d, int quads) {
+		// one record for the whole MB when every block got the same motion (the common case)
+		if (quads == 0xf) {
+			bool same = true;
+			for (int i = 1; i < 16 && same; ++i)
+				same = memcmp(d.ref[i], d.ref[0], sizeof(d.ref[0])) == 0 && memcmp(d.mv[i], d.mv[0], sizeof(d.mv[0])) == 0;
+			if (same) {
+				for (int l = 0; l < 2; ++l)
+					ctx_.set_motion(l, mbx, mby, 0, 0, 4, 4, d.ref[0][l], ref_frame_of(l, d.ref[0][l]), d.mv[0][l][0], d.mv[0][l][1]);
+				emit_mc(m, 0, 0, 4, 4, d.ref[0], d.mv[0]);
+				return;
+			}
+		}
+		for (int q = 0; q < 4; ++q) {
+			if (!((quads >> q) & 1)) continue;
+			const int bx = (q & 1) * 2, by = (q >> 1) * 2;
+			const int step = direct_8x8_inference_ ? 2 : 1;
+			for (int y = by; y < by + 2; y += step)
+				for (int x = bx; x < bx + 2; x += step) {
+					const int i = y * 4 + x;
+					for (int l = 0; l < 2; ++l)
+						ctx_.set_motion(l, mbx, mby, x, y, step, step, d.ref[i][l], ref_frame_of(l, d.ref[i][l]), d.mv[i][l][0], d.mv[i][l][1]);
+					emit_mc(m, x, y, step, step, d.ref[i], d.mv[i]);
+				}
+		}
 	}
 
 	void set_mb_qp(b2_h264_mb &m, const Pps &pps) {
@@ -934,6 +1058,9 @@ private:
 		if (h.type == SLICE_P) {
 			if (mb_type >= 5) mb_type -= 5;          // intra types follow the five P types
 			else { inter_mb(m, mbx, mby, mb_type, pps); return; }
+		} else if (h.type == SLICE_B) {
+			if (mb_type >= 23) mb_type -= 23;        // intra types follow the 23 B types
+			else { b_mb(m, mbx, mby, mb_type, pps); return; }
 		}
 		if (mb_type > 25) throw BitError();
 		int avail = ctx_.mb_avail_mask(mbx, mby, slice_num_);
@@ -1044,8 +1171,8 @@ private:
 			ctx_.predict_mv(0, mbx, mby, x4, y4, pw, ref, slice_num_, shape, part, pred);
 			int mvx = pred[0] + br_.se();
 			int mvy = pred[1] + br_.se();
-			ctx_.set_motion(0, mbx, mby, x4, y4, pw, ph, ref, ref_frame_of(ref), mvx, mvy);
-			emit_mc(m, x4, y4, pw, ph, ref, mvx, mvy);
+			ctx_.set_motion(0, mbx, mby, x4, y4, pw, ph, ref, ref_frame_of(0, ref), mvx, mvy);
+			emit_mc_p(m, x4, y4, pw, ph, ref, mvx, mvy);
 		};
 		if (mb_type == 0) {
 			int r = read_ref();
@@ -1089,14 +1216,149 @@ private:
 		finish_mb(mbx, mby, pps, qp_);
 	}
 
+	// B macroblock (7.3.5.1, 7.3.5.2; Tables 7-14, 7-18)
+	void b_mb(b2_h264_mb &m, int mbx, int mby, int mb_type, const Pps &pps) {
+		const SliceHeader &h = hdr_;
+		MbInfo &info = ctx_.info(mbx, mby);
+		m.type = B2_H4_INTER;
+		info.kind = MB_INTER;
+		memset(ctx_.ipred_of(mbx, mby), 2, 16);
+		struct Part { int8_t x4, y4, pw, ph, shape, part, use, sub; };   // use: 0 direct, 1 L0, 2 L1, 3 Bi
+		Part parts[16];
+		int np = 0;
+		int sub_use[4] = {0, 0, 0, 0};
+		DirectOut dir;
+		int direct_quads = 0;
+		if (mb_type == 0) {
+			direct_quads = 0xf;
+		} else if (mb_type < 22) {
+			// 1..3: 16x16 L0/L1/Bi; 4..21: pairs (16x8, 8x16) with the prediction modes of Table 7-14
+			static const uint8_t modes[22][2] = {{0, 0}, {1, 0}, {2, 0}, {3, 0}, {1, 1}, {1, 1}, {2, 2}, {2, 2}, {1, 2}, {1, 2}, {2, 1}, {2, 1},
+			                                     {1, 3}, {1, 3}, {2, 3}, {2, 3}, {3, 1}, {3, 1}, {3, 2}, {3, 2}, {3, 3}, {3, 3}};
+			if (mb_type <= 3) parts[np++] = Part{0, 0, 4, 4, 0, 0, (int8_t)modes[mb_type][0], 0};
+			else if (mb_type & 1) {   // odd: 8x16
+				parts[np++] = Part{0, 0, 2, 4, 2, 0, (int8_t)modes[mb_type][0], 0};
+				parts[np++] = Part{2, 0, 2, 4, 2, 1, (int8_t)modes[mb_type][1], 1};
+			} else {                  // even: 16x8
+				parts[np++] = Part{0, 0, 4, 2, 1, 0, (int8_t)modes[mb_type][0], 0};
+				parts[np++] = Part{0, 2, 4, 2, 1, 1, (int8_t)modes[mb_type][1], 1};
+			}
+			sub_use[0] = parts[0].use;
+			if (np > 1) sub_use[1] = parts[1].use;
+		} else {
+			// B_8x8: sub_mb_type per quadrant (Table 7-18)
+			static const uint8_t sub_mode[13] = {0, 1, 2, 3, 1, 1, 2, 2, 3, 3, 1, 2, 3};
+			static const uint8_t sub_shape[13] = {0, 0, 0, 0, 1, 2, 1, 2, 1, 2, 3, 3, 3};   // 0 8x8, 1 8x4, 2 4x8, 3 4x4
+			for (int q = 0; q < 4; ++q) {
+				unsigned st = br_.ue();
+				if (st > 12) throw BitError();
+				int bx = (q & 1) * 2, by = (q >> 1) * 2, use = sub_mode[st];
+				sub_use[q] = use;
+				if (use == 0) { direct_quads |= 1 << q; parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 2, 0, 0, 0, (int8_t)q}; continue; }
+				switch (sub_shape[st]) {
+				case 0: parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 2, 0, 0, (int8_t)use, (int8_t)q}; break;
+				case 1: parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 1, 0, 0, (int8_t)use, (int8_t)q};
+				        parts[np++] = Part{(int8_t)bx, (int8_t)(by + 1), 2, 1, 0, 0, (int8_t)use, (int8_t)q}; break;
+				case 2: parts[np++] = Part{(int8_t)bx, (int8_t)by, 1, 2, 0, 0, (int8_t)use, (int8_t)q};
+				        parts[np++] = Part{(int8_t)(bx + 1), (int8_t)by, 1, 2, 0, 0, (int8_t)use, (int8_t)q}; break;
+				default:
+					for (int k = 0; k < 4; ++k) parts[np++] = Part{(int8_t)(bx + (k & 1)), (int8_t)(by + (k >> 1)), 1, 1, 0, 0, (int8_t)use, (int8_t)q};
+					break;
+				}
+			}
+		}
+		if (direct_quads) derive_direct(mbx, mby, dir);
+		// reference indices: list 0 for every (sub-)macroblock partition that uses it, then list 1
+		int ref[4][2];
+		const int nsub = mb_type == 22 ? 4 : (mb_type == 0 ? 0 : (mb_type <= 3 ? 1 : 2));
+		for (int q = 0; q < 4; ++q) ref[q][0] = ref[q][1] = -1;
+		for (int l = 0; l < 2; ++l) {
+			const int nref = h.num_ref_idx_active[l];
+			for (int q = 0; q < nsub; ++q) {
+				if (!(sub_use[q] & (1 << l))) continue;
+				int r = 0;
+				if (nref > 1) {
+					r = nref == 2 ? (int)(br_.get1() ^ 1) : (int)br_.ue();
+					if (r >= nref) throw BitError();
+				}
+				ref[q][l] = r;
+			}
+		}
+		// motion vector differences: list 0 for all partitions in order, then list 1
+		int pmv[16][2][2];
+		memset(pmv, 0, sizeof(pmv));
+		for (int l = 0; l < 2; ++l) {
+			for (int i = 0; i < np; ++i) {
+				const Part &p = parts[i];
+				if (p.use == 0) {
+					// direct sub-macroblock: motion was derived, make it visible to later predictions
+					const int step = direct_8x8_inference_ ? 2 : 1;
+					for (int y = p.y4; y < p.y4 + 2; y += step)
+						for (int x = p.x4; x < p.x4 + 2; x += step) {
+							const int k = y * 4 + x;
+							ctx_.set_motion(l, mbx, mby, x, y, step, step, dir.ref[k][l], ref_frame_of(l, dir.ref[k][l]), dir.mv[k][l][0], dir.mv[k][l][1]);
+						}
+					continue;
+				}
+				if (!(p.use & (1 << l))) { ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, -1, -1, 0, 0); continue; }
+				int16_t pred[2];
+				const int r = ref[p.sub][l];
+				ctx_.predict_mv(l, mbx, mby, p.x4, p.y4, p.pw, r, slice_num_, p.shape, p.part, pred);
+				pmv[i][l][0] = pred[0] + br_.se();
+				pmv[i][l][1] = pred[1] + br_.se();
+				ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, r, ref_frame_of(l, r), pmv[i][l][0], pmv[i][l][1]);
+			}
+		}
+		if (mb_type == 0) {
+			apply_direct(m, mbx, mby, dir, 0xf);
+		} else {
+			for (int i = 0; i < np; ++i) {
+				const Part &p = parts[i];
+				if (p.use == 0) {
+					// records of a direct quadrant (motion already stored above)
+					const int step = direct_8x8_inference_ ? 2 : 1;
+					for (int y = p.y4; y < p.y4 + 2; y += step)
+						for (int x = p.x4; x < p.x4 + 2; x += step) emit_mc(m, x, y, step, step, dir.ref[y * 4 + x], dir.mv[y * 4 + x]);
+					continue;
+				}
+				const int rr[2] = {(p.use & 1) ? ref[p.sub][0] : -1, (p.use & 2) ? ref[p.sub][1] : -1};
+				emit_mc(m, p.x4, p.y4, p.pw, p.ph, rr, pmv[i]);
+			}
+		}
+		unsigned code = br_.ue();
+		if (code > 47) throw BitError();
+		int cbp = cbp_from_code[1][code];
+		if (cbp) read_qp_delta();
+		set_mb_qp(m, pps);
+		residual_luma(m, mbx, mby, cbp & 15, false);
+		residual_chroma(m, mbx, mby, cbp >> 4);
+		info.qp_y = (uint8_t)qp_;
+		info.cbp = (uint8_t)cbp;
+		finish_mb(mbx, mby, pps, qp_);
+	}
+
 	// ---- deblocking strengths (8.7.2.1) for the MB just parsed ------------------------------------
 	// bS of an inter/inter 4x4 block pair: 2 if either block has coefficients, else 1 if the
 	// reference pictures differ or a motion vector component differs by >= 4 quarter samples
+	static inline bool mv_far(const int16_t *a, const int16_t *b) {
+		return (unsigned)(a[0] - b[0] + 3) > 6u || (unsigned)(a[1] - b[1] + 3) > 6u;
+	}
 	inline int bs_inter(size_t g0, size_t g1, bool nz0, bool nz1) const {
 		if (nz0 | nz1) return 2;
-		if (ctx_.refpic[0][g0] != ctx_.refpic[0][g1]) return 1;
-		const int16_t *a = &ctx_.mv[0][g0 * 2], *b = &ctx_.mv[0][g1 * 2];
-		return ((unsigned)(a[0] - b[0] + 3) > 6u || (unsigned)(a[1] - b[1] + 3) > 6u) ? 1 : 0;
+		const int a0 = ctx_.refpic[0][g0], b0 = ctx_.refpic[0][g1];
+		const int16_t *ma0 = &ctx_.mv[0][g0 * 2], *mb0 = &ctx_.mv[0][g1 * 2];
+		if (!bslice_) return (a0 != b0 || mv_far(ma0, mb0)) ? 1 : 0;
+		// two lists: different pictures or number of vectors -> 1; same pictures -> compare the vectors
+		// that point to the same picture (8.7.2.1)
+		const int a1 = ctx_.refpic[1][g0], b1 = ctx_.refpic[1][g1];
+		const int16_t *ma1 = &ctx_.mv[1][g0 * 2], *mb1 = &ctx_.mv[1][g1 * 2];
+		if (!((a0 == b0 && a1 == b1) || (a0 == b1 && a1 == b0))) return 1;
+		if (a0 != a1) {
+			if (a0 == b0) return ((a0 >= 0 && mv_far(ma0, mb0)) || (a1 >= 0 && mv_far(ma1, mb1))) ? 1 : 0;
+			return ((a0 >= 0 && mv_far(ma0, mb1)) || (a1 >= 0 && mv_far(ma1, mb0))) ? 1 : 0;
+		}
+		bool straight = mv_far(ma0, mb0) || mv_far(ma1, mb1), cross = mv_far(ma0, mb1) || mv_far(ma1, mb0);
+		return (straight && cross) ? 1 : 0;
 	}
 
 	void finish_mb(int mbx, int mby, const Pps &pps, int dbk_qp) {
@@ -1135,7 +1397,13 @@ private:
 			const size_t g00 = (size_t)mby * 4 * w4 + (size_t)mbx * 4;
 			unsigned nzm = 0;
 			for (int i = 0; i < 16; ++i) nzm |= (unsigned)(nnz[i] != 0) << i;
-			if (mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt == 1) {
+			if (bslice_ && mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt != 1) {
+				for (int e = 1; e < 4; ++e)
+					for (int sg = 0; sg < 4; ++sg) {
+						bsv |= (uint32_t)bs_inter(g00 + sg * w4 + e - 1, g00 + sg * w4 + e, (nzm >> (sg * 4 + e - 1)) & 1, (nzm >> (sg * 4 + e)) & 1) << (e * 8 + sg * 2);
+						bsh |= (uint32_t)bs_inter(g00 + (e - 1) * w4 + sg, g00 + e * w4 + sg, (nzm >> ((e - 1) * 4 + sg)) & 1, (nzm >> (e * 4 + sg)) & 1) << (e * 8 + sg * 2);
+					}
+			} else if (mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt == 1) {
 				// one partition: no motion discontinuity inside the macroblock
 				for (int e = 1; e < 4; ++e)
 					for (int sg = 0; sg < 4; ++sg) {
@@ -1207,7 +1475,10 @@ private:
 	bool pic_open_;
 	uint32_t prev_first_mb_;
 	std::vector<RefPic> refs_;       // pictures marked "used for reference"
-	std::vector<RefPic> list0_;
+	std::vector<RefPic> list_[2], init0_;
+	ColPic col_[MAX_H264_FRAMES];
+	bool bslice_ = false, direct_8x8_inference_ = true;
+	struct { int mode, denom[2]; int8_t w[2][32][3], o[2][32][3]; } wt_;   // mode 0 default, 1 explicit, 2 implicit
 	int prev_frame_num_, poc_lsb_, poc_msb_, frame_num_offset_, cur_poc_;
 	bool prev_mmco5_;
 	bool unsupported_;

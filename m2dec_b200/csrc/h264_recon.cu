@@ -313,10 +313,11 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 				int sel = 0, mvx = 0, mvy = 0;
 				for (int i = 0; i < cnt; ++i) {
 					int4 raw = __ldg(reinterpret_cast<const int4 *>(rec + i));
-					const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);
+					const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);   // first 16 bytes: pos .. mv
 					int px0 = mc.pos & 3, py0 = mc.pos >> 2;
 					if (x4 >= px0 && x4 < px0 + (mc.size & 15) && y4 >= py0 && y4 < py0 + (mc.size >> 4)) {
-						sel = i; mvx = mc.mv[0][0]; mvy = mc.mv[0][1];
+						const int l = mc.ref_frame[0] >= 0 ? 0 : 1;
+						sel = i; mvx = mc.mv[l][0]; mvy = mc.mv[l][1];
 						break;
 					}
 				}
@@ -394,109 +395,186 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 	const int n_items = s_cbase[N_CLASS];
 	if (tid >= n_items) return;
 	const int item = s_items[tid];
-	int c = 0;
-#pragma unroll
-	for (int k = 1; k < N_CLASS; ++k) c += tid >= s_cbase[k];
 	const int slot = item >> 4, x4 = item & 3, y4 = (item >> 2) & 3;
 	const int mb = mb0 + slot;
 	const int mbx = mb % job.mb_w, mby = mb / job.mb_w;
 	const b2_h264_mb *mp = job.mbs + mb;
-	int4 raw = __ldg(reinterpret_cast<const int4 *>(job.mcs + mp->mc_idx + s_mcsel[item]));
-	const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);
-	const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[0];
+	const b2_h264_mc *mcp = job.mcs + mp->mc_idx + s_mcsel[item];
+	int4 raw0 = __ldg(reinterpret_cast<const int4 *>(mcp)), raw1 = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
+	b2_h264_mc mc;
+	reinterpret_cast<int4 *>(&mc)[0] = raw0;
+	reinterpret_cast<int4 *>(&mc)[1] = raw1;
 	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
 	uint8_t *dst_c = dst_y + luma_size;
-	const int mvx = mc.mv[0][0], mvy = mc.mv[0][1];
-	const int fx = mvx & 3, fy = mvy & 3;
-	const int x = mbx * 16 + x4 * 4 + (mvx >> 2), y = mby * 16 + y4 * 4 + (mvy >> 2);
-	const bool fast = x >= 3 && x + 14 <= W;      // every aligned word touched lies inside the row
 	const uint32_t has = s_has[slot];
+	const int n_lists = (mc.ref_frame[0] >= 0) + (mc.ref_frame[1] >= 0);
 
-	int px[16];
-	if (c == 0) {
+	int px[16], p0[16];
+	int cb_[2][2][2], cr_[2][2][2];      // [list slot][row][sample]
+	int k = 0;
+#pragma unroll 1
+	for (int l = 0; l < 2; ++l) {
+		if (mc.ref_frame[l] < 0) continue;
+		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[l];
+		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1];
+		const int fx = mvx & 3, fy = mvy & 3;
+		const int x = mbx * 16 + x4 * 4 + (mvx >> 2), y = mby * 16 + y4 * 4 + (mvy >> 2);
+		const bool fast = x >= 3 && x + 14 <= W;      // every aligned word touched lies inside the row
+		if (k == 1) {
 #pragma unroll
-		for (int r = 0; r < 4; ++r) {
-			uint32_t w[3];
-			load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x, fast, 1, w);
-#pragma unroll
-			for (int i = 0; i < 4; ++i) px[4 * r + i] = (w[0] >> (8 * i)) & 255;
+			for (int i = 0; i < 16; ++i) p0[i] = px[i];
 		}
-	} else if (c == 1) {
-#pragma unroll
-		for (int r = 0; r < 4; ++r) {
-			uint32_t w[3];
-			int hb[4];
-			load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x - 2, fast, 3, w);
-			hfilter4(w, hb);
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				int b = clip255((hb[i] + 16) >> 5);
-				int g = fx == 1 ? byte_of(w, i + 2) : byte_of(w, i + 3);
-				px[4 * r + i] = fx == 2 ? b : avg2(g, b);
-			}
-		}
-	} else if (c == 2) {
-		uint32_t R[9];
-#pragma unroll
-		for (int k = 0; k < 9; ++k) {
-			uint32_t w[3];
-			load_row(ref + (size_t)min(max(y + k - 2, 0), H - 1) * W, W, x, fast, 1, w);
-			R[k] = w[0];
-		}
-		vhalf4x4(R, px);
-		if (fy != 2) {
+		if (!fx && !fy) {
 #pragma unroll
 			for (int r = 0; r < 4; ++r) {
-				uint32_t g = fy == 1 ? R[r + 2] : R[r + 3];
+				uint32_t w[3];
+				load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x, fast, 1, w);
 #pragma unroll
-				for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2((g >> (8 * i)) & 255, px[4 * r + i]);
+				for (int i = 0; i < 4; ++i) px[4 * r + i] = (w[0] >> (8 * i)) & 255;
+			}
+		} else if (!fy) {
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				uint32_t w[3];
+				int hb[4];
+				load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x - 2, fast, 3, w);
+				hfilter4(w, hb);
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					int b = clip255((hb[i] + 16) >> 5);
+					int g = fx == 1 ? byte_of(w, i + 2) : byte_of(w, i + 3);
+					px[4 * r + i] = fx == 2 ? b : avg2(g, b);
+				}
+			}
+		} else if (!fx) {
+			uint32_t R[9];
+#pragma unroll
+			for (int q = 0; q < 9; ++q) {
+				uint32_t w[3];
+				load_row(ref + (size_t)min(max(y + q - 2, 0), H - 1) * W, W, x, fast, 1, w);
+				R[q] = w[0];
+			}
+			vhalf4x4(R, px);
+			if (fy != 2) {
+#pragma unroll
+				for (int r = 0; r < 4; ++r) {
+					uint32_t g = fy == 1 ? R[r + 2] : R[r + 3];
+#pragma unroll
+					for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2((g >> (8 * i)) & 255, px[4 * r + i]);
+				}
+			}
+		} else if (fx != 2 && fy != 2) {
+			// quarter positions e, g, p, r: average of a horizontal (b / s) and a vertical (h / m) half sample
+			uint32_t R[9];
+			const int xo = fx == 3 ? 1 : 0, yo = fy == 3 ? 1 : 0;
+#pragma unroll
+			for (int q = 0; q < 9; ++q) {
+				uint32_t w[3];
+				load_row(ref + (size_t)min(max(y + q - 2, 0), H - 1) * W, W, x + xo, fast, 1, w);
+				R[q] = w[0];
+			}
+			vhalf4x4(R, px);
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				uint32_t w[3];
+				int hb[4];
+				load_row(ref + (size_t)min(max(y + r + yo, 0), H - 1) * W, W, x - 2, fast, 3, w);
+				hfilter4(w, hb);
+#pragma unroll
+				for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2(clip255((hb[i] + 16) >> 5), px[4 * r + i]);
+			}
+		} else {
+			// centre column (fx == 2) or centre row (fy == 2): j from the unrounded horizontal intermediates
+			int hb[9][4];
+			uint32_t G[9];
+#pragma unroll
+			for (int q = 0; q < 9; ++q) {
+				uint32_t w[3];
+				load_row(ref + (size_t)min(max(y + q - 2, 0), H - 1) * W, W, x - 2, fast, 3, w);
+				hfilter4(w, hb[q]);
+				// bytes of columns 0..3 (fx == 1) or 1..4 (fx == 3) for the vertical half samples
+				G[q] = fx == 3 ? __funnelshift_r(w[0], w[1], 24) : __funnelshift_r(w[0], w[1], 16);
+			}
+			int vh[16];
+			const bool centre_row = fx != 2;       // fy == 2, fx odd: h / m with j
+			if (centre_row) vhalf4x4(G, vh);
+#pragma unroll
+			for (int r = 0; r < 4; ++r)
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					int j1 = (hb[r][i] + hb[r + 5][i]) - 5 * (hb[r + 1][i] + hb[r + 4][i]) + 20 * (hb[r + 2][i] + hb[r + 3][i]);
+					int j = clip255((j1 + 512) >> 10);
+					int v;
+					if (centre_row) v = avg2(vh[4 * r + i], j);
+					else if (fy == 2) v = j;
+					else v = avg2(clip255(((fy == 1 ? hb[r + 2][i] : hb[r + 3][i]) + 16) >> 5), j);
+					px[4 * r + i] = v;
+				}
+		}
+		// chroma: 2x2 samples of Cb and Cr, eighth-pel bilinear in packed 16-bit lanes
+		{
+			const uint8_t *refc = ref + luma_size;
+			const int CH = H >> 1, cw = W >> 1;
+			const int cfx = mvx & 7, cfy = mvy & 7;
+			const int cx = mbx * 8 + x4 * 2 + (mvx >> 3), cy = mby * 8 + y4 * 2 + (mvy >> 3);
+			const bool cfast = cx >= 2 && cx + 6 <= cw;
+			uint32_t hrow[3][2];    // per row: horizontally interpolated (Cb0, Cb1) and (Cr0, Cr1), 16-bit lanes, scale 8
+#pragma unroll
+			for (int r = 0; r < 3; ++r) {
+				const uint8_t *row = refc + (size_t)min(max(cy + r, 0), CH - 1) * W;
+				uint32_t a, bq;     // a = samples 0,1 (Cb0 Cr0 Cb1 Cr1), bq = samples 1,2
+				if (cfast) {
+					uint32_t w[3];
+					load_row(row, W, cx * 2, true, 2, w);
+					a = w[0];
+					bq = __funnelshift_r(w[0], w[1], 16);
+				} else {
+					int x0 = min(max(cx, 0), cw - 1) * 2, x1 = min(max(cx + 1, 0), cw - 1) * 2, x2 = min(max(cx + 2, 0), cw - 1) * 2;
+					uint32_t s0 = __ldg(row + x0) | (__ldg(row + x0 + 1) << 8), s1 = __ldg(row + x1) | (__ldg(row + x1 + 1) << 8),
+					         s2 = __ldg(row + x2) | (__ldg(row + x2 + 1) << 8);
+					a = s0 | (s1 << 16);
+					bq = s1 | (s2 << 16);
+				}
+				uint32_t a_cb = a & 0x00FF00FFu, a_cr = (a >> 8) & 0x00FF00FFu;
+				uint32_t b_cb = bq & 0x00FF00FFu, b_cr = (bq >> 8) & 0x00FF00FFu;
+				hrow[r][0] = (uint32_t)(8 - cfx) * a_cb + (uint32_t)cfx * b_cb;
+				hrow[r][1] = (uint32_t)(8 - cfx) * a_cr + (uint32_t)cfx * b_cr;
+			}
+#pragma unroll
+			for (int r = 0; r < 2; ++r) {
+				uint32_t vcb = ((uint32_t)(8 - cfy) * hrow[r][0] + (uint32_t)cfy * hrow[r + 1][0] + 0x00200020u) >> 6;
+				uint32_t vcr = ((uint32_t)(8 - cfy) * hrow[r][1] + (uint32_t)cfy * hrow[r + 1][1] + 0x00200020u) >> 6;
+				cb_[k][r][0] = vcb & 0x3FF; cb_[k][r][1] = (vcb >> 16) & 0x3FF;
+				cr_[k][r][0] = vcr & 0x3FF; cr_[k][r][1] = (vcr >> 16) & 0x3FF;
 			}
 		}
-	} else if (c == 3) {
-		// quarter positions e, g, p, r: average of a horizontal (b / s) and a vertical (h / m) half sample
-		uint32_t R[9];
-		const int xo = fx == 3 ? 1 : 0, yo = fy == 3 ? 1 : 0;
+		++k;
+	}
+	// ---- weighted sample prediction (default: w = 1, o = 0, logWD = 0) --------------------------------
+	const int first = mc.ref_frame[0] >= 0 ? 0 : 1;
+	if (n_lists == 2) {
+		const int lw = mc.log2wd_y, w0 = mc.w[0][0], w1 = mc.w[1][0], o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
 #pragma unroll
-		for (int k = 0; k < 9; ++k) {
-			uint32_t w[3];
-			load_row(ref + (size_t)min(max(y + k - 2, 0), H - 1) * W, W, x + xo, fast, 1, w);
-			R[k] = w[0];
-		}
-		vhalf4x4(R, px);
+		for (int i = 0; i < 16; ++i) px[i] = clip255(((p0[i] * w0 + px[i] * w1 + (1 << lw)) >> (lw + 1)) + o);
+		const int lc = mc.log2wd_c;
 #pragma unroll
-		for (int r = 0; r < 4; ++r) {
-			uint32_t w[3];
-			int hb[4];
-			load_row(ref + (size_t)min(max(y + r + yo, 0), H - 1) * W, W, x - 2, fast, 3, w);
-			hfilter4(w, hb);
+		for (int r = 0; r < 2; ++r)
 #pragma unroll
-			for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2(clip255((hb[i] + 16) >> 5), px[4 * r + i]);
-		}
-	} else {
-		// centre column (fx == 2) or centre row (fy == 2): j from the unrounded horizontal intermediates
-		int hb[9][4];
-		uint32_t G[9];
+			for (int i = 0; i < 2; ++i) {
+				cb_[0][r][i] = clip255(((cb_[0][r][i] * mc.w[0][1] + cb_[1][r][i] * mc.w[1][1] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][1] + mc.o[1][1] + 1) >> 1));
+				cr_[0][r][i] = clip255(((cr_[0][r][i] * mc.w[0][2] + cr_[1][r][i] * mc.w[1][2] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][2] + mc.o[1][2] + 1) >> 1));
+			}
+	} else if (mc.log2wd_y | mc.log2wd_c | (mc.w[first][0] ^ 1) | (mc.w[first][1] ^ 1) | (mc.w[first][2] ^ 1) | mc.o[first][0] | mc.o[first][1] | mc.o[first][2]) {
+		const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
 #pragma unroll
-		for (int k = 0; k < 9; ++k) {
-			uint32_t w[3];
-			load_row(ref + (size_t)min(max(y + k - 2, 0), H - 1) * W, W, x - 2, fast, 3, w);
-			hfilter4(w, hb[k]);
-			// bytes of columns 0..3 (fx == 1) or 1..4 (fx == 3) for the vertical half samples of class 5
-			G[k] = fx == 3 ? __funnelshift_r(w[0], w[1], 24) : __funnelshift_r(w[0], w[1], 16);
-		}
-		int vh[16];
-		if (c == 5) vhalf4x4(G, vh);
+		for (int i = 0; i < 16; ++i) px[i] = clip255(((px[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
+		const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
 #pragma unroll
-		for (int r = 0; r < 4; ++r)
+		for (int r = 0; r < 2; ++r)
 #pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				int j1 = (hb[r][i] + hb[r + 5][i]) - 5 * (hb[r + 1][i] + hb[r + 4][i]) + 20 * (hb[r + 2][i] + hb[r + 3][i]);
-				int j = clip255((j1 + 512) >> 10);
-				int v;
-				if (c == 5) v = avg2(vh[4 * r + i], j);
-				else if (fy == 2) v = j;
-				else v = avg2(clip255(((fy == 1 ? hb[r + 2][i] : hb[r + 3][i]) + 16) >> 5), j);
-				px[4 * r + i] = v;
+			for (int i = 0; i < 2; ++i) {
+				cb_[0][r][i] = clip255(((cb_[0][r][i] * mc.w[first][1] + rc) >> lc) + mc.o[first][1]);
+				cr_[0][r][i] = clip255(((cr_[0][r][i] * mc.w[first][2] + rc) >> lc) + mc.o[first][2]);
 			}
 	}
 	{
@@ -512,42 +590,11 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 			*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + y4 * 4 + r) * W + mbx * 16 + x4 * 4) = w;
 		}
 	}
-
-	// ---- chroma: 2x2 samples of Cb and Cr, eighth-pel bilinear in packed 16-bit lanes -----------------
 	{
-		const uint8_t *refc = ref + luma_size;
-		const int CH = H >> 1, cw = W >> 1;
-		const int cfx = mvx & 7, cfy = mvy & 7;
-		const int cx = mbx * 8 + x4 * 2 + (mvx >> 3), cy = mby * 8 + y4 * 2 + (mvy >> 3);
-		const bool cfast = cx >= 2 && cx + 6 <= cw;
-		uint32_t hrow[3][2];        // per row: horizontally interpolated (Cb0, Cb1) and (Cr0, Cr1), 16-bit lanes, scale 8
-#pragma unroll
-		for (int r = 0; r < 3; ++r) {
-			const uint8_t *row = refc + (size_t)min(max(cy + r, 0), CH - 1) * W;
-			uint32_t a, bq;     // a = samples 0,1 (Cb0 Cr0 Cb1 Cr1), bq = samples 1,2
-			if (cfast) {
-				uint32_t w[3];
-				load_row(row, W, cx * 2, true, 2, w);
-				a = w[0];
-				bq = __funnelshift_r(w[0], w[1], 16);
-			} else {
-				int x0 = min(max(cx, 0), cw - 1) * 2, x1 = min(max(cx + 1, 0), cw - 1) * 2, x2 = min(max(cx + 2, 0), cw - 1) * 2;
-				uint32_t s0 = __ldg(row + x0) | (__ldg(row + x0 + 1) << 8), s1 = __ldg(row + x1) | (__ldg(row + x1 + 1) << 8),
-				         s2 = __ldg(row + x2) | (__ldg(row + x2 + 1) << 8);
-				a = s0 | (s1 << 16);
-				bq = s1 | (s2 << 16);
-			}
-			uint32_t a_cb = a & 0x00FF00FFu, a_cr = (a >> 8) & 0x00FF00FFu;
-			uint32_t b_cb = bq & 0x00FF00FFu, b_cr = (bq >> 8) & 0x00FF00FFu;
-			hrow[r][0] = (uint32_t)(8 - cfx) * a_cb + (uint32_t)cfx * b_cb;
-			hrow[r][1] = (uint32_t)(8 - cfx) * a_cr + (uint32_t)cfx * b_cr;
-		}
 		const int cblk = (y4 >> 1) * 2 + (x4 >> 1);
 #pragma unroll
 		for (int r = 0; r < 2; ++r) {
-			uint32_t vcb = ((uint32_t)(8 - cfy) * hrow[r][0] + (uint32_t)cfy * hrow[r + 1][0] + 0x00200020u) >> 6;
-			uint32_t vcr = ((uint32_t)(8 - cfy) * hrow[r][1] + (uint32_t)cfy * hrow[r + 1][1] + 0x00200020u) >> 6;
-			int cb0 = vcb & 0x3FF, cb1 = (vcb >> 16) & 0x3FF, cr0 = vcr & 0x3FF, cr1 = (vcr >> 16) & 0x3FF;
+			int cb0 = cb_[0][r][0], cb1 = cb_[0][r][1], cr0 = cr_[0][r][0], cr1 = cr_[0][r][1];
 			const int ro = ((y4 & 1) * 2 + r) * 4 + (x4 & 1) * 2;
 			if ((has >> (16 + cblk)) & 1) { cb0 = clip255(cb0 + s_res[slot][16 + cblk][ro]); cb1 = clip255(cb1 + s_res[slot][16 + cblk][ro + 1]); }
 			if ((has >> (20 + cblk)) & 1) { cr0 = clip255(cr0 + s_res[slot][20 + cblk][ro]); cr1 = clip255(cr1 + s_res[slot][20 + cblk][ro + 1]); }

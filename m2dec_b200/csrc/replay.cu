@@ -96,7 +96,8 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	if (!r || !p || r->codec != B2_CODEC_H264 || (unsigned)lane >= (unsigned)r->lanes) return -1;
 	if (p->mb_w * 16 != r->width || p->mb_h * 16 != r->height || (unsigned)p->dst >= (unsigned)r->pool) return -1;
 	for (uint32_t i = 0; i < p->n_mcs; ++i)
-		if ((unsigned)p->mcs[i].ref_frame[0] >= (unsigned)r->pool) {
+		if ((p->mcs[i].ref_frame[0] >= 0 && p->mcs[i].ref_frame[0] >= r->pool) || (p->mcs[i].ref_frame[1] >= 0 && p->mcs[i].ref_frame[1] >= r->pool) ||
+		    (p->mcs[i].ref_frame[0] < 0 && p->mcs[i].ref_frame[1] < 0)) {
 			set_error("replay: reference frame index %d outside the lane's pool of %d", p->mcs[i].ref_frame[0], r->pool);
 			return -1;
 		}
@@ -130,10 +131,10 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	}
 	for (uint32_t i = 0; i < p->n_mcs; ++i) {
 		int w = (p->mcs[i].size & 15) * 4, h = (p->mcs[i].size >> 4) * 4;
-		rbytes += (uint64_t)w * h * 3 / 2;
+		rbytes += (uint64_t)w * h * 3 / 2 * ((p->mcs[i].ref_frame[0] >= 0) + (p->mcs[i].ref_frame[1] >= 0));
 	}
 	uint64_t S = (uint64_t)r->frame_bytes;
-	r->stats.alg_bytes[0] += n_inter * 384 + rbytes + c_inter + (uint64_t)p->n_mbs * 32 + (uint64_t)p->n_mcs * 16;
+	r->stats.alg_bytes[0] += n_inter * 384 + rbytes + c_inter + (uint64_t)p->n_mbs * 32 + (uint64_t)p->n_mcs * sizeof(b2_h264_mc);
 	if (p->n_intra) r->stats.alg_bytes[1] += (uint64_t)p->n_intra * 384 + c_intra + (uint64_t)p->n_mbs * 32;
 	if (p->deblock) r->stats.alg_bytes[2] += 2 * S + (uint64_t)p->n_mbs * 16;
 	r->stats.pictures++;

@@ -221,7 +221,8 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	}
 	if ((unsigned)p->dst >= (unsigned)s->nframes) return -1;
 	for (uint32_t i = 0; i < p->n_mcs; ++i)
-		if ((unsigned)p->mcs[i].ref_frame[0] >= (unsigned)s->nframes) {
+		if ((p->mcs[i].ref_frame[0] >= 0 && p->mcs[i].ref_frame[0] >= s->nframes) || (p->mcs[i].ref_frame[1] >= 0 && p->mcs[i].ref_frame[1] >= s->nframes) ||
+		    (p->mcs[i].ref_frame[0] < 0 && p->mcs[i].ref_frame[1] < 0)) {
 			set_error("motion record %u references frame %d outside the pool", i, p->mcs[i].ref_frame[0]);
 			return -1;
 		}

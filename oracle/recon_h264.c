@@ -268,28 +268,54 @@ static int luma_sample(const uint8_t *p, int W, int H, int x, int y, int fx, int
 #undef VH
 }
 
+/* weighted sample prediction (8.4.2.3; inter_pred_weighted_onedir / _bidir, weighted_copy,
+ * add_bidir_weighted_type1/2: h264.cpp:6811-6977, 7027-7099).  n = number of lists used. */
+static int weigh(const b2_h264_mc *r, int comp, int n, int first, int p0, int p1)
+{
+	int logwd = comp ? r->log2wd_c : r->log2wd_y;
+	if (n == 1) {
+		int w = r->w[first][comp], o = r->o[first][comp];
+		int rnd = logwd ? 1 << (logwd - 1) : 0;
+		return clip255(((p0 * w + rnd) >> logwd) + o);
+	}
+	return clip255(((p0 * r->w[0][comp] + p1 * r->w[1][comp] + (1 << logwd)) >> (logwd + 1)) + ((r->o[0][comp] + r->o[1][comp] + 1) >> 1));
+}
+
 static void inter_pred(const b2_h264_picture *p, const b2_h264_mc *r, int mbx, int mby, uint8_t *const *luma,
                        uint8_t *const *chroma)
 {
 	int W = p->mb_w * 16, H = p->mb_h * 16;
 	int x0 = mbx * 16 + (r->pos & 3) * 4, y0 = mby * 16 + (r->pos >> 2) * 4;
 	int w = (r->size & 15) * 4, h = (r->size >> 4) * 4;
-	const uint8_t *ry = luma[r->ref_frame[0]], *rc = chroma[r->ref_frame[0]];
 	uint8_t *dy = luma[p->dst], *dc = chroma[p->dst];
-	int mvx = r->mv[0][0], mvy = r->mv[0][1];
+	int n = (r->ref_frame[0] >= 0) + (r->ref_frame[1] >= 0);
+	int first = r->ref_frame[0] >= 0 ? 0 : 1;
+	int cw = W / 2, ch = H / 2;
 	for (int y = 0; y < h; ++y)
-		for (int x = 0; x < w; ++x)
-			dy[(y0 + y) * W + x0 + x] = (uint8_t)luma_sample(ry, W, H, x0 + x + (mvx >> 2), y0 + y + (mvy >> 2), mvx & 3, mvy & 3);
+		for (int x = 0; x < w; ++x) {
+			int pr[2] = {0, 0}, k = 0;
+			for (int l = 0; l < 2; ++l) {
+				if (r->ref_frame[l] < 0) continue;
+				int mvx = r->mv[l][0], mvy = r->mv[l][1];
+				pr[k++] = luma_sample(luma[r->ref_frame[l]], W, H, x0 + x + (mvx >> 2), y0 + y + (mvy >> 2), mvx & 3, mvy & 3);
+			}
+			dy[(y0 + y) * W + x0 + x] = (uint8_t)weigh(r, 0, n, first, pr[0], pr[1]);
+		}
 	/* chroma (8.4.2.2.2; h264.cpp:5267-5296): eighth-pel bilinear on each component */
-	int cw = W / 2, ch = H / 2, fx = mvx & 7, fy = mvy & 7;
 	for (int y = 0; y < h / 2; ++y)
 		for (int x = 0; x < w / 2; ++x)
 			for (int c = 0; c < 2; ++c) {
-				int cx = x0 / 2 + x + (mvx >> 3), cy = y0 / 2 + y + (mvy >> 3);
+				int pr[2] = {0, 0}, k = 0;
+				for (int l = 0; l < 2; ++l) {
+					if (r->ref_frame[l] < 0) continue;
+					const uint8_t *rc = chroma[r->ref_frame[l]];
+					int mvx = r->mv[l][0], mvy = r->mv[l][1], fx = mvx & 7, fy = mvy & 7;
+					int cx = x0 / 2 + x + (mvx >> 3), cy = y0 / 2 + y + (mvy >> 3);
 #define C(dx, dy) rc[clip3(0, ch - 1, cy + (dy)) * W + clip3(0, cw - 1, cx + (dx)) * 2 + c]
-				int v = ((8 - fx) * (8 - fy) * C(0, 0) + fx * (8 - fy) * C(1, 0) + (8 - fx) * fy * C(0, 1) + fx * fy * C(1, 1) + 32) >> 6;
+					pr[k++] = ((8 - fx) * (8 - fy) * C(0, 0) + fx * (8 - fy) * C(1, 0) + (8 - fx) * fy * C(0, 1) + fx * fy * C(1, 1) + 32) >> 6;
 #undef C
-				dc[(y0 / 2 + y) * W + (x0 / 2 + x) * 2 + c] = (uint8_t)v;
+				}
+				dc[(y0 / 2 + y) * W + (x0 / 2 + x) * 2 + c] = (uint8_t)weigh(r, 1 + c, n, first, pr[0], pr[1]);
 			}
 }
 
