@@ -26,6 +26,18 @@ H264_CASES = {
     "h264_biglevels": "mbw=8 mbh=6 frames=6 seed=16 qp=12 big_levels=1 coded_pct=50",
     "h264_constrained": "mbw=8 mbh=6 frames=8 seed=17 constrained_intra=1 intra_pct=30",
     "h264_2x2": "mbw=2 mbh=2 frames=6 seed=21",
+    # Main profile, CAVLC: B pictures, direct modes, weighted prediction
+    "h264_b_bipred": "mbw=8 mbh=6 frames=7 seed=31 refs=2 bframes=2 profile=77 skip_pct=0 direct_pct=0",
+    "h264_b_implicit": "mbw=8 mbh=6 frames=7 seed=32 refs=2 bframes=2 profile=77 skip_pct=0 direct_pct=0 weighted_bipred=2",
+    "h264_b_explicit": "mbw=8 mbh=6 frames=7 seed=33 refs=2 bframes=2 profile=77 skip_pct=0 direct_pct=0 weighted_bipred=1 weighted_pred=1",
+    "h264_b_spatial": "mbw=8 mbh=6 frames=7 seed=34 refs=2 bframes=2 profile=77",
+    "h264_b_temporal": "mbw=8 mbh=6 frames=7 seed=35 refs=2 bframes=2 profile=77 direct_spatial=0",
+    "h264_b_temporal_implicit": "mbw=10 mbh=8 frames=13 seed=36 refs=3 bframes=2 profile=77 direct_spatial=0 weighted_bipred=2",
+    "h264_b3_explicit_slices": "mbw=10 mbh=8 frames=13 seed=37 refs=3 bframes=3 profile=77 weighted_bipred=1 weighted_pred=1 slices=2",
+    "h264_b_direct4x4_spatial": "mbw=10 mbh=8 frames=10 seed=38 refs=2 bframes=1 profile=77 direct_8x8_inference=0",
+    "h264_b_direct4x4_temporal": "mbw=10 mbh=8 frames=10 seed=39 refs=2 bframes=2 profile=77 direct_8x8_inference=0 direct_spatial=0",
+    "h264_b_mixed": "mbw=12 mbh=9 frames=16 seed=40 refs=4 bframes=2 profile=77 intra_pct=20 direct_pct=40 skip_pct=30",
+    "h264_p_weighted": "mbw=9 mbh=6 frames=8 seed=42 refs=3 weighted_pred=1 profile=77",
     "h264_2x3_slices": "mbw=2 mbh=3 frames=6 seed=25 slices=2",
 }
 # Pictures one macroblock wide or high: the compiled reference disagrees with ffmpeg there (its
@@ -36,7 +48,8 @@ H264_REFERENCE_DEVIATES = {
     "h264_col": "mbw=1 mbh=7 frames=5 seed=20 slices=2",
 }
 # committed under tests/golden/ together with the reference's MD5 lines
-H264_GOLDEN = ["h264_basic", "h264_refs3", "h264_slices_dbk_mix", "h264_intra_ipcm", "h264_qp40_cqp", "h264_umv", "h264_constrained"]
+H264_GOLDEN = ["h264_basic", "h264_refs3", "h264_slices_dbk_mix", "h264_intra_ipcm", "h264_qp40_cqp", "h264_umv", "h264_constrained",
+               "h264_b_spatial", "h264_b_temporal_implicit", "h264_b3_explicit_slices", "h264_b_direct4x4_temporal", "h264_p_weighted"]
 
 MPEG2_CASES = {
     "mpeg2_ipb": "mbw=8 mbh=6 frames=7 seed=1",

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "bitwriter.h"
 #include "h264_cavlc_tables.h"
@@ -55,13 +56,21 @@ public:
 	std::vector<uint8_t> run() {
 		write_sps();
 		write_pps();
-		int frame_num = 0, since_idr = 0;
-		for (int f = 0; f < o_.frames; ++f) {
-			bool idr = (f % o_.gop) == 0;
-			if (idr) { frame_num = 0; since_idr = 0; idr_id_ = (idr_id_ + 1) & 0xff; }
-			picture(idr, frame_num, since_idr);
+		// display index d -> POC 2d.  Coded order: anchor first, then the B pictures in front of it.
+		int frame_num = 0, since_idr = 0, done = 0;
+		while (done < o_.frames) {
+			bool idr = done == 0 || (o_.bframes == 0 && (done % o_.gop) == 0);
+			int nb = 0;
+			if (!idr && o_.bframes > 0) {
+				int remaining = o_.frames - done;
+				nb = remaining > o_.bframes ? o_.bframes : remaining - 1;
+			}
+			if (idr) { frame_num = 0; since_idr = 0; idr_id_ = (idr_id_ + 1) & 0xff; poc_base_ = done; refs_.clear(); }
+			picture(idr ? 2 : 0, idr, frame_num, since_idr, done + nb, true);
 			frame_num = (frame_num + 1) & 15;
 			since_idr++;
+			for (int b = 0; b < nb; ++b) picture(1, false, frame_num, since_idr, done + b, false);
+			done += nb + 1;
 		}
 		return out_;
 	}
@@ -87,13 +96,14 @@ private:
 		bw.put(40, 8);               // level 4.0
 		bw.ue(0);                    // seq_parameter_set_id (hazard 10: must be 0)
 		bw.ue(0);                    // log2_max_frame_num_minus4
-		bw.ue(2);                    // pic_order_cnt_type
+		if (o_.bframes > 0) { bw.ue(0); bw.ue(4); }   // pic_order_cnt_type 0, log2_max_pic_order_cnt_lsb = 8
+		else bw.ue(2);               // pic_order_cnt_type 2
 		bw.ue(o_.refs);              // num_ref_frames
 		bw.put1(0);                  // gaps_in_frame_num_value_allowed_flag
 		bw.ue(o_.mbw - 1);
 		bw.ue(o_.mbh - 1);
 		bw.put1(1);                  // frame_mbs_only_flag
-		bw.put1(1);                  // direct_8x8_inference_flag
+		bw.put1(o_.direct_8x8_inference);   // direct_8x8_inference_flag
 		if (o_.crop_bottom || o_.crop_right) {
 			bw.put1(1);
 			bw.ue(0); bw.ue(o_.crop_right / 2); bw.ue(0); bw.ue(o_.crop_bottom / 2);
@@ -112,9 +122,9 @@ private:
 		bw.put1(0);
 		bw.ue(0);                    // num_slice_groups_minus1
 		bw.ue(o_.refs - 1);          // num_ref_idx_l0_default_active_minus1
-		bw.ue(0);
-		bw.put1(0);                  // weighted_pred_flag
-		bw.put(0, 2);
+		bw.ue(o_.refs - 1);          // num_ref_idx_l1_default_active_minus1
+		bw.put1(o_.weighted_pred);   // weighted_pred_flag
+		bw.put(o_.weighted_bipred, 2);
 		bw.se(o_.qp - 26);           // pic_init_qp_minus26
 		bw.se(0);
 		bw.se(o_.chroma_qp_offset);
@@ -126,40 +136,110 @@ private:
 	}
 
 	// ---- picture / slice ---------------------------------------------------------------------------
-	void picture(bool idr, int frame_num, int since_idr) {
+	// slice_kind: 0 P, 1 B, 2 I.  display = display index (POC = 2 * (display - poc_base_)).
+	void picture(int slice_kind, bool idr, int frame_num, int since_idr, int display, bool is_ref) {
+		(void)since_idr;
 		ctx_.begin_picture();
 		int total = o_.mbw * o_.mbh;
 		int nslices = o_.slices < 1 ? 1 : o_.slices;
 		int per = (total + nslices - 1) / nslices;
 		qp_ = o_.qp;
+		kind_ = slice_kind;
+		cur_poc_ = 2 * (display - poc_base_);
+		build_lists();
 		for (int s = 0, first = 0; first < total; ++s, first += per) {
 			int last = first + per < total ? first + per : total;
 			slice_num_ = s;
-			nref_ = idr ? 0 : (since_idr < o_.refs ? since_idr : o_.refs);
 			BitWriter bw;
 			bw.ue(first);
-			bw.ue(idr ? 7 : 5);      // slice_type: all slices of the picture are I / P
+			bw.ue(slice_kind == 2 ? 7 : (slice_kind == 0 ? 5 : 6));   // all slices of the picture have this type
 			bw.ue(0);                // pic_parameter_set_id
 			bw.put(frame_num, 4);
 			if (idr) bw.ue(idr_id_);
-			if (!idr) {
-				bool override_flag = nref_ != o_.refs;
+			if (o_.bframes > 0) bw.put(cur_poc_ & 255, 8);            // pic_order_cnt_lsb
+			if (slice_kind == 1) bw.put1(o_.direct_spatial);
+			if (slice_kind != 2) {
+				nref_[0] = (int)list_[0].size();
+				nref_[1] = (int)list_[1].size();
+				bool override_flag = nref_[0] != o_.refs || (slice_kind == 1 && nref_[1] != o_.refs);
 				bw.put1(override_flag);
-				if (override_flag) bw.ue(nref_ - 1);
+				if (override_flag) { bw.ue(nref_[0] - 1); if (slice_kind == 1) bw.ue(nref_[1] - 1); }
 				bw.put1(0);          // ref_pic_list_modification_flag_l0
+				if (slice_kind == 1) bw.put1(0);
+				if ((slice_kind == 0 && o_.weighted_pred) || (slice_kind == 1 && o_.weighted_bipred == 1)) weight_table(bw, slice_kind == 1);
 			}
-			if (idr) { bw.put1(0); bw.put1(0); }   // no_output_of_prior_pics, long_term_reference_flag
-			else bw.put1(0);                        // adaptive_ref_pic_marking_mode_flag
+			if (is_ref) {
+				if (idr) { bw.put1(0); bw.put1(0); }   // no_output_of_prior_pics, long_term_reference_flag
+				else bw.put1(0);                        // adaptive_ref_pic_marking_mode_flag
+			}
 			int slice_qp = o_.qp + (o_.vary_qp ? rng_.range(-2, 2) : 0);
 			bw.se(slice_qp - o_.qp);
 			qp_ = slice_qp;
 			int idc = o_.deblock ? ((o_.deblock == 2 && (s & 1)) ? 1 : 0) : 1;
 			bw.ue(idc);
 			if (idc != 1) { bw.se(o_.alpha_div2); bw.se(o_.beta_div2); }
-			slice_data(bw, idr, first, last);
+			slice_data(bw, slice_kind == 2, first, last);
 			bw.rbsp_trailing();
-			emit_nal(idr ? 3 : 2, idr ? 5 : 1, bw);
+			emit_nal(idr ? 3 : (is_ref ? 2 : 0), idr ? 5 : 1, bw);
 		}
+		if (is_ref) {
+			// sliding window marking (8.2.5.3) and the co-located motion of this picture
+			int id = next_pic_id_++;
+			for (auto &r : refs_) { r.frame_num_wrap = r.rp.frame_num > frame_num ? r.rp.frame_num - 16 : r.rp.frame_num; }
+			if ((int)refs_.size() >= o_.refs) {
+				int victim = 0;
+				for (size_t i = 1; i < refs_.size(); ++i) if (refs_[i].frame_num_wrap < refs_[victim].frame_num_wrap) victim = (int)i;
+				refs_.erase(refs_.begin() + victim);
+			}
+			WRef nr;
+			nr.rp = RefPic{id, frame_num, -1, cur_poc_};
+			nr.frame_num_wrap = frame_num;
+			ctx_.store_col(nr.col, [&](int f) { for (auto &r : refs_) if (r.rp.frame_idx == f) return r.rp.poc; return 0; });
+			refs_.push_back(std::move(nr));
+		}
+	}
+
+	// reference picture lists as the decoder will build them (8.2.4.2.1 / 8.2.4.2.3), no modification
+	void build_lists() {
+		list_[0].clear(); list_[1].clear();
+		if (kind_ == 2) return;
+		std::vector<const WRef *> v;
+		for (auto &r : refs_) v.push_back(&r);
+		if (kind_ == 0) {
+			std::sort(v.begin(), v.end(), [](const WRef *a, const WRef *b) { return a->frame_num_wrap > b->frame_num_wrap; });
+			for (auto *r : v) list_[0].push_back(r);
+		} else {
+			std::vector<const WRef *> before, after;
+			for (auto *r : v) (r->rp.poc < cur_poc_ ? before : after).push_back(r);
+			std::sort(before.begin(), before.end(), [](const WRef *a, const WRef *b) { return a->rp.poc > b->rp.poc; });
+			std::sort(after.begin(), after.end(), [](const WRef *a, const WRef *b) { return a->rp.poc < b->rp.poc; });
+			list_[0] = before; list_[0].insert(list_[0].end(), after.begin(), after.end());
+			list_[1] = after; list_[1].insert(list_[1].end(), before.begin(), before.end());
+			if (list_[1].size() > 1 && list_[0] == list_[1]) std::swap(list_[1][0], list_[1][1]);
+		}
+		// A P picture that is full of references evicts its oldest one when it is marked; the B pictures
+		// that follow could then not map a co-located vector that points there (temporal direct), so
+		// such P pictures leave the oldest reference unused.
+		if (kind_ == 0 && o_.bframes > 0 && (int)list_[0].size() >= o_.refs && o_.refs > 1) list_[0].resize(o_.refs - 1);
+		for (int l = 0; l < 2; ++l) {
+			if ((int)list_[l].size() > o_.refs) list_[l].resize(o_.refs);
+			rp_[l].clear();
+			for (auto *r : list_[l]) rp_[l].push_back(r->rp);
+		}
+	}
+
+	// explicit weights: log2 denominators <= 6, weights and offsets tame (hazard 4)
+	void weight_table(BitWriter &bw, bool bslice) {
+		int dl = rng_.range(2, 6), dc = rng_.range(2, 6);
+		bw.ue(dl); bw.ue(dc);
+		for (int l = 0; l < (bslice ? 2 : 1); ++l)
+			for (int i = 0; i < nref_[l]; ++i) {
+				bool fl = rng_.chance(70), fc = rng_.chance(70);
+				bw.put1(fl);
+				if (fl) { bw.se((1 << dl) + rng_.range(-(1 << dl) / 4, (1 << dl) / 4)); bw.se(rng_.range(-8, 8)); }
+				bw.put1(fc);
+				if (fc) for (int c = 0; c < 2; ++c) { bw.se((1 << dc) + rng_.range(-(1 << dc) / 4, (1 << dc) / 4)); bw.se(rng_.range(-8, 8)); }
+			}
 	}
 
 	void slice_data(BitWriter &bw, bool idr, int first, int last) {
@@ -168,10 +248,16 @@ private:
 			int mbx = addr % o_.mbw, mby = addr / o_.mbw;
 			ctx_.open_mb(mbx, mby, slice_num_);
 			if (!idr && rng_.chance(o_.skip_pct)) {
-				int16_t mv[2];
-				ctx_.pskip_mv(mbx, mby, slice_num_, mv);
-				ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, 0, mv[0], mv[1]);
-				ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
+				if (kind_ == 1) {
+					DirectOut d;
+					derive_direct(mbx, mby, d);
+					set_direct(mbx, mby, d, 0xf);
+				} else {
+					int16_t mv[2];
+					ctx_.pskip_mv(mbx, mby, slice_num_, mv);
+					ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, pic_of(0, 0), mv[0], mv[1]);
+					ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
+				}
 				MbInfo &info = ctx_.info(mbx, mby);
 				info.kind = MB_SKIP;
 				memset(ctx_.nnz_of(mbx, mby), 0, 24);
@@ -180,6 +266,7 @@ private:
 			}
 			if (!idr) { bw.ue(skip_run); skip_run = 0; }
 			if (idr || rng_.chance(o_.intra_pct)) intra_mb(bw, mbx, mby, idr);
+			else if (kind_ == 1) b_mb(bw, mbx, mby);
 			else inter_mb(bw, mbx, mby);
 		}
 		if (!idr && skip_run) bw.ue(skip_run);
@@ -368,7 +455,7 @@ private:
 		MbInfo &info = ctx_.info(mbx, mby);
 		ctx_.set_intra_motion(mbx, mby);
 		int8_t *ip = ctx_.ipred_of(mbx, mby);
-		int ofs = islice ? 0 : 5;
+		int ofs = islice ? 0 : (kind_ == 1 ? 23 : 5);
 		// chroma mode candidates
 		int cc[4], ncc = 0;
 		cc[ncc++] = 0;
@@ -473,12 +560,12 @@ private:
 		std::vector<Part> parts;
 		int t = rng_.range(0, 99);
 		int mb_type, sub[4] = {0, 0, 0, 0}, refs[4];
-		for (int i = 0; i < 4; ++i) refs[i] = nref_ > 1 ? rng_.range(0, nref_ - 1) : 0;
+		for (int i = 0; i < 4; ++i) refs[i] = nref_[0] > 1 ? rng_.range(0, nref_[0] - 1) : 0;
 		if (t < 40) { mb_type = 0; parts.push_back({0, 0, 4, 4, refs[0], 0, 0}); }
 		else if (t < 55) { mb_type = 1; parts.push_back({0, 0, 4, 2, refs[0], 1, 0}); parts.push_back({0, 2, 4, 2, refs[1], 1, 1}); }
 		else if (t < 70) { mb_type = 2; parts.push_back({0, 0, 2, 4, refs[0], 2, 0}); parts.push_back({2, 0, 2, 4, refs[1], 2, 1}); }
 		else {
-			mb_type = (nref_ > 1 || rng_.chance(50)) ? 3 : 4;   // P_8x8 / P_8x8ref0
+			mb_type = (nref_[0] > 1 || rng_.chance(50)) ? 3 : 4;   // P_8x8 / P_8x8ref0
 			if (mb_type == 4) for (int i = 0; i < 4; ++i) refs[i] = 0;
 			for (int i = 0; i < 4; ++i) {
 				sub[i] = rng_.range(0, 3);
@@ -493,8 +580,8 @@ private:
 		}
 		bw.ue(mb_type);
 		auto put_ref = [&](int r) {
-			if (nref_ <= 1) return;
-			if (nref_ == 2) bw.put1(r ^ 1); else bw.ue(r);
+			if (nref_[0] <= 1) return;
+			if (nref_[0] == 2) bw.put1(r ^ 1); else bw.ue(r);
 		};
 		if (mb_type == 0) put_ref(refs[0]);
 		else if (mb_type == 1 || mb_type == 2) { put_ref(refs[0]); put_ref(refs[1]); }
@@ -509,7 +596,7 @@ private:
 			draw_mv(mbx, mby, pred, mv);
 			bw.se(mv[0] - pred[0]);
 			bw.se(mv[1] - pred[1]);
-			ctx_.set_motion(0, mbx, mby, p.x4, p.y4, p.pw, p.ph, p.ref, p.ref, mv[0], mv[1]);
+			ctx_.set_motion(0, mbx, mby, p.x4, p.y4, p.pw, p.ph, p.ref, pic_of(0, p.ref), mv[0], mv[1]);
 		}
 		Residual r;
 		int qd = draw_qp_delta();
@@ -521,12 +608,123 @@ private:
 		code_chroma(bw, r, mbx, mby);
 	}
 
+	// ---- B pictures ---------------------------------------------------------------------------------------
+	int pic_of(int l, int refidx) const { return refidx >= 0 && refidx < (int)list_[l].size() ? list_[l][refidx]->rp.frame_idx : -1; }
+
+	void derive_direct(int mbx, int mby, DirectOut &d) {
+		const ColPic *col = list_[1].empty() ? nullptr : &list_[1][0]->col;
+		if (o_.direct_spatial) ctx_.direct_spatial(mbx, mby, slice_num_, col, true, o_.direct_8x8_inference != 0, d);
+		else ctx_.direct_temporal(mbx, mby, col, o_.direct_8x8_inference != 0, rp_[0].data(), (int)rp_[0].size(), rp_[1].data(), cur_poc_, d);
+	}
+	void set_direct(int mbx, int mby, const DirectOut &d, int quads) {
+		for (int q = 0; q < 4; ++q) {
+			if (!((quads >> q) & 1)) continue;
+			for (int y = (q >> 1) * 2; y < (q >> 1) * 2 + 2; ++y)
+				for (int x = (q & 1) * 2; x < (q & 1) * 2 + 2; ++x)
+					for (int l = 0; l < 2; ++l)
+						ctx_.set_motion(l, mbx, mby, x, y, 1, 1, d.ref[y * 4 + x][l], pic_of(l, d.ref[y * 4 + x][l]), d.mv[y * 4 + x][l][0], d.mv[y * 4 + x][l][1]);
+		}
+	}
+
+	void b_mb(BitWriter &bw, int mbx, int mby) {
+		MbInfo &info = ctx_.info(mbx, mby);
+		info.kind = MB_INTER;
+		memset(ctx_.ipred_of(mbx, mby), 2, 16);
+		struct Part { int x4, y4, pw, ph, shape, part, use, sub; };
+		std::vector<Part> parts;
+		int sub_use[4] = {0, 0, 0, 0}, sub_type[4] = {0, 0, 0, 0};
+		int mb_type, direct_quads = 0;
+		int t = rng_.range(0, 99);
+		auto mode = [&]() { return rng_.range(1, 3); };
+		if (t < o_.direct_pct) {
+			mb_type = 0;
+			direct_quads = 0xf;
+		} else if (t < o_.direct_pct + 25) {
+			int u = mode();
+			mb_type = u;
+			parts.push_back({0, 0, 4, 4, 0, 0, u, 0});
+			sub_use[0] = u;
+		} else if (t < o_.direct_pct + 55) {
+			static const uint8_t modes[22][2] = {{0, 0}, {1, 0}, {2, 0}, {3, 0}, {1, 1}, {1, 1}, {2, 2}, {2, 2}, {1, 2}, {1, 2}, {2, 1}, {2, 1},
+			                                     {1, 3}, {1, 3}, {2, 3}, {2, 3}, {3, 1}, {3, 1}, {3, 2}, {3, 2}, {3, 3}, {3, 3}};
+			mb_type = rng_.range(4, 21);
+			if (mb_type & 1) { parts.push_back({0, 0, 2, 4, 2, 0, modes[mb_type][0], 0}); parts.push_back({2, 0, 2, 4, 2, 1, modes[mb_type][1], 1}); }
+			else { parts.push_back({0, 0, 4, 2, 1, 0, modes[mb_type][0], 0}); parts.push_back({0, 2, 4, 2, 1, 1, modes[mb_type][1], 1}); }
+			sub_use[0] = modes[mb_type][0];
+			sub_use[1] = modes[mb_type][1];
+		} else {
+			static const uint8_t sub_mode[13] = {0, 1, 2, 3, 1, 1, 2, 2, 3, 3, 1, 2, 3};
+			static const uint8_t sub_shape[13] = {0, 0, 0, 0, 1, 2, 1, 2, 1, 2, 3, 3, 3};
+			mb_type = 22;
+			for (int q = 0; q < 4; ++q) {
+				int st = rng_.chance(o_.direct_pct) ? 0 : rng_.range(1, 12);
+				sub_type[q] = st;
+				int bx = (q & 1) * 2, by = (q >> 1) * 2, use = sub_mode[st];
+				sub_use[q] = use;
+				if (use == 0) { direct_quads |= 1 << q; parts.push_back({bx, by, 2, 2, 0, 0, 0, q}); continue; }
+				switch (sub_shape[st]) {
+				case 0: parts.push_back({bx, by, 2, 2, 0, 0, use, q}); break;
+				case 1: parts.push_back({bx, by, 2, 1, 0, 0, use, q}); parts.push_back({bx, by + 1, 2, 1, 0, 0, use, q}); break;
+				case 2: parts.push_back({bx, by, 1, 2, 0, 0, use, q}); parts.push_back({bx + 1, by, 1, 2, 0, 0, use, q}); break;
+				default: for (int k = 0; k < 4; ++k) parts.push_back({bx + (k & 1), by + (k >> 1), 1, 1, 0, 0, use, q}); break;
+				}
+			}
+		}
+		bw.ue(mb_type);
+		if (mb_type == 22) for (int q = 0; q < 4; ++q) bw.ue(sub_type[q]);
+		DirectOut dir;
+		if (direct_quads) derive_direct(mbx, mby, dir);
+		int ref[4][2];
+		const int nsub = mb_type == 22 ? 4 : (mb_type == 0 ? 0 : (mb_type <= 3 ? 1 : 2));
+		for (int l = 0; l < 2; ++l)
+			for (int q = 0; q < nsub; ++q) {
+				ref[q][l] = -1;
+				if (!(sub_use[q] & (1 << l))) continue;
+				int r = nref_[l] > 1 ? rng_.range(0, nref_[l] - 1) : 0;
+				ref[q][l] = r;
+				if (nref_[l] > 1) { if (nref_[l] == 2) bw.put1(r ^ 1); else bw.ue(r); }
+			}
+		for (int l = 0; l < 2; ++l)
+			for (const Part &p : parts) {
+				if (p.use == 0) {
+					for (int y = p.y4; y < p.y4 + 2; ++y)
+						for (int x = p.x4; x < p.x4 + 2; ++x)
+							ctx_.set_motion(l, mbx, mby, x, y, 1, 1, dir.ref[y * 4 + x][l], pic_of(l, dir.ref[y * 4 + x][l]), dir.mv[y * 4 + x][l][0], dir.mv[y * 4 + x][l][1]);
+					continue;
+				}
+				if (!(p.use & (1 << l))) { ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, -1, -1, 0, 0); continue; }
+				int16_t pred[2];
+				int r = ref[p.sub][l];
+				ctx_.predict_mv(l, mbx, mby, p.x4, p.y4, p.pw, r, slice_num_, p.shape, p.part, pred);
+				int mv[2];
+				draw_mv(mbx, mby, pred, mv);
+				bw.se(mv[0] - pred[0]);
+				bw.se(mv[1] - pred[1]);
+				ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, r, pic_of(l, r), mv[0], mv[1]);
+			}
+		if (mb_type == 0) set_direct(mbx, mby, dir, 0xf);
+		Residual r;
+		int qd = draw_qp_delta();
+		int qp = qp_ + qd;
+		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false);
+		bw.ue(enc_.code_from_cbp[1][r.cbp]);
+		if (r.cbp) { bw.se(qd); qp_ = qp; }
+		code_luma(bw, r, mbx, mby, false);
+		code_chroma(bw, r, mbx, mby);
+	}
+
+	struct WRef { RefPic rp; int frame_num_wrap; ColPic col; };
+	std::vector<WRef> refs_;
+	std::vector<const WRef *> list_[2];
+	std::vector<RefPic> rp_[2];
+	int kind_ = 2, cur_poc_ = 0, poc_base_ = 0, next_pic_id_ = 0;
+	int nref_[2] = {0, 0};
 	H264Opts o_;
 	Rng rng_;
 	Enc enc_;
 	PicCtx ctx_;
 	std::vector<uint8_t> out_;
-	int slice_num_ = 0, nref_ = 0, qp_ = 26, idr_id_ = 0;
+	int slice_num_ = 0, qp_ = 26, idr_id_ = 0;
 };
 
 }  // namespace

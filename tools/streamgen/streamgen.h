@@ -22,6 +22,13 @@ struct H264Opts {
 	int mv_step = 6, mv_range = 96, mv_out = 24;   // quarter-pel step / range, pixels allowed outside
 	int crop_bottom = 0, crop_right = 0;
 	int constrained_intra = 0;
+	// Main-profile features (CAVLC): B pictures between anchors, direct modes, weighted prediction
+	int bframes = 0;           // non-reference B pictures between consecutive P/I pictures (POC type 0)
+	int direct_spatial = 1;    // direct_spatial_mv_pred_flag
+	int direct_pct = 20;       // share of B macroblocks / sub-macroblocks coded as direct, and B_Skip share = skip_pct
+	int weighted_pred = 0;     // explicit weights in P slices
+	int weighted_bipred = 0;   // 0 default, 1 explicit, 2 implicit
+	int direct_8x8_inference = 1;
 };
 
 struct Mpeg2Opts {
