@@ -53,8 +53,13 @@ struct MbInfo {
 	uint8_t cbp;
 	uint8_t t8x8;
 	uint8_t chroma_mode;
-	uint8_t pad;
+	uint8_t cflags;     // CABAC neighbour state: MBF_* bits
 };
+// MbInfo.cflags: coded_block_flag of the DC blocks, and "B_Skip or B_Direct_16x16"
+enum { MBF_CBF_LUMA_DC = 1, MBF_CBF_CB_DC = 2, MBF_CBF_CR_DC = 4, MBF_DIRECT16 = 8, MBF_SHAPE_SHIFT = 4 };
+// bits 4..5 of cflags: partition shape of the macroblock as the reference records it for a
+// co-located picture (col_mbtype_t, h264.h:84-89): 0 16x16 (also intra), 1 16x8, 2 8x16, 3 8x8
+enum { SHAPE_16x16 = 0, SHAPE_16x8 = 1, SHAPE_8x16 = 2, SHAPE_8x8 = 3 };
 
 struct Neighbour {
 	bool avail;
@@ -80,6 +85,7 @@ struct ColBlk {
 };
 struct ColPic {
 	std::vector<ColBlk> b;
+	std::vector<uint8_t> shape;   // per macroblock, SHAPE_*
 };
 // result of direct prediction for one macroblock, per 4x4 block in raster order
 struct DirectOut {
@@ -97,6 +103,11 @@ public:
 	std::vector<int16_t> mv[2];      // [(gy * w4 + gx) * 2]
 	std::vector<int8_t> ref[2];      // per 4x4: -2 not decoded, -1 intra / unused list, >= 0 refIdx
 	std::vector<int8_t> refpic[2];   // per 4x4: frame-pool index of the reference picture, -1 none
+	// CABAC only (9.3.3.1.1.6 / .7): per 4x4 block |mvd| (x, y; saturated) and "refIdx > 0 and not
+	// direct-predicted", both zero for everything that codes neither
+	bool cabac = false;
+	std::vector<uint8_t> mvd[2];
+	std::vector<uint8_t> refgt0[2];
 
 	void resize(int mbw, int mbh) {
 		mb_w = mbw; mb_h = mbh; w4 = mbw * 4; h4 = mbh * 4;
@@ -108,6 +119,8 @@ public:
 			mv[l].assign(n * 16 * 2, 0);
 			ref[l].assign(n * 16, -2);
 			refpic[l].assign(n * 16, -1);
+			mvd[l].assign(n * 16 * 2, 0);
+			refgt0[l].assign(n * 16, 0);
 		}
 	}
 	void begin_picture() {
@@ -149,6 +162,11 @@ public:
 			size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4;
 			memset(&ref[0][g], -2, 4);
 			memset(&ref[1][g], -2, 4);
+			if (cabac)
+				for (int l = 0; l < 2; ++l) {
+					memset(&mvd[l][g * 2], 0, 8);
+					memset(&refgt0[l][g], 0, 4);
+				}
 		}
 		env.mbx = mbx;
 		env.mby = mby;
@@ -261,6 +279,8 @@ public:
 	template <class F>
 	void store_col(ColPic &c, F poc_of_frame) const {
 		c.b.resize((size_t)w4 * h4);
+		c.shape.resize(mb.size());
+		for (size_t i = 0; i < mb.size(); ++i) c.shape[i] = (uint8_t)((mb[i].cflags >> MBF_SHAPE_SHIFT) & 3);
 		for (size_t g = 0; g < c.b.size(); ++g) {
 			ColBlk &o = c.b[g];
 			int l = ref[0][g] >= 0 ? 0 : (ref[1][g] >= 0 ? 1 : -1);
@@ -276,8 +296,12 @@ public:
 	static inline int min_positive(int a, int b) { return (a >= 0 && b >= 0) ? (a < b ? a : b) : (a > b ? a : b); }
 
 	// 8.4.1.2.2: spatial direct prediction of the whole macroblock (open_mb must have been called)
+	// col_shape >= 0: take the co-located block per partition of that shape (what the reference
+	// does for B_Skip / B_Direct_16x16, h264.cpp:9790-9850) instead of per corner / 4x4 block;
+	// both agree unless the reference has overwritten the recorded shape (see derive_direct).
+	// refs_out (optional): the two reference indices before the "both negative" substitution.
 	void direct_spatial(int mbx, int mby, int cur_slice, const ColPic *col, bool col_short_term, bool inference8x8,
-	                    DirectOut &out) const {
+	                    DirectOut &out, int col_shape = -1, int *refs_out = nullptr) const {
 		const int gx = mbx * 4, gy = mby * 4;
 		int refs[2];
 		int16_t mvp[2][2] = {{0, 0}, {0, 0}};
@@ -287,6 +311,7 @@ public:
 			refs[l] = min_positive(a.avail ? a.ref : -1, min_positive(b.avail ? b.ref : -1, c.avail ? c.ref : -1));
 		}
 		bool zero = false;
+		if (refs_out) { refs_out[0] = refs[0]; refs_out[1] = refs[1]; }
 		if (refs[0] < 0 && refs[1] < 0) { refs[0] = refs[1] = 0; zero = true; }
 		else
 			for (int l = 0; l < 2; ++l)
@@ -294,6 +319,9 @@ public:
 		for (int y = 0; y < 4; ++y)
 			for (int x = 0; x < 4; ++x) {
 				int cx = inference8x8 ? (x >> 1) * 3 : x, cy = inference8x8 ? (y >> 1) * 3 : y;
+				if (col_shape == SHAPE_16x16) cx = cy = 0;
+				else if (col_shape == SHAPE_16x8) { cx = 0; cy = y & 2; }
+				else if (col_shape == SHAPE_8x16) { cx = x & 2; cy = 0; }
 				bool col_zero = false;
 				if (col && col_short_term && !col->b.empty()) {
 					const ColBlk &cb = col->b[(size_t)(gy + cy) * w4 + gx + cx];
@@ -341,6 +369,89 @@ public:
 					}
 				}
 			}
+	}
+
+	// --- CABAC ctxIdxInc derivations (9.3.3.1.1.x); open_mb must have been called ----------------
+	inline const MbInfo *mb_left() const { return env.availL ? &mb[(size_t)env.mby * mb_w + env.mbx - 1] : nullptr; }
+	inline const MbInfo *mb_top() const { return env.availT ? &mb[(size_t)(env.mby - 1) * mb_w + env.mbx] : nullptr; }
+	int cabac_inc_skip() const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		return (l && l->kind != MB_SKIP) + (t && t->kind != MB_SKIP);
+	}
+	int cabac_inc_mbtype_i() const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		return (l && l->kind != MB_I4x4 && l->kind != MB_I8x8) + (t && t->kind != MB_I4x4 && t->kind != MB_I8x8);
+	}
+	int cabac_inc_mbtype_b() const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		return (l && !(l->cflags & MBF_DIRECT16)) + (t && !(t->cflags & MBF_DIRECT16));
+	}
+	int cabac_inc_chroma_mode() const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		return (l && kind_is_intra(l->kind) && l->kind != MB_IPCM && l->chroma_mode) +
+		       (t && kind_is_intra(t->kind) && t->kind != MB_IPCM && t->chroma_mode);
+	}
+	int cabac_inc_t8x8() const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		return (l && l->t8x8) + (t && t->t8x8);
+	}
+	// bits = coded_block_pattern luma bins of the current MB decoded so far
+	int cabac_inc_cbp_luma(int b8, int bits) const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		const int ca = l ? l->cbp : 0x0f, cb = t ? t->cbp : 0x0f;
+		switch (b8) {
+		case 0: return !(ca & 2) + 2 * !(cb & 4);
+		case 1: return !(bits & 1) + 2 * !(cb & 8);
+		case 2: return !(ca & 8) + 2 * !(bits & 1);
+		default: return !(bits & 4) + 2 * !(bits & 2);
+		}
+	}
+	int cabac_inc_cbp_chroma(int bin) const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		const int ca = l ? l->cbp >> 4 : 0, cb = t ? t->cbp >> 4 : 0;
+		return bin == 0 ? (ca != 0) + 2 * (cb != 0) : (ca == 2) + 2 * (cb == 2);
+	}
+	int cabac_inc_ref(int list, int x4, int y4) const {
+		const size_t g = (size_t)(env.mby * 4 + y4) * w4 + env.mbx * 4 + x4;
+		const int a = (x4 > 0 || env.availL) ? refgt0[list][g - 1] : 0;
+		const int b = (y4 > 0 || env.availT) ? refgt0[list][g - w4] : 0;
+		return a + 2 * b;
+	}
+	int cabac_mvd_sum(int list, int x4, int y4, int comp) const {
+		const size_t g = (size_t)(env.mby * 4 + y4) * w4 + env.mbx * 4 + x4;
+		const int a = (x4 > 0 || env.availL) ? mvd[list][(g - 1) * 2 + comp] : 0;
+		const int b = (y4 > 0 || env.availT) ? mvd[list][(g - w4) * 2 + comp] : 0;
+		return a + b;
+	}
+	void set_mvd(int list, int x4, int y4, int pw, int ph, int dx, int dy) {
+		dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+		const uint8_t ax = (uint8_t)(dx > 127 ? 127 : dx), ay = (uint8_t)(dy > 127 ? 127 : dy);
+		for (int y = y4; y < y4 + ph; ++y) {
+			size_t g = (size_t)(env.mby * 4 + y) * w4 + env.mbx * 4 + x4;
+			for (int x = 0; x < pw; ++x) { mvd[list][(g + x) * 2] = ax; mvd[list][(g + x) * 2 + 1] = ay; }
+		}
+	}
+	void set_refgt0(int list, int x4, int y4, int pw, int ph, int refidx) {
+		for (int y = y4; y < y4 + ph; ++y)
+			memset(&refgt0[list][(size_t)(env.mby * 4 + y) * w4 + env.mbx * 4 + x4], refidx > 0, pw);
+	}
+	// coded_block_flag: luma 4x4 block at (x4, y4), chroma AC block (x, y) of plane c, DC blocks
+	int cabac_inc_cbf_luma(int x4, int y4, bool cur_intra) const {
+		const int a = x4 > 0 ? env.nnz_cur[y4 * 4 + x4 - 1] != 0 : (env.nnz_left ? env.nnz_left[y4 * 4 + 3] != 0 : cur_intra);
+		const int b = y4 > 0 ? env.nnz_cur[(y4 - 1) * 4 + x4] != 0 : (env.nnz_top ? env.nnz_top[12 + x4] != 0 : cur_intra);
+		return a + 2 * b;
+	}
+	int cabac_inc_cbf_chroma_ac(int c, int x, int y, bool cur_intra) const {
+		const int base = 16 + c * 4;
+		const int a = x > 0 ? env.nnz_cur[base + y * 2] != 0 : (env.nnz_left ? env.nnz_left[base + y * 2 + 1] != 0 : cur_intra);
+		const int b = y > 0 ? env.nnz_cur[base + x] != 0 : (env.nnz_top ? env.nnz_top[base + 2 + x] != 0 : cur_intra);
+		return a + 2 * b;
+	}
+	int cabac_inc_cbf_dc(int flag, bool cur_intra) const {
+		const MbInfo *l = mb_left(), *t = mb_top();
+		const int a = l ? (l->cflags & flag) != 0 : cur_intra;
+		const int b = t ? (t->cflags & flag) != 0 : cur_intra;
+		return a + 2 * b;
 	}
 
 	// 8.3.1.1: predIntra4x4PredMode for the 4x4 block at raster (x4, y4) of the current MB.

@@ -9,14 +9,16 @@
 // parse is written from ITU-T H.264; the reference's observable behaviour is preserved where
 // it decides the output: DPB insertion / bumping / output order (h264.cpp:695-867), frame
 // buffer choice (924-962), POC derivation quirks (1121-1215), slice-header order (1417-1579),
-// picture-end processing (11022-11050).  Scope of this revision: frame pictures, CAVLC,
-// I and P slices (Baseline / Main without B), 4x4 transform.  B slices, CABAC and the 8x8
-// transform are rejected with an error, not approximated.
+// picture-end processing (11022-11050).  Scope: frame pictures; CAVLC and CABAC; I, P and B
+// slices; 4x4 transform, and the 8x8 transform / Intra8x8 under CABAC (the reference's CAVLC
+// 8x8 path is not usable).  Interlaced coding and CAVLC + 8x8 are rejected with
+// an error, not approximated.
 #include <algorithm>
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
 #include "frontend.h"
+#include "h264_cabac.h"
 #include "h264_cavlc_tables.h"
 #include "h264_common.h"
 
@@ -136,6 +138,7 @@ struct SliceHeader {
 	int poc;
 	int num_ref_idx_active[2];
 	bool direct_spatial;
+	int cabac_init_idc;
 	int qp;
 	int disable_deblock, alpha_off, beta_off;
 	// dec_ref_pic_marking
@@ -435,8 +438,8 @@ private:
 		const Pps &pps = pps_[pps_id];
 		const Sps &sps = sps_[pps.sps_id];
 		if (!sps.valid) return -1;
-		if (pps.cabac || pps.transform_8x8 || !sps.frame_mbs_only) {
-			fprintf(stderr, "m2dec_b200: H.264 feature outside this revision (CABAC / 8x8 transform / interlace)\n");
+		if ((pps.transform_8x8 && !pps.cabac) || !sps.frame_mbs_only) {
+			fprintf(stderr, "m2dec_b200: H.264 feature outside this revision (CAVLC with 8x8 transform / interlace)\n");
 			unsupported_ = true;
 			return -3;
 		}
@@ -503,6 +506,11 @@ private:
 				}
 			}
 		}
+		h.cabac_init_idc = 0;
+		if (pps.cabac && st != SLICE_I) {
+			h.cabac_init_idc = (int)br_.ue();
+			if (h.cabac_init_idc > 2) return -1;
+		}
 		h.qp = pps.pic_init_qp + br_.se();
 		h.disable_deblock = 0;
 		h.alpha_off = h.beta_off = 0;
@@ -518,7 +526,10 @@ private:
 		slice_num_++;
 		bslice_ = st == SLICE_B;
 		direct_8x8_inference_ = sps.direct_8x8_inference != 0;
-		slice_data(sps, pps);
+		cabac_ = pps.cabac != 0;
+		ctx_.cabac = cabac_;
+		if (cabac_) slice_data_cabac(pps);
+		else slice_data(sps, pps);
 		// picture end (h264.cpp:11022-11050)
 		if (mb_addr_ >= mb_w_ * mb_h_) {
 			end_picture(sps);
@@ -808,6 +819,77 @@ private:
 		}
 	}
 
+	// ---- slice data (CABAC, 7.3.4 with entropy_coding_mode_flag = 1) -------------------------------
+	void slice_data_cabac(const Pps &pps) {
+		const SliceHeader &h = hdr_;
+		qp_ = h.qp;
+		mb_addr_ = h.first_mb;
+		const int total = mb_w_ * mb_h_;
+		br_.byte_align();     // cabac_alignment_one_bit
+		cs_.e.m.init(h.qp, h.type == SLICE_I ? 0 : 1 + h.cabac_init_idc);
+		cs_.e.start(&br_);
+		last_dqp_ = 0;
+		while (mb_addr_ < total) {
+			bool skipped = false;
+			if (h.type != SLICE_I) {
+				ctx_.open_mb(mb_addr_ % mb_w_, mb_addr_ / mb_w_, slice_num_);
+				skipped = cs_.mb_skip(h.type == SLICE_B, ctx_.cabac_inc_skip(), 0) != 0;
+			}
+			if (skipped) { skip_mb(pps); last_dqp_ = 0; }
+			else macroblock(pps);
+			mb_addr_++;
+			if (br_.overrun()) throw BitError();
+			if (cs_.end_of_slice(0)) break;
+		}
+	}
+
+	// ---- syntax elements, either entropy coder -------------------------------------------------------
+	int rd_mb_type() {
+		if (!cabac_) return (int)br_.ue();
+		if (hdr_.type == SLICE_I) return cs_.mb_type_intra(3, true, ctx_.cabac_inc_mbtype_i(), 0);
+		if (hdr_.type == SLICE_P) return cs_.mb_type_p(0);
+		return cs_.mb_type_b(ctx_.cabac_inc_mbtype_b(), 0);
+	}
+	int rd_sub_mb_type() {
+		if (!cabac_) return (int)br_.ue();
+		return bslice_ ? cs_.sub_mb_type_b(0) : cs_.sub_mb_type_p(0);
+	}
+	// reference index of the partition at (x4, y4), pw x ph 4-pel units
+	int rd_ref(int l, int x4, int y4, int pw, int ph, int nref) {
+		int r = 0;
+		if (nref > 1) {
+			if (cabac_) r = cs_.ref_idx(ctx_.cabac_inc_ref(l, x4, y4), 0);
+			else r = nref == 2 ? (int)(br_.get1() ^ 1) : (int)br_.ue();
+			if (r >= nref) throw BitError();
+		}
+		if (cabac_) ctx_.set_refgt0(l, x4, y4, pw, ph, r);
+		return r;
+	}
+	void rd_mvd(int l, int x4, int y4, int pw, int ph, int d[2]) {
+		if (!cabac_) { d[0] = br_.se(); d[1] = br_.se(); return; }
+		d[0] = cs_.mvd(40, ctx_.cabac_mvd_sum(l, x4, y4, 0), 0);
+		d[1] = cs_.mvd(47, ctx_.cabac_mvd_sum(l, x4, y4, 1), 0);
+		ctx_.set_mvd(l, x4, y4, pw, ph, d[0], d[1]);
+	}
+	int rd_cbp(bool intra) {
+		if (cabac_) return cs_.cbp(ctx_, 0);
+		unsigned code = br_.ue();
+		if (code > 47) throw BitError();
+		return cbp_from_code[intra ? 0 : 1][code];
+	}
+	int rd_chroma_mode() {
+		int v = cabac_ ? cs_.chroma_mode(ctx_.cabac_inc_chroma_mode(), 0) : (int)br_.ue();
+		if (v > 3) throw BitError();
+		return v;
+	}
+	int rd_ipred(int pred) {
+		if (cabac_) return cs_.ipred_mode(pred, 0);
+		if (br_.get1()) return pred;
+		int rem = (int)br_.get(3);
+		return rem < pred ? rem : rem + 1;
+	}
+	bool rd_t8x8() { return cs_.transform8x8(ctx_.cabac_inc_t8x8(), 0) != 0; }
+
 	void open_mb(int mbx, int mby) {
 		ctx_.open_mb(mbx, mby, slice_num_);
 		b2_h264_mb &m = mbs_[(size_t)mby * mb_w_ + mbx];
@@ -872,10 +954,11 @@ private:
 		set_mb_qp(m, pps);
 		if (hdr_.type == SLICE_B) {
 			DirectOut d;
-			derive_direct(mbx, mby, d);
+			set_shape(mbx, mby, derive_direct(mbx, mby, d, true), false);
 			apply_direct(m, mbx, mby, d, 0xf);
 		} else {
 			int16_t mv[2];
+			set_shape(mbx, mby, SHAPE_16x16, false);
 			ctx_.pskip_mv(mbx, mby, slice_num_, mv);
 			ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, ref_frame_of(0, 0), mv[0], mv[1]);
 			emit_mc_p(m, 0, 0, 4, 4, 0, mv[0], mv[1]);
@@ -884,16 +967,41 @@ private:
 		info.kind = MB_SKIP;
 		info.qp_y = (uint8_t)qp_;
 		info.cbp = 0;
+		if (hdr_.type == SLICE_B) info.cflags |= MBF_DIRECT16;
 		memset(ctx_.nnz_of(mbx, mby), 0, 24);
 		finish_mb(mbx, mby, pps, qp_);
 	}
 
 	// ---- direct prediction (B_Skip, B_Direct_16x16, direct 8x8 sub-macroblocks) ------------------
-	void derive_direct(int mbx, int mby, DirectOut &d) {
+	// whole: B_Skip / B_Direct_16x16 (as opposed to a direct sub-macroblock of B_8x8).  Returns
+	// the partition shape the reference then treats the macroblock as (its deblocking-strength
+	// derivation runs on the co-located macroblock's shape, h264.cpp:9426, 10163).
+	int derive_direct(int mbx, int mby, DirectOut &d, bool whole) {
 		const RefPic &c1 = list_[1].empty() ? RefPic{-1, -1, -1, 0} : list_[1][0];
-		const ColPic *col = c1.frame_idx >= 0 ? &col_[c1.frame_idx] : nullptr;
-		if (hdr_.direct_spatial) ctx_.direct_spatial(mbx, mby, slice_num_, col, c1.long_idx < 0, direct_8x8_inference_, d);
-		else ctx_.direct_temporal(mbx, mby, col, direct_8x8_inference_, list_[0].data(), (int)list_[0].size(), list_[1].data(), cur_poc_, d);
+		ColPic *col = c1.frame_idx >= 0 ? &col_[c1.frame_idx] : nullptr;
+		const size_t mbi = (size_t)mby * mb_w_ + mbx;
+		const bool have_shape = col && col->shape.size() > mbi;
+		int shape = have_shape ? col->shape[mbi] : SHAPE_16x16;
+		if (!hdr_.direct_spatial) {
+			ctx_.direct_temporal(mbx, mby, col, direct_8x8_inference_, list_[0].data(), (int)list_[0].size(), list_[1].data(), cur_poc_, d);
+			return shape;
+		}
+		if (!whole) {
+			ctx_.direct_spatial(mbx, mby, slice_num_, col, c1.long_idx < 0, direct_8x8_inference_, d);
+			return shape;
+		}
+		// The reference hands the shape to its bookkeeping by overwriting the co-located
+		// picture's record whenever the co-located motion is not consulted (h264.cpp:9786, 9968,
+		// 9975); later pictures that share the co-located picture see the overwritten value.
+		int refs[2];
+		DirectOut probe;
+		ctx_.direct_spatial(mbx, mby, slice_num_, col, c1.long_idx < 0, direct_8x8_inference_, probe, -1, refs);
+		if ((refs[0] < 0 && refs[1] < 0) || c1.long_idx >= 0 || (refs[0] != 0 && refs[1] != 0)) {
+			shape = SHAPE_16x16;
+			if (have_shape) col->shape[mbi] = SHAPE_16x16;
+		}
+		ctx_.direct_spatial(mbx, mby, slice_num_, col, c1.long_idx < 0, direct_8x8_inference_, d, shape == SHAPE_8x8 ? -1 : shape);
+		return shape;
 	}
 
 	// store the motion of the direct-predicted 8x8 quadrants in `quads` and emit their MC records
@@ -922,6 +1030,16 @@ private:
 					emit_mc(m, x, y, step, step, d.ref[i], d.mv[i]);
 				}
 		}
+	}
+
+	// partition shape of the current MB (kept for co-located use) and the class of its
+	// deblocking-strength derivation in the reference: coded8x8 = P_8x8 / B_8x8
+	// (store_info_intermb8x8) as opposed to a direct-predicted MB on an 8x8 co-located shape
+	void set_shape(int mbx, int mby, int shape, bool coded8x8) {
+		MbInfo &info = ctx_.info(mbx, mby);
+		info.cflags = (uint8_t)((info.cflags & ~(3 << MBF_SHAPE_SHIFT)) | (shape << MBF_SHAPE_SHIFT));
+		// bit 0: MB edges, bit 1: centre edges, bit 2: the other inner edges use the reduced comparison
+		bs_reduced_ = shape == SHAPE_16x16 ? 0 : (shape != SHAPE_8x8 ? 2 : (coded8x8 ? 3 : 6));
 	}
 
 	void set_mb_qp(b2_h264_mb &m, const Pps &pps) {
@@ -999,30 +1117,68 @@ private:
 		return total;
 	}
 
-	// luma 4x4 residuals of one MB for the 8x8 blocks selected by cbp; i16: AC-only blocks
-	void residual_luma(b2_h264_mb &m, int mbx, int mby, int cbp, bool i16) {
+	// luma residual of one MB for the 8x8 blocks selected by cbp; i16: AC-only blocks (cat 1);
+	// t8x8: transform_size_8x8_flag (CABAC only: one 64-coefficient block per 8x8, cat 5)
+	void residual_luma(b2_h264_mb &m, int mbx, int mby, int cbp, bool i16, bool intra, bool t8x8) {
 		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
+		if (t8x8) {
+			for (int q = 0; q < 4; ++q) {
+				const int x4 = (q & 1) * 2, y4 = (q >> 1) * 2;
+				int total = 0;
+				if (cbp & (1 << q)) {
+					int16_t lv[64];
+					memset(lv, 0, sizeof(lv));
+					total = cs_.residual(5, -1, lv, 64);
+					const size_t at = coef_used_;
+					for (int r = 0; r < 4; ++r) new_record();
+					int16_t *rec = &coefs_[at];      // 64 levels, raster 8x8
+					for (int i = 0; i < 64; ++i) rec[zigzag8x8[i]] = lv[i];
+					m.nz |= 0xfu << (1 + 4 * q);
+					if (total > 15) total = 15;
+				}
+				nnz[y4 * 4 + x4] = nnz[y4 * 4 + x4 + 1] = nnz[(y4 + 1) * 4 + x4] = nnz[(y4 + 1) * 4 + x4 + 1] = (uint8_t)total;
+			}
+			return;
+		}
 		for (int k = 0; k < 16; ++k) {
 			int x4 = blk_x[k], y4 = blk_y[k];
 			if (!(cbp & (1 << (k >> 2)))) { nnz[y4 * 4 + x4] = 0; continue; }
-			int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
 			int16_t *rec = new_record();
-			int total = i16 ? residual_block(nc, 15, rec, zigzag4x4, 1) : residual_block(nc, 16, rec, zigzag4x4, 0);
+			int total;
+			if (cabac_) {
+				int16_t lv[16];
+				memset(lv, 0, sizeof(lv));
+				total = cs_.residual(i16 ? 1 : 2, ctx_.cabac_inc_cbf_luma(x4, y4, intra), lv, i16 ? 15 : 16);
+				if (total) for (int i = 0; i < (i16 ? 15 : 16); ++i) rec[zigzag4x4[i + (i16 ? 1 : 0)]] = lv[i];
+			} else {
+				int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
+				total = i16 ? residual_block(nc, 15, rec, zigzag4x4, 1) : residual_block(nc, 16, rec, zigzag4x4, 0);
+			}
 			nnz[y4 * 4 + x4] = (uint8_t)total;
 			if (total) m.nz |= 1u << (1 + k);
 			else drop_record();
 		}
 	}
 
-	void residual_chroma(b2_h264_mb &m, int mbx, int mby, int cbp_chroma) {
+	void residual_chroma(b2_h264_mb &m, int mbx, int mby, int cbp_chroma, bool intra) {
 		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
+		MbInfo &info = ctx_.info(mbx, mby);
 		memset(nnz + 16, 0, 8);
 		if (!cbp_chroma) return;
 		static const uint8_t scan_dc[4] = {0, 1, 2, 3};
 		int16_t dc[16];
 		memset(dc, 0, sizeof(dc));
 		int any = 0;
-		for (int c = 0; c < 2; ++c) any |= residual_block(-1, 4, dc + c * 4, scan_dc, 0);
+		for (int c = 0; c < 2; ++c) {
+			int n;
+			if (cabac_) {
+				n = cs_.residual(3, ctx_.cabac_inc_cbf_dc(MBF_CBF_CB_DC << c, intra), dc + c * 4, 4);
+				if (n) info.cflags |= (uint8_t)(MBF_CBF_CB_DC << c);
+			} else {
+				n = residual_block(-1, 4, dc + c * 4, scan_dc, 0);
+			}
+			any |= n;
+		}
 		if (any) {
 			memcpy(new_record(), dc, sizeof(dc));
 			m.nz |= 1u << 17;
@@ -1031,9 +1187,17 @@ private:
 			for (int c = 0; c < 2; ++c)
 				for (int b = 0; b < 4; ++b) {
 					int x = b & 1, y = b >> 1;
-					int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, x, y, slice_num_);
 					int16_t *rec = new_record();
-					int total = residual_block(nc, 15, rec, zigzag4x4, 1);
+					int total;
+					if (cabac_) {
+						int16_t lv[16];
+						memset(lv, 0, sizeof(lv));
+						total = cs_.residual(4, ctx_.cabac_inc_cbf_chroma_ac(c, x, y, intra), lv, 15);
+						if (total) for (int i = 0; i < 15; ++i) rec[zigzag4x4[i + 1]] = lv[i];
+					} else {
+						int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, x, y, slice_num_);
+						total = residual_block(nc, 15, rec, zigzag4x4, 1);
+					}
 					nnz[16 + c * 4 + b] = (uint8_t)total;
 					if (total) m.nz |= 1u << (18 + c * 4 + b);
 					else drop_record();
@@ -1042,7 +1206,8 @@ private:
 	}
 
 	void read_qp_delta() {
-		int d = br_.se();
+		int d = cabac_ ? cs_.qp_delta(last_dqp_ != 0, 0) : br_.se();
+		last_dqp_ = d;
 		qp_ += d;
 		if (qp_ < 0) qp_ += 52;
 		else if (qp_ >= 52) qp_ -= 52;
@@ -1054,7 +1219,7 @@ private:
 		open_mb(mbx, mby);
 		b2_h264_mb &m = mbs_[mb_addr_];
 		MbInfo &info = ctx_.info(mbx, mby);
-		int mb_type = br_.ue();
+		int mb_type = rd_mb_type();
 		if (h.type == SLICE_P) {
 			if (mb_type >= 5) mb_type -= 5;          // intra types follow the five P types
 			else { inter_mb(m, mbx, mby, mb_type, pps); return; }
@@ -1080,49 +1245,64 @@ private:
 		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
 		int8_t *ip = ctx_.ipred_of(mbx, mby);
 		if (mb_type == 25) {   // I_PCM (h264.cpp:4736-4761)
-			br_.byte_align();
+			if (cabac_) cs_.e.before_pcm();
+			else br_.byte_align();
 			m.type = B2_H4_IPCM;
 			m.nz = 0xfff;
 			for (int r = 0; r < 12; ++r) {
 				uint8_t *dst = (uint8_t *)new_record();
 				for (int i = 0; i < 32; ++i) dst[i] = (uint8_t)br_.get(8);
 			}
+			if (cabac_) cs_.e.start(&br_);
 			set_mb_qp(m, pps);
 			memset(nnz, 16, 24);
 			memset(ip, 2, 16);
 			info.kind = MB_IPCM;
 			info.qp_y = (uint8_t)qp_;
 			info.cbp = 0x2f;
+			info.cflags = MBF_CBF_LUMA_DC | MBF_CBF_CB_DC | MBF_CBF_CR_DC;
+			last_dqp_ = 0;
 			finish_mb(mbx, mby, pps, 0);
 			return;
 		}
 		int cbp;
-		if (mb_type == 0) {   // I_NxN (4x4 only in this revision)
-			m.type = B2_H4_I4x4;
-			info.kind = MB_I4x4;
-			for (int k = 0; k < 16; ++k) {
-				int x4 = blk_x[k], y4 = blk_y[k];
-				int pred = ctx_.predict_ipred(mbx, mby, x4, y4, slice_num_, pps.constrained_intra != 0);
-				int mode = pred;
-				if (!br_.get1()) {
-					int rem = (int)br_.get(3);
-					mode = rem < pred ? rem : rem + 1;
+		if (mb_type == 0) {   // I_NxN
+			const bool t8x8 = pps.transform_8x8 && rd_t8x8();
+			if (t8x8) {
+				m.type = B2_H4_I8x8;
+				m.flags |= B2_H4_T8x8;
+				info.kind = MB_I8x8;
+				info.t8x8 = 1;
+				for (int q = 0; q < 4; ++q) {
+					const int x4 = (q & 1) * 2, y4 = (q >> 1) * 2;
+					int pred = ctx_.predict_ipred(mbx, mby, x4, y4, slice_num_, pps.constrained_intra != 0);
+					int mode = rd_ipred(pred);
+					ip[y4 * 4 + x4] = ip[y4 * 4 + x4 + 1] = ip[(y4 + 1) * 4 + x4] = ip[(y4 + 1) * 4 + x4 + 1] = (int8_t)mode;
+					m.i4_modes[q >> 1] |= (uint8_t)(mode << ((q & 1) * 4));
 				}
-				ip[y4 * 4 + x4] = (int8_t)mode;
-				m.i4_modes[k >> 1] |= (uint8_t)(mode << ((k & 1) * 4));
+			} else {
+				m.type = B2_H4_I4x4;
+				info.kind = MB_I4x4;
+				for (int k = 0; k < 16; ++k) {
+					int x4 = blk_x[k], y4 = blk_y[k];
+					int pred = ctx_.predict_ipred(mbx, mby, x4, y4, slice_num_, pps.constrained_intra != 0);
+					int mode = rd_ipred(pred);
+					ip[y4 * 4 + x4] = (int8_t)mode;
+					m.i4_modes[k >> 1] |= (uint8_t)(mode << ((k & 1) * 4));
+				}
 			}
-			m.chroma_mode = (uint8_t)br_.ue();
-			if (m.chroma_mode > 3) throw BitError();
-			unsigned code = br_.ue();
-			if (code > 47) throw BitError();
-			cbp = cbp_from_code[0][code];
+			m.chroma_mode = (uint8_t)rd_chroma_mode();
+			info.chroma_mode = m.chroma_mode;
+			cbp = rd_cbp(true);
 			// The reference feeds the no-residual Intra4x4 path the unmasked availability
 			// (hazard 8, h264.cpp:3292); carried here so the device needs no special case.
-			m.intra_avail = (uint8_t)((cbp & 15) ? avail_intra : avail);
+			// Intra8x8 always gets the masked value (h264.cpp:4150-4163).
+			m.intra_avail = (uint8_t)((t8x8 || (cbp & 15)) ? avail_intra : avail);
 			m.intra_avail_c = (uint8_t)avail_intra;
 			if (cbp) read_qp_delta();
+			else last_dqp_ = 0;
 			set_mb_qp(m, pps);
-			residual_luma(m, mbx, mby, cbp & 15, false);
+			residual_luma(m, mbx, mby, cbp & 15, false, true, t8x8);
 		} else {               // Intra16x16
 			m.type = B2_H4_I16x16;
 			info.kind = MB_I16x16;
@@ -1133,23 +1313,53 @@ private:
 			int cbp_luma = t >= 12 ? 15 : 0;
 			cbp = cbp_luma | (cbp_chroma << 4);
 			m.intra_avail = m.intra_avail_c = (uint8_t)avail_intra;
-			m.chroma_mode = (uint8_t)br_.ue();
-			if (m.chroma_mode > 3) throw BitError();
+			m.chroma_mode = (uint8_t)rd_chroma_mode();
+			info.chroma_mode = m.chroma_mode;
 			read_qp_delta();
 			set_mb_qp(m, pps);
-			int nc = ctx_.cavlc_nc(mbx, mby, 0, 0, 0, slice_num_);
 			int16_t dc[16];
 			memset(dc, 0, sizeof(dc));
-			if (residual_block(nc, 16, dc, zigzag4x4, 0)) {
+			int ndc;
+			if (cabac_) {
+				int16_t lv[16];
+				memset(lv, 0, sizeof(lv));
+				ndc = cs_.residual(0, ctx_.cabac_inc_cbf_dc(MBF_CBF_LUMA_DC, true), lv, 16);
+				if (ndc) {
+					info.cflags |= MBF_CBF_LUMA_DC;
+					for (int i = 0; i < 16; ++i) dc[zigzag4x4[i]] = lv[i];
+				}
+			} else {
+				int nc = ctx_.cavlc_nc(mbx, mby, 0, 0, 0, slice_num_);
+				ndc = residual_block(nc, 16, dc, zigzag4x4, 0);
+			}
+			if (ndc) {
 				memcpy(new_record(), dc, sizeof(dc));
 				m.nz |= 1;
 			}
-			residual_luma(m, mbx, mby, cbp_luma, true);
+			residual_luma(m, mbx, mby, cbp_luma, true, true, false);
 		}
-		residual_chroma(m, mbx, mby, cbp >> 4);
+		residual_chroma(m, mbx, mby, cbp >> 4, true);
 		info.qp_y = (uint8_t)qp_;
 		info.cbp = (uint8_t)cbp;
-		info.chroma_mode = m.chroma_mode;
+		finish_mb(mbx, mby, pps, qp_);
+	}
+
+	// coded_block_pattern, transform_size_8x8_flag, mb_qp_delta and residual of an inter MB.
+	// may_t8x8: no sub-macroblock partition smaller than 8x8 and, for direct prediction,
+	// direct_8x8_inference_flag (7.3.5)
+	void inter_residual(b2_h264_mb &m, int mbx, int mby, const Pps &pps, bool may_t8x8) {
+		MbInfo &info = ctx_.info(mbx, mby);
+		int cbp = rd_cbp(false);
+		info.cbp = (uint8_t)cbp;      // visible to the chroma bins' own context? no: neighbours only
+		bool t8x8 = false;
+		if ((cbp & 15) && pps.transform_8x8 && may_t8x8) t8x8 = rd_t8x8();
+		if (t8x8) { m.flags |= B2_H4_T8x8; info.t8x8 = 1; }
+		if (cbp) read_qp_delta();
+		else last_dqp_ = 0;
+		set_mb_qp(m, pps);
+		residual_luma(m, mbx, mby, cbp & 15, false, false, t8x8);
+		residual_chroma(m, mbx, mby, cbp >> 4, false);
+		info.qp_y = (uint8_t)qp_;
 		finish_mb(mbx, mby, pps, qp_);
 	}
 
@@ -1159,39 +1369,39 @@ private:
 		m.type = B2_H4_INTER;
 		info.kind = MB_INTER;
 		memset(ctx_.ipred_of(mbx, mby), 2, 16);
-		int nref = h.num_ref_idx_active[0];
-		auto read_ref = [&]() -> int {
-			if (nref <= 1) return 0;
-			int r = nref == 2 ? (int)(br_.get1() ^ 1) : (int)br_.ue();
-			if (r >= nref) throw BitError();
-			return r;
-		};
+		const int nref = h.num_ref_idx_active[0];
 		auto do_part = [&](int x4, int y4, int pw, int ph, int ref, int shape, int part) {
 			int16_t pred[2];
+			int d[2];
 			ctx_.predict_mv(0, mbx, mby, x4, y4, pw, ref, slice_num_, shape, part, pred);
-			int mvx = pred[0] + br_.se();
-			int mvy = pred[1] + br_.se();
+			rd_mvd(0, x4, y4, pw, ph, d);
+			int mvx = pred[0] + d[0];
+			int mvy = pred[1] + d[1];
 			ctx_.set_motion(0, mbx, mby, x4, y4, pw, ph, ref, ref_frame_of(0, ref), mvx, mvy);
 			emit_mc_p(m, x4, y4, pw, ph, ref, mvx, mvy);
 		};
+		bool may_t8x8 = true;
+		set_shape(mbx, mby, mb_type > 3 ? SHAPE_8x8 : mb_type, true);
 		if (mb_type == 0) {
-			int r = read_ref();
+			int r = rd_ref(0, 0, 0, 4, 4, nref);
 			do_part(0, 0, 4, 4, r, 0, 0);
 		} else if (mb_type == 1) {
-			int r0 = read_ref(), r1 = read_ref();
+			int r0 = rd_ref(0, 0, 0, 4, 2, nref), r1 = rd_ref(0, 0, 2, 4, 2, nref);
 			do_part(0, 0, 4, 2, r0, 1, 0);
 			do_part(0, 2, 4, 2, r1, 1, 1);
 		} else if (mb_type == 2) {
-			int r0 = read_ref(), r1 = read_ref();
+			int r0 = rd_ref(0, 0, 0, 2, 4, nref), r1 = rd_ref(0, 2, 0, 2, 4, nref);
 			do_part(0, 0, 2, 4, r0, 2, 0);
 			do_part(2, 0, 2, 4, r1, 2, 1);
 		} else {
+			if (mb_type > 4) throw BitError();
 			int sub[4], ref[4];
 			for (int i = 0; i < 4; ++i) {
-				sub[i] = (int)br_.ue();
+				sub[i] = rd_sub_mb_type();
 				if (sub[i] > 3) throw BitError();
+				if (sub[i]) may_t8x8 = false;
 			}
-			for (int i = 0; i < 4; ++i) ref[i] = mb_type == 4 ? 0 : read_ref();   // P_8x8ref0
+			for (int i = 0; i < 4; ++i) ref[i] = mb_type == 4 ? 0 : rd_ref(0, (i & 1) * 2, (i >> 1) * 2, 2, 2, nref);   // P_8x8ref0
 			for (int i = 0; i < 4; ++i) {
 				int bx = (i & 1) * 2, by = (i >> 1) * 2;
 				switch (sub[i]) {
@@ -1204,16 +1414,7 @@ private:
 				}
 			}
 		}
-		unsigned code = br_.ue();
-		if (code > 47) throw BitError();
-		int cbp = cbp_from_code[1][code];
-		if (cbp) read_qp_delta();
-		set_mb_qp(m, pps);
-		residual_luma(m, mbx, mby, cbp & 15, false);
-		residual_chroma(m, mbx, mby, cbp >> 4);
-		info.qp_y = (uint8_t)qp_;
-		info.cbp = (uint8_t)cbp;
-		finish_mb(mbx, mby, pps, qp_);
+		inter_residual(m, mbx, mby, pps, may_t8x8);
 	}
 
 	// B macroblock (7.3.5.1, 7.3.5.2; Tables 7-14, 7-18)
@@ -1229,8 +1430,12 @@ private:
 		int sub_use[4] = {0, 0, 0, 0};
 		DirectOut dir;
 		int direct_quads = 0;
+		bool may_t8x8 = true;
+		if (mb_type > 22) throw BitError();
 		if (mb_type == 0) {
 			direct_quads = 0xf;
+			info.cflags |= MBF_DIRECT16;
+			may_t8x8 = direct_8x8_inference_;
 		} else if (mb_type < 22) {
 			// 1..3: 16x16 L0/L1/Bi; 4..21: pairs (16x8, 8x16) with the prediction modes of Table 7-14
 			static const uint8_t modes[22][2] = {{0, 0}, {1, 0}, {2, 0}, {3, 0}, {1, 1}, {1, 1}, {2, 2}, {2, 2}, {1, 2}, {1, 2}, {2, 1}, {2, 1},
@@ -1250,11 +1455,17 @@ private:
 			static const uint8_t sub_mode[13] = {0, 1, 2, 3, 1, 1, 2, 2, 3, 3, 1, 2, 3};
 			static const uint8_t sub_shape[13] = {0, 0, 0, 0, 1, 2, 1, 2, 1, 2, 3, 3, 3};   // 0 8x8, 1 8x4, 2 4x8, 3 4x4
 			for (int q = 0; q < 4; ++q) {
-				unsigned st = br_.ue();
+				unsigned st = (unsigned)rd_sub_mb_type();
 				if (st > 12) throw BitError();
 				int bx = (q & 1) * 2, by = (q >> 1) * 2, use = sub_mode[st];
 				sub_use[q] = use;
-				if (use == 0) { direct_quads |= 1 << q; parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 2, 0, 0, 0, (int8_t)q}; continue; }
+				if (use == 0) {
+					direct_quads |= 1 << q;
+					if (!direct_8x8_inference_) may_t8x8 = false;
+					parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 2, 0, 0, 0, (int8_t)q};
+					continue;
+				}
+				if (sub_shape[st]) may_t8x8 = false;
 				switch (sub_shape[st]) {
 				case 0: parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 2, 0, 0, (int8_t)use, (int8_t)q}; break;
 				case 1: parts[np++] = Part{(int8_t)bx, (int8_t)by, 2, 1, 0, 0, (int8_t)use, (int8_t)q};
@@ -1267,7 +1478,11 @@ private:
 				}
 			}
 		}
-		if (direct_quads) derive_direct(mbx, mby, dir);
+		if (mb_type == 0) set_shape(mbx, mby, derive_direct(mbx, mby, dir, true), false);
+		else {
+			if (direct_quads) derive_direct(mbx, mby, dir, false);
+			set_shape(mbx, mby, mb_type == 22 ? SHAPE_8x8 : (mb_type <= 3 ? SHAPE_16x16 : ((mb_type & 1) ? SHAPE_8x16 : SHAPE_16x8)), true);
+		}
 		// reference indices: list 0 for every (sub-)macroblock partition that uses it, then list 1
 		int ref[4][2];
 		const int nsub = mb_type == 22 ? 4 : (mb_type == 0 ? 0 : (mb_type <= 3 ? 1 : 2));
@@ -1276,12 +1491,11 @@ private:
 			const int nref = h.num_ref_idx_active[l];
 			for (int q = 0; q < nsub; ++q) {
 				if (!(sub_use[q] & (1 << l))) continue;
-				int r = 0;
-				if (nref > 1) {
-					r = nref == 2 ? (int)(br_.get1() ^ 1) : (int)br_.ue();
-					if (r >= nref) throw BitError();
-				}
-				ref[q][l] = r;
+				// area the index applies to: the partition (16x16 / 16x8 / 8x16) or the 8x8 quadrant
+				int x4, y4, pw, ph;
+				if (mb_type == 22) { x4 = (q & 1) * 2; y4 = (q >> 1) * 2; pw = ph = 2; }
+				else { x4 = parts[q].x4; y4 = parts[q].y4; pw = parts[q].pw; ph = parts[q].ph; }
+				ref[q][l] = rd_ref(l, x4, y4, pw, ph, nref);
 			}
 		}
 		// motion vector differences: list 0 for all partitions in order, then list 1
@@ -1302,10 +1516,12 @@ private:
 				}
 				if (!(p.use & (1 << l))) { ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, -1, -1, 0, 0); continue; }
 				int16_t pred[2];
+				int d[2];
 				const int r = ref[p.sub][l];
 				ctx_.predict_mv(l, mbx, mby, p.x4, p.y4, p.pw, r, slice_num_, p.shape, p.part, pred);
-				pmv[i][l][0] = pred[0] + br_.se();
-				pmv[i][l][1] = pred[1] + br_.se();
+				rd_mvd(l, p.x4, p.y4, p.pw, p.ph, d);
+				pmv[i][l][0] = pred[0] + d[0];
+				pmv[i][l][1] = pred[1] + d[1];
 				ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, r, ref_frame_of(l, r), pmv[i][l][0], pmv[i][l][1]);
 			}
 		}
@@ -1325,16 +1541,7 @@ private:
 				emit_mc(m, p.x4, p.y4, p.pw, p.ph, rr, pmv[i]);
 			}
 		}
-		unsigned code = br_.ue();
-		if (code > 47) throw BitError();
-		int cbp = cbp_from_code[1][code];
-		if (cbp) read_qp_delta();
-		set_mb_qp(m, pps);
-		residual_luma(m, mbx, mby, cbp & 15, false);
-		residual_chroma(m, mbx, mby, cbp >> 4);
-		info.qp_y = (uint8_t)qp_;
-		info.cbp = (uint8_t)cbp;
-		finish_mb(mbx, mby, pps, qp_);
+		inter_residual(m, mbx, mby, pps, may_t8x8);
 	}
 
 	// ---- deblocking strengths (8.7.2.1) for the MB just parsed ------------------------------------
@@ -1343,7 +1550,11 @@ private:
 	static inline bool mv_far(const int16_t *a, const int16_t *b) {
 		return (unsigned)(a[0] - b[0] + 3) > 6u || (unsigned)(a[1] - b[1] + 3) > 6u;
 	}
-	inline int bs_inter(size_t g0, size_t g1, bool nz0, bool nz1) const {
+	// reduced: where the reference's derivation for this kind of edge skips the crosswise
+	// comparison when all four reference pictures are the same one (str_mv_calc8x8_edge_bidir,
+	// str_mv_calc8x8_half_bidir, is_str_mv_calc16x8_center_bidir, str_mv_calc8x8_inner_bidir:
+	// h264.cpp:8797, 8926, 7476, 9218) -- a deviation from 8.7.2.1 that decides pixels
+	inline int bs_inter(size_t g0, size_t g1, bool nz0, bool nz1, bool reduced = false) const {
 		if (nz0 | nz1) return 2;
 		const int a0 = ctx_.refpic[0][g0], b0 = ctx_.refpic[0][g1];
 		const int16_t *ma0 = &ctx_.mv[0][g0 * 2], *mb0 = &ctx_.mv[0][g1 * 2];
@@ -1358,6 +1569,7 @@ private:
 			return ((a0 >= 0 && mv_far(ma0, mb1)) || (a1 >= 0 && mv_far(ma1, mb0))) ? 1 : 0;
 		}
 		bool straight = mv_far(ma0, mb0) || mv_far(ma1, mb1), cross = mv_far(ma0, mb1) || mv_far(ma1, mb0);
+		if (reduced) return straight ? 1 : 0;
 		return (straight && cross) ? 1 : 0;
 	}
 
@@ -1398,11 +1610,13 @@ private:
 			unsigned nzm = 0;
 			for (int i = 0; i < 16; ++i) nzm |= (unsigned)(nnz[i] != 0) << i;
 			if (bslice_ && mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt != 1) {
-				for (int e = 1; e < 4; ++e)
+				for (int e = 1; e < 4; ++e) {
+					const bool red = (bs_reduced_ >> (e == 2 ? 1 : 2)) & 1;
 					for (int sg = 0; sg < 4; ++sg) {
-						bsv |= (uint32_t)bs_inter(g00 + sg * w4 + e - 1, g00 + sg * w4 + e, (nzm >> (sg * 4 + e - 1)) & 1, (nzm >> (sg * 4 + e)) & 1) << (e * 8 + sg * 2);
-						bsh |= (uint32_t)bs_inter(g00 + (e - 1) * w4 + sg, g00 + e * w4 + sg, (nzm >> ((e - 1) * 4 + sg)) & 1, (nzm >> (e * 4 + sg)) & 1) << (e * 8 + sg * 2);
+						bsv |= (uint32_t)bs_inter(g00 + sg * w4 + e - 1, g00 + sg * w4 + e, (nzm >> (sg * 4 + e - 1)) & 1, (nzm >> (sg * 4 + e)) & 1, red) << (e * 8 + sg * 2);
+						bsh |= (uint32_t)bs_inter(g00 + (e - 1) * w4 + sg, g00 + e * w4 + sg, (nzm >> ((e - 1) * 4 + sg)) & 1, (nzm >> (e * 4 + sg)) & 1, red) << (e * 8 + sg * 2);
 					}
+				}
 			} else if (mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt == 1) {
 				// one partition: no motion discontinuity inside the macroblock
 				for (int e = 1; e < 4; ++e)
@@ -1437,7 +1651,7 @@ private:
 				else {
 					const uint8_t *ln = ctx_.nnz_of(mbx - 1, mby);
 					for (int sg = 0; sg < 4; ++sg)
-						bsv |= (uint32_t)bs_inter(g00 + sg * w4 - 1, g00 + sg * w4, ln[sg * 4 + 3] != 0, nnz[sg * 4] != 0) << (sg * 2);
+						bsv |= (uint32_t)bs_inter(g00 + sg * w4 - 1, g00 + sg * w4, ln[sg * 4 + 3] != 0, nnz[sg * 4] != 0, bs_reduced_ & 1) << (sg * 2);
 				}
 			}
 			if (top_ok) {
@@ -1445,9 +1659,14 @@ private:
 				else {
 					const uint8_t *tn = ctx_.nnz_of(mbx, mby - 1);
 					for (int sg = 0; sg < 4; ++sg)
-						bsh |= (uint32_t)bs_inter(g00 - w4 + sg, g00 + sg, tn[12 + sg] != 0, nnz[sg] != 0) << (sg * 2);
+						bsh |= (uint32_t)bs_inter(g00 - w4 + sg, g00 + sg, tn[12 + sg] != 0, nnz[sg] != 0, bs_reduced_ & 1) << (sg * 2);
 				}
 			}
+		}
+		if (cur.t8x8) {
+			// transform_size_8x8_flag: the 4x4 edges inside the 8x8 blocks are not filtered (8.7)
+			bsv &= 0x00ff00ffu;
+			bsh &= 0x00ff00ffu;
 		}
 		d.bs_v = bsv;
 		d.bs_h = bsh;
@@ -1478,6 +1697,10 @@ private:
 	std::vector<RefPic> list_[2], init0_;
 	ColPic col_[MAX_H264_FRAMES];
 	bool bslice_ = false, direct_8x8_inference_ = true;
+	bool cabac_ = false;
+	int bs_reduced_ = 0;        // see set_shape
+	int last_dqp_ = 0;          // mb_qp_delta of the previous macroblock in decoding order (CABAC ctxIdxInc)
+	CabacSyntax<CabacDec> cs_;
 	struct { int mode, denom[2]; int8_t w[2][32][3], o[2][32][3]; } wt_;   // mode 0 default, 1 explicit, 2 implicit
 	int prev_frame_num_, poc_lsb_, poc_msb_, frame_num_offset_, cur_poc_;
 	bool prev_mmco5_;

@@ -4,13 +4,14 @@
 //                              bilinear, edge replication by coordinate clamp) fused with
 //                              dequantisation + 4x4 inverse transform + residual add/clip for
 //                              every inter macroblock; each output byte is written once.
-//   h264_intra_kernel   K3+K1  intra 4x4 / 16x16 / chroma prediction + residual, and I_PCM, as
+//                              Macroblocks with transform_size_8x8_flag get the 8x8 transform.
+//   h264_intra_kernel   K3+K1  intra 4x4 / 8x8 / 16x16 / chroma prediction + residual, and I_PCM, as
 //                              an MB-diagonal wavefront (slope 2: left, top, top-right deps).
 //   h264_deblock_kernel K4     in-loop filter from the per-MB strength records, same wavefront.
 //
 // Arithmetic restated from the reference (src/lib/h264.cpp): dequant tables 964-1054 and
-// coeff_writeback 2005-2022; 4x4 transform 2145-2269; DC transforms 4309-4404; intra
-// predictors 2510-2997, 4224-4304, 4561-4705; I_PCM 4736-4761; luma MC 5381-6406 (UMV
+// coeff_writeback 2005-2022; 4x4 transform 2145-2269; 8x8 transform 3942-4080; DC transforms
+// 4309-4404; intra predictors 2510-2997, 3315-3929 (8x8), 4224-4304, 4561-4705; I_PCM 4736-4761; luma MC 5381-6406 (UMV
 // 5932-6116); chroma MC 4859-5330; deblock 10253-10663 with tables h264vld.h:4536-4627.
 // HBM-bound integer/byte work: no tensor cores.
 #include "device_common.cuh"
@@ -22,6 +23,10 @@ __constant__ uint8_t c_blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2,
 __constant__ uint8_t c_blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
 __constant__ uint8_t c_r2b[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
 __constant__ uint8_t c_norm_adjust[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
+__constant__ uint8_t c_norm_adjust8[6][6] = {{20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
+                                             {28, 25, 45, 26, 35, 33}, {32, 28, 51, 30, 40, 38}, {36, 32, 58, 34, 46, 43}};
+// class of position (x & 3) + 4 * (y & 3) of an 8x8 block in the normAdjust8x8 pattern (h264.cpp:1036-1046)
+__constant__ uint8_t c_cls8[16] = {0, 3, 4, 3, 3, 1, 5, 1, 4, 5, 2, 5, 3, 1, 5, 1};
 __constant__ uint8_t c_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20,
 	22, 25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
 __constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8,
@@ -123,6 +128,47 @@ __device__ bool block_residual(const H4Job &job, const b2_h264_mb &m, int b, int
 	c[0] += 32;
 	idct4x4(c, res);
 	return true;
+}
+
+// one dimension of the 8x8 inverse transform (8.5.13; ac8x8transform_interim, h264.cpp:3942-3983)
+__device__ __forceinline__ void idct8_1d(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7, int *o) {
+	int a0 = x0 + x4, a4 = x0 - x4, a2 = (x2 >> 1) - x6, a6 = x2 + (x6 >> 1);
+	int b0 = a0 + a6, b2 = a4 + a2, b4 = a4 - a2, b6 = a0 - a6;
+	int a1 = x5 - x3 - x7 - (x7 >> 1), a3 = x1 + x7 - x3 - (x3 >> 1), a5 = x5 + (x5 >> 1) + x7 - x1, a7 = x3 + x5 + x1 + (x1 >> 1);
+	int b1 = a1 + (a7 >> 2), b7 = a7 - (a1 >> 2), b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5;
+	o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1;
+	o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+
+// Residual of the 8x8-transform luma block q (64 levels, raster, in four consecutive records)
+// into the four 4x4 residual slots res[4q .. 4q+3] (sub-block i at (i & 1, i >> 1), raster 4x4).
+// Dequantisation as qp_matrix8x8 (h264.cpp:997-1054): normAdjust8x8 << (qp/6 - 2), and the
+// reference's truncating right shift of the table entry below qp 12.
+__device__ void block_residual8x8(const H4Job &job, const b2_h264_mb &m, int q, int16_t (*res)[16]) {
+	const int16_t *lv = rec_of(job, m, 1 + 4 * q);
+	const int qp = m.qp_y, sh = qp / 6 - 2;
+	int t[64];
+#pragma unroll
+	for (int y = 0; y < 8; ++y) {
+		int4 raw = __ldg(reinterpret_cast<const int4 *>(lv) + y);
+		int16_t l[8];
+		*reinterpret_cast<int4 *>(l) = raw;
+		int c[8];
+#pragma unroll
+		for (int x = 0; x < 8; ++x) {
+			int na = c_norm_adjust8[qp % 6][c_cls8[(x & 3) + 4 * (y & 3)]];
+			c[x] = l[x] * (sh >= 0 ? na << sh : na >> -sh);
+		}
+		if (y == 0) c[0] += 32;
+		idct8_1d(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], &t[8 * y]);
+	}
+#pragma unroll
+	for (int x = 0; x < 8; ++x) {
+		int o[8];
+		idct8_1d(t[x], t[8 + x], t[16 + x], t[24 + x], t[32 + x], t[40 + x], t[48 + x], t[56 + x], o);
+#pragma unroll
+		for (int y = 0; y < 8; ++y) res[4 * q + (y >> 2) * 2 + (x >> 2)][(y & 3) * 4 + (x & 3)] = (int16_t)(o[y] >> 6);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +328,7 @@ __device__ __forceinline__ void vhalf4x4(const uint32_t R[9], int out[16]) {
 	}
 }
 
-__global__ void __launch_bounds__(INTER_THREADS)
+__global__ void __launch_bounds__(INTER_THREADS, 2)
 h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 	__shared__ __align__(16) int16_t s_res[INTER_MBS][24][16];
 	__shared__ uint32_t s_has[INTER_MBS];
@@ -387,7 +433,13 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 		int j = s_coded[k];
 		int slot = j / 24, bk = j % 24;
 		const b2_h264_mb m = job.mbs[mb0 + slot];
-		if (block_residual(job, m, bk, s_res[slot][bk])) atomicOr(&s_has[slot], 1u << bk);
+		if (bk < 16 && (m.flags & B2_H4_T8x8)) {
+			// 8x8 transform: the entry of the first sub-block does the whole block
+			if ((bk & 3) == 0) {
+				block_residual8x8(job, m, bk >> 2, s_res[slot]);
+				atomicOr(&s_has[slot], 0xfu << bk);
+			}
+		} else if (block_residual(job, m, bk, s_res[slot][bk])) atomicOr(&s_has[slot], 1u << bk);
 	}
 	__syncthreads();
 
@@ -608,7 +660,8 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 // intra wavefront: one warp per macroblock of the diagonal x + 2y = d
 // ------------------------------------------------------------------------------------------------
 struct IntraTile {
-	uint8_t y[17][24];      // row 0 = samples above (col 0 = top-left, cols 1..16 above, 17..20 above-right); col 0 = left
+	uint8_t y[17][28];      // row 0 = samples above (col 0 = top-left, cols 1..16 above, 17..24 above-right); col 0 = left
+	uint8_t f8t[20], f8l[12];   // Intra8x8: filtered reference samples p'[-1..15, -1] and p'[-1, -1..7]
 	uint8_t c[2][9][12];    // per component: row 0 above (col 0 top-left), col 0 left
 	int16_t res[24][16];
 	uint32_t has;
@@ -671,6 +724,57 @@ __device__ int pred4x4_sample(const IntraTile &tl, int bx, int by, int mode, int
 #undef L
 }
 
+// availability of 8x8 block q from the MB-level mask (luma_intra8x8_with_residual, h264.cpp:4093-4118)
+__device__ __forceinline__ int blk8_avail(int q, int a) {
+	return q == 0 ? (a & ~4) | ((a & 2) * 2) : (q == 1 ? (a & ~8) | ((a & 2) * 4) | 1 : (q == 2 ? 6 | ((a & 1) * 9) : 11));
+}
+
+// one sample of Intra8x8 prediction from the filtered reference samples (8.3.2.2.2 ff.)
+__device__ int pred8x8_sample(const IntraTile &tl, int mode, int avail, int x, int y) {
+#define PT(i) ((int)tl.f8t[1 + (i)])
+#define PL(i) ((int)tl.f8l[1 + (i)])
+	switch (mode) {
+	case 0: return PT(x);
+	case 1: return PL(y);
+	case 2: {
+		int st = 0, sl = 0;
+		for (int i = 0; i < 8; ++i) { st += PT(i); sl += PL(i); }
+		return (avail & 3) == 3 ? (st + sl + 8) >> 4 : ((avail & 1) ? (sl + 4) >> 3 : ((avail & 2) ? (st + 4) >> 3 : 128));
+	}
+	case 3: return (x == 7 && y == 7) ? (PT(14) + 3 * PT(15) + 2) >> 2 : (PT(x + y) + 2 * PT(x + y + 1) + PT(x + y + 2) + 2) >> 2;
+	case 4:
+		if (x > y) return (PT(x - y - 2) + 2 * PT(x - y - 1) + PT(x - y) + 2) >> 2;
+		if (x < y) return (PL(y - x - 2) + 2 * PL(y - x - 1) + PL(y - x) + 2) >> 2;
+		return (PT(0) + 2 * PT(-1) + PL(0) + 2) >> 2;
+	case 5: {
+		int z = 2 * x - y;
+		if (z >= 0 && !(z & 1)) return (PT(x - (y >> 1) - 1) + PT(x - (y >> 1)) + 1) >> 1;
+		if (z >= 0) return (PT(x - (y >> 1) - 2) + 2 * PT(x - (y >> 1) - 1) + PT(x - (y >> 1)) + 2) >> 2;
+		if (z == -1) return (PL(0) + 2 * PT(-1) + PT(0) + 2) >> 2;
+		return (PL(y - 2 * x - 1) + 2 * PL(y - 2 * x - 2) + PL(y - 2 * x - 3) + 2) >> 2;
+	}
+	case 6: {
+		int z = 2 * y - x;
+		if (z >= 0 && !(z & 1)) return (PL(y - (x >> 1) - 1) + PL(y - (x >> 1)) + 1) >> 1;
+		if (z >= 0) return (PL(y - (x >> 1) - 2) + 2 * PL(y - (x >> 1) - 1) + PL(y - (x >> 1)) + 2) >> 2;
+		if (z == -1) return (PL(0) + 2 * PT(-1) + PT(0) + 2) >> 2;
+		return (PT(x - 2 * y - 1) + 2 * PT(x - 2 * y - 2) + PT(x - 2 * y - 3) + 2) >> 2;
+	}
+	case 7:
+		if (!(y & 1)) return (PT(x + (y >> 1)) + PT(x + (y >> 1) + 1) + 1) >> 1;
+		return (PT(x + (y >> 1)) + 2 * PT(x + (y >> 1) + 1) + PT(x + (y >> 1) + 2) + 2) >> 2;
+	default: {
+		int z = x + 2 * y;
+		if (z > 13) return PL(7);
+		if (z == 13) return (PL(6) + 3 * PL(7) + 2) >> 2;
+		if (!(z & 1)) return (PL(y + (x >> 1)) + PL(y + (x >> 1) + 1) + 1) >> 1;
+		return (PL(y + (x >> 1)) + 2 * PL(y + (x >> 1) + 1) + PL(y + (x >> 1) + 2) + 2) >> 2;
+	}
+	}
+#undef PT
+#undef PL
+}
+
 // Reconstruct one intra macroblock with one warp.  Pixels produced by other warps (rows above)
 // are read through L2 (__ldcg) and results are written through to L2 (__stcg): the wavefront
 // kernel orders warps with progress flags, and L1 is not coherent between SMs.
@@ -696,7 +800,7 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 
 	// ---- neighbours into the tile ------------------------------------------------------------
 	const int a = m.intra_avail | m.intra_avail_c;
-	if (lane < 21) {            // above row: x = -1 .. 19
+	if (lane < 25) {            // above row: x = -1 .. 23
 		int x = lane - 1;
 		bool ok = (a & 2) && !(x < 0 && mbx == 0) && !(x >= 16 && mbx == job.mb_w - 1);
 		tl.y[0][lane] = (ok && mby > 0) ? __ldcg(py - (ptrdiff_t)W + x) : 128;
@@ -713,7 +817,16 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 	}
 	if (lane == 0) tl.has = 0;
 	__syncwarp();
-	if (lane < 24) {
+	if (m.flags & B2_H4_T8x8) {
+		if (lane < 4) {
+			if ((m.nz >> (1 + 4 * lane)) & 1) {
+				block_residual8x8(job, m, lane, tl.res);
+				atomicOr(&tl.has, 0xfu << (4 * lane));
+			}
+		} else if (lane >= 16 && lane < 24) {
+			if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
+		}
+	} else if (lane < 24) {
 		if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
 	}
 	__syncwarp();
@@ -728,6 +841,56 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 				int v = pred4x4_sample(tl, bx, by, mode, blk_avail(k, m.intra_avail), x, y);
 				if ((tl.has >> k) & 1) v = clip255(v + tl.res[k][y * 4 + x]);
 				tl.y[by * 4 + 1 + y][bx * 4 + 1 + x] = (uint8_t)v;
+			}
+			__syncwarp();
+		}
+	} else if (m.type == B2_H4_I8x8) {
+		for (int q = 0; q < 4; ++q) {
+			const int bx = (q & 1) * 8, by = (q >> 1) * 8;
+			const int av = blk8_avail(q, m.intra_avail);
+			const int mode = (m.i4_modes[q >> 1] >> ((q & 1) * 4)) & 15;
+			// reference sample filtering (8.3.2.2.1): lanes 0..15 the row above, 16 the corner, 17..24 the left column
+			{
+				const bool L = av & 1, T = av & 2, TR = av & 4, TL = av & 8;
+				const uint8_t *top = &tl.y[by][bx + 1];          // top[i] = p[i, -1], top[-1] = p[-1, -1]
+#define RT(i) ((int)top[(TR || (i) < 8) ? (i) : 7])
+#define RL(i) ((int)tl.y[by + 1 + (i)][bx])
+				if (lane < 16) {
+					int v = 0;
+					if (T) {
+						if (lane == 0) v = TL ? (RT(-1) + 2 * RT(0) + RT(1) + 2) >> 2 : (3 * RT(0) + RT(1) + 2) >> 2;
+						else if (lane == 15) v = (RT(14) + 3 * RT(15) + 2) >> 2;
+						else v = (RT(lane - 1) + 2 * RT(lane) + RT(lane + 1) + 2) >> 2;
+					}
+					tl.f8t[1 + lane] = (uint8_t)v;
+				} else if (lane == 16) {
+					int v = 0;
+					if (TL) {
+						const int c = top[-1];
+						v = (T && L) ? (RT(0) + 2 * c + RL(0) + 2) >> 2 : (T ? (3 * c + RT(0) + 2) >> 2 : (L ? (3 * c + RL(0) + 2) >> 2 : c));
+					}
+					tl.f8t[0] = tl.f8l[0] = (uint8_t)v;
+				} else if (lane < 25) {
+					const int yy = lane - 17;
+					int v = 0;
+					if (L) {
+						if (yy == 0) v = TL ? ((int)top[-1] + 2 * RL(0) + RL(1) + 2) >> 2 : (3 * RL(0) + RL(1) + 2) >> 2;
+						else if (yy == 7) v = (RL(6) + 3 * RL(7) + 2) >> 2;
+						else v = (RL(yy - 1) + 2 * RL(yy) + RL(yy + 1) + 2) >> 2;
+					}
+					tl.f8l[1 + yy] = (uint8_t)v;
+				}
+#undef RT
+#undef RL
+			}
+			__syncwarp();
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int x = lane & 7, y = (lane >> 3) + 4 * h;
+				int v = pred8x8_sample(tl, mode, av, x, y);
+				const int k = 4 * q + (y >> 2) * 2 + (x >> 2);
+				if ((tl.has >> k) & 1) v = clip255(v + tl.res[k][(y & 3) * 4 + (x & 3)]);
+				tl.y[by + 1 + y][bx + 1 + x] = (uint8_t)v;
 			}
 			__syncwarp();
 		}

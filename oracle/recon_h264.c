@@ -76,6 +76,55 @@ static void add_block4x4(uint8_t *dst, int stride, int step, const int16_t *lv, 
 		}
 }
 
+/* 8x8 dequantisation (qp_matrix8x8, h264.cpp:997-1054): normAdjust8x8 << (qp/6 - 2); for qp < 12
+ * the reference shifts the table entry RIGHT by (2 - qp/6), truncating it (a deviation from 8.5.9
+ * that is part of the reference's observable behaviour and therefore restated). */
+static int level_scale8(int qp, int pos)
+{
+	static const int8_t na[6][6] = {{20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
+	                                {28, 25, 45, 26, 35, 33}, {32, 28, 51, 30, 40, 38}, {36, 32, 58, 34, 46, 43}};
+	int x = pos & 3, y = (pos >> 3) & 3, cls;   /* the class pattern repeats every 4 columns / rows */
+	if (x == 0 && y == 0) cls = 0;
+	else if ((x & 1) && (y & 1)) cls = 1;
+	else if (x == 2 && y == 2) cls = 2;
+	else if ((x == 0 && (y & 1)) || ((x & 1) && y == 0)) cls = 3;
+	else if ((x == 0 && y == 2) || (x == 2 && y == 0)) cls = 4;
+	else cls = 5;
+	int shift = qp / 6 - 2;
+	return shift >= 0 ? na[qp % 6][cls] << shift : na[qp % 6][cls] >> -shift;
+}
+
+/* one dimension of the 8x8 inverse transform (8.5.13; ac8x8transform_interim, h264.cpp:3942-3983) */
+static void idct8_1d(const int *x, int step, int *o)
+{
+	int x0 = x[0], x1 = x[step], x2 = x[2 * step], x3 = x[3 * step], x4 = x[4 * step], x5 = x[5 * step], x6 = x[6 * step], x7 = x[7 * step];
+	int a0 = x0 + x4, a4 = x0 - x4, a2 = (x2 >> 1) - x6, a6 = x2 + (x6 >> 1);
+	int b0 = a0 + a6, b2 = a4 + a2, b4 = a4 - a2, b6 = a0 - a6;
+	int a1 = x5 - x3 - x7 - (x7 >> 1), a3 = x1 + x7 - x3 - (x3 >> 1), a5 = x5 + (x5 >> 1) + x7 - x1, a7 = x3 + x5 + x1 + (x1 >> 1);
+	int b1 = a1 + (a7 >> 2), b7 = a7 - (a1 >> 2), b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5;
+	o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1;
+	o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+
+/* residual add of one 8x8 luma block: lv = 64 levels, raster (ac8x8transform, h264.cpp:3985-4080) */
+static void add_block8x8(uint8_t *dst, int stride, const int16_t *lv, int qp)
+{
+	int c[64], t[64], o[8];
+	for (int i = 0; i < 64; ++i) c[i] = lv[i] * level_scale8(qp, i);
+	c[0] += 32;
+	for (int y = 0; y < 8; ++y) {          /* rows first */
+		idct8_1d(c + 8 * y, 1, o);
+		for (int x = 0; x < 8; ++x) t[8 * y + x] = o[x];
+	}
+	for (int x = 0; x < 8; ++x) {
+		idct8_1d(t + x, 8, o);
+		for (int y = 0; y < 8; ++y) {
+			uint8_t *p = dst + y * stride + x;
+			*p = (uint8_t)clip255(*p + (o[y] >> 6));
+		}
+	}
+}
+
 /* ---- intra prediction -------------------------------------------------------------------------- */
 /* Intra4x4 (8.3.1.2; h264.cpp:2510-2985).  avail: bit0 left, bit1 top, bit2 top-right */
 static void pred4x4(uint8_t *d, int s, int mode, int avail)
@@ -160,6 +209,103 @@ static int blk_avail(int k, int a)
 		tr = r2b[(y - 1) * 4 + x + 1] < k;
 	}
 	return (left ? 1 : 0) | (top ? 2 : 0) | (tr ? 4 : 0);
+}
+
+/* Intra8x8 (8.3.2.2; h264.cpp:3315-3929).  avail: bit0 left, bit1 top, bit2 top-right, bit3
+ * top-left, exactly as the reference's predictors receive it.  Reference samples are filtered
+ * first (8.3.2.2.1); t[1 + x] = p'[x, -1] (x = 0..15), l[1 + y] = p'[-1, y], t[0] = l[0] = p'[-1, -1]. */
+static void pred8x8l(uint8_t *d, int s, int mode, int avail)
+{
+	int L = avail & 1, T = avail & 2, TR = avail & 4, TL = avail & 8;
+	int pt[16], pl[8], ptl = TL ? d[-s - 1] : 0;
+	int t[17], l[9];
+	memset(t, 0, sizeof(t));
+	memset(l, 0, sizeof(l));
+	if (T) {
+		for (int x = 0; x < 8; ++x) pt[x] = d[-s + x];
+		for (int x = 8; x < 16; ++x) pt[x] = TR ? d[-s + x] : pt[7];
+		t[1] = TL ? (ptl + 2 * pt[0] + pt[1] + 2) >> 2 : (3 * pt[0] + pt[1] + 2) >> 2;
+		for (int x = 1; x < 15; ++x) t[1 + x] = (pt[x - 1] + 2 * pt[x] + pt[x + 1] + 2) >> 2;
+		t[16] = (pt[14] + 3 * pt[15] + 2) >> 2;
+	}
+	if (L) {
+		for (int y = 0; y < 8; ++y) pl[y] = d[y * s - 1];
+		l[1] = TL ? (ptl + 2 * pl[0] + pl[1] + 2) >> 2 : (3 * pl[0] + pl[1] + 2) >> 2;
+		for (int y = 1; y < 7; ++y) l[1 + y] = (pl[y - 1] + 2 * pl[y] + pl[y + 1] + 2) >> 2;
+		l[8] = (pl[6] + 3 * pl[7] + 2) >> 2;
+	}
+	if (TL) {
+		int v;
+		if (T && L) v = (pt[0] + 2 * ptl + pl[0] + 2) >> 2;
+		else if (T) v = (3 * ptl + pt[0] + 2) >> 2;
+		else if (L) v = (3 * ptl + pl[0] + 2) >> 2;
+		else v = ptl;
+		t[0] = l[0] = v;
+	}
+#define PT(x) t[1 + (x)]
+#define PL(y) l[1 + (y)]
+	for (int y = 0; y < 8; ++y)
+		for (int x = 0; x < 8; ++x) {
+			int v;
+			switch (mode) {
+			case 0: v = PT(x); break;
+			case 1: v = PL(y); break;
+			case 2: {
+				int st = 0, sl = 0;
+				for (int i = 0; i < 8; ++i) { st += PT(i); sl += PL(i); }
+				v = (T && L) ? (st + sl + 8) >> 4 : (L ? (sl + 4) >> 3 : (T ? (st + 4) >> 3 : 128));
+				break;
+			}
+			case 3: v = (x == 7 && y == 7) ? (PT(14) + 3 * PT(15) + 2) >> 2 : (PT(x + y) + 2 * PT(x + y + 1) + PT(x + y + 2) + 2) >> 2; break;
+			case 4:
+				if (x > y) v = (PT(x - y - 2) + 2 * PT(x - y - 1) + PT(x - y) + 2) >> 2;
+				else if (x < y) v = (PL(y - x - 2) + 2 * PL(y - x - 1) + PL(y - x) + 2) >> 2;
+				else v = (PT(0) + 2 * PT(-1) + PL(0) + 2) >> 2;
+				break;
+			case 5: {
+				int z = 2 * x - y;
+				if (z >= 0 && !(z & 1)) v = (PT(x - (y >> 1) - 1) + PT(x - (y >> 1)) + 1) >> 1;
+				else if (z >= 0) v = (PT(x - (y >> 1) - 2) + 2 * PT(x - (y >> 1) - 1) + PT(x - (y >> 1)) + 2) >> 2;
+				else if (z == -1) v = (PL(0) + 2 * PT(-1) + PT(0) + 2) >> 2;
+				else v = (PL(y - 2 * x - 1) + 2 * PL(y - 2 * x - 2) + PL(y - 2 * x - 3) + 2) >> 2;
+				break;
+			}
+			case 6: {
+				int z = 2 * y - x;
+				if (z >= 0 && !(z & 1)) v = (PL(y - (x >> 1) - 1) + PL(y - (x >> 1)) + 1) >> 1;
+				else if (z >= 0) v = (PL(y - (x >> 1) - 2) + 2 * PL(y - (x >> 1) - 1) + PL(y - (x >> 1)) + 2) >> 2;
+				else if (z == -1) v = (PL(0) + 2 * PT(-1) + PT(0) + 2) >> 2;
+				else v = (PT(x - 2 * y - 1) + 2 * PT(x - 2 * y - 2) + PT(x - 2 * y - 3) + 2) >> 2;
+				break;
+			}
+			case 7:
+				v = !(y & 1) ? (PT(x + (y >> 1)) + PT(x + (y >> 1) + 1) + 1) >> 1
+				             : (PT(x + (y >> 1)) + 2 * PT(x + (y >> 1) + 1) + PT(x + (y >> 1) + 2) + 2) >> 2;
+				break;
+			default: {
+				int z = x + 2 * y;
+				if (z > 13) v = PL(7);
+				else if (z == 13) v = (PL(6) + 3 * PL(7) + 2) >> 2;
+				else if (!(z & 1)) v = (PL(y + (x >> 1)) + PL(y + (x >> 1) + 1) + 1) >> 1;
+				else v = (PL(y + (x >> 1)) + 2 * PL(y + (x >> 1) + 1) + PL(y + (x >> 1) + 2) + 2) >> 2;
+				break;
+			}
+			}
+			d[y * s + x] = (uint8_t)v;
+		}
+#undef PT
+#undef PL
+}
+
+/* availability of 8x8 block q from the MB-level mask (luma_intra8x8_with_residual, h264.cpp:4093-4118) */
+static int blk8_avail(int q, int a)
+{
+	switch (q) {
+	case 0: return (a & ~4) | ((a & 2) * 2);
+	case 1: return (a & ~8) | ((a & 2) * 4) | 1;
+	case 2: return 6 | ((a & 1) * 9);
+	default: return 11;
+	}
 }
 
 /* Intra16x16 (8.3.3) */
@@ -362,6 +508,12 @@ static void recon_mb(const b2_h264_picture *p, int mbx, int mby, uint8_t *const 
 	}
 	if (m->type == B2_H4_INTER) {
 		for (int i = 0; i < m->mc_cnt; ++i) inter_pred(p, &p->mcs[m->mc_idx + i], mbx, mby, luma, chroma);
+		if (m->flags & B2_H4_T8x8) {
+			for (int q = 0; q < 4; ++q) {
+				const int16_t *lv = rec_of(p, m, 1 + 4 * q);
+				if (lv) add_block8x8(dy + (q >> 1) * 8 * W + (q & 1) * 8, W, lv, m->qp_y);
+			}
+		} else
 		for (int k = 0; k < 16; ++k) {
 			const int16_t *lv = rec_of(p, m, 1 + k);
 			if (lv) add_block4x4(dy + blk_y[k] * 4 * W + blk_x[k] * 4, W, 1, lv, m->qp_y, 0);
@@ -376,6 +528,14 @@ static void recon_mb(const b2_h264_picture *p, int mbx, int mby, uint8_t *const 
 			pred4x4(d, W, mode, blk_avail(k, m->intra_avail));
 			const int16_t *lv = rec_of(p, m, 1 + k);
 			if (lv) add_block4x4(d, W, 1, lv, m->qp_y, 0);
+		}
+	} else if (m->type == B2_H4_I8x8) {   /* luma_intra8x8_with_residual (h264.cpp:4083-4127) */
+		for (int q = 0; q < 4; ++q) {
+			uint8_t *d = dy + (q >> 1) * 8 * W + (q & 1) * 8;
+			int mode = (m->i4_modes[q >> 1] >> ((q & 1) * 4)) & 15;
+			pred8x8l(d, W, mode, blk8_avail(q, m->intra_avail));
+			const int16_t *lv = rec_of(p, m, 1 + 4 * q);
+			if (lv) add_block8x8(d, W, lv, m->qp_y);
 		}
 	} else {   /* Intra16x16 (h264.cpp:4407-4552) */
 		pred16x16(dy, W, m->i16_mode, m->intra_avail);

@@ -100,6 +100,23 @@ def test_cuda_matches_oracle_degenerate(name):
     assert m2dec_b200.decode_file("h264", data) == util.oracle_md5("h264", data)
 
 
+@pytest.mark.parametrize("name", sorted(streams.H264_ORACLE_ONLY))
+def test_oracle_only_streams_decode(name):
+    """Streams the reference cannot parse (see streams.H264_ORACLE_ONLY): the product parse must
+    still deliver every picture."""
+    args = streams.H264_ORACLE_ONLY[name]
+    frames = int(dict(a.split("=") for a in args.split())["frames"])
+    assert len(util.oracle_md5("h264", streams.generate("h264", args))) == frames
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(streams.H264_ORACLE_ONLY))
+def test_cuda_matches_oracle_only(name):
+    import m2dec_b200
+    data = streams.generate("h264", streams.H264_ORACLE_ONLY[name])
+    assert m2dec_b200.decode_file("h264", data) == util.oracle_md5("h264", data)
+
+
 @pytest.mark.gpu
 def test_cuda_concurrent_streams():
     """Many decoder contexts on host threads at once (one CUDA stream each): every stream must

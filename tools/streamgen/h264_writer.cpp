@@ -1,7 +1,7 @@
 // h264_writer.cpp — TEST-ONLY H.264 elementary-stream writer (not an encoder: it does not look
 // at pictures).  It draws random but *valid* syntax — macroblock types, partitions, motion
 // vectors, intra modes, coefficient levels, QP changes, slices — and entropy-codes it with
-// CAVLC, so that every reconstruction path of a decoder is exercised with known-legal input.
+// CAVLC or CABAC, so that every reconstruction path of a decoder is exercised with known-legal input.
 // Streams stay inside the region where the reference decoder is well defined (SURVEY.md §8a
 // hazards 1, 2, 5, 10): bounded residual amplitude, beta_offset >= alpha_offset,
 // seq_parameter_set_id 0, disable_deblocking_filter_idc in {0, 1}.
@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <vector>
 #include "bitwriter.h"
+#include "cabac_enc.h"
 #include "h264_cavlc_tables.h"
 #include "h264_common.h"
 #include "streamgen.h"
@@ -50,7 +51,12 @@ int level_scale(int qp, int x, int y) {
 class Writer {
 public:
 	Writer(const H264Opts &o) : o_(o), rng_((uint64_t)o.seed) {
+		// transform_size_8x8_flag and direct prediction: the reference reads the flag for
+		// B_Direct_16x16 even without direct_8x8_inference_flag (h264.cpp:9420); stay where it
+		// agrees with the standard
+		if (o_.transform8x8 && o_.bframes > 0) o_.direct_8x8_inference = 1;
 		ctx_.resize(o.mbw, o.mbh);
+		ctx_.cabac = o_.cabac != 0;
 	}
 
 	std::vector<uint8_t> run() {
@@ -95,6 +101,7 @@ private:
 		bw.put(0, 8);
 		bw.put(40, 8);               // level 4.0
 		bw.ue(0);                    // seq_parameter_set_id (hazard 10: must be 0)
+		if (o_.profile == 100) { bw.ue(1); bw.ue(0); bw.ue(0); bw.put1(0); bw.put1(0); }   // 4:2:0, 8 bit, no scaling matrices
 		bw.ue(0);                    // log2_max_frame_num_minus4
 		if (o_.bframes > 0) { bw.ue(0); bw.ue(4); }   // pic_order_cnt_type 0, log2_max_pic_order_cnt_lsb = 8
 		else bw.ue(2);               // pic_order_cnt_type 2
@@ -118,7 +125,7 @@ private:
 	void write_pps() {
 		BitWriter bw;
 		bw.ue(0); bw.ue(0);
-		bw.put1(0);                  // entropy_coding_mode_flag: CAVLC
+		bw.put1(o_.cabac);           // entropy_coding_mode_flag
 		bw.put1(0);
 		bw.ue(0);                    // num_slice_groups_minus1
 		bw.ue(o_.refs - 1);          // num_ref_idx_l0_default_active_minus1
@@ -131,6 +138,11 @@ private:
 		bw.put1(1);                  // deblocking_filter_control_present_flag
 		bw.put1(o_.constrained_intra);
 		bw.put1(0);
+		if (o_.transform8x8) {
+			bw.put1(1);              // transform_8x8_mode_flag
+			bw.put1(0);              // pic_scaling_matrix_present_flag
+			bw.se(o_.chroma_qp_offset);   // second_chroma_qp_index_offset
+		}
 		bw.rbsp_trailing();
 		emit_nal(3, 8, bw);
 	}
@@ -172,14 +184,25 @@ private:
 				if (idr) { bw.put1(0); bw.put1(0); }   // no_output_of_prior_pics, long_term_reference_flag
 				else bw.put1(0);                        // adaptive_ref_pic_marking_mode_flag
 			}
+			int init_idc = 0;
+			if (o_.cabac && slice_kind != 2) { init_idc = o_.cabac_init_idc < 0 ? rng_.range(0, 2) : o_.cabac_init_idc; bw.ue(init_idc); }
 			int slice_qp = o_.qp + (o_.vary_qp ? rng_.range(-2, 2) : 0);
 			bw.se(slice_qp - o_.qp);
 			qp_ = slice_qp;
 			int idc = o_.deblock ? ((o_.deblock == 2 && (s & 1)) ? 1 : 0) : 1;
 			bw.ue(idc);
 			if (idc != 1) { bw.se(o_.alpha_div2); bw.se(o_.beta_div2); }
-			slice_data(bw, slice_kind == 2, first, last);
-			bw.rbsp_trailing();
+			if (o_.cabac) {
+				while (!bw.aligned()) bw.put1(1);   // cabac_alignment_one_bit
+				cs_.e.m.init(slice_qp, slice_kind == 2 ? 0 : 1 + init_idc);
+				cs_.e.start(&bw);
+				last_dqp_ = 0;
+				slice_data_cabac(bw, slice_kind == 2, first, last);
+				bw.align_zero();     // the flush wrote rbsp_stop_one_bit
+			} else {
+				slice_data(bw, slice_kind == 2, first, last);
+				bw.rbsp_trailing();
+			}
 			emit_nal(idr ? 3 : (is_ref ? 2 : 0), idr ? 5 : 1, bw);
 		}
 		if (is_ref) {
@@ -228,7 +251,7 @@ private:
 		}
 	}
 
-	// explicit weights: log2 denominators <= 6, weights and offsets tame (hazard 4)
+	// explicit weights: log2 denominators <= 6, weights <= 64 and small offsets (hazard 4)
 	void weight_table(BitWriter &bw, bool bslice) {
 		int dl = rng_.range(2, 6), dc = rng_.range(2, 6);
 		bw.ue(dl); bw.ue(dc);
@@ -236,9 +259,11 @@ private:
 			for (int i = 0; i < nref_[l]; ++i) {
 				bool fl = rng_.chance(70), fc = rng_.chance(70);
 				bw.put1(fl);
-				if (fl) { bw.se((1 << dl) + rng_.range(-(1 << dl) / 4, (1 << dl) / 4)); bw.se(rng_.range(-8, 8)); }
+				// w0 + w1 <= 128 keeps the reference's 16-bit saturating bi-prediction sum exact (hazard 4)
+				auto weight = [&](int d) { int w = (1 << d) + rng_.range(-(1 << d) / 4, (1 << d) / 4); return w > 64 ? 64 : w; };
+				if (fl) { bw.se(weight(dl)); bw.se(rng_.range(-8, 8)); }
 				bw.put1(fc);
-				if (fc) for (int c = 0; c < 2; ++c) { bw.se((1 << dc) + rng_.range(-(1 << dc) / 4, (1 << dc) / 4)); bw.se(rng_.range(-8, 8)); }
+				if (fc) for (int c = 0; c < 2; ++c) { bw.se(weight(dc)); bw.se(rng_.range(-8, 8)); }
 			}
 	}
 
@@ -248,19 +273,7 @@ private:
 			int mbx = addr % o_.mbw, mby = addr / o_.mbw;
 			ctx_.open_mb(mbx, mby, slice_num_);
 			if (!idr && rng_.chance(o_.skip_pct)) {
-				if (kind_ == 1) {
-					DirectOut d;
-					derive_direct(mbx, mby, d);
-					set_direct(mbx, mby, d, 0xf);
-				} else {
-					int16_t mv[2];
-					ctx_.pskip_mv(mbx, mby, slice_num_, mv);
-					ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, pic_of(0, 0), mv[0], mv[1]);
-					ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
-				}
-				MbInfo &info = ctx_.info(mbx, mby);
-				info.kind = MB_SKIP;
-				memset(ctx_.nnz_of(mbx, mby), 0, 24);
+				skip_motion(mbx, mby);
 				skip_run++;
 				continue;
 			}
@@ -271,6 +284,85 @@ private:
 		}
 		if (!idr && skip_run) bw.ue(skip_run);
 	}
+
+	void skip_motion(int mbx, int mby) {
+		if (kind_ == 1) {
+			DirectOut d;
+			derive_direct(mbx, mby, d);
+			set_direct(mbx, mby, d, 0xf);
+		} else {
+			int16_t mv[2];
+			ctx_.pskip_mv(mbx, mby, slice_num_, mv);
+			ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, pic_of(0, 0), mv[0], mv[1]);
+			ctx_.set_motion(1, mbx, mby, 0, 0, 4, 4, -1, -1, 0, 0);
+		}
+		MbInfo &info = ctx_.info(mbx, mby);
+		info.kind = MB_SKIP;
+		info.cbp = 0;
+		if (kind_ == 1) info.cflags |= MBF_DIRECT16;
+		memset(ctx_.nnz_of(mbx, mby), 0, 24);
+	}
+
+	void slice_data_cabac(BitWriter &bw, bool idr, int first, int last) {
+		for (int addr = first; addr < last; ++addr) {
+			int mbx = addr % o_.mbw, mby = addr / o_.mbw;
+			ctx_.open_mb(mbx, mby, slice_num_);
+			bool skip = !idr && rng_.chance(o_.skip_pct);
+			if (!idr) cs_.mb_skip(kind_ == 1, ctx_.cabac_inc_skip(), skip);
+			if (skip) {
+				skip_motion(mbx, mby);
+				last_dqp_ = 0;
+			} else if (idr || rng_.chance(o_.intra_pct)) intra_mb(bw, mbx, mby, idr);
+			else if (kind_ == 1) b_mb(bw, mbx, mby);
+			else inter_mb(bw, mbx, mby);
+			cs_.end_of_slice(addr == last - 1);
+		}
+	}
+
+	// ---- syntax elements, either entropy coder ----------------------------------------------------------
+	void put_mb_type(BitWriter &bw, int v) {
+		if (!o_.cabac) { bw.ue(v); return; }
+		if (kind_ == 2) cs_.mb_type_intra(3, true, ctx_.cabac_inc_mbtype_i(), v);
+		else if (kind_ == 0) cs_.mb_type_p(v);
+		else cs_.mb_type_b(ctx_.cabac_inc_mbtype_b(), v);
+	}
+	void put_sub_mb_type(BitWriter &bw, int v) {
+		if (!o_.cabac) { bw.ue(v); return; }
+		if (kind_ == 1) cs_.sub_mb_type_b(v); else cs_.sub_mb_type_p(v);
+	}
+	void put_ref(BitWriter &bw, int l, int x4, int y4, int pw, int ph, int r) {
+		if (nref_[l] > 1) {
+			if (o_.cabac) cs_.ref_idx(ctx_.cabac_inc_ref(l, x4, y4), r);
+			else if (nref_[l] == 2) bw.put1(r ^ 1);
+			else bw.ue(r);
+		}
+		if (o_.cabac) ctx_.set_refgt0(l, x4, y4, pw, ph, r);
+	}
+	void put_mvd(BitWriter &bw, int l, int x4, int y4, int pw, int ph, int dx, int dy) {
+		if (!o_.cabac) { bw.se(dx); bw.se(dy); return; }
+		cs_.mvd(40, ctx_.cabac_mvd_sum(l, x4, y4, 0), dx);
+		cs_.mvd(47, ctx_.cabac_mvd_sum(l, x4, y4, 1), dy);
+		ctx_.set_mvd(l, x4, y4, pw, ph, dx, dy);
+	}
+	void put_cbp(BitWriter &bw, bool intra, int cbp) {
+		if (o_.cabac) cs_.cbp(ctx_, cbp);
+		else bw.ue(enc_.code_from_cbp[intra ? 0 : 1][cbp]);
+	}
+	void put_qp_delta(BitWriter &bw, int d) {
+		if (o_.cabac) cs_.qp_delta(last_dqp_ != 0, d);
+		else bw.se(d);
+		last_dqp_ = d;
+	}
+	void put_chroma_mode(BitWriter &bw, int v) {
+		if (o_.cabac) cs_.chroma_mode(ctx_.cabac_inc_chroma_mode(), v);
+		else bw.ue(v);
+	}
+	void put_ipred(BitWriter &bw, int pred, int mode) {
+		if (o_.cabac) { cs_.ipred_mode(pred, mode); return; }
+		if (mode == pred) bw.put1(1);
+		else { bw.put1(0); bw.put(mode < pred ? mode : mode - 1, 3); }
+	}
+	void put_t8x8(int v) { cs_.transform8x8(ctx_.cabac_inc_t8x8(), v); }
 
 	// ---- residual generation / coding ---------------------------------------------------------------
 	// Draw up to `maxc` coefficients in scan order for a 4x4 block whose dequantised L1 amplitude
@@ -347,15 +439,60 @@ private:
 		int16_t cdc[2][4];
 		int16_t cac[2][4][16];
 		bool cac_coded[2][4];
+		int16_t luma8[4][64];     // transform_size_8x8_flag: levels of the four 8x8 blocks in scan order
 		int cbp;
 	};
 
+	// dequantisation scale of position (x, y) of an 8x8 block (flat matrices, 8.5.9 normAdjust8x8)
+	static int level_scale8(int qp, int x, int y) {
+		static const int na[6][6] = {{20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
+		                             {28, 25, 45, 26, 35, 33}, {32, 28, 51, 30, 40, 38}, {36, 32, 58, 34, 46, 43}};
+		int cls;
+		if ((x & 3) == 0 && (y & 3) == 0) cls = 0;
+		else if ((x & 1) && (y & 1)) cls = 1;
+		else if ((x & 3) == 2 && (y & 3) == 2) cls = 2;
+		else if (((x & 3) == 0 && (y & 1)) || ((x & 1) && (y & 3) == 0)) cls = 3;
+		else if (((x & 3) == 0 && (y & 3) == 2) || ((x & 3) == 2 && (y & 3) == 0)) cls = 4;
+		else cls = 5;
+		return (na[qp % 6][cls] << (qp / 6)) >> 2;
+	}
+
+	int draw_block8(int16_t *lv, int qp, int *budget) {
+		memset(lv, 0, sizeof(int16_t) * 64);
+		int n = 1 + (int)(rng_.next() % 6);
+		if (rng_.chance(8)) n = rng_.range(7, 40);
+		int cnt = 0;
+		for (int i = 0; i < n; ++i) {
+			int pos = rng_.chance(70) ? rng_.range(0, 9) : rng_.range(0, 63);
+			if (lv[pos]) continue;
+			int mag = rng_.chance(75) ? 1 : rng_.range(2, o_.max_level);
+			int r = zigzag8x8[pos];
+			int sc = level_scale8(qp, r & 7, r >> 3);
+			int cost = (mag * sc + 63) / 64 + 1;
+			if (cost > *budget) {
+				mag = 1;
+				cost = (sc + 63) / 64 + 1;
+				if (cost > *budget) continue;
+			}
+			*budget -= cost;
+			lv[pos] = (int16_t)(rng_.chance(50) ? mag : -mag);
+			cnt++;
+		}
+		return cnt;
+	}
+
 	// decide the residual of one MB (after QP is final); i16 selects the Intra16x16 layout
-	void draw_residual(Residual &r, int qp, int qpc0, int qpc1, bool i16) {
+	void draw_residual(Residual &r, int qp, int qpc0, int qpc1, bool i16, bool t8x8 = false) {
 		memset(&r, 0, sizeof(r));
 		int budget = o_.amp_budget;
 		int cbp = 0;
-		if (i16) {
+		if (t8x8) {
+			for (int q = 0; q < 4; ++q) {
+				if (!rng_.chance(o_.coded_pct * 2 > 100 ? 100 : o_.coded_pct * 2)) continue;
+				int b = budget;
+				if (draw_block8(r.luma8[q], qp, &b) > 0) cbp |= 1 << q;
+			}
+		} else if (i16) {
 			if (rng_.chance(70)) {
 				int n = rng_.range(1, 4);
 				for (int i = 0; i < n; ++i) {
@@ -407,30 +544,80 @@ private:
 		r.cbp = cbp | (cmode << 4);
 	}
 
-	void code_luma(BitWriter &bw, const Residual &r, int mbx, int mby, bool i16) {
+	void code_luma(BitWriter &bw, const Residual &r, int mbx, int mby, bool i16, bool intra = false, bool t8x8 = false) {
 		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
 		static const int16_t zero[16] = {0};
+		if (t8x8) {
+			for (int q = 0; q < 4; ++q) {
+				const int x4 = (q & 1) * 2, y4 = (q >> 1) * 2;
+				int total = 0;
+				if (r.cbp & (1 << q)) {
+					int16_t lv[64];
+					memcpy(lv, r.luma8[q], sizeof(lv));
+					total = cs_.residual(5, -1, lv, 64);
+					if (total > 15) total = 15;
+				}
+				nnz[y4 * 4 + x4] = nnz[y4 * 4 + x4 + 1] = nnz[(y4 + 1) * 4 + x4] = nnz[(y4 + 1) * 4 + x4 + 1] = (uint8_t)total;
+			}
+			return;
+		}
 		for (int k = 0; k < 16; ++k) {
 			int x4 = blk_x[k], y4 = blk_y[k];
 			if (!(r.cbp & (1 << (k >> 2)))) { nnz[y4 * 4 + x4] = 0; continue; }
-			int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
-			nnz[y4 * 4 + x4] = (uint8_t)code_block(bw, r.luma_coded[k] ? r.luma[k] : zero, i16 ? 15 : 16, nc);
+			const int16_t *src = r.luma_coded[k] ? r.luma[k] : zero;
+			if (o_.cabac) {
+				int16_t lv[16];
+				memcpy(lv, src, sizeof(lv));
+				nnz[y4 * 4 + x4] = (uint8_t)cs_.residual(i16 ? 1 : 2, ctx_.cabac_inc_cbf_luma(x4, y4, intra), lv, i16 ? 15 : 16);
+			} else {
+				int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
+				nnz[y4 * 4 + x4] = (uint8_t)code_block(bw, src, i16 ? 15 : 16, nc);
+			}
 		}
 	}
 
-	void code_chroma(BitWriter &bw, const Residual &r, int mbx, int mby) {
+	void code_chroma(BitWriter &bw, const Residual &r, int mbx, int mby, bool intra = false) {
 		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
+		MbInfo &info = ctx_.info(mbx, mby);
 		memset(nnz + 16, 0, 8);
 		int cm = r.cbp >> 4;
 		if (!cm) return;
 		static const int16_t zero[16] = {0};
-		for (int c = 0; c < 2; ++c) code_block(bw, r.cdc[c], 4, -1);
+		for (int c = 0; c < 2; ++c) {
+			if (o_.cabac) {
+				int16_t lv[4];
+				memcpy(lv, r.cdc[c], sizeof(lv));
+				if (cs_.residual(3, ctx_.cabac_inc_cbf_dc(MBF_CBF_CB_DC << c, intra), lv, 4)) info.cflags |= (uint8_t)(MBF_CBF_CB_DC << c);
+			} else {
+				code_block(bw, r.cdc[c], 4, -1);
+			}
+		}
 		if (cm & 2)
 			for (int c = 0; c < 2; ++c)
 				for (int b = 0; b < 4; ++b) {
-					int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, b & 1, b >> 1, slice_num_);
-					nnz[16 + c * 4 + b] = (uint8_t)code_block(bw, r.cac_coded[c][b] ? r.cac[c][b] : zero, 15, nc);
+					const int16_t *src = r.cac_coded[c][b] ? r.cac[c][b] : zero;
+					if (o_.cabac) {
+						int16_t lv[16];
+						memcpy(lv, src, sizeof(lv));
+						nnz[16 + c * 4 + b] = (uint8_t)cs_.residual(4, ctx_.cabac_inc_cbf_chroma_ac(c, b & 1, b >> 1, intra), lv, 15);
+					} else {
+						int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, b & 1, b >> 1, slice_num_);
+						nnz[16 + c * 4 + b] = (uint8_t)code_block(bw, src, 15, nc);
+					}
 				}
+	}
+
+	// coded_block_pattern [+ transform_size_8x8_flag] + mb_qp_delta + residual of a non-Intra16x16 MB
+	void code_cbp_residual(BitWriter &bw, Residual &r, int mbx, int mby, bool intra, bool t8x8, int qd, int qp) {
+		MbInfo &info = ctx_.info(mbx, mby);
+		put_cbp(bw, intra, r.cbp);
+		info.cbp = (uint8_t)r.cbp;
+		if (!intra && o_.transform8x8 && may_t8x8_ && (r.cbp & 15)) put_t8x8(t8x8);
+		if (t8x8 && (intra || (r.cbp & 15))) info.t8x8 = 1;
+		if (r.cbp) { put_qp_delta(bw, qd); qp_ = qp; }
+		else last_dqp_ = 0;
+		code_luma(bw, r, mbx, mby, false, intra, t8x8);
+		code_chroma(bw, r, mbx, mby, intra);
 	}
 
 	int draw_qp_delta() {
@@ -465,20 +652,27 @@ private:
 		int chroma_mode = pick(cc, ncc);
 		int r100 = rng_.range(0, 99);
 		if (r100 < o_.ipcm_pct) {
-			bw.ue(ofs + 25);
+			put_mb_type(bw, ofs + 25);
 			bw.align_zero();
 			for (int i = 0; i < 384; ++i) bw.put((uint32_t)rng_.range(0, 255), 8);
+			if (o_.cabac) cs_.e.start(&bw);
 			info.kind = MB_IPCM;
+			info.cbp = 0x2f;
+			info.cflags = MBF_CBF_LUMA_DC | MBF_CBF_CB_DC | MBF_CBF_CR_DC;
+			last_dqp_ = 0;
 			memset(ctx_.nnz_of(mbx, mby), 16, 24);
 			memset(ip, 2, 16);
 			return;
 		}
 		Residual r;
-		if (r100 < 55) {   // Intra4x4
-			info.kind = MB_I4x4;
-			bw.ue(ofs + 0);
-			for (int k = 0; k < 16; ++k) {
-				int x4 = blk_x[k], y4 = blk_y[k];
+		may_t8x8_ = false;
+		if (r100 < 55) {   // Intra NxN
+			const bool t8x8 = o_.transform8x8 && rng_.chance(50);
+			info.kind = t8x8 ? MB_I8x8 : MB_I4x4;
+			put_mb_type(bw, ofs + 0);
+			if (o_.transform8x8) put_t8x8(t8x8);
+			for (int k = 0; k < (t8x8 ? 4 : 16); ++k) {
+				int x4 = t8x8 ? (k & 1) * 2 : blk_x[k], y4 = t8x8 ? (k >> 1) * 2 : blk_y[k];
 				bool l = x4 > 0 || L, t = y4 > 0 || T;
 				bool tl = (x4 > 0 && y4 > 0) || (x4 == 0 && y4 > 0 && L) || (y4 == 0 && x4 > 0 && T) || (x4 == 0 && y4 == 0 && TL);
 				int cand[9], n = 0;
@@ -493,39 +687,47 @@ private:
 				bool ok = false;
 				for (int i = 0; i < n; ++i) ok |= cand[i] == mode;
 				if (!ok) mode = 2;
-				if (mode == pred) bw.put1(1);
-				else { bw.put1(0); bw.put(mode < pred ? mode : mode - 1, 3); }
+				put_ipred(bw, pred, mode);
 				ip[y4 * 4 + x4] = (int8_t)mode;
+				if (t8x8) ip[y4 * 4 + x4 + 1] = ip[(y4 + 1) * 4 + x4] = ip[(y4 + 1) * 4 + x4 + 1] = (int8_t)mode;
 			}
-			bw.ue(chroma_mode);
+			put_chroma_mode(bw, chroma_mode);
+			info.chroma_mode = (uint8_t)chroma_mode;
 			int qd = draw_qp_delta();
 			int qp = qp_ + qd;
-			draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false);
-			bw.ue(enc_.code_from_cbp[0][r.cbp]);
-			if (r.cbp) { bw.se(qd); qp_ = qp; }
-			code_luma(bw, r, mbx, mby, false);
-		} else {           // Intra16x16
-			info.kind = MB_I16x16;
-			memset(ip, 2, 16);
-			int cand[4], n = 0;
-			cand[n++] = 2;
-			if (T) cand[n++] = 0;
-			if (L) cand[n++] = 1;
-			if (L && T && TL) cand[n++] = 3;
-			int mode = pick(cand, n);
-			int qd = draw_qp_delta();
-			int qp = qp_ + qd;
-			draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), true);
-			int cl = (r.cbp & 15) ? 1 : 0, cchroma = r.cbp >> 4;
-			bw.ue(ofs + 1 + mode + cchroma * 4 + cl * 12);
-			bw.ue(chroma_mode);
-			bw.se(qd);
-			qp_ = qp;
+			draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false, t8x8);
+			code_cbp_residual(bw, r, mbx, mby, true, t8x8, qd, qp);
+			return;
+		}
+		// Intra16x16
+		info.kind = MB_I16x16;
+		memset(ip, 2, 16);
+		int cand[4], n = 0;
+		cand[n++] = 2;
+		if (T) cand[n++] = 0;
+		if (L) cand[n++] = 1;
+		if (L && T && TL) cand[n++] = 3;
+		int mode = pick(cand, n);
+		int qd = draw_qp_delta();
+		int qp = qp_ + qd;
+		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), true);
+		int cl = (r.cbp & 15) ? 1 : 0, cchroma = r.cbp >> 4;
+		put_mb_type(bw, ofs + 1 + mode + cchroma * 4 + cl * 12);
+		put_chroma_mode(bw, chroma_mode);
+		info.chroma_mode = (uint8_t)chroma_mode;
+		info.cbp = (uint8_t)r.cbp;
+		put_qp_delta(bw, qd);
+		qp_ = qp;
+		if (o_.cabac) {
+			int16_t lv[16];
+			memcpy(lv, r.luma_dc, sizeof(lv));
+			if (cs_.residual(0, ctx_.cabac_inc_cbf_dc(MBF_CBF_LUMA_DC, true), lv, 16)) info.cflags |= MBF_CBF_LUMA_DC;
+		} else {
 			int nc = ctx_.cavlc_nc(mbx, mby, 0, 0, 0, slice_num_);
 			code_block(bw, r.luma_dc, 16, nc);
-			code_luma(bw, r, mbx, mby, true);
 		}
-		code_chroma(bw, r, mbx, mby);
+		code_luma(bw, r, mbx, mby, true, true, false);
+		code_chroma(bw, r, mbx, mby, true);
 	}
 
 	// ---- inter -------------------------------------------------------------------------------------------
@@ -565,10 +767,12 @@ private:
 		else if (t < 55) { mb_type = 1; parts.push_back({0, 0, 4, 2, refs[0], 1, 0}); parts.push_back({0, 2, 4, 2, refs[1], 1, 1}); }
 		else if (t < 70) { mb_type = 2; parts.push_back({0, 0, 2, 4, refs[0], 2, 0}); parts.push_back({2, 0, 2, 4, refs[1], 2, 1}); }
 		else {
-			mb_type = (nref_[0] > 1 || rng_.chance(50)) ? 3 : 4;   // P_8x8 / P_8x8ref0
+			const bool plain = nref_[0] > 1 || rng_.chance(50);
+			mb_type = (plain || o_.cabac) ? 3 : 4;   // P_8x8 / P_8x8ref0 (the latter does not exist under CABAC)
 			if (mb_type == 4) for (int i = 0; i < 4; ++i) refs[i] = 0;
 			for (int i = 0; i < 4; ++i) {
 				sub[i] = rng_.range(0, 3);
+				if (o_.transform8x8 && (t & 1)) sub[i] = 0;    // half of the P_8x8 MBs may use the 8x8 transform
 				int bx = (i & 1) * 2, by = (i >> 1) * 2;
 				switch (sub[i]) {
 				case 0: parts.push_back({bx, by, 2, 2, refs[i], 0, 0}); break;
@@ -578,34 +782,29 @@ private:
 				}
 			}
 		}
-		bw.ue(mb_type);
-		auto put_ref = [&](int r) {
-			if (nref_[0] <= 1) return;
-			if (nref_[0] == 2) bw.put1(r ^ 1); else bw.ue(r);
-		};
-		if (mb_type == 0) put_ref(refs[0]);
-		else if (mb_type == 1 || mb_type == 2) { put_ref(refs[0]); put_ref(refs[1]); }
+		put_mb_type(bw, mb_type);
+		may_t8x8_ = true;
+		if (mb_type == 0) put_ref(bw, 0, 0, 0, 4, 4, refs[0]);
+		else if (mb_type == 1) { put_ref(bw, 0, 0, 0, 4, 2, refs[0]); put_ref(bw, 0, 0, 2, 4, 2, refs[1]); }
+		else if (mb_type == 2) { put_ref(bw, 0, 0, 0, 2, 4, refs[0]); put_ref(bw, 0, 2, 0, 2, 4, refs[1]); }
 		else {
-			for (int i = 0; i < 4; ++i) bw.ue(sub[i]);
-			if (mb_type == 3) for (int i = 0; i < 4; ++i) put_ref(refs[i]);
+			for (int i = 0; i < 4; ++i) { put_sub_mb_type(bw, sub[i]); if (sub[i]) may_t8x8_ = false; }
+			if (mb_type == 3) for (int i = 0; i < 4; ++i) put_ref(bw, 0, (i & 1) * 2, (i >> 1) * 2, 2, 2, refs[i]);
 		}
 		for (const Part &p : parts) {
 			int16_t pred[2];
 			ctx_.predict_mv(0, mbx, mby, p.x4, p.y4, p.pw, p.ref, slice_num_, p.shape, p.part, pred);
 			int mv[2];
 			draw_mv(mbx, mby, pred, mv);
-			bw.se(mv[0] - pred[0]);
-			bw.se(mv[1] - pred[1]);
+			put_mvd(bw, 0, p.x4, p.y4, p.pw, p.ph, mv[0] - pred[0], mv[1] - pred[1]);
 			ctx_.set_motion(0, mbx, mby, p.x4, p.y4, p.pw, p.ph, p.ref, pic_of(0, p.ref), mv[0], mv[1]);
 		}
 		Residual r;
 		int qd = draw_qp_delta();
 		int qp = qp_ + qd;
-		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false);
-		bw.ue(enc_.code_from_cbp[1][r.cbp]);
-		if (r.cbp) { bw.se(qd); qp_ = qp; }
-		code_luma(bw, r, mbx, mby, false);
-		code_chroma(bw, r, mbx, mby);
+		const bool t8x8 = o_.transform8x8 && may_t8x8_ && rng_.chance(50);
+		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false, t8x8);
+		code_cbp_residual(bw, r, mbx, mby, false, t8x8, qd, qp);
 	}
 
 	// ---- B pictures ---------------------------------------------------------------------------------------
@@ -657,7 +856,9 @@ private:
 			static const uint8_t sub_shape[13] = {0, 0, 0, 0, 1, 2, 1, 2, 1, 2, 3, 3, 3};
 			mb_type = 22;
 			for (int q = 0; q < 4; ++q) {
-				int st = rng_.chance(o_.direct_pct) ? 0 : rng_.range(1, 12);
+				// with transform_8x8_mode the reference reads transform_size_8x8_flag for every B_8x8
+				// (need_transform_size_8x8, h264.cpp:1306) although sub-8x8 partitions exclude it
+				int st = rng_.chance(o_.direct_pct) ? 0 : rng_.range(1, o_.transform8x8 ? 3 : 12);
 				sub_type[q] = st;
 				int bx = (q & 1) * 2, by = (q >> 1) * 2, use = sub_mode[st];
 				sub_use[q] = use;
@@ -670,8 +871,14 @@ private:
 				}
 			}
 		}
-		bw.ue(mb_type);
-		if (mb_type == 22) for (int q = 0; q < 4; ++q) bw.ue(sub_type[q]);
+		put_mb_type(bw, mb_type);
+		may_t8x8_ = mb_type != 0 || o_.direct_8x8_inference;
+		if (mb_type == 0) info.cflags |= MBF_DIRECT16;
+		if (mb_type == 22)
+			for (int q = 0; q < 4; ++q) {
+				put_sub_mb_type(bw, sub_type[q]);
+				if (sub_type[q] > 3 || (sub_type[q] == 0 && !o_.direct_8x8_inference)) may_t8x8_ = false;
+			}
 		DirectOut dir;
 		if (direct_quads) derive_direct(mbx, mby, dir);
 		int ref[4][2];
@@ -682,7 +889,8 @@ private:
 				if (!(sub_use[q] & (1 << l))) continue;
 				int r = nref_[l] > 1 ? rng_.range(0, nref_[l] - 1) : 0;
 				ref[q][l] = r;
-				if (nref_[l] > 1) { if (nref_[l] == 2) bw.put1(r ^ 1); else bw.ue(r); }
+				if (mb_type == 22) put_ref(bw, l, (q & 1) * 2, (q >> 1) * 2, 2, 2, r);
+				else put_ref(bw, l, parts[q].x4, parts[q].y4, parts[q].pw, parts[q].ph, r);
 			}
 		for (int l = 0; l < 2; ++l)
 			for (const Part &p : parts) {
@@ -698,19 +906,16 @@ private:
 				ctx_.predict_mv(l, mbx, mby, p.x4, p.y4, p.pw, r, slice_num_, p.shape, p.part, pred);
 				int mv[2];
 				draw_mv(mbx, mby, pred, mv);
-				bw.se(mv[0] - pred[0]);
-				bw.se(mv[1] - pred[1]);
+				put_mvd(bw, l, p.x4, p.y4, p.pw, p.ph, mv[0] - pred[0], mv[1] - pred[1]);
 				ctx_.set_motion(l, mbx, mby, p.x4, p.y4, p.pw, p.ph, r, pic_of(l, r), mv[0], mv[1]);
 			}
 		if (mb_type == 0) set_direct(mbx, mby, dir, 0xf);
 		Residual r;
 		int qd = draw_qp_delta();
 		int qp = qp_ + qd;
-		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false);
-		bw.ue(enc_.code_from_cbp[1][r.cbp]);
-		if (r.cbp) { bw.se(qd); qp_ = qp; }
-		code_luma(bw, r, mbx, mby, false);
-		code_chroma(bw, r, mbx, mby);
+		const bool t8x8 = o_.transform8x8 && may_t8x8_ && rng_.chance(50);
+		draw_residual(r, qp, chroma_qp(qp, o_.chroma_qp_offset), chroma_qp(qp, o_.chroma_qp_offset), false, t8x8);
+		code_cbp_residual(bw, r, mbx, mby, false, t8x8, qd, qp);
 	}
 
 	struct WRef { RefPic rp; int frame_num_wrap; ColPic col; };
@@ -725,6 +930,9 @@ private:
 	PicCtx ctx_;
 	std::vector<uint8_t> out_;
 	int slice_num_ = 0, qp_ = 26, idr_id_ = 0;
+	int last_dqp_ = 0;
+	bool may_t8x8_ = false;
+	CabacSyntax<CabacEnc> cs_;
 };
 
 }  // namespace

@@ -28,6 +28,7 @@ int main(int argc, char **argv) {
 		OPT(ipcm_pct) OPT(coded_pct) OPT(max_level) OPT(big_levels) OPT(amp_budget) OPT(mv_step) OPT(mv_range)
 		OPT(mv_out) OPT(crop_bottom) OPT(crop_right) OPT(constrained_intra)
 		OPT(bframes) OPT(direct_spatial) OPT(direct_pct) OPT(weighted_pred) OPT(weighted_bipred) OPT(direct_8x8_inference)
+		OPT(cabac) OPT(cabac_init_idc) OPT(transform8x8)
 		data = sg::write_h264(o);
 	} else if (codec == "mpeg2") {
 		sg::Mpeg2Opts o;

@@ -29,6 +29,10 @@ struct H264Opts {
 	int weighted_pred = 0;     // explicit weights in P slices
 	int weighted_bipred = 0;   // 0 default, 1 explicit, 2 implicit
 	int direct_8x8_inference = 1;
+	// entropy coder / High-profile tools
+	int cabac = 0;             // entropy_coding_mode_flag
+	int cabac_init_idc = -1;   // -1: drawn per slice
+	int transform8x8 = 0;      // transform_8x8_mode_flag (needs cabac = 1 and profile = 100): Intra8x8 + 8x8 residual
 };
 
 struct Mpeg2Opts {
