@@ -164,7 +164,8 @@ def main():
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000 * t / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
+            "config": {"workload": workload, "lanes_per_gpu": a.lanes, "frames_per_lane": a.frames, "coded_size": "1920x1088",
+                       "display_size": "1920x1080", "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -174,6 +175,7 @@ def main():
     import torch
     import m2dec_b200
     from m2dec_b200 import _native as L
+    from m2dec_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the reconstruction path has no CPU fallback")
@@ -185,7 +187,7 @@ def main():
 
     # ---- build the workload: parse on the host once, make every picture resident in HBM ------
     t_prep = time.perf_counter()
-    seeds = [100 + rank * 1000 + i for i in range(a.lanes)]
+    seeds = shard.rank_seeds(rank, a.lanes)
     streams = [make_stream(s, a.frames) for s in seeds]
     rp = m2dec_b200.Replay("h264", MBW * 16, MBH * 16, a.lanes, pool_frames=18, cuda_device=local)
     for lane, s in enumerate(streams):
@@ -243,12 +245,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device time of the last timed step (events between the phases of every sub-step)
     kernel_ms = [st.kernel_ms[i] for i in range(3)]
-    if dist is not None:
-        tt = torch.tensor([total_ms], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
     frames_per_step = a.lanes * a.frames
-    value = world * frames_per_step * a.steps / (total_ms / 1000.0)
+    value = shard.whole_job_rate(frames_per_step * a.steps, total_ms / 1000.0, dist, "cuda")
+    total_ms = shard.max_over_ranks(total_ms, dist, "cuda")
 
     # ---- end to end through the plugin table with host buffers --------------------------------
     ne = min(a.e2e_streams, a.lanes)
@@ -305,12 +304,9 @@ def main():
     run_pool()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
     e2e_frames = sum(frames_out)
-    e2e_value = world * e2e_frames / e2e_s
+    e2e_value = shard.whole_job_rate(e2e_frames, e2e_s, dist, "cuda")
+    e2e_s = shard.max_over_ranks(e2e_s, dist, "cuda")
     h2d = sum(c[0] for c in counts)
     d2h = sum(c[1] for c in counts)
 

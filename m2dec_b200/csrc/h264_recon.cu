@@ -802,7 +802,9 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 	const int a = m.intra_avail | m.intra_avail_c;
 	if (lane < 25) {            // above row: x = -1 .. 23
 		int x = lane - 1;
-		bool ok = (a & 2) && !(x < 0 && mbx == 0) && !(x >= 16 && mbx == job.mb_w - 1);
+		// each part of the row by its own availability bit, as the reference's predictors see them
+		// (the top-left bit survives constrained-intra masking of the MB above, h264.cpp:3271-3273)
+		bool ok = x < 0 ? (a & 8) && mbx > 0 : (x < 16 ? (a & 2) != 0 : (a & 4) && mbx < job.mb_w - 1);
 		tl.y[0][lane] = (ok && mby > 0) ? __ldcg(py - (ptrdiff_t)W + x) : 128;
 	}
 	if (lane < 16) tl.y[1 + lane][0] = ((a & 1) && mbx > 0) ? __ldcg(py + (size_t)lane * W - 1) : 128;

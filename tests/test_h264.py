@@ -149,3 +149,24 @@ def test_cuda_1080p_baseline():
     gpu = m2dec_b200.decode_file("h264", data)
     want = util.ref_md5(data, "264") if util.have_ref() else util.oracle_md5("h264", data)
     assert len(gpu) == 6 and gpu == want
+
+
+@pytest.mark.gpu
+def test_cuda_1080p_high_cabac_b():
+    """BASELINE config 3: H.264 CABAC 1920x1080 with B pictures, weighted prediction, both direct
+    modes' machinery and the High-profile 8x8 transform / Intra8x8."""
+    import m2dec_b200
+    data = streams.generate("h264", "mbw=120 mbh=68 frames=7 seed=43 crop_bottom=8 refs=2 bframes=2 cabac=1 profile=100 "
+                                    "transform8x8=1 weighted_pred=1 weighted_bipred=2 intra_pct=10")
+    gpu = m2dec_b200.decode_file("h264", data)
+    want = util.ref_md5(data, "264") if util.have_ref() else util.oracle_md5("h264", data)
+    assert len(gpu) == 7 and gpu == want
+
+
+def test_oracle_1080p_high_cabac_b_slice():
+    """Same configuration, 1920x1088 coded, fewer frames: product parse + CPU oracle vs the compiled reference."""
+    if not util.have_ref():
+        pytest.skip("oracle/_ref not built")
+    data = streams.generate("h264", "mbw=120 mbh=68 frames=4 seed=44 crop_bottom=8 refs=2 bframes=2 cabac=1 profile=100 "
+                                    "transform8x8=1 weighted_pred=1 weighted_bipred=1 direct_spatial=0")
+    assert util.oracle_md5("h264", data) == util.ref_md5(data, "264")
