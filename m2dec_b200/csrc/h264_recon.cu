@@ -1228,7 +1228,7 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 constexpr int WAVE_WARPS = 8;
 
 template <int PHASE>   // 1 intra, 2 deblock
-__global__ void __launch_bounds__(32 * WAVE_WARPS)
+__global__ void __launch_bounds__(32 * WAVE_WARPS, PHASE == 2 ? 3 : 2)
 h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
 	__shared__ union { IntraTile intra; DbkTile dbk; } s_tile[WAVE_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
