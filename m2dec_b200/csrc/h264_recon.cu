@@ -1211,10 +1211,14 @@ __device__ void deblock_mb(const H4Job &job, const b2_h264_dbk *dp, int mbx, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// persistent wavefront: a warp owns one MB row of one picture and walks it left to right, staying
-// two macroblocks behind the row above (left / top / top-right dependencies).  Rows are handed out
-// through a ticket counter in (row, job) order, so the warp a row waits for always holds an earlier
-// ticket and is already running: no deadlock whatever the CTA scheduling order.
+// deblocking, second form: one warp walks a macroblock row and keeps a sliding tile.
+//   * all 32 lanes run one code path: lanes 0..15 hold a luma line of 20 samples, lanes 16..31 a
+//     chroma line of ONE component (10 samples parked at v[2..11], so that the chroma edges sit at
+//     the register positions of luma edges 0 and 1);
+//   * the last four columns of a macroblock stay in shared memory for the next macroblock's left
+//     edge instead of going through L2 (they are stored once, when final);
+//   * the untouched pixels and the strength record of the next macroblock that needs work are
+//     fetched while the current one is filtered.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire(const int *p) {
 	int v;
@@ -1225,26 +1229,291 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Progress of a macroblock row ("macroblocks < n are final") as seen by the row below.  Rows of
+// one CTA's group hand it over through shared memory with CTA-scope fences; only the first row of
+// a group reads, and only the last one writes, the GPU-scope flag in global memory.
+struct RowSync {
+	volatile int *sm_above;   // row above is in this CTA (else null)
+	const int *gl_above;      // row above belongs to another CTA (else null)
+	volatile int *sm_my;
+	int *gl_my;               // null: no other CTA reads this row's progress
+	int seen;                 // progress of the row above known so far
+
+	__device__ __forceinline__ void wait(int want, int lane) {
+		if (seen >= want) return;
+		if (sm_above) {
+			if (lane == 0) {
+				while ((seen = *sm_above) < want) { }
+				__threadfence_block();
+			}
+		} else if (gl_above) {
+			if (lane == 0) {
+				while ((seen = ld_acquire(gl_above)) < want) __nanosleep(32);
+			}
+		} else {
+			seen = 1 << 30;
+		}
+		seen = __shfl_sync(0xffffffffu, seen, 0);
+	}
+	// all lanes' stores so far become visible before the new value (the caller has them behind a __syncwarp)
+	__device__ __forceinline__ void publish(int v, int lane) {
+		__syncwarp();
+		if (lane == 0) {
+			if (gl_my) st_release(gl_my, v);
+			else __threadfence_block();
+			*sm_my = v;
+		}
+	}
+};
+
+struct DbkTables { uint8_t alpha[52], beta[52], tc0[52][4]; };
+
+__device__ __forceinline__ void dbk_filter(int *v, const int q, const int bs, const int alpha, const int beta, const int tc0, const bool luma) {
+	const int p0 = v[q - 1], p1 = v[q - 2], p2 = v[q - 3], q0 = v[q], q1 = v[q + 1], q2 = v[q + 2];
+	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+	const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
+	if (bs < 4) {
+		const int tc = luma ? tc0 + ap + aq : tc0 + 1, avg = (p0 + q0 + 1) >> 1;
+		if (ap) v[q - 2] = p1 + min(max((p2 + avg - 2 * p1) >> 1, -tc0), tc0);
+		if (aq) v[q + 1] = q1 + min(max((q2 + avg - 2 * q1) >> 1, -tc0), tc0);
+		const int delta = min(max(((q0 - p0) * 4 + (p1 - q1) + 4) >> 3, -tc), tc);
+		v[q - 1] = clip255(p0 + delta);
+		v[q] = clip255(q0 - delta);
+	} else {
+		const bool strong = luma && abs(p0 - q0) < (alpha >> 2) + 2;
+		if (strong && ap) {
+			const int p3 = v[q - 4];
+			v[q - 1] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+			v[q - 2] = (p2 + p1 + p0 + q0 + 2) >> 2;
+			v[q - 3] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+		} else {
+			v[q - 1] = (2 * p1 + p0 + q1 + 2) >> 2;
+		}
+		if (strong && aq) {
+			const int q3 = v[q + 3];
+			v[q] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+			v[q + 1] = (p0 + q0 + q1 + q2 + 2) >> 2;
+			v[q + 2] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+		} else {
+			v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
+		}
+	}
+}
+
+// the (up to four) edges of one line held in v[]; bits = the 32-bit strength word of the
+// direction, seg = 4-sample segment of this line, qpc / qpn = QP of this MB / of the MB across edge 0
+__device__ __forceinline__ void dbk_line(int *v, const DbkTables &tb, uint32_t bits, int seg, bool luma, bool edge0_ok, bool edge0_bs4,
+                                         int qpc, int qpn, int aoff, int boff) {
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		if (!luma && i >= 2) break;
+		const int e = luma ? i : 2 * i;                 // chroma edges 0 / 1 of the register layout are luma edges 0 / 2
+		int bs = (bits >> (8 * e + 2 * seg)) & 3;
+		if (!bs || (e == 0 && !edge0_ok)) continue;
+		if (e == 0 && edge0_bs4) bs = 4;
+		const int qp = e ? qpc : (qpc + qpn + 1) >> 1;
+		const int ia = min(max(qp + aoff, 0), 51), ib = min(max(qp + boff, 0), 51);
+		const int alpha = tb.alpha[ia];
+		if (alpha) dbk_filter(v, 4 + 4 * i, bs, alpha, tb.beta[ib], bs < 4 ? tb.tc0[ia][bs - 1] : 0, luma);
+	}
+}
+
+// One row chunk: macroblocks x0 + k for the set bits k of `todo`, left to right.
+__device__ void deblock_chunk(const H4Job &job, const DbkTables &tb, DbkTile &tl, int mby, int x0, unsigned todo, int lane,
+                              RowSync &sy, int &done_to) {
+	const int mb_w = job.mb_w, W = mb_w * 16, H = job.mb_h * 16;
+	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
+	uint8_t *fc = fy + (size_t)W * H;
+	const bool luma = lane < 16;
+	const int comp = lane & 1;                              // chroma lanes: component
+	const int line = luma ? lane : (lane - 16) >> 1;        // V pass: picture line inside the MB (chroma: 0..7)
+	// V-pass source line of this lane inside the picture (bytes), without the MB x offset
+	const uint8_t *line_base = luma ? fy + (size_t)(mby * 16 + line) * W : fc + (size_t)(mby * 8 + line) * W;
+	uint32_t nw[4] = {0, 0, 0, 0};       // prefetched own words of the next macroblock
+	uint4 nd = make_uint4(0, 0, 0, 0);   // its strength record
+	uint32_t nql = 0, nqt = 0;           // QP words of its left / top neighbour records
+	bool have_next = false, carry_in = false;
+	while (todo) {
+		const int k = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const int x = x0 + k;
+		const int kn = todo ? __ffs(todo) - 1 : -1;
+		const bool carry_out = kn == k + 1;               // the next macroblock takes over columns 12..15
+		if (x > done_to) sy.publish(x, lane);              // the stretch that needed nothing
+		const b2_h264_dbk *dp = job.dbk + (size_t)mby * mb_w + x;
+		uint32_t w[5];
+		uint4 dr;
+		uint32_t ql, qt;
+		if (have_next) {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) w[1 + i] = nw[i];
+			dr = nd; ql = nql; qt = nqt;
+		} else {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) w[1 + i] = __ldcg(reinterpret_cast<const uint32_t *>(line_base + x * 16 + 4 * i));
+			dr = __ldg(reinterpret_cast<const uint4 *>(dp));
+			ql = x > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dp - 1) + 2) : 0;
+			qt = mby > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dp - mb_w) + 2) : 0;
+		}
+		if (mby > 0) sy.wait(min(x + 2, mb_w), lane);
+		// rows above the macroblock (final once the row above is two macroblocks ahead): lanes 0..15 one
+		// word of luma rows -4..-1, lanes 16..23 one word of chroma rows -2..-1
+		uint32_t tw = 0;
+		if (mby > 0 && lane < 24) {
+			const uint8_t *src = luma ? fy + (size_t)(mby * 16 - 4 + (lane >> 2)) * W : fc + (size_t)(mby * 8 - 2 + ((lane - 16) >> 2)) * W;
+			tw = __ldcg(reinterpret_cast<const uint32_t *>(src + x * 16 + 4 * (lane & 3)));
+		}
+		// left four columns: from the tile when the previous macroblock left them there
+		if (carry_in) w[0] = *reinterpret_cast<const uint32_t *>(luma ? &tl.y[4 + line][0] : &tl.c[2 + line][0]);
+		else w[0] = x > 0 ? __ldcg(reinterpret_cast<const uint32_t *>(line_base + x * 16 - 4)) : 0;
+		// prefetch for the next macroblock of this chunk
+		have_next = kn >= 0;
+		if (have_next) {
+			const int xn = x0 + kn;
+			const b2_h264_dbk *dn = job.dbk + (size_t)mby * mb_w + xn;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) nw[i] = __ldcg(reinterpret_cast<const uint32_t *>(line_base + xn * 16 + 4 * i));
+			nd = __ldg(reinterpret_cast<const uint4 *>(dn));
+			nql = __ldg(reinterpret_cast<const uint32_t *>(dn - 1) + 2);      // xn > 0 always
+			nqt = mby > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dn - mb_w) + 2) : 0;
+		}
+		// ---- record fields ---------------------------------------------------------------------------
+		const uint32_t bs_v = dr.x, bs_h = dr.y;
+		const int flags = (dr.z >> 24) & 255;
+		const int aoff = (int8_t)(dr.w & 255), boff = (int8_t)((dr.w >> 8) & 255);
+		const int qsel = luma ? 0 : 8 + 8 * comp;            // byte of the QP word: qp_y, qp_cb, qp_cr
+		const int qpc = (int8_t)((dr.z >> qsel) & 255), qpl = (int8_t)((ql >> qsel) & 255), qpt = (int8_t)((qt >> qsel) & 255);
+		const bool left_ok = flags & B2_DBK_LEFT_EDGE, top_ok = flags & B2_DBK_TOP_EDGE;
+		// ---- V pass ----------------------------------------------------------------------------------
+		{
+			int v[20];
+#pragma unroll
+			for (int i = 0; i < 20; ++i) v[i] = 0;
+			if (luma) {
+#pragma unroll
+				for (int i = 0; i < 20; ++i) v[i] = (w[i >> 2] >> ((i & 3) * 8)) & 255;
+			} else {
+#pragma unroll
+				for (int i = 0; i < 10; ++i) v[2 + i] = (w[i >> 1] >> (((i & 1) * 2 + comp) * 8)) & 255;
+			}
+			if (bs_v) dbk_line(v, tb, bs_v, luma ? line >> 2 : line >> 1, luma, left_ok, flags & B2_DBK_LEFT_BS4, qpc, qpl, aoff, boff);
+			if (luma) {
+				uint32_t *dstw = reinterpret_cast<uint32_t *>(&tl.y[4 + line][0]);
+#pragma unroll
+				for (int j = 0; j < 5; ++j)
+					dstw[j] = (uint32_t)v[4 * j] | ((uint32_t)v[4 * j + 1] << 8) | ((uint32_t)v[4 * j + 2] << 16) | ((uint32_t)v[4 * j + 3] << 24);
+			} else {
+				uint8_t *dstb = &tl.c[2 + line][comp];
+#pragma unroll
+				for (int i = 0; i < 10; ++i) dstb[2 * i] = (uint8_t)v[2 + i];
+			}
+			if (lane < 24) {
+				uint32_t *dstw = reinterpret_cast<uint32_t *>(luma ? &tl.y[lane >> 2][4] : &tl.c[(lane - 16) >> 2][4]);
+				dstw[lane & 3] = tw;
+			}
+		}
+		__syncwarp();
+		// ---- H pass: lanes 0..15 luma column, lanes 16..31 chroma byte column ---------------------------
+		if (bs_h) {
+			const int col = lane & 15;
+			int v[20];
+#pragma unroll
+			for (int i = 0; i < 20; ++i) v[i] = 0;
+			if (luma) {
+#pragma unroll
+				for (int i = 0; i < 20; ++i) v[i] = tl.y[i][4 + col];
+			} else {
+#pragma unroll
+				for (int i = 0; i < 10; ++i) v[2 + i] = tl.c[i][4 + col];
+			}
+			dbk_line(v, tb, bs_h, col >> 2, luma, top_ok, flags & B2_DBK_TOP_BS4, qpc, qpt, aoff, boff);
+			if (luma) {
+#pragma unroll
+				for (int i = 1; i < 20; ++i) tl.y[i][4 + col] = (uint8_t)v[i];
+			} else {
+#pragma unroll
+				for (int i = 1; i < 10; ++i) tl.c[i][4 + col] = (uint8_t)v[2 + i];
+			}
+			__syncwarp();
+		}
+		// ---- store what is final: columns -4..11 (or ..15 when nobody takes them over) of the lines, and
+		//      the rows above (luma -3..-1 by lanes 24..26, chroma -1 by lane 27) ---------------------------
+		if (lane < 24) {
+			const int li = lane < 16 ? lane : lane - 16;
+			const uint32_t *srcw = reinterpret_cast<const uint32_t *>(lane < 16 ? &tl.y[4 + li][0] : &tl.c[2 + li][0]);
+			uint8_t *dst = (lane < 16 ? fy + (size_t)(mby * 16 + li) * W : fc + (size_t)(mby * 8 + li) * W) + x * 16;
+			if (x > 0) __stcg(reinterpret_cast<uint32_t *>(dst - 4), srcw[0]);
+#pragma unroll
+			for (int j = 1; j < 4; ++j) __stcg(reinterpret_cast<uint32_t *>(dst + 4 * (j - 1)), srcw[j]);
+			if (!carry_out) __stcg(reinterpret_cast<uint32_t *>(dst + 12), srcw[4]);
+		} else if (lane < 28 && top_ok) {
+			const bool tl_luma = lane < 27;
+			const int r = tl_luma ? lane - 27 : -1;                 // luma rows -3..-1, chroma row -1
+			const uint32_t *srcw = reinterpret_cast<const uint32_t *>(tl_luma ? &tl.y[4 + r][4] : &tl.c[2 + r][4]);
+			uint8_t *dst = (tl_luma ? fy + (size_t)(mby * 16 + r) * W : fc + (size_t)(mby * 8 + r) * W) + x * 16;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) __stcg(reinterpret_cast<uint32_t *>(dst + 4 * j), srcw[j]);
+		}
+		__syncwarp();
+		if (carry_out && lane < 24) {
+			uint32_t *rw = reinterpret_cast<uint32_t *>(lane < 16 ? &tl.y[4 + lane][0] : &tl.c[2 + lane - 16][0]);
+			rw[0] = rw[4];
+		}
+		carry_in = carry_out;
+		// progress: everything up to x is final, except columns 12..15 of x itself when they were carried
+		// over -- which the row below does not touch before it has seen x + 2
+		done_to = x + 1;
+		sy.publish(x + 1, lane);
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent wavefront: a warp owns one MB row of one picture and walks it left to right, staying
+// two macroblocks behind the row above (left / top / top-right dependencies).  Rows are handed out
+// through a ticket counter in (row, job) order, so the warp a row waits for always holds an earlier
+// ticket and is already running: no deadlock whatever the CTA scheduling order.
+// ------------------------------------------------------------------------------------------------
+
 constexpr int WAVE_WARPS = 8;
 
 template <int PHASE>   // 1 intra, 2 deblock
 __global__ void __launch_bounds__(32 * WAVE_WARPS, PHASE == 2 ? 3 : 2)
 h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
 	__shared__ union { IntraTile intra; DbkTile dbk; } s_tile[WAVE_WARPS];
+	__shared__ DbkTables s_tb;
+	__shared__ int s_ticket;
+	__shared__ int s_prog[WAVE_WARPS];
+	if (PHASE == 2) {
+		for (int i = threadIdx.x; i < 52; i += blockDim.x) {
+			s_tb.alpha[i] = c_alpha[i];
+			s_tb.beta[i] = c_beta[i];
+			s_tb.tc0[i][0] = c_tc0[i][0]; s_tb.tc0[i][1] = c_tc0[i][1]; s_tb.tc0[i][2] = c_tc0[i][2]; s_tb.tc0[i][3] = 0;
+		}
+	}
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int *ticket = sync_area;
-	int *progress = sync_area + 32;           // [n_jobs][mb_h]: macroblocks of the row that are final
-	const int total = n_jobs * mb_h;
+	int *progress = sync_area + 32;           // [n_jobs][mb_h]: macroblocks of the row that are final (rows read across CTAs only)
+	const int groups = (mb_h + WAVE_WARPS - 1) / WAVE_WARPS;
+	const int total = n_jobs * groups;
 	for (;;) {
-		int t = 0;
-		if (lane == 0) t = atomicAdd(ticket, 1);
-		t = __shfl_sync(0xffffffffu, t, 0);
+		__syncthreads();                       // the previous group is complete: s_ticket / s_prog may be reused
+		if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+		if (threadIdx.x < WAVE_WARPS) s_prog[threadIdx.x] = 0;
+		__syncthreads();
+		const int t = s_ticket;
 		if (t >= total) return;
-		const int j = t % n_jobs, mby = t / n_jobs;
+		// group-major ticket order: the group a CTA waits for (same picture, rows just above) always
+		// holds an earlier ticket, so its CTA is resident or done -- no deadlock
+		const int j = t % n_jobs, mby = (t / n_jobs) * WAVE_WARPS + warp;
+		if (mby >= mb_h) continue;
+		RowSync sy;
+		sy.sm_above = warp > 0 ? &s_prog[warp - 1] : nullptr;
+		sy.gl_above = (warp == 0 && mby > 0) ? progress + (size_t)j * mb_h + mby - 1 : nullptr;
+		sy.sm_my = &s_prog[warp];
+		sy.gl_my = (warp == WAVE_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
+		sy.seen = 0;
 		const H4Job job = jobs[j];
-		int *my = progress + (size_t)j * mb_h + mby;
-		const int *above = my - 1;
-		int seen = 0;                          // progress of the row above known so far
 		for (int x0 = 0; x0 < mb_w; x0 += 32) {
 			// which of the next 32 macroblocks need work in this phase
 			int mbx = x0 + lane;
@@ -1258,41 +1527,24 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 			}
 			unsigned todo = __ballot_sync(0xffffffffu, need);
 			int done_to = x0;                  // macroblocks < done_to are final
+			if (PHASE == 2) {
+				deblock_chunk(job, s_tb, s_tile[warp].dbk, mby, x0, todo, lane, sy, done_to);
+				todo = 0;
+			}
 			while (todo) {
 				int k = __ffs(todo) - 1;
 				todo &= todo - 1;
 				int x = x0 + k;
-				if (x > done_to) {             // publish the stretch that needed nothing
-					__syncwarp();
-					if (lane == 0) st_release(my, x);
-				}
-				if (mby > 0) {
-					int want = min(x + 2, mb_w);
-					if (seen < want) {
-						if (lane == 0) {
-							while ((seen = ld_acquire(above)) < want) __nanosleep(64);
-						}
-						seen = __shfl_sync(0xffffffffu, seen, 0);
-					}
-				}
-				if (PHASE == 1) {
-					const b2_h264_mb m = job.mbs[(size_t)mby * mb_w + x];
-					intra_mb(job, m, x, mby, s_tile[warp].intra, lane);
-				} else {
-					deblock_mb(job, &job.dbk[(size_t)mby * mb_w + x], x, mby, s_tile[warp].dbk, lane);
-				}
-				__syncwarp();
+				if (x > done_to) sy.publish(x, lane);     // the stretch that needed nothing
+				if (mby > 0) sy.wait(min(x + 2, mb_w), lane);
+				const b2_h264_mb m = job.mbs[(size_t)mby * mb_w + x];
+				intra_mb(job, m, x, mby, s_tile[warp].intra, lane);
 				done_to = x + 1;
-				if (lane == 0) st_release(my, done_to);
+				sy.publish(done_to, lane);
 			}
 			int end = min(x0 + 32, mb_w);
-			if (done_to < end) {
-				// the rest of the chunk needs no work here, but the row above must still have produced
-				// what *later phases of this row's neighbours* rely on?  No: progress only orders work of
-				// this phase, and a macroblock without work has nothing to wait for.
-				__syncwarp();
-				if (lane == 0) st_release(my, end);
-			}
+			// a macroblock without work in this phase has nothing to wait for
+			if (done_to < end) sy.publish(end, lane);
 		}
 	}
 }
@@ -1313,8 +1565,7 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 	} else {
 		int *area = sync_area;
 		B2_CUDA_OK(cudaMemsetAsync(area, 0, h264_sync_bytes(n_jobs, mb_h), stream));
-		int rows = n_jobs * mb_h;
-		int ctas = (rows + WAVE_WARPS - 1) / WAVE_WARPS;
+		int ctas = n_jobs * ((mb_h + WAVE_WARPS - 1) / WAVE_WARPS);
 		int cap = 148 * 6;
 		if (ctas > cap) ctas = cap;
 		if (phase == 1) h264_wave_kernel<1><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);

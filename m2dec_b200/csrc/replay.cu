@@ -3,6 +3,13 @@
 // This is how the reconstruction kernels are driven at throughput: a single 1080p picture is
 // ~14 MB of traffic (~2 us at HBM speed, less than a launch), so frames of independent
 // streams / closed GOPs are batched into each launch (SURVEY.md §7 "hard parts").
+//
+// The intra and deblocking kernels are wavefronts: one launch cannot finish faster than the
+// dependency chain of a single picture (254 macroblock steps at 1080p), however many pictures it
+// holds, and runs with few rows in flight while that chain ramps up and down.  The lanes are
+// can therefore be split into groups ($B2_REPLAY_GROUPS), each with its own CUDA stream and chain of
+// launches; the groups are independent, so their kernels overlap on the device.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "device_common.cuh"
@@ -12,10 +19,17 @@ using namespace b2;
 namespace {
 struct Blob { uint8_t *dev; size_t bytes; };
 struct Step {
-	std::vector<H4Job> h4;       // one job per lane that has a picture at this step
+	std::vector<H4Job> h4;       // one job per lane (of the group) that has a picture at this step
 	std::vector<M2Job> m2;
 	void *d_jobs = nullptr;
 	bool any_inter = false, any_intra = false, deblock = false;
+};
+struct Group {
+	cudaStream_t stream = nullptr;
+	int *sync_area = nullptr;
+	std::vector<Step> steps;
+	std::vector<cudaEvent_t> ev;     // 4 per step when timing
+	cudaEvent_t done = nullptr;
 };
 }  // namespace
 
@@ -23,14 +37,12 @@ struct b2_replay {
 	int dev, codec, width, height, lanes, pool;
 	size_t frame_bytes;
 	uint8_t *frames;
-	int *sync_area;
-	cudaStream_t stream;
+	cudaStream_t stream;             // time line: begin / end / mark events; the groups fork from and join it
+	std::vector<Group> groups;       // lane l belongs to group l % groups.size()
 	std::vector<Blob> blobs;
 	std::vector<int> lane_len;
-	std::vector<Step> steps;
 	bool dirty;
 	b2_replay_stats stats;
-	std::vector<cudaEvent_t> ev;     // 4 per step when timing
 	cudaEvent_t ev_begin, ev_end, ev_mark[2];
 	bool timed_pending;
 	float acc_ms[3];
@@ -54,7 +66,19 @@ extern "C" int b2_replay_create(int cuda_device, int codec, int width, int heigh
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaMalloc(&r->frames, r->frame_bytes * pool_frames * lanes));
 	B2_CUDA_OK(cudaMemset(r->frames, 0, r->frame_bytes * pool_frames * lanes));
-	B2_CUDA_OK(cudaMalloc(&r->sync_area, h264_sync_bytes(lanes, height / 16)));
+	// default: one group.  Measured on B200 (64 and 128 lanes of 1080p, 3 pictures each): 2 / 4 / 8
+	// groups took 1.04x / 1.15x / 1.19x and 0.99x / 1.09x / 1.26x the time of one group -- the
+	// kernels are bound by their own synchronisation, not by the ramps.
+	int ng = 1;
+	if (const char *e = getenv("B2_REPLAY_GROUPS")) ng = atoi(e);
+	if (ng < 1) ng = 1;
+	if (ng > lanes) ng = lanes;
+	r->groups.resize(ng);
+	for (Group &g : r->groups) {
+		B2_CUDA_OK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+		B2_CUDA_OK(cudaMalloc(&g.sync_area, h264_sync_bytes((lanes + ng - 1) / ng, height / 16)));
+		B2_CUDA_OK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+	}
 	B2_CUDA_OK(cudaEventCreate(&r->ev_begin));
 	B2_CUDA_OK(cudaEventCreate(&r->ev_end));
 	B2_CUDA_OK(cudaEventCreate(&r->ev_mark[0]));
@@ -68,12 +92,19 @@ extern "C" void b2_replay_destroy(b2_replay *r) {
 	cudaSetDevice(r->dev);
 	cudaStreamSynchronize(r->stream);
 	for (Blob &b : r->blobs) cudaFree(b.dev);
-	for (Step &s : r->steps) if (s.d_jobs) cudaFree(s.d_jobs);
-	for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
+	for (Group &g : r->groups) {
+		cudaStreamSynchronize(g.stream);
+		for (Step &s : g.steps) if (s.d_jobs) cudaFree(s.d_jobs);
+		for (cudaEvent_t e : g.ev) cudaEventDestroy(e);
+		cudaEventDestroy(g.done);
+		cudaFree(g.sync_area);
+		cudaStreamDestroy(g.stream);
+	}
 	cudaEventDestroy(r->ev_begin);
 	cudaEventDestroy(r->ev_end);
+	cudaEventDestroy(r->ev_mark[0]);
+	cudaEventDestroy(r->ev_mark[1]);
 	cudaFree(r->frames);
-	cudaFree(r->sync_area);
 	cudaStreamDestroy(r->stream);
 	delete r;
 }
@@ -116,8 +147,9 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	job.coefs = (const int16_t *)(d + off[3]);
 	job.dst = p->dst; job.mb_w = p->mb_w; job.mb_h = p->mb_h;
 	int t = r->lane_len[lane]++;
-	if ((int)r->steps.size() <= t) r->steps.resize(t + 1);
-	Step &s = r->steps[t];
+	std::vector<Step> &steps = r->groups[lane % r->groups.size()].steps;
+	if ((int)steps.size() <= t) steps.resize(t + 1);
+	Step &s = steps[t];
 	s.h4.push_back(job);
 	s.any_inter |= p->n_intra < p->n_mbs;
 	s.any_intra |= p->n_intra > 0;
@@ -160,8 +192,9 @@ extern "C" int b2_replay_add_mpeg2(b2_replay *r, int lane, const b2_m2_picture *
 	job.coefs = (const int16_t *)(d + off[1]);
 	job.mb_w = p->mb_w; job.mb_h = p->mb_h;
 	int t = r->lane_len[lane]++;
-	if ((int)r->steps.size() <= t) r->steps.resize(t + 1);
-	r->steps[t].m2.push_back(job);
+	std::vector<Step> &steps = r->groups[lane % r->groups.size()].steps;
+	if ((int)steps.size() <= t) steps.resize(t + 1);
+	steps[t].m2.push_back(job);
 	uint64_t rbytes = 0;
 	for (uint32_t i = 0; i < p->n_mbs; ++i) {
 		int f = p->mbs[i].flags;
@@ -175,16 +208,18 @@ extern "C" int b2_replay_add_mpeg2(b2_replay *r, int lane, const b2_m2_picture *
 
 static int finalize(b2_replay *r) {
 	if (!r->dirty) return 0;
-	for (Step &s : r->steps) {
-		if (s.d_jobs) { cudaFree(s.d_jobs); s.d_jobs = nullptr; }
-		size_t bytes = r->codec == B2_CODEC_H264 ? s.h4.size() * sizeof(H4Job) : s.m2.size() * sizeof(M2Job);
-		if (!bytes) continue;
-		B2_CUDA_OK(cudaMalloc(&s.d_jobs, bytes));
-		B2_CUDA_OK(cudaMemcpy(s.d_jobs, r->codec == B2_CODEC_H264 ? (const void *)s.h4.data() : (const void *)s.m2.data(), bytes, cudaMemcpyHostToDevice));
+	for (Group &g : r->groups) {
+		for (Step &s : g.steps) {
+			if (s.d_jobs) { cudaFree(s.d_jobs); s.d_jobs = nullptr; }
+			size_t bytes = r->codec == B2_CODEC_H264 ? s.h4.size() * sizeof(H4Job) : s.m2.size() * sizeof(M2Job);
+			if (!bytes) continue;
+			B2_CUDA_OK(cudaMalloc(&s.d_jobs, bytes));
+			B2_CUDA_OK(cudaMemcpy(s.d_jobs, r->codec == B2_CODEC_H264 ? (const void *)s.h4.data() : (const void *)s.m2.data(), bytes, cudaMemcpyHostToDevice));
+		}
+		for (cudaEvent_t e : g.ev) cudaEventDestroy(e);
+		g.ev.resize(g.steps.size() * 4);
+		for (auto &e : g.ev) B2_CUDA_OK(cudaEventCreate(&e));
 	}
-	for (cudaEvent_t e : r->ev) cudaEventDestroy(e);
-	r->ev.resize(r->steps.size() * 4);
-	for (auto &e : r->ev) B2_CUDA_OK(cudaEventCreate(&e));
 	r->dirty = false;
 	return 0;
 }
@@ -196,23 +231,36 @@ extern "C" int b2_replay_run(b2_replay *r, int timed) {
 	const int mb_w = r->width / 16, mb_h = r->height / 16;
 	uint64_t launches = 0;
 	B2_CUDA_OK(cudaEventRecord(r->ev_begin, r->stream));
-	for (size_t t = 0; t < r->steps.size(); ++t) {
-		Step &s = r->steps[t];
-		if (!s.d_jobs) continue;
-		if (r->codec == B2_CODEC_MPEG2) {
-			if (launch_mpeg2(r->stream, (const M2Job *)s.d_jobs, (int)s.m2.size(), mb_w, mb_h) < 0) return -1;
-			launches++;
-			continue;
+	size_t n_steps = 0;
+	for (Group &g : r->groups) {
+		B2_CUDA_OK(cudaStreamWaitEvent(g.stream, r->ev_begin, 0));
+		if (g.steps.size() > n_steps) n_steps = g.steps.size();
+	}
+	// step-major issue order: the groups' chains advance together
+	for (size_t t = 0; t < n_steps; ++t) {
+		for (Group &g : r->groups) {
+			if (t >= g.steps.size()) continue;
+			Step &s = g.steps[t];
+			if (!s.d_jobs) continue;
+			if (r->codec == B2_CODEC_MPEG2) {
+				if (launch_mpeg2(g.stream, (const M2Job *)s.d_jobs, (int)s.m2.size(), mb_w, mb_h) < 0) return -1;
+				launches++;
+				continue;
+			}
+			const H4Job *jobs = (const H4Job *)s.d_jobs;
+			int n = (int)s.h4.size();
+			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 0], g.stream));
+			if (s.any_inter && launch_h264_phase(g.stream, 0, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
+			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 1], g.stream));
+			if (s.any_intra && launch_h264_phase(g.stream, 1, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
+			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 2], g.stream));
+			if (s.deblock && launch_h264_phase(g.stream, 2, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
+			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 3], g.stream));
 		}
-		const H4Job *jobs = (const H4Job *)s.d_jobs;
-		int n = (int)s.h4.size();
-		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 0], r->stream));
-		if (s.any_inter && launch_h264_phase(r->stream, 0, jobs, n, mb_w, mb_h, r->sync_area, &launches) < 0) return -1;
-		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 1], r->stream));
-		if (s.any_intra && launch_h264_phase(r->stream, 1, jobs, n, mb_w, mb_h, r->sync_area, &launches) < 0) return -1;
-		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 2], r->stream));
-		if (s.deblock && launch_h264_phase(r->stream, 2, jobs, n, mb_w, mb_h, r->sync_area, &launches) < 0) return -1;
-		if (timed) B2_CUDA_OK(cudaEventRecord(r->ev[t * 4 + 3], r->stream));
+	}
+	for (Group &g : r->groups) {
+		B2_CUDA_OK(cudaEventRecord(g.done, g.stream));
+		B2_CUDA_OK(cudaStreamWaitEvent(r->stream, g.done, 0));
 	}
 	B2_CUDA_OK(cudaEventRecord(r->ev_end, r->stream));
 	r->stats.launches = launches;
@@ -226,16 +274,23 @@ extern "C" int b2_replay_sync(b2_replay *r) {
 	B2_CUDA_OK(cudaStreamSynchronize(r->stream));
 	B2_CUDA_OK(cudaEventElapsedTime(&r->stats.total_ms, r->ev_begin, r->ev_end));
 	if (r->timed_pending) {
+		// Per-kernel device time.  With one group these are the launches' own durations.  With
+		// several, launches of different groups overlap, so the event intervals are summed per
+		// kernel and the run's wall time is attributed to the kernels in proportion to those sums.
 		float acc[3] = {0, 0, 0};
 		if (r->codec == B2_CODEC_H264) {
-			for (size_t t = 0; t < r->steps.size(); ++t) {
-				if (!r->steps[t].d_jobs) continue;
-				for (int k = 0; k < 3; ++k) {
-					float ms = 0;
-					B2_CUDA_OK(cudaEventElapsedTime(&ms, r->ev[t * 4 + k], r->ev[t * 4 + k + 1]));
-					acc[k] += ms;
+			for (Group &g : r->groups)
+				for (size_t t = 0; t < g.steps.size(); ++t) {
+					if (!g.steps[t].d_jobs) continue;
+					for (int k = 0; k < 3; ++k) {
+						float ms = 0;
+						B2_CUDA_OK(cudaEventElapsedTime(&ms, g.ev[t * 4 + k], g.ev[t * 4 + k + 1]));
+						acc[k] += ms;
+					}
 				}
-			}
+			float sum = acc[0] + acc[1] + acc[2];
+			if (r->groups.size() > 1 && sum > 0)
+				for (int k = 0; k < 3; ++k) acc[k] = acc[k] / sum * r->stats.total_ms;
 		} else {
 			acc[0] = r->stats.total_ms;
 		}
