@@ -322,8 +322,19 @@ def main():
     alg = [int(st.alg_bytes[i]) for i in range(3)]
     achieved = alg[dom] / (kernel_ms[dom] / 1000.0) / 1e9 if kernel_ms[dom] > 0 else 0.0
     whole = sum(alg) / (st.total_ms / 1000.0) / 1e9 if st.total_ms > 0 else 0.0
+    # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture,
+    # scaled to this run's pictures per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        per_launch = tj["dram_bytes_per_launch"].get(names[dom])
+        if per_launch:
+            traffic = per_launch / tj["pictures_per_launch"] * a.lanes
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, P-picture step)",
+                "alg_bytes_per_launch": alg[dom] / max(1, a.frames - (1 if dom == 0 else 0)),
+                "peak_source": peak_src,
                 "per_kernel": {names[i]: {"ms_per_step": kernel_ms[i], "alg_bytes_per_step": alg[i],
                                           "GBps": (alg[i] / (kernel_ms[i] / 1000.0) / 1e9 if kernel_ms[i] > 0 else None)}
                                for i in range(3)},
