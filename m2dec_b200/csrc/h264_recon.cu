@@ -1514,6 +1514,7 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 		sy.gl_my = (warp == WAVE_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
 		sy.seen = 0;
 		const H4Job job = jobs[j];
+		if (PHASE == 1 && h264_intra_sparse(job.n_intra, mb_w * mb_h)) continue;     // h264_intra_sparse_kernel's
 		for (int x0 = 0; x0 < mb_w; x0 += 32) {
 			// which of the next 32 macroblocks need work in this phase
 			int mbx = x0 + lane;
@@ -1549,11 +1550,60 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 	}
 }
 
+// Intra macroblocks of pictures that have few of them (P / B pictures).  A warp takes 32 consecutive
+// macroblocks (raster order) at a time and reconstructs the intra ones among them; an intra
+// macroblock waits only for those of its left / top-left / top / top-right neighbours that are intra
+// themselves and that it may read (availability bits) -- inter neighbours were finished by the
+// kernel before.  Chunks are handed out in raster order, so a neighbour always belongs to a chunk
+// with an earlier ticket: no deadlock as long as every CTA of the grid is resident (persistent grid).
+__global__ void __launch_bounds__(32 * WAVE_WARPS, 2)
+h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
+	__shared__ IntraTile s_tile[WAVE_WARPS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int *ticket = sync_area + 1;
+	int *done = sync_area + 32;                // [n_jobs][n_mbs]
+	const int n_mbs = mb_w * mb_h, chunks = (n_mbs + 31) / 32;
+	const int total = n_jobs * chunks;
+	for (;;) {
+		int t = 0;
+		if (lane == 0) t = atomicAdd(ticket, 1);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= total) return;
+		const int j = t % n_jobs, c = t / n_jobs;
+		const H4Job job = jobs[j];
+		if (!h264_intra_sparse(job.n_intra, n_mbs) || job.n_intra == 0) continue;
+		int *flags = done + (size_t)j * n_mbs;
+		const int mb = c * 32 + lane;
+		unsigned todo = __ballot_sync(0xffffffffu, mb < n_mbs && job.mbs[mb].type != B2_H4_INTER);
+		while (todo) {
+			const int k = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const int m = c * 32 + k, mbx = m % mb_w, mby = m / mb_w;
+			const b2_h264_mb hdr = job.mbs[m];
+			if (lane < 4) {
+				// neighbour of lane: 0 left, 1 top, 2 top-right, 3 top-left (the availability bit order)
+				const int a = hdr.intra_avail | hdr.intra_avail_c;
+				const int nx = mbx + (lane == 0 || lane == 3 ? -1 : (lane == 2 ? 1 : 0)), ny = mby - (lane != 0);
+				if (((a >> lane) & 1) && nx >= 0 && nx < mb_w && ny >= 0) {
+					const int nb = ny * mb_w + nx;
+					if (job.mbs[nb].type != B2_H4_INTER)
+						while (!ld_acquire(flags + nb)) __nanosleep(32);
+				}
+			}
+			__syncwarp();
+			intra_mb(job, hdr, mbx, mby, s_tile[warp], lane);
+			__syncwarp();
+			if (lane == 0) st_release(flags + m, 1);
+		}
+	}
+}
+
 }  // namespace
 
-// bytes of scratch (ticket counter + per-row progress flags) the wavefront kernels need; the
-// caller owns one such area per CUDA stream, since kernels of different streams run concurrently
-size_t h264_sync_bytes(int n_jobs, int mb_h) { return (32 + (size_t)n_jobs * mb_h) * sizeof(int); }
+// ticket counters (32 ints) + row progress [n_jobs][mb_h] (wavefronts) or per-macroblock flags
+// [n_jobs][mb_w * mb_h] (sparse intra); the caller owns one such area per CUDA stream, since kernels
+// of different streams run concurrently
+size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h) { return (32 + (size_t)n_jobs * mb_w * mb_h) * sizeof(int); }
 
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches) {
 	if (n_jobs <= 0) return 0;
@@ -1564,7 +1614,17 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		if (launches) ++*launches;
 	} else {
 		int *area = sync_area;
-		B2_CUDA_OK(cudaMemsetAsync(area, 0, h264_sync_bytes(n_jobs, mb_h), stream));
+		if (phase == 3) {
+			B2_CUDA_OK(cudaMemsetAsync(area, 0, h264_sync_bytes(n_jobs, mb_w, mb_h), stream));
+			const int chunks = n_jobs * ((mb_w * mb_h + 31) / 32);
+			int ctas = (chunks + WAVE_WARPS - 1) / WAVE_WARPS;
+			if (ctas > 148 * 2) ctas = 148 * 2;      // persistent: every CTA resident (2 per SM)
+			h264_intra_sparse_kernel<<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+			if (launches) ++*launches;
+			B2_CUDA_OK(cudaGetLastError());
+			return 0;
+		}
+		B2_CUDA_OK(cudaMemsetAsync(area, 0, (32 + (size_t)n_jobs * mb_h) * sizeof(int), stream));
 		int ctas = n_jobs * ((mb_h + WAVE_WARPS - 1) / WAVE_WARPS);
 		int cap = 148 * 6;
 		if (ctas > cap) ctas = cap;
@@ -1576,10 +1636,11 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 	return 0;
 }
 
-int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool any_intra,
+int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool intra_dense, bool intra_sparse,
                 bool deblock, int *sync_area, uint64_t *launches) {
 	if (any_inter && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
-	if (any_intra && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
+	if (intra_dense && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
+	if (intra_sparse && launch_h264_phase(stream, 3, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (deblock && launch_h264_phase(stream, 2, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	return 0;
 }

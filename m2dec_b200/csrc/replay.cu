@@ -22,7 +22,7 @@ struct Step {
 	std::vector<H4Job> h4;       // one job per lane (of the group) that has a picture at this step
 	std::vector<M2Job> m2;
 	void *d_jobs = nullptr;
-	bool any_inter = false, any_intra = false, deblock = false;
+	bool any_inter = false, intra_dense = false, intra_sparse = false, deblock = false;
 };
 struct Group {
 	cudaStream_t stream = nullptr;
@@ -66,9 +66,10 @@ extern "C" int b2_replay_create(int cuda_device, int codec, int width, int heigh
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaMalloc(&r->frames, r->frame_bytes * pool_frames * lanes));
 	B2_CUDA_OK(cudaMemset(r->frames, 0, r->frame_bytes * pool_frames * lanes));
-	// default: one group.  Measured on B200 (64 and 128 lanes of 1080p, 3 pictures each): 2 / 4 / 8
-	// groups took 1.04x / 1.15x / 1.19x and 0.99x / 1.09x / 1.26x the time of one group -- the
-	// kernels are bound by their own synchronisation, not by the ramps.
+	// default: one group.  Measured on B200 (64 and 128 lanes of 1080p): 2 / 4 / 8 groups took
+	// 1.04x / 1.15x / 1.19x and 0.99x / 1.09x / 1.26x the time of one group, and no better with the
+	// wavefront kernels on high-priority streams: the inter kernel owns the whole register file of an
+	// SM while it runs, so the chains of different groups hardly overlap.
 	int ng = 1;
 	if (const char *e = getenv("B2_REPLAY_GROUPS")) ng = atoi(e);
 	if (ng < 1) ng = 1;
@@ -76,7 +77,7 @@ extern "C" int b2_replay_create(int cuda_device, int codec, int width, int heigh
 	r->groups.resize(ng);
 	for (Group &g : r->groups) {
 		B2_CUDA_OK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-		B2_CUDA_OK(cudaMalloc(&g.sync_area, h264_sync_bytes((lanes + ng - 1) / ng, height / 16)));
+		B2_CUDA_OK(cudaMalloc(&g.sync_area, h264_sync_bytes((lanes + ng - 1) / ng, width / 16, height / 16)));
 		B2_CUDA_OK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
 	}
 	B2_CUDA_OK(cudaEventCreate(&r->ev_begin));
@@ -145,14 +146,14 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	job.dbk = (const b2_h264_dbk *)(d + off[1]);
 	job.mcs = (const b2_h264_mc *)(d + off[2]);
 	job.coefs = (const int16_t *)(d + off[3]);
-	job.dst = p->dst; job.mb_w = p->mb_w; job.mb_h = p->mb_h;
+	job.dst = p->dst; job.mb_w = p->mb_w; job.mb_h = p->mb_h; job.n_intra = (int32_t)p->n_intra;
 	int t = r->lane_len[lane]++;
 	std::vector<Step> &steps = r->groups[lane % r->groups.size()].steps;
 	if ((int)steps.size() <= t) steps.resize(t + 1);
 	Step &s = steps[t];
 	s.h4.push_back(job);
 	s.any_inter |= p->n_intra < p->n_mbs;
-	s.any_intra |= p->n_intra > 0;
+	if (p->n_intra > 0) (h264_intra_sparse((int)p->n_intra, (int)p->n_mbs) ? s.intra_sparse : s.intra_dense) = true;
 	s.deblock |= p->deblock != 0;
 	// algorithmic bytes: S(1 + 2 dbk) + R + C + M, split by kernel
 	uint64_t n_inter = 0, c_inter = 0, c_intra = 0, rbytes = 0;
@@ -252,10 +253,12 @@ extern "C" int b2_replay_run(b2_replay *r, int timed) {
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 0], g.stream));
 			if (s.any_inter && launch_h264_phase(g.stream, 0, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 1], g.stream));
-			if (s.any_intra && launch_h264_phase(g.stream, 1, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
+			if (s.intra_dense && launch_h264_phase(g.stream, 1, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
+			if (s.intra_sparse && launch_h264_phase(g.stream, 3, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 2], g.stream));
 			if (s.deblock && launch_h264_phase(g.stream, 2, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 3], g.stream));
+
 		}
 	}
 	for (Group &g : r->groups) {

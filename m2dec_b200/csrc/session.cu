@@ -121,7 +121,7 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	for (int i = 0; i < nframes; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
 	if (cache_get(cuda_device, false, s->frame_bytes * nframes, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
 	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * nframes, s->stream));
-	if (cache_get(cuda_device, false, h264_sync_bytes(1, height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
+	if (cache_get(cuda_device, false, h264_sync_bytes(1, width / 16, height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
 	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming));
 	*out = s;
 	return 0;
@@ -245,6 +245,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	job.dst = p->dst;
 	job.mb_w = p->mb_w;
 	job.mb_h = p->mb_h;
+	job.n_intra = (int32_t)p->n_intra;
 	memcpy(sl->host, &job, sizeof(job));
 	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
 	memcpy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
@@ -252,7 +253,8 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (p->n_coef_recs) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
-	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs, p->n_intra > 0,
+	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs,
+	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
 	                p->deblock != 0, s->sync_area, &s->launches) < 0) return -1;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));

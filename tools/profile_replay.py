@@ -1,7 +1,9 @@
 """Short kernel-replay run for profiling (ncu): parse a few synthetic 1080p streams, make the SoA
-resident, run the replay a few times.  No e2e, no verification (tests/ and bench.py do that)."""
+resident, run the replay a few times.  No e2e, no verification (tests/ and bench.py do that).
+--codec mpeg2 runs BASELINE config 4 (MPEG-2 MP@HL 1920x1088 I/P/B) through mpeg2_recon_kernel."""
 import argparse
 import os
+import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,16 +12,31 @@ import bench  # noqa: E402
 import m2dec_b200  # noqa: E402
 
 ap = argparse.ArgumentParser()
+ap.add_argument("--codec", default="h264", choices=["h264", "mpeg2"])
 ap.add_argument("--lanes", type=int, default=16)
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--runs", type=int, default=2)
 a = ap.parse_args()
-rp = m2dec_b200.Replay("h264", bench.MBW * 16, bench.MBH * 16, a.lanes, pool_frames=18)
+
+
+def stream(seed):
+    if a.codec == "h264":
+        return bench.make_stream(seed, a.frames)
+    args = "mbw=%d mbh=%d frames=%d seed=%d bframes=2 gop=12 mv_range=64" % (bench.MBW, bench.MBH, a.frames, seed)
+    return subprocess.run([bench.STREAMGEN, "mpeg2", *args.split()], stdout=subprocess.PIPE, check=True).stdout
+
+
+rp = m2dec_b200.Replay(a.codec, bench.MBW * 16, bench.MBH * 16, a.lanes, pool_frames=18 if a.codec == "h264" else 4)
 for lane in range(a.lanes):
-    rp.load_stream(lane, bench.make_stream(100 + lane, a.frames))
+    n = rp.load_stream(lane, stream(100 + lane))
+    assert n == a.frames, (n, a.frames)
 for _ in range(a.runs):
     rp.run(timed=True)
     rp.sync()
 st = rp.stats()
-print("pictures", st.pictures, "launches", st.launches, "ms", [st.kernel_ms[i] for i in range(3)], st.total_ms)
+alg = [int(st.alg_bytes[i]) for i in range(3)]
+ms = [st.kernel_ms[i] for i in range(3)]
+print("pictures", st.pictures, "launches", st.launches, "ms", ms, st.total_ms)
+print("alg GB/s per kernel", [round(alg[i] / ms[i] / 1e6, 1) if ms[i] > 0 else None for i in range(3)],
+      "fps", round(st.pictures / st.total_ms * 1000.0, 1))
 rp.close()
