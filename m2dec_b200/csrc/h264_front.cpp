@@ -257,14 +257,25 @@ private:
 		int type = hdr & 31;
 		if (type != NAL_SLICE && type != NAL_IDR && type != NAL_SPS && type != NAL_PPS) return 0;
 		// strip emulation prevention bytes (7.4.1.1) and trailing zero bytes
-		rbsp_.clear();
-		rbsp_.reserve(len);
-		int zeros = 0;
-		for (size_t i = 1; i < len; ++i) {
-			uint8_t b = data[i];
-			if (zeros >= 2 && b == 3) { zeros = 0; continue; }
-			rbsp_.push_back(b);
-			zeros = b ? 0 : zeros + 1;
+		rbsp_.resize(len);
+		{
+			// copy runs between 00 00 03 sequences; a candidate needs a zero at every second byte
+			uint8_t *dst = rbsp_.data();
+			size_t i = 1, run = 1;
+			while (i + 2 < len) {
+				if (data[i + 1] != 0) { i += 2; continue; }
+				if (data[i] == 0 && data[i + 2] == 3) {
+					memcpy(dst, data + run, i + 2 - run);
+					dst += i + 2 - run;
+					i += 3;
+					run = i;
+				} else {
+					i += 1;
+				}
+			}
+			memcpy(dst, data + run, len - run);
+			dst += len - run;
+			rbsp_.resize((size_t)(dst - rbsp_.data()));
 		}
 		while (!rbsp_.empty() && rbsp_.back() == 0) rbsp_.pop_back();
 		br_.init(rbsp_.data(), rbsp_.size());
@@ -720,7 +731,8 @@ private:
 		// reference marking (8.2.5) and DPB insertion (h264.cpp:10840-10873, 11036-11045)
 		int max_fn = 1 << sps.log2_max_frame_num;
 		bool mmco5 = false;
-		if (h.nal_ref_idc) ctx_.store_col(col_[cur_frame_], [&](int f) { return f >= 0 ? (int)frames_[f].cnt : 0; });
+		// co-located motion for later direct prediction; Baseline streams have no B slices to use it
+		if (h.nal_ref_idc && sps.profile_idc != 66) ctx_.store_col(col_[cur_frame_], [&](int f) { return f >= 0 ? (int)frames_[f].cnt : 0; });
 		if (h.nal_ref_idc) {
 			if (h.idr) {
 				refs_.clear();

@@ -1268,34 +1268,42 @@ struct RowSync {
 
 struct DbkTables { uint8_t alpha[52], beta[52], tc0[52][4]; };
 
-__device__ __forceinline__ void dbk_filter(int *v, const int q, const int bs, const int alpha, const int beta, const int tc0, const bool luma) {
+// One edge of one line, without data-dependent branches for the common case (bS < 4): the filtered
+// values are computed for every lane and selected by the line's own conditions, so lanes that differ
+// in strength, thresholds or sample activity stay converged.  `on` = this lane filters this edge at all.
+__device__ __forceinline__ void dbk_filter(int *v, const int q, const bool on, const int bs, const int alpha, const int beta, const int tc0, const bool luma) {
 	const int p0 = v[q - 1], p1 = v[q - 2], p2 = v[q - 3], q0 = v[q], q1 = v[q + 1], q2 = v[q + 2];
-	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+	const bool act = on && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
 	const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
-	if (bs < 4) {
+	const bool normal = act && bs < 4;
+	{
 		const int tc = luma ? tc0 + ap + aq : tc0 + 1, avg = (p0 + q0 + 1) >> 1;
-		if (ap) v[q - 2] = p1 + min(max((p2 + avg - 2 * p1) >> 1, -tc0), tc0);
-		if (aq) v[q + 1] = q1 + min(max((q2 + avg - 2 * q1) >> 1, -tc0), tc0);
+		const int np1 = p1 + min(max((p2 + avg - 2 * p1) >> 1, -tc0), tc0);
+		const int nq1 = q1 + min(max((q2 + avg - 2 * q1) >> 1, -tc0), tc0);
 		const int delta = min(max(((q0 - p0) * 4 + (p1 - q1) + 4) >> 3, -tc), tc);
-		v[q - 1] = clip255(p0 + delta);
-		v[q] = clip255(q0 - delta);
-	} else {
-		const bool strong = luma && abs(p0 - q0) < (alpha >> 2) + 2;
-		if (strong && ap) {
-			const int p3 = v[q - 4];
-			v[q - 1] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
-			v[q - 2] = (p2 + p1 + p0 + q0 + 2) >> 2;
-			v[q - 3] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
-		} else {
-			v[q - 1] = (2 * p1 + p0 + q1 + 2) >> 2;
-		}
-		if (strong && aq) {
-			const int q3 = v[q + 3];
-			v[q] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
-			v[q + 1] = (p0 + q0 + q1 + q2 + 2) >> 2;
-			v[q + 2] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
-		} else {
-			v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
+		if (normal && ap) v[q - 2] = np1;
+		if (normal && aq) v[q + 1] = nq1;
+		if (normal) { v[q - 1] = clip255(p0 + delta); v[q] = clip255(q0 - delta); }
+	}
+	if (__any_sync(__activemask(), act && bs == 4)) {
+		if (act && bs == 4) {
+			const bool strong = luma && abs(p0 - q0) < (alpha >> 2) + 2;
+			if (strong && ap) {
+				const int p3 = v[q - 4];
+				v[q - 1] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+				v[q - 2] = (p2 + p1 + p0 + q0 + 2) >> 2;
+				v[q - 3] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+			} else {
+				v[q - 1] = (2 * p1 + p0 + q1 + 2) >> 2;
+			}
+			if (strong && aq) {
+				const int q3 = v[q + 3];
+				v[q] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+				v[q + 1] = (p0 + q0 + q1 + q2 + 2) >> 2;
+				v[q + 2] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+			} else {
+				v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
+			}
 		}
 	}
 }
@@ -1306,15 +1314,17 @@ __device__ __forceinline__ void dbk_line(int *v, const DbkTables &tb, uint32_t b
                                          int qpc, int qpn, int aoff, int boff) {
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		if (!luma && i >= 2) break;
 		const int e = luma ? i : 2 * i;                 // chroma edges 0 / 1 of the register layout are luma edges 0 / 2
-		int bs = (bits >> (8 * e + 2 * seg)) & 3;
-		if (!bs || (e == 0 && !edge0_ok)) continue;
+		// whole edge without strength for every lane (common for inner edges): skip it, warp-uniformly
+		const uint32_t ebits = e < 4 ? (bits >> (8 * e)) & 255u : 0u;
+		int bs = (ebits >> (2 * seg)) & 3;
+		bool on = bs != 0 && !(e == 0 && !edge0_ok) && (luma || i < 2);
+		if (!__any_sync(__activemask(), on)) continue;
 		if (e == 0 && edge0_bs4) bs = 4;
 		const int qp = e ? qpc : (qpc + qpn + 1) >> 1;
 		const int ia = min(max(qp + aoff, 0), 51), ib = min(max(qp + boff, 0), 51);
 		const int alpha = tb.alpha[ia];
-		if (alpha) dbk_filter(v, 4 + 4 * i, bs, alpha, tb.beta[ib], bs < 4 ? tb.tc0[ia][bs - 1] : 0, luma);
+		dbk_filter(v, 4 + 4 * i, on && alpha != 0, bs, alpha, tb.beta[ib], tb.tc0[ia][bs < 4 ? (bs ? bs - 1 : 0) : 3], luma);
 	}
 }
 

@@ -1,6 +1,7 @@
 """Kernel replay (include/b2_recon.h, b2_replay_*): parse streams once on the host, keep every
 picture's SoA resident in HBM, then reconstruct picture #t of all lanes per batched launch."""
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -18,6 +19,7 @@ class Replay:
         if L.lib.b2_replay_create(cuda_device, CODEC_ID[codec], width, height, lanes, pool_frames, C.byref(h)) < 0:
             raise RuntimeError("b2_replay_create failed: %s" % (L.lib.b2_last_error() or b"").decode())
         self.h = h
+        self._lock = threading.Lock()      # b2_replay_add_* is not re-entrant; parses may run on many threads
         self.outputs = [[] for _ in range(lanes)]     # per lane: output-order list of frame-pool indices... filled by load_stream
 
     def close(self):
@@ -34,7 +36,9 @@ class Replay:
         add = L.lib.b2_replay_add_h264 if self.codec == MODE_H264 else L.lib.b2_replay_add_mpeg2
 
         def tap(dec, codec, pic):
-            if add(self.h, lane, pic) < 0:
+            with self._lock:
+                rc = add(self.h, lane, pic)
+            if rc < 0:
                 raise RuntimeError("b2_replay_add failed: %s" % (L.lib.b2_last_error() or b"").decode())
             dsts.append(C.cast(pic, C.POINTER(C.c_int32))[dst_field])
             n[0] += 1
