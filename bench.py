@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lanes", type=int, default=128, help="independent 1080p streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
+    ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
     ap.add_argument("--e2e-streams", type=int, default=16)
     ap.add_argument("--e2e-reps", type=int, default=5, help="timed repetitions of the end-to-end pool run")
     ap.add_argument("--verify-lanes", type=int, default=8, help="lanes whose every frame is MD5-checked against the reference")
@@ -197,9 +198,13 @@ def main():
         n = rp.load_stream(lane, streams[lane])
         assert n == a.frames, (n, a.frames)
 
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max(1, min(ncores, 16))) as pool:
-        list(pool.map(prepare, range(a.lanes)))
+    if a.prep_threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max(1, min(ncores, a.prep_threads))) as pool:
+            list(pool.map(prepare, range(a.lanes)))
+    else:
+        for lane in range(a.lanes):
+            prepare(lane)
     t_prep = time.perf_counter() - t_prep
 
     # ---- parity (untimed): every frame of the first lanes against the compiled reference -----
