@@ -173,6 +173,11 @@ def main():
         }))
         return 0
 
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL's version
+    # banner, for one) is sent to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import m2dec_b200
@@ -383,7 +388,8 @@ def main():
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0
