@@ -205,7 +205,7 @@ def main():
 
     if a.prep_threads > 1:
         from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max(1, min(ncores, a.prep_threads))) as pool:
+        with ThreadPoolExecutor(max(1, min(ncores // world, a.prep_threads))) as pool:
             list(pool.map(prepare, range(a.lanes)))
     else:
         for lane in range(a.lanes):
@@ -268,7 +268,7 @@ def main():
 
     # ---- end to end through the plugin table with host buffers --------------------------------
     ne = min(a.e2e_streams, a.lanes)
-    threads_n = max(1, min(ne, ncores))
+    threads_n = max(1, min(ne, ncores // world))     # the ranks of a node share its host cores
     counts = [None] * ne
     frames_out = [0] * ne
 
