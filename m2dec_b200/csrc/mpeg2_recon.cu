@@ -119,6 +119,39 @@ __device__ __forceinline__ int fetch_hp(const uint8_t *__restrict__ plane, int s
 	return (a + b + c + d + 2) >> 2;
 }
 
+// Four horizontally adjacent half-pel samples as one packed word.  Fast path: the row segment is read
+// with aligned 32-bit loads and funnel shifts, the averages are done on packed bytes (`__vavgu4` is
+// exactly AVERAGE2, (a + b + 1) >> 1) or, for the 2x2 case, in two sets of 16-bit lanes.  Positions
+// whose words would leave the plane take the clamped byte path.
+__device__ __forceinline__ uint32_t fetch_hp4(const uint8_t *__restrict__ plane, int stride, int rows,
+                                              int x, int y, int hx, int hy, int xstep, int ystep) {
+	const int y1 = y + (hy ? ystep : 0);
+	const bool fast = x >= 0 && (x & ~3) + 12 <= stride && y >= 0 && y1 < rows;
+	if (!fast) {
+		uint32_t w = 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) w |= (uint32_t)fetch_hp(plane, stride, rows, x + i, y, hx, hy, xstep, ystep) << (8 * i);
+		return w;
+	}
+	const uint8_t *p0 = plane + (size_t)y * stride + x;
+	const uint32_t *a0 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)3);
+	const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p0) & 3) * 8;
+	const unsigned nsh = 8u * (unsigned)xstep;            // horizontal neighbour: 1 byte (luma) or 2 (NV12 chroma)
+	uint32_t w0 = __ldg(a0), w1 = __ldg(a0 + 1), w2 = __ldg(a0 + 2);
+	const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+	const uint32_t a = lo, b = __funnelshift_r(lo, hi, nsh);
+	if (!hy) return hx ? __vavgu4(a, b) : a;
+	const uint32_t *a1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(a0) + (size_t)ystep * stride);
+	w0 = __ldg(a1); w1 = __ldg(a1 + 1); w2 = __ldg(a1 + 2);
+	const uint32_t lo1 = __funnelshift_r(w0, w1, sh), hi1 = __funnelshift_r(w1, w2, sh);
+	const uint32_t c = lo1, d = __funnelshift_r(lo1, hi1, nsh);
+	if (!hx) return __vavgu4(a, c);
+	const uint32_t m = 0x00FF00FFu;
+	const uint32_t e = (a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u;
+	const uint32_t o = ((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u;
+	return ((e >> 2) & m) | (((o >> 2) & m) << 8);
+}
+
 __global__ void __launch_bounds__(MBS * TPM)
 mpeg2_recon_kernel(const M2Job *__restrict__ jobs) {
 	__shared__ __align__(16) int16_t s_tmp[MBS][6][64];
@@ -170,7 +203,7 @@ mpeg2_recon_kernel(const M2Job *__restrict__ jobs) {
 	if (intra) {
 		px[0] = px[1] = px[2] = px[3] = 0;
 	} else {
-		int acc[4] = {0, 0, 0, 0};
+		uint32_t acc = 0;
 		int ndir = 0;
 #pragma unroll
 		for (int dir = 0; dir < 2; ++dir) {
@@ -193,16 +226,13 @@ mpeg2_recon_kernel(const M2Job *__restrict__ jobs) {
 				sy = mb_row0 + row + (mvy >> 1);
 				ystep = 1;
 			}
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				// NV12: bytes alternate Cb/Cr, so byte i's horizontal neighbour is 2 bytes away
-				int v = fetch_hp(ref, W, rows_plane, sx + i, sy, hx, hy, xstep, ystep);
-				acc[i] = ndir ? ((acc[i] + v + 1) >> 1) : v;
-			}
+			// NV12: bytes alternate Cb/Cr, so a byte's horizontal neighbour is 2 bytes away
+			const uint32_t v = fetch_hp4(ref, W, rows_plane, sx, sy, hx, hy, xstep, ystep);
+			acc = ndir ? __vavgu4(acc, v) : v;
 			ndir++;
 		}
 #pragma unroll
-		for (int i = 0; i < 4; ++i) px[i] = acc[i];
+		for (int i = 0; i < 4; ++i) px[i] = (acc >> (8 * i)) & 255;
 	}
 
 	// residual
