@@ -14,6 +14,7 @@
 // 4309-4404; intra predictors 2510-2997, 3315-3929 (8x8), 4224-4304, 4561-4705; I_PCM 4736-4761; luma MC 5381-6406 (UMV
 // 5932-6116); chroma MC 4859-5330; deblock 10253-10663 with tables h264vld.h:4536-4627.
 // HBM-bound integer/byte work: no tensor cores.
+#include <stdlib.h>
 #include "device_common.cuh"
 
 namespace b2 {
@@ -653,6 +654,209 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 			uint32_t w = (uint32_t)cb0 | ((uint32_t)cr0 << 8) | ((uint32_t)cb1 << 16) | ((uint32_t)cr1 << 24);
 			*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + y4 * 2 + r) * W + mbx * 16 + x4 * 4) = w;
 		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// inter kernel, strip form.  Work item = a vertical strip of one motion-compensation record: 8 (or 4)
+// luma samples wide, the full height of the partition (4..16 rows), plus its chroma.  The strip is
+// produced row by row, so reference rows, filter state and code are shared by all rows of the strip
+// instead of being set up again for every 4x4 block; the residual of the blocks the strip crosses is
+// transformed by the same thread into a private shared-memory scratch, so there is no separate
+// residual phase and only the sort needs block-wide barriers.
+// ------------------------------------------------------------------------------------------------
+constexpr int I5_MBS = 64;
+constexpr int I5_THREADS = 256;
+constexpr int I5_CLASSES = 12;        // interpolation class (0..5) + 6 * (strip is 8 wide)
+
+// item: bits 0..5 MB slot, 6..9 record, 10..11 x (4-sample units inside the MB), 12..13 y, 14..16 height
+// (4-sample units), 17 wide, 18..21 class
+__device__ __forceinline__ uint32_t i5_pack(int slot, int rec, int x4, int y4, int h4, int wide, int cls) {
+	return (uint32_t)slot | ((uint32_t)rec << 6) | ((uint32_t)x4 << 10) | ((uint32_t)y4 << 12) | ((uint32_t)h4 << 14) | ((uint32_t)wide << 17) | ((uint32_t)cls << 18);
+}
+
+__device__ __forceinline__ int frac_class(int fx, int fy) {
+	if (!fx && !fy) return 0;
+	if (!fy) return 1;
+	if (!fx) return 2;
+	if (fx == 2) return 4;          // b / s with j, or j alone
+	if (fy == 2) return 5;          // h / m with j
+	return 3;                       // b / s with h / m
+}
+
+// One strip.  rs = this thread's residual scratch (64 + 2 int16).
+__device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc &mc, int mbx, int mby, int x4, int y4, int h4, bool wide,
+                         int16_t *rs) {
+	const int W = job.mb_w * 16, H = job.mb_h * 16;
+	const size_t luma_size = (size_t)W * H;
+	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
+	uint8_t *dst_c = dst_y + luma_size;
+	const int nq = wide ? 2 : 1;                       // words (4 samples) per luma row of the strip
+	const int px0 = mbx * 16 + x4 * 4, py0 = mby * 16 + y4 * 4, h = h4 * 4;
+	const bool bi = mc.ref_frame[0] >= 0 && mc.ref_frame[1] >= 0;
+	const int first = mc.ref_frame[0] >= 0 ? 0 : 1;
+	const bool t8 = m.flags & B2_H4_T8x8;
+	const bool weighted = !bi && (mc.log2wd_y | mc.log2wd_c | (mc.w[first][0] ^ 1) | (mc.w[first][1] ^ 1) | (mc.w[first][2] ^ 1) | mc.o[first][0] | mc.o[first][1] | mc.o[first][2]);
+
+	// ---- luma ---------------------------------------------------------------------------------------
+	int pass = 0;
+	for (int l = 0; l < 2; ++l) {
+		if (mc.ref_frame[l] < 0) continue;
+		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[l];
+		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1], fx = mvx & 3, fy = mvy & 3;
+		const int rx = px0 + (mvx >> 2), ry = py0 + (mvy >> 2);
+		const bool last = !bi || pass == 1;
+		uint32_t coded = 0;                              // which of the strip's blocks of this row group have a residual
+		for (int r = 0; r < h; ++r) {
+			if (last) {
+				// residual of the blocks this row group crosses
+				if (t8) {
+					if ((r & 7) == 0) {
+						const int q8 = ((y4 + (r >> 2)) >> 1) * 2 + (x4 >> 1);
+						coded = (m.nz >> (1 + 4 * q8)) & 1 ? 0xfu : 0u;
+						if (coded) block_residual8x8(job, m, q8, reinterpret_cast<int16_t(*)[16]>(rs) - 4 * q8);
+					}
+				} else if ((r & 3) == 0) {
+					coded = 0;
+					for (int q = 0; q < nq; ++q) {
+						const int b = c_r2b[(y4 + (r >> 2)) * 4 + x4 + q];
+						if (((m.nz >> (1 + b)) & 1) && block_residual(job, m, b, rs + q * 16)) coded |= 1u << q;
+					}
+				}
+			}
+			uint8_t *drow = dst_y + (size_t)(py0 + r) * W + px0;
+			for (int q = 0; q < nq; ++q) {
+				int p[4];
+				luma_quad(ref, W, H, rx + 4 * q, ry + r, fx, fy, p);
+				if (!last) {
+					*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+					continue;
+				}
+				if (bi) {
+					const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
+					const int lw = mc.log2wd_y, o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
+#pragma unroll
+					for (int i = 0; i < 4; ++i) p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][0] + p[i] * mc.w[1][0] + (1 << lw)) >> (lw + 1)) + o);
+				} else if (weighted) {
+					const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
+#pragma unroll
+					for (int i = 0; i < 4; ++i) p[i] = clip255(((p[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
+				}
+				// block of this word inside the scratch: 4x4 path block q; 8x8 path sub-block (row half, q)
+				const int sb = t8 ? ((r >> 2) & 1) * 2 + q : q;
+				if ((coded >> sb) & 1) {
+					const int16_t *res = rs + sb * 16 + (r & 3) * 4;
+#pragma unroll
+					for (int i = 0; i < 4; ++i) p[i] = clip255(p[i] + res[i]);
+				}
+				*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+			}
+		}
+		++pass;
+	}
+	// ---- chroma: nq words (Cb Cr Cb Cr) per row, h / 2 rows -----------------------------------------------
+	pass = 0;
+	for (int l = 0; l < 2; ++l) {
+		if (mc.ref_frame[l] < 0) continue;
+		const uint8_t *refc = job.frames + job.frame_bytes * mc.ref_frame[l] + luma_size;
+		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1];
+		const bool last = !bi || pass == 1;
+		uint32_t coded = 0;
+		const int cy0 = y4 * 2, cx0 = x4 * 2;            // chroma sample position inside the MB
+		for (int r = 0; r < h / 2; ++r) {
+			const int cy = cy0 + r;
+			if (last && (r == 0 || (cy & 3) == 0)) {
+				const int cblk = (cy >> 2) * 2 + (cx0 >> 2);
+				coded = 0;
+				for (int comp = 0; comp < 2; ++comp)
+					if (block_residual(job, m, 16 + comp * 4 + cblk, rs + comp * 16)) coded |= 1u << comp;
+			}
+			uint8_t *drow = dst_c + (size_t)(mby * 8 + cy) * W + px0;
+			for (int q = 0; q < nq; ++q) {
+				int p[4];
+				chroma_quad(refc, W, H >> 1, px0 + 4 * q, mby * 8 + cy, mvx, mvy, p);
+				if (!last) {
+					*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+					continue;
+				}
+				if (bi) {
+					const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
+					const int lc = mc.log2wd_c;
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						const int c = 1 + (i & 1);
+						p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][c] + p[i] * mc.w[1][c] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][c] + mc.o[1][c] + 1) >> 1));
+					}
+				} else if (weighted) {
+					const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						const int c = 1 + (i & 1);
+						p[i] = clip255(((p[i] * mc.w[first][c] + rc) >> lc) + mc.o[first][c]);
+					}
+				}
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int comp = i & 1, cx = cx0 + 2 * q + (i >> 1);
+					if ((coded >> comp) & 1) p[i] = clip255(p[i] + rs[comp * 16 + (cy & 3) * 4 + (cx & 3)]);
+				}
+				*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+			}
+		}
+		++pass;
+	}
+}
+
+__global__ void __launch_bounds__(I5_THREADS, 2)
+h264_inter5_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
+	__shared__ uint32_t s_items[I5_MBS * 16];
+	__shared__ int s_cnt[I5_CLASSES + 1];
+	__shared__ int s_pos[I5_CLASSES];
+	__shared__ __align__(4) int16_t s_rs[I5_THREADS][66];
+	const H4Job job = jobs[blockIdx.y];
+	const int tid = threadIdx.x;
+	const int mb0 = blockIdx.x * I5_MBS;
+	if (tid <= I5_CLASSES) s_cnt[tid] = 0;
+	__syncthreads();
+	// two passes over the (macroblock, record) pairs: count the strips per class, then place them
+	for (int place = 0; place < 2; ++place) {
+		for (int e = tid; e < I5_MBS * 16; e += I5_THREADS) {
+			const int slot = e >> 4, ri = e & 15, mb = mb0 + slot;
+			if (mb >= n_mbs) continue;
+			const b2_h264_mb *mp = job.mbs + mb;
+			if (mp->type != B2_H4_INTER || ri >= mp->mc_cnt) continue;
+			const int4 raw = __ldg(reinterpret_cast<const int4 *>(job.mcs + mp->mc_idx + ri));
+			const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);      // first 16 bytes: pos .. mv
+			const int l = mc.ref_frame[0] >= 0 ? 0 : 1;
+			const int w4 = mc.size & 15, h4 = mc.size >> 4, x4 = mc.pos & 3, y4 = mc.pos >> 2;
+			const int wide = w4 >= 2;
+			const int cls = frac_class(mc.mv[l][0] & 3, mc.mv[l][1] & 3) + 6 * wide;
+			const int n = wide ? w4 >> 1 : 1;
+			if (!place) { atomicAdd(&s_cnt[cls], n); continue; }
+			const int at = atomicAdd(&s_pos[cls], n);
+			for (int k = 0; k < n; ++k) s_items[at + k] = i5_pack(slot, ri, x4 + 2 * k, y4, h4, wide, cls);
+		}
+		__syncthreads();
+		if (!place) {
+			if (tid == 0) {
+				int acc = 0;
+				for (int c = 0; c < I5_CLASSES; ++c) { s_pos[c] = acc; acc += s_cnt[c]; }
+				s_cnt[I5_CLASSES] = acc;
+			}
+			__syncthreads();
+		}
+	}
+	const int total = s_cnt[I5_CLASSES];
+	for (int it = tid; it < total; it += I5_THREADS) {
+		const uint32_t item = s_items[it];
+		const int slot = item & 63, ri = (item >> 6) & 15;
+		const int mb = mb0 + slot;
+		const b2_h264_mb m = job.mbs[mb];
+		const b2_h264_mc *mcp = job.mcs + m.mc_idx + ri;
+		b2_h264_mc mc;
+		reinterpret_cast<int4 *>(&mc)[0] = __ldg(reinterpret_cast<const int4 *>(mcp));
+		reinterpret_cast<int4 *>(&mc)[1] = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
+		i5_strip(job, m, mc, mb % job.mb_w, mb / job.mb_w, (item >> 10) & 3, (item >> 12) & 3, (item >> 14) & 7, (item >> 17) & 1, s_rs[tid]);
 	}
 }
 
@@ -1619,8 +1823,14 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 	if (n_jobs <= 0) return 0;
 	if (phase == 0) {
 		const int n_mbs = mb_w * mb_h;
-		dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
-		h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
+		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 0;
+		if (use5) {
+			dim3 grid5((n_mbs + I5_MBS - 1) / I5_MBS, n_jobs);
+			h264_inter5_kernel<<<grid5, I5_THREADS, 0, stream>>>(d_jobs, n_mbs);
+		} else {
+			dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
+			h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
+		}
 		if (launches) ++*launches;
 	} else {
 		int *area = sync_area;
