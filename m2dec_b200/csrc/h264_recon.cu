@@ -684,32 +684,268 @@ __device__ __forceinline__ int frac_class(int fx, int fy) {
 	return 3;                       // b / s with h / m
 }
 
-// One strip.  rs = this thread's residual scratch (64 + 2 int16).
-__device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc &mc, int mbx, int mby, int x4, int y4, int h4, bool wide,
-                         int16_t *rs) {
+// ---- reference rows as packed words -------------------------------------------------------------------
+__device__ __noinline__ uint4 load_words_clamped(const uint8_t *__restrict__ row, int W, int x, int nwords) {
+	uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int i = 0; i < 16; ++i)
+		if (i < nwords * 4) out[i >> 2] |= (uint32_t)__ldg(row + min(max(x + i, 0), W - 1)) << ((i & 3) * 8);
+	return make_uint4(out[0], out[1], out[2], out[3]);
+}
+// NV12 chroma row: clamping is per sample pair, bytes keep their component (x is even)
+__device__ __noinline__ uint4 load_chroma_clamped(const uint8_t *__restrict__ row, int W, int x, int nwords) {
+	uint32_t out[4] = {0, 0, 0, 0};
+	const int cw = W >> 1;
+#pragma unroll
+	for (int i = 0; i < 16; ++i)
+		if (i < nwords * 4) out[i >> 2] |= (uint32_t)__ldg(row + min(max((x >> 1) + (i >> 1), 0), cw - 1) * 2 + (i & 1)) << ((i & 3) * 8);
+	return make_uint4(out[0], out[1], out[2], out[3]);
+}
+// N words (N <= 4) of bytes x .. x + 4N - 1 of a row.  fast: x >= 0 and every aligned word touched is inside the row
+template <int N, bool CHROMA>
+__device__ __forceinline__ void load_words(const uint8_t *__restrict__ row, int W, int x, bool fast, uint32_t *out) {
+	if (fast) {
+		const uint8_t *p = row + x;
+		const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+		const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+		uint32_t w[N + 1];
+#pragma unroll
+		for (int k = 0; k <= N; ++k) w[k] = __ldg(a + k);
+#pragma unroll
+		for (int k = 0; k < N; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
+	} else {
+		const uint4 v = CHROMA ? load_chroma_clamped(row, W, x, N) : load_words_clamped(row, W, x, N);
+		out[0] = v.x;
+		if (N > 1) out[1] = v.y;
+		if (N > 2) out[2] = v.z;
+		if (N > 3) out[3] = v.w;
+	}
+}
+__device__ __forceinline__ bool words_fast(int x, int n, int W) { return x >= 0 && (x & ~3) + 4 * (n + 1) <= W; }
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {
+	int d;
+	asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+// four clipped horizontal half samples b = clip((b1 + 16) >> 5) of window words pk[0..2], packed
+__device__ __forceinline__ uint32_t hhalf4(const uint32_t pk[3]) {
+	int hb[4];
+	hfilter4(pk, hb);
+	return pack4(clip255((hb[0] + 16) >> 5), clip255((hb[1] + 16) >> 5), clip255((hb[2] + 16) >> 5), clip255((hb[3] + 16) >> 5));
+}
+// four clipped vertical half samples from six rows split into even / odd byte lanes, packed
+__device__ __forceinline__ uint32_t vhalf4(const uint32_t E[6], const uint32_t O[6]) {
+	const uint32_t te = vtap_packed(E[0], E[1], E[2], E[3], E[4], E[5]), to = vtap_packed(O[0], O[1], O[2], O[3], O[4], O[5]);
+	return pack4(vfinish(te & 0xFFFFu), vfinish(to & 0xFFFFu), vfinish(te >> 16), vfinish(to >> 16));
+}
+
+// Luma prediction of a strip NQ words wide and h rows high at integer position (x, y) + fraction (fx, fy),
+// produced row by row: sink(r, words) is called for r = 0 .. h - 1 in order.  Classes 4 and 5 (the centre
+// sample j) exist for NQ == 1 only: their filter state would not fit the registers at 8 samples.
+template <int NQ, class Sink>
+__device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int h, Sink &&sink) {
+	const int cls = frac_class(fx, fy);
+	const uint32_t M = 0x00FF00FFu;
+#define ROWP(yy) (ref + (size_t)min(max((yy), 0), H - 1) * W)
+	if (cls == 0) {
+		const bool fast = words_fast(x, NQ, W);
+		for (int r = 0; r < h; ++r) {
+			uint32_t pw[NQ];
+			load_words<NQ, false>(ROWP(y + r), W, x, fast, pw);
+			sink(r, pw);
+		}
+	} else if (cls == 1) {
+		const bool fast = words_fast(x - 2, NQ + 2, W);
+		for (int r = 0; r < h; ++r) {
+			uint32_t w[NQ + 2], pw[NQ];
+			load_words<NQ + 2, false>(ROWP(y + r), W, x - 2, fast, w);
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) {
+				uint32_t b = hhalf4(&w[q]);
+				if (fx != 2) b = __vavgu4(__funnelshift_r(w[q], w[q + 1], fx == 1 ? 16 : 24), b);
+				pw[q] = b;
+			}
+			sink(r, pw);
+		}
+	} else if (cls == 2) {
+		const bool fast = words_fast(x, NQ, W);
+		uint32_t E[NQ][6], O[NQ][6];
+#pragma unroll
+		for (int q = 0; q < NQ; ++q)
+#pragma unroll
+			for (int j = 0; j < 6; ++j) E[q][j] = O[q][j] = 0;
+		for (int k = 0; k < h + 5; ++k) {
+			uint32_t w[NQ], pw[NQ];
+			load_words<NQ, false>(ROWP(y - 2 + k), W, x, fast, w);
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+				for (int j = 0; j < 5; ++j) { E[q][j] = E[q][j + 1]; O[q][j] = O[q][j + 1]; }
+				E[q][5] = w[q] & M;
+				O[q][5] = (w[q] >> 8) & M;
+			}
+			if (k < 5) continue;
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) {
+				uint32_t hw = vhalf4(E[q], O[q]);
+				if (fy != 2) hw = __vavgu4(fy == 1 ? (E[q][2] | (O[q][2] << 8)) : (E[q][3] | (O[q][3] << 8)), hw);
+				pw[q] = hw;
+			}
+			sink(k - 5, pw);
+		}
+	} else if (cls == 3) {
+		const bool fast = words_fast(x - 2, NQ + 2, W);
+		const bool xo = fx == 3, yo = fy == 3;
+		uint32_t E[NQ][6], O[NQ][6], bq[NQ][4];
+#pragma unroll
+		for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+			for (int j = 0; j < 6; ++j) E[q][j] = O[q][j] = 0;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) bq[q][j] = 0;
+		}
+		for (int k = 0; k < h + 5; ++k) {
+			uint32_t w[NQ + 2], pw[NQ];
+			load_words<NQ + 2, false>(ROWP(y - 2 + k), W, x - 2, fast, w);
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+				for (int j = 0; j < 5; ++j) { E[q][j] = E[q][j + 1]; O[q][j] = O[q][j + 1]; }
+#pragma unroll
+				for (int j = 0; j < 3; ++j) bq[q][j] = bq[q][j + 1];
+				const uint32_t vr = __funnelshift_r(w[q], w[q + 1], xo ? 24 : 16);      // samples at x + xo
+				E[q][5] = vr & M;
+				O[q][5] = (vr >> 8) & M;
+				bq[q][3] = hhalf4(&w[q]);                                            // b of this row
+			}
+			if (k < 5) continue;
+			// output row r = k - 5: vertical half sample over rows r .. r + 5, b of row r + 2 + yo = k - 3 + yo
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) pw[q] = __vavgu4(yo ? bq[q][1] : bq[q][0], vhalf4(E[q], O[q]));
+			sink(k - 5, pw);
+		}
+	} else if (NQ == 1) {
+		// centre sample j from unrounded horizontal intermediates (biased to unsigned 16 bit, two vertically
+		// adjacent rows per register) with dp2a down the column; cls 4: alone or averaged with b / s,
+		// cls 5: averaged with the vertical half sample h / m
+		const bool fast = words_fast(x - 2, 3, W);
+		const bool xo = fx == 3, yo = fy == 3, with_b = cls == 4 && fy != 2, with_h = cls == 5;
+		uint32_t PW[5][4], prevb[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0}, E[6], O[6];
+#pragma unroll
+		for (int j = 0; j < 5; ++j)
+#pragma unroll
+			for (int c = 0; c < 4; ++c) PW[j][c] = 0;
+#pragma unroll
+		for (int j = 0; j < 6; ++j) E[j] = O[j] = 0;
+		const uint32_t T0 = (1u & 255u) | ((uint32_t)(-5 & 255) << 8), T1 = 20u | (20u << 8), T2 = (uint32_t)(-5 & 255) | (1u << 8);
+		for (int k = 0; k < h + 5; ++k) {
+			uint32_t w[3];
+			load_words<3, false>(ROWP(y - 2 + k), W, x - 2, fast, w);
+			int hb[4];
+			hfilter4(w, hb);
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+#pragma unroll
+				for (int c = 0; c < 4; ++c) PW[j][c] = PW[j + 1][c];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const uint32_t cur = (uint32_t)(hb[c] + 2560);
+				PW[4][c] = prevb[c] | (cur << 16);
+				prevb[c] = cur;
+			}
+			if (with_b) {
+#pragma unroll
+				for (int j = 0; j < 3; ++j) bq[j] = bq[j + 1];
+				bq[3] = pack4(clip255((hb[0] + 16) >> 5), clip255((hb[1] + 16) >> 5), clip255((hb[2] + 16) >> 5), clip255((hb[3] + 16) >> 5));
+			}
+			if (with_h) {
+#pragma unroll
+				for (int j = 0; j < 5; ++j) { E[j] = E[j + 1]; O[j] = O[j + 1]; }
+				const uint32_t vr = __funnelshift_r(w[0], w[1], xo ? 24 : 16);
+				E[5] = vr & M;
+				O[5] = (vr >> 8) & M;
+			}
+			if (k < 5) continue;
+			int jv[4];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const int j1 = dp2a_lo_us(PW[0][c], T0, dp2a_lo_us(PW[2][c], T1, dp2a_lo_us(PW[4][c], T2, -32 * 2560)));
+				jv[c] = clip255((j1 + 512) >> 10);
+			}
+			uint32_t pw = pack4(jv[0], jv[1], jv[2], jv[3]);
+			if (with_b) pw = __vavgu4(yo ? bq[1] : bq[0], pw);
+			if (with_h) pw = __vavgu4(vhalf4(E, O), pw);
+			sink(k - 5, &pw);
+		}
+	}
+#undef ROWP
+}
+
+// Chroma prediction (eighth-sample bilinear, 16-bit lanes): NQ words (Cb Cr Cb Cr) per row, `rows` rows, at
+// byte column xb (even) / chroma row cy of the picture
+template <int NQ, class Sink>
+__device__ __forceinline__ void i5_chroma(const uint8_t *__restrict__ refc, int W, int CH, int xb, int cy, int mvx, int mvy, int rows, Sink &&sink) {
+	const uint32_t M = 0x00FF00FFu;
+	const uint32_t cfx = mvx & 7, cfy = mvy & 7;
+	const int x = xb + (mvx >> 3) * 2, y = cy + (mvy >> 3);
+	const bool fast = words_fast(x, NQ + 1, W);
+	uint32_t pcb[NQ], pcr[NQ];
+#pragma unroll
+	for (int q = 0; q < NQ; ++q) pcb[q] = pcr[q] = 0;
+	for (int k = 0; k <= rows; ++k) {
+		uint32_t w[NQ + 1], pw[NQ];
+		load_words<NQ + 1, true>(refc + (size_t)min(max(y + k, 0), CH - 1) * W, W, x, fast, w);
+#pragma unroll
+		for (int q = 0; q < NQ; ++q) {
+			const uint32_t a = w[q], b = __funnelshift_r(w[q], w[q + 1], 16);
+			const uint32_t hcb = (8u - cfx) * (a & M) + cfx * (b & M), hcr = (8u - cfx) * ((a >> 8) & M) + cfx * ((b >> 8) & M);
+			const uint32_t vcb = ((8u - cfy) * pcb[q] + cfy * hcb + 0x00200020u) >> 6, vcr = ((8u - cfy) * pcr[q] + cfy * hcr + 0x00200020u) >> 6;
+			pw[q] = (vcb & M) | ((vcr & M) << 8);
+			pcb[q] = hcb;
+			pcr[q] = hcr;
+		}
+		if (k) sink(k - 1, pw);
+	}
+}
+
+// One strip.  rs = this thread's residual scratch (64 + 2 int16); rows = this thread's column of the
+// row buffer (word k at rows[k * I5_THREADS]): the class-specific predictors only park their rows there,
+// and one finishing loop per plane adds weights and residual, so that code exists once.
+template <int NQ>
+__device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc &mc, int mbx, int mby, int x4, int y4, int h4, int16_t *rs,
+                         uint32_t *rows) {
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
 	const size_t luma_size = (size_t)W * H;
 	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
 	uint8_t *dst_c = dst_y + luma_size;
-	const int nq = wide ? 2 : 1;                       // words (4 samples) per luma row of the strip
 	const int px0 = mbx * 16 + x4 * 4, py0 = mby * 16 + y4 * 4, h = h4 * 4;
 	const bool bi = mc.ref_frame[0] >= 0 && mc.ref_frame[1] >= 0;
 	const int first = mc.ref_frame[0] >= 0 ? 0 : 1;
 	const bool t8 = m.flags & B2_H4_T8x8;
-	const bool weighted = !bi && (mc.log2wd_y | mc.log2wd_c | (mc.w[first][0] ^ 1) | (mc.w[first][1] ^ 1) | (mc.w[first][2] ^ 1) | mc.o[first][0] | mc.o[first][1] | mc.o[first][2]);
-
-	// ---- luma ---------------------------------------------------------------------------------------
+	const bool plain_w = !(mc.log2wd_y | mc.log2wd_c | (mc.w[0][0] ^ 1) | (mc.w[0][1] ^ 1) | (mc.w[0][2] ^ 1) | (mc.w[1][0] ^ 1) | (mc.w[1][1] ^ 1) | (mc.w[1][2] ^ 1) |
+	                       mc.o[0][0] | mc.o[0][1] | mc.o[0][2] | mc.o[1][0] | mc.o[1][1] | mc.o[1][2]);      // default prediction for whatever lists are used
+	auto park = [&](int r, const uint32_t *pw) {
+#pragma unroll
+		for (int q = 0; q < NQ; ++q) rows[(r * NQ + q) * I5_THREADS] = pw[q];
+	};
 	int pass = 0;
 	for (int l = 0; l < 2; ++l) {
 		if (mc.ref_frame[l] < 0) continue;
 		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[l];
-		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1], fx = mvx & 3, fy = mvy & 3;
-		const int rx = px0 + (mvx >> 2), ry = py0 + (mvy >> 2);
+		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1];
 		const bool last = !bi || pass == 1;
-		uint32_t coded = 0;                              // which of the strip's blocks of this row group have a residual
-		for (int r = 0; r < h; ++r) {
-			if (last) {
-				// residual of the blocks this row group crosses
+		// ---- luma -------------------------------------------------------------------------------------
+		i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, park);
+		{
+			uint32_t coded = 0;                          // which of the strip's blocks of this row group have a residual
+			for (int r = 0; r < h; ++r) {
+				uint8_t *drow = dst_y + (size_t)(py0 + r) * W + px0;
+				if (!last) {
+#pragma unroll
+					for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(drow + 4 * q) = rows[(r * NQ + q) * I5_THREADS];
+					continue;
+				}
 				if (t8) {
 					if ((r & 7) == 0) {
 						const int q8 = ((y4 + (r >> 2)) >> 1) * 2 + (x4 >> 1);
@@ -718,89 +954,99 @@ __device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc
 					}
 				} else if ((r & 3) == 0) {
 					coded = 0;
-					for (int q = 0; q < nq; ++q) {
+					for (int q = 0; q < NQ; ++q) {
 						const int b = c_r2b[(y4 + (r >> 2)) * 4 + x4 + q];
 						if (((m.nz >> (1 + b)) & 1) && block_residual(job, m, b, rs + q * 16)) coded |= 1u << q;
 					}
 				}
-			}
-			uint8_t *drow = dst_y + (size_t)(py0 + r) * W + px0;
-			for (int q = 0; q < nq; ++q) {
-				int p[4];
-				luma_quad(ref, W, H, rx + 4 * q, ry + r, fx, fy, p);
-				if (!last) {
-					*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-					continue;
-				}
-				if (bi) {
-					const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
-					const int lw = mc.log2wd_y, o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
 #pragma unroll
-					for (int i = 0; i < 4; ++i) p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][0] + p[i] * mc.w[1][0] + (1 << lw)) >> (lw + 1)) + o);
-				} else if (weighted) {
-					const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
+				for (int q = 0; q < NQ; ++q) {
+					uint32_t w = rows[(r * NQ + q) * I5_THREADS];
+					const int sb = t8 ? ((r >> 2) & 1) * 2 + (x4 & 1) + q : q;      // narrow strips may sit in the right half of an 8x8 block
+					const bool has = (coded >> sb) & 1;
+					if (bi && plain_w) w = __vavgu4(*reinterpret_cast<const uint32_t *>(drow + 4 * q), w);
+					if (has || !plain_w) {
+						int p[4];
 #pragma unroll
-					for (int i = 0; i < 4; ++i) p[i] = clip255(((p[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
-				}
-				// block of this word inside the scratch: 4x4 path block q; 8x8 path sub-block (row half, q)
-				const int sb = t8 ? ((r >> 2) & 1) * 2 + q : q;
-				if ((coded >> sb) & 1) {
-					const int16_t *res = rs + sb * 16 + (r & 3) * 4;
+						for (int i = 0; i < 4; ++i) p[i] = (w >> (8 * i)) & 255;
+						if (!plain_w) {
+							if (bi) {
+								const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
+								const int lw = mc.log2wd_y, o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
 #pragma unroll
-					for (int i = 0; i < 4; ++i) p[i] = clip255(p[i] + res[i]);
+								for (int i = 0; i < 4; ++i) p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][0] + p[i] * mc.w[1][0] + (1 << lw)) >> (lw + 1)) + o);
+							} else {
+								const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
+#pragma unroll
+								for (int i = 0; i < 4; ++i) p[i] = clip255(((p[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
+							}
+						}
+						if (has) {
+							const int16_t *res = rs + sb * 16 + (r & 3) * 4;
+#pragma unroll
+							for (int i = 0; i < 4; ++i) p[i] = clip255(p[i] + res[i]);
+						}
+						w = pack4(p[0], p[1], p[2], p[3]);
+					}
+					*reinterpret_cast<uint32_t *>(drow + 4 * q) = w;
 				}
-				*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 			}
 		}
-		++pass;
-	}
-	// ---- chroma: nq words (Cb Cr Cb Cr) per row, h / 2 rows -----------------------------------------------
-	pass = 0;
-	for (int l = 0; l < 2; ++l) {
-		if (mc.ref_frame[l] < 0) continue;
-		const uint8_t *refc = job.frames + job.frame_bytes * mc.ref_frame[l] + luma_size;
-		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1];
-		const bool last = !bi || pass == 1;
-		uint32_t coded = 0;
+		// ---- chroma: NQ words (Cb Cr Cb Cr) per row, h / 2 rows -------------------------------------------
 		const int cy0 = y4 * 2, cx0 = x4 * 2;            // chroma sample position inside the MB
-		for (int r = 0; r < h / 2; ++r) {
-			const int cy = cy0 + r;
-			if (last && (r == 0 || (cy & 3) == 0)) {
-				const int cblk = (cy >> 2) * 2 + (cx0 >> 2);
-				coded = 0;
-				for (int comp = 0; comp < 2; ++comp)
-					if (block_residual(job, m, 16 + comp * 4 + cblk, rs + comp * 16)) coded |= 1u << comp;
-			}
-			uint8_t *drow = dst_c + (size_t)(mby * 8 + cy) * W + px0;
-			for (int q = 0; q < nq; ++q) {
-				int p[4];
-				chroma_quad(refc, W, H >> 1, px0 + 4 * q, mby * 8 + cy, mvx, mvy, p);
+		i5_chroma<NQ>(ref + luma_size, W, H >> 1, px0, mby * 8 + cy0, mvx, mvy, h / 2, park);
+		{
+			uint32_t coded = 0;
+			for (int r = 0; r < h / 2; ++r) {
+				const int cy = cy0 + r;
+				uint8_t *drow = dst_c + (size_t)(mby * 8 + cy) * W + px0;
 				if (!last) {
-					*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#pragma unroll
+					for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(drow + 4 * q) = rows[(r * NQ + q) * I5_THREADS];
 					continue;
 				}
-				if (bi) {
-					const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
-					const int lc = mc.log2wd_c;
-#pragma unroll
-					for (int i = 0; i < 4; ++i) {
-						const int c = 1 + (i & 1);
-						p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][c] + p[i] * mc.w[1][c] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][c] + mc.o[1][c] + 1) >> 1));
-					}
-				} else if (weighted) {
-					const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
-#pragma unroll
-					for (int i = 0; i < 4; ++i) {
-						const int c = 1 + (i & 1);
-						p[i] = clip255(((p[i] * mc.w[first][c] + rc) >> lc) + mc.o[first][c]);
-					}
+				if (r == 0 || (cy & 3) == 0) {
+					const int cblk = (cy >> 2) * 2 + (cx0 >> 2);
+					coded = 0;
+					if ((m.nz >> 17) & 0x1ff)                   // any chroma record at all
+						for (int comp = 0; comp < 2; ++comp)
+							if (block_residual(job, m, 16 + comp * 4 + cblk, rs + comp * 16)) coded |= 1u << comp;
 				}
 #pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					const int comp = i & 1, cx = cx0 + 2 * q + (i >> 1);
-					if ((coded >> comp) & 1) p[i] = clip255(p[i] + rs[comp * 16 + (cy & 3) * 4 + (cx & 3)]);
+				for (int q = 0; q < NQ; ++q) {
+					uint32_t w = rows[(r * NQ + q) * I5_THREADS];
+					if (bi && plain_w) w = __vavgu4(*reinterpret_cast<const uint32_t *>(drow + 4 * q), w);
+					if (coded || !plain_w) {
+						int p[4];
+#pragma unroll
+						for (int i = 0; i < 4; ++i) p[i] = (w >> (8 * i)) & 255;
+						if (!plain_w) {
+							if (bi) {
+								const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
+								const int lc = mc.log2wd_c;
+#pragma unroll
+								for (int i = 0; i < 4; ++i) {
+									const int c = 1 + (i & 1);
+									p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][c] + p[i] * mc.w[1][c] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][c] + mc.o[1][c] + 1) >> 1));
+								}
+							} else {
+								const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
+#pragma unroll
+								for (int i = 0; i < 4; ++i) {
+									const int c = 1 + (i & 1);
+									p[i] = clip255(((p[i] * mc.w[first][c] + rc) >> lc) + mc.o[first][c]);
+								}
+							}
+						}
+#pragma unroll
+						for (int i = 0; i < 4; ++i) {
+							const int comp = i & 1, cx = cx0 + 2 * q + (i >> 1);
+							if ((coded >> comp) & 1) p[i] = clip255(p[i] + rs[comp * 16 + (cy & 3) * 4 + (cx & 3)]);
+						}
+						w = pack4(p[0], p[1], p[2], p[3]);
+					}
+					*reinterpret_cast<uint32_t *>(drow + 4 * q) = w;
 				}
-				*reinterpret_cast<uint32_t *>(drow + 4 * q) = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 			}
 		}
 		++pass;
@@ -809,10 +1055,13 @@ __device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc
 
 __global__ void __launch_bounds__(I5_THREADS, 2)
 h264_inter5_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
-	__shared__ uint32_t s_items[I5_MBS * 16];
+	// dynamic shared memory (more than the 48 KB a kernel may declare statically)
+	extern __shared__ __align__(16) uint8_t s_dyn[];
+	uint32_t (*s_rows)[I5_THREADS] = reinterpret_cast<uint32_t(*)[I5_THREADS]>(s_dyn);                       // per thread: up to 16 rows x 2 words of prediction
+	int16_t (*s_rs)[66] = reinterpret_cast<int16_t(*)[66]>(s_dyn + sizeof(uint32_t) * 32 * I5_THREADS);     // per thread: residual scratch
+	uint32_t *s_items = reinterpret_cast<uint32_t *>(s_dyn + sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS);
 	__shared__ int s_cnt[I5_CLASSES + 1];
 	__shared__ int s_pos[I5_CLASSES];
-	__shared__ __align__(4) int16_t s_rs[I5_THREADS][66];
 	const H4Job job = jobs[blockIdx.y];
 	const int tid = threadIdx.x;
 	const int mb0 = blockIdx.x * I5_MBS;
@@ -829,12 +1078,16 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 			const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);      // first 16 bytes: pos .. mv
 			const int l = mc.ref_frame[0] >= 0 ? 0 : 1;
 			const int w4 = mc.size & 15, h4 = mc.size >> 4, x4 = mc.pos & 3, y4 = mc.pos >> 2;
-			const int wide = w4 >= 2;
-			const int cls = frac_class(mc.mv[l][0] & 3, mc.mv[l][1] & 3) + 6 * wide;
-			const int n = wide ? w4 >> 1 : 1;
+			// both lists must be narrow-capable if either needs the centre sample
+			int fc = frac_class(mc.mv[l][0] & 3, mc.mv[l][1] & 3);
+			bool centre = fc >= 4;
+			if (mc.ref_frame[0] >= 0 && mc.ref_frame[1] >= 0) centre |= frac_class(mc.mv[1][0] & 3, mc.mv[1][1] & 3) >= 4;
+			const int wide = w4 >= 2 && !centre;
+			const int cls = fc + 6 * wide;
+			const int n = wide ? w4 >> 1 : w4;
 			if (!place) { atomicAdd(&s_cnt[cls], n); continue; }
 			const int at = atomicAdd(&s_pos[cls], n);
-			for (int k = 0; k < n; ++k) s_items[at + k] = i5_pack(slot, ri, x4 + 2 * k, y4, h4, wide, cls);
+			for (int k = 0; k < n; ++k) s_items[at + k] = i5_pack(slot, ri, x4 + (wide ? 2 * k : k), y4, h4, wide, cls);
 		}
 		__syncthreads();
 		if (!place) {
@@ -856,7 +1109,8 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 		b2_h264_mc mc;
 		reinterpret_cast<int4 *>(&mc)[0] = __ldg(reinterpret_cast<const int4 *>(mcp));
 		reinterpret_cast<int4 *>(&mc)[1] = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
-		i5_strip(job, m, mc, mb % job.mb_w, mb / job.mb_w, (item >> 10) & 3, (item >> 12) & 3, (item >> 14) & 7, (item >> 17) & 1, s_rs[tid]);
+		if ((item >> 17) & 1) i5_strip<2>(job, m, mc, mb % job.mb_w, mb / job.mb_w, (item >> 10) & 3, (item >> 12) & 3, (item >> 14) & 7, s_rs[tid], &s_rows[0][tid]);
+		else i5_strip<1>(job, m, mc, mb % job.mb_w, mb / job.mb_w, (item >> 10) & 3, (item >> 12) & 3, (item >> 14) & 7, s_rs[tid], &s_rows[0][tid]);
 	}
 }
 
@@ -1826,7 +2080,13 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 0;
 		if (use5) {
 			dim3 grid5((n_mbs + I5_MBS - 1) / I5_MBS, n_jobs);
-			h264_inter5_kernel<<<grid5, I5_THREADS, 0, stream>>>(d_jobs, n_mbs);
+			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint32_t) * I5_MBS * 16;
+			static bool attr_set = false;       // per process; the attribute is per device function
+			if (!attr_set) {
+				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+				attr_set = true;
+			}
+			h264_inter5_kernel<<<grid5, I5_THREADS, smem5, stream>>>(d_jobs, n_mbs);
 		} else {
 			dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
 			h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
