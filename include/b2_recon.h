@@ -145,6 +145,14 @@ typedef struct {
 	const b2_h264_dbk *dbk;
 	const b2_h264_mc *mcs;
 	const int16_t *coefs;
+	/* Work list of the inter kernel: one item per vertical strip of a motion-compensation record (8
+	 * luma samples wide, or 4 for 4-wide partitions and for records that need the centre half sample
+	 * j; full height of the partition), sorted by (class, height) so that a warp runs one code path.
+	 * bits 0..19 macroblock index, 20..23 record index inside the macroblock, 24..25 strip index inside
+	 * the record, 26..29 class = interpolation class of the first used list (0 integer, 1 horizontal,
+	 * 2 vertical, 3 diagonal, 4 / 5 centre column / row) + 6 if the strip is 8 samples wide.           */
+	const uint32_t *items;
+	uint32_t n_items;
 } b2_h264_picture;
 
 /* ------------------------------------------------------------------------------------ */

@@ -38,6 +38,8 @@ struct H4Job {
 	const b2_h264_mc *mcs;
 	const int16_t *coefs;
 	int32_t dst, mb_w, mb_h, n_intra;
+	const uint32_t *items;      // b2_h264_picture.items
+	uint32_t n_items, pad;
 };
 // A picture with few intra macroblocks (P / B pictures) goes through the sparse intra kernel, which
 // orders macroblocks by per-macroblock flags; a mostly-intra picture through the row wavefront.
@@ -45,8 +47,10 @@ __host__ __device__ inline bool h264_intra_sparse(int n_intra, int n_mbs) { retu
 // phase: 0 inter (MC + residual), 1 intra wavefront (dense pictures), 2 deblock wavefront,
 // 3 intra, sparse pictures
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h);
-int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches);
-int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool intra_dense,
+// max_items: largest n_items among the jobs (phase 0 only)
+int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
+                      uint32_t max_items = 0);
+int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense,
                 bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches);
 
 __device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }

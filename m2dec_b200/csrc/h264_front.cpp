@@ -701,6 +701,7 @@ private:
 		mbs_.assign(n, b2_h264_mb());
 		dbk_.assign(n, b2_h264_dbk());
 		mcs_.clear();
+		for (auto &b : items_) b.clear();
 		coef_used_ = 0;
 		n_intra_ = 0;
 		any_deblock_ = false;
@@ -726,6 +727,10 @@ private:
 		p.dbk = dbk_.data();
 		p.mcs = mcs_.data();
 		p.coefs = coefs_.data();
+		items_all_.clear();
+		for (const auto &b : items_) items_all_.insert(items_all_.end(), b.begin(), b.end());
+		p.items = items_all_.data();
+		p.n_items = (uint32_t)items_all_.size();
 		backend.submit(B2_CODEC_H264, &p);
 		pic_open_ = false;
 		// reference marking (8.2.5) and DPB insertion (h264.cpp:10840-10873, 11036-11045)
@@ -948,6 +953,18 @@ private:
 			}
 			r.log2wd_y = r.log2wd_c = 5;
 			for (int c = 0; c < 3; ++c) { r.w[0][c] = (int8_t)w0; r.w[1][c] = (int8_t)w1; }
+		}
+		// work items of the inter kernel (include/b2_recon.h): strips of this record, bucketed by class and height
+		{
+			auto frac_class = [](int fx, int fy) { return (!fx && !fy) ? 0 : (!fy ? 1 : (!fx ? 2 : (fx == 2 ? 4 : (fy == 2 ? 5 : 3)))); };
+			const int first = ref[0] >= 0 ? 0 : 1;
+			const int fc = frac_class(r.mv[first][0] & 3, r.mv[first][1] & 3);
+			bool centre = fc >= 4;
+			if (bi) centre |= frac_class(r.mv[1][0] & 3, r.mv[1][1] & 3) >= 4;
+			const int wide = pw >= 2 && !centre;
+			const int cls = fc + 6 * wide, n = wide ? pw >> 1 : pw;
+			std::vector<uint32_t> &bucket = items_[cls * 3 + (ph == 4 ? 2 : ph - 1)];
+			for (int k = 0; k < n; ++k) bucket.push_back((uint32_t)mb_addr_ | ((uint32_t)m.mc_cnt << 20) | ((uint32_t)k << 24) | ((uint32_t)cls << 26));
 		}
 		mcs_.push_back(r);
 		m.mc_cnt++;
@@ -1723,6 +1740,7 @@ private:
 	std::vector<b2_h264_mb> mbs_;
 	std::vector<b2_h264_dbk> dbk_;
 	std::vector<b2_h264_mc> mcs_;
+	std::vector<uint32_t> items_[36], items_all_;      // inter work items per (class, height) bucket / concatenated
 	std::vector<int16_t> coefs_;
 	size_t coef_used_ = 0;
 	uint32_t n_intra_;

@@ -665,7 +665,6 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 // transformed by the same thread into a private shared-memory scratch, so there is no separate
 // residual phase and only the sort needs block-wide barriers.
 // ------------------------------------------------------------------------------------------------
-constexpr int I5_MBS = 64;
 constexpr int I5_THREADS = 256;
 constexpr int I5_CLASSES = 12;        // interpolation class (0..5) + 6 * (strip is 8 wide)
 
@@ -1054,64 +1053,26 @@ __device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc
 }
 
 __global__ void __launch_bounds__(I5_THREADS, 2)
-h264_inter5_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
+h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	// dynamic shared memory (more than the 48 KB a kernel may declare statically)
 	extern __shared__ __align__(16) uint8_t s_dyn[];
 	uint32_t (*s_rows)[I5_THREADS] = reinterpret_cast<uint32_t(*)[I5_THREADS]>(s_dyn);                       // per thread: up to 16 rows x 2 words of prediction
 	int16_t (*s_rs)[66] = reinterpret_cast<int16_t(*)[66]>(s_dyn + sizeof(uint32_t) * 32 * I5_THREADS);     // per thread: residual scratch
-	uint32_t *s_items = reinterpret_cast<uint32_t *>(s_dyn + sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS);
-	__shared__ int s_cnt[I5_CLASSES + 1];
-	__shared__ int s_pos[I5_CLASSES];
 	const H4Job job = jobs[blockIdx.y];
 	const int tid = threadIdx.x;
-	const int mb0 = blockIdx.x * I5_MBS;
-	if (tid <= I5_CLASSES) s_cnt[tid] = 0;
-	__syncthreads();
-	// two passes over the (macroblock, record) pairs: count the strips per class, then place them
-	for (int place = 0; place < 2; ++place) {
-		for (int e = tid; e < I5_MBS * 16; e += I5_THREADS) {
-			const int slot = e >> 4, ri = e & 15, mb = mb0 + slot;
-			if (mb >= n_mbs) continue;
-			const b2_h264_mb *mp = job.mbs + mb;
-			if (mp->type != B2_H4_INTER || ri >= mp->mc_cnt) continue;
-			const int4 raw = __ldg(reinterpret_cast<const int4 *>(job.mcs + mp->mc_idx + ri));
-			const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);      // first 16 bytes: pos .. mv
-			const int l = mc.ref_frame[0] >= 0 ? 0 : 1;
-			const int w4 = mc.size & 15, h4 = mc.size >> 4, x4 = mc.pos & 3, y4 = mc.pos >> 2;
-			// both lists must be narrow-capable if either needs the centre sample
-			int fc = frac_class(mc.mv[l][0] & 3, mc.mv[l][1] & 3);
-			bool centre = fc >= 4;
-			if (mc.ref_frame[0] >= 0 && mc.ref_frame[1] >= 0) centre |= frac_class(mc.mv[1][0] & 3, mc.mv[1][1] & 3) >= 4;
-			const int wide = w4 >= 2 && !centre;
-			const int cls = fc + 6 * wide;
-			const int n = wide ? w4 >> 1 : w4;
-			if (!place) { atomicAdd(&s_cnt[cls], n); continue; }
-			const int at = atomicAdd(&s_pos[cls], n);
-			for (int k = 0; k < n; ++k) s_items[at + k] = i5_pack(slot, ri, x4 + (wide ? 2 * k : k), y4, h4, wide, cls);
-		}
-		__syncthreads();
-		if (!place) {
-			if (tid == 0) {
-				int acc = 0;
-				for (int c = 0; c < I5_CLASSES; ++c) { s_pos[c] = acc; acc += s_cnt[c]; }
-				s_cnt[I5_CLASSES] = acc;
-			}
-			__syncthreads();
-		}
-	}
-	const int total = s_cnt[I5_CLASSES];
-	for (int it = tid; it < total; it += I5_THREADS) {
-		const uint32_t item = s_items[it];
-		const int slot = item & 63, ri = (item >> 6) & 15;
-		const int mb = mb0 + slot;
-		const b2_h264_mb m = job.mbs[mb];
-		const b2_h264_mc *mcp = job.mcs + m.mc_idx + ri;
-		b2_h264_mc mc;
-		reinterpret_cast<int4 *>(&mc)[0] = __ldg(reinterpret_cast<const int4 *>(mcp));
-		reinterpret_cast<int4 *>(&mc)[1] = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
-		if ((item >> 17) & 1) i5_strip<2>(job, m, mc, mb % job.mb_w, mb / job.mb_w, (item >> 10) & 3, (item >> 12) & 3, (item >> 14) & 7, s_rs[tid], &s_rows[0][tid]);
-		else i5_strip<1>(job, m, mc, mb % job.mb_w, mb / job.mb_w, (item >> 10) & 3, (item >> 12) & 3, (item >> 14) & 7, s_rs[tid], &s_rows[0][tid]);
-	}
+	const uint32_t it = blockIdx.x * I5_THREADS + tid;
+	if (it >= job.n_items) return;
+	// the list comes sorted by (class, height) from the host: a warp runs one interpolation path
+	const uint32_t item = __ldg(job.items + it);
+	const int mb = item & 0xfffff, ri = (item >> 20) & 15, k = (item >> 24) & 3, wide = ((item >> 26) & 15) >= 6;
+	const b2_h264_mb m = job.mbs[mb];
+	const b2_h264_mc *mcp = job.mcs + m.mc_idx + ri;
+	b2_h264_mc mc;
+	reinterpret_cast<int4 *>(&mc)[0] = __ldg(reinterpret_cast<const int4 *>(mcp));
+	reinterpret_cast<int4 *>(&mc)[1] = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
+	const int x4 = (mc.pos & 3) + (wide ? 2 * k : k), y4 = mc.pos >> 2, h4 = mc.size >> 4;
+	if (wide) i5_strip<2>(job, m, mc, mb % job.mb_w, mb / job.mb_w, x4, y4, h4, s_rs[tid], &s_rows[0][tid]);
+	else i5_strip<1>(job, m, mc, mb % job.mb_w, mb / job.mb_w, x4, y4, h4, s_rs[tid], &s_rows[0][tid]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2073,20 +2034,21 @@ h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, i
 // of different streams run concurrently
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h) { return (32 + (size_t)n_jobs * mb_w * mb_h) * sizeof(int); }
 
-int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches) {
+int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
+                      uint32_t max_items) {
 	if (n_jobs <= 0) return 0;
 	if (phase == 0) {
 		const int n_mbs = mb_w * mb_h;
 		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 0;
 		if (use5) {
-			dim3 grid5((n_mbs + I5_MBS - 1) / I5_MBS, n_jobs);
-			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint32_t) * I5_MBS * 16;
+			dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
+			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS;
 			static bool attr_set = false;       // per process; the attribute is per device function
 			if (!attr_set) {
 				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
 				attr_set = true;
 			}
-			h264_inter5_kernel<<<grid5, I5_THREADS, smem5, stream>>>(d_jobs, n_mbs);
+			h264_inter5_kernel<<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
 		} else {
 			dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
 			h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
@@ -2116,9 +2078,9 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 	return 0;
 }
 
-int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, bool any_inter, bool intra_dense, bool intra_sparse,
+int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense, bool intra_sparse,
                 bool deblock, int *sync_area, uint64_t *launches) {
-	if (any_inter && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
+	if (max_items && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches, max_items) < 0) return -1;
 	if (intra_dense && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (intra_sparse && launch_h264_phase(stream, 3, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (deblock && launch_h264_phase(stream, 2, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;

@@ -22,7 +22,8 @@ struct Step {
 	std::vector<H4Job> h4;       // one job per lane (of the group) that has a picture at this step
 	std::vector<M2Job> m2;
 	void *d_jobs = nullptr;
-	bool any_inter = false, intra_dense = false, intra_sparse = false, deblock = false;
+	bool intra_dense = false, intra_sparse = false, deblock = false;
+	uint32_t max_items = 0;
 };
 struct Group {
 	cudaStream_t stream = nullptr;
@@ -137,7 +138,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	std::vector<size_t> off;
 	uint8_t *d;
 	if (upload(r, {{p->mbs, sizeof(b2_h264_mb) * p->n_mbs}, {p->dbk, sizeof(b2_h264_dbk) * p->n_mbs},
-	               {p->mcs, sizeof(b2_h264_mc) * p->n_mcs}, {p->coefs, (size_t)p->n_coef_recs * 32}}, &off, &d) < 0) return -1;
+	               {p->mcs, sizeof(b2_h264_mc) * p->n_mcs}, {p->coefs, (size_t)p->n_coef_recs * 32}, {p->items, (size_t)p->n_items * 4}}, &off, &d) < 0) return -1;
 	H4Job job;
 	memset(&job, 0, sizeof(job));
 	job.frames = r->frames + r->frame_bytes * r->pool * lane;
@@ -146,13 +147,15 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	job.dbk = (const b2_h264_dbk *)(d + off[1]);
 	job.mcs = (const b2_h264_mc *)(d + off[2]);
 	job.coefs = (const int16_t *)(d + off[3]);
+	job.items = (const uint32_t *)(d + off[4]);
+	job.n_items = p->n_items;
 	job.dst = p->dst; job.mb_w = p->mb_w; job.mb_h = p->mb_h; job.n_intra = (int32_t)p->n_intra;
 	int t = r->lane_len[lane]++;
 	std::vector<Step> &steps = r->groups[lane % r->groups.size()].steps;
 	if ((int)steps.size() <= t) steps.resize(t + 1);
 	Step &s = steps[t];
 	s.h4.push_back(job);
-	s.any_inter |= p->n_intra < p->n_mbs;
+	if (p->n_items > s.max_items) s.max_items = p->n_items;
 	if (p->n_intra > 0) (h264_intra_sparse((int)p->n_intra, (int)p->n_mbs) ? s.intra_sparse : s.intra_dense) = true;
 	s.deblock |= p->deblock != 0;
 	// algorithmic bytes: S(1 + 2 dbk) + R + C + M, split by kernel
@@ -251,7 +254,7 @@ extern "C" int b2_replay_run(b2_replay *r, int timed) {
 			const H4Job *jobs = (const H4Job *)s.d_jobs;
 			int n = (int)s.h4.size();
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 0], g.stream));
-			if (s.any_inter && launch_h264_phase(g.stream, 0, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
+			if (s.max_items && launch_h264_phase(g.stream, 0, jobs, n, mb_w, mb_h, g.sync_area, &launches, s.max_items) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 1], g.stream));
 			if (s.intra_dense && launch_h264_phase(g.stream, 1, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (s.intra_sparse && launch_h264_phase(g.stream, 3, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;

@@ -231,7 +231,8 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	size_t off_dbk = align_up(off_mbs + sizeof(b2_h264_mb) * p->n_mbs, 256);
 	size_t off_mcs = align_up(off_dbk + sizeof(b2_h264_dbk) * p->n_mbs, 256);
 	size_t off_coef = align_up(off_mcs + sizeof(b2_h264_mc) * p->n_mcs, 256);
-	size_t total = off_coef + (size_t)p->n_coef_recs * 32;
+	size_t off_items = align_up(off_coef + (size_t)p->n_coef_recs * 32, 256);
+	size_t total = off_items + (size_t)p->n_items * 4;
 	StageSlot *sl;
 	if (acquire_slot(s, total, &sl) < 0) return -1;
 	H4Job job;
@@ -246,14 +247,17 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	job.mb_w = p->mb_w;
 	job.mb_h = p->mb_h;
 	job.n_intra = (int32_t)p->n_intra;
+	job.items = (const uint32_t *)(sl->dev + off_items);
+	job.n_items = p->n_items;
 	memcpy(sl->host, &job, sizeof(job));
 	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
 	memcpy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
 	if (p->n_mcs) memcpy(sl->host + off_mcs, p->mcs, sizeof(b2_h264_mc) * p->n_mcs);
 	if (p->n_coef_recs) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
+	if (p->n_items) memcpy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
-	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_intra < p->n_mbs,
+	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_items,
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
 	                p->deblock != 0, s->sync_area, &s->launches) < 0) return -1;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
