@@ -184,7 +184,20 @@ void b2_session_destroy(b2_session *s);
 /* Asynchronous: copies the picture's SoA into pinned staging, enqueues H2D + kernels.     */
 int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *pic);
 int b2_session_submit_h264(b2_session *s, const b2_h264_picture *pic);
-/* Waits for everything queued so far, then copies frame `idx` to host memory.             */
+/* Tell the session where the application keeps frame `idx` (the m2d_frame_t of set_frames,  */
+/* reference m2d.h:66-75).  When these buffers are page-locked (b2_host_alloc below, or the    */
+/* application's own cudaHostAlloc / cudaHostRegister) every picture is copied out as soon as  */
+/* its kernels are queued and b2_session_download() only waits for that copy; pageable         */
+/* buffers keep the copy-on-demand behaviour.  The plugin front ends call this from            */
+/* set_frames().                                                                               */
+int b2_session_bind_host_frame(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma);
+/* Page-locked host memory for the application's frame buffers (replaces the `new byte_t[]` of */
+/* reference src/app/frames.h), usable from every device; cuda_device < 0: the calling         */
+/* thread's current device.  NULL without a CUDA device.                                       */
+void *b2_host_alloc(size_t bytes, int cuda_device);
+void b2_host_free(void *p);
+/* Makes frame `idx` visible in host memory: waits for the picture that wrote it (not for    */
+/* pictures queued behind it) and copies it out unless it was bound and is there already.   */
 int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma);
 int b2_session_upload(b2_session *s, int idx, const uint8_t *luma, const uint8_t *chroma);
 int b2_session_sync(b2_session *s);

@@ -68,6 +68,10 @@ lib.b2_context_set_tap.argtypes = [C.c_void_p, TAP_CB, C.c_void_p, C.c_int]
 lib.b2_context_set_device.argtypes = [C.c_void_p, C.c_int]
 lib.b2_context_release.argtypes = [C.c_void_p]
 lib.b2_device_count.restype = C.c_int
+lib.b2_host_alloc.argtypes = [C.c_size_t, C.c_int]
+lib.b2_host_alloc.restype = C.c_void_p
+lib.b2_host_free.argtypes = [C.c_void_p]
+lib.b2_host_free.restype = None
 lib.b2_last_error.restype = C.c_char_p
 
 

@@ -5,7 +5,7 @@
 
 namespace b2 {
 
-Backend::Backend() : tap_(nullptr), tap_arg_(nullptr), device_off_(false), dead_(false), cuda_device_(0), sess_(nullptr), codec_(0), width_(0), height_(0), nframes_(0) {
+Backend::Backend() : tap_(nullptr), tap_arg_(nullptr), device_off_(false), dead_(false), cuda_device_(0), sess_(nullptr), codec_(0), width_(0), height_(0), nframes_(0), n_host_(0) {
 	const char *e = getenv("B2_CUDA_DEVICE");
 	if (e) cuda_device_ = atoi(e);
 }
@@ -27,7 +27,9 @@ int Backend::configure(int codec, int width, int height, int nframes) {
 		fprintf(stderr, "m2dec_b200: cannot create CUDA reconstruction session: %s\n", b2_last_error());
 		sess_ = nullptr;
 		dead_ = true;
+		return err;
 	}
+	for (int i = 0; i < n_host_ && i < nframes; ++i) b2_session_bind_host_frame(sess_, i, host_luma_[i], host_chroma_[i]);
 	return err;
 }
 

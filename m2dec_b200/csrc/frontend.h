@@ -29,7 +29,12 @@ public:
 	~Backend();
 	void set_tap(b2_picture_tap tap, void *arg, int device_off) { tap_ = tap; tap_arg_ = arg; device_off_ = device_off != 0; }
 	void set_device(int dev) { cuda_device_ = dev; }
-	// (re)create the device frame pool; called from set_frames
+	// the application's frame buffers (set_frames): frame i of the device pool is copied out to them
+	void bind_frames(const m2d_frame_t *frames, int n) {
+		n_host_ = n < 64 ? n : 64;
+		for (int i = 0; i < n_host_; ++i) { host_luma_[i] = frames[i].luma; host_chroma_[i] = frames[i].chroma; }
+	}
+	// (re)create the device frame pool; called from set_frames (after bind_frames)
 	int configure(int codec, int width, int height, int nframes);
 	// same, but keeps the existing session when nothing changed (called at every picture start)
 	int ensure(int codec, int width, int height, int nframes) {
@@ -52,6 +57,8 @@ private:
 	int cuda_device_;
 	b2_session *sess_;
 	int codec_, width_, height_, nframes_;
+	int n_host_;
+	uint8_t *host_luma_[64], *host_chroma_[64];
 };
 
 }  // namespace b2

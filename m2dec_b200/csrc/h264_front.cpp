@@ -204,6 +204,7 @@ public:
 		memset(lru_, 0, sizeof(lru_));
 		memset(host_valid_, 0, sizeof(host_valid_));
 		const Sps &s = sps_[active_sps_];
+		backend.bind_frames(frames_, num);
 		return backend.configure(B2_CODEC_H264, s.width, s.height, num);
 	}
 

@@ -2039,7 +2039,7 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 	if (n_jobs <= 0) return 0;
 	if (phase == 0) {
 		const int n_mbs = mb_w * mb_h;
-		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 0;
+		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 1;     // 0: the older 4x4-item kernel (kept for comparison)
 		if (use5) {
 			dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
 			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS;

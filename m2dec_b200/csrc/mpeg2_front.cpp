@@ -112,6 +112,7 @@ public:
 		memcpy(frames_, frames, sizeof(frames_[0]) * num);
 		cur_idx_ = -1;
 		memset(host_valid_, 0, sizeof(host_valid_));
+		backend.bind_frames(frames_, num);
 		return backend.configure(B2_CODEC_MPEG2, mb_w_ * 16, mb_h_ * 16, num);
 	}
 

@@ -3,6 +3,7 @@
 // each picture's SoA travels host -> HBM in a single asynchronous copy.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -78,6 +79,13 @@ struct b2_session {
 	int *sync_area;                 // wavefront ticket / progress flags of this stream
 	cudaEvent_t frame_done[64];     // recorded after the kernels that write frame i
 	bool frame_written[64];
+	// Caller-owned host frame buffers (m2d_frame_t of set_frames).  A frame whose host buffers could be
+	// page-locked is copied out as soon as its picture is queued ("eager"), so that the application's
+	// peek / get finds it there; otherwise it is copied when asked for.
+	uint8_t *host_luma[64], *host_chroma[64];
+	uint8_t host_state[64];         // 0 not looked at yet, 1 page-locked by the application, 2 pageable
+	cudaEvent_t copy_done[64];      // recorded on the copy stream after the eager copy of frame i
+	bool eager[64];                 // host buffers of frame i hold (or will hold, after copy_done) its current content
 	StageSlot slots[NSLOT];
 	int next_slot;
 	uint64_t launches;
@@ -118,11 +126,15 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	if (nframes > 64) { set_error("b2_session_create: at most 64 frames"); delete s; return -1; }
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-	for (int i = 0; i < nframes; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
+	for (int i = 0; i < nframes; ++i) {
+		B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
+		// waited for by host threads that have nothing else to do meanwhile: block, do not spin
+		B2_CUDA_OK(cudaEventCreateWithFlags(&s->copy_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+	}
 	if (cache_get(cuda_device, false, s->frame_bytes * nframes, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
 	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * nframes, s->stream));
 	if (cache_get(cuda_device, false, h264_sync_bytes(1, width / 16, height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
-	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming));
+	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
 	*out = s;
 	return 0;
 }
@@ -136,8 +148,11 @@ extern "C" void b2_session_destroy(b2_session *s) {
 		cache_put(s->dev, false, s->slots[i].cap_dev, s->slots[i].dev);
 		cudaEventDestroy(s->slots[i].done);
 	}
-	for (int i = 0; i < s->nframes; ++i) cudaEventDestroy(s->frame_done[i]);
 	cudaStreamSynchronize(s->copy_stream);
+	for (int i = 0; i < s->nframes; ++i) {
+		cudaEventDestroy(s->frame_done[i]);
+		cudaEventDestroy(s->copy_done[i]);
+	}
 	cache_put(s->dev, false, s->frames_alloc, s->frames);
 	cache_put(s->dev, false, s->sync_alloc, s->sync_area);
 	cudaStreamDestroy(s->copy_stream);
@@ -173,6 +188,71 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+extern "C" int b2_session_bind_host_frame(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma) {
+	if (!s || (unsigned)idx >= (unsigned)s->nframes) return -1;
+	if (s->eager[idx]) {
+		cudaSetDevice(s->dev);
+		cudaStreamSynchronize(s->copy_stream);
+	}
+	if (s->host_luma[idx] != luma || s->host_chroma[idx] != chroma) s->host_state[idx] = 0;
+	s->host_luma[idx] = luma;
+	s->host_chroma[idx] = chroma;
+	s->eager[idx] = false;
+	return 0;
+}
+
+extern "C" void *b2_host_alloc(size_t bytes, int cuda_device) {
+	void *p = nullptr;
+	if (b2_device_count() <= 0) return nullptr;
+	if (cuda_device >= 0 && cudaSetDevice(cuda_device) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void b2_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+// Before the kernels of a picture that (re)writes frame `dst` are queued: they must not overtake an
+// eager copy of the frame's previous content that is still in flight.
+static int before_write(b2_session *s, int dst) {
+	if (s->eager[dst]) B2_CUDA_OK(cudaStreamWaitEvent(s->stream, s->copy_done[dst], 0));
+	s->eager[dst] = false;
+	return 0;
+}
+
+// After frame_done[dst] has been recorded: queue the copy into the caller's frame buffers when they are
+// page-locked.  Pageable buffers are left to b2_session_download: a copy into pageable
+// memory would block the parsing thread here until the kernels are done.
+static int after_write(b2_session *s, int dst) {
+	static const bool off = getenv("B2_NO_EAGER_D2H") != nullptr;
+	if (off || !s->host_luma[dst] || !s->host_chroma[dst]) return 0;
+	const size_t ls = (size_t)s->width * s->height;
+	if (s->host_state[dst] == 0) {
+		// page-locked by the application (b2_host_alloc, cudaHostAlloc, cudaHostRegister)?  Page-locking here, per
+		// stream, would cost more than it saves (milliseconds per buffer).
+		cudaPointerAttributes al, ac;
+		const bool pinned = cudaPointerGetAttributes(&al, s->host_luma[dst]) == cudaSuccess && al.type == cudaMemoryTypeHost &&
+		                    cudaPointerGetAttributes(&ac, s->host_chroma[dst]) == cudaSuccess && ac.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		s->host_state[dst] = pinned ? 1 : 2;
+	}
+	if (s->host_state[dst] != 1) return 0;
+	const uint8_t *src = s->frames + s->frame_bytes * dst;
+	B2_CUDA_OK(cudaStreamWaitEvent(s->copy_stream, s->frame_done[dst], 0));
+	B2_CUDA_OK(cudaMemcpyAsync(s->host_luma[dst], src, ls, cudaMemcpyDeviceToHost, s->copy_stream));
+	B2_CUDA_OK(cudaMemcpyAsync(s->host_chroma[dst], src + ls, ls / 2, cudaMemcpyDeviceToHost, s->copy_stream));
+	B2_CUDA_OK(cudaEventRecord(s->copy_done[dst], s->copy_stream));
+	s->d2h_bytes += ls + ls / 2;
+	s->eager[dst] = true;
+	return 0;
+}
+
 extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 	if (!s || !p || s->codec != B2_CODEC_MPEG2) return -1;
 	if (p->mb_w * 16 != s->width || p->mb_h * 16 != s->height) {
@@ -204,13 +284,14 @@ extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 	if (p->n_blocks) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_blocks * 128);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
+	if (before_write(s, p->dst) < 0) return -1;
 	if (launch_mpeg2(s->stream, (const M2Job *)sl->dev, 1, p->mb_w, p->mb_h) < 0) return -1;
 	s->launches++;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
 	s->frame_written[p->dst] = true;
 	sl->pending = true;
-	return 0;
+	return after_write(s, p->dst);
 }
 
 extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
@@ -257,6 +338,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (p->n_items) memcpy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
+	if (before_write(s, p->dst) < 0) return -1;
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_items,
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
 	                p->deblock != 0, s->sync_area, &s->launches) < 0) return -1;
@@ -264,7 +346,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
 	s->frame_written[p->dst] = true;
 	sl->pending = true;
-	return 0;
+	return after_write(s, p->dst);
 }
 
 extern "C" int b2_session_sync(b2_session *s) {
@@ -279,6 +361,11 @@ extern "C" int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_
 	B2_CUDA_OK(cudaSetDevice(s->dev));
 	size_t ls = (size_t)s->width * s->height;
 	const uint8_t *src = s->frames + s->frame_bytes * idx;
+	if (s->eager[idx] && luma == s->host_luma[idx] && chroma == s->host_chroma[idx]) {
+		// already on its way (or there) since the picture was queued
+		B2_CUDA_OK(cudaEventSynchronize(s->copy_done[idx]));
+		return 0;
+	}
 	// wait for the picture that last wrote this frame only, not for pictures queued behind it:
 	// the host keeps parsing ahead while earlier frames are copied out
 	if (s->frame_written[idx]) B2_CUDA_OK(cudaStreamWaitEvent(s->copy_stream, s->frame_done[idx], 0));

@@ -27,17 +27,36 @@ class Frames:
     """Caller-owned frame buffers (reference src/app/frames.h): 16-byte aligned luma W*H and
     NV12 chroma W*H/2."""
 
-    def __init__(self, width, height, num, second_len):
+    def __init__(self, width, height, num, second_len, pinned=True, cuda_device=-1):
         self.width, self.height = width, height
         self.luma_len = width * height
-        self.luma = [_align16(np.zeros(self.luma_len + 15, np.uint8)) for _ in range(num)]
-        self.chroma = [_align16(np.zeros(self.luma_len // 2 + 15, np.uint8)) for _ in range(num)]
+        # one page-locked block for all frames (b2_host_alloc) when a CUDA device is there: finished
+        # pictures are then copied straight into these buffers as soon as their kernels are queued
+        fb = self.luma_len * 3 // 2
+        self._pinned = L.lib.b2_host_alloc(fb * num, cuda_device) if pinned else None
+        if self._pinned:
+            blk = np.ctypeslib.as_array(C.cast(self._pinned, C.POINTER(C.c_uint8)), shape=(fb * num,))
+            blk[:] = 0
+            self.luma = [blk[i * fb:i * fb + self.luma_len] for i in range(num)]
+            self.chroma = [blk[i * fb + self.luma_len:(i + 1) * fb] for i in range(num)]
+        else:
+            self.luma = [_align16(np.zeros(self.luma_len + 15, np.uint8)) for _ in range(num)]
+            self.chroma = [_align16(np.zeros(self.luma_len // 2 + 15, np.uint8)) for _ in range(num)]
         self.second = np.zeros(max(second_len, 1), np.uint8)
         self.array = (L.FrameT * num)()
         for i in range(num):
             self.array[i].luma = self.luma[i].ctypes.data
             self.array[i].chroma = self.chroma[i].ctypes.data
         self.num = num
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pinned", None):
+                self.luma = self.chroma = None
+                L.lib.b2_host_free(self._pinned)
+                self._pinned = None
+        except Exception:
+            pass
 
     def sufficient(self, num, luma_len, second_len):
         return num <= self.num and luma_len <= self.luma_len and second_len <= len(self.second)
@@ -49,13 +68,13 @@ _frames_pool = {}
 _frames_lock = __import__("threading").Lock()
 
 
-def _frames_acquire(width, height, num, second_len):
+def _frames_acquire(width, height, num, second_len, pinned=True, cuda_device=-1):
     key = (width, height, num)
     with _frames_lock:
         lst = _frames_pool.get(key)
         if lst:
             return lst.pop()
-    return Frames(width, height, num, second_len)
+    return Frames(width, height, num, second_len, pinned, cuda_device)
 
 
 def _frames_release(fr):
@@ -88,6 +107,7 @@ def frame_md5(frm):
 class M2Decoder:
     def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None):
         self.codec = codec
+        self._device_off, self._cuda_device = device_off, cuda_device
         self.func = L.func_table(_TABLES[codec])
         self._data = np.frombuffer(bytes(data), np.uint8)
         self._fed = False
@@ -145,7 +165,8 @@ class M2Decoder:
         bufnum = min(bufnum, H264D_MAX_FRAME_NUM if self.codec == MODE_H264 else MAX_FRAME_NUM)
         if self.frames is not None and self.frames.sufficient(bufnum, width * height, info.additional_size):
             return 0
-        self.frames = _frames_acquire(width, height, bufnum, info.additional_size)
+        self.frames = _frames_acquire(width, height, bufnum, info.additional_size, not self._device_off,
+                                      -1 if self._cuda_device is None else self._cuda_device)
         self.info = info
         r = self.func.set_frames(self.ctx, bufnum, self.frames.array,
                                  self.frames.second.ctypes.data, info.additional_size)

@@ -31,8 +31,10 @@ def run(device_off, threads):
     dt = time.perf_counter() - t0
     return frames[0] / dt, dt
 
-for off in (True, False):
-    for th in (1, 4, 8, 16):
+TH = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 4, 8, 16]
+OFF = (False,) if os.environ.get("PROBE_DEVICE_ONLY") else (True, False)
+for off in OFF:
+    for th in TH:
         if th > N: continue
         run(off, th)
         fps, dt = run(off, th)
