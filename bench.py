@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
     ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
     ap.add_argument("--e2e-streams", type=int, default=16)
-    ap.add_argument("--e2e-reps", type=int, default=5, help="timed repetitions of the end-to-end pool run")
+    ap.add_argument("--e2e-reps", type=int, default=8, help="timed repetitions of the end-to-end pool run")
     ap.add_argument("--verify-lanes", type=int, default=8, help="lanes whose every frame is MD5-checked against the reference")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -316,12 +316,15 @@ def main():
             t.join()
 
     run_pool(check=True)   # warm-up (untimed): CUDA context, buffer cache; output MD5-checked against the reference
+    run_pool()             # second warm-up pass in the timed configuration (no MD5 on the worker threads)
     barrier()
     e2e_frames = 0
     t0 = time.perf_counter()
     for _ in range(a.e2e_reps):
+        t_rep = time.perf_counter()
         run_pool()
         e2e_frames += sum(frames_out)
+        sys.stderr.write("e2e repetition: %d frames in %.3f s\n" % (sum(frames_out), time.perf_counter() - t_rep))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_value = shard.whole_job_rate(e2e_frames, e2e_s, dist, "cuda")

@@ -17,6 +17,7 @@
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
+#include <emmintrin.h>
 #include "frontend.h"
 #include "h264_cabac.h"
 #include "h264_cavlc_tables.h"
@@ -1634,6 +1635,96 @@ private:
 			bsv = bsh = 0xffffff00u;
 			if (left_ok) { bsv |= 0xff; d.flags |= B2_DBK_LEFT_BS4; }
 			if (top_ok) { bsh |= 0xff; d.flags |= B2_DBK_TOP_BS4; }
+		} else if (!bslice_) {
+			// P slices (one list): every pair of 4x4 blocks across an edge is 2 when either block has
+			// coefficients, else 1 when the reference pictures differ or a vector component differs by four
+			// quarter samples or more.  Done for the 16 blocks at once: one 16-bit mask per rule and
+			// direction (bit y * 4 + x = the edge on the left of / above block (x, y)), spread into the
+			// 2-bit fields of the record through two 16-entry tables.
+			const size_t w4 = (size_t)ctx_.w4;
+			const size_t g00 = (size_t)mby * 4 * w4 + (size_t)mbx * 4;
+			unsigned nzm = 0;
+			for (int i = 0; i < 16; ++i) nzm |= (unsigned)(nnz[i] != 0) << i;
+			const bool left_inter = left_ok && !kind_is_intra(ctx_.info(mbx - 1, mby).kind);
+			const bool top_inter = top_ok && !kind_is_intra(ctx_.info(mbx, mby - 1).kind);
+			unsigned two_v = (nzm | (nzm << 1)) & 0xEEEEu, two_h = (nzm | (nzm << 4)) & 0xFFF0u;
+			if (left_inter) {
+				const uint8_t *ln = ctx_.nnz_of(mbx - 1, mby);
+				for (int sg = 0; sg < 4; ++sg) two_v |= (unsigned)((ln[sg * 4 + 3] | nnz[sg * 4]) != 0) << (sg * 4);
+			}
+			if (top_inter) {
+				const uint8_t *tn = ctx_.nnz_of(mbx, mby - 1);
+				for (int sg = 0; sg < 4; ++sg) two_h |= (unsigned)((tn[12 + sg] | nnz[sg]) != 0) << sg;
+			}
+			unsigned far_v = 0, far_h = 0;
+			if (mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt != 1 || left_inter || top_inter) {
+				const int16_t *mvb = ctx_.mv[0].data();
+				const int8_t *rpb = ctx_.refpic[0].data();
+				const __m128i three = _mm_set1_epi16(3);
+				for (int y = 0; y < 4; ++y) {
+					const size_t g = g00 + y * w4;
+					const __m128i cur = _mm_loadu_si128(reinterpret_cast<const __m128i *>(mvb + g * 2));
+					int32_t rc;
+					memcpy(&rc, rpb + g, 4);
+					const __m128i rcv = _mm_cvtsi32_si128(rc);
+					// the block on the left: same row, one block earlier
+					{
+						// (first column of the picture: the same row shifted, whatever lands in block 0 is masked below)
+						const __m128i oth = mbx ? _mm_loadu_si128(reinterpret_cast<const __m128i *>(mvb + (g - 1) * 2)) : _mm_slli_si128(cur, 4);
+						const __m128i d = _mm_max_epi16(_mm_subs_epi16(cur, oth), _mm_subs_epi16(oth, cur));
+						const __m128i f = _mm_cmpgt_epi16(d, three);                          // per component
+						const int mvbits = _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpeq_epi32(f, _mm_setzero_si128()))) ^ 15;
+						int32_t ro;
+						if (mbx) memcpy(&ro, rpb + g - 1, 4);
+						else ro = (int32_t)((uint32_t)rc << 8);
+						const int rbits = (_mm_movemask_epi8(_mm_cmpeq_epi8(rcv, _mm_cvtsi32_si128(ro))) & 15) ^ 15;
+						far_v |= (unsigned)(mvbits | rbits) << (y * 4);
+					}
+					// the block above
+					if (y > 0 || mby > 0) {
+						const size_t gu = g - w4;
+						const __m128i oth = _mm_loadu_si128(reinterpret_cast<const __m128i *>(mvb + gu * 2));
+						const __m128i d = _mm_max_epi16(_mm_subs_epi16(cur, oth), _mm_subs_epi16(oth, cur));
+						const __m128i f = _mm_cmpgt_epi16(d, three);
+						const int mvbits = _mm_movemask_ps(_mm_castsi128_ps(_mm_cmpeq_epi32(f, _mm_setzero_si128()))) ^ 15;
+						int32_t ro;
+						memcpy(&ro, rpb + gu, 4);
+						const int rbits = (_mm_movemask_epi8(_mm_cmpeq_epi8(rcv, _mm_cvtsi32_si128(ro))) & 15) ^ 15;
+						far_h |= (unsigned)(mvbits | rbits) << (y * 4);
+					}
+				}
+			}
+			const unsigned mask_v = left_inter ? 0xFFFFu : 0xEEEEu, mask_h = top_inter ? 0xFFFFu : 0xFFF0u;
+			const unsigned one_v = far_v & ~two_v & mask_v, one_h = far_h & ~two_h & mask_h;
+			// vertical edges: field of (edge x, segment y) at bit x * 8 + y * 2; horizontal: (edge y, segment x) at y * 8 + x * 2
+			static const uint32_t spread_v[16] = {0x00000000u, 0x00000001u, 0x00000100u, 0x00000101u, 0x00010000u, 0x00010001u, 0x00010100u, 0x00010101u,
+			                                      0x01000000u, 0x01000001u, 0x01000100u, 0x01000101u, 0x01010000u, 0x01010001u, 0x01010100u, 0x01010101u};
+			static const uint32_t spread_h[16] = {0x00, 0x01, 0x04, 0x05, 0x10, 0x11, 0x14, 0x15, 0x40, 0x41, 0x44, 0x45, 0x50, 0x51, 0x54, 0x55};
+			for (int y = 0; y < 4; ++y) {
+				bsv |= ((spread_v[(two_v >> (4 * y)) & 15] << 1) | spread_v[(one_v >> (4 * y)) & 15]) << (2 * y);
+				bsh |= ((spread_h[(two_h >> (4 * y)) & 15] << 1) | spread_h[(one_h >> (4 * y)) & 15]) << (8 * y);
+			}
+			if (left_ok && !left_inter) { bsv |= 0xff; d.flags |= B2_DBK_LEFT_BS4; }
+			if (top_ok && !top_inter) { bsh |= 0xff; d.flags |= B2_DBK_TOP_BS4; }
+#ifdef B2_CHECK_BS
+			{
+				uint32_t cv = 0, ch = 0;
+				for (int e = 1; e < 4; ++e)
+					for (int sg = 0; sg < 4; ++sg) {
+						cv |= (uint32_t)bs_inter(g00 + sg * w4 + e - 1, g00 + sg * w4 + e, (nzm >> (sg * 4 + e - 1)) & 1, (nzm >> (sg * 4 + e)) & 1) << (e * 8 + sg * 2);
+						ch |= (uint32_t)bs_inter(g00 + (e - 1) * w4 + sg, g00 + e * w4 + sg, (nzm >> ((e - 1) * 4 + sg)) & 1, (nzm >> (e * 4 + sg)) & 1) << (e * 8 + sg * 2);
+					}
+				if (left_ok) {
+					if (!left_inter) cv |= 0xff;
+					else { const uint8_t *ln = ctx_.nnz_of(mbx - 1, mby); for (int sg = 0; sg < 4; ++sg) cv |= (uint32_t)bs_inter(g00 + sg * w4 - 1, g00 + sg * w4, ln[sg * 4 + 3] != 0, nnz[sg * 4] != 0) << (sg * 2); }
+				}
+				if (top_ok) {
+					if (!top_inter) ch |= 0xff;
+					else { const uint8_t *tn = ctx_.nnz_of(mbx, mby - 1); for (int sg = 0; sg < 4; ++sg) ch |= (uint32_t)bs_inter(g00 - w4 + sg, g00 + sg, tn[12 + sg] != 0, nnz[sg] != 0) << (sg * 2); }
+				}
+				if (cv != bsv || ch != bsh) fprintf(stderr, "bs mismatch mb %d,%d: v %08x want %08x  h %08x want %08x  (nzm %04x far_v %04x far_h %04x mc %d)\n", mbx, mby, bsv, cv, bsh, ch, nzm, far_v, far_h, mbs_[(size_t)mby * mb_w_ + mbx].mc_cnt);
+			}
+#endif
 		} else {
 			const size_t w4 = (size_t)ctx_.w4;
 			const size_t g00 = (size_t)mby * 4 * w4 + (size_t)mbx * 4;

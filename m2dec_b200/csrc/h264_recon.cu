@@ -119,8 +119,14 @@ __device__ bool block_residual(const H4Job &job, const b2_h264_mb &m, int b, int
 		int16_t l[16];
 		*reinterpret_cast<int4 *>(l) = r0;
 		*reinterpret_cast<int4 *>(l + 8) = r1;
+		// the three scale factors of the position classes, looked up once per block
+		const int sh = qp / 6, rem = qp - 6 * sh;
+		const int s0 = (int)c_norm_adjust[rem][0] << sh, s1 = (int)c_norm_adjust[rem][1] << sh, s2 = (int)c_norm_adjust[rem][2] << sh;
 #pragma unroll
-		for (int i = 0; i < 16; ++i) c[i] = l[i] * level_scale4(qp, i);
+		for (int i = 0; i < 16; ++i) {
+			const int x = i & 3, y = i >> 2;
+			c[i] = l[i] * ((!(x & 1) && !(y & 1)) ? s0 : (((x & 1) && (y & 1)) ? s1 : s2));
+		}
 	} else {
 #pragma unroll
 		for (int i = 0; i < 16; ++i) c[i] = 0;
