@@ -754,17 +754,26 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 	const uint32_t M = 0x00FF00FFu;
 #define ROWP(yy) (ref + (size_t)min(max((yy), 0), H - 1) * W)
 	if (cls == 0) {
+		// (every class: the words of the next reference row are fetched before the current row is worked on)
 		const bool fast = words_fast(x, NQ, W);
+		uint32_t nx[NQ];
+		load_words<NQ, false>(ROWP(y), W, x, fast, nx);
 		for (int r = 0; r < h; ++r) {
 			uint32_t pw[NQ];
-			load_words<NQ, false>(ROWP(y + r), W, x, fast, pw);
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) pw[q] = nx[q];
+			if (r + 1 < h) load_words<NQ, false>(ROWP(y + r + 1), W, x, fast, nx);
 			sink(r, pw);
 		}
 	} else if (cls == 1) {
 		const bool fast = words_fast(x - 2, NQ + 2, W);
+		uint32_t nx[NQ + 2];
+		load_words<NQ + 2, false>(ROWP(y), W, x - 2, fast, nx);
 		for (int r = 0; r < h; ++r) {
 			uint32_t w[NQ + 2], pw[NQ];
-			load_words<NQ + 2, false>(ROWP(y + r), W, x - 2, fast, w);
+#pragma unroll
+			for (int q = 0; q < NQ + 2; ++q) w[q] = nx[q];
+			if (r + 1 < h) load_words<NQ + 2, false>(ROWP(y + r + 1), W, x - 2, fast, nx);
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
 				uint32_t b = hhalf4(&w[q]);
@@ -780,9 +789,13 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 		for (int q = 0; q < NQ; ++q)
 #pragma unroll
 			for (int j = 0; j < 6; ++j) E[q][j] = O[q][j] = 0;
+		uint32_t nx[NQ];
+		load_words<NQ, false>(ROWP(y - 2), W, x, fast, nx);
 		for (int k = 0; k < h + 5; ++k) {
 			uint32_t w[NQ], pw[NQ];
-			load_words<NQ, false>(ROWP(y - 2 + k), W, x, fast, w);
+#pragma unroll
+			for (int q = 0; q < NQ; ++q) w[q] = nx[q];
+			if (k + 1 < h + 5) load_words<NQ, false>(ROWP(y - 1 + k), W, x, fast, nx);
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -810,9 +823,13 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 #pragma unroll
 			for (int j = 0; j < 4; ++j) bq[q][j] = 0;
 		}
+		uint32_t nx[NQ + 2];
+		load_words<NQ + 2, false>(ROWP(y - 2), W, x - 2, fast, nx);
 		for (int k = 0; k < h + 5; ++k) {
 			uint32_t w[NQ + 2], pw[NQ];
-			load_words<NQ + 2, false>(ROWP(y - 2 + k), W, x - 2, fast, w);
+#pragma unroll
+			for (int q = 0; q < NQ + 2; ++q) w[q] = nx[q];
+			if (k + 1 < h + 5) load_words<NQ + 2, false>(ROWP(y - 1 + k), W, x - 2, fast, nx);
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -844,9 +861,13 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 #pragma unroll
 		for (int j = 0; j < 6; ++j) E[j] = O[j] = 0;
 		const uint32_t T0 = (1u & 255u) | ((uint32_t)(-5 & 255) << 8), T1 = 20u | (20u << 8), T2 = (uint32_t)(-5 & 255) | (1u << 8);
+		uint32_t nx[3];
+		load_words<3, false>(ROWP(y - 2), W, x - 2, fast, nx);
 		for (int k = 0; k < h + 5; ++k) {
 			uint32_t w[3];
-			load_words<3, false>(ROWP(y - 2 + k), W, x - 2, fast, w);
+#pragma unroll
+			for (int q = 0; q < 3; ++q) w[q] = nx[q];
+			if (k + 1 < h + 5) load_words<3, false>(ROWP(y - 1 + k), W, x - 2, fast, nx);
 			int hb[4];
 			hfilter4(w, hb);
 #pragma unroll
@@ -898,9 +919,13 @@ __device__ __forceinline__ void i5_chroma(const uint8_t *__restrict__ refc, int 
 	uint32_t pcb[NQ], pcr[NQ];
 #pragma unroll
 	for (int q = 0; q < NQ; ++q) pcb[q] = pcr[q] = 0;
+	uint32_t nx[NQ + 1];
+	load_words<NQ + 1, true>(refc + (size_t)min(max(y, 0), CH - 1) * W, W, x, fast, nx);
 	for (int k = 0; k <= rows; ++k) {
 		uint32_t w[NQ + 1], pw[NQ];
-		load_words<NQ + 1, true>(refc + (size_t)min(max(y + k, 0), CH - 1) * W, W, x, fast, w);
+#pragma unroll
+		for (int q = 0; q < NQ + 1; ++q) w[q] = nx[q];
+		if (k < rows) load_words<NQ + 1, true>(refc + (size_t)min(max(y + k + 1, 0), CH - 1) * W, W, x, fast, nx);
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) {
 			const uint32_t a = w[q], b = __funnelshift_r(w[q], w[q + 1], 16);
