@@ -1716,16 +1716,17 @@ struct RowSync {
 	}
 };
 
-struct DbkTables { uint8_t alpha[52], beta[52], tc0[52][4]; };
+struct alignas(4) DbkTables { uint8_t alpha[52], beta[52], tc0[52][4]; };
 
 // One edge of one line, without data-dependent branches for the common case (bS < 4): the filtered
 // values are computed for every lane and selected by the line's own conditions, so lanes that differ
 // in strength, thresholds or sample activity stay converged.  `on` = this lane filters this edge at all.
+template <bool MAY_BS4>
 __device__ __forceinline__ void dbk_filter(int *v, const int q, const bool on, const int bs, const int alpha, const int beta, const int tc0, const bool luma) {
 	const int p0 = v[q - 1], p1 = v[q - 2], p2 = v[q - 3], q0 = v[q], q1 = v[q + 1], q2 = v[q + 2];
 	const bool act = on && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
 	const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
-	const bool normal = act && bs < 4;
+	const bool normal = act && (!MAY_BS4 || bs < 4);
 	{
 		const int tc = luma ? tc0 + ap + aq : tc0 + 1, avg = (p0 + q0 + 1) >> 1;
 		const int np1 = p1 + min(max((p2 + avg - 2 * p1) >> 1, -tc0), tc0);
@@ -1735,7 +1736,8 @@ __device__ __forceinline__ void dbk_filter(int *v, const int q, const bool on, c
 		if (normal && aq) v[q + 1] = nq1;
 		if (normal) { v[q - 1] = clip255(p0 + delta); v[q] = clip255(q0 - delta); }
 	}
-	if (__any_sync(__activemask(), act && bs == 4)) {
+	// bS 4 exists on macroblock edges only (edge 0): the inner edges are straight-line code
+	if (MAY_BS4 && __any_sync(__activemask(), act && bs == 4)) {
 		if (act && bs == 4) {
 			const bool strong = luma && abs(p0 - q0) < (alpha >> 2) + 2;
 			if (strong && ap) {
@@ -1762,19 +1764,27 @@ __device__ __forceinline__ void dbk_filter(int *v, const int q, const bool on, c
 // direction, seg = 4-sample segment of this line, qpc / qpn = QP of this MB / of the MB across edge 0
 __device__ __forceinline__ void dbk_line(int *v, const DbkTables &tb, uint32_t bits, int seg, bool luma, bool edge0_ok, bool edge0_bs4,
                                          int qpc, int qpn, int aoff, int boff) {
+	// thresholds of the inner edges (this macroblock's QP) and of edge 0 (mean with the neighbour's)
+	const int iai = min(max(qpc + aoff, 0), 51), ibi = min(max(qpc + boff, 0), 51);
+	const int qp0 = (qpc + qpn + 1) >> 1;
+	const int ia0 = min(max(qp0 + aoff, 0), 51), ib0 = min(max(qp0 + boff, 0), 51);
+	const int alpha_i = tb.alpha[iai], beta_i = tb.beta[ibi], alpha_0 = tb.alpha[ia0], beta_0 = tb.beta[ib0];
+	const uint32_t tc_i = *reinterpret_cast<const uint32_t *>(tb.tc0[iai]), tc_0 = *reinterpret_cast<const uint32_t *>(tb.tc0[ia0]);
+	const uint32_t lbits = bits >> (2 * seg);       // this line's strength of edge e in bits 8e, 8e+1
+	{
+		int bs = lbits & 3;
+		const bool on = bs != 0 && edge0_ok;
+		if (edge0_bs4) bs = 4;
+		if (__any_sync(__activemask(), on))
+			dbk_filter<true>(v, 4, on && alpha_0 != 0, bs, alpha_0, beta_0, (tc_0 >> (8 * (bs < 4 ? (bs ? bs - 1 : 0) : 3))) & 255, luma);
+	}
+	if (!(bits & 0xffffff00u)) return;               // no inner edge of this macroblock has a strength
 #pragma unroll
-	for (int i = 0; i < 4; ++i) {
+	for (int i = 1; i < 4; ++i) {
 		const int e = luma ? i : 2 * i;                 // chroma edges 0 / 1 of the register layout are luma edges 0 / 2
-		// whole edge without strength for every lane (common for inner edges): skip it, warp-uniformly
-		const uint32_t ebits = e < 4 ? (bits >> (8 * e)) & 255u : 0u;
-		int bs = (ebits >> (2 * seg)) & 3;
-		bool on = bs != 0 && !(e == 0 && !edge0_ok) && (luma || i < 2);
-		if (!__any_sync(__activemask(), on)) continue;
-		if (e == 0 && edge0_bs4) bs = 4;
-		const int qp = e ? qpc : (qpc + qpn + 1) >> 1;
-		const int ia = min(max(qp + aoff, 0), 51), ib = min(max(qp + boff, 0), 51);
-		const int alpha = tb.alpha[ia];
-		dbk_filter(v, 4 + 4 * i, on && alpha != 0, bs, alpha, tb.beta[ib], tb.tc0[ia][bs < 4 ? (bs ? bs - 1 : 0) : 3], luma);
+		const int bs = e < 4 ? (lbits >> (8 * e)) & 3 : 0;
+		const bool on = bs != 0 && (luma || i < 2);
+		dbk_filter<false>(v, 4 + 4 * i, on && alpha_i != 0, bs, alpha_i, beta_i, (tc_i >> (8 * (bs ? bs - 1 : 0))) & 255, luma);
 	}
 }
 
