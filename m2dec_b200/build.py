@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [NVCC] + ARCH + common + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [NVCC] + ARCH + common + os.environ.get("B2_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for cmd, p in procs:

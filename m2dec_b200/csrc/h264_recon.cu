@@ -1945,10 +1945,14 @@ __device__ void deblock_chunk(const H4Job &job, const DbkTables &tb, DbkTile &tl
 // ticket and is already running: no deadlock whatever the CTA scheduling order.
 // ------------------------------------------------------------------------------------------------
 
-constexpr int WAVE_WARPS = 8;
+#ifndef B2_WAVE_WARPS
+#define B2_WAVE_WARPS 4
+#endif
+constexpr int WAVE_WARPS = B2_WAVE_WARPS;
+constexpr int WAVE_CTAS_DBK = 24 / WAVE_WARPS, WAVE_CTAS_INTRA = 16 / WAVE_WARPS;    // resident CTAs per SM (register budget)
 
 template <int PHASE>   // 1 intra, 2 deblock
-__global__ void __launch_bounds__(32 * WAVE_WARPS, PHASE == 2 ? 3 : 2)
+__global__ void __launch_bounds__(32 * WAVE_WARPS, PHASE == 2 ? WAVE_CTAS_DBK : WAVE_CTAS_INTRA)
 h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
 	__shared__ union { IntraTile intra; DbkTile dbk; } s_tile[WAVE_WARPS];
 	__shared__ DbkTables s_tb;
@@ -2026,7 +2030,7 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 // themselves and that it may read (availability bits) -- inter neighbours were finished by the
 // kernel before.  Chunks are handed out in raster order, so a neighbour always belongs to a chunk
 // with an earlier ticket: no deadlock as long as every CTA of the grid is resident (persistent grid).
-__global__ void __launch_bounds__(32 * WAVE_WARPS, 2)
+__global__ void __launch_bounds__(32 * WAVE_WARPS, WAVE_CTAS_INTRA)
 h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
 	__shared__ IntraTile s_tile[WAVE_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2101,7 +2105,7 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 			B2_CUDA_OK(cudaMemsetAsync(area, 0, h264_sync_bytes(n_jobs, mb_w, mb_h), stream));
 			const int chunks = n_jobs * ((mb_w * mb_h + 31) / 32);
 			int ctas = (chunks + WAVE_WARPS - 1) / WAVE_WARPS;
-			if (ctas > 148 * 2) ctas = 148 * 2;      // persistent: every CTA resident (2 per SM)
+			if (ctas > 148 * WAVE_CTAS_INTRA) ctas = 148 * WAVE_CTAS_INTRA;      // persistent: every CTA resident
 			h264_intra_sparse_kernel<<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 			if (launches) ++*launches;
 			B2_CUDA_OK(cudaGetLastError());
@@ -2109,7 +2113,7 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		}
 		B2_CUDA_OK(cudaMemsetAsync(area, 0, (32 + (size_t)n_jobs * mb_h) * sizeof(int), stream));
 		int ctas = n_jobs * ((mb_h + WAVE_WARPS - 1) / WAVE_WARPS);
-		int cap = 148 * 6;
+		int cap = 148 * 2 * WAVE_CTAS_DBK;
 		if (ctas > cap) ctas = cap;
 		if (phase == 1) h264_wave_kernel<1><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 		else h264_wave_kernel<2><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
