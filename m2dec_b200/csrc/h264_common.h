@@ -160,8 +160,9 @@ public:
 		m.slice = (uint16_t)cur_slice;
 		for (int y = 0; y < 4; ++y) {
 			size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4;
-			memset(&ref[0][g], -2, 4);
-			memset(&ref[1][g], -2, 4);
+			const uint32_t undecoded = 0xFEFEFEFEu;       // -2 in every block
+			memcpy(&ref[0][g], &undecoded, 4);
+			memcpy(&ref[1][g], &undecoded, 4);
 			if (cabac)
 				for (int l = 0; l < 2; ++l) {
 					memset(&mvd[l][g * 2], 0, 8);
@@ -182,12 +183,28 @@ public:
 	// fill a w4 x h4 partition (4-pel units) of the current MB
 	void set_motion(int list, int mbx, int mby, int x4, int y4, int pw, int ph, int refidx, int pic, int mvx, int mvy) {
 		const uint32_t packed = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
-		for (int y = y4; y < y4 + ph; ++y) {
-			size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x4;
-			memset(&ref[list][g], refidx, pw);
-			memset(&refpic[list][g], pic, pw);
-			uint32_t *m = reinterpret_cast<uint32_t *>(&mv[list][g * 2]);
-			for (int x = 0; x < pw; ++x) m[x] = packed;
+		size_t g = (size_t)(mby * 4 + y4) * w4 + mbx * 4 + x4;
+		int8_t *rp = &ref[list][g], *pp = &refpic[list][g];
+		uint32_t *m = reinterpret_cast<uint32_t *>(&mv[list][g * 2]);
+		// pw is 1, 2 or 4: fixed-size stores instead of memset calls
+		if (pw == 4) {
+			const uint32_t r4 = 0x01010101u * (uint8_t)refidx, p4 = 0x01010101u * (uint8_t)pic;
+			for (int y = 0; y < ph; ++y, rp += w4, pp += w4, m += w4) {
+				memcpy(rp, &r4, 4);
+				memcpy(pp, &p4, 4);
+				m[0] = m[1] = m[2] = m[3] = packed;
+			}
+		} else if (pw == 2) {
+			const uint16_t r2 = (uint16_t)(0x0101u * (uint8_t)refidx), p2 = (uint16_t)(0x0101u * (uint8_t)pic);
+			for (int y = 0; y < ph; ++y, rp += w4, pp += w4, m += w4) {
+				memcpy(rp, &r2, 2);
+				memcpy(pp, &p2, 2);
+				m[0] = m[1] = packed;
+			}
+		} else {
+			for (int y = 0; y < ph; ++y, rp += w4, pp += w4, m += w4) {
+				for (int x = 0; x < pw; ++x) { rp[x] = (int8_t)refidx; pp[x] = (int8_t)pic; m[x] = packed; }
+			}
 		}
 	}
 	void set_intra_motion(int mbx, int mby) {

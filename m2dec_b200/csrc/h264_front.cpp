@@ -924,14 +924,13 @@ private:
 
 	// one mb->inter_pred call: ref[lx] < 0 = list unused
 	void emit_mc(b2_h264_mb &m, int x4, int y4, int pw, int ph, const int ref[2], const int mv[2][2]) {
-		b2_h264_mc r;
-		memset(&r, 0, sizeof(r));
+		// default prediction: weights 1, offsets 0, both lists unused
+		static const b2_h264_mc proto = {0, 0, {-1, -1}, {-1, -1}, 0, 0, {{0, 0}, {0, 0}}, {{1, 1, 1}, {1, 1, 1}}, {{0, 0, 0}, {0, 0, 0}}, {0, 0, 0, 0}};
+		b2_h264_mc r = proto;
 		r.pos = (uint8_t)((y4 << 2) | x4);
 		r.size = (uint8_t)((ph << 4) | pw);
 		for (int lx = 0; lx < 2; ++lx) {
 			r.ref_idx[lx] = (int8_t)ref[lx];
-			r.ref_frame[lx] = -1;
-			for (int c = 0; c < 3; ++c) { r.w[lx][c] = 1; r.o[lx][c] = 0; }
 			if (ref[lx] < 0) continue;
 			int f = ref_frame_of(lx, ref[lx]);
 			r.ref_frame[lx] = (int8_t)(f < 0 ? cur_frame_ : f);
@@ -1087,11 +1086,12 @@ private:
 		memset(r, 0, 32);
 		return r;
 	}
-	// give the last record back (nothing was coded in it)
-	inline void drop_record() { coef_used_ -= 16; }
 
 	// residual_block_cavlc (7.3.5.3.2 / 9.2): returns total_coeff; levels go to out[scan[...]]
-	int residual_block(int nc, int max_coeff, int16_t *out, const uint8_t *scan, int scan_ofs) {
+	// out() is asked for the destination only once the block turns out to have coefficients, so that
+	// empty blocks (most of them) cost neither a record nor its clearing
+	template <class Out>
+	inline int residual_block(int nc, int max_coeff, Out &&out_of, const uint8_t *scan, int scan_ofs) {
 		const H264Tables &t = tables();
 		const Vlc &ct = nc < 0 ? t.coeff_token[4] : (nc < 2 ? t.coeff_token[0] : (nc < 4 ? t.coeff_token[1] : (nc < 8 ? t.coeff_token[2] : t.coeff_token[3])));
 		if (nc >= 0 && nc < 2 && br_.peek(1)) { br_.skip(1); return 0; }
@@ -1100,6 +1100,7 @@ private:
 		int total = tok >> 2, t1 = tok & 3;
 		if (total == 0) return 0;
 		if (total > max_coeff) throw BitError();
+		int16_t *out = out_of();
 		int level[16];
 		for (int i = 0; i < t1; ++i) level[i] = br_.get1() ? -1 : 1;
 		int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
@@ -1174,20 +1175,22 @@ private:
 		for (int k = 0; k < 16; ++k) {
 			int x4 = blk_x[k], y4 = blk_y[k];
 			if (!(cbp & (1 << (k >> 2)))) { nnz[y4 * 4 + x4] = 0; continue; }
-			int16_t *rec = new_record();
 			int total;
 			if (cabac_) {
 				int16_t lv[16];
 				memset(lv, 0, sizeof(lv));
 				total = cs_.residual(i16 ? 1 : 2, ctx_.cabac_inc_cbf_luma(x4, y4, intra), lv, i16 ? 15 : 16);
-				if (total) for (int i = 0; i < (i16 ? 15 : 16); ++i) rec[zigzag4x4[i + (i16 ? 1 : 0)]] = lv[i];
+				if (total) {
+					int16_t *rec = new_record();
+					for (int i = 0; i < (i16 ? 15 : 16); ++i) rec[zigzag4x4[i + (i16 ? 1 : 0)]] = lv[i];
+				}
 			} else {
 				int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
+				auto rec = [this]() { return new_record(); };
 				total = i16 ? residual_block(nc, 15, rec, zigzag4x4, 1) : residual_block(nc, 16, rec, zigzag4x4, 0);
 			}
 			nnz[y4 * 4 + x4] = (uint8_t)total;
 			if (total) m.nz |= 1u << (1 + k);
-			else drop_record();
 		}
 	}
 
@@ -1206,7 +1209,8 @@ private:
 				n = cs_.residual(3, ctx_.cabac_inc_cbf_dc(MBF_CBF_CB_DC << c, intra), dc + c * 4, 4);
 				if (n) info.cflags |= (uint8_t)(MBF_CBF_CB_DC << c);
 			} else {
-				n = residual_block(-1, 4, dc + c * 4, scan_dc, 0);
+				int16_t *dst = dc + c * 4;
+				n = residual_block(-1, 4, [dst]() { return dst; }, scan_dc, 0);
 			}
 			any |= n;
 		}
@@ -1218,20 +1222,21 @@ private:
 			for (int c = 0; c < 2; ++c)
 				for (int b = 0; b < 4; ++b) {
 					int x = b & 1, y = b >> 1;
-					int16_t *rec = new_record();
 					int total;
 					if (cabac_) {
 						int16_t lv[16];
 						memset(lv, 0, sizeof(lv));
 						total = cs_.residual(4, ctx_.cabac_inc_cbf_chroma_ac(c, x, y, intra), lv, 15);
-						if (total) for (int i = 0; i < 15; ++i) rec[zigzag4x4[i + 1]] = lv[i];
+						if (total) {
+							int16_t *rec = new_record();
+							for (int i = 0; i < 15; ++i) rec[zigzag4x4[i + 1]] = lv[i];
+						}
 					} else {
 						int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, x, y, slice_num_);
-						total = residual_block(nc, 15, rec, zigzag4x4, 1);
+						total = residual_block(nc, 15, [this]() { return new_record(); }, zigzag4x4, 1);
 					}
 					nnz[16 + c * 4 + b] = (uint8_t)total;
 					if (total) m.nz |= 1u << (18 + c * 4 + b);
-					else drop_record();
 				}
 		}
 	}
@@ -1361,7 +1366,7 @@ private:
 				}
 			} else {
 				int nc = ctx_.cavlc_nc(mbx, mby, 0, 0, 0, slice_num_);
-				ndc = residual_block(nc, 16, dc, zigzag4x4, 0);
+				ndc = residual_block(nc, 16, [&dc]() { return dc; }, zigzag4x4, 0);
 			}
 			if (ndc) {
 				memcpy(new_record(), dc, sizeof(dc));
