@@ -964,8 +964,21 @@ private:
 			if (bi) centre |= frac_class(r.mv[1][0] & 3, r.mv[1][1] & 3) >= 4;
 			const int wide = pw >= 2 && !centre;
 			const int cls = fc + 6 * wide, n = wide ? pw >> 1 : pw;
-			std::vector<uint32_t> &bucket = items_[cls * 3 + (ph == 4 ? 2 : ph - 1)];
-			for (int k = 0; k < n; ++k) bucket.push_back((uint32_t)mb_addr_ | ((uint32_t)m.mc_cnt << 20) | ((uint32_t)k << 24) | ((uint32_t)cls << 26));
+			// strips whose reference window (6-tap margins included) leaves the picture take the clamped loads: they go
+			// to buckets of their own (the last 36), so that a warp of the kernel is all fast path or all clamped
+			const int W = mb_w_ * 16, H = mb_h_ * 16, sw = wide ? 8 : 4;
+			const int mbx = mb_addr_ % mb_w_, mby = mb_addr_ / mb_w_;
+			const int hidx = ph == 4 ? 2 : ph - 1;
+			for (int k = 0; k < n; ++k) {
+				const int px = mbx * 16 + x4 * 4 + k * sw, py = mby * 16 + y4 * 4;
+				bool edge = false;
+				for (int lx = 0; lx < 2; ++lx) {
+					if (ref[lx] < 0) continue;
+					const int x0 = px + (r.mv[lx][0] >> 2), y0 = py + (r.mv[lx][1] >> 2);
+					edge |= x0 - 6 < 0 || x0 + sw + 12 > W || y0 - 3 < 0 || y0 + ph * 4 + 4 > H;
+				}
+				items_[(edge ? 36 : 0) + cls * 3 + hidx].push_back((uint32_t)mb_addr_ | ((uint32_t)m.mc_cnt << 20) | ((uint32_t)k << 24) | ((uint32_t)cls << 26));
+			}
 		}
 		mcs_.push_back(r);
 		m.mc_cnt++;
@@ -1837,7 +1850,7 @@ private:
 	std::vector<b2_h264_mb> mbs_;
 	std::vector<b2_h264_dbk> dbk_;
 	std::vector<b2_h264_mc> mcs_;
-	std::vector<uint32_t> items_[36], items_all_;      // inter work items per (class, height) bucket / concatenated
+	std::vector<uint32_t> items_[72], items_all_;      // inter work items per (class, height) bucket / concatenated
 	std::vector<int16_t> coefs_;
 	size_t coef_used_ = 0;
 	uint32_t n_intra_;

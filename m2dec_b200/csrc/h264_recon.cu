@@ -939,148 +939,47 @@ __device__ __forceinline__ void i5_chroma(const uint8_t *__restrict__ refc, int 
 	}
 }
 
-// One strip.  rs = this thread's residual scratch (64 + 2 int16); rows = this thread's column of the
-// row buffer (word k at rows[k * I5_THREADS]): the class-specific predictors only park their rows there,
-// and one finishing loop per plane adds weights and residual, so that code exists once.
+// One strip, in phases.  The class-specific predictors only park their rows in shared memory (rows = this
+// thread's column of the row buffer, word k at rows[k * I5_THREADS]); weights and the second list are
+// folded in there; the residual is then added by the whole warp at once: every lane lists the coded
+// blocks of its strip in a per-warp queue and the lanes take the queued blocks 32 at a time (dequantise,
+// transform, add into the owner's parked rows), so that the transform runs with full warps although only
+// a quarter of the blocks carries a residual.  Strips of 8x8-transform macroblocks (rare) keep their
+// residual in the owning thread.
+constexpr int I5_QUEUE = 256;         // queue entries per warp: 32 lanes x (up to 8 luma blocks | 2 chroma block rows)
+
 template <int NQ>
-__device__ void i5_strip(const H4Job &job, const b2_h264_mb &m, const b2_h264_mc &mc, int mbx, int mby, int x4, int y4, int h4, int16_t *rs,
-                         uint32_t *rows) {
-	const int W = job.mb_w * 16, H = job.mb_h * 16;
-	const size_t luma_size = (size_t)W * H;
-	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
-	uint8_t *dst_c = dst_y + luma_size;
-	const int px0 = mbx * 16 + x4 * 4, py0 = mby * 16 + y4 * 4, h = h4 * 4;
-	const bool bi = mc.ref_frame[0] >= 0 && mc.ref_frame[1] >= 0;
-	const int first = mc.ref_frame[0] >= 0 ? 0 : 1;
-	const bool t8 = m.flags & B2_H4_T8x8;
-	const bool plain_w = !(mc.log2wd_y | mc.log2wd_c | (mc.w[0][0] ^ 1) | (mc.w[0][1] ^ 1) | (mc.w[0][2] ^ 1) | (mc.w[1][0] ^ 1) | (mc.w[1][1] ^ 1) | (mc.w[1][2] ^ 1) |
-	                       mc.o[0][0] | mc.o[0][1] | mc.o[0][2] | mc.o[1][0] | mc.o[1][1] | mc.o[1][2]);      // default prediction for whatever lists are used
-	auto park = [&](int r, const uint32_t *pw) {
+__device__ __forceinline__ void i5_first_list(const uint8_t *__restrict__ ref, uint8_t *dst_y, uint8_t *dst_c, int W, int H, int px0, int py0,
+                                              int cyp, int mvx, int mvy, int h) {
+	// first list of a bi-predicted strip: straight to the destination, the second list is combined with it
+	i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, [&](int r, const uint32_t *pw) {
+#pragma unroll
+		for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(dst_y + (size_t)(py0 + r) * W + px0 + 4 * q) = pw[q];
+	});
+	i5_chroma<NQ>(ref + (size_t)W * H, W, H >> 1, px0, cyp, mvx, mvy, h / 2, [&](int r, const uint32_t *pw) {
+#pragma unroll
+		for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(dst_c + (size_t)(cyp + r) * W + px0 + 4 * q) = pw[q];
+	});
+}
+
+template <int NQ>
+__device__ __forceinline__ void i5_park_luma(const uint8_t *__restrict__ ref, int W, int H, int px0, int py0, int mvx, int mvy, int h, uint32_t *rows) {
+	i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, [&](int r, const uint32_t *pw) {
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) rows[(r * NQ + q) * I5_THREADS] = pw[q];
-	};
-	int pass = 0;
-	for (int l = 0; l < 2; ++l) {
-		if (mc.ref_frame[l] < 0) continue;
-		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[l];
-		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1];
-		const bool last = !bi || pass == 1;
-		// ---- luma -------------------------------------------------------------------------------------
-		i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, park);
-		{
-			uint32_t coded = 0;                          // which of the strip's blocks of this row group have a residual
-			for (int r = 0; r < h; ++r) {
-				uint8_t *drow = dst_y + (size_t)(py0 + r) * W + px0;
-				if (!last) {
+	});
+}
+template <int NQ>
+__device__ __forceinline__ void i5_park_chroma(const uint8_t *__restrict__ refc, int W, int CH, int px0, int cyp, int mvx, int mvy, int rows_n, uint32_t *rows) {
+	i5_chroma<NQ>(refc, W, CH, px0, cyp, mvx, mvy, rows_n, [&](int r, const uint32_t *pw) {
 #pragma unroll
-					for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(drow + 4 * q) = rows[(r * NQ + q) * I5_THREADS];
-					continue;
-				}
-				if (t8) {
-					if ((r & 7) == 0) {
-						const int q8 = ((y4 + (r >> 2)) >> 1) * 2 + (x4 >> 1);
-						coded = (m.nz >> (1 + 4 * q8)) & 1 ? 0xfu : 0u;
-						if (coded) block_residual8x8(job, m, q8, reinterpret_cast<int16_t(*)[16]>(rs) - 4 * q8);
-					}
-				} else if ((r & 3) == 0) {
-					coded = 0;
-					for (int q = 0; q < NQ; ++q) {
-						const int b = c_r2b[(y4 + (r >> 2)) * 4 + x4 + q];
-						if (((m.nz >> (1 + b)) & 1) && block_residual(job, m, b, rs + q * 16)) coded |= 1u << q;
-					}
-				}
-#pragma unroll
-				for (int q = 0; q < NQ; ++q) {
-					uint32_t w = rows[(r * NQ + q) * I5_THREADS];
-					const int sb = t8 ? ((r >> 2) & 1) * 2 + (x4 & 1) + q : q;      // narrow strips may sit in the right half of an 8x8 block
-					const bool has = (coded >> sb) & 1;
-					if (bi && plain_w) w = __vavgu4(*reinterpret_cast<const uint32_t *>(drow + 4 * q), w);
-					if (has || !plain_w) {
-						int p[4];
-#pragma unroll
-						for (int i = 0; i < 4; ++i) p[i] = (w >> (8 * i)) & 255;
-						if (!plain_w) {
-							if (bi) {
-								const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
-								const int lw = mc.log2wd_y, o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
-#pragma unroll
-								for (int i = 0; i < 4; ++i) p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][0] + p[i] * mc.w[1][0] + (1 << lw)) >> (lw + 1)) + o);
-							} else {
-								const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
-#pragma unroll
-								for (int i = 0; i < 4; ++i) p[i] = clip255(((p[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
-							}
-						}
-						if (has) {
-							const int16_t *res = rs + sb * 16 + (r & 3) * 4;
-#pragma unroll
-							for (int i = 0; i < 4; ++i) p[i] = clip255(p[i] + res[i]);
-						}
-						w = pack4(p[0], p[1], p[2], p[3]);
-					}
-					*reinterpret_cast<uint32_t *>(drow + 4 * q) = w;
-				}
-			}
-		}
-		// ---- chroma: NQ words (Cb Cr Cb Cr) per row, h / 2 rows -------------------------------------------
-		const int cy0 = y4 * 2, cx0 = x4 * 2;            // chroma sample position inside the MB
-		i5_chroma<NQ>(ref + luma_size, W, H >> 1, px0, mby * 8 + cy0, mvx, mvy, h / 2, park);
-		{
-			uint32_t coded = 0;
-			for (int r = 0; r < h / 2; ++r) {
-				const int cy = cy0 + r;
-				uint8_t *drow = dst_c + (size_t)(mby * 8 + cy) * W + px0;
-				if (!last) {
-#pragma unroll
-					for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(drow + 4 * q) = rows[(r * NQ + q) * I5_THREADS];
-					continue;
-				}
-				if (r == 0 || (cy & 3) == 0) {
-					const int cblk = (cy >> 2) * 2 + (cx0 >> 2);
-					coded = 0;
-					if ((m.nz >> 17) & 0x1ff)                   // any chroma record at all
-						for (int comp = 0; comp < 2; ++comp)
-							if (block_residual(job, m, 16 + comp * 4 + cblk, rs + comp * 16)) coded |= 1u << comp;
-				}
-#pragma unroll
-				for (int q = 0; q < NQ; ++q) {
-					uint32_t w = rows[(r * NQ + q) * I5_THREADS];
-					if (bi && plain_w) w = __vavgu4(*reinterpret_cast<const uint32_t *>(drow + 4 * q), w);
-					if (coded || !plain_w) {
-						int p[4];
-#pragma unroll
-						for (int i = 0; i < 4; ++i) p[i] = (w >> (8 * i)) & 255;
-						if (!plain_w) {
-							if (bi) {
-								const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow + 4 * q);
-								const int lc = mc.log2wd_c;
-#pragma unroll
-								for (int i = 0; i < 4; ++i) {
-									const int c = 1 + (i & 1);
-									p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][c] + p[i] * mc.w[1][c] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][c] + mc.o[1][c] + 1) >> 1));
-								}
-							} else {
-								const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
-#pragma unroll
-								for (int i = 0; i < 4; ++i) {
-									const int c = 1 + (i & 1);
-									p[i] = clip255(((p[i] * mc.w[first][c] + rc) >> lc) + mc.o[first][c]);
-								}
-							}
-						}
-#pragma unroll
-						for (int i = 0; i < 4; ++i) {
-							const int comp = i & 1, cx = cx0 + 2 * q + (i >> 1);
-							if ((coded >> comp) & 1) p[i] = clip255(p[i] + rs[comp * 16 + (cy & 3) * 4 + (cx & 3)]);
-						}
-						w = pack4(p[0], p[1], p[2], p[3]);
-					}
-					*reinterpret_cast<uint32_t *>(drow + 4 * q) = w;
-				}
-			}
-		}
-		++pass;
-	}
+		for (int q = 0; q < NQ; ++q) rows[(r * NQ + q) * I5_THREADS] = pw[q];
+	});
+}
+
+// four samples + four residuals, clipped
+__device__ __forceinline__ uint32_t add_res4(uint32_t w, int r0, int r1, int r2, int r3) {
+	return pack4(clip255((int)(w & 255) + r0), clip255((int)((w >> 8) & 255) + r1), clip255((int)((w >> 16) & 255) + r2), clip255((int)(w >> 24) + r3));
 }
 
 __global__ void __launch_bounds__(I5_THREADS, 2)
@@ -1089,21 +988,223 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	extern __shared__ __align__(16) uint8_t s_dyn[];
 	uint32_t (*s_rows)[I5_THREADS] = reinterpret_cast<uint32_t(*)[I5_THREADS]>(s_dyn);                       // per thread: up to 16 rows x 2 words of prediction
 	int16_t (*s_rs)[66] = reinterpret_cast<int16_t(*)[66]>(s_dyn + sizeof(uint32_t) * 32 * I5_THREADS);     // per thread: residual scratch
+	uint16_t (*s_queue)[I5_QUEUE] = reinterpret_cast<uint16_t(*)[I5_QUEUE]>(s_dyn + sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS);
 	const H4Job job = jobs[blockIdx.y];
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t it = blockIdx.x * I5_THREADS + tid;
-	if (it >= job.n_items) return;
+	// whole warps beyond the list leave; in the list's last warp the lanes without an item stay (as strips of
+	// height 0) for the warp-wide parts
+	if ((it & ~31u) >= job.n_items) return;
+	const bool valid = it < job.n_items;
 	// the list comes sorted by (class, height) from the host: a warp runs one interpolation path
-	const uint32_t item = __ldg(job.items + it);
+	const uint32_t item = __ldg(job.items + (valid ? it : job.n_items - 1));
 	const int mb = item & 0xfffff, ri = (item >> 20) & 15, k = (item >> 24) & 3, wide = ((item >> 26) & 15) >= 6;
 	const b2_h264_mb m = job.mbs[mb];
 	const b2_h264_mc *mcp = job.mcs + m.mc_idx + ri;
 	b2_h264_mc mc;
 	reinterpret_cast<int4 *>(&mc)[0] = __ldg(reinterpret_cast<const int4 *>(mcp));
 	reinterpret_cast<int4 *>(&mc)[1] = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
-	const int x4 = (mc.pos & 3) + (wide ? 2 * k : k), y4 = mc.pos >> 2, h4 = mc.size >> 4;
-	if (wide) i5_strip<2>(job, m, mc, mb % job.mb_w, mb / job.mb_w, x4, y4, h4, s_rs[tid], &s_rows[0][tid]);
-	else i5_strip<1>(job, m, mc, mb % job.mb_w, mb / job.mb_w, x4, y4, h4, s_rs[tid], &s_rows[0][tid]);
+	const int nq = wide ? 2 : 1;
+	const int x4 = (mc.pos & 3) + (wide ? 2 * k : k), y4 = mc.pos >> 2, h4 = valid ? mc.size >> 4 : 0, h = h4 * 4;
+	const int mbx = mb % job.mb_w, mby = mb / job.mb_w;
+	const int W = job.mb_w * 16, H = job.mb_h * 16;
+	const size_t luma_size = (size_t)W * H;
+	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
+	uint8_t *dst_c = dst_y + luma_size;
+	const int px0 = mbx * 16 + x4 * 4, py0 = mby * 16 + y4 * 4;
+	const int cy0 = y4 * 2, cx0 = x4 * 2, cyp = mby * 8 + cy0;         // chroma sample position inside the MB / chroma row in the picture
+	const bool bi = mc.ref_frame[0] >= 0 && mc.ref_frame[1] >= 0;
+	const int first = mc.ref_frame[0] >= 0 ? 0 : 1, lastl = bi ? 1 : first;
+	const bool t8 = m.flags & B2_H4_T8x8;
+	const bool plain_w = !(mc.log2wd_y | mc.log2wd_c | (mc.w[0][0] ^ 1) | (mc.w[0][1] ^ 1) | (mc.w[0][2] ^ 1) | (mc.w[1][0] ^ 1) | (mc.w[1][1] ^ 1) | (mc.w[1][2] ^ 1) |
+	                       mc.o[0][0] | mc.o[0][1] | mc.o[0][2] | mc.o[1][0] | mc.o[1][1] | mc.o[1][2]);      // default prediction for whatever lists are used
+	uint32_t *rows = &s_rows[0][tid];
+	int16_t *rs = s_rs[tid];
+	uint16_t *queue = s_queue[warp];
+	const unsigned lt_mask = (1u << lane) - 1;
+	const uint8_t *refl = job.frames + job.frame_bytes * mc.ref_frame[lastl];
+	const int mvx = mc.mv[lastl][0], mvy = mc.mv[lastl][1];
+
+	// ---- first list of a bi-predicted strip ---------------------------------------------------------------
+	if (bi && h) {
+		const uint8_t *ref0 = job.frames + job.frame_bytes * mc.ref_frame[0];
+		if (wide) i5_first_list<2>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
+		else i5_first_list<1>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
+	}
+	// ---- luma: prediction of the (last) list, parked -------------------------------------------------------
+	if (h) {
+		if (wide) i5_park_luma<2>(refl, W, H, px0, py0, mvx, mvy, h, rows);
+		else i5_park_luma<1>(refl, W, H, px0, py0, mvx, mvy, h, rows);
+	}
+	if (bi || !plain_w) {
+		for (int r = 0; r < h; ++r)
+			for (int q = 0; q < nq; ++q) {
+				uint32_t w = rows[(r * nq + q) * I5_THREADS];
+				const uint8_t *drow = dst_y + (size_t)(py0 + r) * W + px0 + 4 * q;
+				if (plain_w) w = __vavgu4(*reinterpret_cast<const uint32_t *>(drow), w);
+				else {
+					int p[4];
+#pragma unroll
+					for (int i = 0; i < 4; ++i) p[i] = (w >> (8 * i)) & 255;
+					if (bi) {
+						const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow);
+						const int lw = mc.log2wd_y, o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
+#pragma unroll
+						for (int i = 0; i < 4; ++i) p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][0] + p[i] * mc.w[1][0] + (1 << lw)) >> (lw + 1)) + o);
+					} else {
+						const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
+#pragma unroll
+						for (int i = 0; i < 4; ++i) p[i] = clip255(((p[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
+					}
+					w = pack4(p[0], p[1], p[2], p[3]);
+				}
+				rows[(r * nq + q) * I5_THREADS] = w;
+			}
+	}
+	// ---- luma residual, warp-wide ---------------------------------------------------------------------------
+	{
+		int n_jobs = 0;
+#pragma unroll
+		for (int s = 0; s < 8; ++s) {
+			const int g = s >> 1, q = s & 1;
+			bool coded = false;
+			int b = 0;
+			if (g < h4 && q < nq && !t8) {
+				b = c_r2b[(y4 + g) * 4 + x4 + q];
+				coded = (m.nz >> (1 + b)) & 1;
+			}
+			const unsigned bal = __ballot_sync(0xffffffffu, coded);
+			if (coded) queue[n_jobs + __popc(bal & lt_mask)] = (uint16_t)(lane | (g << 5) | (q << 7) | (b << 8));
+			n_jobs += __popc(bal);
+		}
+		__syncwarp();
+		for (int j0 = 0; j0 < n_jobs; j0 += 32) {
+			const bool has = j0 + lane < n_jobs;
+			const int e = has ? queue[j0 + lane] : 0, o = e & 31;
+			b2_h264_mb mo;           // what the transform needs to know of the owner's macroblock
+			mo.type = B2_H4_INTER;
+			mo.nz = __shfl_sync(0xffffffffu, m.nz, o);
+			mo.coef_idx = __shfl_sync(0xffffffffu, m.coef_idx, o);
+			mo.qp_y = (uint8_t)__shfl_sync(0xffffffffu, (int)m.qp_y, o);
+			const int nqo = __shfl_sync(0xffffffffu, nq, o);
+			if (has) {
+				const int g = (e >> 5) & 3, q = (e >> 7) & 1;
+				int16_t res[16];
+				block_residual(job, mo, (e >> 8) & 15, res);
+				uint32_t *orow = &s_rows[0][(tid & ~31) + o] + ((4 * g) * nqo + q) * I5_THREADS;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					uint32_t *pw = orow + j * nqo * I5_THREADS;
+					*pw = add_res4(*pw, res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]);
+				}
+			}
+		}
+		__syncwarp();
+	}
+	if (t8) {
+		// 8x8 transform: partitions are at least 8x8 here, the strip crosses whole 8-row groups
+		for (int r = 0; r < h; r += 8) {
+			const int q8 = ((y4 + (r >> 2)) >> 1) * 2 + (x4 >> 1);
+			if (!((m.nz >> (1 + 4 * q8)) & 1)) continue;
+			block_residual8x8(job, m, q8, reinterpret_cast<int16_t(*)[16]>(rs) - 4 * q8);
+			for (int rr = r; rr < r + 8 && rr < h; ++rr)
+				for (int q = 0; q < nq; ++q) {
+					const int16_t *res = rs + (((rr >> 2) & 1) * 2 + (x4 & 1) + q) * 16 + (rr & 3) * 4;      // narrow strips may sit in the right half of an 8x8 block
+					uint32_t *pw = rows + (rr * nq + q) * I5_THREADS;
+					*pw = add_res4(*pw, res[0], res[1], res[2], res[3]);
+				}
+		}
+	}
+	for (int r = 0; r < h; ++r)
+		for (int q = 0; q < nq; ++q) *reinterpret_cast<uint32_t *>(dst_y + (size_t)(py0 + r) * W + px0 + 4 * q) = rows[(r * nq + q) * I5_THREADS];
+	__syncwarp();       // the parked rows are reused for chroma: nobody may still be adding luma residuals
+
+	// ---- chroma: nq words (Cb Cr Cb Cr) per row, h / 2 rows ------------------------------------------------------
+	const int hc = h / 2;
+	if (h) {
+		if (wide) i5_park_chroma<2>(refl + luma_size, W, H >> 1, px0, cyp, mvx, mvy, hc, rows);
+		else i5_park_chroma<1>(refl + luma_size, W, H >> 1, px0, cyp, mvx, mvy, hc, rows);
+	}
+	if (bi || !plain_w) {
+		for (int r = 0; r < hc; ++r)
+			for (int q = 0; q < nq; ++q) {
+				uint32_t w = rows[(r * nq + q) * I5_THREADS];
+				const uint8_t *drow = dst_c + (size_t)(cyp + r) * W + px0 + 4 * q;
+				if (plain_w) w = __vavgu4(*reinterpret_cast<const uint32_t *>(drow), w);
+				else {
+					int p[4];
+#pragma unroll
+					for (int i = 0; i < 4; ++i) p[i] = (w >> (8 * i)) & 255;
+					if (bi) {
+						const uint32_t w0 = *reinterpret_cast<const uint32_t *>(drow);
+						const int lc = mc.log2wd_c;
+#pragma unroll
+						for (int i = 0; i < 4; ++i) {
+							const int c = 1 + (i & 1);
+							p[i] = clip255((((int)((w0 >> (8 * i)) & 255) * mc.w[0][c] + p[i] * mc.w[1][c] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][c] + mc.o[1][c] + 1) >> 1));
+						}
+					} else {
+						const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
+#pragma unroll
+						for (int i = 0; i < 4; ++i) {
+							const int c = 1 + (i & 1);
+							p[i] = clip255(((p[i] * mc.w[first][c] + rc) >> lc) + mc.o[first][c]);
+						}
+					}
+					w = pack4(p[0], p[1], p[2], p[3]);
+				}
+				rows[(r * nq + q) * I5_THREADS] = w;
+			}
+	}
+	// ---- chroma residual, warp-wide: one queue entry per row of chroma blocks the strip touches (both components) ----
+	{
+		int n_jobs = 0;
+#pragma unroll
+		for (int s = 0; s < 2; ++s) {
+			const bool coded = hc > 0 && ((m.nz >> 17) & 0x1ff) && s * 4 < cy0 + hc && s * 4 + 4 > cy0;
+			const unsigned bal = __ballot_sync(0xffffffffu, coded);
+			if (coded) queue[n_jobs + __popc(bal & lt_mask)] = (uint16_t)(lane | (s << 5));
+			n_jobs += __popc(bal);
+		}
+		__syncwarp();
+		for (int j0 = 0; j0 < n_jobs; j0 += 32) {
+			const bool has = j0 + lane < n_jobs;
+			const int e = has ? queue[j0 + lane] : 0, o = e & 31;
+			b2_h264_mb mo;
+			mo.type = B2_H4_INTER;
+			mo.nz = __shfl_sync(0xffffffffu, m.nz, o);
+			mo.coef_idx = __shfl_sync(0xffffffffu, m.coef_idx, o);
+			mo.qp_cb = (uint8_t)__shfl_sync(0xffffffffu, (int)m.qp_cb, o);
+			mo.qp_cr = (uint8_t)__shfl_sync(0xffffffffu, (int)m.qp_cr, o);
+			const int geo = __shfl_sync(0xffffffffu, nq | (cx0 << 2) | (cy0 << 6) | (hc << 10), o);
+			if (has) {
+				const int nqo = geo & 3, cxo = (geo >> 2) & 15, cyo = (geo >> 6) & 15, hco = geo >> 10, br = (e >> 5) & 1;
+				const int cblk = br * 2 + (cxo >> 2);
+				unsigned ok = 0;
+				for (int comp = 0; comp < 2; ++comp)
+					if (block_residual(job, mo, 16 + comp * 4 + cblk, rs + comp * 16)) ok |= 1u << comp;
+				if (ok) {
+					const int ca = max(cyo, br * 4), cb = min(cyo + hco, br * 4 + 4);
+					for (int cy = ca; cy < cb; ++cy)
+						for (int q = 0; q < nqo; ++q) {
+							uint32_t *pw = &s_rows[0][(tid & ~31) + o] + ((cy - cyo) * nqo + q) * I5_THREADS;
+							const uint32_t w = *pw;
+							int p[4];
+#pragma unroll
+							for (int i = 0; i < 4; ++i) {
+								const int comp = i & 1, cx = cxo + 2 * q + (i >> 1);
+								p[i] = (w >> (8 * i)) & 255;
+								if ((ok >> comp) & 1) p[i] = clip255(p[i] + rs[comp * 16 + (cy & 3) * 4 + (cx & 3)]);
+							}
+							*pw = pack4(p[0], p[1], p[2], p[3]);
+						}
+				}
+			}
+		}
+		__syncwarp();
+	}
+	for (int r = 0; r < hc; ++r)
+		for (int q = 0; q < nq; ++q) *reinterpret_cast<uint32_t *>(dst_c + (size_t)(cyp + r) * W + px0 + 4 * q) = rows[(r * nq + q) * I5_THREADS];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1949,7 +2050,10 @@ __device__ void deblock_chunk(const H4Job &job, const DbkTables &tb, DbkTile &tl
 #define B2_WAVE_WARPS 4
 #endif
 constexpr int WAVE_WARPS = B2_WAVE_WARPS;
-constexpr int WAVE_CTAS_DBK = 24 / WAVE_WARPS, WAVE_CTAS_INTRA = 16 / WAVE_WARPS;    // resident CTAs per SM (register budget)
+#ifndef B2_DBK_WARPS_PER_SM
+#define B2_DBK_WARPS_PER_SM 24
+#endif
+constexpr int WAVE_CTAS_DBK = B2_DBK_WARPS_PER_SM / WAVE_WARPS, WAVE_CTAS_INTRA = 16 / WAVE_WARPS;    // resident CTAs per SM (register budget)
 
 template <int PHASE>   // 1 intra, 2 deblock
 __global__ void __launch_bounds__(32 * WAVE_WARPS, PHASE == 2 ? WAVE_CTAS_DBK : WAVE_CTAS_INTRA)
@@ -2087,7 +2191,7 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 1;     // 0: the older 4x4-item kernel (kept for comparison)
 		if (use5) {
 			dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
-			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS;
+			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint16_t) * I5_QUEUE * (I5_THREADS / 32);
 			static bool attr_set = false;       // per process; the attribute is per device function
 			if (!attr_set) {
 				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
