@@ -1791,6 +1791,9 @@ struct RowSync {
 	int seen;                 // progress of the row above known so far
 
 	__device__ __forceinline__ void wait(int want, int lane) {
+#ifdef B2_DBK_NOWAIT      // timing experiment only (wrong pixels): what the kernels cost without the dependencies
+		return;
+#endif
 		if (seen >= want) return;
 		if (sm_above) {
 			if (lane == 0) {
@@ -1825,8 +1828,10 @@ struct alignas(4) DbkTables { uint8_t alpha[52], beta[52], tc0[52][4]; };
 template <bool MAY_BS4>
 __device__ __forceinline__ void dbk_filter(int *v, const int q, const bool on, const int bs, const int alpha, const int beta, const int tc0, const bool luma) {
 	const int p0 = v[q - 1], p1 = v[q - 2], p2 = v[q - 3], q0 = v[q], q1 = v[q + 1], q2 = v[q + 2];
-	const bool act = on && abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta;
-	const bool ap = luma && abs(p2 - p0) < beta, aq = luma && abs(q2 - q0) < beta;
+	// |d| < t as one unsigned comparison, (unsigned)(d + t - 1) < 2t - 1 (t >= 1; a zero threshold switches the edge off)
+	const unsigned am = (unsigned)(alpha - 1), a2 = (unsigned)(2 * alpha - 1), bm = (unsigned)(beta - 1), b2 = (unsigned)(2 * beta - 1);
+	const bool act = on && beta != 0 && (unsigned)(p0 - q0) + am < a2 && (unsigned)(p1 - p0) + bm < b2 && (unsigned)(q1 - q0) + bm < b2;
+	const bool ap = luma && (unsigned)(p2 - p0) + bm < b2, aq = luma && (unsigned)(q2 - q0) + bm < b2;
 	const bool normal = act && (!MAY_BS4 || bs < 4);
 	{
 		const int tc = luma ? tc0 + ap + aq : tc0 + 1, avg = (p0 + q0 + 1) >> 1;
@@ -1840,7 +1845,7 @@ __device__ __forceinline__ void dbk_filter(int *v, const int q, const bool on, c
 	// bS 4 exists on macroblock edges only (edge 0): the inner edges are straight-line code
 	if (MAY_BS4 && __any_sync(__activemask(), act && bs == 4)) {
 		if (act && bs == 4) {
-			const bool strong = luma && abs(p0 - q0) < (alpha >> 2) + 2;
+			const bool strong = luma && (unsigned)(p0 - q0 + (alpha >> 2) + 1) < (unsigned)(2 * ((alpha >> 2) + 2) - 1);
 			if (strong && ap) {
 				const int p3 = v[q - 4];
 				v[q - 1] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
