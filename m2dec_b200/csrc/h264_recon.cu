@@ -2058,7 +2058,10 @@ constexpr int WAVE_WARPS = B2_WAVE_WARPS;
 #ifndef B2_DBK_WARPS_PER_SM
 #define B2_DBK_WARPS_PER_SM 24
 #endif
-constexpr int WAVE_CTAS_DBK = B2_DBK_WARPS_PER_SM / WAVE_WARPS, WAVE_CTAS_INTRA = 16 / WAVE_WARPS;    // resident CTAs per SM (register budget)
+#ifndef B2_INTRA_WARPS_PER_SM
+#define B2_INTRA_WARPS_PER_SM 32
+#endif
+constexpr int WAVE_CTAS_DBK = B2_DBK_WARPS_PER_SM / WAVE_WARPS, WAVE_CTAS_INTRA = B2_INTRA_WARPS_PER_SM / WAVE_WARPS;    // resident CTAs per SM (register budget)
 
 template <int PHASE>   // 1 intra, 2 deblock
 __global__ void __launch_bounds__(32 * WAVE_WARPS, PHASE == 2 ? WAVE_CTAS_DBK : WAVE_CTAS_INTRA)
