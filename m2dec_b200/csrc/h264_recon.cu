@@ -2136,6 +2136,359 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Deblocking, two pictures per warp.  The kernel above spends its instructions per sample and per
+// macroblock; here every register holds the same sample of TWO pictures of the launch (16-bit
+// lanes: picture A low, B high), the filter runs on both with the packed 16x2 integer
+// instructions of sm_100 (VIADD.16x2, VIMNMX.S16x2, VABSDIFF4) and plain 32-bit arithmetic on
+// biased lanes, and all per-macroblock work (waiting, publishing, addressing, the transposes
+// through shared memory) is done once for the pair.  Lane roles, tile layout and the order of
+// operations are those of deblock_chunk; conditions are carried as bit 15 of each lane
+// ((threshold - 1 + 0x8000) - |difference| has the bit set exactly when the test holds) and
+// applied by masking the clipping bounds, so the filter has no branch except the bS 4 case.
+// ------------------------------------------------------------------------------------------------
+struct DbkTile2 {
+	uint32_t y[20][21];     // one packed pair per sample; rows -4..15 at r + 4, columns -4..15 at c + 4; odd pitch: conflict-free rows and columns
+	uint32_t c[10][21];     // chroma rows -2..7 at r + 2, byte columns (Cb Cr interleaved) -4..15 at c + 4
+};
+
+__device__ __forceinline__ uint32_t vneg2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
+__device__ __forceinline__ uint32_t bits_mask(uint32_t bits) { return bits - (bits >> 15); }     // 0x8000 per lane -> 0x7fff per lane
+__device__ __forceinline__ uint32_t vsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+// clip3(-t, t, x) per lane
+__device__ __forceinline__ uint32_t vclamp2(uint32_t x, uint32_t t) { return __vmins2(__vmaxs2(x, vneg2(t)), t); }
+
+template <bool MAY_BS4>
+__device__ __forceinline__ void dbk_filter2(uint32_t *v, const int q, const uint32_t onbits, const uint32_t bs4bits, const uint32_t alpha2, const uint32_t beta2,
+                                            const uint32_t tc02, const bool luma) {
+	const uint32_t p0 = v[q - 1], p1 = v[q - 2], p2 = v[q - 3], q0 = v[q], q1 = v[q + 1], q2 = v[q + 2];
+	const uint32_t B15 = 0x80008000u;
+	const uint32_t am = alpha2 + 0x7FFF7FFFu, bm = beta2 + 0x7FFF7FFFu;      // a zero threshold never passes
+	const uint32_t d0 = __vabsdiffu4(p0, q0);
+	const uint32_t act = (am - d0) & (bm - __vabsdiffu4(p1, p0)) & (bm - __vabsdiffu4(q1, q0)) & onbits;
+	const uint32_t lum = luma ? B15 : 0u;
+	const uint32_t ap = (bm - __vabsdiffu4(p2, p0)) & lum, aq = (bm - __vabsdiffu4(q2, q0)) & lum;
+	const uint32_t nb = MAY_BS4 ? act & ~bs4bits : act;
+	const uint32_t mn = bits_mask(nb);
+	const uint32_t tc = (tc02 + (luma ? (ap >> 15) + (aq >> 15) : 0x00010001u)) & mn;
+	// delta = clip3(-tc, tc, ((q0 - p0) * 4 + (p1 - q1) + 4) >> 3): lanes biased by 2048 so that they stay positive
+	const uint32_t X = ((q0 - p0) << 2) + (p1 - q1) + 0x08040804u;
+	const uint32_t delta = vclamp2(__vadd2((X >> 3) & 0x1FFF1FFFu, 0xFF00FF00u), tc);
+	uint32_t np0 = __vimin_s16x2_relu(__vadd2(p0, delta), 0x00FF00FFu);
+	uint32_t nq0 = __vimin_s16x2_relu(__vadd2(q0, vneg2(delta)), 0x00FF00FFu);
+	const uint32_t avg = ((p0 + q0 + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+	const uint32_t t0 = tc02 & mn;
+	const uint32_t zp = __vadd2(((p2 + avg + 0x02000200u - (p1 << 1)) >> 1) & 0x7FFF7FFFu, 0xFF00FF00u);
+	const uint32_t zq = __vadd2(((q2 + avg + 0x02000200u - (q1 << 1)) >> 1) & 0x7FFF7FFFu, 0xFF00FF00u);
+	uint32_t np1 = __vadd2(p1, vclamp2(zp, t0 & bits_mask(ap)));
+	uint32_t nq1 = __vadd2(q1, vclamp2(zq, t0 & bits_mask(aq)));
+	if (MAY_BS4) {
+		const uint32_t a4 = act & bs4bits;
+		if (__any_sync(__activemask(), a4 != 0)) {
+			const uint32_t p3 = v[q - 4], q3 = v[q + 3];
+			const uint32_t sm = ((alpha2 >> 2) & 0x3FFF3FFFu) + 0x80018001u;          // (alpha >> 2) + 2, as a biased threshold
+			const uint32_t st = (sm - d0) & lum & a4;
+			const uint32_t msp = bits_mask(st & ap), msq = bits_mask(st & aq), m4 = bits_mask(a4);
+			const uint32_t pq = p0 + q0;
+			const uint32_t sp0 = ((p2 + 2 * p1 + 2 * pq + q1 + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+			const uint32_t sp1 = ((p2 + p1 + pq + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+			const uint32_t sp2 = ((2 * p3 + 3 * p2 + p1 + pq + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+			const uint32_t wp0 = ((2 * p1 + p0 + q1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+			const uint32_t sq0 = ((q2 + 2 * q1 + 2 * pq + p1 + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+			const uint32_t sq1 = ((q2 + q1 + pq + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+			const uint32_t sq2 = ((2 * q3 + 3 * q2 + q1 + pq + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+			const uint32_t wq0 = ((2 * q1 + q0 + p1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+			np0 = vsel(msp, sp0, vsel(m4, wp0, np0));
+			np1 = vsel(msp, sp1, np1);
+			v[q - 3] = vsel(msp, sp2, p2);
+			nq0 = vsel(msq, sq0, vsel(m4, wq0, nq0));
+			nq1 = vsel(msq, sq1, nq1);
+			v[q + 2] = vsel(msq, sq2, q2);
+		}
+	}
+	v[q - 1] = np0;
+	v[q] = nq0;
+	v[q - 2] = np1;
+	v[q + 1] = nq1;
+}
+
+struct DbkSide {            // what one picture of the pair contributes to a line: strengths, flags, QPs, offsets
+	uint32_t bits;
+	bool edge0_ok, edge0_bs4;
+	int qpc, qpn, aoff, boff;
+};
+
+__device__ __forceinline__ void dbk_line2(uint32_t *v, const DbkTables &tb, const DbkSide &A, const DbkSide &B, int seg, bool luma) {
+	uint32_t alpha_i, beta_i, alpha_0, beta_0, tci[2], tc0[2];
+	{
+		const int ia = min(max(A.qpc + A.aoff, 0), 51), ib = min(max(A.qpc + A.boff, 0), 51), q0 = (A.qpc + A.qpn + 1) >> 1;
+		const int ja = min(max(q0 + A.aoff, 0), 51), jb = min(max(q0 + A.boff, 0), 51);
+		alpha_i = tb.alpha[ia]; beta_i = tb.beta[ib]; alpha_0 = tb.alpha[ja]; beta_0 = tb.beta[jb];
+		tci[0] = *reinterpret_cast<const uint32_t *>(tb.tc0[ia]);
+		tc0[0] = *reinterpret_cast<const uint32_t *>(tb.tc0[ja]);
+	}
+	{
+		const int ia = min(max(B.qpc + B.aoff, 0), 51), ib = min(max(B.qpc + B.boff, 0), 51), q0 = (B.qpc + B.qpn + 1) >> 1;
+		const int ja = min(max(q0 + B.aoff, 0), 51), jb = min(max(q0 + B.boff, 0), 51);
+		alpha_i |= (uint32_t)tb.alpha[ia] << 16; beta_i |= (uint32_t)tb.beta[ib] << 16; alpha_0 |= (uint32_t)tb.alpha[ja] << 16; beta_0 |= (uint32_t)tb.beta[jb] << 16;
+		tci[1] = *reinterpret_cast<const uint32_t *>(tb.tc0[ia]);
+		tc0[1] = *reinterpret_cast<const uint32_t *>(tb.tc0[ja]);
+	}
+	const uint32_t la = A.bits >> (2 * seg), lb = B.bits >> (2 * seg);       // this line's strength of edge e in bits 8e, 8e + 1
+	{
+		const int bsa = la & 3, bsb = lb & 3;
+		const bool ona = bsa != 0 && A.edge0_ok, onb = bsb != 0 && B.edge0_ok;
+		const uint32_t onbits = (ona ? 0x8000u : 0u) | (onb ? 0x80000000u : 0u);
+		const uint32_t bs4bits = (A.edge0_bs4 ? 0x8000u : 0u) | (B.edge0_bs4 ? 0x80000000u : 0u);
+		const uint32_t tc = ((tc0[0] >> (8 * (bsa ? bsa - 1 : 0))) & 255u) | (((tc0[1] >> (8 * (bsb ? bsb - 1 : 0))) & 255u) << 16);
+		if (__any_sync(__activemask(), onbits != 0)) dbk_filter2<true>(v, 4, onbits, bs4bits, alpha_0, beta_0, tc, luma);
+	}
+	if (!((A.bits | B.bits) & 0xffffff00u)) return;          // no inner edge of either macroblock has a strength
+#pragma unroll
+	for (int i = 1; i < 4; ++i) {
+		const int e = luma ? i : 2 * i;                  // chroma edges 0 / 1 of the register layout are luma edges 0 / 2
+		const bool exists = luma || i < 2;
+		const int bsa = (e < 4 && exists) ? (la >> (8 * e)) & 3 : 0, bsb = (e < 4 && exists) ? (lb >> (8 * e)) & 3 : 0;
+		const uint32_t onbits = (bsa ? 0x8000u : 0u) | (bsb ? 0x80000000u : 0u);
+		const uint32_t tc = ((tci[0] >> (8 * (bsa ? bsa - 1 : 0))) & 255u) | (((tci[1] >> (8 * (bsb ? bsb - 1 : 0))) & 255u) << 16);
+		dbk_filter2<false>(v, 4 + 4 * i, onbits, 0u, alpha_i, beta_i, tc, luma);
+	}
+}
+
+// bytes (s0, s1) of word a and of word b as two packed pairs: [a.s0, 0, b.s0, 0] and [a.s1, 0, b.s1, 0]
+__device__ __forceinline__ void pair2(uint32_t a, uint32_t b, uint32_t sel, uint32_t &o0, uint32_t &o1) {
+	const uint32_t t = __byte_perm(a, b, sel);            // [a.s0, a.s1, b.s0, b.s1]
+	o0 = t & 0x00FF00FFu;
+	o1 = (t >> 8) & 0x00FF00FFu;
+}
+// four consecutive packed pairs -> the word of picture A and the word of picture B
+__device__ __forceinline__ void unpair4(const uint32_t *e, uint32_t &wa, uint32_t &wb) {
+	const uint32_t x01 = __byte_perm(e[0], e[1], 0x6240), x23 = __byte_perm(e[2], e[3], 0x6240);     // [e0.A, e1.A, e0.B, e1.B]
+	wa = __byte_perm(x01, x23, 0x5410);
+	wb = __byte_perm(x01, x23, 0x7632);
+}
+
+// One row chunk of a picture pair: macroblocks x0 + k for the set bits k of `todo` (needed by either picture), left to right.
+__device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB, const DbkTables &tb, DbkTile2 &tl, int mby, int x0, unsigned todo, int lane,
+                               RowSync &sy, int &done_to) {
+	const int mb_w = jobA.mb_w, W = mb_w * 16, H = jobA.mb_h * 16;
+	uint8_t *const fyA = jobA.frames + jobA.frame_bytes * jobA.dst, *const fyB = jobB.frames + jobB.frame_bytes * jobB.dst;
+	uint8_t *const fcA = fyA + (size_t)W * H, *const fcB = fyB + (size_t)W * H;
+	const bool luma = lane < 16;
+	const int comp = lane & 1;                              // chroma lanes: component
+	const int line = luma ? lane : (lane - 16) >> 1;        // V pass: picture line inside the MB (chroma: 0..7)
+	const size_t line_off = luma ? (size_t)(mby * 16 + line) * W : (size_t)(mby * 8 + line) * W;
+	const uint8_t *const lbA = (luma ? fyA : fcA) + line_off, *const lbB = (luma ? fyB : fcB) + line_off;
+	uint32_t *const trow = luma ? tl.y[4 + line] : tl.c[2 + line];      // this lane's line in the tile
+	const uint32_t csel = comp ? 0x7531u : 0x6420u;         // chroma: bytes (comp, 2 + comp) of both words
+	bool carry_in = false;
+	while (todo) {
+		const int k = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const int x = x0 + k;
+		const bool carry_out = todo && (__ffs(todo) - 1 == k + 1);      // the next macroblock takes over columns 12..15
+		if (x > done_to) sy.publish(x, lane);              // the stretch that needed nothing
+		const size_t mbi = (size_t)mby * mb_w + x;
+		const b2_h264_dbk *dpA = jobA.dbk + mbi, *dpB = jobB.dbk + mbi;
+		uint4 drA = __ldg(reinterpret_cast<const uint4 *>(dpA)), drB = __ldg(reinterpret_cast<const uint4 *>(dpB));
+		const uint32_t qlA = x > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpA - 1) + 2) : 0, qlB = x > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpB - 1) + 2) : 0;
+		const uint32_t qtA = mby > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpA - mb_w) + 2) : 0, qtB = mby > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpB - mb_w) + 2) : 0;
+		if ((drA.z >> 24) & B2_DBK_OFF) drA.x = drA.y = 0;
+		if (((drB.z >> 24) & B2_DBK_OFF) || !validB) drB.x = drB.y = 0;
+		uint32_t wA[5], wB[5];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			wA[1 + i] = __ldcg(reinterpret_cast<const uint32_t *>(lbA + x * 16 + 4 * i));
+			wB[1 + i] = __ldcg(reinterpret_cast<const uint32_t *>(lbB + x * 16 + 4 * i));
+		}
+		wA[0] = wB[0] = 0;
+		if (!carry_in && x > 0) {
+			wA[0] = __ldcg(reinterpret_cast<const uint32_t *>(lbA + x * 16 - 4));
+			wB[0] = __ldcg(reinterpret_cast<const uint32_t *>(lbB + x * 16 - 4));
+		}
+		if (mby > 0) sy.wait(min(x + 2, mb_w), lane);
+		// rows above the macroblock (final once the row above is two macroblocks ahead): lanes 0..15 one
+		// word of luma rows -4..-1, lanes 16..23 one word of chroma rows -2..-1
+		uint32_t twA = 0, twB = 0;
+		if (mby > 0 && lane < 24) {
+			const size_t off = (luma ? (size_t)(mby * 16 - 4 + (lane >> 2)) * W : (size_t)(mby * 8 - 2 + ((lane - 16) >> 2)) * W) + x * 16 + 4 * (lane & 3);
+			twA = __ldcg(reinterpret_cast<const uint32_t *>((luma ? fyA : fcA) + off));
+			twB = __ldcg(reinterpret_cast<const uint32_t *>((luma ? fyB : fcB) + off));
+		}
+		// ---- record fields ---------------------------------------------------------------------------
+		const int qsel = luma ? 0 : 8 + 8 * comp;            // byte of the QP word: qp_y, qp_cb, qp_cr
+		DbkSide sA, sB;
+		const int flagsA = (drA.z >> 24) & 255, flagsB = (drB.z >> 24) & 255;
+		sA.qpc = (int8_t)((drA.z >> qsel) & 255); sB.qpc = (int8_t)((drB.z >> qsel) & 255);
+		sA.aoff = (int8_t)(drA.w & 255); sA.boff = (int8_t)((drA.w >> 8) & 255);
+		sB.aoff = (int8_t)(drB.w & 255); sB.boff = (int8_t)((drB.w >> 8) & 255);
+		const bool topA = flagsA & B2_DBK_TOP_EDGE, topB = (flagsB & B2_DBK_TOP_EDGE) && validB;
+		// ---- V pass ----------------------------------------------------------------------------------
+		{
+			uint32_t v[20];
+			if (luma) {
+#pragma unroll
+				for (int j = 0; j < 5; ++j) {
+					pair2(wA[j], wB[j], 0x5410u, v[4 * j], v[4 * j + 1]);
+					pair2(wA[j], wB[j], 0x7632u, v[4 * j + 2], v[4 * j + 3]);
+				}
+				if (carry_in) {
+#pragma unroll
+					for (int i = 0; i < 4; ++i) v[i] = trow[i];
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < 20; ++i) v[i] = 0;
+#pragma unroll
+				for (int j = 0; j < 5; ++j) pair2(wA[j], wB[j], csel, v[2 + 2 * j], v[3 + 2 * j]);
+				if (carry_in) { v[2] = trow[comp]; v[3] = trow[2 + comp]; }
+			}
+			if (drA.x | drB.x) {
+				sA.bits = drA.x; sB.bits = drB.x;
+				sA.edge0_ok = flagsA & B2_DBK_LEFT_EDGE; sB.edge0_ok = flagsB & B2_DBK_LEFT_EDGE;
+				sA.edge0_bs4 = flagsA & B2_DBK_LEFT_BS4; sB.edge0_bs4 = flagsB & B2_DBK_LEFT_BS4;
+				sA.qpn = (int8_t)((qlA >> qsel) & 255); sB.qpn = (int8_t)((qlB >> qsel) & 255);
+				dbk_line2(v, tb, sA, sB, luma ? line >> 2 : line >> 1, luma);
+			}
+			if (luma) {
+#pragma unroll
+				for (int i = 0; i < 20; ++i) trow[i] = v[i];
+			} else {
+#pragma unroll
+				for (int i = 0; i < 10; ++i) trow[2 * i + comp] = v[2 + i];
+			}
+			if (lane < 24) {
+				uint32_t *d = (luma ? tl.y[lane >> 2] : tl.c[(lane - 16) >> 2]) + 4 + 4 * (lane & 3);
+				pair2(twA, twB, 0x5410u, d[0], d[1]);
+				pair2(twA, twB, 0x7632u, d[2], d[3]);
+			}
+		}
+		__syncwarp();
+		// ---- H pass: lanes 0..15 luma column, lanes 16..31 chroma byte column ---------------------------
+		if (drA.y | drB.y) {
+			const int col = lane & 15;
+			uint32_t v[20];
+			if (luma) {
+#pragma unroll
+				for (int i = 0; i < 20; ++i) v[i] = tl.y[i][4 + col];
+			} else {
+#pragma unroll
+				for (int i = 0; i < 20; ++i) v[i] = 0;
+#pragma unroll
+				for (int i = 0; i < 10; ++i) v[2 + i] = tl.c[i][4 + col];
+			}
+			sA.bits = drA.y; sB.bits = drB.y;
+			sA.edge0_ok = flagsA & B2_DBK_TOP_EDGE; sB.edge0_ok = flagsB & B2_DBK_TOP_EDGE;
+			sA.edge0_bs4 = flagsA & B2_DBK_TOP_BS4; sB.edge0_bs4 = flagsB & B2_DBK_TOP_BS4;
+			sA.qpn = (int8_t)((qtA >> qsel) & 255); sB.qpn = (int8_t)((qtB >> qsel) & 255);
+			dbk_line2(v, tb, sA, sB, col >> 2, luma);
+			if (luma) {
+#pragma unroll
+				for (int i = 1; i < 20; ++i) tl.y[i][4 + col] = v[i];
+			} else {
+#pragma unroll
+				for (int i = 1; i < 10; ++i) tl.c[i][4 + col] = v[2 + i];
+			}
+			__syncwarp();
+		}
+		// ---- store what is final: columns -4..11 (or ..15 when nobody takes them over) of the lines, and
+		//      the rows above (luma -3..-1 by lanes 24..26, chroma -1 by lane 27) ---------------------------
+		if (lane < 24) {
+			const int li = lane < 16 ? lane : lane - 16;
+			const uint32_t *src = lane < 16 ? tl.y[4 + li] : tl.c[2 + li];
+			const size_t off = (lane < 16 ? (size_t)(mby * 16 + li) * W : (size_t)(mby * 8 + li) * W) + x * 16;
+			uint8_t *dA = (lane < 16 ? fyA : fcA) + off, *dB = (lane < 16 ? fyB : fcB) + off;
+#pragma unroll
+			for (int j = 0; j < 5; ++j) {
+				if ((j == 0 && x == 0) || (j == 4 && carry_out)) continue;
+				uint32_t wa, wb;
+				unpair4(src + 4 * j, wa, wb);
+				__stcg(reinterpret_cast<uint32_t *>(dA + 4 * (j - 1)), wa);
+				if (validB) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * (j - 1)), wb);
+			}
+		} else if (lane < 28 && (topA || topB)) {
+			const bool tl_luma = lane < 27;
+			const int r = tl_luma ? lane - 27 : -1;                 // luma rows -3..-1, chroma row -1
+			const uint32_t *src = (tl_luma ? tl.y[4 + r] : tl.c[2 + r]) + 4;
+			const size_t off = (tl_luma ? (size_t)(mby * 16 + r) * W : (size_t)(mby * 8 + r) * W) + x * 16;
+			uint8_t *dA = (tl_luma ? fyA : fcA) + off, *dB = (tl_luma ? fyB : fcB) + off;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				uint32_t wa, wb;
+				unpair4(src + 4 * j, wa, wb);
+				if (topA) __stcg(reinterpret_cast<uint32_t *>(dA + 4 * j), wa);
+				if (topB) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * j), wb);
+			}
+		}
+		__syncwarp();
+		if (carry_out && lane < 24) {
+			uint32_t *rw = lane < 16 ? tl.y[4 + lane] : tl.c[2 + lane - 16];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) rw[i] = rw[16 + i];
+		}
+		carry_in = carry_out;
+		done_to = x + 1;
+		sy.publish(x + 1, lane);
+		__syncwarp();
+	}
+}
+
+constexpr int DBK2_CTAS = 4;        // resident CTAs per SM (register budget)
+
+__global__ void __launch_bounds__(32 * WAVE_WARPS, DBK2_CTAS)
+h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
+	__shared__ DbkTile2 s_tile[WAVE_WARPS];
+	__shared__ DbkTables s_tb;
+	__shared__ int s_ticket;
+	__shared__ int s_prog[WAVE_WARPS];
+	for (int i = threadIdx.x; i < 52; i += blockDim.x) {
+		s_tb.alpha[i] = c_alpha[i];
+		s_tb.beta[i] = c_beta[i];
+		s_tb.tc0[i][0] = c_tc0[i][0]; s_tb.tc0[i][1] = c_tc0[i][1]; s_tb.tc0[i][2] = c_tc0[i][2]; s_tb.tc0[i][3] = 0;
+	}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int *ticket = sync_area;
+	int *progress = sync_area + 32;           // [pairs][mb_h]: macroblocks of the row that are final (rows read across CTAs only)
+	const int groups = (mb_h + WAVE_WARPS - 1) / WAVE_WARPS, pairs = (n_jobs + 1) / 2;
+	const int total = pairs * groups;
+	for (;;) {
+		__syncthreads();                       // the previous group is complete: s_ticket / s_prog may be reused
+		if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
+		if (threadIdx.x < WAVE_WARPS) s_prog[threadIdx.x] = 0;
+		__syncthreads();
+		const int t = s_ticket;
+		if (t >= total) return;
+		// group-major ticket order, as in h264_wave_kernel
+		const int j = t % pairs, mby = (t / pairs) * WAVE_WARPS + warp;
+		if (mby >= mb_h) continue;
+		RowSync sy;
+		sy.sm_above = warp > 0 ? &s_prog[warp - 1] : nullptr;
+		sy.gl_above = (warp == 0 && mby > 0) ? progress + (size_t)j * mb_h + mby - 1 : nullptr;
+		sy.sm_my = &s_prog[warp];
+		sy.gl_my = (warp == WAVE_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
+		sy.seen = 0;
+		const bool validB = 2 * j + 1 < n_jobs;
+		const H4Job jobA = jobs[2 * j], jobB = jobs[validB ? 2 * j + 1 : 2 * j];
+		for (int x0 = 0; x0 < mb_w; x0 += 32) {
+			const int mbx = x0 + lane;
+			bool need = false;
+			if (mbx < mb_w) {
+				const b2_h264_dbk *d = &jobA.dbk[(size_t)mby * mb_w + mbx];
+				need = !(d->flags & B2_DBK_OFF) && (d->bs_v | d->bs_h);
+				if (validB) {
+					d = &jobB.dbk[(size_t)mby * mb_w + mbx];
+					need |= !(d->flags & B2_DBK_OFF) && (d->bs_v | d->bs_h);
+				}
+			}
+			unsigned todo = __ballot_sync(0xffffffffu, need);
+			int done_to = x0;                  // macroblocks < done_to are final
+			deblock_chunk2(jobA, jobB, validB, s_tb, s_tile[warp], mby, x0, todo, lane, sy, done_to);
+			const int end = min(x0 + 32, mb_w);
+			if (done_to < end) sy.publish(end, lane);
+		}
+	}
+}
+
 // Intra macroblocks of pictures that have few of them (P / B pictures).  A warp takes 32 consecutive
 // macroblocks (raster order) at a time and reconstructs the intra ones among them; an intra
 // macroblock waits only for those of its left / top-left / top / top-right neighbours that are intra
@@ -2228,7 +2581,16 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		int cap = 148 * 2 * WAVE_CTAS_DBK;
 		if (ctas > cap) ctas = cap;
 		if (phase == 1) h264_wave_kernel<1><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
-		else h264_wave_kernel<2><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+		else {
+			static const int dbk2 = getenv("B2_DBK2") ? atoi(getenv("B2_DBK2")) : 0;
+			if (dbk2 && n_jobs > 1) {
+				int ctas2 = ((n_jobs + 1) / 2) * ((mb_h + WAVE_WARPS - 1) / WAVE_WARPS);
+				if (ctas2 > 148 * 2 * DBK2_CTAS) ctas2 = 148 * 2 * DBK2_CTAS;
+				h264_deblock2_kernel<<<ctas2, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+			} else {
+				h264_wave_kernel<2><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+			}
+		}
 		if (launches) ++*launches;
 	}
 	B2_CUDA_OK(cudaGetLastError());
