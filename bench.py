@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lanes", type=int, default=128, help="independent 1080p streams per GPU")
+    ap.add_argument("--lanes", type=int, default=256, help="independent 1080p streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
     ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
     ap.add_argument("--e2e-streams", type=int, default=16)

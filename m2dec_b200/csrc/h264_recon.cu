@@ -2582,7 +2582,8 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		if (ctas > cap) ctas = cap;
 		if (phase == 1) h264_wave_kernel<1><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 		else {
-			static const int dbk2 = getenv("B2_DBK2") ? atoi(getenv("B2_DBK2")) : 0;
+			// batched launches pair the pictures up (two per warp); a single picture keeps the one-picture kernel
+			static const int dbk2 = getenv("B2_DBK2") ? atoi(getenv("B2_DBK2")) : 1;
 			if (dbk2 && n_jobs > 1) {
 				int ctas2 = ((n_jobs + 1) / 2) * ((mb_h + WAVE_WARPS - 1) / WAVE_WARPS);
 				if (ctas2 > 148 * 2 * DBK2_CTAS) ctas2 = 148 * 2 * DBK2_CTAS;

@@ -17,7 +17,9 @@ LANES = [
     "seed=204 refs=2 bframes=2 profile=77 weighted_bipred=1 weighted_pred=1",
     "seed=205 cabac=1 profile=100 transform8x8=1 refs=2 bframes=1",
     "seed=206 qp=40 alpha_div2=3 beta_div2=4 chroma_qp_offset=4",
-    "seed=207 qp=30 mv_range=300 mv_out=60 skip_pct=40",       # an odd number of lanes: the last one has no partner picture
+    "seed=207 qp=30 mv_range=300 mv_out=60 skip_pct=40",
+    "seed=208 deblock=0",                                       # loop filter off, paired with a picture that has it on
+    "seed=209 qp=20 coded_pct=60 alpha_div2=-2 beta_div2=1",    # an odd number of lanes: the last one has no partner picture
 ]
 
 
@@ -29,7 +31,7 @@ def _md5(y, c):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nlanes", [len(LANES), 2, 1])
+@pytest.mark.parametrize("nlanes", [len(LANES), 8, 2, 1])
 def test_replay_matches_oracle(nlanes):
     import m2dec_b200
     data = [streams.generate("h264", GEOM + " " + a) for a in LANES[:nlanes]]
