@@ -339,7 +339,9 @@ def main():
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peak, peak_src = peaks()
-    names = ["h264_inter_kernel", "h264_intra_kernel", "h264_deblock_kernel"]
+    # the kernels behind the three phases of a replay step (m2dec_b200/csrc/h264_recon.cu)
+    names = ["h264_inter5_kernel", "h264_intra_sparse_kernel (P) / h264_wave_kernel<1> (I)", "h264_deblock2_kernel"]
+    phase = ["inter", "intra", "deblock"]
     dom = max(range(3), key=lambda i: kernel_ms[i])
     alg = [int(st.alg_bytes[i]) for i in range(3)]
     achieved = alg[dom] / (kernel_ms[dom] / 1000.0) / 1e9 if kernel_ms[dom] > 0 else 0.0
@@ -347,10 +349,10 @@ def main():
     # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture,
     # scaled to this run's pictures per launch
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")       # written by tools/summarize_ncu.py
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        per_launch = tj["dram_bytes_per_launch"].get(names[dom])
+        per_launch = tj["dram_bytes_per_launch"].get(phase[dom])
         if per_launch:
             traffic = per_launch / tj["pictures_per_launch"] * a.lanes
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
