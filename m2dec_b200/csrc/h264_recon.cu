@@ -2298,8 +2298,10 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 		uint32_t wA[5], wB[5];
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			wA[1 + i] = __ldcg(reinterpret_cast<const uint32_t *>(lbA + x * 16 + 4 * i));
-			wB[1 + i] = __ldcg(reinterpret_cast<const uint32_t *>(lbB + x * 16 + 4 * i));
+			// the macroblock's own samples have not been touched by this launch yet (L1 starts a launch empty), so they
+			// may come through L1: one 128-byte line serves this line of eight macroblocks
+			wA[1 + i] = __ldca(reinterpret_cast<const uint32_t *>(lbA + x * 16 + 4 * i));
+			wB[1 + i] = __ldca(reinterpret_cast<const uint32_t *>(lbB + x * 16 + 4 * i));
 		}
 		wA[0] = wB[0] = 0;
 		if (!carry_in && x > 0) {
