@@ -2435,14 +2435,18 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 	}
 }
 
-constexpr int DBK2_CTAS = 4;        // resident CTAs per SM (register budget)
+#ifndef B2_DBK2_WARPS
+#define B2_DBK2_WARPS 2
+#endif
+constexpr int DBK2_WARPS = B2_DBK2_WARPS;          // rows per CTA
+constexpr int DBK2_CTAS = 16 / DBK2_WARPS;        // resident CTAs per SM (register budget: 16 warps of 128 registers)
 
-__global__ void __launch_bounds__(32 * WAVE_WARPS, DBK2_CTAS)
+__global__ void __launch_bounds__(32 * DBK2_WARPS, DBK2_CTAS)
 h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
-	__shared__ DbkTile2 s_tile[WAVE_WARPS];
+	__shared__ DbkTile2 s_tile[DBK2_WARPS];
 	__shared__ DbkTables s_tb;
 	__shared__ int s_ticket;
-	__shared__ int s_prog[WAVE_WARPS];
+	__shared__ int s_prog[DBK2_WARPS];
 	for (int i = threadIdx.x; i < 52; i += blockDim.x) {
 		s_tb.alpha[i] = c_alpha[i];
 		s_tb.beta[i] = c_beta[i];
@@ -2451,23 +2455,23 @@ h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int m
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int *ticket = sync_area;
 	int *progress = sync_area + 32;           // [pairs][mb_h]: macroblocks of the row that are final (rows read across CTAs only)
-	const int groups = (mb_h + WAVE_WARPS - 1) / WAVE_WARPS, pairs = (n_jobs + 1) / 2;
+	const int groups = (mb_h + DBK2_WARPS - 1) / DBK2_WARPS, pairs = (n_jobs + 1) / 2;
 	const int total = pairs * groups;
 	for (;;) {
 		__syncthreads();                       // the previous group is complete: s_ticket / s_prog may be reused
 		if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
-		if (threadIdx.x < WAVE_WARPS) s_prog[threadIdx.x] = 0;
+		if (threadIdx.x < DBK2_WARPS) s_prog[threadIdx.x] = 0;
 		__syncthreads();
 		const int t = s_ticket;
 		if (t >= total) return;
 		// group-major ticket order, as in h264_wave_kernel
-		const int j = t % pairs, mby = (t / pairs) * WAVE_WARPS + warp;
+		const int j = t % pairs, mby = (t / pairs) * DBK2_WARPS + warp;
 		if (mby >= mb_h) continue;
 		RowSync sy;
 		sy.sm_above = warp > 0 ? &s_prog[warp - 1] : nullptr;
 		sy.gl_above = (warp == 0 && mby > 0) ? progress + (size_t)j * mb_h + mby - 1 : nullptr;
 		sy.sm_my = &s_prog[warp];
-		sy.gl_my = (warp == WAVE_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
+		sy.gl_my = (warp == DBK2_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
 		sy.seen = 0;
 		const bool validB = 2 * j + 1 < n_jobs;
 		const H4Job jobA = jobs[2 * j], jobB = jobs[validB ? 2 * j + 1 : 2 * j];
@@ -2587,9 +2591,9 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 			// batched launches pair the pictures up (two per warp); a single picture keeps the one-picture kernel
 			static const int dbk2 = getenv("B2_DBK2") ? atoi(getenv("B2_DBK2")) : 1;
 			if (dbk2 && n_jobs > 1) {
-				int ctas2 = ((n_jobs + 1) / 2) * ((mb_h + WAVE_WARPS - 1) / WAVE_WARPS);
+				int ctas2 = ((n_jobs + 1) / 2) * ((mb_h + DBK2_WARPS - 1) / DBK2_WARPS);
 				if (ctas2 > 148 * 2 * DBK2_CTAS) ctas2 = 148 * 2 * DBK2_CTAS;
-				h264_deblock2_kernel<<<ctas2, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+				h264_deblock2_kernel<<<ctas2, 32 * DBK2_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 			} else {
 				h264_wave_kernel<2><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 			}
