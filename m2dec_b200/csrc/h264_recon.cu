@@ -671,7 +671,13 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 // transformed by the same thread into a private shared-memory scratch, so there is no separate
 // residual phase and only the sort needs block-wide barriers.
 // ------------------------------------------------------------------------------------------------
-constexpr int I5_THREADS = 256;
+#ifndef B2_I5_THREADS
+#define B2_I5_THREADS 128
+#endif
+#ifndef B2_I5_CTAS
+#define B2_I5_CTAS 5
+#endif
+constexpr int I5_THREADS = B2_I5_THREADS;
 constexpr int I5_CLASSES = 12;        // interpolation class (0..5) + 6 * (strip is 8 wide)
 
 // item: bits 0..5 MB slot, 6..9 record, 10..11 x (4-sample units inside the MB), 12..13 y, 14..16 height
@@ -982,7 +988,7 @@ __device__ __forceinline__ uint32_t add_res4(uint32_t w, int r0, int r1, int r2,
 	return pack4(clip255((int)(w & 255) + r0), clip255((int)((w >> 8) & 255) + r1), clip255((int)((w >> 16) & 255) + r2), clip255((int)(w >> 24) + r3));
 }
 
-__global__ void __launch_bounds__(I5_THREADS, 2)
+__global__ void __launch_bounds__(I5_THREADS, B2_I5_CTAS)
 h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	// dynamic shared memory (more than the 48 KB a kernel may declare statically)
 	extern __shared__ __align__(16) uint8_t s_dyn[];
