@@ -2445,7 +2445,10 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 #define B2_DBK2_WARPS 2
 #endif
 constexpr int DBK2_WARPS = B2_DBK2_WARPS;          // rows per CTA
-constexpr int DBK2_CTAS = 16 / DBK2_WARPS;        // resident CTAs per SM (register budget: 16 warps of 128 registers)
+#ifndef B2_DBK2_WARPS_PER_SM
+#define B2_DBK2_WARPS_PER_SM 16
+#endif
+constexpr int DBK2_CTAS = B2_DBK2_WARPS_PER_SM / DBK2_WARPS;        // resident CTAs per SM (register budget: 16 warps of 128 registers)
 
 __global__ void __launch_bounds__(32 * DBK2_WARPS, DBK2_CTAS)
 h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
