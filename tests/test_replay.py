@@ -48,3 +48,22 @@ def test_replay_matches_oracle(nlanes):
                 assert got == want[lane], "lane %d (%s)" % (lane, LANES[lane])
     finally:
         rp.close()
+
+
+@pytest.mark.gpu
+def test_pageable_and_page_locked_frame_buffers_agree():
+    """The plugin path copies a picture out as soon as it is queued when the application's frame
+    buffers are page-locked (b2_host_alloc), and on demand when they are pageable: same frames."""
+    import m2dec_b200
+    from m2dec_b200 import decoder
+    data = streams.generate("h264", GEOM + " " + LANES[3])
+    want = util.oracle_md5("h264", data)
+    assert m2dec_b200.decode_file("h264", data) == want          # page-locked (default when a device is present)
+    saved, decoder._frames_pool = decoder._frames_pool, {}
+    orig = decoder.Frames.__init__
+    try:
+        decoder.Frames.__init__ = lambda self, w, h, n, s, pinned=True, cuda_device=-1: orig(self, w, h, n, s, False, cuda_device)
+        assert m2dec_b200.decode_file("h264", data) == want      # pageable numpy buffers
+    finally:
+        decoder.Frames.__init__ = orig
+        decoder._frames_pool = saved
