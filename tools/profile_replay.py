@@ -13,6 +13,7 @@ import m2dec_b200  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--codec", default="h264", choices=["h264", "mpeg2"])
+ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="H.264: c2 = Baseline CAVLC I/P (the bench workload), c3 = High CABAC I/P/B with weighted prediction and the 8x8 transform (BASELINE config 3)")
 ap.add_argument("--lanes", type=int, default=16)
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--runs", type=int, default=2)
@@ -20,6 +21,10 @@ a = ap.parse_args()
 
 
 def stream(seed):
+    if a.codec == "h264" and a.workload == "c3":
+        args = ("mbw=%d mbh=%d frames=%d seed=%d crop_bottom=8 refs=2 bframes=2 cabac=1 profile=100 transform8x8=1 "
+                "weighted_pred=1 weighted_bipred=1 gop=1000 qp=28 intra_pct=10 skip_pct=15 coded_pct=25" % (bench.MBW, bench.MBH, a.frames, seed))
+        return subprocess.run([bench.STREAMGEN, "h264", *args.split()], stdout=subprocess.PIPE, check=True).stdout
     if a.codec == "h264":
         return bench.make_stream(seed, a.frames)
     args = "mbw=%d mbh=%d frames=%d seed=%d bframes=2 gop=12 mv_range=64" % (bench.MBW, bench.MBH, a.frames, seed)
