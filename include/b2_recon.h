@@ -153,6 +153,11 @@ typedef struct {
 	 * 2 vertical, 3 diagonal, 4 / 5 centre column / row) + 6 if the strip is 8 samples wide.           */
 	const uint32_t *items;
 	uint32_t n_items;
+	/* The first n_items_first items are the FIRST-list passes of bi-predicted strips (class = that of
+	 * list 0; the kernel writes their prediction to the destination in a launch of its own); the rest
+	 * is one item per strip for its last (or only) list, class = that list's, which combines with the
+	 * first pass, adds the residual and stores.  Both parts are sorted by (class, height, edge).      */
+	uint32_t n_items_first;
 } b2_h264_picture;
 
 /* ------------------------------------------------------------------------------------ */

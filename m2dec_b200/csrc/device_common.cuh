@@ -39,7 +39,7 @@ struct H4Job {
 	const int16_t *coefs;
 	int32_t dst, mb_w, mb_h, n_intra;
 	const uint32_t *items;      // b2_h264_picture.items
-	uint32_t n_items, pad;
+	uint32_t n_items, n_first;  // b2_h264_picture.n_items / n_items_first
 };
 // A picture with few intra macroblocks (P / B pictures) goes through the sparse intra kernel, which
 // orders macroblocks by per-macroblock flags; a mostly-intra picture through the row wavefront.
@@ -49,9 +49,9 @@ __host__ __device__ inline bool h264_intra_sparse(int n_intra, int n_mbs) { retu
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h);
 // max_items: largest n_items among the jobs (phase 0 only)
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
-                      uint32_t max_items = 0);
+                      uint32_t max_items = 0, uint32_t max_first = 0);
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense,
-                bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches);
+                bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first = 0);
 
 __device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 

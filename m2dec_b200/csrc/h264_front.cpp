@@ -704,6 +704,7 @@ private:
 		dbk_.assign(n, b2_h264_dbk());
 		mcs_.clear();
 		for (auto &b : items_) b.clear();
+		for (auto &b : items_first_) b.clear();
 		coef_used_ = 0;
 		n_intra_ = 0;
 		any_deblock_ = false;
@@ -730,6 +731,8 @@ private:
 		p.mcs = mcs_.data();
 		p.coefs = coefs_.data();
 		items_all_.clear();
+		for (const auto &b : items_first_) items_all_.insert(items_all_.end(), b.begin(), b.end());
+		p.n_items_first = (uint32_t)items_all_.size();
 		for (const auto &b : items_) items_all_.insert(items_all_.end(), b.begin(), b.end());
 		p.items = items_all_.data();
 		p.n_items = (uint32_t)items_all_.size();
@@ -955,15 +958,16 @@ private:
 			r.log2wd_y = r.log2wd_c = 5;
 			for (int c = 0; c < 3; ++c) { r.w[0][c] = (int8_t)w0; r.w[1][c] = (int8_t)w1; }
 		}
-		// work items of the inter kernel (include/b2_recon.h): strips of this record, bucketed by class and height
+		// work items of the inter kernel (include/b2_recon.h): strips of this record, bucketed by class and height.
+		// A bi-predicted strip has two: the first-list pass (class of list 0; a launch of its own) and the
+		// finishing pass (class of list 1); a strip with one list only the latter.
 		{
 			auto frac_class = [](int fx, int fy) { return (!fx && !fy) ? 0 : (!fy ? 1 : (!fx ? 2 : (fx == 2 ? 4 : (fy == 2 ? 5 : 3)))); };
-			const int first = ref[0] >= 0 ? 0 : 1;
-			const int fc = frac_class(r.mv[first][0] & 3, r.mv[first][1] & 3);
-			bool centre = fc >= 4;
-			if (bi) centre |= frac_class(r.mv[1][0] & 3, r.mv[1][1] & 3) >= 4;
+			const int first = ref[0] >= 0 ? 0 : 1, last = bi ? 1 : first;
+			const int fc_first = frac_class(r.mv[first][0] & 3, r.mv[first][1] & 3), fc_last = frac_class(r.mv[last][0] & 3, r.mv[last][1] & 3);
+			const bool centre = fc_first >= 4 || fc_last >= 4;      // the centre sample's filter state does not fit 8-wide strips
 			const int wide = pw >= 2 && !centre;
-			const int cls = fc + 6 * wide, n = wide ? pw >> 1 : pw;
+			const int n = wide ? pw >> 1 : pw;
 			// strips whose reference window (6-tap margins included) leaves the picture take the clamped loads: they go
 			// to buckets of their own (the last 36), so that a warp of the kernel is all fast path or all clamped
 			const int W = mb_w_ * 16, H = mb_h_ * 16, sw = wide ? 8 : 4;
@@ -971,13 +975,17 @@ private:
 			const int hidx = ph == 4 ? 2 : ph - 1;
 			for (int k = 0; k < n; ++k) {
 				const int px = mbx * 16 + x4 * 4 + k * sw, py = mby * 16 + y4 * 4;
-				bool edge = false;
-				for (int lx = 0; lx < 2; ++lx) {
-					if (ref[lx] < 0) continue;
+				auto edge = [&](int lx) {
 					const int x0 = px + (r.mv[lx][0] >> 2), y0 = py + (r.mv[lx][1] >> 2);
-					edge |= x0 - 6 < 0 || x0 + sw + 12 > W || y0 - 3 < 0 || y0 + ph * 4 + 4 > H;
+					return x0 - 6 < 0 || x0 + sw + 12 > W || y0 - 3 < 0 || y0 + ph * 4 + 4 > H;
+				};
+				const uint32_t word = (uint32_t)mb_addr_ | ((uint32_t)m.mc_cnt << 20) | ((uint32_t)k << 24);
+				const int cls_last = fc_last + 6 * wide;
+				items_[(edge(last) ? 36 : 0) + cls_last * 3 + hidx].push_back(word | ((uint32_t)cls_last << 26));
+				if (bi) {
+					const int cls_first = fc_first + 6 * wide;
+					items_first_[(edge(0) ? 36 : 0) + cls_first * 3 + hidx].push_back(word | ((uint32_t)cls_first << 26));
 				}
-				items_[(edge ? 36 : 0) + cls * 3 + hidx].push_back((uint32_t)mb_addr_ | ((uint32_t)m.mc_cnt << 20) | ((uint32_t)k << 24) | ((uint32_t)cls << 26));
 			}
 		}
 		mcs_.push_back(r);
@@ -1850,7 +1858,7 @@ private:
 	std::vector<b2_h264_mb> mbs_;
 	std::vector<b2_h264_dbk> dbk_;
 	std::vector<b2_h264_mc> mcs_;
-	std::vector<uint32_t> items_[72], items_all_;      // inter work items per (class, height) bucket / concatenated
+	std::vector<uint32_t> items_[72], items_first_[72], items_all_;      // inter work items per (class, height) bucket / concatenated
 	std::vector<int16_t> coefs_;
 	size_t coef_used_ = 0;
 	uint32_t n_intra_;

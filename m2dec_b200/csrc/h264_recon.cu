@@ -988,8 +988,13 @@ __device__ __forceinline__ uint32_t add_res4(uint32_t w, int r0, int r1, int r2,
 	return pack4(clip255((int)(w & 255) + r0), clip255((int)((w >> 8) & 255) + r1), clip255((int)((w >> 16) & 255) + r2), clip255((int)(w >> 24) + r3));
 }
 
+// MODE 0: one launch does everything (the first list of a bi-predicted strip inside the thread) -- used when no
+// picture of the launch has bi-predicted strips, where it is the same code as MODE 2 but allocates its registers
+// better (895 vs 825 GB/s on P pictures); MODE 1: first-list passes; MODE 2: finishing passes.
+template <int MODE>
 __global__ void __launch_bounds__(I5_THREADS, B2_I5_CTAS)
 h264_inter5_kernel(const H4Job *__restrict__ jobs) {
+	constexpr bool first_pass = MODE == 1;
 	// dynamic shared memory (more than the 48 KB a kernel may declare statically)
 	extern __shared__ __align__(16) uint8_t s_dyn[];
 	uint32_t (*s_rows)[I5_THREADS] = reinterpret_cast<uint32_t(*)[I5_THREADS]>(s_dyn);                       // per thread: up to 16 rows x 2 words of prediction
@@ -998,12 +1003,15 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	const H4Job job = jobs[blockIdx.y];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t it = blockIdx.x * I5_THREADS + tid;
+	// first_pass: the first-list passes of bi-predicted strips (items [0, n_first)); else one item per strip
+	// for its last list (items [n_first, n_items)).  Each part is sorted by the class of ITS list.
+	const uint32_t base = MODE == 2 ? job.n_first : 0u, count = MODE == 0 ? job.n_items : (MODE == 1 ? job.n_first : job.n_items - job.n_first);
 	// whole warps beyond the list leave; in the list's last warp the lanes without an item stay (as strips of
 	// height 0) for the warp-wide parts
-	if ((it & ~31u) >= job.n_items) return;
-	const bool valid = it < job.n_items;
+	if ((it & ~31u) >= count) return;
+	const bool valid = it < count;
 	// the list comes sorted by (class, height) from the host: a warp runs one interpolation path
-	const uint32_t item = __ldg(job.items + (valid ? it : job.n_items - 1));
+	const uint32_t item = __ldg(job.items + base + (valid ? it : count - 1));
 	const int mb = item & 0xfffff, ri = (item >> 20) & 15, k = (item >> 24) & 3, wide = ((item >> 26) & 15) >= 6;
 	const b2_h264_mb m = job.mbs[mb];
 	const b2_h264_mc *mcp = job.mcs + m.mc_idx + ri;
@@ -1031,11 +1039,14 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	const uint8_t *refl = job.frames + job.frame_bytes * mc.ref_frame[lastl];
 	const int mvx = mc.mv[lastl][0], mvy = mc.mv[lastl][1];
 
-	// ---- first list of a bi-predicted strip ---------------------------------------------------------------
-	if (bi && h) {
-		const uint8_t *ref0 = job.frames + job.frame_bytes * mc.ref_frame[0];
-		if (wide) i5_first_list<2>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
-		else i5_first_list<1>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
+	// ---- first list of a bi-predicted strip: a launch of its own, before the one that finishes the strips ----
+	if (MODE != 2) {
+		if (bi && h) {
+			const uint8_t *ref0 = job.frames + job.frame_bytes * mc.ref_frame[0];
+			if (wide) i5_first_list<2>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
+			else i5_first_list<1>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
+		}
+		if (first_pass) return;
 	}
 	// ---- luma: prediction of the (last) list, parked -------------------------------------------------------
 	if (h) {
@@ -2560,7 +2571,7 @@ h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, i
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h) { return (32 + (size_t)n_jobs * mb_w * mb_h) * sizeof(int); }
 
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
-                      uint32_t max_items) {
+                      uint32_t max_items, uint32_t max_first) {
 	if (n_jobs <= 0) return 0;
 	if (phase == 0) {
 		const int n_mbs = mb_w * mb_h;
@@ -2570,10 +2581,19 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint16_t) * I5_QUEUE * (I5_THREADS / 32);
 			static bool attr_set = false;       // per process; the attribute is per device function
 			if (!attr_set) {
-				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
 				attr_set = true;
 			}
-			h264_inter5_kernel<<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
+			if (max_first) {
+				dim3 grid_first((max_first + I5_THREADS - 1) / I5_THREADS, n_jobs);
+				h264_inter5_kernel<1><<<grid_first, I5_THREADS, smem5, stream>>>(d_jobs);
+				if (launches) ++*launches;
+				h264_inter5_kernel<2><<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
+			} else {
+				h264_inter5_kernel<0><<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
+			}
 		} else {
 			dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
 			h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
@@ -2614,8 +2634,8 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 }
 
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense, bool intra_sparse,
-                bool deblock, int *sync_area, uint64_t *launches) {
-	if (max_items && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches, max_items) < 0) return -1;
+                bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first) {
+	if (max_items && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches, max_items, max_first) < 0) return -1;
 	if (intra_dense && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (intra_sparse && launch_h264_phase(stream, 3, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (deblock && launch_h264_phase(stream, 2, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;

@@ -23,7 +23,7 @@ struct Step {
 	std::vector<M2Job> m2;
 	void *d_jobs = nullptr;
 	bool intra_dense = false, intra_sparse = false, deblock = false;
-	uint32_t max_items = 0;
+	uint32_t max_items = 0, max_first = 0;
 };
 struct Group {
 	cudaStream_t stream = nullptr;
@@ -149,6 +149,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	job.coefs = (const int16_t *)(d + off[3]);
 	job.items = (const uint32_t *)(d + off[4]);
 	job.n_items = p->n_items;
+	job.n_first = p->n_items_first;
 	job.dst = p->dst; job.mb_w = p->mb_w; job.mb_h = p->mb_h; job.n_intra = (int32_t)p->n_intra;
 	int t = r->lane_len[lane]++;
 	std::vector<Step> &steps = r->groups[lane % r->groups.size()].steps;
@@ -156,6 +157,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	Step &s = steps[t];
 	s.h4.push_back(job);
 	if (p->n_items > s.max_items) s.max_items = p->n_items;
+	if (p->n_items_first > s.max_first) s.max_first = p->n_items_first;
 	if (p->n_intra > 0) (h264_intra_sparse((int)p->n_intra, (int)p->n_mbs) ? s.intra_sparse : s.intra_dense) = true;
 	s.deblock |= p->deblock != 0;
 	// algorithmic bytes: S(1 + 2 dbk) + R + C + M, split by kernel
@@ -254,7 +256,7 @@ extern "C" int b2_replay_run(b2_replay *r, int timed) {
 			const H4Job *jobs = (const H4Job *)s.d_jobs;
 			int n = (int)s.h4.size();
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 0], g.stream));
-			if (s.max_items && launch_h264_phase(g.stream, 0, jobs, n, mb_w, mb_h, g.sync_area, &launches, s.max_items) < 0) return -1;
+			if (s.max_items && launch_h264_phase(g.stream, 0, jobs, n, mb_w, mb_h, g.sync_area, &launches, s.max_items, s.max_first) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 1], g.stream));
 			if (s.intra_dense && launch_h264_phase(g.stream, 1, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (s.intra_sparse && launch_h264_phase(g.stream, 3, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;

@@ -330,6 +330,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	job.n_intra = (int32_t)p->n_intra;
 	job.items = (const uint32_t *)(sl->dev + off_items);
 	job.n_items = p->n_items;
+	job.n_first = p->n_items_first;
 	memcpy(sl->host, &job, sizeof(job));
 	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
 	memcpy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
@@ -341,7 +342,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (before_write(s, p->dst) < 0) return -1;
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_items,
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
-	                p->deblock != 0, s->sync_area, &s->launches) < 0) return -1;
+	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first) < 0) return -1;
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
 	s->frame_written[p->dst] = true;
