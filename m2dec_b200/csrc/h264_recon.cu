@@ -181,84 +181,8 @@ __device__ void block_residual8x8(const H4Job &job, const b2_h264_mb &m, int q, 
 // ------------------------------------------------------------------------------------------------
 // inter prediction
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
-// Four horizontally adjacent luma samples at integer position (x..x+3, y) + fraction (fx, fy).
-// Loads the (up to) 6 x 9 reference window once, with edge replication by clamping.
-__device__ void luma_quad(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int out[4]) {
-	const int r0 = fy ? -2 : 0, r1 = fy ? 3 : 0;
-	const int c0 = fx ? -2 : 0, c1 = fx ? 6 : 3;
-	// horizontal half-pel intermediates (unrounded) for the rows that are needed
-	int hb[6][4];       // b1 for rows -2..3 at columns 0..3
-	int px[6][5];       // integer samples rows -2..3, columns 0..4
-	int vh[5];          // h1 (vertical, unrounded) at columns 0..4, row 0
-#pragma unroll
-	for (int r = 0; r < 6; ++r) {
-		int ry = r - 2;
-		if (ry < r0 || ry > r1) continue;
-		int yy = min(max(y + ry, 0), H - 1);
-		const uint8_t *row = ref + (size_t)yy * W;
-		int v[9];
-#pragma unroll
-		for (int c = 0; c < 9; ++c) {
-			int cx = c - 2;
-			v[c] = (cx >= c0 && cx <= c1) ? (int)__ldg(row + min(max(x + cx, 0), W - 1)) : 0;
-		}
-#pragma unroll
-		for (int i = 0; i < 5; ++i) px[r][i] = v[i + 2];
-		if (fx) {
-#pragma unroll
-			for (int i = 0; i < 4; ++i) hb[r][i] = tap6(v[i], v[i + 1], v[i + 2], v[i + 3], v[i + 4], v[i + 5]);
-		}
-	}
-	if (fy) {
-#pragma unroll
-		for (int i = 0; i < 5; ++i) vh[i] = tap6(px[0][i], px[1][i], px[2][i], px[3][i], px[4][i], px[5][i]);
-	}
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		int G = px[2][i];
-		int v;
-		if (!fx && !fy) {
-			v = G;
-		} else if (!fy) {
-			int b = clip255((hb[2][i] + 16) >> 5);
-			v = fx == 2 ? b : ((fx == 1 ? G : px[2][i + 1]) + b + 1) >> 1;
-		} else if (!fx) {
-			int h = clip255((vh[i] + 16) >> 5);
-			v = fy == 2 ? h : ((fy == 1 ? G : px[3][i]) + h + 1) >> 1;
-		} else {
-			int b = clip255((hb[2][i] + 16) >> 5);
-			int s = clip255((hb[3][i] + 16) >> 5);
-			int h = clip255((vh[i] + 16) >> 5);
-			int m = clip255((vh[i + 1] + 16) >> 5);
-			int j = clip255((tap6(hb[0][i], hb[1][i], hb[2][i], hb[3][i], hb[4][i], hb[5][i]) + 512) >> 10);
-			if (fx == 2 && fy == 2) v = j;
-			else if (fx == 2) v = ((fy == 1 ? b : s) + j + 1) >> 1;
-			else if (fy == 2) v = ((fx == 1 ? h : m) + j + 1) >> 1;
-			else v = ((fy == 1 ? b : s) + (fx == 1 ? h : m) + 1) >> 1;
-		}
-		out[i] = v;
-	}
-}
-
-// Four adjacent NV12 chroma bytes (Cb Cr Cb Cr) starting at byte xb (even) of chroma row y.
-__device__ void chroma_quad(const uint8_t *__restrict__ ref, int W, int CH, int xb, int y, int mvx, int mvy, int out[4]) {
-	int fx = mvx & 7, fy = mvy & 7;
-	int cw = W >> 1;
-	int cy0 = min(max(y + (mvy >> 3), 0), CH - 1), cy1 = min(max(y + (mvy >> 3) + 1, 0), CH - 1);
-	const uint8_t *r0 = ref + (size_t)cy0 * W, *r1 = ref + (size_t)cy1 * W;
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		int comp = i & 1;
-		int cx = (xb >> 1) + (i >> 1) + (mvx >> 3);
-		int x0 = min(max(cx, 0), cw - 1) * 2 + comp, x1 = min(max(cx + 1, 0), cw - 1) * 2 + comp;
-		int A = __ldg(r0 + x0), B = __ldg(r0 + x1), C = __ldg(r1 + x0), D = __ldg(r1 + x1);
-		out[i] = ((8 - fx) * (8 - fy) * A + fx * (8 - fy) * B + (8 - fx) * fy * C + fx * fy * D + 32) >> 6;
-	}
-}
-
-// ---- inter kernel ----------------------------------------------------------------------------------
+// ---- inter kernel, 4x4 items (kept behind B2_INTER5=0 as the comparison baseline of the strip kernel) ----
 // Work item = one 4x4 luma block of an inter macroblock plus its 2x2 Cb and Cr samples.  A CTA takes
 // 32 consecutive macroblocks (512 items), and
 //   A. classifies every item by the interpolation it needs (copy / horizontal / vertical /
@@ -678,13 +602,7 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 #define B2_I5_CTAS 5
 #endif
 constexpr int I5_THREADS = B2_I5_THREADS;
-constexpr int I5_CLASSES = 12;        // interpolation class (0..5) + 6 * (strip is 8 wide)
 
-// item: bits 0..5 MB slot, 6..9 record, 10..11 x (4-sample units inside the MB), 12..13 y, 14..16 height
-// (4-sample units), 17 wide, 18..21 class
-__device__ __forceinline__ uint32_t i5_pack(int slot, int rec, int x4, int y4, int h4, int wide, int cls) {
-	return (uint32_t)slot | ((uint32_t)rec << 6) | ((uint32_t)x4 << 10) | ((uint32_t)y4 << 12) | ((uint32_t)h4 << 14) | ((uint32_t)wide << 17) | ((uint32_t)cls << 18);
-}
 
 __device__ __forceinline__ int frac_class(int fx, int fy) {
 	if (!fx && !fy) return 0;
@@ -1540,53 +1458,6 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 	}
 }
 
-// ------------------------------------------------------------------------------------------------
-// deblocking wavefront: one warp per macroblock of the diagonal
-// ------------------------------------------------------------------------------------------------
-// filter one line across an edge; p = pointer to q0, st = step across the edge
-__device__ void filter_line(uint8_t *px, ptrdiff_t st, int bs, int alpha, int beta, int tc0, bool luma) {
-	int p0 = px[-st], p1 = px[-2 * st], q0 = px[0], q1 = px[st];
-	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-	if (bs == 4) {
-		if (luma) {
-			int p2 = px[-3 * st], q2 = px[2 * st];
-			bool strong = abs(p0 - q0) < (alpha >> 2) + 2;
-			if (strong && abs(p2 - p0) < beta) {
-				int p3 = px[-4 * st];
-				px[-st] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-				px[-2 * st] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-				px[-3 * st] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-			} else {
-				px[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-			}
-			if (strong && abs(q2 - q0) < beta) {
-				int q3 = px[3 * st];
-				px[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-				px[st] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-				px[2 * st] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-			} else {
-				px[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-			}
-		} else {
-			px[-st] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-			px[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
-		}
-		return;
-	}
-	int tc;
-	if (luma) {
-		int p2 = px[-3 * st], q2 = px[2 * st];
-		int ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
-		tc = tc0 + ap + aq;
-		if (ap) px[-2 * st] = (uint8_t)(p1 + min(max((p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1, -tc0), tc0));
-		if (aq) px[st] = (uint8_t)(q1 + min(max((q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1, -tc0), tc0));
-	} else {
-		tc = tc0 + 1;
-	}
-	int delta = min(max(((q0 - p0) * 4 + (p1 - q1) + 4) >> 3, -tc), tc);
-	px[-st] = (uint8_t)clip255(p0 + delta);
-	px[0] = (uint8_t)clip255(q0 - delta);
-}
 
 // Deblock one macroblock with one warp, in two register passes.
 //   V pass (vertical edges): lane l < 16 holds luma row l (columns -4..15) unpacked in registers,
@@ -1600,183 +1471,6 @@ struct DbkTile {
 	uint8_t y[20][36];      // rows -4..15 at index r+4, columns -4..15 at index c+4; 36-byte pitch: conflict-free columns
 	uint8_t c[10][36];      // chroma rows -2..7 at index r+2, byte columns -4..15 at index c+4
 };
-
-// filter across the edge in front of v[q]: p3..p0 = v[q-4..q-1], q0..q3 = v[q..q+3], stride `st` entries
-template <int ST>
-__device__ __forceinline__ void filter_regs(int *v, int q, int bs, int alpha, int beta, int tc0, bool luma) {
-	int p0 = v[q - ST], p1 = v[q - 2 * ST], q0 = v[q], q1 = v[q + ST];
-	if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
-	if (bs == 4) {
-		if (luma) {
-			int p2 = v[q - 3 * ST], q2 = v[q + 2 * ST];
-			bool strong = abs(p0 - q0) < (alpha >> 2) + 2;
-			if (strong && abs(p2 - p0) < beta) {
-				int p3 = v[q - 4 * ST];
-				v[q - ST] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
-				v[q - 2 * ST] = (p2 + p1 + p0 + q0 + 2) >> 2;
-				v[q - 3 * ST] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
-			} else {
-				v[q - ST] = (2 * p1 + p0 + q1 + 2) >> 2;
-			}
-			if (strong && abs(q2 - q0) < beta) {
-				int q3 = v[q + 3 * ST];
-				v[q] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
-				v[q + ST] = (p0 + q0 + q1 + q2 + 2) >> 2;
-				v[q + 2 * ST] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
-			} else {
-				v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
-			}
-		} else {
-			v[q - ST] = (2 * p1 + p0 + q1 + 2) >> 2;
-			v[q] = (2 * q1 + q0 + p1 + 2) >> 2;
-		}
-		return;
-	}
-	int tc;
-	if (luma) {
-		int p2 = v[q - 3 * ST], q2 = v[q + 2 * ST];
-		int ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
-		tc = tc0 + ap + aq;
-		if (ap) v[q - 2 * ST] = p1 + min(max((p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1, -tc0), tc0);
-		if (aq) v[q + ST] = q1 + min(max((q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1, -tc0), tc0);
-	} else {
-		tc = tc0 + 1;
-	}
-	int delta = min(max(((q0 - p0) * 4 + (p1 - q1) + 4) >> 3, -tc), tc);
-	v[q - ST] = clip255(p0 + delta);
-	v[q] = clip255(q0 - delta);
-}
-
-struct EdgeParams { int alpha, beta, ia; };
-__device__ __forceinline__ EdgeParams edge_params(int qp, int aoff, int boff) {
-	EdgeParams e;
-	e.ia = min(max(qp + aoff, 0), 51);
-	int ib = min(max(qp + boff, 0), 51);
-	e.alpha = c_alpha[e.ia];
-	e.beta = c_beta[ib];
-	return e;
-}
-
-__device__ void deblock_mb(const H4Job &job, const b2_h264_dbk *dp, int mbx, int mby, DbkTile &tl, int lane) {
-	const b2_h264_dbk d = *dp;
-	const int W = job.mb_w * 16, H = job.mb_h * 16;
-	uint8_t *fy = job.frames + job.frame_bytes * job.dst;
-	uint8_t *py = fy + (size_t)mby * 16 * W + mbx * 16;
-	uint8_t *pc = fy + (size_t)W * H + (size_t)mby * 8 * W + mbx * 16;
-	const bool left_ok = d.flags & B2_DBK_LEFT_EDGE, top_ok = d.flags & B2_DBK_TOP_EDGE;
-	int nqy[2] = {0, 0}, nqb[2] = {0, 0}, nqr[2] = {0, 0};
-	if (left_ok) { const b2_h264_dbk *n = dp - 1; nqy[0] = n->qp_y; nqb[0] = n->qp_cb; nqr[0] = n->qp_cr; }
-	if (top_ok) { const b2_h264_dbk *n = dp - job.mb_w; nqy[1] = n->qp_y; nqb[1] = n->qp_cb; nqr[1] = n->qp_cr; }
-
-	// ---- V pass ---------------------------------------------------------------------------------
-	if (lane < 24) {
-		const bool luma = lane < 16;
-		const int row = luma ? lane : lane - 16;
-		const uint8_t *src = luma ? py + (size_t)row * W : pc + (size_t)row * W;
-		uint32_t w[5];
-		w[0] = mbx > 0 ? __ldcg(reinterpret_cast<const uint32_t *>(src - 4)) : 0;
-#pragma unroll
-		for (int k = 1; k < 5; ++k) w[k] = __ldcg(reinterpret_cast<const uint32_t *>(src + (k - 1) * 4));
-		int v[20];
-#pragma unroll
-		for (int i = 0; i < 20; ++i) v[i] = (w[i >> 2] >> ((i & 3) * 8)) & 255;
-		if (luma) {
-			const int seg = row >> 2;
-#pragma unroll
-			for (int e = 0; e < 4; ++e) {
-				int bs = (d.bs_v >> (8 * e + 2 * seg)) & 3;
-				if (!bs || (e == 0 && !left_ok)) continue;
-				if (e == 0 && (d.flags & B2_DBK_LEFT_BS4)) bs = 4;
-				EdgeParams ep = edge_params(e ? d.qp_y : (d.qp_y + nqy[0] + 1) >> 1, d.alpha_off, d.beta_off);
-				if (ep.alpha) filter_regs<1>(v, 4 + 4 * e, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, true);
-			}
-		} else {
-			const int seg = row >> 1;
-#pragma unroll
-			for (int e = 0; e < 4; e += 2) {
-				int bs = (d.bs_v >> (8 * e + 2 * seg)) & 3;
-				if (!bs || (e == 0 && !left_ok)) continue;
-				if (e == 0 && (d.flags & B2_DBK_LEFT_BS4)) bs = 4;
-#pragma unroll
-				for (int comp = 0; comp < 2; ++comp) {
-					int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr[0] : nqb[0];
-					EdgeParams ep = edge_params(e ? qc : (qc + qn + 1) >> 1, d.alpha_off, d.beta_off);
-					if (ep.alpha) filter_regs<2>(v, 4 + 4 * e + comp, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, false);
-				}
-			}
-		}
-		uint32_t *dstw = reinterpret_cast<uint32_t *>(luma ? &tl.y[4 + row][0] : &tl.c[2 + row][0]);
-#pragma unroll
-		for (int k = 0; k < 5; ++k)
-			dstw[k] = (uint32_t)v[4 * k] | ((uint32_t)v[4 * k + 1] << 8) | ((uint32_t)v[4 * k + 2] << 16) | ((uint32_t)v[4 * k + 3] << 24);
-	} else if (lane < 30 && mby > 0) {
-		// rows above: luma -4..-1 (lanes 24..27), chroma -2..-1 (lanes 28, 29); columns 0..15 only
-		const bool luma = lane < 28;
-		const int r = luma ? lane - 28 : lane - 30;          // -4..-1 / -2..-1
-		const uint8_t *src = luma ? py + (ptrdiff_t)r * W : pc + (ptrdiff_t)r * W;
-		uint32_t *dstw = reinterpret_cast<uint32_t *>(luma ? &tl.y[4 + r][0] : &tl.c[2 + r][0]);
-#pragma unroll
-		for (int k = 1; k < 5; ++k) dstw[k] = __ldcg(reinterpret_cast<const uint32_t *>(src + (k - 1) * 4));
-	}
-	__syncwarp();
-	// ---- H pass ---------------------------------------------------------------------------------
-	if (d.bs_h) {
-		const bool luma = lane < 16;
-		const int col = lane & 15;
-		if (luma) {
-			int v[20];
-#pragma unroll
-			for (int i = 0; i < 20; ++i) v[i] = tl.y[i][4 + col];
-			const int seg = col >> 2;
-#pragma unroll
-			for (int e = 0; e < 4; ++e) {
-				int bs = (d.bs_h >> (8 * e + 2 * seg)) & 3;
-				if (!bs || (e == 0 && !top_ok)) continue;
-				if (e == 0 && (d.flags & B2_DBK_TOP_BS4)) bs = 4;
-				EdgeParams ep = edge_params(e ? d.qp_y : (d.qp_y + nqy[1] + 1) >> 1, d.alpha_off, d.beta_off);
-				if (ep.alpha) filter_regs<1>(v, 4 + 4 * e, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, true);
-			}
-#pragma unroll
-			for (int i = 1; i < 20; ++i) tl.y[i][4 + col] = (uint8_t)v[i];
-		} else {
-			int v[10];
-#pragma unroll
-			for (int i = 0; i < 10; ++i) v[i] = tl.c[i][4 + col];
-			const int seg = col >> 2, comp = col & 1;
-#pragma unroll
-			for (int e = 0; e < 4; e += 2) {
-				int bs = (d.bs_h >> (8 * e + 2 * seg)) & 3;
-				if (!bs || (e == 0 && !top_ok)) continue;
-				if (e == 0 && (d.flags & B2_DBK_TOP_BS4)) bs = 4;
-				int qc = comp ? d.qp_cr : d.qp_cb, qn = comp ? nqr[1] : nqb[1];
-				EdgeParams ep = edge_params(e ? qc : (qc + qn + 1) >> 1, d.alpha_off, d.beta_off);
-				if (ep.alpha) filter_regs<1>(v, 2 + 2 * e, bs, ep.alpha, ep.beta, bs < 4 ? c_tc0[ep.ia][bs - 1] : 0, false);
-			}
-#pragma unroll
-			for (int i = 1; i < 10; ++i) tl.c[i][4 + col] = (uint8_t)v[i];
-		}
-		__syncwarp();
-	}
-	// ---- store: luma rows -3..15, chroma rows -1..7; word 0 (columns -4..-1) only when a left MB exists
-#pragma unroll
-	for (int k = 0; k < 3; ++k) {
-		int i = lane + 32 * k;
-		if (i < 95) {
-			int r = i / 5 - 3, w = i % 5;
-			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (w > 0 && top_ok);
-			if (ok) __stcg(reinterpret_cast<uint32_t *>(py + (ptrdiff_t)r * W + (w - 1) * 4), *reinterpret_cast<const uint32_t *>(&tl.y[r + 4][w * 4]));
-		}
-	}
-#pragma unroll
-	for (int k = 0; k < 2; ++k) {
-		int i = lane + 32 * k;
-		if (i < 45) {
-			int r = i / 5 - 1, w = i % 5;
-			bool ok = r >= 0 ? (w > 0 || mbx > 0) : (w > 0 && top_ok);
-			if (ok) __stcg(reinterpret_cast<uint32_t *>(pc + (ptrdiff_t)r * W + (w - 1) * 4), *reinterpret_cast<const uint32_t *>(&tl.c[r + 2][w * 4]));
-		}
-	}
-}
 
 // ------------------------------------------------------------------------------------------------
 // deblocking, second form: one warp walks a macroblock row and keeps a sliding tile.
