@@ -1858,9 +1858,11 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 // ((threshold - 1 + 0x8000) - |difference| has the bit set exactly when the test holds) and
 // applied by masking the clipping bounds, so the filter has no branch except the bS 4 case.
 // ------------------------------------------------------------------------------------------------
-struct DbkTile2 {
-	uint32_t y[20][21];     // one packed pair per sample; rows -4..15 at r + 4, columns -4..15 at c + 4; odd pitch: conflict-free rows and columns
-	uint32_t c[10][21];     // chroma rows -2..7 at r + 2, byte columns (Cb Cr interleaved) -4..15 at c + 4
+struct alignas(16) DbkTile2 {
+	// one packed pair per sample; rows -4..15 at r + 4, columns -4..15 at c + 4.  Pitch 28 words: rows are 16-byte
+	// aligned (whole lines move as 128-bit accesses) and eight consecutive rows start in eight different bank groups
+	uint32_t y[20][28];
+	uint32_t c[10][28];     // chroma rows -2..7 at r + 2, byte columns (Cb Cr interleaved) -4..15 at c + 4
 };
 
 __device__ __forceinline__ uint32_t vneg2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
@@ -2047,7 +2049,7 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 				}
 				if (carry_in) {
 #pragma unroll
-					for (int i = 0; i < 4; ++i) v[i] = trow[i];
+					for (int i = 0; i < 4; ++i) v[i] = trow[i];       // (one 128-bit load: the row is 16-byte aligned)
 				}
 			} else {
 #pragma unroll
@@ -2065,15 +2067,17 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 			}
 			if (luma) {
 #pragma unroll
-				for (int i = 0; i < 20; ++i) trow[i] = v[i];
+				for (int j = 0; j < 5; ++j) reinterpret_cast<uint4 *>(trow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 			} else {
 #pragma unroll
 				for (int i = 0; i < 10; ++i) trow[2 * i + comp] = v[2 + i];
 			}
 			if (lane < 24) {
 				uint32_t *d = (luma ? tl.y[lane >> 2] : tl.c[(lane - 16) >> 2]) + 4 + 4 * (lane & 3);
-				pair2(twA, twB, 0x5410u, d[0], d[1]);
-				pair2(twA, twB, 0x7632u, d[2], d[3]);
+				uint4 e;
+				pair2(twA, twB, 0x5410u, e.x, e.y);
+				pair2(twA, twB, 0x7632u, e.z, e.w);
+				*reinterpret_cast<uint4 *>(d) = e;
 			}
 		}
 		__syncwarp();
@@ -2115,7 +2119,9 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 			for (int j = 0; j < 5; ++j) {
 				if ((j == 0 && x == 0) || (j == 4 && carry_out)) continue;
 				uint32_t wa, wb;
-				unpair4(src + 4 * j, wa, wb);
+				const uint4 e4 = *reinterpret_cast<const uint4 *>(src + 4 * j);
+				const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+				unpair4(ev, wa, wb);
 				__stcg(reinterpret_cast<uint32_t *>(dA + 4 * (j - 1)), wa);
 				if (validB) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * (j - 1)), wb);
 			}
@@ -2128,7 +2134,9 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 #pragma unroll
 			for (int j = 0; j < 4; ++j) {
 				uint32_t wa, wb;
-				unpair4(src + 4 * j, wa, wb);
+				const uint4 e4 = *reinterpret_cast<const uint4 *>(src + 4 * j);
+				const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+				unpair4(ev, wa, wb);
 				if (topA) __stcg(reinterpret_cast<uint32_t *>(dA + 4 * j), wa);
 				if (topB) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * j), wb);
 			}
@@ -2137,7 +2145,7 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 		if (carry_out && lane < 24) {
 			uint32_t *rw = lane < 16 ? tl.y[4 + lane] : tl.c[2 + lane - 16];
 #pragma unroll
-			for (int i = 0; i < 4; ++i) rw[i] = rw[16 + i];
+			for (int i = 0; i < 4; ++i) rw[i] = rw[16 + i];      // (16-byte aligned both ways)
 		}
 		carry_in = carry_out;
 		done_to = x + 1;
