@@ -1,13 +1,14 @@
 // h264_recon.cu — K1..K4: H.264 picture reconstruction on sm_100a.
 //
-//   h264_inter_kernel   K2+K1  motion compensation (luma 6-tap quarter-pel, chroma eighth-pel
-//                              bilinear, edge replication by coordinate clamp) fused with
-//                              dequantisation + 4x4 inverse transform + residual add/clip for
-//                              every inter macroblock; each output byte is written once.
-//                              Macroblocks with transform_size_8x8_flag get the 8x8 transform.
-//   h264_intra_kernel   K3+K1  intra 4x4 / 8x8 / 16x16 / chroma prediction + residual, and I_PCM, as
-//                              an MB-diagonal wavefront (slope 2: left, top, top-right deps).
-//   h264_deblock_kernel K4     in-loop filter from the per-MB strength records, same wavefront.
+//   h264_inter5_kernel       K2+K1  motion compensation (luma 6-tap quarter-pel, chroma eighth-pel bilinear, edge
+//                                   replication by coordinate clamp, both lists, weighted prediction) fused with
+//                                   dequantisation + 4x4 / 8x8 inverse transform + residual add/clip for every
+//                                   inter macroblock; work item = one vertical strip of a motion record, from a
+//                                   host-sorted list; each output byte is written once.
+//   h264_wave_kernel<1>      K3+K1  intra 4x4 / 8x8 / 16x16 / chroma prediction + residual, and I_PCM, as a
+//   h264_intra_sparse_kernel        persistent MB-row wavefront (I pictures) / per-macroblock flags (P, B pictures).
+//   h264_deblock2_kernel     K4     in-loop filter from the per-MB strength records, two pictures per warp on
+//   h264_wave_kernel<2>             packed 16x2 lanes (batched launches) / one picture per launch (plugin path).
 //
 // Arithmetic restated from the reference (src/lib/h264.cpp): dequant tables 964-1054 and
 // coeff_writeback 2005-2022; 4x4 transform 2145-2269; 8x8 transform 3942-4080; DC transforms
@@ -182,22 +183,7 @@ __device__ void block_residual8x8(const H4Job &job, const b2_h264_mb &m, int q, 
 // inter prediction
 // ------------------------------------------------------------------------------------------------
 
-// ---- inter kernel, 4x4 items (kept behind B2_INTER5=0 as the comparison baseline of the strip kernel) ----
-// Work item = one 4x4 luma block of an inter macroblock plus its 2x2 Cb and Cr samples.  A CTA takes
-// 32 consecutive macroblocks (512 items), and
-//   A. classifies every item by the interpolation it needs (copy / horizontal / vertical /
-//      diagonal / centre column / centre row) and counting-sorts the items by class in shared
-//      memory, so that warps run one interpolation path instead of diverging over six;
-//   B. compacts the coded 4x4 blocks (luma + chroma) and runs their dequantisation + inverse
-//      transform, one block per thread, into shared memory;
-//   C. per item: reference window in packed registers (aligned 32-bit loads + funnel shift), the
-//      6-tap filter as dp4a dot products (horizontal) / packed 16-bit lanes (vertical), residual add,
-//      clip, four luma word stores; chroma eighth-pel bilinear in packed 16-bit lanes, two word stores.
-// Every output byte of an inter macroblock is written exactly once.
-__device__ __forceinline__ int byte_of(const uint32_t w[3], int i) { return (w[i >> 2] >> ((i & 3) * 8)) & 255; }
-constexpr int INTER_MBS = 32;
-constexpr int INTER_THREADS = INTER_MBS * 16;
-constexpr int N_CLASS = 6;
+// ---- helpers of the inter kernel: packed reference rows, 6-tap filters --------------------------------
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
 	int d;
@@ -214,378 +200,11 @@ __device__ __forceinline__ void hfilter4(const uint32_t pk[3], int out[4]) {
 	out[3] = dp4a_us(pk[0], PACK4(0, 0, 0, 1), dp4a_us(pk[1], PACK4(-5, 20, 20, -5), dp4a_us(pk[2], PACK4(1, 0, 0, 0), 0)));
 }
 
-// n bytes (n <= 12) starting at column x of a reference row, as little-endian words; columns are
-// clamped to the picture (edge replication) on the slow path
-__device__ __forceinline__ void load_row(const uint8_t *__restrict__ row, int W, int x, bool fast, int nwords, uint32_t out[3]) {
-	if (fast) {
-		const uint8_t *p = row + x;
-		const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-		unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-		uint32_t w0 = __ldg(a), w1 = __ldg(a + 1);
-		out[0] = __funnelshift_r(w0, w1, sh);
-		if (nwords > 1) {
-			uint32_t w2 = __ldg(a + 2);
-			out[1] = __funnelshift_r(w1, w2, sh);
-			if (nwords > 2) out[2] = __funnelshift_r(w2, __ldg(a + 3), sh);
-		}
-	} else {
-		out[0] = out[1] = out[2] = 0;
-		for (int i = 0; i < nwords * 4; ++i) out[i >> 2] |= (uint32_t)__ldg(row + min(max(x + i, 0), W - 1)) << ((i & 3) * 8);
-	}
-}
-
-__device__ __forceinline__ int avg2(int a, int b) { return (a + b + 1) >> 1; }
-
 // vertical 6-tap on two packed 16-bit lanes; result lanes carry a +2560 bias
 __device__ __forceinline__ uint32_t vtap_packed(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
 	return (a + f) + 20u * (c + d) + 0x0A000A00u - 5u * (b + e);
 }
 __device__ __forceinline__ int vfinish(uint32_t lane16) { return clip255(((int)lane16 - 2560 + 16) >> 5); }
-
-// vertical half-sample values h(r, c) = clip((tap6 + 16) >> 5) for rows 0..3, columns 0..3 of the words R[0..8]
-// (R[k] = four bytes of reference row y - 2 + k)
-__device__ __forceinline__ void vhalf4x4(const uint32_t R[9], int out[16]) {
-	uint32_t E[9], O[9];
-#pragma unroll
-	for (int k = 0; k < 9; ++k) { E[k] = R[k] & 0x00FF00FFu; O[k] = (R[k] >> 8) & 0x00FF00FFu; }
-#pragma unroll
-	for (int r = 0; r < 4; ++r) {
-		uint32_t te = vtap_packed(E[r], E[r + 1], E[r + 2], E[r + 3], E[r + 4], E[r + 5]);
-		uint32_t to = vtap_packed(O[r], O[r + 1], O[r + 2], O[r + 3], O[r + 4], O[r + 5]);
-		out[4 * r + 0] = vfinish(te & 0xFFFFu);
-		out[4 * r + 1] = vfinish(to & 0xFFFFu);
-		out[4 * r + 2] = vfinish(te >> 16);
-		out[4 * r + 3] = vfinish(to >> 16);
-	}
-}
-
-__global__ void __launch_bounds__(INTER_THREADS, 2)
-h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
-	__shared__ __align__(16) int16_t s_res[INTER_MBS][24][16];
-	__shared__ uint32_t s_has[INTER_MBS];
-	__shared__ uint16_t s_items[INTER_THREADS];
-	__shared__ uint16_t s_coded[INTER_MBS * 24];
-	__shared__ uint8_t s_mcsel[INTER_THREADS];
-	__shared__ int s_wcnt[N_CLASS][INTER_THREADS / 32];
-	__shared__ int s_cbase[N_CLASS + 1];
-	__shared__ int s_ccnt[2 * (INTER_THREADS / 32) + 1];
-
-	const H4Job job = jobs[blockIdx.y];
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int mb0 = blockIdx.x * INTER_MBS;
-	const int W = job.mb_w * 16, H = job.mb_h * 16;
-	const size_t luma_size = (size_t)W * H;
-
-	// ---- A. classify + counting sort -------------------------------------------------------------
-	int cls = 7;
-	{
-		const int mb = mb0 + (tid >> 4);
-		if (tid < INTER_MBS) s_has[tid] = 0;
-		if (mb < n_mbs) {
-			const b2_h264_mb *mp = job.mbs + mb;
-			if (mp->type == B2_H4_INTER) {
-				const int x4 = tid & 3, y4 = (tid >> 2) & 3;
-				const int cnt = mp->mc_cnt;
-				const b2_h264_mc *rec = job.mcs + mp->mc_idx;
-				int sel = 0, mvx = 0, mvy = 0;
-				for (int i = 0; i < cnt; ++i) {
-					int4 raw = __ldg(reinterpret_cast<const int4 *>(rec + i));
-					const b2_h264_mc &mc = *reinterpret_cast<const b2_h264_mc *>(&raw);   // first 16 bytes: pos .. mv
-					int px0 = mc.pos & 3, py0 = mc.pos >> 2;
-					if (x4 >= px0 && x4 < px0 + (mc.size & 15) && y4 >= py0 && y4 < py0 + (mc.size >> 4)) {
-						const int l = mc.ref_frame[0] >= 0 ? 0 : 1;
-						sel = i; mvx = mc.mv[l][0]; mvy = mc.mv[l][1];
-						break;
-					}
-				}
-				s_mcsel[tid] = (uint8_t)sel;
-				const int fx = mvx & 3, fy = mvy & 3;
-				if (!fx && !fy) cls = 0;
-				else if (!fy) cls = 1;
-				else if (!fx) cls = 2;
-				else if (fx == 2) cls = 4;          // b / s with j, or j alone
-				else if (fy == 2) cls = 5;          // h / m with j
-				else cls = 3;                       // b / s with h / m
-			}
-		}
-	}
-	int rank = 0;
-#pragma unroll
-	for (int c = 0; c < N_CLASS; ++c) {
-		unsigned mask = __ballot_sync(0xffffffffu, cls == c);
-		if (cls == c) rank = __popc(mask & ((1u << lane) - 1));
-		if (lane == 0) s_wcnt[c][warp] = __popc(mask);
-	}
-	// ---- B. list of coded 4x4 blocks (luma 0..15, Cb 16..19, Cr 20..23) --------------------------
-	int coded_rank[2];
-	bool coded[2];
-#pragma unroll
-	for (int rnd = 0; rnd < 2; ++rnd) {
-		int j = tid + rnd * INTER_THREADS;
-		bool c = false;
-		if (j < INTER_MBS * 24) {
-			int mb = mb0 + j / 24, bk = j % 24;
-			if (mb < n_mbs) {
-				const b2_h264_mb *mp = job.mbs + mb;
-				if (mp->type == B2_H4_INTER) {
-					uint32_t nz = mp->nz;
-					c = bk < 16 ? (nz >> (1 + bk)) & 1 : (((nz >> (2 + bk)) & 1) || ((nz >> 17) & 1));
-				}
-			}
-		}
-		unsigned mask = __ballot_sync(0xffffffffu, c);
-		coded[rnd] = c;
-		coded_rank[rnd] = __popc(mask & ((1u << lane) - 1));
-		if (lane == 0) s_ccnt[warp + rnd * (INTER_THREADS / 32)] = __popc(mask);
-	}
-	__syncthreads();
-	if (tid == 0) {
-		int acc = 0;
-		for (int c = 0; c < N_CLASS; ++c) {
-			s_cbase[c] = acc;
-			for (int w = 0; w < INTER_THREADS / 32; ++w) { int n = s_wcnt[c][w]; s_wcnt[c][w] = acc; acc += n; }
-		}
-		s_cbase[N_CLASS] = acc;
-	} else if (tid == 32) {
-		int acc = 0;
-		const int nw = 2 * (INTER_THREADS / 32);
-		for (int w = 0; w < nw; ++w) { int n = s_ccnt[w]; s_ccnt[w] = acc; acc += n; }
-		s_ccnt[nw] = acc;
-	}
-	__syncthreads();
-	if (cls < N_CLASS) s_items[s_wcnt[cls][warp] + rank] = (uint16_t)tid;
-#pragma unroll
-	for (int rnd = 0; rnd < 2; ++rnd)
-		if (coded[rnd]) s_coded[s_ccnt[warp + rnd * (INTER_THREADS / 32)] + coded_rank[rnd]] = (uint16_t)(tid + rnd * INTER_THREADS);
-	__syncthreads();
-	// ---- residuals of the coded blocks -------------------------------------------------------------
-	const int n_coded = s_ccnt[2 * (INTER_THREADS / 32)];
-	for (int k = tid; k < n_coded; k += INTER_THREADS) {
-		int j = s_coded[k];
-		int slot = j / 24, bk = j % 24;
-		const b2_h264_mb m = job.mbs[mb0 + slot];
-		if (bk < 16 && (m.flags & B2_H4_T8x8)) {
-			// 8x8 transform: the entry of the first sub-block does the whole block
-			if ((bk & 3) == 0) {
-				block_residual8x8(job, m, bk >> 2, s_res[slot]);
-				atomicOr(&s_has[slot], 0xfu << bk);
-			}
-		} else if (block_residual(job, m, bk, s_res[slot][bk])) atomicOr(&s_has[slot], 1u << bk);
-	}
-	__syncthreads();
-
-	// ---- C. one item per thread, in class order ------------------------------------------------------
-	const int n_items = s_cbase[N_CLASS];
-	if (tid >= n_items) return;
-	const int item = s_items[tid];
-	const int slot = item >> 4, x4 = item & 3, y4 = (item >> 2) & 3;
-	const int mb = mb0 + slot;
-	const int mbx = mb % job.mb_w, mby = mb / job.mb_w;
-	const b2_h264_mb *mp = job.mbs + mb;
-	const b2_h264_mc *mcp = job.mcs + mp->mc_idx + s_mcsel[item];
-	int4 raw0 = __ldg(reinterpret_cast<const int4 *>(mcp)), raw1 = __ldg(reinterpret_cast<const int4 *>(mcp) + 1);
-	b2_h264_mc mc;
-	reinterpret_cast<int4 *>(&mc)[0] = raw0;
-	reinterpret_cast<int4 *>(&mc)[1] = raw1;
-	uint8_t *dst_y = job.frames + job.frame_bytes * job.dst;
-	uint8_t *dst_c = dst_y + luma_size;
-	const uint32_t has = s_has[slot];
-	const int n_lists = (mc.ref_frame[0] >= 0) + (mc.ref_frame[1] >= 0);
-
-	int px[16], p0[16];
-	int cb_[2][2][2], cr_[2][2][2];      // [list slot][row][sample]
-	int k = 0;
-#pragma unroll 1
-	for (int l = 0; l < 2; ++l) {
-		if (mc.ref_frame[l] < 0) continue;
-		const uint8_t *ref = job.frames + job.frame_bytes * mc.ref_frame[l];
-		const int mvx = mc.mv[l][0], mvy = mc.mv[l][1];
-		const int fx = mvx & 3, fy = mvy & 3;
-		const int x = mbx * 16 + x4 * 4 + (mvx >> 2), y = mby * 16 + y4 * 4 + (mvy >> 2);
-		const bool fast = x >= 3 && x + 14 <= W;      // every aligned word touched lies inside the row
-		if (k == 1) {
-#pragma unroll
-			for (int i = 0; i < 16; ++i) p0[i] = px[i];
-		}
-		if (!fx && !fy) {
-#pragma unroll
-			for (int r = 0; r < 4; ++r) {
-				uint32_t w[3];
-				load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x, fast, 1, w);
-#pragma unroll
-				for (int i = 0; i < 4; ++i) px[4 * r + i] = (w[0] >> (8 * i)) & 255;
-			}
-		} else if (!fy) {
-#pragma unroll
-			for (int r = 0; r < 4; ++r) {
-				uint32_t w[3];
-				int hb[4];
-				load_row(ref + (size_t)min(max(y + r, 0), H - 1) * W, W, x - 2, fast, 3, w);
-				hfilter4(w, hb);
-#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					int b = clip255((hb[i] + 16) >> 5);
-					int g = fx == 1 ? byte_of(w, i + 2) : byte_of(w, i + 3);
-					px[4 * r + i] = fx == 2 ? b : avg2(g, b);
-				}
-			}
-		} else if (!fx) {
-			uint32_t R[9];
-#pragma unroll
-			for (int q = 0; q < 9; ++q) {
-				uint32_t w[3];
-				load_row(ref + (size_t)min(max(y + q - 2, 0), H - 1) * W, W, x, fast, 1, w);
-				R[q] = w[0];
-			}
-			vhalf4x4(R, px);
-			if (fy != 2) {
-#pragma unroll
-				for (int r = 0; r < 4; ++r) {
-					uint32_t g = fy == 1 ? R[r + 2] : R[r + 3];
-#pragma unroll
-					for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2((g >> (8 * i)) & 255, px[4 * r + i]);
-				}
-			}
-		} else if (fx != 2 && fy != 2) {
-			// quarter positions e, g, p, r: average of a horizontal (b / s) and a vertical (h / m) half sample
-			uint32_t R[9];
-			const int xo = fx == 3 ? 1 : 0, yo = fy == 3 ? 1 : 0;
-#pragma unroll
-			for (int q = 0; q < 9; ++q) {
-				uint32_t w[3];
-				load_row(ref + (size_t)min(max(y + q - 2, 0), H - 1) * W, W, x + xo, fast, 1, w);
-				R[q] = w[0];
-			}
-			vhalf4x4(R, px);
-#pragma unroll
-			for (int r = 0; r < 4; ++r) {
-				uint32_t w[3];
-				int hb[4];
-				load_row(ref + (size_t)min(max(y + r + yo, 0), H - 1) * W, W, x - 2, fast, 3, w);
-				hfilter4(w, hb);
-#pragma unroll
-				for (int i = 0; i < 4; ++i) px[4 * r + i] = avg2(clip255((hb[i] + 16) >> 5), px[4 * r + i]);
-			}
-		} else {
-			// centre column (fx == 2) or centre row (fy == 2): j from the unrounded horizontal intermediates
-			int hb[9][4];
-			uint32_t G[9];
-#pragma unroll
-			for (int q = 0; q < 9; ++q) {
-				uint32_t w[3];
-				load_row(ref + (size_t)min(max(y + q - 2, 0), H - 1) * W, W, x - 2, fast, 3, w);
-				hfilter4(w, hb[q]);
-				// bytes of columns 0..3 (fx == 1) or 1..4 (fx == 3) for the vertical half samples
-				G[q] = fx == 3 ? __funnelshift_r(w[0], w[1], 24) : __funnelshift_r(w[0], w[1], 16);
-			}
-			int vh[16];
-			const bool centre_row = fx != 2;       // fy == 2, fx odd: h / m with j
-			if (centre_row) vhalf4x4(G, vh);
-#pragma unroll
-			for (int r = 0; r < 4; ++r)
-#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					int j1 = (hb[r][i] + hb[r + 5][i]) - 5 * (hb[r + 1][i] + hb[r + 4][i]) + 20 * (hb[r + 2][i] + hb[r + 3][i]);
-					int j = clip255((j1 + 512) >> 10);
-					int v;
-					if (centre_row) v = avg2(vh[4 * r + i], j);
-					else if (fy == 2) v = j;
-					else v = avg2(clip255(((fy == 1 ? hb[r + 2][i] : hb[r + 3][i]) + 16) >> 5), j);
-					px[4 * r + i] = v;
-				}
-		}
-		// chroma: 2x2 samples of Cb and Cr, eighth-pel bilinear in packed 16-bit lanes
-		{
-			const uint8_t *refc = ref + luma_size;
-			const int CH = H >> 1, cw = W >> 1;
-			const int cfx = mvx & 7, cfy = mvy & 7;
-			const int cx = mbx * 8 + x4 * 2 + (mvx >> 3), cy = mby * 8 + y4 * 2 + (mvy >> 3);
-			const bool cfast = cx >= 2 && cx + 6 <= cw;
-			uint32_t hrow[3][2];    // per row: horizontally interpolated (Cb0, Cb1) and (Cr0, Cr1), 16-bit lanes, scale 8
-#pragma unroll
-			for (int r = 0; r < 3; ++r) {
-				const uint8_t *row = refc + (size_t)min(max(cy + r, 0), CH - 1) * W;
-				uint32_t a, bq;     // a = samples 0,1 (Cb0 Cr0 Cb1 Cr1), bq = samples 1,2
-				if (cfast) {
-					uint32_t w[3];
-					load_row(row, W, cx * 2, true, 2, w);
-					a = w[0];
-					bq = __funnelshift_r(w[0], w[1], 16);
-				} else {
-					int x0 = min(max(cx, 0), cw - 1) * 2, x1 = min(max(cx + 1, 0), cw - 1) * 2, x2 = min(max(cx + 2, 0), cw - 1) * 2;
-					uint32_t s0 = __ldg(row + x0) | (__ldg(row + x0 + 1) << 8), s1 = __ldg(row + x1) | (__ldg(row + x1 + 1) << 8),
-					         s2 = __ldg(row + x2) | (__ldg(row + x2 + 1) << 8);
-					a = s0 | (s1 << 16);
-					bq = s1 | (s2 << 16);
-				}
-				uint32_t a_cb = a & 0x00FF00FFu, a_cr = (a >> 8) & 0x00FF00FFu;
-				uint32_t b_cb = bq & 0x00FF00FFu, b_cr = (bq >> 8) & 0x00FF00FFu;
-				hrow[r][0] = (uint32_t)(8 - cfx) * a_cb + (uint32_t)cfx * b_cb;
-				hrow[r][1] = (uint32_t)(8 - cfx) * a_cr + (uint32_t)cfx * b_cr;
-			}
-#pragma unroll
-			for (int r = 0; r < 2; ++r) {
-				uint32_t vcb = ((uint32_t)(8 - cfy) * hrow[r][0] + (uint32_t)cfy * hrow[r + 1][0] + 0x00200020u) >> 6;
-				uint32_t vcr = ((uint32_t)(8 - cfy) * hrow[r][1] + (uint32_t)cfy * hrow[r + 1][1] + 0x00200020u) >> 6;
-				cb_[k][r][0] = vcb & 0x3FF; cb_[k][r][1] = (vcb >> 16) & 0x3FF;
-				cr_[k][r][0] = vcr & 0x3FF; cr_[k][r][1] = (vcr >> 16) & 0x3FF;
-			}
-		}
-		++k;
-	}
-	// ---- weighted sample prediction (default: w = 1, o = 0, logWD = 0) --------------------------------
-	const int first = mc.ref_frame[0] >= 0 ? 0 : 1;
-	if (n_lists == 2) {
-		const int lw = mc.log2wd_y, w0 = mc.w[0][0], w1 = mc.w[1][0], o = (mc.o[0][0] + mc.o[1][0] + 1) >> 1;
-#pragma unroll
-		for (int i = 0; i < 16; ++i) px[i] = clip255(((p0[i] * w0 + px[i] * w1 + (1 << lw)) >> (lw + 1)) + o);
-		const int lc = mc.log2wd_c;
-#pragma unroll
-		for (int r = 0; r < 2; ++r)
-#pragma unroll
-			for (int i = 0; i < 2; ++i) {
-				cb_[0][r][i] = clip255(((cb_[0][r][i] * mc.w[0][1] + cb_[1][r][i] * mc.w[1][1] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][1] + mc.o[1][1] + 1) >> 1));
-				cr_[0][r][i] = clip255(((cr_[0][r][i] * mc.w[0][2] + cr_[1][r][i] * mc.w[1][2] + (1 << lc)) >> (lc + 1)) + ((mc.o[0][2] + mc.o[1][2] + 1) >> 1));
-			}
-	} else if (mc.log2wd_y | mc.log2wd_c | (mc.w[first][0] ^ 1) | (mc.w[first][1] ^ 1) | (mc.w[first][2] ^ 1) | mc.o[first][0] | mc.o[first][1] | mc.o[first][2]) {
-		const int lw = mc.log2wd_y, rnd = lw ? 1 << (lw - 1) : 0;
-#pragma unroll
-		for (int i = 0; i < 16; ++i) px[i] = clip255(((px[i] * mc.w[first][0] + rnd) >> lw) + mc.o[first][0]);
-		const int lc = mc.log2wd_c, rc = lc ? 1 << (lc - 1) : 0;
-#pragma unroll
-		for (int r = 0; r < 2; ++r)
-#pragma unroll
-			for (int i = 0; i < 2; ++i) {
-				cb_[0][r][i] = clip255(((cb_[0][r][i] * mc.w[first][1] + rc) >> lc) + mc.o[first][1]);
-				cr_[0][r][i] = clip255(((cr_[0][r][i] * mc.w[first][2] + rc) >> lc) + mc.o[first][2]);
-			}
-	}
-	{
-		const int b = c_r2b[y4 * 4 + x4];
-		if ((has >> b) & 1) {
-			const int16_t *res = s_res[slot][b];
-#pragma unroll
-			for (int i = 0; i < 16; ++i) px[i] = clip255(px[i] + res[i]);
-		}
-#pragma unroll
-		for (int r = 0; r < 4; ++r) {
-			uint32_t w = (uint32_t)px[4 * r] | ((uint32_t)px[4 * r + 1] << 8) | ((uint32_t)px[4 * r + 2] << 16) | ((uint32_t)px[4 * r + 3] << 24);
-			*reinterpret_cast<uint32_t *>(dst_y + (size_t)(mby * 16 + y4 * 4 + r) * W + mbx * 16 + x4 * 4) = w;
-		}
-	}
-	{
-		const int cblk = (y4 >> 1) * 2 + (x4 >> 1);
-#pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			int cb0 = cb_[0][r][0], cb1 = cb_[0][r][1], cr0 = cr_[0][r][0], cr1 = cr_[0][r][1];
-			const int ro = ((y4 & 1) * 2 + r) * 4 + (x4 & 1) * 2;
-			if ((has >> (16 + cblk)) & 1) { cb0 = clip255(cb0 + s_res[slot][16 + cblk][ro]); cb1 = clip255(cb1 + s_res[slot][16 + cblk][ro + 1]); }
-			if ((has >> (20 + cblk)) & 1) { cr0 = clip255(cr0 + s_res[slot][20 + cblk][ro]); cr1 = clip255(cr1 + s_res[slot][20 + cblk][ro + 1]); }
-			uint32_t w = (uint32_t)cb0 | ((uint32_t)cr0 << 8) | ((uint32_t)cb1 << 16) | ((uint32_t)cr1 << 24);
-			*reinterpret_cast<uint32_t *>(dst_c + (size_t)(mby * 8 + y4 * 2 + r) * W + mbx * 16 + x4 * 4) = w;
-		}
-	}
-}
 
 // ------------------------------------------------------------------------------------------------
 // inter kernel, strip form.  Work item = a vertical strip of one motion-compensation record: 8 (or 4)
@@ -602,7 +221,6 @@ h264_inter_kernel(const H4Job *__restrict__ jobs, int n_mbs) {
 #define B2_I5_CTAS 5
 #endif
 constexpr int I5_THREADS = B2_I5_THREADS;
-
 
 __device__ __forceinline__ int frac_class(int fx, int fy) {
 	if (!fx && !fy) return 0;
@@ -1458,7 +1076,6 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 	}
 }
 
-
 // Deblock one macroblock with one warp, in two register passes.
 //   V pass (vertical edges): lane l < 16 holds luma row l (columns -4..15) unpacked in registers,
 //   lanes 16..23 hold the eight chroma rows (byte columns -4..15); the four edges of the row are
@@ -2276,29 +1893,22 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
                       uint32_t max_items, uint32_t max_first) {
 	if (n_jobs <= 0) return 0;
 	if (phase == 0) {
-		const int n_mbs = mb_w * mb_h;
-		static const int use5 = getenv("B2_INTER5") ? atoi(getenv("B2_INTER5")) : 1;     // 0: the older 4x4-item kernel (kept for comparison)
-		if (use5) {
-			dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
-			constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint16_t) * I5_QUEUE * (I5_THREADS / 32);
-			static bool attr_set = false;       // per process; the attribute is per device function
-			if (!attr_set) {
-				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-				B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-				attr_set = true;
-			}
-			if (max_first) {
-				dim3 grid_first((max_first + I5_THREADS - 1) / I5_THREADS, n_jobs);
-				h264_inter5_kernel<1><<<grid_first, I5_THREADS, smem5, stream>>>(d_jobs);
-				if (launches) ++*launches;
-				h264_inter5_kernel<2><<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
-			} else {
-				h264_inter5_kernel<0><<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
-			}
+		dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
+		constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint16_t) * I5_QUEUE * (I5_THREADS / 32);
+		static bool attr_set = false;       // per process; the attribute is per device function
+		if (!attr_set) {
+			B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+			B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+			B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+			attr_set = true;
+		}
+		if (max_first) {
+			dim3 grid_first((max_first + I5_THREADS - 1) / I5_THREADS, n_jobs);
+			h264_inter5_kernel<1><<<grid_first, I5_THREADS, smem5, stream>>>(d_jobs);
+			if (launches) ++*launches;
+			h264_inter5_kernel<2><<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
 		} else {
-			dim3 grid((n_mbs + INTER_MBS - 1) / INTER_MBS, n_jobs);
-			h264_inter_kernel<<<grid, INTER_THREADS, 0, stream>>>(d_jobs, n_mbs);
+			h264_inter5_kernel<0><<<grid5, I5_THREADS, smem5, stream>>>(d_jobs);
 		}
 		if (launches) ++*launches;
 	} else {
