@@ -137,8 +137,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=256, help="independent 1080p streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
     ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
-    ap.add_argument("--e2e-streams", type=int, default=16)
-    ap.add_argument("--e2e-reps", type=int, default=8, help="timed repetitions of the end-to-end pool run")
+    ap.add_argument("--e2e-streams", type=int, default=32, help="streams per end-to-end repetition (two per host thread on a 16-core box: an even tail)")
+    ap.add_argument("--e2e-reps", type=int, default=6, help="timed repetitions of the end-to-end pool run")
     ap.add_argument("--verify-lanes", type=int, default=8, help="lanes whose every frame is MD5-checked against the reference")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
