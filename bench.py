@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
     ap.add_argument("--e2e-streams", type=int, default=32, help="streams per end-to-end repetition (two per host thread on a 16-core box: an even tail)")
     ap.add_argument("--e2e-reps", type=int, default=6, help="timed repetitions of the end-to-end pool run")
-    ap.add_argument("--verify-lanes", type=int, default=8, help="lanes whose every frame is MD5-checked against the reference")
+    ap.add_argument("--verify-lanes", type=int, default=32, help="lanes whose every frame is MD5-checked against the reference")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,20 +259,25 @@ def main():
         if os.path.exists(REF_BIN) and nver:
             paths = write_streams(streams[:nver], d)
             run_reference_cli(paths, min(ncores, nver), md5=True)
-            verify_kind = "compiled reference (oracle/_ref/h264dec -O)"
+            verify_kind = "compiled reference (oracle/_ref/h264dec -O), hashed on the device (b2_replay_md5)"
             import hashlib
             for lane in range(nver):
                 golden = open(os.path.join(d, "s%03d.out" % lane), "rb").read().split()
                 assert len(golden) == a.frames, (len(golden), a.frames)
                 goldens[lane] = [g.decode() for g in golden]
-                for t, idx in enumerate(rp.outputs[lane]):
+                # every picture of the lane hashed on the device (b2_replay_md5: 16 bytes per picture come back);
+                # the first two lanes are also downloaded and hashed on the host, which checks the device MD5 itself
+                got = rp.md5([(lane, idx) for idx in rp.outputs[lane]], width=1920, height=1080)
+                if [g.encode() for g in got] != golden:
+                    raise SystemExit("bench.py: MD5 mismatch in lane %d" % lane)
+                for t, idx in enumerate(rp.outputs[lane] if lane < 2 else []):
                     y, c = rp.download(lane, idx)
                     h = hashlib.md5()
                     h.update(np.ascontiguousarray(y[:1080]).tobytes())
                     h.update(np.ascontiguousarray(c[:540]).tobytes())
                     if h.hexdigest().encode() != golden[t]:
                         raise SystemExit("bench.py: MD5 mismatch lane %d picture %d" % (lane, t))
-                    verified += 1
+                verified += len(got)
 
     # ---- timed region: K steps, one step = all lanes x frames ---------------------------------
     def barrier():

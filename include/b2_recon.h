@@ -249,6 +249,12 @@ int b2_replay_mark(b2_replay *r, int which);
 int b2_replay_elapsed_ms(b2_replay *r, float *ms);
 int b2_replay_get_stats(b2_replay *r, b2_replay_stats *out);
 int b2_replay_download(b2_replay *r, int lane, int idx, uint8_t *luma, uint8_t *chroma);
+/* MD5 of n reconstructed pictures on the device, as the reference application hashes an output   */
+/* frame for `h264dec -O` (src/app/filewrite.h:11-29, 91-124; src/app/md5.c): the cropped luma    */
+/* rows (window crop_left, crop_top, width x height), then the cropped rows of the interleaved    */
+/* CbCr plane.  Picture i is frame frame_idx[i] of lane lanes[i]; digests receives 16 bytes per   */
+/* picture.  Waits for the runs queued so far.                                                    */
+int b2_replay_md5(b2_replay *r, int n, const int *lanes, const int *frame_idx, int crop_left, int crop_top, int width, int height, uint8_t *digests);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,7 @@ lib.b2_replay_run.argtypes = [C.c_void_p, C.c_int]
 lib.b2_replay_sync.argtypes = [C.c_void_p]
 lib.b2_replay_get_stats.argtypes = [C.c_void_p, C.POINTER(ReplayStats)]
 lib.b2_replay_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.b2_replay_md5.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 lib.b2_context_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3)]
 lib.b2_replay_mark.argtypes = [C.c_void_p, C.c_int]
 lib.b2_replay_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]

@@ -53,6 +53,10 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense,
                 bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first = 0);
 
+// md5.cu: MD5 of a cropped window of n frames (one thread per frame); d_slots / d_out are device pointers
+int md5_pictures(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, const int *d_slots, int n, int stride, int rows, int left, int top, int w, int h,
+                 uint8_t *d_out);
+
 __device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 }  // namespace b2

@@ -325,6 +325,32 @@ extern "C" int b2_replay_download(b2_replay *r, int lane, int idx, uint8_t *luma
 	return 0;
 }
 
+extern "C" int b2_replay_md5(b2_replay *r, int n, const int *lanes, const int *frame_idx, int crop_left, int crop_top, int width, int height, uint8_t *digests) {
+	if (!r || n < 0 || !lanes || !frame_idx || !digests || crop_left < 0 || crop_top < 0 || width <= 0 || height <= 0 || (height & 1) || (crop_top & 1) ||
+	    crop_left + width > r->width || crop_top + height > r->height) return -1;
+	if (n == 0) return 0;
+	std::vector<int> slots(n);
+	for (int i = 0; i < n; ++i) {
+		if ((unsigned)lanes[i] >= (unsigned)r->lanes || (unsigned)frame_idx[i] >= (unsigned)r->pool) return -1;
+		slots[i] = r->pool * lanes[i] + frame_idx[i];
+	}
+	B2_CUDA_OK(cudaSetDevice(r->dev));
+	int *d_slots = nullptr;
+	uint8_t *d_out = nullptr;
+	B2_CUDA_OK(cudaMalloc(&d_slots, sizeof(int) * n));
+	B2_CUDA_OK(cudaMalloc(&d_out, (size_t)16 * n));
+	int rc = 0;
+	if (cudaMemcpyAsync(d_slots, slots.data(), sizeof(int) * n, cudaMemcpyHostToDevice, r->stream) != cudaSuccess ||
+	    md5_pictures(r->stream, r->frames, r->frame_bytes, d_slots, n, r->width, r->height, crop_left, crop_top, width, height, d_out) < 0 ||
+	    cudaMemcpyAsync(digests, d_out, (size_t)16 * n, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess) {
+		set_error("b2_replay_md5: %s", cudaGetErrorString(cudaGetLastError()));
+		rc = -1;
+	}
+	cudaFree(d_slots);
+	cudaFree(d_out);
+	return rc;
+}
+
 extern "C" int b2_replay_mark(b2_replay *r, int which) {
 	if (!r || (unsigned)which > 1) return -1;
 	B2_CUDA_OK(cudaSetDevice(r->dev));

@@ -74,6 +74,17 @@ class Replay:
         L.lib.b2_replay_get_stats(self.h, C.byref(st))
         return st
 
+    def md5(self, pictures, width=None, height=None, left=0, top=0):
+        """MD5 hex digests of `pictures` = [(lane, frame index), ...], computed on the device over the
+        cropped window, as `h264dec -O` would print them."""
+        n = len(pictures)
+        lanes = np.asarray([p[0] for p in pictures], np.int32)
+        idxs = np.asarray([p[1] for p in pictures], np.int32)
+        out = np.empty(16 * max(n, 1), np.uint8)
+        if L.lib.b2_replay_md5(self.h, n, lanes.ctypes.data, idxs.ctypes.data, left, top, width or self.width, height or self.height, out.ctypes.data) < 0:
+            raise RuntimeError("b2_replay_md5 failed: %s" % (L.lib.b2_last_error() or b"").decode())
+        return [out[16 * i:16 * i + 16].tobytes().hex() for i in range(n)]
+
     def download(self, lane, idx):
         luma = np.empty(self.width * self.height, np.uint8)
         chroma = np.empty(self.width * self.height // 2, np.uint8)

@@ -67,3 +67,28 @@ def test_pageable_and_page_locked_frame_buffers_agree():
     finally:
         decoder.Frames.__init__ = orig
         decoder._frames_pool = saved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom,window", [("mbw=8 mbh=6 frames=5", (0, 0, 128, 96)), ("mbw=8 mbh=6 frames=5", (0, 2, 128, 90)),
+                                         ("mbw=10 mbh=8 frames=5", (0, 0, 160, 128)), ("mbw=10 mbh=8 frames=5", (6, 4, 150, 120))])
+def test_device_md5_matches_hashlib(geom, window):
+    """b2_replay_md5 (one thread per picture) against hashlib over the downloaded, cropped planes:
+    the word-aligned path (width a multiple of 64) and the byte path, with and without cropping."""
+    import m2dec_b200
+    left, top, w, h = window
+    mbw, mbh = int(geom.split()[0][4:]), int(geom.split()[1][4:])
+    rp = m2dec_b200.Replay("h264", mbw * 16, mbh * 16, 3, pool_frames=24)
+    try:
+        for lane in range(3):
+            assert rp.load_stream(lane, streams.generate("h264", geom + " seed=%d" % (300 + lane))) == 5
+        rp.run()
+        rp.sync()
+        pics = [(lane, idx) for lane in range(3) for idx in rp.outputs[lane]]
+        want = []
+        for lane, idx in pics:
+            y, c = rp.download(lane, idx)
+            want.append(_md5(y[top:top + h, left:left + w], c[top // 2:top // 2 + h // 2, left:left + w]))
+        assert rp.md5(pics, width=w, height=h, left=left, top=top) == want
+    finally:
+        rp.close()
