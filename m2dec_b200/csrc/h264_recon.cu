@@ -1475,6 +1475,11 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 // ((threshold - 1 + 0x8000) - |difference| has the bit set exactly when the test holds) and
 // applied by masking the clipping bounds, so the filter has no branch except the bS 4 case.
 // ------------------------------------------------------------------------------------------------
+// progress of a row is published every so many macroblocks (a power of two): fewer release stores and flag
+// writes, at the price of the row below running that much further behind
+#ifndef B2_DBK2_PUBLISH_EVERY
+#define B2_DBK2_PUBLISH_EVERY 2
+#endif
 struct alignas(16) DbkTile2 {
 	// one packed pair per sample; rows -4..15 at r + 4, columns -4..15 at c + 4.  Pitch 28 words: rows are 16-byte
 	// aligned (whole lines move as 128-bit accesses) and eight consecutive rows start in eight different bank groups
@@ -1766,7 +1771,7 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 		}
 		carry_in = carry_out;
 		done_to = x + 1;
-		sy.publish(x + 1, lane);
+		if (((x + 1) & (B2_DBK2_PUBLISH_EVERY - 1)) == 0 || x + 1 == mb_w || !todo) sy.publish(x + 1, lane);
 		__syncwarp();
 	}
 }
