@@ -55,7 +55,6 @@ int cache_get(int dev, bool pinned, size_t bytes, void **out, size_t *actual = n
 	else B2_CUDA_OK(cudaMalloc(out, bytes));
 	return 0;
 }
-size_t g_sizes_dummy = 0;
 void cache_put(int dev, bool pinned, size_t bytes, void *ptr) {
 	if (!ptr) return;
 	std::lock_guard<std::mutex> lk(g_cache_mu);
