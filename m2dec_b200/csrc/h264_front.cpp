@@ -913,6 +913,8 @@ private:
 	bool rd_t8x8() { return cs_.transform8x8(ctx_.cabac_inc_t8x8(), 0) != 0; }
 
 	void open_mb(int mbx, int mby) {
+		cur_mbx_ = mbx;         // (kept for emit_mc: no division per motion record)
+		cur_mby_ = mby;
 		ctx_.open_mb(mbx, mby, slice_num_);
 		b2_h264_mb &m = mbs_[(size_t)mby * mb_w_ + mbx];
 		memset(&m, 0, sizeof(m));
@@ -971,7 +973,7 @@ private:
 			// strips whose reference window (6-tap margins included) leaves the picture take the clamped loads: they go
 			// to buckets of their own (the last 36), so that a warp of the kernel is all fast path or all clamped
 			const int W = mb_w_ * 16, H = mb_h_ * 16, sw = wide ? 8 : 4;
-			const int mbx = mb_addr_ % mb_w_, mby = mb_addr_ / mb_w_;
+			const int mbx = cur_mbx_, mby = cur_mby_;
 			const int hidx = ph == 4 ? 2 : ph - 1;
 			for (int k = 0; k < n; ++k) {
 				const int px = mbx * 16 + x4 * 4 + k * sw, py = mby * 16 + y4 * 4;
@@ -1858,6 +1860,7 @@ private:
 	std::vector<b2_h264_mb> mbs_;
 	std::vector<b2_h264_dbk> dbk_;
 	std::vector<b2_h264_mc> mcs_;
+	int cur_mbx_ = 0, cur_mby_ = 0;                           // macroblock being parsed (set by open_mb)
 	std::vector<uint32_t> items_[72], items_first_[72], items_all_;      // inter work items per (class, height) bucket / concatenated
 	std::vector<int16_t> coefs_;
 	size_t coef_used_ = 0;
