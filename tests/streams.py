@@ -26,6 +26,11 @@ H264_CASES = {
     "h264_biglevels": "mbw=8 mbh=6 frames=6 seed=16 qp=12 big_levels=1 coded_pct=50",
     "h264_constrained": "mbw=8 mbh=6 frames=8 seed=17 constrained_intra=1 intra_pct=30",
     "h264_2x2": "mbw=2 mbh=2 frames=6 seed=21",
+    # nearly full 4x4 blocks (13-16 coefficients): the long coeff_token codes and total_zeros tables 13-15
+    # (round 2: total_zeros of 15 coefficients was inverted in writer and parser alike; the reference stopped)
+    "h264_full_blocks": "mbw=12 mbh=8 frames=6 seed=5 dense_pct=30",
+    "h264_full_blocks_intra": "mbw=12 mbh=8 frames=6 seed=6 dense_pct=60 coded_pct=60 intra_pct=30",
+    "h264_full_blocks_b": "mbw=12 mbh=8 frames=8 seed=7 dense_pct=40 bframes=2 profile=77 refs=2",
     # Main profile, CAVLC: B pictures, direct modes, weighted prediction
     "h264_b_bipred": "mbw=8 mbh=6 frames=7 seed=31 refs=2 bframes=2 profile=77 skip_pct=0 direct_pct=0",
     "h264_b_implicit": "mbw=8 mbh=6 frames=7 seed=32 refs=2 bframes=2 profile=77 skip_pct=0 direct_pct=0 weighted_bipred=2",
@@ -51,6 +56,7 @@ H264_CASES = {
     "h264_cabac_b3_explicit_slices": "mbw=10 mbh=8 frames=13 seed=59 cabac=1 profile=77 refs=3 bframes=3 weighted_bipred=1 weighted_pred=1 slices=2",
     "h264_cabac_b_direct4x4": "mbw=10 mbh=8 frames=10 seed=60 cabac=1 profile=77 refs=2 bframes=1 direct_8x8_inference=0",
     "h264_cabac_b_mixed": "mbw=12 mbh=9 frames=16 seed=61 cabac=1 profile=77 refs=4 bframes=2 intra_pct=20 direct_pct=40 skip_pct=30",
+    "h264_cabac_full_blocks": "mbw=12 mbh=8 frames=6 seed=8 dense_pct=40 cabac=1 profile=77",
     "h264_cabac_skippy": "mbw=6 mbh=5 frames=10 seed=62 cabac=1 profile=77 skip_pct=60 cabac_init_idc=1",
     # High profile: CABAC + 8x8 transform + Intra8x8
     "h264_high_i": "mbw=8 mbh=6 frames=2 seed=71 cabac=1 profile=100 transform8x8=1 gop=1",
@@ -63,6 +69,7 @@ H264_CASES = {
     "h264_high_qp8_trunc": "mbw=8 mbh=6 frames=6 seed=78 cabac=1 profile=100 transform8x8=1 qp=8 coded_pct=50 vary_qp=0",
     "h264_high_big": "mbw=20 mbh=12 frames=24 seed=79 cabac=1 profile=100 transform8x8=1 refs=4 gop=20 slices=2 bframes=1",
     "h264_high_umv_dense": "mbw=9 mbh=5 frames=8 seed=80 cabac=1 profile=100 transform8x8=1 qp=22 coded_pct=60 mv_range=300 mv_out=60",
+    "h264_high_full_blocks": "mbw=12 mbh=8 frames=6 seed=9 dense_pct=40 cabac=1 profile=100 transform8x8=1",
     "h264_high_2x2": "mbw=2 mbh=2 frames=6 seed=81 cabac=1 profile=100 transform8x8=1",
 }
 # Pictures one macroblock wide or high: the compiled reference disagrees with ffmpeg there (its
@@ -81,7 +88,7 @@ H264_ORACLE_ONLY = {
     "h264_high_constrained": "mbw=8 mbh=6 frames=8 seed=82 cabac=1 profile=100 transform8x8=1 constrained_intra=1 intra_pct=30",
 }
 # committed under tests/golden/ together with the reference's MD5 lines
-H264_GOLDEN = ["h264_basic", "h264_refs3", "h264_slices_dbk_mix", "h264_intra_ipcm", "h264_qp40_cqp", "h264_umv", "h264_constrained",
+H264_GOLDEN = ["h264_basic", "h264_full_blocks", "h264_refs3", "h264_slices_dbk_mix", "h264_intra_ipcm", "h264_qp40_cqp", "h264_umv", "h264_constrained",
                "h264_b_spatial", "h264_b_temporal_implicit", "h264_b3_explicit_slices", "h264_b_direct4x4_temporal", "h264_p_weighted",
                "h264_cabac_ip", "h264_cabac_intra_ipcm", "h264_cabac_b3_explicit_slices", "h264_cabac_b_mixed",
                "h264_high_ip", "h264_high_b_temporal_w", "h264_high_slices_dbk", "h264_high_intra_ipcm", "h264_high_qp8_trunc"]

@@ -369,6 +369,16 @@ private:
 	// (sum |level| * scale / 64) must stay below *budget; returns the number of non-zero levels.
 	int draw_block(int16_t *lv, int maxc, int first_scan, int qp, int *budget) {
 		memset(lv, 0, sizeof(int16_t) * 16);
+		if (o_.dense_pct && rng_.chance(o_.dense_pct)) {
+			// nearly full block (maxc - 3 .. maxc coefficients of magnitude 1-2): reaches the long coeff_token
+			// codes and the total_zeros tables of 13-15 coefficients; draws nothing when the option is off
+			int holes = rng_.range(0, 3), cnt = 0;
+			for (int pos = 0; pos < maxc; ++pos) lv[pos] = (int16_t)((rng_.chance(85) ? 1 : 2) * (rng_.chance(50) ? 1 : -1));
+			for (int i = 0; i < holes; ++i) lv[rng_.range(0, maxc - 1)] = 0;
+			for (int pos = 0; pos < maxc; ++pos) cnt += lv[pos] != 0;
+			*budget = 0;
+			return cnt;
+		}
 		int n = 1 + (int)(rng_.next() % 4);
 		if (rng_.chance(8)) n = rng_.range(5, maxc);
 		int cnt = 0;

@@ -25,7 +25,7 @@ int main(int argc, char **argv) {
 		sg::H264Opts o;
 		OPT(mbw) OPT(mbh) OPT(frames) OPT(seed) OPT(profile) OPT(gop) OPT(refs) OPT(qp) OPT(chroma_qp_offset)
 		OPT(vary_qp) OPT(deblock) OPT(alpha_div2) OPT(beta_div2) OPT(slices) OPT(intra_pct) OPT(skip_pct)
-		OPT(ipcm_pct) OPT(coded_pct) OPT(max_level) OPT(big_levels) OPT(amp_budget) OPT(mv_step) OPT(mv_range)
+		OPT(ipcm_pct) OPT(coded_pct) OPT(max_level) OPT(big_levels) OPT(dense_pct) OPT(amp_budget) OPT(mv_step) OPT(mv_range)
 		OPT(mv_out) OPT(crop_bottom) OPT(crop_right) OPT(constrained_intra)
 		OPT(bframes) OPT(direct_spatial) OPT(direct_pct) OPT(weighted_pred) OPT(weighted_bipred) OPT(direct_8x8_inference)
 		OPT(cabac) OPT(cabac_init_idc) OPT(transform8x8)

@@ -18,6 +18,7 @@ struct H264Opts {
 	int slices = 1;
 	int intra_pct = 10, skip_pct = 15, ipcm_pct = 1, coded_pct = 25;
 	int max_level = 3, big_levels = 0;
+	int dense_pct = 0;         // share of coded 4x4 blocks that are nearly full (13-16 coefficients)
 	int amp_budget = 200;      // bound on the L1 amplitude of a block's residual (hazards 1, 2)
 	int mv_step = 6, mv_range = 96, mv_out = 24;   // quarter-pel step / range, pixels allowed outside
 	int crop_bottom = 0, crop_right = 0;
