@@ -167,6 +167,13 @@ typedef struct {
 /* ------------------------------------------------------------------------------------ */
 typedef int (*b2_picture_tap)(void *arg, int codec, const void *picture /* b2_m2_picture* or b2_h264_picture* */);
 
+/* Structural check of a picture's records against a frame pool of `nframes` frames: every index inside
+ * its array, every enumerated field inside its range (the kernels check nothing).  0 = sound, < 0 = not
+ * (b2_last_error() says which record).  b2_session_submit_* and b2_replay_add_* run it on every picture;
+ * it is exported for hosts that build the records themselves.                                          */
+int b2_h264_picture_check(const b2_h264_picture *picture, int nframes);
+int b2_mpeg2_picture_check(const b2_m2_picture *picture, int nframes);
+
 /* Attach a tap to a decoder context created through m2d_gpu_func / h264d_gpu_func.
  * If device_off != 0 the context runs parse-only: nothing is sent to a GPU and frame-out
  * returns the caller's buffers untouched (whatever the tap's owner put there).            */
@@ -186,6 +193,9 @@ int b2_device_count(void);                           /* <0: CUDA unavailable    
 const char *b2_last_error(void);
 int b2_session_create(int cuda_device, int codec, int width, int height, int nframes, b2_session **out);
 void b2_session_destroy(b2_session *s);
+/* Closed sessions leave their device / page-locked buffers on a process-wide free list (at most 4 GiB of each
+ * kind is kept) so that the next session does not pay cudaMalloc; this frees all of them.                    */
+void b2_cache_trim(void);
 /* Asynchronous: copies the picture's SoA into pinned staging, enqueues H2D + kernels.     */
 int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *pic);
 int b2_session_submit_h264(b2_session *s, const b2_h264_picture *pic);

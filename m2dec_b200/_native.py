@@ -93,3 +93,5 @@ lib.b2_replay_md5.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_i
 lib.b2_context_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3)]
 lib.b2_replay_mark.argtypes = [C.c_void_p, C.c_int]
 lib.b2_replay_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+lib.b2_h264_picture_check.argtypes = [C.c_void_p, C.c_int]
+lib.b2_mpeg2_picture_check.argtypes = [C.c_void_p, C.c_int]

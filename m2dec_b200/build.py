@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libm2dec_b200.so")
 
-CPP = ["bits.cpp", "backend.cpp", "plugin.cpp", "mpeg2_front.cpp", "h264_front.cpp"]
+CPP = ["bits.cpp", "backend.cpp", "plugin.cpp", "validate.cpp", "mpeg2_front.cpp", "h264_front.cpp"]
 CU = ["session.cu", "mpeg2_recon.cu", "h264_recon.cu", "replay.cu", "md5.cu"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

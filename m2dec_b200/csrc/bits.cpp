@@ -58,57 +58,105 @@ extern "C" int m2d_next_start_code(const byte_t *src, int len) {
 
 namespace b2 {
 
-int next_unit(dec_bits *s, Unit *u) {
-	// 1. locate the start code that opens the unit
-	for (;;) {
-		long avail = s->cur ? (long)(s->tail - s->cur) : 0;
-		long pos = avail >= 3 ? find_start_code(s->cur, avail) : -1;
-		if (pos >= 0) { s->cur += pos; break; }
-		// keep nothing: a start code split across application buffers before any unit
-		// began is not supported (the reference handles it with prev_[], bitio.c:117-120)
-		if (s->cur) s->cur = s->tail;
-		if (s->refill(s->refill_arg) < 0) return -1;
+// The application's buffer [cur, tail) is only valid until the next refill() (the reference's
+// bitio.c keeps a few bytes of its own and the reference application refills one and the same
+// buffer, src/app/m2decoder.cpp), so every byte that is still needed is copied into `pending`
+// BEFORE refill() is called.  `pending` holds, while unit_open, the bytes of the unit read so far
+// (they follow a start code); otherwise the last (at most two) bytes seen, which may be the
+// beginning of a start code that straddles two buffers.
+
+// A start code whose first byte(s) are the last bytes of `pd` and whose 01 lies in [cur, cur + avail):
+// returns the number of its bytes inside pd (1 or 2) and sets *used to the number inside the buffer;
+// 0 if there is none.
+static int straddling_start_code(const std::vector<uint8_t> &pd, const uint8_t *cur, long avail, int *used) {
+	int pn = pd.size() < 2 ? (int)pd.size() : 2;
+	int bn = avail < 2 ? (int)avail : 2;
+	uint8_t t[4];
+	for (int i = 0; i < pn; ++i) t[i] = pd[pd.size() - pn + i];
+	for (int i = 0; i < bn; ++i) t[pn + i] = cur[i];
+	for (int i = 0; i < pn && i + 2 < pn + bn; ++i) {
+		if (t[i] == 0 && t[i + 1] == 0 && t[i + 2] == 1) {
+			*used = i + 3 - pn;
+			return pn - i;
+		}
 	}
-	// 2. find where it ends
-	long avail = (long)(s->tail - s->cur);
-	long nxt = find_start_code(s->cur, avail);
-	if (nxt >= 0) {
-		u->data = s->cur;
-		u->len = (size_t)(nxt - 3);
-		s->cur += nxt - 3;
-		return 0;
-	}
-	// unit runs to the end of this buffer: ask for more; if none, the unit ends here
-	const uint8_t *start = s->cur;
-	size_t len = (size_t)avail;
-	const uint8_t *old_tail = s->tail;
+	return 0;
+}
+
+// refill() and report whether bytes arrived
+static bool more_data(dec_bits *s) {
 	s->cur = s->tail;
-	if (s->refill(s->refill_arg) < 0 || s->tail == old_tail) {
-		u->data = start;
-		u->len = len;
-		return 0;
-	}
+	if (s->refill(s->refill_arg) < 0) return false;
+	return s->cur && s->cur < s->tail;
+}
+
+int next_unit(dec_bits *s, Unit *u) {
 	if (!s->pending) s->pending = new std::vector<uint8_t>();
 	std::vector<uint8_t> &pd = *s->pending;
-	pd.assign(start, start + len);
-	for (;;) {
-		size_t from = pd.size() >= 2 ? pd.size() - 2 : 0;
-		pd.insert(pd.end(), s->cur, s->tail);
-		long q = find_start_code(pd.data() + from, (long)(pd.size() - from));
-		if (q >= 0) {
-			size_t unit_len = from + (size_t)q - 3;
-			size_t consumed_new = unit_len > (pd.size() - (size_t)(s->tail - s->cur))
-				? unit_len - (pd.size() - (size_t)(s->tail - s->cur)) : 0;
-			s->cur += consumed_new;
-			pd.resize(unit_len);
+	if (s->pending_returned) {       // the unit handed out by the previous call lived in `pending`
+		pd.clear();
+		s->pending_returned = false;
+	}
+	// 1. locate the start code that opens the unit
+	while (!s->unit_open) {
+		long avail = s->cur ? (long)(s->tail - s->cur) : 0;
+		int used = 0;
+		if (avail > 0 && straddling_start_code(pd, s->cur, avail, &used)) {
+			s->cur += used;
+			pd.clear();
+			s->unit_open = true;
 			break;
 		}
-		s->cur = s->tail;
-		if (s->refill(s->refill_arg) < 0) break;
+		long pos = avail >= 3 ? find_start_code(s->cur, avail) : -1;
+		if (pos >= 0) {
+			s->cur += pos;
+			pd.clear();
+			s->unit_open = true;
+			break;
+		}
+		// keep the last two bytes seen: they may begin a start code that ends in the next buffer
+		for (long i = avail > 2 ? avail - 2 : 0; i < avail; ++i) pd.push_back(s->cur[i]);
+		if (pd.size() > 2) pd.erase(pd.begin(), pd.end() - 2);
+		if (!more_data(s)) return -1;
 	}
-	u->data = pd.data();
-	u->len = pd.size();
-	return 0;
+	// 2. find where it ends: the unit is `pending` followed by [cur, ...)
+	for (;;) {
+		long avail = s->cur ? (long)(s->tail - s->cur) : 0;
+		int used = 0, inside = avail > 0 ? straddling_start_code(pd, s->cur, avail, &used) : 0;
+		if (inside) {
+			// the next start code began in the previous buffer: its zeros are not part of this unit
+			pd.resize(pd.size() - (size_t)inside);
+			s->cur += used;
+			u->data = pd.data();
+			u->len = pd.size();
+			s->pending_returned = true;
+			return 0;            // unit_open stays set: cur is just behind the next start code
+		}
+		long nxt = avail >= 3 ? find_start_code(s->cur, avail) : -1;
+		if (nxt >= 0) {
+			if (pd.empty()) {
+				u->data = s->cur;    // whole unit inside the application's buffer: no copy
+				u->len = (size_t)(nxt - 3);
+			} else {
+				pd.insert(pd.end(), s->cur, s->cur + (nxt - 3));
+				u->data = pd.data();
+				u->len = pd.size();
+				s->pending_returned = true;
+			}
+			s->cur += nxt;
+			return 0;
+		}
+		// the unit runs to the end of this buffer: take the bytes along, then ask for more
+		if (avail > 0) pd.insert(pd.end(), s->cur, s->tail);
+		if (!more_data(s)) {
+			// end of data: the unit ends here
+			s->unit_open = false;
+			u->data = pd.data();
+			u->len = pd.size();
+			s->pending_returned = true;
+			return 0;
+		}
+	}
 }
 
 }  // namespace b2

@@ -20,7 +20,9 @@ struct dec_bits_t {
 	int (*refill)(void *);    // returns <0 when the application has no more data
 	void *refill_arg;
 	void *id;
-	std::vector<uint8_t> *pending;  // bytes of a unit that straddles application buffers
+	std::vector<uint8_t> *pending;  // bytes carried over a refill (see next_unit, bits.cpp)
+	bool unit_open;           // cur is inside a unit (behind its start code)
+	bool pending_returned;    // the last unit handed out lives in `pending`
 };
 
 namespace b2 {

@@ -14,6 +14,7 @@
 // 8x8 path is not usable).  Interlaced coding and CAVLC + 8x8 are rejected with
 // an error, not approximated.
 #include <algorithm>
+#include <exception>
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -31,6 +32,7 @@ using namespace h4;
 enum { NAL_SLICE = 1, NAL_IDR = 5, NAL_SEI = 6, NAL_SPS = 7, NAL_PPS = 8 };
 enum { SLICE_P = 0, SLICE_B = 1, SLICE_I = 2 };
 enum { MAX_H264_FRAMES = 64 };
+enum { kMaxMbDim = 1024, kMaxMbs = 139264 };   // 16384 samples per side; MaxFS of level 6.2
 
 struct Sps {
 	bool valid;
@@ -173,6 +175,7 @@ public:
 		frame_num_offset_ = 0;
 		prev_mmco5_ = false;
 		mb_w_ = mb_h_ = 0;
+		frames_w_ = frames_h_ = 0;
 		unsupported_ = false;
 		memset(&hdr_, 0, sizeof(hdr_));
 		nal_ref_idc_ = nal_type_ = 0;
@@ -205,6 +208,9 @@ public:
 		memset(lru_, 0, sizeof(lru_));
 		memset(host_valid_, 0, sizeof(host_valid_));
 		const Sps &s = sps_[active_sps_];
+		if (!s.valid) return -1;
+		frames_w_ = s.width;     // the application sized its buffers for this SPS (get_info): pictures of any
+		frames_h_ = s.height;    // other size are refused in slice(), they would overrun those buffers
 		backend.bind_frames(frames_, num);
 		return backend.configure(B2_CODEC_H264, s.width, s.height, num);
 	}
@@ -221,6 +227,11 @@ public:
 				err = nal(u.data, u.len);
 			} catch (const BitError &) {
 				return -2;     // bitstream error: the reference longjmps to its setjmp and returns -2
+			} catch (const std::exception &e) {
+				// allocation failure and the like: nothing may unwind through the extern "C" entry point
+				fprintf(stderr, "m2dec_b200: H.264 decode_picture: %s\n", e.what());
+				pic_open_ = false;
+				return -1;
 			}
 			if (err != 0) return err;
 		}
@@ -295,6 +306,11 @@ private:
 			int id = parse_sps();
 			if (id < 0) return 0;      // reference: a bad SPS ends decode_picture only through err<0 on slices
 			active_sps_ = id;
+			if (pic_open_ && (mb_w_ != sps_[id].width >> 4 || mb_h_ != sps_[id].height >> 4)) {
+				// the size changes under an unfinished picture: drop it, its tables have the old geometry
+				pic_open_ = false;
+				prev_first_mb_ = UINT32_MAX;
+			}
 			mb_w_ = sps_[id].width >> 4;
 			mb_h_ = sps_[id].height >> 4;
 			if (header_cb_) header_cb_(header_arg_, stream_->id);
@@ -331,8 +347,10 @@ private:
 		if (p == 44 || p == 83 || p == 86 || p == 100 || p == 110 || p == 118 || p == 128 || p == 122 || p == 244) {
 			unsigned chroma = br_.ue();
 			if (chroma == 3) br_.skip(1);
-			br_.ue();
-			br_.ue();
+			unsigned depth_y = br_.ue(), depth_c = br_.ue();
+			// the reconstruction kernels are 4:2:0, 8 bit (as the reference, which ignores these fields and
+			// would decode garbage)
+			if (chroma != 1 || depth_y != 0 || depth_c != 0) return -1;
 			br_.skip(1);
 			if (br_.get1()) {
 				// scaling lists are parsed and discarded, as in the reference (h264.cpp:254-305)
@@ -341,10 +359,15 @@ private:
 				for (int i = 0; i < n8; ++i) if (br_.get1()) skip_scaling_list(64);
 			}
 		}
-		s.log2_max_frame_num = br_.ue() + 4;
-		s.poc_type = br_.ue();
+		// ranges of 7.4.2.1.1: out-of-range values would become shift counts / read lengths further down
+		unsigned l2fn = br_.ue(), poc_type = br_.ue();
+		if (l2fn > 12 || poc_type > 2) return -1;
+		s.log2_max_frame_num = (int)l2fn + 4;
+		s.poc_type = (int)poc_type;
 		if (s.poc_type == 0) {
-			s.log2_max_poc_lsb = br_.ue() + 4;
+			unsigned l2poc = br_.ue();
+			if (l2poc > 12) return -1;
+			s.log2_max_poc_lsb = (int)l2poc + 4;
 		} else if (s.poc_type == 1) {
 			s.delta_pic_order_always_zero = br_.get1();
 			s.offset_for_non_ref_pic = br_.se();
@@ -353,15 +376,24 @@ private:
 			int acc = 0;
 			for (int i = 0; i < s.num_ref_frames_in_cycle; ++i) { acc += br_.se(); s.offset_for_ref_frame[i] = acc; }
 		}
-		s.num_ref_frames = br_.ue();
-		if (s.num_ref_frames > 16) return -1;
+		unsigned nref = br_.ue();
+		if (nref > 16) return -1;
+		s.num_ref_frames = (int)nref;
 		s.gaps_allowed = br_.get1();
-		s.width = (br_.ue() + 1) * 16;
-		s.height = (br_.ue() + 1) * 16;
+		// picture size: m2d_info_t carries int16 sizes (m2d.h:49-57), Table A-1 ends at MaxFS = 139264 macroblocks
+		unsigned wmb = br_.ue(), hmb = br_.ue();
+		if (wmb >= kMaxMbDim || hmb >= kMaxMbDim || (uint64_t)(wmb + 1) * (hmb + 1) > kMaxMbs) return -1;
+		s.width = (int)(wmb + 1) * 16;
+		s.height = (int)(hmb + 1) * 16;
 		s.frame_mbs_only = br_.get1();
 		if (!s.frame_mbs_only) s.mbaff = br_.get1();
 		s.direct_8x8_inference = br_.get1();
-		if (br_.get1()) for (int i = 0; i < 4; ++i) s.crop[i] = br_.ue() * 2;
+		if (br_.get1()) {
+			unsigned c[4];
+			for (int i = 0; i < 4; ++i) c[i] = br_.ue();
+			if ((uint64_t)c[0] + c[1] >= (unsigned)s.width / 2 || (uint64_t)c[2] + c[3] >= (unsigned)s.height / 2) return -1;
+			for (int i = 0; i < 4; ++i) s.crop[i] = (int)c[i] * 2;
+		}
 		// VUI is not needed for reconstruction
 		s.max_dpb_mbs = max_dpb_mbs(s.profile_idc, s.level_idc, s.constraint);
 		if (br_.overrun()) return -1;
@@ -400,13 +432,18 @@ private:
 		p.cabac = br_.get1();
 		p.pic_order_present = br_.get1();
 		if (br_.ue() > 0) return;   // FMO: not supported by the reference either (h264.cpp:418-421)
-		p.num_ref_idx_active[0] = br_.ue() + 1;
-		p.num_ref_idx_active[1] = br_.ue() + 1;
+		unsigned n0 = br_.ue(), n1 = br_.ue();
+		if (n0 > 31 || n1 > 31) return;
+		p.num_ref_idx_active[0] = (int)n0 + 1;
+		p.num_ref_idx_active[1] = (int)n1 + 1;
 		p.weighted_pred = br_.get1();
 		p.weighted_bipred_idc = br_.get(2);
+		if (p.weighted_bipred_idc > 2) return;
 		p.pic_init_qp = br_.se() + 26;
+		if (p.pic_init_qp < 0 || p.pic_init_qp > 51) return;
 		br_.se();
 		p.chroma_qp_offset[0] = p.chroma_qp_offset[1] = br_.se();
+		if (p.chroma_qp_offset[0] < -12 || p.chroma_qp_offset[0] > 12) return;
 		p.deblocking_control = br_.get1();
 		p.constrained_intra = br_.get1();
 		p.redundant_pic_cnt = br_.get1();
@@ -414,6 +451,7 @@ private:
 			p.transform_8x8 = br_.get1();
 			if (br_.get1()) { /* pic scaling matrix: flags only are consumed by the reference (h264.cpp:437-438) */ }
 			p.chroma_qp_offset[1] = br_.se();
+			if (p.chroma_qp_offset[1] < -12 || p.chroma_qp_offset[1] > 12) return;
 		}
 		p.valid = !br_.overrun();
 		pps_[id] = p;
@@ -456,6 +494,11 @@ private:
 			unsupported_ = true;
 			return -3;
 		}
+		// the application's frame buffers (and the device pool) were sized by set_frames for frames_w_ x frames_h_
+		if (sps.width != frames_w_ || sps.height != frames_h_) return -1;
+		// first_mb_in_slice is ue(v): up to 2^32 - 2.  It becomes the macroblock address every table of the
+		// picture is indexed with
+		if (first_mb >= (uint32_t)((sps.width >> 4) * (sps.height >> 4))) return -1;
 		if (new_picture) begin_picture(sps);
 		prev_first_mb_ = first_mb;
 		h.first_mb = (int)first_mb;
@@ -525,14 +568,17 @@ private:
 			if (h.cabac_init_idc > 2) return -1;
 		}
 		h.qp = pps.pic_init_qp + br_.se();
+		if (h.qp < 0 || h.qp > 51) return -1;    // SliceQPY indexes the dequantisation and filter tables
 		h.disable_deblock = 0;
 		h.alpha_off = h.beta_off = 0;
 		if (pps.deblocking_control) {
 			h.disable_deblock = br_.ue();
 			if (h.disable_deblock > 2) return -1;
 			if (h.disable_deblock != 1) {
-				h.alpha_off = br_.se() * 2;
-				h.beta_off = br_.se() * 2;
+				int a = br_.se(), b = br_.se();
+				if (a < -6 || a > 6 || b < -6 || b > 6) return -1;
+				h.alpha_off = a * 2;
+				h.beta_off = b * 2;
 			}
 		}
 		if (br_.overrun()) throw BitError();
@@ -702,6 +748,7 @@ private:
 		size_t n = (size_t)mb_w_ * mb_h_;
 		mbs_.assign(n, b2_h264_mb());
 		dbk_.assign(n, b2_h264_dbk());
+		mb_seen_.assign(n, 0);
 		mcs_.clear();
 		for (auto &b : items_) b.clear();
 		for (auto &b : items_first_) b.clear();
@@ -916,6 +963,11 @@ private:
 		cur_mbx_ = mbx;         // (kept for emit_mc: no division per motion record)
 		cur_mby_ = mby;
 		ctx_.open_mb(mbx, mby, slice_num_);
+		// a macroblock address comes once per picture; a (damaged) slice that runs into macroblocks an earlier
+		// slice already delivered would leave their motion records and work items behind
+		uint8_t &seen = mb_seen_[(size_t)mby * mb_w_ + mbx];
+		if (seen) throw BitError();
+		seen = 1;
 		b2_h264_mb &m = mbs_[(size_t)mby * mb_w_ + mbx];
 		memset(&m, 0, sizeof(m));
 		m.coef_idx = (uint32_t)(coef_used_ / 16);
@@ -1266,6 +1318,7 @@ private:
 
 	void read_qp_delta() {
 		int d = cabac_ ? cs_.qp_delta(last_dqp_ != 0, 0) : br_.se();
+		if (d < -26 || d > 25) throw BitError();   // 7.4.5: outside this range the QP leaves 0..51 (a table index on the device)
 		last_dqp_ = d;
 		qp_ += d;
 		if (qp_ < 0) qp_ += 52;
@@ -1842,6 +1895,7 @@ private:
 	int cur_frame_;
 	bool pic_open_;
 	uint32_t prev_first_mb_;
+	int frames_w_ = 0, frames_h_ = 0;   // coded size set_frames was called for
 	std::vector<RefPic> refs_;       // pictures marked "used for reference"
 	std::vector<RefPic> list_[2], init0_;
 	ColPic col_[MAX_H264_FRAMES];
@@ -1859,6 +1913,7 @@ private:
 	PicCtx ctx_;
 	std::vector<b2_h264_mb> mbs_;
 	std::vector<b2_h264_dbk> dbk_;
+	std::vector<uint8_t> mb_seen_;          // macroblock addresses delivered in the open picture
 	std::vector<b2_h264_mc> mcs_;
 	int cur_mbx_ = 0, cur_mby_ = 0;                           // macroblock being parsed (set by open_mb)
 	std::vector<uint32_t> items_[72], items_first_[72], items_all_;      // inter work items per (class, height) bucket / concatenated

@@ -1900,13 +1900,7 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 	if (phase == 0) {
 		dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
 		constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint16_t) * I5_QUEUE * (I5_THREADS / 32);
-		static bool attr_set = false;       // per process; the attribute is per device function
-		if (!attr_set) {
-			B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-			B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-			B2_CUDA_OK(cudaFuncSetAttribute(h264_inter5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-			attr_set = true;
-		}
+		static_assert(smem5 <= 48 * 1024, "above 48 KB the kernels need cudaFuncAttributeMaxDynamicSharedMemorySize, per device");
 		if (max_first) {
 			dim3 grid_first((max_first + I5_THREADS - 1) / I5_THREADS, n_jobs);
 			h264_inter5_kernel<1><<<grid_first, I5_THREADS, smem5, stream>>>(d_jobs);

@@ -9,6 +9,7 @@
 // saturation and mismatch control (945-1097).  Scope: MPEG-2 frame pictures (progressive or
 // interlaced frame pictures with field prediction / field DCT).  Field pictures and MPEG-1
 // streams are rejected (the reference handles field pictures only partially).
+#include <exception>
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -73,6 +74,7 @@ public:
 		intra_vlc_format_ = 0;
 		alternate_scan_ = 0;
 		num_frames_ = 0;
+		frames_mb_w_ = frames_mb_h_ = 0;
 		cur_idx_ = -1;
 		ref_idx_[0] = ref_idx_[1] = 0;
 		memset(lru_, 0, sizeof(lru_));
@@ -112,6 +114,8 @@ public:
 		memcpy(frames_, frames, sizeof(frames_[0]) * num);
 		cur_idx_ = -1;
 		memset(host_valid_, 0, sizeof(host_valid_));
+		frames_mb_w_ = mb_w_;    // the application sized its buffers for this geometry (get_info); slices of
+		frames_mb_h_ = mb_h_;    // any other are ignored, their pictures would overrun those buffers
 		backend.bind_frames(frames_, num);
 		return backend.configure(B2_CODEC_MPEG2, mb_w_ * 16, mb_h_ * 16, num);
 	}
@@ -121,7 +125,15 @@ public:
 		for (;;) {
 			if (backend.dead()) return -4;   // no CUDA device: nothing else can reconstruct
 			Unit u;
-			if (next_unit(stream_, &u) < 0) return -1;
+			if (next_unit(stream_, &u) < 0) {
+				// end of data: a picture whose last macroblock never came (truncated stream, lost last
+				// slice) is still submitted, so that frame-out does not hand out stale pixels
+				try {
+					flush_picture();
+				} catch (const std::exception &) {
+				}
+				return -1;
+			}
 			if (u.len == 0) continue;
 			int code = u.data[0];
 			br_.init(u.data + 1, u.len - 1);
@@ -130,6 +142,11 @@ public:
 				r = dispatch(code);
 			} catch (const BitError &) {
 				r = 0;   // the reference unwinds to m2d_dispatch_one_nal and carries on (mpeg2.cpp:666-668)
+			} catch (const std::exception &e) {
+				// allocation failure and the like: nothing may unwind through the extern "C" entry point
+				fprintf(stderr, "m2dec_b200: MPEG-2 decode_picture: %s\n", e.what());
+				picture_open_ = false;
+				return -1;
 			}
 			if (r == 1) return 1;
 		}
@@ -186,6 +203,8 @@ private:
 	}
 
 	void set_size(int w, int h) {
+		// a size change under an open picture: submit it first, its records have the old geometry
+		if (picture_open_ && (((w + 15) >> 4) != mb_w_ || ((h + 15) >> 4) != mb_h_)) flush_picture();
 		width_ = w;
 		height_ = h;
 		mb_w_ = (w + 15) >> 4;
@@ -336,6 +355,7 @@ private:
 		if (!is_mpeg2_ || picture_structure_ != 3 || mb_w_ == 0) return 0;
 		if (pic_type_ < I_PIC || pic_type_ > B_PIC) return 0;  // unsupported: ignore slice data
 		if (num_frames_ == 0) return 0;
+		if (mb_w_ != frames_mb_w_ || mb_h_ != frames_mb_h_) return 0;
 		q_scale_ = qscale_from_code(br_.get(5));
 		int row = code - 1;
 		if (row == 0) {
@@ -448,6 +468,7 @@ private:
 
 	// one motion vector component (mpeg2.cpp:1189-1212)
 	int mv_component(int16_t *pred, int f_code, int shift) {
+		if (f_code == 0) throw BitError();   // forbidden value (6.3.10): r_size would be a negative shift count
 		int r_size = f_code - 1;
 		int code = tables().motion.decode(br_);
 		if (code == Vlc::INVALID) throw BitError();
@@ -489,9 +510,11 @@ private:
 		}
 	}
 
-	int16_t *new_block() {
+	// Coefficient records of a whole macroblock at once: a bitstream error in the middle of the macroblock
+	// then leaves zero blocks behind, never a cbp that claims records which do not exist.
+	int16_t *new_blocks(int count) {
 		size_t n = coefs_.size();
-		coefs_.resize(n + 64, 0);
+		coefs_.resize(n + 64 * (size_t)count, 0);
 		return &coefs_[n];
 	}
 
@@ -582,10 +605,11 @@ private:
 			m->flags = B2_M2_INTRA | (dct_type ? B2_M2_FIELD_DCT : 0);
 			m->cbp = 0x3f;
 			m->coef_idx = (uint32_t)(coefs_.size() / 64);
+			int16_t *blocks = new_blocks(6);
 			for (int k = 0; k < 6; ++k) {
 				int comp = k < 4 ? 0 : k - 3;
 				int dc = intra_dc(comp);
-				int16_t *blk = new_block();
+				int16_t *blk = blocks + 64 * k;
 				blk[0] = (int16_t)dc;
 				coefficients(blk, false, 1);
 			}
@@ -620,9 +644,10 @@ private:
 			if (cbp == Vlc::INVALID) throw BitError();
 			m->cbp = (uint8_t)cbp;
 			m->coef_idx = (uint32_t)(coefs_.size() / 64);
+			int16_t *blk = new_blocks(__builtin_popcount((unsigned)cbp & 63u)) - 64;
 			for (int k = 0; k < 6; ++k) {
 				if (!(cbp & (1 << (5 - k)))) continue;
-				int16_t *blk = new_block();
+				blk += 64;
 				int idx = 0;
 				if (br_.peek(1)) {   // "1s": first coefficient, run 0 level +-1 (mpeg2.cpp:1318-1340)
 					int neg = (int)(br_.get(2) & 1);
@@ -656,6 +681,7 @@ private:
 	int16_t dc_pred_[3];
 	int16_t pmv_[2][2][2];
 	bool picture_open_;
+	int frames_mb_w_ = 0, frames_mb_h_ = 0;   // geometry set_frames was called for
 	std::vector<b2_m2_mb> mbs_;
 	std::vector<int16_t> coefs_;
 	b2_m2_mb scratch_mb_;

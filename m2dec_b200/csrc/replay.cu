@@ -128,12 +128,7 @@ static int upload(b2_replay *r, const std::vector<std::pair<const void *, size_t
 extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture *p) {
 	if (!r || !p || r->codec != B2_CODEC_H264 || (unsigned)lane >= (unsigned)r->lanes) return -1;
 	if (p->mb_w * 16 != r->width || p->mb_h * 16 != r->height || (unsigned)p->dst >= (unsigned)r->pool) return -1;
-	for (uint32_t i = 0; i < p->n_mcs; ++i)
-		if ((p->mcs[i].ref_frame[0] >= 0 && p->mcs[i].ref_frame[0] >= r->pool) || (p->mcs[i].ref_frame[1] >= 0 && p->mcs[i].ref_frame[1] >= r->pool) ||
-		    (p->mcs[i].ref_frame[0] < 0 && p->mcs[i].ref_frame[1] < 0)) {
-			set_error("replay: reference frame index %d outside the lane's pool of %d", p->mcs[i].ref_frame[0], r->pool);
-			return -1;
-		}
+	if (b2_h264_picture_check(p, r->pool) < 0) return -1;
 	B2_CUDA_OK(cudaSetDevice(r->dev));
 	std::vector<size_t> off;
 	uint8_t *d;
@@ -183,7 +178,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 extern "C" int b2_replay_add_mpeg2(b2_replay *r, int lane, const b2_m2_picture *p) {
 	if (!r || !p || r->codec != B2_CODEC_MPEG2 || (unsigned)lane >= (unsigned)r->lanes) return -1;
 	if (p->mb_w * 16 != r->width || p->mb_h * 16 != r->height) return -1;
-	if ((unsigned)p->dst >= (unsigned)r->pool || (unsigned)p->fwd >= (unsigned)r->pool || (unsigned)p->bwd >= (unsigned)r->pool) return -1;
+	if (b2_mpeg2_picture_check(p, r->pool) < 0) return -1;
 	B2_CUDA_OK(cudaSetDevice(r->dev));
 	std::vector<size_t> off;
 	uint8_t *d;

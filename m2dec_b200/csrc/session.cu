@@ -60,7 +60,34 @@ void cache_put(int dev, bool pinned, size_t bytes, void *ptr) {
 	std::lock_guard<std::mutex> lk(g_cache_mu);
 	g_cache.push_back(CachedBuf{dev, pinned, bytes, ptr});
 }
+// Free the oldest cached buffers until at most `keep` bytes of each kind (device / pinned) stay on the
+// free lists: a long-running server that has seen many geometries does not keep the peak of all of them.
+constexpr size_t kCacheKeepBytes = (size_t)4 << 30;
+void cache_trim(size_t keep) {
+	std::vector<CachedBuf> drop;
+	{
+		std::lock_guard<std::mutex> lk(g_cache_mu);
+		for (int pinned = 0; pinned < 2; ++pinned) {
+			size_t total = 0;
+			for (const CachedBuf &c : g_cache) if (c.pinned == (pinned != 0)) total += c.bytes;
+			for (size_t i = 0; i < g_cache.size() && total > keep;) {
+				if (g_cache[i].pinned == (pinned != 0)) {
+					total -= g_cache[i].bytes;
+					drop.push_back(g_cache[i]);
+					g_cache.erase(g_cache.begin() + i);
+				} else ++i;
+			}
+		}
+	}
+	for (const CachedBuf &c : drop) {
+		cudaSetDevice(c.dev);
+		if (c.pinned) cudaFreeHost(c.ptr); else cudaFree(c.ptr);
+	}
+}
 }  // namespace
+
+// Release every buffer on the process-wide free lists (device and page-locked host memory of closed sessions).
+extern "C" void b2_cache_trim(void) { cache_trim(0); }
 
 struct StageSlot {
 	uint8_t *host;
@@ -103,6 +130,23 @@ extern "C" int b2_device_count(void) {
 	return n;
 }
 
+static int session_build(b2_session *s) {
+	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < s->nframes; ++i) {
+		B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
+		// waited for by host threads that have nothing else to do meanwhile: block, do not spin
+		B2_CUDA_OK(cudaEventCreateWithFlags(&s->copy_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+	}
+	if (cache_get(s->dev, false, s->frame_bytes * s->nframes, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
+	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * s->nframes, s->stream));
+	if (cache_get(s->dev, false, h264_sync_bytes(1, s->width / 16, s->height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
+	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
+	return 0;
+}
+
+extern "C" void b2_session_destroy(b2_session *s);
+
 extern "C" int b2_session_create(int cuda_device, int codec, int width, int height, int nframes, b2_session **out) {
 	if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || nframes <= 0) {
 		set_error("b2_session_create: bad arguments (%dx%d, %d frames)", width, height, nframes);
@@ -114,6 +158,7 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 		return -1;
 	}
 	B2_CUDA_OK(cudaSetDevice(cuda_device));
+	if (nframes > 64) { set_error("b2_session_create: at most 64 frames"); return -1; }
 	b2_session *s = new b2_session();
 	memset(s, 0, sizeof(*s));
 	s->dev = cuda_device;
@@ -122,18 +167,12 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	s->height = height;
 	s->nframes = nframes;
 	s->frame_bytes = (size_t)width * height * 3 / 2;
-	if (nframes > 64) { set_error("b2_session_create: at most 64 frames"); delete s; return -1; }
-	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-	for (int i = 0; i < nframes; ++i) {
-		B2_CUDA_OK(cudaEventCreateWithFlags(&s->frame_done[i], cudaEventDisableTiming));
-		// waited for by host threads that have nothing else to do meanwhile: block, do not spin
-		B2_CUDA_OK(cudaEventCreateWithFlags(&s->copy_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+	// a failure anywhere below releases what was obtained so far (b2_session_destroy copes with a partly built
+	// session: everything is zero until it is created)
+	if (session_build(s) < 0) {
+		b2_session_destroy(s);
+		return -1;
 	}
-	if (cache_get(cuda_device, false, s->frame_bytes * nframes, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
-	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * nframes, s->stream));
-	if (cache_get(cuda_device, false, h264_sync_bytes(1, width / 16, height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
-	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
 	*out = s;
 	return 0;
 }
@@ -141,22 +180,24 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 extern "C" void b2_session_destroy(b2_session *s) {
 	if (!s) return;
 	cudaSetDevice(s->dev);
-	cudaStreamSynchronize(s->stream);
+	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (int i = 0; i < NSLOT; ++i) {
 		cache_put(s->dev, true, s->slots[i].cap_host, s->slots[i].host);
 		cache_put(s->dev, false, s->slots[i].cap_dev, s->slots[i].dev);
-		cudaEventDestroy(s->slots[i].done);
+		if (s->slots[i].done) cudaEventDestroy(s->slots[i].done);
 	}
-	cudaStreamSynchronize(s->copy_stream);
+	if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
 	for (int i = 0; i < s->nframes; ++i) {
-		cudaEventDestroy(s->frame_done[i]);
-		cudaEventDestroy(s->copy_done[i]);
+		if (s->frame_done[i]) cudaEventDestroy(s->frame_done[i]);
+		if (s->copy_done[i]) cudaEventDestroy(s->copy_done[i]);
 	}
 	cache_put(s->dev, false, s->frames_alloc, s->frames);
 	cache_put(s->dev, false, s->sync_alloc, s->sync_area);
-	cudaStreamDestroy(s->copy_stream);
-	cudaStreamDestroy(s->stream);
+	if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	cudaGetLastError();
 	delete s;
+	cache_trim(kCacheKeepBytes);
 }
 
 // Obtain a staging slot of at least `bytes`, waiting for its previous use to drain.
@@ -258,8 +299,7 @@ extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 		set_error("picture %dx%d MB does not match session %dx%d", p->mb_w, p->mb_h, s->width, s->height);
 		return -1;
 	}
-	if ((unsigned)p->dst >= (unsigned)s->nframes || (unsigned)p->fwd >= (unsigned)s->nframes ||
-	    (unsigned)p->bwd >= (unsigned)s->nframes) return -1;
+	if (b2_mpeg2_picture_check(p, s->nframes) < 0) return -1;
 	B2_CUDA_OK(cudaSetDevice(s->dev));
 	size_t off_mbs = align_up(sizeof(M2Job), 256);
 	size_t off_coef = align_up(off_mbs + sizeof(b2_m2_mb) * p->n_mbs, 256);
@@ -299,13 +339,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 		set_error("picture %dx%d MB does not match session %dx%d", p->mb_w, p->mb_h, s->width, s->height);
 		return -1;
 	}
-	if ((unsigned)p->dst >= (unsigned)s->nframes) return -1;
-	for (uint32_t i = 0; i < p->n_mcs; ++i)
-		if ((p->mcs[i].ref_frame[0] >= 0 && p->mcs[i].ref_frame[0] >= s->nframes) || (p->mcs[i].ref_frame[1] >= 0 && p->mcs[i].ref_frame[1] >= s->nframes) ||
-		    (p->mcs[i].ref_frame[0] < 0 && p->mcs[i].ref_frame[1] < 0)) {
-			set_error("motion record %u references frame %d outside the pool", i, p->mcs[i].ref_frame[0]);
-			return -1;
-		}
+	if (b2_h264_picture_check(p, s->nframes) < 0) return -1;
 	B2_CUDA_OK(cudaSetDevice(s->dev));
 	size_t off_mbs = align_up(sizeof(H4Job), 256);
 	size_t off_dbk = align_up(off_mbs + sizeof(b2_h264_mb) * p->n_mbs, 256);

@@ -105,8 +105,12 @@ def frame_md5(frm):
 
 
 class M2Decoder:
-    def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None):
+    def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None, chunk=0):
+        """chunk > 0: the stream is handed over `chunk` bytes at a time through ONE reused buffer, as the
+        reference application refills its input buffer (bytes of an earlier refill do not stay valid)."""
         self.codec = codec
+        self._chunk, self._pos = int(chunk), 0
+        self._chunk_buf = np.empty(max(int(chunk), 1), np.uint8)
         self._device_off, self._cuda_device = device_off, cuda_device
         self.func = L.func_table(_TABLES[codec])
         self._data = np.frombuffer(bytes(data), np.uint8)
@@ -146,6 +150,15 @@ class M2Decoder:
 
     # reference h264dec.cpp:67-84: hand the whole file over once, then report end of data
     def _on_refill(self, _arg):
+        if self._chunk > 0:
+            n = min(self._chunk, len(self._data) - self._pos)
+            if n <= 0:
+                return -1
+            self._chunk_buf[:] = 0xA5                       # whatever was there before is gone
+            self._chunk_buf[:n] = self._data[self._pos:self._pos + n]
+            self._pos += n
+            L.lib.dec_bits_set_data(self.stream, self._chunk_buf.ctypes.data, n, None)
+            return 0
         if self._fed:
             return -1
         self._fed = True

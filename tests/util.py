@@ -50,6 +50,10 @@ def oracle_tap(dec, codec, pic):
     luma = (C.c_void_p * n)(*[fr.array[i].luma for i in range(n)])
     chroma = (C.c_void_p * n)(*[fr.array[i].chroma for i in range(n)])
     o = oracle()
+    # every picture the front end emits must pass the structural check the device entry points run
+    from m2dec_b200 import _native as L
+    check = L.lib.b2_mpeg2_picture_check if codec == 1 else L.lib.b2_h264_picture_check
+    assert check(C.c_void_p(pic), n) == 0, (L.lib.b2_last_error() or b"").decode()
     if codec == 1:
         return o.oracle_mpeg2_picture(C.c_void_p(pic), luma, chroma)
     return o.oracle_h264_picture(C.c_void_p(pic), luma, chroma)
