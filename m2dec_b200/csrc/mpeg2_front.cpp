@@ -106,6 +106,7 @@ public:
 
 	int set_frames(int num, const m2d_frame_t *frames) {
 		if (num < 0 || num > MAX_M2_FRAMES || !frames) return -1;
+		if (mb_w_ <= 0 || mb_h_ <= 0 || (long)mb_w_ * mb_h_ > 139264) return -1;   // no (usable) sequence header yet
 		for (int i = 0; i < num; ++i) {
 			if (!frames[i].luma || !frames[i].chroma) return -1;
 			if (((uintptr_t)frames[i].luma | (uintptr_t)frames[i].chroma) & 15) return -1;
@@ -355,7 +356,7 @@ private:
 		if (!is_mpeg2_ || picture_structure_ != 3 || mb_w_ == 0) return 0;
 		if (pic_type_ < I_PIC || pic_type_ > B_PIC) return 0;  // unsupported: ignore slice data
 		if (num_frames_ == 0) return 0;
-		if (mb_w_ != frames_mb_w_ || mb_h_ != frames_mb_h_) return 0;
+		if (mb_w_ <= 0 || mb_h_ <= 0 || mb_w_ != frames_mb_w_ || mb_h_ != frames_mb_h_) return 0;
 		q_scale_ = qscale_from_code(br_.get(5));
 		int row = code - 1;
 		if (row == 0) {

@@ -29,6 +29,8 @@ def _decode(codec, data, **kw):
     dec = M2Decoder(codec, data, tap=tap, device_off=True, **kw)
     try:
         dec.run(lambda f: out.__setitem__(0, out[0] + 1))
+    except RuntimeError:
+        pass                    # the application gives up: set_frames refused the geometry of a damaged header
     finally:
         dec.close()
     return out[0], stats["pics"], stats["bad"]
@@ -183,6 +185,12 @@ def test_size_change_without_new_frames_is_refused():
 
 
 DAMAGED = sorted(f for f in os.listdir(os.path.join(util.GOLDEN, "damaged")) if f.endswith(".264"))
+
+
+def test_damaged_mpeg2_without_sequence_header():
+    """A sequence_extension with no sequence_header before it (width 8192, height 0): nothing may be decoded."""
+    data = open(os.path.join(util.GOLDEN, "damaged", "mpeg2_22_3275.m2v"), "rb").read()
+    assert _decode("mpeg2", data)[1:] == (0, 0)
 
 
 @pytest.mark.parametrize("name", DAMAGED)
