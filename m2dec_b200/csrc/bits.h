@@ -42,30 +42,30 @@ public:
 		p_ = data; end_ = data + len; cache_ = 0; n_ = 0; fake_ = 0;
 	}
 	// look at the next n (1..32) bits, MSB first
-	inline uint32_t peek(int n) {
+	inline __attribute__((always_inline)) uint32_t peek(int n) {
 		if (n_ < n) fill();
 		return (uint32_t)(cache_ >> (64 - n));
 	}
-	inline void skip(int n) {
+	inline __attribute__((always_inline)) void skip(int n) {
 		if (n_ < n) fill();
 		cache_ <<= n;
 		n_ -= n;
 	}
-	inline uint32_t get(int n) {
+	inline __attribute__((always_inline)) uint32_t get(int n) {
 		if (n == 0) return 0;
 		uint32_t v = peek(n);
 		cache_ <<= n;
 		n_ -= n;
 		return v;
 	}
-	inline uint32_t get1() {
+	inline __attribute__((always_inline)) uint32_t get1() {
 		if (n_ < 1) fill();
 		uint32_t v = (uint32_t)(cache_ >> 63);
 		cache_ <<= 1;
 		n_ -= 1;
 		return v;
 	}
-	inline uint32_t ue() {
+	inline __attribute__((always_inline)) uint32_t ue() {
 		uint32_t look = peek(32);
 		if (look & 0x80000000u) { skip(1); return 0; }
 		if (!look) { skip(32); return 0; }
@@ -73,7 +73,7 @@ public:
 		skip(zeros + 1);
 		return (1u << zeros) - 1 + get(zeros);
 	}
-	inline int32_t se() {
+	inline __attribute__((always_inline)) int32_t se() {
 		uint32_t k = ue();
 		int32_t t = (int32_t)((k + 1) >> 1);
 		return (k & 1) ? t : -t;

@@ -60,7 +60,7 @@ struct Pps {
 };
 
 struct H264Tables {
-	Vlc coeff_token[5], total_zeros[15], total_zeros_cdc[3], run_before[7];
+	VlcSmall coeff_token[5], total_zeros[15], total_zeros_cdc[3], run_before[7];
 	H264Tables() {
 		for (int i = 0; i < 5; ++i) coeff_token[i].build(h4t::coeff_token_tabs[i].codes, h4t::coeff_token_tabs[i].n, 8);
 		for (int i = 0; i < 15; ++i) total_zeros[i].build(h4t::total_zeros_tabs[i].codes, h4t::total_zeros_tabs[i].n, 9);
@@ -152,7 +152,7 @@ struct SliceHeader {
 
 class H264Decoder {
 public:
-	explicit H264Decoder(dec_bits *stream) : stream_(stream) { reset(-1, nullptr, nullptr); }
+	explicit H264Decoder(dec_bits *stream) : stream_(stream), tab_(&tables()) { reset(-1, nullptr, nullptr); }
 	Backend backend;
 
 	void reset(int dpb_max, int (*cb)(void *, void *), void *arg) {
@@ -1166,30 +1166,39 @@ private:
 	// out() is asked for the destination only once the block turns out to have coefficients, so that
 	// empty blocks (most of them) cost neither a record nor its clearing
 	template <class Out>
-	inline int residual_block(int nc, int max_coeff, Out &&out_of, const uint8_t *scan, int scan_ofs) {
-		const H264Tables &t = tables();
-		const Vlc &ct = nc < 0 ? t.coeff_token[4] : (nc < 2 ? t.coeff_token[0] : (nc < 4 ? t.coeff_token[1] : (nc < 8 ? t.coeff_token[2] : t.coeff_token[3])));
-		if (nc >= 0 && nc < 2 && br_.peek(1)) { br_.skip(1); return 0; }
-		int tok = ct.decode(br_);
-		if (tok == Vlc::INVALID) throw BitError();
-		int total = tok >> 2, t1 = tok & 3;
-		if (total == 0) return 0;
+	inline __attribute__((always_inline)) int residual_block(int nc, int max_coeff, Out &&out_of, const uint8_t *scan, int scan_ofs) {
+		const H264Tables &t = *tab_;
+		// one 32-bit look serves coeff_token (at most 16 bits) and the trailing-ones signs (at most 3)
+		uint32_t look = br_.peek(32);
+		if (nc >= 0 && nc < 2 && (look >> 31)) { br_.skip(1); return 0; }      // "1": no coefficients (the most frequent code)
+		const VlcSmall &ct = nc < 0 ? t.coeff_token[4] : (nc < 2 ? t.coeff_token[0] : (nc < 4 ? t.coeff_token[1] : (nc < 8 ? t.coeff_token[2] : t.coeff_token[3])));
+		int len;
+		const int tok = ct.lookup(look >> 16, &len);
+		if (tok < 0) throw BitError();
+		const int total = tok >> 2, t1 = tok & 3;
+		if (total == 0) { br_.skip(len); return 0; }
 		if (total > max_coeff) throw BitError();
 		int16_t *out = out_of();
 		int level[16];
-		for (int i = 0; i < t1; ++i) level[i] = br_.get1() ? -1 : 1;
+		for (int i = 0; i < t1; ++i) level[i] = 1 - 2 * (int)((look >> (31 - len - i)) & 1);
+		br_.skip(len + t1);
 		int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
 		for (int i = t1; i < total; ++i) {
-			// level_prefix: count leading zeros, then the terminating one
-			uint32_t look = br_.peek(32);
+			// level_prefix: count leading zeros, then the terminating one; the suffix comes from the same look
+			look = br_.peek(32);
 			if (!look) throw BitError();
-			int prefix = __builtin_clz(look);
-			br_.skip(prefix + 1);
+			const int prefix = __builtin_clz(look);
 			int code = (prefix < 15 ? prefix : 15) << suffix_len;
 			int size = suffix_len;
 			if (prefix == 14 && suffix_len == 0) size = 4;
 			else if (prefix >= 15) size = prefix - 3;
-			if (size) code += (int)br_.get(size);
+			if (prefix + 1 + size <= 32) {
+				if (size) code += (int)((look << (prefix + 1)) >> (32 - size));
+				br_.skip(prefix + 1 + size);
+			} else {
+				br_.skip(prefix + 1);
+				code += (int)br_.get(size);
+			}
 			if (prefix >= 15 && suffix_len == 0) code += 15;
 			if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
 			if (i == t1 && t1 < 3) code += 2;
@@ -1199,28 +1208,36 @@ private:
 			int a = lv < 0 ? -lv : lv;
 			if (suffix_len < 6 && a > (3 << (suffix_len - 1))) suffix_len++;
 		}
+		// total_zeros (at most 9 bits) and the run_before codes (at most 11 bits each) from shared looks
+		look = br_.peek(32);
+		int used = 0;
 		int zeros_left = 0;
 		if (total < max_coeff) {
-			const Vlc &tz = max_coeff == 4 ? t.total_zeros_cdc[total - 1] : t.total_zeros[total - 1];
-			zeros_left = tz.decode(br_);
-			if (zeros_left == Vlc::INVALID) throw BitError();
+			const VlcSmall &tz = max_coeff == 4 ? t.total_zeros_cdc[total - 1] : t.total_zeros[total - 1];
+			zeros_left = tz.lookup(look >> 16, &len);
+			if (zeros_left < 0) throw BitError();
+			used = len;
 		}
 		// levels come highest frequency first
 		int pos = total + zeros_left - 1;
+		if (pos >= max_coeff) throw BitError();
+		scan += scan_ofs;
 		for (int i = 0; i < total; ++i) {
-			if (pos < 0 || pos >= max_coeff) throw BitError();
 			int lv = level[i];
 			if (lv > 32767) lv = 32767;
 			if (lv < -32768) lv = -32768;
-			out[scan[pos + scan_ofs]] = (int16_t)lv;
+			out[scan[pos]] = (int16_t)lv;
 			if (i < total - 1 && zeros_left > 0) {
-				int rb = t.run_before[(zeros_left > 7 ? 7 : zeros_left) - 1].decode(br_);
-				if (rb == Vlc::INVALID) throw BitError();
+				if (used > 16) { br_.skip(used); look = br_.peek(32); used = 0; }
+				const int rb = t.run_before[(zeros_left > 7 ? 7 : zeros_left) - 1].lookup((look << used) >> 16, &len);
+				if (rb < 0 || rb > zeros_left) throw BitError();
+				used += len;
 				zeros_left -= rb;
 				pos -= rb;
 			}
 			pos--;
 		}
+		br_.skip(used);
 		return total;
 	}
 
@@ -1895,6 +1912,7 @@ private:
 	int cur_frame_;
 	bool pic_open_;
 	uint32_t prev_first_mb_;
+	const H264Tables *tab_;             // the CAVLC tables (built once per process)
 	int frames_w_ = 0, frames_h_ = 0;   // coded size set_frames was called for
 	std::vector<RefPic> refs_;       // pictures marked "used for reference"
 	std::vector<RefPic> list_[2], init0_;

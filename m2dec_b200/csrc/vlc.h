@@ -64,7 +64,7 @@ public:
 		}
 	}
 	// Returns the decoded value, or INVALID (no bits consumed) for an undefined code.
-	inline int32_t decode(BitReader &br) const {
+	inline __attribute__((always_inline)) int32_t decode(BitReader &br) const {
 		uint32_t v = br.peek(maxlen_);
 		const Entry *e = &tab_[v >> (maxlen_ - l1_)];
 		if (e->len == -1) e = &tab_[(uint32_t)e->value + (v & ((1u << (maxlen_ - l1_)) - 1))];
@@ -77,6 +77,55 @@ private:
 	struct Entry { int32_t value; int8_t len; };
 	std::vector<Entry> tab_;
 	int l1_, maxlen_;
+};
+
+// Compact two-level table for codes of at most 16 bits and values 0..255 (the H.264 CAVLC tables): 16-bit
+// entries, so that all tables of the residual parse together stay a few KB of L1.  Entry: value in bits 0..7,
+// code length in bits 8..12 (0 = undefined code), bit 15 = link to a second-level table (value = its number).
+class VlcSmall {
+public:
+	enum { INVALID = -1 };
+	VlcSmall() : l1_(0), l2_(0) {}
+	void build(const VlcCode *codes, int n, int l1bits) {
+		int maxlen = 0;
+		std::vector<uint32_t> code(n);
+		std::vector<int> len(n);
+		for (int i = 0; i < n; ++i) {
+			len[i] = vlc_parse(codes[i].bits, &code[i]);
+			if (len[i] > maxlen) maxlen = len[i];
+		}
+		l1_ = l1bits < maxlen ? l1bits : maxlen;
+		l2_ = maxlen - l1_;
+		tab_.assign((size_t)1 << l1_, 0);
+		int n_sub = 0;
+		for (int i = 0; i < n; ++i) {
+			const uint16_t leaf = (uint16_t)((len[i] << 8) | (codes[i].value & 255));
+			if (len[i] <= l1_) {
+				const uint32_t base = code[i] << (l1_ - len[i]);
+				for (uint32_t k = 0; k < (1u << (l1_ - len[i])); ++k) tab_[base + k] = leaf;
+			} else {
+				const uint32_t prefix = code[i] >> (len[i] - l1_);
+				if (!(tab_[prefix] & 0x8000)) {
+					tab_[prefix] = (uint16_t)(0x8000 | n_sub++);
+					tab_.resize(tab_.size() + ((size_t)1 << l2_), 0);
+				}
+				const uint32_t off = ((uint32_t)1 << l1_) + ((uint32_t)(tab_[prefix] & 255) << l2_);
+				const int rem = len[i] - l1_;
+				const uint32_t base = (code[i] & ((1u << rem) - 1)) << (l2_ - rem);
+				for (uint32_t k = 0; k < (1u << (l2_ - rem)); ++k) tab_[off + base + k] = leaf;
+			}
+		}
+	}
+	// look16 = the next 16 bits of the stream.  Returns the value and sets *len, or INVALID (undefined code).
+	inline __attribute__((always_inline)) int lookup(uint32_t look16, int *len) const {
+		uint32_t e = tab_[look16 >> (16 - l1_)];
+		if (e & 0x8000) e = tab_[(1u << l1_) + ((e & 255) << l2_) + ((look16 >> (16 - l1_ - l2_)) & ((1u << l2_) - 1))];
+		*len = (int)(e >> 8);
+		return e ? (int)(e & 255) : (int)INVALID;
+	}
+private:
+	std::vector<uint16_t> tab_;
+	int l1_, l2_;
 };
 
 }  // namespace b2

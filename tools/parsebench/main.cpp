@@ -24,6 +24,38 @@ const char *b2_last_error(void) { return ""; }
 }
 namespace b2 { void set_error(const char *, ...) {} }
 
+#ifdef PARSEBENCH_SAMPLE
+// poor man's sampling profiler (no perf in the image): SIGPROF every 250 us, program counters to pcs.txt;
+// tools/parsebench/report.py turns them into per-function / per-line shares with addr2line
+#include <signal.h>
+#include <sys/time.h>
+#include <ucontext.h>
+static uint64_t g_pcs[1 << 20];
+static volatile int g_npcs = 0;
+static void on_prof(int, siginfo_t *, void *uc) {
+	if (g_npcs < (1 << 20)) g_pcs[g_npcs++] = (uint64_t)((ucontext_t *)uc)->uc_mcontext.gregs[REG_RIP];
+}
+static void sample_start() {
+	struct sigaction sa;
+	memset(&sa, 0, sizeof(sa));
+	sa.sa_sigaction = on_prof;
+	sa.sa_flags = SA_SIGINFO | SA_RESTART;
+	sigaction(SIGPROF, &sa, nullptr);
+	struct itimerval tv = {{0, 250}, {0, 250}};
+	setitimer(ITIMER_PROF, &tv, nullptr);
+}
+static void sample_stop() {
+	struct itimerval tv = {{0, 0}, {0, 0}};
+	setitimer(ITIMER_PROF, &tv, nullptr);
+	FILE *f = fopen("pcs.txt", "w");
+	for (int i = 0; i < g_npcs; ++i) fprintf(f, "%llx\n", (unsigned long long)g_pcs[i]);
+	fclose(f);
+}
+#else
+static void sample_start() {}
+static void sample_stop() {}
+#endif
+
 struct App {
 	const m2d_func_table_t *f;
 	void *ctx;
@@ -73,6 +105,7 @@ int main(int argc, char **argv) {
 	int reps = argc > 3 ? atoi(argv[3]) : 5;
 	double best = 1e30;
 	long pics = 0;
+	sample_start();
 	for (int r = 0; r < reps; ++r) {
 		std::vector<uint8_t> ctx(a.f->context_size);
 		a.ctx = ctx.data();
@@ -91,6 +124,7 @@ int main(int argc, char **argv) {
 		if (dt < best) best = dt;
 		pics = a.pictures;
 	}
+	sample_stop();
 	printf("%ld pictures, %.3f ms per picture (best of %d), %.1f Mbit/s\n", pics, 1000.0 * best / (pics ? pics : 1), reps,
 	       a.data.size() * 8.0 / best / 1e6);
 	return 0;
