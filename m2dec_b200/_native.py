@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libm2dec_b200.so")
+# B2_LIB: another build of the library (kernel experiments: tools/variants.py)
+LIB_PATH = os.environ.get("B2_LIB") or os.path.join(HERE, "libm2dec_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

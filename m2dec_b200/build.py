@@ -26,11 +26,13 @@ def _newer(src_list, out):
     return any(os.path.getmtime(p) > t for p in deps if os.path.isfile(p))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, extra=(), objdir=None):
+    """out / extra / objdir: a variant build (other -D flags) next to the product library, for kernel experiments."""
+    OUT = out or globals()["OUT"]
     srcs = [os.path.join(CSRC, f) for f in CPP + CU if os.path.exists(os.path.join(CSRC, f))]
     if not force and not _newer(srcs, OUT):
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     common = ["-O3", "-std=c++17", "-lineinfo", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
@@ -39,7 +41,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [NVCC] + ARCH + common + os.environ.get("B2_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [NVCC] + ARCH + common + os.environ.get("B2_NVCC_EXTRA", "").split() + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for cmd, p in procs:

@@ -1107,6 +1107,32 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 __device__ __forceinline__ void st_release(int *p, int v) {
 	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Spinning on a flag: every ld.acquire.gpu carries an L1 invalidation (CCTL.IVALL; 10 % of the stall samples of
+// the round-1 deblocking kernel), so the loop polls with relaxed loads and one acquire fence follows the hit.
+#ifndef B2_SPIN_RELAXED
+#define B2_SPIN_RELAXED 1
+#endif
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+	int v;
+	asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void fence_acquire() {
+#if B2_SPIN_RELAXED != 2      // (2: timing experiment without the fence)
+	asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+// wait until *p >= want; returns the value seen
+__device__ __forceinline__ int spin_until(const int *p, int want) {
+	int v;
+#if B2_SPIN_RELAXED
+	while ((v = ld_relaxed(p)) < want) __nanosleep(32);
+	fence_acquire();
+#else
+	while ((v = ld_acquire(p)) < want) __nanosleep(32);
+#endif
+	return v;
+}
 
 // Progress of a macroblock row ("macroblocks < n are final") as seen by the row below.  Rows of
 // one CTA's group hand it over through shared memory with CTA-scope fences; only the first row of
@@ -1129,9 +1155,7 @@ struct RowSync {
 				__threadfence_block();
 			}
 		} else if (gl_above) {
-			if (lane == 0) {
-				while ((seen = ld_acquire(gl_above)) < want) __nanosleep(32);
-			}
+			if (lane == 0) seen = spin_until(gl_above, want);
 		} else {
 			seen = 1 << 30;
 		}
@@ -1487,6 +1511,23 @@ struct alignas(16) DbkTile2 {
 	uint32_t c[10][28];     // chroma rows -2..7 at r + 2, byte columns (Cb Cr interleaved) -4..15 at c + 4
 };
 
+// What a warp stages per chunk of 32 macroblocks so that nothing inside the macroblock loop waits for a global
+// load it could have asked for earlier (the round-2 profile had 20 % of the kernel's stall samples on the first
+// use of the strength record and of the macroblock's own samples): the strength records of both pictures and the
+// QP words of the row above (read once per chunk, by the pass that finds the macroblocks needing work), and a
+// two-slot ring that the own samples of the NEXT macroblock are copied into (cp.async) while the current one
+// is filtered.
+struct alignas(16) DbkStage2 {
+	uint4 rec[2][32];           // [picture][macroblock of the chunk]
+	uint32_t qp_top[2][32];     // word 2 (QPs, flags) of the record above
+	uint4 own[2][2][24];        // [slot][picture][line: luma 0..15, chroma 16..23]: 16 bytes of the line
+};
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint32_t vneg2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ uint32_t bits_mask(uint32_t bits) { return bits - (bits >> 15); }     // 0x8000 per lane -> 0x7fff per lane
 __device__ __forceinline__ uint32_t vsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
@@ -1604,7 +1645,7 @@ __device__ __forceinline__ void unpair4(const uint32_t *e, uint32_t &wa, uint32_
 }
 
 // One row chunk of a picture pair: macroblocks x0 + k for the set bits k of `todo` (needed by either picture), left to right.
-__device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB, const DbkTables &tb, DbkTile2 &tl, int mby, int x0, unsigned todo, int lane,
+__device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB, const DbkTables &tb, DbkTile2 &tl, DbkStage2 &sg, int mby, int x0, unsigned todo, int lane,
                                RowSync &sy, int &done_to) {
 	const int mb_w = jobA.mb_w, W = mb_w * 16, H = jobA.mb_h * 16;
 	uint8_t *const fyA = jobA.frames + jobA.frame_bytes * jobA.dst, *const fyB = jobB.frames + jobB.frame_bytes * jobB.dst;
@@ -1617,27 +1658,43 @@ __device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB
 	uint32_t *const trow = luma ? tl.y[4 + line] : tl.c[2 + line];      // this lane's line in the tile
 	const uint32_t csel = comp ? 0x7531u : 0x6420u;         // chroma: bytes (comp, 2 + comp) of both words
 	bool carry_in = false;
+	// own samples of a macroblock into a ring slot: luma lanes copy their line of both pictures, the two lanes of a
+	// chroma line one picture each.  (Nobody else writes these samples before this row has published them.)
+	const int own_line = luma ? line : 16 + line;
+	auto fetch_own = [&](int xx, int slot) {
+		if (luma || !comp) cp_async16(&sg.own[slot][0][own_line], lbA + xx * 16);
+		if (luma || comp) cp_async16(&sg.own[slot][1][own_line], lbB + xx * 16);
+		cp_async_commit();
+	};
+	int slot = 0;
+	if (todo) fetch_own(x0 + __ffs(todo) - 1, 0);
 	while (todo) {
 		const int k = __ffs(todo) - 1;
 		todo &= todo - 1;
 		const int x = x0 + k;
 		const bool carry_out = todo && (__ffs(todo) - 1 == k + 1);      // the next macroblock takes over columns 12..15
+		if (todo) fetch_own(x0 + __ffs(todo) - 1, slot ^ 1);             // the next macroblock's samples, while this one is filtered
 		if (x > done_to) sy.publish(x, lane);              // the stretch that needed nothing
-		const size_t mbi = (size_t)mby * mb_w + x;
-		const b2_h264_dbk *dpA = jobA.dbk + mbi, *dpB = jobB.dbk + mbi;
-		uint4 drA = __ldg(reinterpret_cast<const uint4 *>(dpA)), drB = __ldg(reinterpret_cast<const uint4 *>(dpB));
-		const uint32_t qlA = x > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpA - 1) + 2) : 0, qlB = x > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpB - 1) + 2) : 0;
-		const uint32_t qtA = mby > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpA - mb_w) + 2) : 0, qtB = mby > 0 ? __ldg(reinterpret_cast<const uint32_t *>(dpB - mb_w) + 2) : 0;
+		uint4 drA = sg.rec[0][k], drB = sg.rec[1][k];
+		uint32_t qlA = 0, qlB = 0;
+		if (k > 0) { qlA = sg.rec[0][k - 1].z; qlB = sg.rec[1][k - 1].z; }
+		else if (x > 0) {
+			const size_t mbi = (size_t)mby * mb_w + x;
+			qlA = __ldg(reinterpret_cast<const uint32_t *>(jobA.dbk + mbi - 1) + 2);
+			qlB = __ldg(reinterpret_cast<const uint32_t *>(jobB.dbk + mbi - 1) + 2);
+		}
+		const uint32_t qtA = sg.qp_top[0][k], qtB = sg.qp_top[1][k];
 		if ((drA.z >> 24) & B2_DBK_OFF) drA.x = drA.y = 0;
 		if (((drB.z >> 24) & B2_DBK_OFF) || !validB) drB.x = drB.y = 0;
 		uint32_t wA[5], wB[5];
-#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			// the macroblock's own samples have not been touched by this launch yet (L1 starts a launch empty), so they
-			// may come through L1: one 128-byte line serves this line of eight macroblocks
-			wA[1 + i] = __ldca(reinterpret_cast<const uint32_t *>(lbA + x * 16 + 4 * i));
-			wB[1 + i] = __ldca(reinterpret_cast<const uint32_t *>(lbB + x * 16 + 4 * i));
+		if (todo) cp_async_wait<1>(); else cp_async_wait<0>();
+		__syncwarp();
+		{
+			const uint4 oa = sg.own[slot][0][own_line], ob = sg.own[slot][1][own_line];
+			wA[1] = oa.x; wA[2] = oa.y; wA[3] = oa.z; wA[4] = oa.w;
+			wB[1] = ob.x; wB[2] = ob.y; wB[3] = ob.z; wB[4] = ob.w;
 		}
+		slot ^= 1;
 		wA[0] = wB[0] = 0;
 		if (!carry_in && x > 0) {
 			wA[0] = __ldcg(reinterpret_cast<const uint32_t *>(lbA + x * 16 - 4));
@@ -1788,6 +1845,7 @@ constexpr int DBK2_CTAS = B2_DBK2_WARPS_PER_SM / DBK2_WARPS;        // resident 
 __global__ void __launch_bounds__(32 * DBK2_WARPS, DBK2_CTAS)
 h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
 	__shared__ DbkTile2 s_tile[DBK2_WARPS];
+	__shared__ DbkStage2 s_stage[DBK2_WARPS];
 	__shared__ DbkTables s_tb;
 	__shared__ int s_ticket;
 	__shared__ int s_prog[DBK2_WARPS];
@@ -1820,19 +1878,29 @@ h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int m
 		const bool validB = 2 * j + 1 < n_jobs;
 		const H4Job jobA = jobs[2 * j], jobB = jobs[validB ? 2 * j + 1 : 2 * j];
 		for (int x0 = 0; x0 < mb_w; x0 += 32) {
+			// one pass over the chunk's strength records: which macroblocks need work, and everything the loop
+			// will want from the records goes to shared memory
 			const int mbx = x0 + lane;
-			bool need = false;
+			DbkStage2 &sg = s_stage[warp];
+			uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+			uint32_t ta = 0, tb = 0;
 			if (mbx < mb_w) {
-				const b2_h264_dbk *d = &jobA.dbk[(size_t)mby * mb_w + mbx];
-				need = !(d->flags & B2_DBK_OFF) && (d->bs_v | d->bs_h);
-				if (validB) {
-					d = &jobB.dbk[(size_t)mby * mb_w + mbx];
-					need |= !(d->flags & B2_DBK_OFF) && (d->bs_v | d->bs_h);
+				const size_t mbi = (size_t)mby * mb_w + mbx;
+				ra = __ldg(reinterpret_cast<const uint4 *>(jobA.dbk + mbi));
+				if (validB) rb = __ldg(reinterpret_cast<const uint4 *>(jobB.dbk + mbi));
+				if (mby > 0) {
+					ta = __ldg(reinterpret_cast<const uint32_t *>(jobA.dbk + mbi - mb_w) + 2);
+					tb = __ldg(reinterpret_cast<const uint32_t *>(jobB.dbk + mbi - mb_w) + 2);
 				}
 			}
+			__syncwarp();                      // the previous chunk's readers are done
+			sg.rec[0][lane] = ra; sg.rec[1][lane] = rb;
+			sg.qp_top[0][lane] = ta; sg.qp_top[1][lane] = tb;
+			__syncwarp();
+			const bool need = (!((ra.z >> 24) & B2_DBK_OFF) && (ra.x | ra.y)) || (!((rb.z >> 24) & B2_DBK_OFF) && (rb.x | rb.y));
 			unsigned todo = __ballot_sync(0xffffffffu, need);
 			int done_to = x0;                  // macroblocks < done_to are final
-			deblock_chunk2(jobA, jobB, validB, s_tb, s_tile[warp], mby, x0, todo, lane, sy, done_to);
+			deblock_chunk2(jobA, jobB, validB, s_tb, s_tile[warp], sg, mby, x0, todo, lane, sy, done_to);
 			const int end = min(x0 + 32, mb_w);
 			if (done_to < end) sy.publish(end, lane);
 		}
@@ -1876,7 +1944,7 @@ h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, i
 				if (((a >> lane) & 1) && nx >= 0 && nx < mb_w && ny >= 0) {
 					const int nb = ny * mb_w + nx;
 					if (job.mbs[nb].type != B2_H4_INTER)
-						while (!ld_acquire(flags + nb)) __nanosleep(32);
+						spin_until(flags + nb, 1);
 				}
 			}
 			__syncwarp();
