@@ -31,7 +31,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 STREAMGEN = os.path.join(ROOT, "tools", "_bin", "streamgen")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "h264dec")
-METRIC = "1080p frames/sec (H.264 Baseline CAVLC I/P, bit-exact MD5 vs reference)"
+E2EBENCH = os.path.join(ROOT, "tools", "_bin", "e2ebench")
+# `value` and `e2e` are the same unit on the same streams, measured at two places (the docstring above): the name says so
+METRIC = ("1080p frames/sec/GPU, H.264 Baseline CAVLC I/P, every frame bit-exact (MD5) vs the reference decoder -- "
+          "value: reconstruction (pictures pre-parsed, records resident in HBM; parse, H2D and D2H excluded); "
+          "e2e: elementary stream in host memory to frames in host memory through m2d_func_table_t")
 UNIT = "frames/s"
 MBW, MBH = 120, 68                      # 1920x1088 coded, 1920x1080 displayed
 FRAME_BYTES = MBW * 16 * MBH * 16 * 3 // 2
@@ -357,22 +361,58 @@ def main():
         for t in ths:
             t.join()
 
-    run_pool(check=True)   # warm-up (untimed): CUDA context, buffer cache; output MD5-checked against the reference
-    run_pool()             # second warm-up pass in the timed configuration (no MD5 on the worker threads)
-    barrier()
-    e2e_frames = 0
-    t0 = time.perf_counter()
-    for _ in range(a.e2e_reps):
-        t_rep = time.perf_counter()
-        run_pool()
-        e2e_frames += sum(frames_out)
-        sys.stderr.write("e2e repetition: %d frames in %.3f s\n" % (sum(frames_out), time.perf_counter() - t_rep))
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    run_pool(check=True)   # the Python host (m2dec_b200.M2Decoder): untimed, every frame MD5-checked against the reference
+    e2e_host = "m2dec_b200.M2Decoder (Python threads)"
+    native = os.path.exists(E2EBENCH) and not os.environ.get("B2_BENCH_PYTHON_E2E")
+    if native:
+        # The timed host is native (tools/e2ebench: C++ threads around the same plugin table, as the reference
+        # application is C++): the Python threads cost 20 % of the end-to-end rate at 16 threads.
+        e2e_host = "tools/e2ebench (C++ threads)"
+        with tempfile.TemporaryDirectory() as d:
+            paths = write_streams(streams[:ne], d)
+            # untimed: every frame's MD5 (computed by e2ebench on the frames in host memory) against the reference's lines
+            r = subprocess.run([E2EBENCH, "h264", str(threads_n), "1", str(local), "1"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            if r.returncode != 0:
+                raise SystemExit("bench.py: e2ebench failed: " + r.stderr[-500:])
+            for line in r.stdout.splitlines():
+                f = line.split()
+                if f and f[0] == "stream":
+                    i = int(f[1])
+                    if int(f[2]) != a.frames:
+                        raise SystemExit("bench.py: e2ebench stream %d gave %s frames" % (i, f[2]))
+                    if i in goldens:
+                        if f[3:] != goldens[i]:
+                            raise SystemExit("bench.py: e2ebench MD5 mismatch on stream %d" % i)
+                        e2e_checked[0] += len(goldens[i])
+            barrier()
+            # repetition 0 is the warm-up (CUDA context, page-locked frame buffers, buffer cache)
+            r = subprocess.run([E2EBENCH, "h264", str(threads_n), str(a.e2e_reps + 1), str(local), "0"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            if r.returncode != 0:
+                raise SystemExit("bench.py: e2ebench failed: " + r.stderr[-500:])
+            reps = [float(l.split()[-2]) for l in r.stderr.splitlines() if l.startswith("e2ebench repetition")]
+            assert len(reps) == a.e2e_reps + 1, r.stderr
+            for t_rep in reps[1:]:
+                sys.stderr.write("e2e repetition: %d frames in %.3f s\n" % (ne * a.frames, t_rep))
+            tot = r.stdout.split()
+            e2e_frames = ne * a.frames * a.e2e_reps
+            e2e_s = sum(reps[1:])
+            h2d, d2h = int(tot[tot.index("h2d") + 1]), int(tot[tot.index("d2h") + 1])
+    else:
+        run_pool()             # second warm-up pass in the timed configuration (no MD5 on the worker threads)
+        barrier()
+        e2e_frames = 0
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_reps):
+            t_rep = time.perf_counter()
+            run_pool()
+            e2e_frames += sum(frames_out)
+            sys.stderr.write("e2e repetition: %d frames in %.3f s\n" % (sum(frames_out), time.perf_counter() - t_rep))
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        h2d = sum(c[0] for c in counts)      # bytes of one repetition (= one pass over the e2e streams)
+        d2h = sum(c[1] for c in counts)
     e2e_value = shard.whole_job_rate(e2e_frames, e2e_s, dist, "cuda")
     e2e_s = shard.max_over_ranks(e2e_s, dist, "cuda")
-    h2d = sum(c[0] for c in counts)      # bytes of one repetition (= one pass over the e2e streams)
-    d2h = sum(c[1] for c in counts)
 
     if rank != 0:
         if dist is not None:
@@ -436,6 +476,7 @@ def main():
                    "partitioning": "independent streams per GPU, no collective", "host_prep_s": t_prep},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "streams": ne, "repetitions": a.e2e_reps, "frames": e2e_frames, "md5_checked_frames": e2e_checked[0], "host_threads": threads_n, "seconds": e2e_s,
+                "host": e2e_host,
                 "path": "m2d_func_table_t (h264d_gpu_func): host ES -> parse -> H2D SoA -> kernels -> D2H every output frame"},
         "gpu_launches": int(st.launches) * a.steps,
         "roofline": roofline,

@@ -199,6 +199,10 @@ void b2_cache_trim(void);
 /* Asynchronous: copies the picture's SoA into pinned staging, enqueues H2D + kernels.     */
 int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *pic);
 int b2_session_submit_h264(b2_session *s, const b2_h264_picture *pic);
+/* Every submitted picture goes through b2_*_picture_check (about 0.2 ms of host time for a 1080p picture).  A
+ * producer whose records are sound by construction may switch it off: the library's own front ends do (their
+ * records are checked by tests/ on every test stream and under fuzzing; B2_CHECK_RECORDS=1 keeps it on).        */
+int b2_session_set_record_check(b2_session *s, int on);
 /* Tell the session where the application keeps frame `idx` (the m2d_frame_t of set_frames,  */
 /* reference m2d.h:66-75).  When these buffers are page-locked (b2_host_alloc below, or the    */
 /* application's own cudaHostAlloc / cudaHostRegister) every picture is copied out as soon as  */

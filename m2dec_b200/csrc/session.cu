@@ -25,6 +25,27 @@ using namespace b2;
 
 enum { NSLOT = 4 };
 
+// B2_TRACE=1: where the calling (parsing) thread's time goes inside this file, per session, printed at destroy.
+// Development aid for the end-to-end path (every microsecond here is taken from the parse).
+#include <chrono>
+namespace {
+const bool g_trace = getenv("B2_TRACE") != nullptr;
+enum { T_CHECK, T_SLOT, T_PACK, T_H2D, T_LAUNCH, T_EVENTS, T_D2H_QUEUE, T_FETCH_WAIT, T_CREATE, T_N };
+const char *const g_trace_names[T_N] = {"record check", "slot wait", "pack SoA", "H2D enqueue", "kernel launches", "event records", "D2H enqueue", "frame wait", "session create (per picture)"};
+struct Trace {
+	double us[T_N] = {0};
+	uint64_t pictures = 0;
+	std::chrono::steady_clock::time_point t;
+	inline void begin() { if (g_trace) t = std::chrono::steady_clock::now(); }
+	inline void lap(int k) {
+		if (!g_trace) return;
+		auto n = std::chrono::steady_clock::now();
+		us[k] += std::chrono::duration<double, std::micro>(n - t).count();
+		t = n;
+	}
+};
+}  // namespace
+
 // Process-wide free lists: cudaMalloc / cudaMallocHost / cudaFree synchronise the whole device, so a
 // server that opens and closes streams all the time must not call them per stream.
 namespace {
@@ -116,6 +137,8 @@ struct b2_session {
 	int next_slot;
 	uint64_t launches;
 	uint64_t h2d_bytes, d2h_bytes;
+	bool check_records;             // run b2_*_picture_check on every submitted picture (default)
+	Trace trace;
 };
 
 extern "C" const char *b2_last_error(void) { return b2::g_err; }
@@ -167,18 +190,27 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	s->height = height;
 	s->nframes = nframes;
 	s->frame_bytes = (size_t)width * height * 3 / 2;
+	s->check_records = true;
 	// a failure anywhere below releases what was obtained so far (b2_session_destroy copes with a partly built
 	// session: everything is zero until it is created)
+	s->trace.begin();
 	if (session_build(s) < 0) {
 		b2_session_destroy(s);
 		return -1;
 	}
+	s->trace.lap(T_CREATE);
 	*out = s;
 	return 0;
 }
 
 extern "C" void b2_session_destroy(b2_session *s) {
 	if (!s) return;
+	if (g_trace && s->trace.pictures) {
+		char line[512];
+		int n = snprintf(line, sizeof(line), "m2dec_b200 trace: %llu pictures, us per picture:", (unsigned long long)s->trace.pictures);
+		for (int k = 0; k < T_N; ++k) n += snprintf(line + n, sizeof(line) - n, " %s %.1f,", g_trace_names[k], s->trace.us[k] / s->trace.pictures);
+		fprintf(stderr, "%s\n", line);
+	}
 	cudaSetDevice(s->dev);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (int i = 0; i < NSLOT; ++i) {
@@ -227,6 +259,26 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Records into the page-locked staging slot with non-temporal stores: the slot is read by the copy engine only,
+// so the 2 MB of a picture neither wait for the slot's old lines to be fetched (read-for-ownership) nor push the
+// parse's working set out of the core's caches.  dst is 16-byte aligned (slot offsets are multiples of 256).
+#include <emmintrin.h>
+static void stream_copy(void *dst, const void *src, size_t n) {
+	uint8_t *d = (uint8_t *)dst;
+	const uint8_t *s = (const uint8_t *)src;
+	if (((uintptr_t)d & 15) == 0) {
+		for (; n >= 64; n -= 64, d += 64, s += 64) {
+			const __m128i a = _mm_loadu_si128((const __m128i *)s), b = _mm_loadu_si128((const __m128i *)(s + 16));
+			const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+			_mm_stream_si128((__m128i *)d, a);
+			_mm_stream_si128((__m128i *)(d + 16), b);
+			_mm_stream_si128((__m128i *)(d + 32), c);
+			_mm_stream_si128((__m128i *)(d + 48), e);
+		}
+	}
+	if (n) memcpy(d, s, n);
+}
 
 extern "C" int b2_session_bind_host_frame(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma) {
 	if (!s || (unsigned)idx >= (unsigned)s->nframes) return -1;
@@ -299,7 +351,7 @@ extern "C" int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *p) {
 		set_error("picture %dx%d MB does not match session %dx%d", p->mb_w, p->mb_h, s->width, s->height);
 		return -1;
 	}
-	if (b2_mpeg2_picture_check(p, s->nframes) < 0) return -1;
+	if (s->check_records && b2_mpeg2_picture_check(p, s->nframes) < 0) return -1;
 	B2_CUDA_OK(cudaSetDevice(s->dev));
 	size_t off_mbs = align_up(sizeof(M2Job), 256);
 	size_t off_coef = align_up(off_mbs + sizeof(b2_m2_mb) * p->n_mbs, 256);
@@ -339,7 +391,9 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 		set_error("picture %dx%d MB does not match session %dx%d", p->mb_w, p->mb_h, s->width, s->height);
 		return -1;
 	}
-	if (b2_h264_picture_check(p, s->nframes) < 0) return -1;
+	s->trace.begin();
+	if (s->check_records && b2_h264_picture_check(p, s->nframes) < 0) return -1;
+	s->trace.lap(T_CHECK);
 	B2_CUDA_OK(cudaSetDevice(s->dev));
 	size_t off_mbs = align_up(sizeof(H4Job), 256);
 	size_t off_dbk = align_up(off_mbs + sizeof(b2_h264_mb) * p->n_mbs, 256);
@@ -349,6 +403,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	size_t total = off_items + (size_t)p->n_items * 4;
 	StageSlot *sl;
 	if (acquire_slot(s, total, &sl) < 0) return -1;
+	s->trace.lap(T_SLOT);
 	H4Job job;
 	memset(&job, 0, sizeof(job));
 	job.frames = s->frames;
@@ -365,22 +420,36 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	job.n_items = p->n_items;
 	job.n_first = p->n_items_first;
 	memcpy(sl->host, &job, sizeof(job));
-	memcpy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
-	memcpy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
-	if (p->n_mcs) memcpy(sl->host + off_mcs, p->mcs, sizeof(b2_h264_mc) * p->n_mcs);
-	if (p->n_coef_recs) memcpy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
-	if (p->n_items) memcpy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
+	stream_copy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
+	stream_copy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
+	if (p->n_mcs) stream_copy(sl->host + off_mcs, p->mcs, sizeof(b2_h264_mc) * p->n_mcs);
+	if (p->n_coef_recs) stream_copy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
+	if (p->n_items) stream_copy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
+	_mm_sfence();                 // the streamed stores are globally visible before the copy engine is told to read
+	s->trace.lap(T_PACK);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
 	if (before_write(s, p->dst) < 0) return -1;
+	s->trace.lap(T_H2D);
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_items,
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
 	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first) < 0) return -1;
+	s->trace.lap(T_LAUNCH);
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
 	s->frame_written[p->dst] = true;
 	sl->pending = true;
-	return after_write(s, p->dst);
+	s->trace.lap(T_EVENTS);
+	const int rc = after_write(s, p->dst);
+	s->trace.lap(T_D2H_QUEUE);
+	s->trace.pictures++;
+	return rc;
+}
+
+extern "C" int b2_session_set_record_check(b2_session *s, int on) {
+	if (!s) return -1;
+	s->check_records = on != 0;
+	return 0;
 }
 
 extern "C" int b2_session_sync(b2_session *s) {
@@ -397,7 +466,13 @@ extern "C" int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_
 	const uint8_t *src = s->frames + s->frame_bytes * idx;
 	if (s->eager[idx] && luma == s->host_luma[idx] && chroma == s->host_chroma[idx]) {
 		// already on its way (or there) since the picture was queued
-		B2_CUDA_OK(cudaEventSynchronize(s->copy_done[idx]));
+		s->trace.begin();
+		// (the copy usually finished pictures ago: ask before going to sleep on the event)
+		if (cudaEventQuery(s->copy_done[idx]) != cudaSuccess) {
+			cudaGetLastError();
+			B2_CUDA_OK(cudaEventSynchronize(s->copy_done[idx]));
+		}
+		s->trace.lap(T_FETCH_WAIT);
 		return 0;
 	}
 	// wait for the picture that last wrote this frame only, not for pictures queued behind it:
