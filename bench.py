@@ -265,13 +265,17 @@ def main():
             run_reference_cli(paths, min(ncores, nver), md5=True)
             verify_kind = "compiled reference (oracle/_ref/h264dec -O), hashed on the device (b2_replay_md5)"
             import hashlib
+            # every picture of the verified lanes hashed on the device in one launch (b2_replay_md5: 16 bytes per picture
+            # come back); the first two lanes are also downloaded and hashed on the host, which checks the device MD5 itself
+            all_got = rp.md5([(lane, idx) for lane in range(nver) for idx in rp.outputs[lane]], width=1920, height=1080)
+            pos = 0
             for lane in range(nver):
                 golden = open(os.path.join(d, "s%03d.out" % lane), "rb").read().split()
-                assert len(golden) == a.frames, (len(golden), a.frames)
+                if len(golden) != a.frames:
+                    raise SystemExit("bench.py: the reference decoded %d of %d frames of lane %d" % (len(golden), a.frames, lane))
                 goldens[lane] = [g.decode() for g in golden]
-                # every picture of the lane hashed on the device (b2_replay_md5: 16 bytes per picture come back);
-                # the first two lanes are also downloaded and hashed on the host, which checks the device MD5 itself
-                got = rp.md5([(lane, idx) for idx in rp.outputs[lane]], width=1920, height=1080)
+                got = all_got[pos:pos + len(rp.outputs[lane])]
+                pos += len(rp.outputs[lane])
                 if [g.encode() for g in got] != golden:
                     raise SystemExit("bench.py: MD5 mismatch in lane %d" % lane)
                 for t, idx in enumerate(rp.outputs[lane] if lane < 2 else []):
@@ -431,7 +435,7 @@ def main():
     # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture,
     # scaled to this run's pictures per launch
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")       # written by tools/summarize_ncu.py
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")       # written by tools/summarize_ncu.py from the round's ncu --set full capture
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         per_launch = tj["dram_bytes_per_launch"].get(phase[dom])

@@ -84,6 +84,46 @@ struct Stream {
 	uint64_t stats[3] = {0, 0, 0};      // bytes host -> device, device -> host, kernel launches (of the last decode)
 };
 
+#ifdef E2EBENCH_SAMPLE
+// SIGPROF sampler (no perf in the image): program counters + /proc/self/maps to e2e_pcs.txt / e2e_maps.txt;
+// tools/e2ebench/report.py buckets them by mapping and, inside libm2dec_b200.so, by function
+#include <signal.h>
+#include <sys/time.h>
+#include <ucontext.h>
+static uint64_t g_pcs[1 << 21];
+static std::atomic<int> g_npcs(0);
+static void on_prof(int, siginfo_t *, void *uc) {
+	int i = g_npcs.fetch_add(1);
+	if (i < (1 << 21)) g_pcs[i] = (uint64_t)((ucontext_t *)uc)->uc_mcontext.gregs[REG_RIP];
+}
+static void sample_start() {
+	struct sigaction sa;
+	memset(&sa, 0, sizeof(sa));
+	sa.sa_sigaction = on_prof;
+	sa.sa_flags = SA_SIGINFO | SA_RESTART;
+	sigaction(SIGPROF, &sa, nullptr);
+	struct itimerval tv = {{0, 1000}, {0, 1000}};
+	setitimer(ITIMER_PROF, &tv, nullptr);
+}
+static void sample_stop() {
+	struct itimerval tv = {{0, 0}, {0, 0}};
+	setitimer(ITIMER_PROF, &tv, nullptr);
+	FILE *f = fopen("e2e_pcs.txt", "w");
+	int n = g_npcs.load();
+	if (n > (1 << 21)) n = 1 << 21;
+	for (int i = 0; i < n; ++i) fprintf(f, "%llx\n", (unsigned long long)g_pcs[i]);
+	fclose(f);
+	FILE *m = fopen("/proc/self/maps", "r"), *o = fopen("e2e_maps.txt", "w");
+	char line[1024];
+	while (fgets(line, sizeof(line), m)) fputs(line, o);
+	fclose(m);
+	fclose(o);
+}
+#else
+static void sample_start() {}
+static void sample_stop() {}
+#endif
+
 struct FramePool {          // the application's frame buffers of one thread, reused from stream to stream
 	uint8_t *block = nullptr;
 	size_t bytes = 0;
@@ -213,6 +253,7 @@ int main(int argc, char **argv) {
 	std::atomic<bool> ok(true);
 	double seconds = 0;
 	for (int rep = 0; rep < reps; ++rep) {
+		if (rep == 1) sample_start();       // (repetition 0 is the warm-up)
 		std::atomic<int> next(0);
 		auto t0 = std::chrono::steady_clock::now();
 		std::vector<std::thread> ths;
@@ -237,6 +278,7 @@ int main(int argc, char **argv) {
 		fprintf(stderr, "e2ebench repetition %d: %.3f s\n", rep, dt);
 		seconds += dt;
 	}
+	sample_stop();
 	if (!ok) { fprintf(stderr, "e2ebench: a stream failed: %s\n", b2_last_error()); return 4; }
 	uint64_t tot[3] = {0, 0, 0};
 	for (const Stream &st : streams)

@@ -24,7 +24,7 @@ KEEP = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
 
 
 def short(name):
-    m = re.search(r"(h264_\w+|mpeg2_\w+)(<[^>]*>)?", name)
+    m = re.search(r"(h264_\w+|mpeg2_\w+|md5_\w+)(<[^>]*>)?", name)
     return (m.group(1) + (m.group(2) or "")) if m else name
 
 
@@ -82,7 +82,8 @@ def launch(path, out_txt):
     lines = ["kernel                                 grid             launches     total ms     avg us    share of the replay launches"]
     for (k, g), v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         replay = is_replay(k, g)
-        lines.append("%-38s %-16s %8d %12.3f %10.1f %8s" % (k, g, v[0], v[1], 1000 * v[1] / v[0], ("%.1f%%" % (100 * v[1] / big)) if replay else "e2e"))
+        label = ("%.1f%%" % (100 * v[1] / big)) if replay else ("verification (untimed)" if "md5" in k else "e2e")
+        lines.append("%-38s %-16s %8d %12.3f %10.1f %8s" % (k[:38], g, v[0], v[1], 1000 * v[1] / v[0], label))
     open(out_txt, "w").write("\n".join(lines) + "\n")
 
 
