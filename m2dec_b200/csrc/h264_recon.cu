@@ -879,8 +879,30 @@ __device__ int pred8x8_sample(const IntraTile &tl, int mode, int avail, int x, i
 #undef PL
 }
 
-// Reconstruct one intra macroblock with one warp.  Pixels produced by other warps (rows above)
-// are read through L2 (__ldcg) and results are written through to L2 (__stcg): the wavefront
+// The residual of an intra macroblock (every coded 4x4 / 8x8 block dequantised and transformed into tl.res, one
+// block per lane).  It needs nothing from the neighbours, so the kernels run it BEFORE they wait for the
+// macroblocks this one predicts from: the coefficient loads and the transforms are off the dependency chain
+// between neighbouring intra macroblocks.
+__device__ void intra_residual(const H4Job &job, const b2_h264_mb &m, IntraTile &tl, int lane) {
+	if (m.type == B2_H4_IPCM) return;
+	if (lane == 0) tl.has = 0;
+	__syncwarp();
+	if (m.flags & B2_H4_T8x8) {
+		if (lane < 4) {
+			if ((m.nz >> (1 + 4 * lane)) & 1) {
+				block_residual8x8(job, m, lane, tl.res);
+				atomicOr(&tl.has, 0xfu << (4 * lane));
+			}
+		} else if (lane >= 16 && lane < 24) {
+			if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
+		}
+	} else if (lane < 24) {
+		if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
+	}
+}
+
+// Reconstruct one intra macroblock with one warp (intra_residual has run).  Pixels produced by other warps
+// (rows above) are read through L2 (__ldcg) and results are written through to L2 (__stcg): the wavefront
 // kernel orders warps with progress flags, and L1 is not coherent between SMs.
 __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby, IntraTile &tl, int lane) {
 	const int W = job.mb_w * 16, H = job.mb_h * 16;
@@ -920,20 +942,6 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 	if (lane < 16) {            // chroma left: rows 0..7, two components
 		int row = lane >> 1, comp = lane & 1;
 		tl.c[comp][1 + row][0] = ((a & 1) && mbx > 0) ? __ldcg(pc + (size_t)row * W - 2 + comp) : 128;
-	}
-	if (lane == 0) tl.has = 0;
-	__syncwarp();
-	if (m.flags & B2_H4_T8x8) {
-		if (lane < 4) {
-			if ((m.nz >> (1 + 4 * lane)) & 1) {
-				block_residual8x8(job, m, lane, tl.res);
-				atomicOr(&tl.has, 0xfu << (4 * lane));
-			}
-		} else if (lane >= 16 && lane < 24) {
-			if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
-		}
-	} else if (lane < 24) {
-		if (block_residual(job, m, lane, tl.res[lane])) atomicOr(&tl.has, 1u << lane);
 	}
 	__syncwarp();
 
@@ -1122,11 +1130,17 @@ __device__ __forceinline__ void fence_acquire() {
 	asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
 }
+#ifndef B2_GL_SPIN_NS
+#define B2_GL_SPIN_NS 32
+#endif
+#ifndef B2_SM_SPIN_NS
+#define B2_SM_SPIN_NS 64
+#endif
 // wait until *p >= want; returns the value seen
 __device__ __forceinline__ int spin_until(const int *p, int want) {
 	int v;
 #if B2_SPIN_RELAXED
-	while ((v = ld_relaxed(p)) < want) __nanosleep(32);
+	while ((v = ld_relaxed(p)) < want) __nanosleep(B2_GL_SPIN_NS);
 	fence_acquire();
 #else
 	while ((v = ld_acquire(p)) < want) __nanosleep(32);
@@ -1143,19 +1157,28 @@ struct RowSync {
 	volatile int *sm_my;
 	int *gl_my;               // null: no other CTA reads this row's progress
 	int seen;                 // progress of the row above known so far
+	// Experiment knob (B2_DBK2_LEAD, default 0 = off): a row that has to wait resumes only once the row above is
+	// `lead` macroblocks further (or complete, `limit` = macroblocks per row), so that rows running at the same speed
+	// stay apart and stop polling right behind their producer.  Measured on B200 (256 lanes): every lead costs
+	// throughput (packed deblocking 660 GB/s at 0, 577 at 4, 427 at 8, 296 at 16): a launch is one wave of all its
+	// pictures, ~18 resident rows per picture pair, and each macroblock of extra distance is paid 68 times per
+	// picture as rows that have not started yet.
+	int lead, limit;
 
 	__device__ __forceinline__ void wait(int want, int lane) {
 #ifdef B2_DBK_NOWAIT      // timing experiment only (wrong pixels): what the kernels cost without the dependencies
 		return;
 #endif
 		if (seen >= want) return;
+		const int target = min(want + lead, limit);
 		if (sm_above) {
 			if (lane == 0) {
-				while ((seen = *sm_above) < want) { }
+				if (lead) { while ((seen = *sm_above) < target) __nanosleep(B2_SM_SPIN_NS); }
+				else { while ((seen = *sm_above) < target) { } }
 				__threadfence_block();
 			}
 		} else if (gl_above) {
-			if (lane == 0) seen = spin_until(gl_above, want);
+			if (lane == 0) seen = spin_until(gl_above, target);
 		} else {
 			seen = 1 << 30;
 		}
@@ -1451,6 +1474,8 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 		sy.sm_my = &s_prog[warp];
 		sy.gl_my = (warp == WAVE_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
 		sy.seen = 0;
+		sy.lead = 0;
+		sy.limit = mb_w;
 		const H4Job job = jobs[j];
 		if (PHASE == 1 && h264_intra_sparse(job.n_intra, mb_w * mb_h)) continue;     // h264_intra_sparse_kernel's
 		for (int x0 = 0; x0 < mb_w; x0 += 32) {
@@ -1475,8 +1500,9 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 				todo &= todo - 1;
 				int x = x0 + k;
 				if (x > done_to) sy.publish(x, lane);     // the stretch that needed nothing
-				if (mby > 0) sy.wait(min(x + 2, mb_w), lane);
 				const b2_h264_mb m = job.mbs[(size_t)mby * mb_w + x];
+				intra_residual(job, m, s_tile[warp].intra, lane);
+				if (mby > 0) sy.wait(min(x + 2, mb_w), lane);
 				intra_mb(job, m, x, mby, s_tile[warp].intra, lane);
 				done_to = x + 1;
 				sy.publish(done_to, lane);
@@ -1504,6 +1530,10 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 #ifndef B2_DBK2_PUBLISH_EVERY
 #define B2_DBK2_PUBLISH_EVERY 2
 #endif
+// how far a row that had to wait lets the row above get ahead before it resumes (RowSync::lead)
+#ifndef B2_DBK2_LEAD
+#define B2_DBK2_LEAD 0
+#endif
 struct alignas(16) DbkTile2 {
 	// one packed pair per sample; rows -4..15 at r + 4, columns -4..15 at c + 4.  Pitch 28 words: rows are 16-byte
 	// aligned (whole lines move as 128-bit accesses) and eight consecutive rows start in eight different bank groups
@@ -1522,6 +1552,7 @@ struct alignas(16) DbkStage2 {
 	uint32_t qp_top[2][32];     // word 2 (QPs, flags) of the record above
 	uint4 own[2][2][24];        // [slot][picture][line: luma 0..15, chroma 16..23]: 16 bytes of the line
 };
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -1875,6 +1906,8 @@ h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int m
 		sy.sm_my = &s_prog[warp];
 		sy.gl_my = (warp == DBK2_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
 		sy.seen = 0;
+		sy.lead = B2_DBK2_LEAD;
+		sy.limit = mb_w;
 		const bool validB = 2 * j + 1 < n_jobs;
 		const H4Job jobA = jobs[2 * j], jobB = jobs[validB ? 2 * j + 1 : 2 * j];
 		for (int x0 = 0; x0 < mb_w; x0 += 32) {
@@ -1937,6 +1970,7 @@ h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, i
 			todo &= todo - 1;
 			const int m = c * 32 + k, mbx = m % mb_w, mby = m / mb_w;
 			const b2_h264_mb hdr = job.mbs[m];
+			intra_residual(job, hdr, s_tile[warp], lane);
 			if (lane < 4) {
 				// neighbour of lane: 0 left, 1 top, 2 top-right, 3 top-left (the availability bit order)
 				const int a = hdr.intra_avail | hdr.intra_avail_c;
