@@ -60,24 +60,81 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML from a thread of this
+    process (a sample every 20 ms; begin() / end() mark the timed region, samples outside it are dropped) -- an
+    `nvidia-smi -lms` child needs the better part of a second to come up, more than a short timed region lasts;
+    it remains the fallback where the NVML binding is not usable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.path = gpu, None, None
+        self.thread, self.stop_flag, self.samples, self.t0, self.t1 = None, False, [], None, None
+        self.how = None
+
+    def _nvml_loop(self, nv, h):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons_fn(h))))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    idx = int(ids[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.max_sm = nv, float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            import threading
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             f = tempfile.NamedTemporaryFile(delete=False, suffix=".csv")
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30)]
+            names = [("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap")]
+            reasons = set()
+            for _, _, r in inside:
+                for n, suffix in names:
+                    bit = getattr(nv, "nvmlClocksEventReason" + suffix, None) or getattr(nv, "nvmlClocksThrottleReason" + suffix, 0)
+                    if r & bit:
+                        reasons.add(n)
+            if inside:
+                out = {"sm_mhz": statistics.median([x[1] for x in inside]), "sm_max_mhz": self.max_sm, "reasons": sorted(reasons),
+                       "samples": len(inside), "source": "nvml, every 20 ms inside the timed region"}
+            return out
         if not self.proc:
             return out
         self.proc.terminate()
@@ -101,7 +158,8 @@ class ClockSampler:
                     reasons.add(n)
         os.unlink(self.path)
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "source": "nvidia-smi -lms 100 (started before the warm-up)"}
         return out
 
 
@@ -294,19 +352,21 @@ def main():
         rp.sync()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        rp.run()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        rp.run()
+    barrier()
     kernel_ms = [0.0, 0.0, 0.0]
+    sampler.begin()
     rp.mark(0)
     for _ in range(a.steps):
         rp.run(timed=True)
     rp.mark(1)
     rp.sync()
     barrier()
+    sampler.end()
     total_ms = rp.elapsed_ms()
     st = rp.stats()
     clocks = sampler.stop() if rank == 0 else None
@@ -365,6 +425,7 @@ def main():
         for t in ths:
             t.join()
 
+    e2e_digest = None
     run_pool(check=True)   # the Python host (m2dec_b200.M2Decoder): untimed, every frame MD5-checked against the reference
     e2e_host = "m2dec_b200.M2Decoder (Python threads)"
     native = os.path.exists(E2EBENCH) and not os.environ.get("B2_BENCH_PYTHON_E2E")
@@ -401,6 +462,26 @@ def main():
             e2e_frames = ne * a.frames * a.e2e_reps
             e2e_s = sum(reps[1:])
             h2d, d2h = int(tot[tot.index("h2d") + 1]), int(tot[tot.index("d2h") + 1])
+            # Digest mode (SURVEY 8f rank 1 behind the plugin table, what `h264dec -O` produces): frames hashed on the
+            # device, 16 bytes per frame come back.  Same streams and threads; every digest of the verified streams is
+            # compared with the reference's line.  Reported next to e2e, not instead of it.
+            if world == 1 and not os.environ.get("B2_BENCH_NO_DIGEST"):
+                r = subprocess.run([E2EBENCH, "h264", str(threads_n), str(a.e2e_reps + 1), str(local), "2"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                if r.returncode != 0:
+                    raise SystemExit("bench.py: e2ebench (digest mode) failed: " + r.stderr[-500:])
+                dchecked = 0
+                for line in r.stdout.splitlines():
+                    f = line.split()
+                    if f and f[0] == "stream" and int(f[1]) in goldens:
+                        if f[3:] != goldens[int(f[1])]:
+                            raise SystemExit("bench.py: device MD5 mismatch on stream %s (digest mode)" % f[1])
+                        dchecked += len(f) - 3
+                dreps = [float(l.split()[-2]) for l in r.stderr.splitlines() if l.startswith("e2ebench repetition")]
+                dtot = r.stdout.split()
+                e2e_digest = {"value": ne * a.frames * a.e2e_reps / sum(dreps[1:]), "unit": UNIT,
+                              "h2d_bytes_per_step": int(dtot[dtot.index("h2d") + 1]), "d2h_bytes_per_step": int(dtot[dtot.index("d2h") + 1]),
+                              "md5_checked_frames": dchecked,
+                              "path": "m2d_func_table_t + b2_context_set_md5 / b2_context_frame_md5: host ES -> parse -> H2D SoA -> kernels -> MD5 of the cropped frame on the device -> 16 bytes D2H per frame"}
     else:
         run_pool()             # second warm-up pass in the timed configuration (no MD5 on the worker threads)
         barrier()
@@ -487,6 +568,8 @@ def main():
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
+    if e2e_digest is not None:
+        out["e2e_device_md5"] = e2e_digest
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     if dist is not None:

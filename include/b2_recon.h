@@ -14,6 +14,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include "m2d_plugin.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -182,6 +183,15 @@ int b2_context_set_tap(void *ctx, b2_picture_tap tap, void *arg, int device_off)
 int b2_context_set_device(void *ctx, int cuda_device);
 /* Release device resources held by a context (the reference API has no destroy hook).     */
 int b2_context_release(void *ctx);
+/* Digest mode behind the plugin table (b2_session_set_md5 above): call after init(), before the first       */
+/* decode_picture().  peek / get_decoded_frame then return frames whose host buffers are NOT filled;         */
+/* b2_context_frame_md5() returns the MD5 the reference's `-O` writer would print for that frame (window and */
+/* pitch taken from the stream's headers exactly as the front end fills m2d_frame_t).  The digest of a frame */
+/* stays valid until the decoder reuses the frame buffer, as the pixels do in the reference; handing         */
+/* set_frames() a few frames more than get_info() asks for lets the application collect digests a few        */
+/* pictures late without ever waiting for a hash.                                           */
+int b2_context_set_md5(void *ctx, int on);
+int b2_context_frame_md5(void *ctx, const m2d_frame_t *frame, uint8_t digest[16]);
 
 /* ------------------------------------------------------------------------------------ */
 /* Device side.  A session owns one CUDA stream, a pool of device-resident NV12 frames    */
@@ -219,6 +229,17 @@ void b2_host_free(void *p);
 /* pictures queued behind it) and copies it out unless it was bound and is there already.   */
 int b2_session_download(b2_session *s, int idx, uint8_t *luma, uint8_t *chroma);
 int b2_session_upload(b2_session *s, int idx, const uint8_t *luma, const uint8_t *chroma);
+/* Digest mode: what the reference application's MD5 writer computes per output frame  */
+/* (`h264dec -O`: src/app/filewrite.h:91-124 FileWriterMd5::writeframe over write_cropping, src/app/md5.c)   */
+/* is computed on the device instead -- the cropped luma rows, then the cropped rows of the interleaved CbCr */
+/* plane, both addressed with row pitch `stride` (the application's m2d_frame_t.width).  While it is on,     */
+/* every submitted picture is hashed behind its kernels and only the 16-byte digest is copied to the host;   */
+/* frames are no longer copied into the bound host buffers.  A frame is not overwritten by a later picture   */
+/* before its hash has read it.  b2_session_md5() waits for the digest of the picture last decoded into      */
+/* frame `idx` (a hash of a 1080p frame takes ~30 ms -- MD5 is one serial chain -- so an application that    */
+/* wants throughput asks for a frame's digest a few pictures after the frame came out).                      */
+int b2_session_set_md5(b2_session *s, int on, int stride, int crop_left, int crop_top, int width, int height);
+int b2_session_md5(b2_session *s, int idx, uint8_t digest[16]);
 int b2_session_sync(b2_session *s);
 /* Number of kernel launches issued by this session so far.                                */
 uint64_t b2_session_launches(const b2_session *s);

@@ -5,7 +5,8 @@
 
 namespace b2 {
 
-Backend::Backend() : tap_(nullptr), tap_arg_(nullptr), device_off_(false), dead_(false), cuda_device_(0), sess_(nullptr), codec_(0), width_(0), height_(0), nframes_(0), n_host_(0) {
+Backend::Backend() : tap_(nullptr), tap_arg_(nullptr), device_off_(false), dead_(false), cuda_device_(0), sess_(nullptr), codec_(0), width_(0), height_(0), nframes_(0), n_host_(0),
+                     md5_(false), md5_stride_(0), md5_left_(0), md5_top_(0), md5_w_(0), md5_h_(0) {
 	const char *e = getenv("B2_CUDA_DEVICE");
 	if (e) cuda_device_ = atoi(e);
 }
@@ -33,6 +34,12 @@ int Backend::configure(int codec, int width, int height, int nframes) {
 	static const bool keep_check = getenv("B2_CHECK_RECORDS") != nullptr;
 	if (!keep_check) b2_session_set_record_check(sess_, 0);
 	for (int i = 0; i < n_host_ && i < nframes; ++i) b2_session_bind_host_frame(sess_, i, host_luma_[i], host_chroma_[i]);
+	if (md5_ && b2_session_set_md5(sess_, 1, md5_stride_, md5_left_, md5_top_, md5_w_, md5_h_) < 0) {
+		fprintf(stderr, "m2dec_b200: digest mode: %s\n", b2_last_error());
+		release();
+		dead_ = true;
+		return -1;
+	}
 	return err;
 }
 
@@ -48,8 +55,15 @@ int Backend::submit(int codec, const void *picture) {
 	return r;
 }
 
+int Backend::frame_md5(const m2d_frame_t *frame, uint8_t digest[16]) {
+	if (!frame || !digest || !sess_ || !md5_) return -1;
+	for (int i = 0; i < n_host_; ++i)
+		if (host_luma_[i] == frame->luma) return b2_session_md5(sess_, i, digest);
+	return -1;
+}
+
 int Backend::fetch(int idx, uint8_t *luma, uint8_t *chroma) {
-	if (device_off_) return 0;
+	if (device_off_ || md5_) return 0;
 	if (!sess_) return -1;
 	int r = b2_session_download(sess_, idx, luma, chroma);
 	if (r < 0) fprintf(stderr, "m2dec_b200: frame download failed: %s\n", b2_last_error());

@@ -56,6 +56,8 @@ int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, 
 // md5.cu: MD5 of a cropped window of n frames (one thread per frame); d_slots / d_out are device pointers
 int md5_pictures(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, const int *d_slots, int n, int stride, int rows, int left, int top, int w, int h,
                  uint8_t *d_out);
+// the same for one frame whose planes the application addresses with row pitch `stride` (m2d_frame_t.width)
+int md5_frame(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, int slot, int stride, size_t plane_bytes, int left, int top, int w, int h, uint8_t *d_out);
 
 __device__ __forceinline__ int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 

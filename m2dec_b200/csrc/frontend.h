@@ -29,6 +29,13 @@ public:
 	~Backend();
 	void set_tap(b2_picture_tap tap, void *arg, int device_off) { tap_ = tap; tap_arg_ = arg; device_off_ = device_off != 0; }
 	void set_device(int dev) { cuda_device_ = dev; }
+	// digest mode (b2_context_set_md5): frames are hashed on the device, fetch() copies nothing
+	void set_md5(bool on) { md5_ = on; }
+	bool md5() const { return md5_; }
+	// the window and row pitch the application's MD5 writer would use for this stream's frames (the front end knows
+	// them from the sequence header / SPS); must be called before configure()
+	void set_md5_window(int stride, int left, int top, int w, int h) { md5_stride_ = stride; md5_left_ = left; md5_top_ = top; md5_w_ = w; md5_h_ = h; }
+	int frame_md5(const m2d_frame_t *frame, uint8_t digest[16]);
 	// the application's frame buffers (set_frames): frame i of the device pool is copied out to them
 	void bind_frames(const m2d_frame_t *frames, int n) {
 		n_host_ = n < 64 ? n : 64;
@@ -59,6 +66,8 @@ private:
 	int codec_, width_, height_, nframes_;
 	int n_host_;
 	uint8_t *host_luma_[64], *host_chroma_[64];
+	bool md5_;
+	int md5_stride_, md5_left_, md5_top_, md5_w_, md5_h_;
 };
 
 }  // namespace b2

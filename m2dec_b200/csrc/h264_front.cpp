@@ -212,6 +212,8 @@ public:
 		frames_w_ = s.width;     // the application sized its buffers for this SPS (get_info): pictures of any
 		frames_h_ = s.height;    // other size are refused in slice(), they would overrun those buffers
 		backend.bind_frames(frames_, num);
+		// what the application's writer hashes of a frame of this SPS: pitch m2d_frame_t.width, the cropping window
+		backend.set_md5_window(s.width, s.crop[0], s.crop[2], s.width - s.crop[0] - s.crop[1], s.height - s.crop[2] - s.crop[3]);
 		return backend.configure(B2_CODEC_H264, s.width, s.height, num);
 	}
 

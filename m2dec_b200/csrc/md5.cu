@@ -39,7 +39,9 @@ __device__ void md5_block(uint32_t st[4], const uint32_t m[16]) {
 	st[0] += a; st[1] += b; st[2] += c; st[3] += d;
 }
 
-// The message as a byte stream over the two cropped planes.
+// The message as a byte stream over the two cropped planes.  `stride` is the row pitch the APPLICATION reads the planes
+// with (m2d_frame_t.width: the reference's writer, filewrite.h:99-124, addresses both planes with it), `plane` the
+// distance from the luma plane to the CbCr plane.
 struct Cursor {
 	const uint8_t *luma, *chroma;
 	int stride, left, top, w, h;     // window in luma samples; chroma rows: top / 2 .. top / 2 + h / 2 - 1, same byte columns
@@ -56,35 +58,51 @@ struct Cursor {
 	}
 };
 
-__global__ void md5_pictures_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, const int *__restrict__ slots, int n, int stride, int rows, int left, int top,
-                                    int w, int h, uint8_t *__restrict__ out) {
+__global__ void md5_pictures_kernel(const uint8_t *__restrict__ frames, size_t frame_bytes, const int *__restrict__ slots, int slot0, int n, int stride, size_t plane_bytes,
+                                    int left, int top, int w, int h, uint8_t *__restrict__ out) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	Cursor cu;
-	cu.luma = frames + frame_bytes * (size_t)slots[i];
-	cu.chroma = cu.luma + (size_t)stride * rows;
+	cu.luma = frames + frame_bytes * (size_t)(slots ? slots[i] : slot0 + i);
+	cu.chroma = cu.luma + plane_bytes;
 	cu.stride = stride; cu.left = left; cu.top = top; cu.w = w; cu.h = h;
 	cu.plane = 0; cu.row = 0; cu.col = 0;
 	uint32_t st[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
-	const uint64_t total = (uint64_t)w * h * 3 / 2;
-	const bool aligned = (w & 63) == 0 && ((left | stride) & 3) == 0;      // every 64-byte block lies inside one row, word-aligned
+	const uint64_t total = (uint64_t)w * h + (uint64_t)w * (h >> 1);
+	// every 64-byte block lies inside one row, 16-byte aligned: four 128-bit loads per block, and the next block is
+	// asked for before the current one is hashed (the chain of 64 dependent steps hides the load)
+	const bool aligned = (w & 63) == 0 && ((left | stride) & 15) == 0 && (plane_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(cu.luma) & 15) == 0;
 	uint64_t done = 0;
 	uint32_t m[16];
-	for (; done + 64 <= total; done += 64) {
-		if (aligned) {
-			const uint32_t *p = reinterpret_cast<const uint32_t *>(cu.ptr());
+	if (aligned && total >= 64) {
+		uint4 nx[4];
+		{
+			const uint4 *p = reinterpret_cast<const uint4 *>(cu.ptr());
 #pragma unroll
-			for (int k = 0; k < 16; ++k) m[k] = __ldg(p + k);
+			for (int k = 0; k < 4; ++k) nx[k] = __ldg(p + k);
 			cu.advance(64);
-		} else {
+		}
+		for (; done + 64 <= total; done += 64) {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) { m[4 * k] = nx[k].x; m[4 * k + 1] = nx[k].y; m[4 * k + 2] = nx[k].z; m[4 * k + 3] = nx[k].w; }
+			if (done + 128 <= total) {
+				const uint4 *p = reinterpret_cast<const uint4 *>(cu.ptr());
+#pragma unroll
+				for (int k = 0; k < 4; ++k) nx[k] = __ldg(p + k);
+				cu.advance(64);
+			}
+			md5_block(st, m);
+		}
+	} else {
+		for (; done + 64 <= total; done += 64) {
 #pragma unroll
 			for (int k = 0; k < 16; ++k) {
 				uint32_t v = 0;
 				for (int b = 0; b < 4; ++b) { v |= (uint32_t)__ldg(cu.ptr()) << (8 * b); cu.advance(1); }
 				m[k] = v;
 			}
+			md5_block(st, m);
 		}
-		md5_block(st, m);
 	}
 	// tail: the remaining bytes, 0x80, zeros, the length in bits
 	const int rem = (int)(total - done);
@@ -110,7 +128,15 @@ __global__ void md5_pictures_kernel(const uint8_t *__restrict__ frames, size_t f
 int md5_pictures(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, const int *d_slots, int n, int stride, int rows, int left, int top, int w, int h,
                  uint8_t *d_out) {
 	if (n <= 0) return 0;
-	md5_pictures_kernel<<<(n + 31) / 32, 32, 0, stream>>>(frames, frame_bytes, d_slots, n, stride, rows, left, top, w, h, d_out);
+	md5_pictures_kernel<<<(n + 31) / 32, 32, 0, stream>>>(frames, frame_bytes, d_slots, 0, n, stride, (size_t)stride * rows, left, top, w, h, d_out);
+	B2_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+// one frame (index `slot`), its planes addressed as the application does: row pitch `stride`, CbCr plane `plane_bytes`
+// behind the luma plane
+int md5_frame(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, int slot, int stride, size_t plane_bytes, int left, int top, int w, int h, uint8_t *d_out) {
+	md5_pictures_kernel<<<1, 32, 0, stream>>>(frames, frame_bytes, nullptr, slot, 1, stride, plane_bytes, left, top, w, h, d_out);
 	B2_CUDA_OK(cudaGetLastError());
 	return 0;
 }

@@ -118,6 +118,9 @@ public:
 		frames_mb_w_ = mb_w_;    // the application sized its buffers for this geometry (get_info); slices of
 		frames_mb_h_ = mb_h_;    // any other are ignored, their pictures would overrun those buffers
 		backend.bind_frames(frames_, num);
+		// frames go out with width / height of the sequence header and the application's own (zero) crop fields: its
+		// writer reads both planes with pitch `width`
+		backend.set_md5_window(width_, 0, 0, width_, height_);
 		return backend.configure(B2_CODEC_MPEG2, mb_w_ * 16, mb_h_ * 16, num);
 	}
 

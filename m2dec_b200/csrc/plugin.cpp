@@ -31,6 +31,19 @@ extern "C" int b2_context_set_device(void *ctx, int cuda_device) {
 	return 0;
 }
 
+extern "C" int b2_context_set_md5(void *ctx, int on) {
+	b2::Backend *be = b2::backend_of(ctx);
+	if (!be) return -1;
+	be->set_md5(on != 0);
+	return 0;
+}
+
+extern "C" int b2_context_frame_md5(void *ctx, const m2d_frame_t *frame, uint8_t digest[16]) {
+	b2::Backend *be = b2::backend_of(ctx);
+	if (!be) return -1;
+	return be->frame_md5(frame, digest);
+}
+
 extern "C" int b2_context_release(void *ctx) {
 	b2::CtxBlob *b = (b2::CtxBlob *)ctx;
 	if (!b || b->magic != b2::kCtxMagic) return -1;

@@ -138,6 +138,16 @@ struct b2_session {
 	uint64_t launches;
 	uint64_t h2d_bytes, d2h_bytes;
 	bool check_records;             // run b2_*_picture_check on every submitted picture (default)
+	// Digest mode (b2_session_set_md5): every reconstructed picture is hashed on the device (md5.cu), on one of a
+	// few side streams, and only its 16-byte MD5 comes back; the pixels stay in HBM.
+	bool md5_on;
+	int md5_stride, md5_left, md5_top, md5_w, md5_h;
+	cudaStream_t md5_streams[12];   // one hash takes tens of milliseconds (a serial chain): several run side by side
+	size_t md5_dev_alloc, md5_host_alloc;
+	int md5_next;
+	uint8_t *md5_dev, *md5_host;    // [nframes][16]
+	cudaEvent_t md5_done[64];       // digest of frame i is in md5_host
+	bool md5_pending[64];
 	Trace trace;
 };
 
@@ -219,9 +229,15 @@ extern "C" void b2_session_destroy(b2_session *s) {
 		if (s->slots[i].done) cudaEventDestroy(s->slots[i].done);
 	}
 	if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+	for (int i = 0; i < 12; ++i)
+		if (s->md5_streams[i]) { cudaStreamSynchronize(s->md5_streams[i]); cudaStreamDestroy(s->md5_streams[i]); }
+	// (through the free lists: cudaMalloc / cudaFree would wait for every hash in flight on the device)
+	cache_put(s->dev, false, s->md5_dev_alloc, s->md5_dev);
+	cache_put(s->dev, true, s->md5_host_alloc, s->md5_host);
 	for (int i = 0; i < s->nframes; ++i) {
 		if (s->frame_done[i]) cudaEventDestroy(s->frame_done[i]);
 		if (s->copy_done[i]) cudaEventDestroy(s->copy_done[i]);
+		if (s->md5_done[i]) cudaEventDestroy(s->md5_done[i]);
 	}
 	cache_put(s->dev, false, s->frames_alloc, s->frames);
 	cache_put(s->dev, false, s->sync_alloc, s->sync_area);
@@ -315,6 +331,8 @@ extern "C" void b2_host_free(void *p) {
 static int before_write(b2_session *s, int dst) {
 	if (s->eager[dst]) B2_CUDA_OK(cudaStreamWaitEvent(s->stream, s->copy_done[dst], 0));
 	s->eager[dst] = false;
+	// ... nor a hash of the previous content that is still reading it
+	if (s->md5_pending[dst]) B2_CUDA_OK(cudaStreamWaitEvent(s->stream, s->md5_done[dst], 0));
 	return 0;
 }
 
@@ -322,6 +340,20 @@ static int before_write(b2_session *s, int dst) {
 // page-locked.  Pageable buffers are left to b2_session_download: a copy into pageable
 // memory would block the parsing thread here until the kernels are done.
 static int after_write(b2_session *s, int dst) {
+	if (s->md5_on) {
+		// digest mode: hash the frame behind its kernels, bring 16 bytes back; no pixels cross PCIe
+		cudaStream_t ms = s->md5_streams[s->md5_next];
+		s->md5_next = (s->md5_next + 1) % 12;
+		B2_CUDA_OK(cudaStreamWaitEvent(ms, s->frame_done[dst], 0));
+		if (md5_frame(ms, s->frames, s->frame_bytes, dst, s->md5_stride, (size_t)s->width * s->height, s->md5_left, s->md5_top, s->md5_w, s->md5_h,
+		              s->md5_dev + 16 * dst) < 0) return -1;
+		s->launches++;
+		B2_CUDA_OK(cudaMemcpyAsync(s->md5_host + 16 * dst, s->md5_dev + 16 * dst, 16, cudaMemcpyDeviceToHost, ms));
+		B2_CUDA_OK(cudaEventRecord(s->md5_done[dst], ms));
+		s->md5_pending[dst] = true;
+		s->d2h_bytes += 16;
+		return 0;
+	}
 	static const bool off = getenv("B2_NO_EAGER_D2H") != nullptr;
 	if (off || !s->host_luma[dst] || !s->host_chroma[dst]) return 0;
 	const size_t ls = (size_t)s->width * s->height;
@@ -444,6 +476,38 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	s->trace.lap(T_D2H_QUEUE);
 	s->trace.pictures++;
 	return rc;
+}
+
+extern "C" int b2_session_set_md5(b2_session *s, int on, int stride, int crop_left, int crop_top, int width, int height) {
+	if (!s) return -1;
+	if (!on) { s->md5_on = false; return 0; }
+	if (stride <= 0 || crop_left < 0 || crop_top < 0 || width <= 0 || height <= 0 || crop_left + width > stride ||
+	    (size_t)(crop_top + height) * stride > (size_t)s->width * s->height) {
+		set_error("b2_session_set_md5: window %d,%d %dx%d (pitch %d) outside the %dx%d frame", crop_left, crop_top, width, height, stride, s->width, s->height);
+		return -1;
+	}
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	if (!s->md5_dev) {
+		if (cache_get(s->dev, false, 16 * 64, (void **)&s->md5_dev, &s->md5_dev_alloc) < 0) return -1;
+		if (cache_get(s->dev, true, 16 * 64, (void **)&s->md5_host, &s->md5_host_alloc) < 0) return -1;
+		for (int i = 0; i < 12; ++i) B2_CUDA_OK(cudaStreamCreateWithFlags(&s->md5_streams[i], cudaStreamNonBlocking));
+		for (int i = 0; i < s->nframes; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->md5_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
+	}
+	s->md5_stride = stride; s->md5_left = crop_left; s->md5_top = crop_top; s->md5_w = width; s->md5_h = height;
+	s->md5_on = true;
+	return 0;
+}
+
+extern "C" int b2_session_md5(b2_session *s, int idx, uint8_t digest[16]) {
+	if (!s || (unsigned)idx >= (unsigned)s->nframes || !digest) return -1;
+	if (!s->md5_on || !s->md5_pending[idx]) { set_error("b2_session_md5: frame %d has no digest (digest mode off, or nothing was decoded into it)", idx); return -1; }
+	B2_CUDA_OK(cudaSetDevice(s->dev));
+	if (cudaEventQuery(s->md5_done[idx]) != cudaSuccess) {
+		cudaGetLastError();
+		B2_CUDA_OK(cudaEventSynchronize(s->md5_done[idx]));
+	}
+	memcpy(digest, s->md5_host + 16 * idx, 16);
+	return 0;
 }
 
 extern "C" int b2_session_set_record_check(b2_session *s, int on) {

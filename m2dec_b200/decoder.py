@@ -105,9 +105,11 @@ def frame_md5(frm):
 
 
 class M2Decoder:
-    def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None, chunk=0):
+    def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None, chunk=0, device_md5=False):
         """chunk > 0: the stream is handed over `chunk` bytes at a time through ONE reused buffer, as the
-        reference application refills its input buffer (bytes of an earlier refill do not stay valid)."""
+        reference application refills its input buffer (bytes of an earlier refill do not stay valid).
+        device_md5: digest mode (b2_context_set_md5) -- frames are hashed on the device, `frame_digest(frm)`
+        returns what `frame_md5(frm)` would, the frame buffers themselves are not filled."""
         self.codec = codec
         self._chunk, self._pos = int(chunk), 0
         self._chunk_buf = np.empty(max(int(chunk), 1), np.uint8)
@@ -131,6 +133,8 @@ class M2Decoder:
             L.lib.b2_context_set_tap(self.ctx, self._tap_cb, None, 1 if device_off else 0)
         if cuda_device is not None:
             L.lib.b2_context_set_device(self.ctx, cuda_device)
+        if device_md5:
+            L.lib.b2_context_set_md5(self.ctx, 1)
         self.stream = self.func.stream_pos(self.ctx)
         L.lib.dec_bits_set_callback(self.stream, self._refill_cb, None)
 
@@ -147,6 +151,13 @@ class M2Decoder:
             self.close()
         except Exception:
             pass
+
+    def frame_digest(self, frm):
+        """MD5 (hex) of an output frame as computed on the device (digest mode)."""
+        out = (C.c_uint8 * 16)()
+        if L.lib.b2_context_frame_md5(self.ctx, C.byref(frm), out) < 0:
+            raise RuntimeError("b2_context_frame_md5: %s" % (L.lib.b2_last_error() or b"").decode())
+        return bytes(out).hex()
 
     # reference h264dec.cpp:67-84: hand the whole file over once, then report end of data
     def _on_refill(self, _arg):
@@ -230,7 +241,7 @@ def decode_file(codec, data, post=None, **kw):
     md5s = []
 
     def _post(frm):
-        md5s.append(frame_md5(frm))
+        md5s.append(dec.frame_digest(frm) if kw.get("device_md5") else frame_md5(frm))
         if post is not None:
             post(frm)
 

@@ -3,7 +3,10 @@
 // page-locked application frame buffers.  One decoder context per stream, T host threads, the decode loop of the
 // reference application (src/app/m2decoder.h:132-157, h264dec.cpp:251-257).  Links libm2dec_b200.so; the Python
 // bench drives it and checks its frame hashes against the frames the (MD5-verified) Python path produced.
-//   e2ebench <h264|mpeg2> <threads> <repetitions> <cuda device> <md5 0|1> file...
+//   e2ebench <h264|mpeg2> <threads> <repetitions> <cuda device> <md5 0|1|2> file...
+// md5 = 2: digest mode (b2_context_set_md5): the frames are hashed ON THE DEVICE and only their 16-byte MD5s come
+// back; a frame's digest is collected DIGEST_LAG output frames after the frame came out (a hash takes ~30 ms, the
+// decoder does not reuse a frame buffer that soon: on_header hands it 16 frames more than it asks for).
 // Output: one line "frames F seconds S h2d B d2h B launches L" (seconds = sum over the repetitions; per-repetition
 // times go to stderr), then with md5=1 one line per stream: "stream i n m0 m1 ..." = the MD5 of every output frame
 // as `h264dec -O` of the reference prints it (cropped luma rows, then cropped interleaved-CbCr rows;
@@ -13,6 +16,7 @@
 #include <string.h>
 #include <atomic>
 #include <chrono>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -144,7 +148,19 @@ struct App {
 	int frames_w = 0, frames_h = 0;
 	long n_frames = 0;
 	bool failed = false;
+	bool digest = false;                 // md5 = 2
+	std::deque<m2d_frame_t> pending;     // frames whose digest has not been collected yet
 };
+enum { DIGEST_LAG = 10 };
+
+static void collect_digest(App *a) {
+	uint8_t d[16];
+	if (b2_context_frame_md5(a->ctx.data(), &a->pending.front(), d) < 0) { a->failed = true; a->pending.pop_front(); return; }
+	a->pending.pop_front();
+	char out[33];
+	for (int i = 0; i < 16; ++i) snprintf(out + 2 * i, 3, "%02x", d[i]);
+	a->out->hashes.push_back(std::string(out, 32));
+}
 
 static int on_refill(void *arg) {
 	App *a = (App *)arg;
@@ -182,6 +198,11 @@ static int on_header(void *arg, void *) {        // reference m2decoder.h:54-80
 
 static void post(App *a, const m2d_frame_t &fr) {
 	a->n_frames++;
+	if (a->digest) {
+		a->pending.push_back(fr);
+		while (a->pending.size() > DIGEST_LAG) collect_digest(a);
+		return;
+	}
 	if (!a->hash) return;
 	const int stride = fr.width, width = stride - fr.crop[0] - fr.crop[1], height = fr.height - fr.crop[2] - fr.crop[3];
 	Md5 m;
@@ -214,10 +235,12 @@ static bool run_stream(App *a, const Stream *in, Stream *out) {
 	a->fed = false;
 	a->frames_w = a->frames_h = 0;
 	a->frames.clear();
-	if (a->hash) out->hashes.clear();
+	if (a->hash || a->digest) out->hashes.clear();
+	a->pending.clear();
 	void *c = a->ctx.data();
 	if (a->f->init(c, -1, on_header, a) < 0) return false;
 	b2_context_set_device(c, a->device);
+	if (a->digest) b2_context_set_md5(c, 1);
 	dec_bits_set_callback(a->f->stream_pos(c), on_refill, a);
 	for (;;) {
 		int err = decode(a);
@@ -226,6 +249,8 @@ static bool run_stream(App *a, const Stream *in, Stream *out) {
 	}
 	m2d_frame_t fr;
 	while (a->f->peek_decoded_frame(c, &fr, 1) > 0) { post(a, fr); a->f->get_decoded_frame(c, &fr, 1); }
+	while (!a->pending.empty()) collect_digest(a);
+	if (a->failed) { b2_context_release(c); return false; }
 	b2_context_stats(c, out->stats);
 	b2_context_release(c);
 	return true;
@@ -235,7 +260,7 @@ int main(int argc, char **argv) {
 	if (argc < 7) { fprintf(stderr, "usage: e2ebench h264|mpeg2 threads repetitions device hash file...\n"); return 2; }
 	const bool h264 = !strcmp(argv[1], "h264");
 	const int threads = atoi(argv[2]), reps = atoi(argv[3]), device = atoi(argv[4]);
-	const bool hash = atoi(argv[5]) != 0;
+	const bool hash = atoi(argv[5]) == 1, digest = atoi(argv[5]) == 2;
 	std::vector<Stream> streams(argc - 6);
 	for (int i = 6; i < argc; ++i) {
 		FILE *fp = fopen(argv[i], "rb");
@@ -264,6 +289,7 @@ int main(int argc, char **argv) {
 				a.h264 = h264;
 				a.device = device;
 				a.hash = hash;
+				a.digest = digest;
 				a.ctx.resize(f->context_size);
 				a.pool = &pools[t];
 				for (;;) {
@@ -285,7 +311,7 @@ int main(int argc, char **argv) {
 		for (int k = 0; k < 3; ++k) tot[k] += st.stats[k];
 	// (traffic and launches of ONE pass over the streams)
 	printf("frames %ld seconds %.6f h2d %llu d2h %llu launches %llu\n", frames.load(), seconds, (unsigned long long)tot[0], (unsigned long long)tot[1], (unsigned long long)tot[2]);
-	if (hash)
+	if (hash || digest)
 		for (size_t i = 0; i < streams.size(); ++i) {
 			printf("stream %zu %zu", i, streams[i].hashes.size());
 			for (const std::string &h : streams[i].hashes) printf(" %s", h.c_str());

@@ -20,6 +20,8 @@ int b2_session_bind_host_frame(b2_session *, int, uint8_t *, uint8_t *) { return
 int b2_session_download(b2_session *, int, uint8_t *, uint8_t *) { return -1; }
 int b2_session_traffic(const b2_session *, uint64_t *) { return -1; }
 int b2_session_set_record_check(b2_session *, int) { return -1; }
+int b2_session_set_md5(b2_session *, int, int, int, int, int, int) { return -1; }
+int b2_session_md5(b2_session *, int, uint8_t *) { return -1; }
 uint64_t b2_session_launches(const b2_session *) { return 0; }
 const char *b2_last_error(void) { return ""; }
 }
