@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lanes", type=int, default=256, help="independent 1080p streams per GPU")
+    ap.add_argument("--lanes", type=int, default=512, help="independent 1080p streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
     ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
     ap.add_argument("--e2e-streams", type=int, default=32, help="streams per end-to-end repetition (two per host thread on a 16-core box: an even tail)")
@@ -507,7 +507,7 @@ def main():
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peak, peak_src = peaks()
     # the kernels behind the three phases of a replay step (m2dec_b200/csrc/h264_recon.cu)
-    names = ["h264_inter5_kernel", "h264_intra_sparse_kernel (P) / h264_wave_kernel<1> (I)", "h264_deblock2_kernel"]
+    names = ["h264_inter5_kernel", "h264_intra_sparse_kernel (P) / h264_wave_kernel<1> (I)", "h264_deblock3_kernel"]
     phase = ["inter", "intra", "deblock"]
     dom = max(range(3), key=lambda i: kernel_ms[i])
     alg = [int(st.alg_bytes[i]) for i in range(3)]

@@ -7,8 +7,9 @@
 //                                   host-sorted list; each output byte is written once.
 //   h264_wave_kernel<1>      K3+K1  intra 4x4 / 8x8 / 16x16 / chroma prediction + residual, and I_PCM, as a
 //   h264_intra_sparse_kernel        persistent MB-row wavefront (I pictures) / per-macroblock flags (P, B pictures).
-//   h264_deblock2_kernel     K4     in-loop filter from the per-MB strength records, two pictures per warp on
-//   h264_wave_kernel<2>             packed 16x2 lanes (batched launches) / one picture per launch (plugin path).
+//   h264_deblock3_kernel     K4     in-loop filter from the per-MB strength records: two pictures (packed 16x2 lanes)
+//   h264_wave_kernel<2>             and two macroblock rows per warp (batched launches) / one picture per launch
+//                                   (plugin path).
 //
 // Arithmetic restated from the reference (src/lib/h264.cpp): dequant tables 964-1054 and
 // coeff_writeback 2005-2022; 4x4 transform 2145-2269; 8x8 transform 3942-4080; DC transforms
@@ -1515,44 +1516,15 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Deblocking, two pictures per warp.  The kernel above spends its instructions per sample and per
-// macroblock; here every register holds the same sample of TWO pictures of the launch (16-bit
-// lanes: picture A low, B high), the filter runs on both with the packed 16x2 integer
-// instructions of sm_100 (VIADD.16x2, VIMNMX.S16x2, VABSDIFF4) and plain 32-bit arithmetic on
-// biased lanes, and all per-macroblock work (waiting, publishing, addressing, the transposes
-// through shared memory) is done once for the pair.  Lane roles, tile layout and the order of
-// operations are those of deblock_chunk; conditions are carried as bit 15 of each lane
-// ((threshold - 1 + 0x8000) - |difference| has the bit set exactly when the test holds) and
-// applied by masking the clipping bounds, so the filter has no branch except the bS 4 case.
+// Deblocking of batched launches: helpers of the packed form.  The one-picture kernel above spends its
+// instructions per sample and per macroblock; in h264_deblock3_kernel every register holds the same sample of
+// TWO pictures of the launch (16-bit lanes: picture A low, B high), the filter runs on both with the packed
+// 16x2 integer instructions of sm_100 (VIADD.16x2, VIMNMX.S16x2, VABSDIFF4) and plain 32-bit arithmetic on
+// biased lanes, and all per-macroblock work (waiting, publishing, addressing, the transposes through shared
+// memory) is done once for the pair.  Conditions are carried as bit 15 of each lane ((threshold - 1 + 0x8000) -
+// |difference| has the bit set exactly when the test holds) and applied by masking the clipping bounds, so the
+// filter has no branch except the bS 4 case.
 // ------------------------------------------------------------------------------------------------
-// progress of a row is published every so many macroblocks (a power of two): fewer release stores and flag
-// writes, at the price of the row below running that much further behind
-#ifndef B2_DBK2_PUBLISH_EVERY
-#define B2_DBK2_PUBLISH_EVERY 2
-#endif
-// how far a row that had to wait lets the row above get ahead before it resumes (RowSync::lead)
-#ifndef B2_DBK2_LEAD
-#define B2_DBK2_LEAD 0
-#endif
-struct alignas(16) DbkTile2 {
-	// one packed pair per sample; rows -4..15 at r + 4, columns -4..15 at c + 4.  Pitch 28 words: rows are 16-byte
-	// aligned (whole lines move as 128-bit accesses) and eight consecutive rows start in eight different bank groups
-	uint32_t y[20][28];
-	uint32_t c[10][28];     // chroma rows -2..7 at r + 2, byte columns (Cb Cr interleaved) -4..15 at c + 4
-};
-
-// What a warp stages per chunk of 32 macroblocks so that nothing inside the macroblock loop waits for a global
-// load it could have asked for earlier (the round-2 profile had 20 % of the kernel's stall samples on the first
-// use of the strength record and of the macroblock's own samples): the strength records of both pictures and the
-// QP words of the row above (read once per chunk, by the pass that finds the macroblocks needing work), and a
-// two-slot ring that the own samples of the NEXT macroblock are copied into (cp.async) while the current one
-// is filtered.
-struct alignas(16) DbkStage2 {
-	uint4 rec[2][32];           // [picture][macroblock of the chunk]
-	uint32_t qp_top[2][32];     // word 2 (QPs, flags) of the record above
-	uint4 own[2][2][24];        // [slot][picture][line: luma 0..15, chroma 16..23]: 16 bytes of the line
-};
-
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -1565,67 +1537,121 @@ __device__ __forceinline__ uint32_t vsel(uint32_t m, uint32_t a, uint32_t b) { r
 // clip3(-t, t, x) per lane
 __device__ __forceinline__ uint32_t vclamp2(uint32_t x, uint32_t t) { return __vmins2(__vmaxs2(x, vneg2(t)), t); }
 
-template <bool MAY_BS4>
-__device__ __forceinline__ void dbk_filter2(uint32_t *v, const int q, const uint32_t onbits, const uint32_t bs4bits, const uint32_t alpha2, const uint32_t beta2,
-                                            const uint32_t tc02, const bool luma) {
-	const uint32_t p0 = v[q - 1], p1 = v[q - 2], p2 = v[q - 3], q0 = v[q], q1 = v[q + 1], q2 = v[q + 2];
-	const uint32_t B15 = 0x80008000u;
-	const uint32_t am = alpha2 + 0x7FFF7FFFu, bm = beta2 + 0x7FFF7FFFu;      // a zero threshold never passes
-	const uint32_t d0 = __vabsdiffu4(p0, q0);
-	const uint32_t act = (am - d0) & (bm - __vabsdiffu4(p1, p0)) & (bm - __vabsdiffu4(q1, q0)) & onbits;
-	const uint32_t lum = luma ? B15 : 0u;
-	const uint32_t ap = (bm - __vabsdiffu4(p2, p0)) & lum, aq = (bm - __vabsdiffu4(q2, q0)) & lum;
-	const uint32_t nb = MAY_BS4 ? act & ~bs4bits : act;
-	const uint32_t mn = bits_mask(nb);
-	const uint32_t tc = (tc02 + (luma ? (ap >> 15) + (aq >> 15) : 0x00010001u)) & mn;
-	// delta = clip3(-tc, tc, ((q0 - p0) * 4 + (p1 - q1) + 4) >> 3): lanes biased by 2048 so that they stay positive
-	const uint32_t X = ((q0 - p0) << 2) + (p1 - q1) + 0x08040804u;
-	const uint32_t delta = vclamp2(__vadd2((X >> 3) & 0x1FFF1FFFu, 0xFF00FF00u), tc);
-	uint32_t np0 = __vimin_s16x2_relu(__vadd2(p0, delta), 0x00FF00FFu);
-	uint32_t nq0 = __vimin_s16x2_relu(__vadd2(q0, vneg2(delta)), 0x00FF00FFu);
-	const uint32_t avg = ((p0 + q0 + 0x00010001u) >> 1) & 0x7FFF7FFFu;
-	const uint32_t t0 = tc02 & mn;
-	const uint32_t zp = __vadd2(((p2 + avg + 0x02000200u - (p1 << 1)) >> 1) & 0x7FFF7FFFu, 0xFF00FF00u);
-	const uint32_t zq = __vadd2(((q2 + avg + 0x02000200u - (q1 << 1)) >> 1) & 0x7FFF7FFFu, 0xFF00FF00u);
-	uint32_t np1 = __vadd2(p1, vclamp2(zp, t0 & bits_mask(ap)));
-	uint32_t nq1 = __vadd2(q1, vclamp2(zq, t0 & bits_mask(aq)));
-	if (MAY_BS4) {
-		const uint32_t a4 = act & bs4bits;
-		if (__any_sync(__activemask(), a4 != 0)) {
-			const uint32_t p3 = v[q - 4], q3 = v[q + 3];
-			const uint32_t sm = ((alpha2 >> 2) & 0x3FFF3FFFu) + 0x80018001u;          // (alpha >> 2) + 2, as a biased threshold
-			const uint32_t st = (sm - d0) & lum & a4;
-			const uint32_t msp = bits_mask(st & ap), msq = bits_mask(st & aq), m4 = bits_mask(a4);
-			const uint32_t pq = p0 + q0;
-			const uint32_t sp0 = ((p2 + 2 * p1 + 2 * pq + q1 + 0x00040004u) >> 3) & 0x1FFF1FFFu;
-			const uint32_t sp1 = ((p2 + p1 + pq + 0x00020002u) >> 2) & 0x3FFF3FFFu;
-			const uint32_t sp2 = ((2 * p3 + 3 * p2 + p1 + pq + 0x00040004u) >> 3) & 0x1FFF1FFFu;
-			const uint32_t wp0 = ((2 * p1 + p0 + q1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
-			const uint32_t sq0 = ((q2 + 2 * q1 + 2 * pq + p1 + 0x00040004u) >> 3) & 0x1FFF1FFFu;
-			const uint32_t sq1 = ((q2 + q1 + pq + 0x00020002u) >> 2) & 0x3FFF3FFFu;
-			const uint32_t sq2 = ((2 * q3 + 3 * q2 + q1 + pq + 0x00040004u) >> 3) & 0x1FFF1FFFu;
-			const uint32_t wq0 = ((2 * q1 + q0 + p1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
-			np0 = vsel(msp, sp0, vsel(m4, wp0, np0));
-			np1 = vsel(msp, sp1, np1);
-			v[q - 3] = vsel(msp, sp2, p2);
-			nq0 = vsel(msq, sq0, vsel(m4, wq0, nq0));
-			nq1 = vsel(msq, sq1, nq1);
-			v[q + 2] = vsel(msq, sq2, q2);
-		}
-	}
-	v[q - 1] = np0;
-	v[q] = nq0;
-	v[q - 2] = np1;
-	v[q + 1] = nq1;
-}
-
 struct DbkSide {            // what one picture of the pair contributes to a line: strengths, flags, QPs, offsets
 	uint32_t bits;
 	bool edge0_ok, edge0_bs4;
 	int qpc, qpn, aoff, boff;
 };
 
-__device__ __forceinline__ void dbk_line2(uint32_t *v, const DbkTables &tb, const DbkSide &A, const DbkSide &B, int seg, bool luma) {
+// bytes (s0, s1) of word a and of word b as two packed pairs: [a.s0, 0, b.s0, 0] and [a.s1, 0, b.s1, 0]
+__device__ __forceinline__ void pair2(uint32_t a, uint32_t b, uint32_t sel, uint32_t &o0, uint32_t &o1) {
+	const uint32_t t = __byte_perm(a, b, sel);            // [a.s0, a.s1, b.s0, b.s1]
+	o0 = t & 0x00FF00FFu;
+	o1 = (t >> 8) & 0x00FF00FFu;
+}
+// four consecutive packed pairs -> the word of picture A and the word of picture B
+__device__ __forceinline__ void unpair4(const uint32_t *e, uint32_t &wa, uint32_t &wb) {
+	const uint32_t x01 = __byte_perm(e[0], e[1], 0x6240), x23 = __byte_perm(e[2], e[3], 0x6240);     // [e0.A, e1.A, e0.B, e1.B]
+	wa = __byte_perm(x01, x23, 0x5410);
+	wb = __byte_perm(x01, x23, 0x7632);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deblocking, two pictures AND two macroblock rows per warp.  In the kernel above the 16 chroma lanes of a
+// warp ride along through all four luma edges of a pass (a quarter of the lane-instructions does nothing, and
+// the chroma lanes pay for the luma-only half of the filter), and every row waits for the row above through a
+// flag.  Here a warp owns rows 2g and 2g + 1 of a picture pair and walks them together, the lower row two
+// macroblocks behind the upper one: step s filters macroblock (2g, s) in lanes 0..15 and (2g + 1, s - 2) in lanes
+// 16..31 -- what the lower macroblock needs from the row above was finished by this very warp one step earlier,
+// so half of the row-to-row dependencies need no flag at all.  Luma and chroma are separate passes, both on all
+// 32 lanes: luma = one line (V pass) / column (H pass) of 20 samples per lane and four edges of the full filter;
+// chroma = one line / byte column of 10 samples per lane and two edges of the chroma filter (no p1 / q1 terms).
+// Tile: one packed pair per 32-bit entry (picture A low / B high 16 bits); columns 12..15 of a macroblock stay in
+// the tile as columns -4..-1 of the next one (carry) when both have work; row progress through RowSync flags.
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) DbkRow3 {    // per macroblock row of the warp
+	uint32_t y[20][28];         // luma tile: rows -4..15 at r + 4, columns -4..15 at c + 4 (one packed pair per sample)
+	uint32_t c[10][28];         // chroma tile: rows -2..7 at r + 2, byte columns -4..15 at c + 4
+	uint4 rec[2][32];           // strength records of the current chunk of 32 macroblocks, [picture]
+	uint32_t qp_top[2][32];     // QP word of the records above
+	uint4 own[2][2][24];        // [slot][picture][line: luma 0..15, chroma 16..23]: the macroblock's own samples (cp.async ring)
+};
+
+template <bool MAY_BS4, bool LUMA>
+__device__ __forceinline__ void dbk_filter3(uint32_t *v, const int q, const uint32_t onbits, const uint32_t bs4bits, const uint32_t alpha2, const uint32_t beta2,
+                                            const uint32_t tc02) {
+	const uint32_t p0 = v[q - 1], p1 = v[q - 2], q0 = v[q], q1 = v[q + 1];
+	const uint32_t B15 = 0x80008000u;
+	const uint32_t am = alpha2 + 0x7FFF7FFFu, bm = beta2 + 0x7FFF7FFFu;      // a zero threshold never passes
+	const uint32_t d0 = __vabsdiffu4(p0, q0);
+	const uint32_t act = (am - d0) & (bm - __vabsdiffu4(p1, p0)) & (bm - __vabsdiffu4(q1, q0)) & onbits;
+	const uint32_t nb = MAY_BS4 ? act & ~bs4bits : act;
+	const uint32_t mn = bits_mask(nb);
+	const uint32_t X = ((q0 - p0) << 2) + (p1 - q1) + 0x08040804u;
+	const uint32_t xs = (X >> 3) & 0x1FFF1FFFu;
+	if (LUMA) {
+		const uint32_t p2 = v[q - 3], q2 = v[q + 2];
+		const uint32_t ap = (bm - __vabsdiffu4(p2, p0)) & B15, aq = (bm - __vabsdiffu4(q2, q0)) & B15;
+		const uint32_t tc = (tc02 + (ap >> 15) + (aq >> 15)) & mn;
+		const uint32_t delta = vclamp2(__vadd2(xs, 0xFF00FF00u), tc);
+		uint32_t np0 = __vimin_s16x2_relu(__vadd2(p0, delta), 0x00FF00FFu);
+		uint32_t nq0 = __vimin_s16x2_relu(__vadd2(q0, vneg2(delta)), 0x00FF00FFu);
+		const uint32_t avg = ((p0 + q0 + 0x00010001u) >> 1) & 0x7FFF7FFFu;
+		const uint32_t t0 = tc02 & mn;
+		const uint32_t zp = __vadd2(((p2 + avg + 0x02000200u - (p1 << 1)) >> 1) & 0x7FFF7FFFu, 0xFF00FF00u);
+		const uint32_t zq = __vadd2(((q2 + avg + 0x02000200u - (q1 << 1)) >> 1) & 0x7FFF7FFFu, 0xFF00FF00u);
+		uint32_t np1 = __vadd2(p1, vclamp2(zp, t0 & bits_mask(ap)));
+		uint32_t nq1 = __vadd2(q1, vclamp2(zq, t0 & bits_mask(aq)));
+		if (MAY_BS4) {
+			const uint32_t a4 = act & bs4bits;
+			if (__any_sync(__activemask(), a4 != 0)) {
+				const uint32_t p3 = v[q - 4], q3 = v[q + 3];
+				const uint32_t sm = ((alpha2 >> 2) & 0x3FFF3FFFu) + 0x80018001u;          // (alpha >> 2) + 2, as a biased threshold
+				const uint32_t st = (sm - d0) & a4;
+				const uint32_t msp = bits_mask(st & ap), msq = bits_mask(st & aq), m4 = bits_mask(a4);
+				const uint32_t pq = p0 + q0;
+				const uint32_t sp0 = ((p2 + 2 * p1 + 2 * pq + q1 + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+				const uint32_t sp1 = ((p2 + p1 + pq + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+				const uint32_t sp2 = ((2 * p3 + 3 * p2 + p1 + pq + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+				const uint32_t wp0 = ((2 * p1 + p0 + q1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+				const uint32_t sq0 = ((q2 + 2 * q1 + 2 * pq + p1 + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+				const uint32_t sq1 = ((q2 + q1 + pq + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+				const uint32_t sq2 = ((2 * q3 + 3 * q2 + q1 + pq + 0x00040004u) >> 3) & 0x1FFF1FFFu;
+				const uint32_t wq0 = ((2 * q1 + q0 + p1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+				np0 = vsel(msp, sp0, vsel(m4, wp0, np0));
+				np1 = vsel(msp, sp1, np1);
+				v[q - 3] = vsel(msp, sp2, p2);
+				nq0 = vsel(msq, sq0, vsel(m4, wq0, nq0));
+				nq1 = vsel(msq, sq1, nq1);
+				v[q + 2] = vsel(msq, sq2, q2);
+			}
+		}
+		v[q - 1] = np0;
+		v[q] = nq0;
+		v[q - 2] = np1;
+		v[q + 1] = nq1;
+	} else {
+		// chroma: tc = tc0 + 1, only p0 / q0 change; bS 4: (2 p1 + p0 + q1 + 2) >> 2
+		const uint32_t tc = (tc02 + 0x00010001u) & mn;
+		const uint32_t delta = vclamp2(__vadd2(xs, 0xFF00FF00u), tc);
+		uint32_t np0 = __vimin_s16x2_relu(__vadd2(p0, delta), 0x00FF00FFu);
+		uint32_t nq0 = __vimin_s16x2_relu(__vadd2(q0, vneg2(delta)), 0x00FF00FFu);
+		if (MAY_BS4) {
+			const uint32_t m4 = bits_mask(act & bs4bits);
+			const uint32_t wp0 = ((2 * p1 + p0 + q1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+			const uint32_t wq0 = ((2 * q1 + q0 + p1 + 0x00020002u) >> 2) & 0x3FFF3FFFu;
+			np0 = vsel(m4, wp0, np0);
+			nq0 = vsel(m4, wq0, nq0);
+		}
+		v[q - 1] = np0;
+		v[q] = nq0;
+	}
+}
+
+// The edges of one line: luma v[0..19] (edges at 4, 8, 12, 16), chroma v[0..9] (samples -2..7: edges at 2 and 6 = luma
+// edges 0 and 2 of the strength words)
+template <bool LUMA>
+__device__ __forceinline__ void dbk_line3(uint32_t *v, const DbkTables &tb, const DbkSide &A, const DbkSide &B, int seg) {
 	uint32_t alpha_i, beta_i, alpha_0, beta_0, tci[2], tc0[2];
 	{
 		const int ia = min(max(A.qpc + A.aoff, 0), 51), ib = min(max(A.qpc + A.boff, 0), 51), q0 = (A.qpc + A.qpn + 1) >> 1;
@@ -1648,238 +1674,313 @@ __device__ __forceinline__ void dbk_line2(uint32_t *v, const DbkTables &tb, cons
 		const uint32_t onbits = (ona ? 0x8000u : 0u) | (onb ? 0x80000000u : 0u);
 		const uint32_t bs4bits = (A.edge0_bs4 ? 0x8000u : 0u) | (B.edge0_bs4 ? 0x80000000u : 0u);
 		const uint32_t tc = ((tc0[0] >> (8 * (bsa ? bsa - 1 : 0))) & 255u) | (((tc0[1] >> (8 * (bsb ? bsb - 1 : 0))) & 255u) << 16);
-		if (__any_sync(__activemask(), onbits != 0)) dbk_filter2<true>(v, 4, onbits, bs4bits, alpha_0, beta_0, tc, luma);
+		if (__any_sync(__activemask(), onbits != 0)) dbk_filter3<true, LUMA>(v, LUMA ? 4 : 2, onbits, bs4bits, alpha_0, beta_0, tc);
 	}
-	if (!((A.bits | B.bits) & 0xffffff00u)) return;          // no inner edge of either macroblock has a strength
+	if (LUMA) {
+		if (!__any_sync(__activemask(), ((A.bits | B.bits) & 0xffffff00u) != 0)) return;          // no inner edge of any macroblock of the warp has a strength
 #pragma unroll
-	for (int i = 1; i < 4; ++i) {
-		const int e = luma ? i : 2 * i;                  // chroma edges 0 / 1 of the register layout are luma edges 0 / 2
-		const bool exists = luma || i < 2;
-		const int bsa = (e < 4 && exists) ? (la >> (8 * e)) & 3 : 0, bsb = (e < 4 && exists) ? (lb >> (8 * e)) & 3 : 0;
+		for (int e = 1; e < 4; ++e) {
+			const int bsa = (la >> (8 * e)) & 3, bsb = (lb >> (8 * e)) & 3;
+			const uint32_t onbits = (bsa ? 0x8000u : 0u) | (bsb ? 0x80000000u : 0u);
+			const uint32_t tc = ((tci[0] >> (8 * (bsa ? bsa - 1 : 0))) & 255u) | (((tci[1] >> (8 * (bsb ? bsb - 1 : 0))) & 255u) << 16);
+			dbk_filter3<false, true>(v, 4 + 4 * e, onbits, 0u, alpha_i, beta_i, tc);
+		}
+	} else {
+		const int bsa = (la >> 16) & 3, bsb = (lb >> 16) & 3;
 		const uint32_t onbits = (bsa ? 0x8000u : 0u) | (bsb ? 0x80000000u : 0u);
+		if (!__any_sync(__activemask(), onbits != 0)) return;
 		const uint32_t tc = ((tci[0] >> (8 * (bsa ? bsa - 1 : 0))) & 255u) | (((tci[1] >> (8 * (bsb ? bsb - 1 : 0))) & 255u) << 16);
-		dbk_filter2<false>(v, 4 + 4 * i, onbits, 0u, alpha_i, beta_i, tc, luma);
+		dbk_filter3<false, false>(v, 6, onbits, 0u, alpha_i, beta_i, tc);
 	}
 }
 
-// bytes (s0, s1) of word a and of word b as two packed pairs: [a.s0, 0, b.s0, 0] and [a.s1, 0, b.s1, 0]
-__device__ __forceinline__ void pair2(uint32_t a, uint32_t b, uint32_t sel, uint32_t &o0, uint32_t &o1) {
-	const uint32_t t = __byte_perm(a, b, sel);            // [a.s0, a.s1, b.s0, b.s1]
-	o0 = t & 0x00FF00FFu;
-	o1 = (t >> 8) & 0x00FF00FFu;
-}
-// four consecutive packed pairs -> the word of picture A and the word of picture B
-__device__ __forceinline__ void unpair4(const uint32_t *e, uint32_t &wa, uint32_t &wb) {
-	const uint32_t x01 = __byte_perm(e[0], e[1], 0x6240), x23 = __byte_perm(e[2], e[3], 0x6240);     // [e0.A, e1.A, e0.B, e1.B]
-	wa = __byte_perm(x01, x23, 0x5410);
-	wb = __byte_perm(x01, x23, 0x7632);
+// the strength records of macroblocks xs .. xs + 31 of row mby (both pictures) and the QP words of the row above, into the row's staging
+__device__ __forceinline__ void dbk3_load_chunk(DbkRow3 &R, const H4Job &job0, const H4Job &job1, bool valid1, int mby, int xs, int lane) {
+	const int mb_w = job0.mb_w, mbx = xs + lane;
+	uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+	uint32_t ta = 0, tb = 0;
+	if (mbx < mb_w) {
+		const size_t mbi = (size_t)mby * mb_w + mbx;
+		ra = __ldg(reinterpret_cast<const uint4 *>(job0.dbk + mbi));
+		if (valid1) rb = __ldg(reinterpret_cast<const uint4 *>(job1.dbk + mbi));
+		if (mby > 0) {
+			ta = __ldg(reinterpret_cast<const uint32_t *>(job0.dbk + mbi - mb_w) + 2);
+			tb = __ldg(reinterpret_cast<const uint32_t *>(job1.dbk + mbi - mb_w) + 2);
+		}
+	}
+	if ((ra.z >> 24) & B2_DBK_OFF) ra.x = ra.y = 0;
+	if (((rb.z >> 24) & B2_DBK_OFF) || !valid1) rb.x = rb.y = 0;
+	__syncwarp();                      // the previous chunk's readers are done
+	R.rec[0][lane] = ra; R.rec[1][lane] = rb;
+	R.qp_top[0][lane] = ta; R.qp_top[1][lane] = tb;
+	__syncwarp();
 }
 
-// One row chunk of a picture pair: macroblocks x0 + k for the set bits k of `todo` (needed by either picture), left to right.
-__device__ void deblock_chunk2(const H4Job &jobA, const H4Job &jobB, bool validB, const DbkTables &tb, DbkTile2 &tl, DbkStage2 &sg, int mby, int x0, unsigned todo, int lane,
-                               RowSync &sy, int &done_to) {
-	const int mb_w = jobA.mb_w, W = mb_w * 16, H = jobA.mb_h * 16;
-	uint8_t *const fyA = jobA.frames + jobA.frame_bytes * jobA.dst, *const fyB = jobB.frames + jobB.frame_bytes * jobB.dst;
-	uint8_t *const fcA = fyA + (size_t)W * H, *const fcB = fyB + (size_t)W * H;
-	const bool luma = lane < 16;
-	const int comp = lane & 1;                              // chroma lanes: component
-	const int line = luma ? lane : (lane - 16) >> 1;        // V pass: picture line inside the MB (chroma: 0..7)
-	const size_t line_off = luma ? (size_t)(mby * 16 + line) * W : (size_t)(mby * 8 + line) * W;
-	const uint8_t *const lbA = (luma ? fyA : fcA) + line_off, *const lbB = (luma ? fyB : fcB) + line_off;
-	uint32_t *const trow = luma ? tl.y[4 + line] : tl.c[2 + line];      // this lane's line in the tile
-	const uint32_t csel = comp ? 0x7531u : 0x6420u;         // chroma: bytes (comp, 2 + comp) of both words
+#ifndef B2_DBK3_WARPS
+#define B2_DBK3_WARPS 1
+#endif
+constexpr int DBK3_WARPS = B2_DBK3_WARPS;          // row pairs per CTA
+#ifndef B2_DBK3_WARPS_PER_SM
+#define B2_DBK3_WARPS_PER_SM 16
+#endif
+constexpr int DBK3_CTAS = B2_DBK3_WARPS_PER_SM / DBK3_WARPS;
+#ifndef B2_DBK3_PUBLISH_EVERY
+#define B2_DBK3_PUBLISH_EVERY 2
+#endif
+
+// Rows r0 and r0 + 1 (if has_r1) of a picture pair, all macroblocks, left to right.
+__device__ void deblock_rows3(const H4Job &job0, const H4Job &job1, const bool valid1, const DbkTables &tb, DbkRow3 *rows, const int r0, const bool has_r1,
+                              const int lane, RowSync &sy) {
+	const int mb_w = job0.mb_w, W = mb_w * 16, H = job0.mb_h * 16;
+	const int half = lane >> 4, l16 = lane & 15;
+	DbkRow3 &R = rows[half];
+	const int mby = r0 + half;
+	const bool row_ok = half == 0 || has_r1;
+	uint8_t *const fy0 = job0.frames + job0.frame_bytes * job0.dst, *const fy1 = job1.frames + job1.frame_bytes * job1.dst;
+	uint8_t *const fc0 = fy0 + (size_t)W * H, *const fc1 = fy1 + (size_t)W * H;
+	const size_t yline = (size_t)(mby * 16 + l16) * W;               // luma V pass: this lane's line
+	const int cline = l16 >> 1, comp = l16 & 1;                      // chroma V pass: line 0..7, component
+	const size_t cl_off = (size_t)(mby * 8 + cline) * W;
+	const uint32_t csel = comp ? 0x7531u : 0x6420u;
+	uint32_t *const trow = R.y[4 + l16];
+	uint32_t *const crow = R.c[2 + cline];
 	bool carry_in = false;
-	// own samples of a macroblock into a ring slot: luma lanes copy their line of both pictures, the two lanes of a
-	// chroma line one picture each.  (Nobody else writes these samples before this row has published them.)
-	const int own_line = luma ? line : 16 + line;
-	auto fetch_own = [&](int xx, int slot) {
-		if (luma || !comp) cp_async16(&sg.own[slot][0][own_line], lbA + xx * 16);
-		if (luma || comp) cp_async16(&sg.own[slot][1][own_line], lbB + xx * 16);
+	const int steps = mb_w + (has_r1 ? 2 : 0);
+	// own samples of the macroblocks of step `st` into ring slot st & 1: luma lanes their line of both pictures; the chroma
+	// lines of a macroblock (8 lines x 2 pictures) one per lane
+	auto fetch_own = [&](int st) {
+		const int xx = half ? st - 2 : st;
+		if (row_ok && xx >= 0 && xx < mb_w) {
+			const int sl = st & 1;
+			cp_async16(&R.own[sl][0][l16], fy0 + yline + xx * 16);
+			if (valid1) cp_async16(&R.own[sl][1][l16], fy1 + yline + xx * 16);
+			const int pic = l16 >> 3, cln = l16 & 7;
+			if (pic == 0 || valid1) cp_async16(&R.own[sl][pic][16 + cln], (pic ? fc1 : fc0) + (size_t)(mby * 8 + cln) * W + xx * 16);
+		}
 		cp_async_commit();
 	};
-	int slot = 0;
-	if (todo) fetch_own(x0 + __ffs(todo) - 1, 0);
-	while (todo) {
-		const int k = __ffs(todo) - 1;
-		todo &= todo - 1;
-		const int x = x0 + k;
-		const bool carry_out = todo && (__ffs(todo) - 1 == k + 1);      // the next macroblock takes over columns 12..15
-		if (todo) fetch_own(x0 + __ffs(todo) - 1, slot ^ 1);             // the next macroblock's samples, while this one is filtered
-		if (x > done_to) sy.publish(x, lane);              // the stretch that needed nothing
-		uint4 drA = sg.rec[0][k], drB = sg.rec[1][k];
-		uint32_t qlA = 0, qlB = 0;
-		if (k > 0) { qlA = sg.rec[0][k - 1].z; qlB = sg.rec[1][k - 1].z; }
-		else if (x > 0) {
-			const size_t mbi = (size_t)mby * mb_w + x;
-			qlA = __ldg(reinterpret_cast<const uint32_t *>(jobA.dbk + mbi - 1) + 2);
-			qlB = __ldg(reinterpret_cast<const uint32_t *>(jobB.dbk + mbi - 1) + 2);
+	fetch_own(0);
+	for (int s = 0; s < steps; ++s) {
+		const int x = half ? s - 2 : s;
+		const bool in_row = row_ok && x >= 0 && x < mb_w;
+		if (s < mb_w && (s & 31) == 0) dbk3_load_chunk(rows[0], job0, job1, valid1, r0, s, lane);
+		if (has_r1 && s >= 2 && s - 2 < mb_w && ((s - 2) & 31) == 0) dbk3_load_chunk(rows[1], job0, job1, valid1, r0 + 1, s - 2, lane);
+		fetch_own(s + 1);
+		const int k = x & 31;
+		uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+		bool next_need = false;
+		if (in_row) {
+			d0 = R.rec[0][k]; d1 = R.rec[1][k];
+			if (k < 31 && x + 1 < mb_w) {
+				const uint4 n0 = R.rec[0][k + 1], n1 = R.rec[1][k + 1];
+				next_need = (n0.x | n0.y | n1.x | n1.y) != 0;
+			}
 		}
-		const uint32_t qtA = sg.qp_top[0][k], qtB = sg.qp_top[1][k];
-		if ((drA.z >> 24) & B2_DBK_OFF) drA.x = drA.y = 0;
-		if (((drB.z >> 24) & B2_DBK_OFF) || !validB) drB.x = drB.y = 0;
-		uint32_t wA[5], wB[5];
-		if (todo) cp_async_wait<1>(); else cp_async_wait<0>();
-		__syncwarp();
-		{
-			const uint4 oa = sg.own[slot][0][own_line], ob = sg.own[slot][1][own_line];
-			wA[1] = oa.x; wA[2] = oa.y; wA[3] = oa.z; wA[4] = oa.w;
-			wB[1] = ob.x; wB[2] = ob.y; wB[3] = ob.z; wB[4] = ob.w;
-		}
-		slot ^= 1;
-		wA[0] = wB[0] = 0;
-		if (!carry_in && x > 0) {
-			wA[0] = __ldcg(reinterpret_cast<const uint32_t *>(lbA + x * 16 - 4));
-			wB[0] = __ldcg(reinterpret_cast<const uint32_t *>(lbB + x * 16 - 4));
-		}
-		if (mby > 0) sy.wait(min(x + 2, mb_w), lane);
-		// rows above the macroblock (final once the row above is two macroblocks ahead): lanes 0..15 one
-		// word of luma rows -4..-1, lanes 16..23 one word of chroma rows -2..-1
-		uint32_t twA = 0, twB = 0;
-		if (mby > 0 && lane < 24) {
-			const size_t off = (luma ? (size_t)(mby * 16 - 4 + (lane >> 2)) * W : (size_t)(mby * 8 - 2 + ((lane - 16) >> 2)) * W) + x * 16 + 4 * (lane & 3);
-			twA = __ldcg(reinterpret_cast<const uint32_t *>((luma ? fyA : fcA) + off));
-			twB = __ldcg(reinterpret_cast<const uint32_t *>((luma ? fyB : fcB) + off));
-		}
-		// ---- record fields ---------------------------------------------------------------------------
-		const int qsel = luma ? 0 : 8 + 8 * comp;            // byte of the QP word: qp_y, qp_cb, qp_cr
-		DbkSide sA, sB;
-		const int flagsA = (drA.z >> 24) & 255, flagsB = (drB.z >> 24) & 255;
-		sA.qpc = (int8_t)((drA.z >> qsel) & 255); sB.qpc = (int8_t)((drB.z >> qsel) & 255);
-		sA.aoff = (int8_t)(drA.w & 255); sA.boff = (int8_t)((drA.w >> 8) & 255);
-		sB.aoff = (int8_t)(drB.w & 255); sB.boff = (int8_t)((drB.w >> 8) & 255);
-		const bool topA = flagsA & B2_DBK_TOP_EDGE, topB = (flagsB & B2_DBK_TOP_EDGE) && validB;
-		// ---- V pass ----------------------------------------------------------------------------------
-		{
-			uint32_t v[20];
-			if (luma) {
+		const bool need = (d0.x | d0.y | d1.x | d1.y) != 0;        // (records of macroblocks with the filter off were cleared when staged)
+		const bool carry_out = need && next_need;                  // the next macroblock takes over columns 12..15
+		const unsigned need_bal = __ballot_sync(0xffffffffu, need);
+		if (need_bal) {
+			if ((need_bal & 1u) && r0 > 0) sy.wait(min(s + 2, mb_w), lane);
+			uint32_t ql0 = 0, ql1 = 0, qt0 = 0, qt1 = 0;
+			if (need) {
+				if (k > 0) { ql0 = R.rec[0][k - 1].z; ql1 = R.rec[1][k - 1].z; }
+				else if (x > 0) {
+					const size_t mbi = (size_t)mby * mb_w + x;
+					ql0 = __ldg(reinterpret_cast<const uint32_t *>(job0.dbk + mbi - 1) + 2);
+					ql1 = __ldg(reinterpret_cast<const uint32_t *>(job1.dbk + mbi - 1) + 2);
+				}
+				qt0 = R.qp_top[0][k]; qt1 = R.qp_top[1][k];
+			}
+			const int flags0 = (d0.z >> 24) & 255, flags1 = (d1.z >> 24) & 255;
+			DbkSide sA, sB;
+			sA.aoff = (int8_t)(d0.w & 255); sA.boff = (int8_t)((d0.w >> 8) & 255);
+			sB.aoff = (int8_t)(d1.w & 255); sB.boff = (int8_t)((d1.w >> 8) & 255);
+			// rows above the macroblock, one word per lane and picture: luma rows -4..-1, chroma rows -2..-1 (lanes < 8 of the half)
+			uint32_t tw0 = 0, tw1 = 0, tc0w = 0, tc1w = 0;
+			if (need && mby > 0) {
+				const size_t off = (size_t)(mby * 16 - 4 + (l16 >> 2)) * W + x * 16 + 4 * (l16 & 3);
+				tw0 = __ldcg(reinterpret_cast<const uint32_t *>(fy0 + off));
+				tw1 = __ldcg(reinterpret_cast<const uint32_t *>(fy1 + off));
+				if (l16 < 8) {
+					const size_t offc = (size_t)(mby * 8 - 2 + (l16 >> 2)) * W + x * 16 + 4 * (l16 & 3);
+					tc0w = __ldcg(reinterpret_cast<const uint32_t *>(fc0 + offc));
+					tc1w = __ldcg(reinterpret_cast<const uint32_t *>(fc1 + offc));
+				}
+			}
+			// left four columns when the previous macroblock did not leave them in the tile
+			uint32_t wl0 = 0, wl1 = 0, cl0 = 0, cl1 = 0;
+			if (need && !carry_in && x > 0) {
+				wl0 = __ldcg(reinterpret_cast<const uint32_t *>(fy0 + yline + x * 16 - 4));
+				wl1 = __ldcg(reinterpret_cast<const uint32_t *>(fy1 + yline + x * 16 - 4));
+				cl0 = __ldcg(reinterpret_cast<const uint32_t *>(fc0 + cl_off + x * 16 - 4));
+				cl1 = __ldcg(reinterpret_cast<const uint32_t *>(fc1 + cl_off + x * 16 - 4));
+			}
+			cp_async_wait<1>();
+			__syncwarp();
+			const int sl = s & 1;
+			// ---- luma V pass: lane = line ------------------------------------------------------------------
+			{
+				uint32_t v[20];
+				const uint4 oa = R.own[sl][0][l16], ob = R.own[sl][1][l16];
+				const uint32_t w0[5] = {wl0, oa.x, oa.y, oa.z, oa.w}, w1[5] = {wl1, ob.x, ob.y, ob.z, ob.w};
 #pragma unroll
 				for (int j = 0; j < 5; ++j) {
-					pair2(wA[j], wB[j], 0x5410u, v[4 * j], v[4 * j + 1]);
-					pair2(wA[j], wB[j], 0x7632u, v[4 * j + 2], v[4 * j + 3]);
+					pair2(w0[j], w1[j], 0x5410u, v[4 * j], v[4 * j + 1]);
+					pair2(w0[j], w1[j], 0x7632u, v[4 * j + 2], v[4 * j + 3]);
 				}
 				if (carry_in) {
-#pragma unroll
-					for (int i = 0; i < 4; ++i) v[i] = trow[i];       // (one 128-bit load: the row is 16-byte aligned)
+					const uint4 c4 = *reinterpret_cast<const uint4 *>(trow);
+					v[0] = c4.x; v[1] = c4.y; v[2] = c4.z; v[3] = c4.w;
 				}
-			} else {
+				if (__any_sync(0xffffffffu, (d0.x | d1.x) != 0)) {
+					sA.bits = d0.x; sB.bits = d1.x;
+					sA.edge0_ok = flags0 & B2_DBK_LEFT_EDGE; sB.edge0_ok = flags1 & B2_DBK_LEFT_EDGE;
+					sA.edge0_bs4 = flags0 & B2_DBK_LEFT_BS4; sB.edge0_bs4 = flags1 & B2_DBK_LEFT_BS4;
+					sA.qpc = (int8_t)(d0.z & 255); sB.qpc = (int8_t)(d1.z & 255);
+					sA.qpn = (int8_t)(ql0 & 255); sB.qpn = (int8_t)(ql1 & 255);
+					dbk_line3<true>(v, tb, sA, sB, l16 >> 2);
+				}
+				if (need) {
 #pragma unroll
-				for (int i = 0; i < 20; ++i) v[i] = 0;
-#pragma unroll
-				for (int j = 0; j < 5; ++j) pair2(wA[j], wB[j], csel, v[2 + 2 * j], v[3 + 2 * j]);
-				if (carry_in) { v[2] = trow[comp]; v[3] = trow[2 + comp]; }
+					for (int j = 0; j < 5; ++j) reinterpret_cast<uint4 *>(trow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					uint4 e;
+					pair2(tw0, tw1, 0x5410u, e.x, e.y);
+					pair2(tw0, tw1, 0x7632u, e.z, e.w);
+					*reinterpret_cast<uint4 *>(R.y[l16 >> 2] + 4 + 4 * (l16 & 3)) = e;
+				}
 			}
-			if (drA.x | drB.x) {
-				sA.bits = drA.x; sB.bits = drB.x;
-				sA.edge0_ok = flagsA & B2_DBK_LEFT_EDGE; sB.edge0_ok = flagsB & B2_DBK_LEFT_EDGE;
-				sA.edge0_bs4 = flagsA & B2_DBK_LEFT_BS4; sB.edge0_bs4 = flagsB & B2_DBK_LEFT_BS4;
-				sA.qpn = (int8_t)((qlA >> qsel) & 255); sB.qpn = (int8_t)((qlB >> qsel) & 255);
-				dbk_line2(v, tb, sA, sB, luma ? line >> 2 : line >> 1, luma);
-			}
-			if (luma) {
+			// ---- chroma V pass: lane = line of one component (samples -2..7 in v[0..9]) ----------------------
+			const int qsel = 8 + 8 * comp;
+			{
+				uint32_t v[10];
+				const uint4 oa = R.own[sl][0][16 + cline], ob = R.own[sl][1][16 + cline];
+				const uint32_t w0[5] = {cl0, oa.x, oa.y, oa.z, oa.w}, w1[5] = {cl1, ob.x, ob.y, ob.z, ob.w};
 #pragma unroll
-				for (int j = 0; j < 5; ++j) reinterpret_cast<uint4 *>(trow)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-			} else {
+				for (int j = 0; j < 5; ++j) pair2(w0[j], w1[j], csel, v[2 * j], v[2 * j + 1]);
+				if (carry_in) { v[0] = crow[comp]; v[1] = crow[2 + comp]; }
+				if (__any_sync(0xffffffffu, (d0.x | d1.x) != 0)) {
+					sA.bits = d0.x; sB.bits = d1.x;
+					sA.edge0_ok = flags0 & B2_DBK_LEFT_EDGE; sB.edge0_ok = flags1 & B2_DBK_LEFT_EDGE;
+					sA.edge0_bs4 = flags0 & B2_DBK_LEFT_BS4; sB.edge0_bs4 = flags1 & B2_DBK_LEFT_BS4;
+					sA.qpc = (int8_t)((d0.z >> qsel) & 255); sB.qpc = (int8_t)((d1.z >> qsel) & 255);
+					sA.qpn = (int8_t)((ql0 >> qsel) & 255); sB.qpn = (int8_t)((ql1 >> qsel) & 255);
+					dbk_line3<false>(v, tb, sA, sB, cline >> 1);
+				}
+				if (need) {
 #pragma unroll
-				for (int i = 0; i < 10; ++i) trow[2 * i + comp] = v[2 + i];
-			}
-			if (lane < 24) {
-				uint32_t *d = (luma ? tl.y[lane >> 2] : tl.c[(lane - 16) >> 2]) + 4 + 4 * (lane & 3);
-				uint4 e;
-				pair2(twA, twB, 0x5410u, e.x, e.y);
-				pair2(twA, twB, 0x7632u, e.z, e.w);
-				*reinterpret_cast<uint4 *>(d) = e;
-			}
-		}
-		__syncwarp();
-		// ---- H pass: lanes 0..15 luma column, lanes 16..31 chroma byte column ---------------------------
-		if (drA.y | drB.y) {
-			const int col = lane & 15;
-			uint32_t v[20];
-			if (luma) {
-#pragma unroll
-				for (int i = 0; i < 20; ++i) v[i] = tl.y[i][4 + col];
-			} else {
-#pragma unroll
-				for (int i = 0; i < 20; ++i) v[i] = 0;
-#pragma unroll
-				for (int i = 0; i < 10; ++i) v[2 + i] = tl.c[i][4 + col];
-			}
-			sA.bits = drA.y; sB.bits = drB.y;
-			sA.edge0_ok = flagsA & B2_DBK_TOP_EDGE; sB.edge0_ok = flagsB & B2_DBK_TOP_EDGE;
-			sA.edge0_bs4 = flagsA & B2_DBK_TOP_BS4; sB.edge0_bs4 = flagsB & B2_DBK_TOP_BS4;
-			sA.qpn = (int8_t)((qtA >> qsel) & 255); sB.qpn = (int8_t)((qtB >> qsel) & 255);
-			dbk_line2(v, tb, sA, sB, col >> 2, luma);
-			if (luma) {
-#pragma unroll
-				for (int i = 1; i < 20; ++i) tl.y[i][4 + col] = v[i];
-			} else {
-#pragma unroll
-				for (int i = 1; i < 10; ++i) tl.c[i][4 + col] = v[2 + i];
+					for (int i = 0; i < 10; ++i) crow[2 * i + comp] = v[i];
+					if (l16 < 8) {
+						uint4 e;
+						pair2(tc0w, tc1w, 0x5410u, e.x, e.y);
+						pair2(tc0w, tc1w, 0x7632u, e.z, e.w);
+						*reinterpret_cast<uint4 *>(R.c[l16 >> 2] + 4 + 4 * (l16 & 3)) = e;
+					}
+				}
 			}
 			__syncwarp();
-		}
-		// ---- store what is final: columns -4..11 (or ..15 when nobody takes them over) of the lines, and
-		//      the rows above (luma -3..-1 by lanes 24..26, chroma -1 by lane 27) ---------------------------
-		if (lane < 24) {
-			const int li = lane < 16 ? lane : lane - 16;
-			const uint32_t *src = lane < 16 ? tl.y[4 + li] : tl.c[2 + li];
-			const size_t off = (lane < 16 ? (size_t)(mby * 16 + li) * W : (size_t)(mby * 8 + li) * W) + x * 16;
-			uint8_t *dA = (lane < 16 ? fyA : fcA) + off, *dB = (lane < 16 ? fyB : fcB) + off;
+			// ---- H pass: lane = luma column, then chroma byte column -----------------------------------------
+			if (__any_sync(0xffffffffu, (d0.y | d1.y) != 0)) {
+				sA.bits = d0.y; sB.bits = d1.y;
+				sA.edge0_ok = flags0 & B2_DBK_TOP_EDGE; sB.edge0_ok = flags1 & B2_DBK_TOP_EDGE;
+				sA.edge0_bs4 = flags0 & B2_DBK_TOP_BS4; sB.edge0_bs4 = flags1 & B2_DBK_TOP_BS4;
+				{
+					uint32_t v[20];
 #pragma unroll
-			for (int j = 0; j < 5; ++j) {
-				if ((j == 0 && x == 0) || (j == 4 && carry_out)) continue;
-				uint32_t wa, wb;
-				const uint4 e4 = *reinterpret_cast<const uint4 *>(src + 4 * j);
-				const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
-				unpair4(ev, wa, wb);
-				__stcg(reinterpret_cast<uint32_t *>(dA + 4 * (j - 1)), wa);
-				if (validB) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * (j - 1)), wb);
+					for (int i = 0; i < 20; ++i) v[i] = R.y[i][4 + l16];
+					sA.qpc = (int8_t)(d0.z & 255); sB.qpc = (int8_t)(d1.z & 255);
+					sA.qpn = (int8_t)(qt0 & 255); sB.qpn = (int8_t)(qt1 & 255);
+					dbk_line3<true>(v, tb, sA, sB, l16 >> 2);
+					if (need) {
+#pragma unroll
+						for (int i = 1; i < 20; ++i) R.y[i][4 + l16] = v[i];
+					}
+				}
+				{
+					uint32_t v[10];
+#pragma unroll
+					for (int i = 0; i < 10; ++i) v[i] = R.c[i][4 + l16];
+					sA.qpc = (int8_t)((d0.z >> qsel) & 255); sB.qpc = (int8_t)((d1.z >> qsel) & 255);
+					sA.qpn = (int8_t)((qt0 >> qsel) & 255); sB.qpn = (int8_t)((qt1 >> qsel) & 255);
+					dbk_line3<false>(v, tb, sA, sB, l16 >> 2);
+					if (need) {
+#pragma unroll
+						for (int i = 1; i < 10; ++i) R.c[i][4 + l16] = v[i];
+					}
+				}
+				__syncwarp();
 			}
-		} else if (lane < 28 && (topA || topB)) {
-			const bool tl_luma = lane < 27;
-			const int r = tl_luma ? lane - 27 : -1;                 // luma rows -3..-1, chroma row -1
-			const uint32_t *src = (tl_luma ? tl.y[4 + r] : tl.c[2 + r]) + 4;
-			const size_t off = (tl_luma ? (size_t)(mby * 16 + r) * W : (size_t)(mby * 8 + r) * W) + x * 16;
-			uint8_t *dA = (tl_luma ? fyA : fcA) + off, *dB = (tl_luma ? fyB : fcB) + off;
+			// ---- store what is final: columns -4..11 (or ..15 when nobody takes them over) of the macroblock's lines,
+			//      and the rows above it (luma -3..-1, chroma -1: lanes 0..3 of the half) --------------------------------
+			if (need) {
+				{
+					uint8_t *dA = fy0 + yline + x * 16, *dB = fy1 + yline + x * 16;
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				uint32_t wa, wb;
-				const uint4 e4 = *reinterpret_cast<const uint4 *>(src + 4 * j);
-				const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
-				unpair4(ev, wa, wb);
-				if (topA) __stcg(reinterpret_cast<uint32_t *>(dA + 4 * j), wa);
-				if (topB) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * j), wb);
+					for (int j = 0; j < 5; ++j) {
+						if ((j == 0 && x == 0) || (j == 4 && carry_out)) continue;
+						uint32_t wa, wb;
+						const uint4 e4 = *reinterpret_cast<const uint4 *>(trow + 4 * j);
+						const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+						unpair4(ev, wa, wb);
+						__stcg(reinterpret_cast<uint32_t *>(dA + 4 * (j - 1)), wa);
+						if (valid1) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * (j - 1)), wb);
+					}
+				}
+				{
+					// chroma: lane = (picture, line)
+					const int pic = l16 >> 3, cln = l16 & 7;
+					if (pic == 0 || valid1) {
+						const uint32_t *src = R.c[2 + cln];
+						uint8_t *d = (pic ? fc1 : fc0) + (size_t)(mby * 8 + cln) * W + x * 16;
+#pragma unroll
+						for (int j = 0; j < 5; ++j) {
+							if ((j == 0 && x == 0) || (j == 4 && carry_out)) continue;
+							uint32_t wa, wb;
+							const uint4 e4 = *reinterpret_cast<const uint4 *>(src + 4 * j);
+							const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+							unpair4(ev, wa, wb);
+							__stcg(reinterpret_cast<uint32_t *>(d + 4 * (j - 1)), pic ? wb : wa);
+						}
+					}
+				}
+				const bool top0 = flags0 & B2_DBK_TOP_EDGE, top1 = (flags1 & B2_DBK_TOP_EDGE) && valid1;
+				if (l16 < 4 && (top0 || top1)) {
+					const bool tl_luma = l16 < 3;
+					const int r = tl_luma ? l16 - 3 : -1;                 // luma rows -3..-1, chroma row -1
+					const uint32_t *src = (tl_luma ? R.y[4 + r] : R.c[2 + r]) + 4;
+					const size_t off = (tl_luma ? (size_t)(mby * 16 + r) * W : (size_t)(mby * 8 + r) * W) + x * 16;
+					uint8_t *dA = (tl_luma ? fy0 : fc0) + off, *dB = (tl_luma ? fy1 : fc1) + off;
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						uint32_t wa, wb;
+						const uint4 e4 = *reinterpret_cast<const uint4 *>(src + 4 * j);
+						const uint32_t ev[4] = {e4.x, e4.y, e4.z, e4.w};
+						unpair4(ev, wa, wb);
+						if (top0) __stcg(reinterpret_cast<uint32_t *>(dA + 4 * j), wa);
+						if (top1) __stcg(reinterpret_cast<uint32_t *>(dB + 4 * j), wb);
+					}
+				}
 			}
-		}
-		__syncwarp();
-		if (carry_out && lane < 24) {
-			uint32_t *rw = lane < 16 ? tl.y[4 + lane] : tl.c[2 + lane - 16];
-#pragma unroll
-			for (int i = 0; i < 4; ++i) rw[i] = rw[16 + i];      // (16-byte aligned both ways)
+			__syncwarp();
+			if (carry_out) {
+				*reinterpret_cast<uint4 *>(trow) = *reinterpret_cast<const uint4 *>(trow + 16);
+				if (l16 < 8) *reinterpret_cast<uint4 *>(R.c[2 + l16]) = *reinterpret_cast<const uint4 *>(R.c[2 + l16] + 16);
+			}
 		}
 		carry_in = carry_out;
-		done_to = x + 1;
-		if (((x + 1) & (B2_DBK2_PUBLISH_EVERY - 1)) == 0 || x + 1 == mb_w || !todo) sy.publish(x + 1, lane);
+		// progress of the pair's last row: macroblocks < n are done
+		const int n = has_r1 ? s - 1 : s + 1;
+		if (n > 0 && ((n & (B2_DBK3_PUBLISH_EVERY - 1)) == 0 || n == mb_w)) sy.publish(n, lane);
 		__syncwarp();
 	}
+	cp_async_wait<0>();
 }
 
-#ifndef B2_DBK2_WARPS
-#define B2_DBK2_WARPS 2
-#endif
-constexpr int DBK2_WARPS = B2_DBK2_WARPS;          // rows per CTA
-#ifndef B2_DBK2_WARPS_PER_SM
-#define B2_DBK2_WARPS_PER_SM 16
-#endif
-constexpr int DBK2_CTAS = B2_DBK2_WARPS_PER_SM / DBK2_WARPS;        // resident CTAs per SM (register budget: 16 warps of 128 registers)
-
-__global__ void __launch_bounds__(32 * DBK2_WARPS, DBK2_CTAS)
-h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
-	__shared__ DbkTile2 s_tile[DBK2_WARPS];
-	__shared__ DbkStage2 s_stage[DBK2_WARPS];
+__global__ void __launch_bounds__(32 * DBK3_WARPS, DBK3_CTAS)
+h264_deblock3_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
+	__shared__ DbkRow3 s_rows[DBK3_WARPS][2];
 	__shared__ DbkTables s_tb;
 	__shared__ int s_ticket;
-	__shared__ int s_prog[DBK2_WARPS];
+	__shared__ int s_prog[DBK3_WARPS];
 	for (int i = threadIdx.x; i < 52; i += blockDim.x) {
 		s_tb.alpha[i] = c_alpha[i];
 		s_tb.beta[i] = c_beta[i];
@@ -1888,55 +1989,32 @@ h264_deblock2_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int m
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int *ticket = sync_area;
 	int *progress = sync_area + 32;           // [pairs][mb_h]: macroblocks of the row that are final (rows read across CTAs only)
-	const int groups = (mb_h + DBK2_WARPS - 1) / DBK2_WARPS, pairs = (n_jobs + 1) / 2;
+	const int row_pairs = (mb_h + 1) / 2, groups = (row_pairs + DBK3_WARPS - 1) / DBK3_WARPS, pairs = (n_jobs + 1) / 2;
 	const int total = pairs * groups;
 	for (;;) {
 		__syncthreads();                       // the previous group is complete: s_ticket / s_prog may be reused
 		if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1);
-		if (threadIdx.x < DBK2_WARPS) s_prog[threadIdx.x] = 0;
+		if (threadIdx.x < DBK3_WARPS) s_prog[threadIdx.x] = 0;
 		__syncthreads();
 		const int t = s_ticket;
 		if (t >= total) return;
 		// group-major ticket order, as in h264_wave_kernel
-		const int j = t % pairs, mby = (t / pairs) * DBK2_WARPS + warp;
-		if (mby >= mb_h) continue;
+		const int j = t % pairs, rp = (t / pairs) * DBK3_WARPS + warp;
+		if (rp >= row_pairs) continue;
+		const int r0 = 2 * rp;
+		const bool has_r1 = r0 + 1 < mb_h;
+		const int last = has_r1 ? r0 + 1 : r0;
 		RowSync sy;
 		sy.sm_above = warp > 0 ? &s_prog[warp - 1] : nullptr;
-		sy.gl_above = (warp == 0 && mby > 0) ? progress + (size_t)j * mb_h + mby - 1 : nullptr;
+		sy.gl_above = (warp == 0 && r0 > 0) ? progress + (size_t)j * mb_h + r0 - 1 : nullptr;
 		sy.sm_my = &s_prog[warp];
-		sy.gl_my = (warp == DBK2_WARPS - 1 && mby + 1 < mb_h) ? progress + (size_t)j * mb_h + mby : nullptr;
+		sy.gl_my = (warp == DBK3_WARPS - 1 && last + 1 < mb_h) ? progress + (size_t)j * mb_h + last : nullptr;
 		sy.seen = 0;
-		sy.lead = B2_DBK2_LEAD;
+		sy.lead = 0;
 		sy.limit = mb_w;
-		const bool validB = 2 * j + 1 < n_jobs;
-		const H4Job jobA = jobs[2 * j], jobB = jobs[validB ? 2 * j + 1 : 2 * j];
-		for (int x0 = 0; x0 < mb_w; x0 += 32) {
-			// one pass over the chunk's strength records: which macroblocks need work, and everything the loop
-			// will want from the records goes to shared memory
-			const int mbx = x0 + lane;
-			DbkStage2 &sg = s_stage[warp];
-			uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
-			uint32_t ta = 0, tb = 0;
-			if (mbx < mb_w) {
-				const size_t mbi = (size_t)mby * mb_w + mbx;
-				ra = __ldg(reinterpret_cast<const uint4 *>(jobA.dbk + mbi));
-				if (validB) rb = __ldg(reinterpret_cast<const uint4 *>(jobB.dbk + mbi));
-				if (mby > 0) {
-					ta = __ldg(reinterpret_cast<const uint32_t *>(jobA.dbk + mbi - mb_w) + 2);
-					tb = __ldg(reinterpret_cast<const uint32_t *>(jobB.dbk + mbi - mb_w) + 2);
-				}
-			}
-			__syncwarp();                      // the previous chunk's readers are done
-			sg.rec[0][lane] = ra; sg.rec[1][lane] = rb;
-			sg.qp_top[0][lane] = ta; sg.qp_top[1][lane] = tb;
-			__syncwarp();
-			const bool need = (!((ra.z >> 24) & B2_DBK_OFF) && (ra.x | ra.y)) || (!((rb.z >> 24) & B2_DBK_OFF) && (rb.x | rb.y));
-			unsigned todo = __ballot_sync(0xffffffffu, need);
-			int done_to = x0;                  // macroblocks < done_to are final
-			deblock_chunk2(jobA, jobB, validB, s_tb, s_tile[warp], sg, mby, x0, todo, lane, sy, done_to);
-			const int end = min(x0 + 32, mb_w);
-			if (done_to < end) sy.publish(end, lane);
-		}
+		const bool valid1 = 2 * j + 1 < n_jobs;
+		const H4Job job0 = jobs[2 * j], job1 = jobs[valid1 ? 2 * j + 1 : 2 * j];
+		deblock_rows3(job0, job1, valid1, s_tb, s_rows[warp], r0, has_r1, lane, sy);
 	}
 }
 
@@ -2030,12 +2108,12 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 		if (ctas > cap) ctas = cap;
 		if (phase == 1) h264_wave_kernel<1><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 		else {
-			// batched launches pair the pictures up (two per warp); a single picture keeps the one-picture kernel
-			static const int dbk2 = getenv("B2_DBK2") ? atoi(getenv("B2_DBK2")) : 1;
-			if (dbk2 && n_jobs > 1) {
-				int ctas2 = ((n_jobs + 1) / 2) * ((mb_h + DBK2_WARPS - 1) / DBK2_WARPS);
-				if (ctas2 > 148 * 2 * DBK2_CTAS) ctas2 = 148 * 2 * DBK2_CTAS;
-				h264_deblock2_kernel<<<ctas2, 32 * DBK2_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
+			// batched launches pair the pictures up (two pictures and two rows per warp); a single picture keeps the one-picture kernel
+			static const bool one_picture = getenv("B2_DBK_ONE_PICTURE") != nullptr;     // (development: the scalar kernel for batched launches too)
+			if (!one_picture && n_jobs > 1) {
+				int ctas3 = ((n_jobs + 1) / 2) * (((mb_h + 1) / 2 + DBK3_WARPS - 1) / DBK3_WARPS);
+				if (ctas3 > 148 * 2 * DBK3_CTAS) ctas3 = 148 * 2 * DBK3_CTAS;
+				h264_deblock3_kernel<<<ctas3, 32 * DBK3_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 			} else {
 				h264_wave_kernel<2><<<ctas, 32 * WAVE_WARPS, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, area);
 			}

@@ -15,7 +15,7 @@ import re
 import subprocess
 import sys
 
-PHASE = [("h264_inter5_kernel", "inter"), ("h264_intra_sparse_kernel", "intra"), ("h264_deblock2_kernel", "deblock")]
+PHASE = [("h264_inter5_kernel", "inter"), ("h264_intra_sparse_kernel", "intra"), ("h264_deblock3_kernel", "deblock")]
 KEEP = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
