@@ -44,6 +44,9 @@ struct H4Job {
 // A picture with few intra macroblocks (P / B pictures) goes through the sparse intra kernel, which
 // orders macroblocks by per-macroblock flags; a mostly-intra picture through the row wavefront.
 __host__ __device__ inline bool h264_intra_sparse(int n_intra, int n_mbs) { return n_intra * 3 < n_mbs; }
+// The inter kernel fetches reference rows as whole 16-byte chunks: the chunk that holds the last bytes of a frame
+// pool's last row may be read 16 bytes past it (never used), so pools are allocated with this many spare bytes.
+constexpr size_t H4_POOL_TAIL = 256;
 // phase: 0 inter (MC + residual), 1 intra wavefront (dense pictures), 2 deblock wavefront,
 // 3 intra, sparse pictures
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h);

@@ -194,18 +194,23 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
 #define PACK4(a, b, c, d) ((uint32_t)((a) & 255) | ((uint32_t)((b) & 255) << 8) | ((uint32_t)((c) & 255) << 16) | ((uint32_t)((d) & 255) << 24))
 
 // (1,-5,20,20,-5,1) across window bytes c..c+5 for output columns c = 0..3 of a 12-byte window
+template <int BIAS = 0>
 __device__ __forceinline__ void hfilter4(const uint32_t pk[3], int out[4]) {
-	out[0] = dp4a_us(pk[0], PACK4(1, -5, 20, 20), dp4a_us(pk[1], PACK4(-5, 1, 0, 0), 0));
-	out[1] = dp4a_us(pk[0], PACK4(0, 1, -5, 20), dp4a_us(pk[1], PACK4(20, -5, 1, 0), 0));
-	out[2] = dp4a_us(pk[0], PACK4(0, 0, 1, -5), dp4a_us(pk[1], PACK4(20, 20, -5, 1), 0));
-	out[3] = dp4a_us(pk[0], PACK4(0, 0, 0, 1), dp4a_us(pk[1], PACK4(-5, 20, 20, -5), dp4a_us(pk[2], PACK4(1, 0, 0, 0), 0)));
+	out[0] = dp4a_us(pk[0], PACK4(1, -5, 20, 20), dp4a_us(pk[1], PACK4(-5, 1, 0, 0), BIAS));
+	out[1] = dp4a_us(pk[0], PACK4(0, 1, -5, 20), dp4a_us(pk[1], PACK4(20, -5, 1, 0), BIAS));
+	out[2] = dp4a_us(pk[0], PACK4(0, 0, 1, -5), dp4a_us(pk[1], PACK4(20, 20, -5, 1), BIAS));
+	out[3] = dp4a_us(pk[0], PACK4(0, 0, 0, 1), dp4a_us(pk[1], PACK4(-5, 20, 20, -5), dp4a_us(pk[2], PACK4(1, 0, 0, 0), BIAS)));
 }
 
 // vertical 6-tap on two packed 16-bit lanes; result lanes carry a +2560 bias
 __device__ __forceinline__ uint32_t vtap_packed(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
 	return (a + f) + 20u * (c + d) + 0x0A000A00u - 5u * (b + e);
 }
-__device__ __forceinline__ int vfinish(uint32_t lane16) { return clip255(((int)lane16 - 2560 + 16) >> 5); }
+// clip255((v + 16) >> 5) of both lanes at once (lanes carry v + 2560, and 2560 = 80 * 32): results in bytes 0 and 2
+__device__ __forceinline__ uint32_t vfinish2(uint32_t t) {
+	const uint32_t u = ((t + 0x00100010u) >> 5) & 0x07FF07FFu;
+	return __vimin_s16x2_relu(__vsub2(u, 0x00500050u), 0x00FF00FFu);
+}
 
 // ------------------------------------------------------------------------------------------------
 // inter kernel, strip form.  Work item = a vertical strip of one motion-compensation record: 8 (or 4)
@@ -232,6 +237,15 @@ __device__ __forceinline__ int frac_class(int fx, int fy) {
 	return 3;                       // b / s with h / m
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async16_ca(void *smem, const void *gmem) {      // through L1: neighbouring strips share sectors
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
 // ---- reference rows as packed words -------------------------------------------------------------------
 __device__ __noinline__ uint4 load_words_clamped(const uint8_t *__restrict__ row, int W, int x, int nwords) {
 	uint32_t out[4] = {0, 0, 0, 0};
@@ -249,27 +263,70 @@ __device__ __noinline__ uint4 load_chroma_clamped(const uint8_t *__restrict__ ro
 		if (i < nwords * 4) out[i >> 2] |= (uint32_t)__ldg(row + min(max((x >> 1) + (i >> 1), 0), cw - 1) * 2 + (i & 1)) << ((i & 3) * 8);
 	return make_uint4(out[0], out[1], out[2], out[3]);
 }
-// N words (N <= 4) of bytes x .. x + 4N - 1 of a row.  fast: x >= 0 and every aligned word touched is inside the row
-template <int N, bool CHROMA>
-__device__ __forceinline__ void load_words(const uint8_t *__restrict__ row, int W, int x, bool fast, uint32_t *out) {
-	if (fast) {
-		const uint8_t *p = row + x;
-		const uint32_t *a = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-		const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
-		uint32_t w[N + 1];
-#pragma unroll
-		for (int k = 0; k <= N; ++k) w[k] = __ldg(a + k);
-#pragma unroll
-		for (int k = 0; k < N; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], sh);
-	} else {
-		const uint4 v = CHROMA ? load_chroma_clamped(row, W, x, N) : load_words_clamped(row, W, x, N);
-		out[0] = v.x;
-		if (N > 1) out[1] = v.y;
-		if (N > 2) out[2] = v.z;
-		if (N > 3) out[3] = v.w;
-	}
-}
 __device__ __forceinline__ bool words_fast(int x, int n, int W) { return x >= 0 && (x & ~3) + 4 * (n + 1) <= W; }
+
+// Reference rows of a strip: N words (N <= 4) of bytes x .. x + 4N - 1 of rows y0, y0 + 1, ... (rows clamped into the
+// plane).  The ncu source view of the register-prefetch form (next row's LDGs issued one row ahead) had 30 % of the
+// kernel's stall samples on the first use of those loads: a row of work is shorter than a trip to L2 / HBM, and the
+// registers for a deeper prefetch are not there (96 per thread at 20 warps per SM).  Here the rows travel through a
+// per-lane ring in shared memory instead: the two 16-byte chunks that hold the window are copied asynchronously
+// (cp.async, I5_DEPTH - 1 rows ahead, no registers in flight, 2 requests per row instead of N + 1), and read back as two
+// 128-bit words from which the window is cut with selects and funnel shifts.  The chunk behind a row's last bytes
+// may belong to the next row or to the pool's spare tail (H4_POOL_TAIL): it is fetched, never used.
+// Strips whose window leaves the picture (fast == false; bucketed apart by the host) load clamped bytes as before.
+constexpr int I5_DEPTH = 4;
+template <int N, bool CHROMA>
+struct RowFetch {
+	const uint8_t *ref;
+	int W, H, x;
+	bool fast;
+	unsigned o;
+	uint4 *ring;            // this lane's entry of chunk 0 of slot 0; chunk c of slot s is 32 * (2 s + c) entries on
+	__device__ __forceinline__ RowFetch(const uint8_t *ref_, int W_, int H_, int x_, uint4 *ring_)
+	    : ref(ref_), W(W_), H(H_), x(x_), fast(words_fast(x_, N, W_)), o((unsigned)x_ & 15u), ring(ring_) {}
+	__device__ __forceinline__ const uint8_t *rowp(int yy) const { return ref + (size_t)min(max(yy, 0), H - 1) * W; }
+	// row yy is the k-th row of the strip
+	__device__ __forceinline__ void issue(int k, int yy, bool on) {
+		if (on && fast) {
+			const uint8_t *a = rowp(yy) + (x & ~15);
+			uint4 *d = ring + 64 * (k & (I5_DEPTH - 1));
+			cp_async16_ca(d, a);
+			cp_async16_ca(d + 32, a + 16);
+		}
+		cp_async_commit();
+	}
+	__device__ __forceinline__ void start(int y0, int total) {
+#pragma unroll
+		for (int i = 0; i < I5_DEPTH - 1; ++i) issue(i, y0 + i, i < total);
+	}
+	// asks for row k + I5_DEPTH - 1 (if the strip has one) and hands out row k
+	__device__ __forceinline__ void next(int k, int y0, int total, uint32_t *out) {
+		issue(k + I5_DEPTH - 1, y0 + k + I5_DEPTH - 1, k + I5_DEPTH - 1 < total);
+		if (fast) {
+			cp_async_wait<I5_DEPTH - 1>();
+			const uint4 *d = ring + 64 * (k & (I5_DEPTH - 1));
+			const uint4 c0 = d[0], c1 = d[32];
+			uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+			if (o & 8) {
+#pragma unroll
+				for (int j = 0; j <= N + 1; ++j) w[j] = w[j + 2];
+			}
+			if (o & 4) {
+#pragma unroll
+				for (int j = 0; j <= N; ++j) w[j] = w[j + 1];
+			}
+			const unsigned sh = (o & 3) * 8;
+#pragma unroll
+			for (int j = 0; j < N; ++j) out[j] = __funnelshift_r(w[j], w[j + 1], sh);
+		} else {
+			const uint4 v = CHROMA ? load_chroma_clamped(rowp(y0 + k), W, x, N) : load_words_clamped(rowp(y0 + k), W, x, N);
+			out[0] = v.x;
+			if (N > 1) out[1] = v.y;
+			if (N > 2) out[2] = v.z;
+			if (N > 3) out[3] = v.w;
+		}
+	}
+};
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
 __device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {
 	int d;
@@ -279,44 +336,38 @@ __device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {
 // four clipped horizontal half samples b = clip((b1 + 16) >> 5) of window words pk[0..2], packed
 __device__ __forceinline__ uint32_t hhalf4(const uint32_t pk[3]) {
 	int hb[4];
-	hfilter4(pk, hb);
-	return pack4(clip255((hb[0] + 16) >> 5), clip255((hb[1] + 16) >> 5), clip255((hb[2] + 16) >> 5), clip255((hb[3] + 16) >> 5));
+	hfilter4<16>(pk, hb);           // the rounding term rides in the accumulator
+	return pack4(clip255(hb[0] >> 5), clip255(hb[1] >> 5), clip255(hb[2] >> 5), clip255(hb[3] >> 5));
 }
 // four clipped vertical half samples from six rows split into even / odd byte lanes, packed
-__device__ __forceinline__ uint32_t vhalf4(const uint32_t E[6], const uint32_t O[6]) {
-	const uint32_t te = vtap_packed(E[0], E[1], E[2], E[3], E[4], E[5]), to = vtap_packed(O[0], O[1], O[2], O[3], O[4], O[5]);
-	return pack4(vfinish(te & 0xFFFFu), vfinish(to & 0xFFFFu), vfinish(te >> 16), vfinish(to >> 16));
+// (the six rows are a ring: row i of the window is entry (J + 1 + i) % 6, J = the entry written last)
+__device__ __forceinline__ uint32_t vhalf4(const uint32_t E[6], const uint32_t O[6], const int J) {
+	const uint32_t te = vtap_packed(E[(J + 1) % 6], E[(J + 2) % 6], E[(J + 3) % 6], E[(J + 4) % 6], E[(J + 5) % 6], E[J]);
+	const uint32_t to = vtap_packed(O[(J + 1) % 6], O[(J + 2) % 6], O[(J + 3) % 6], O[(J + 4) % 6], O[(J + 5) % 6], O[J]);
+	return __byte_perm(vfinish2(te), vfinish2(to), 0x6240);
 }
 
 // Luma prediction of a strip NQ words wide and h rows high at integer position (x, y) + fraction (fx, fy),
 // produced row by row: sink(r, words) is called for r = 0 .. h - 1 in order.  Classes 4 and 5 (the centre
 // sample j) exist for NQ == 1 only: their filter state would not fit the registers at 8 samples.
 template <int NQ, class Sink>
-__device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int h, Sink &&sink) {
+__device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, int H, int x, int y, int fx, int fy, int h, uint4 *ring, Sink &&sink) {
 	const int cls = frac_class(fx, fy);
 	const uint32_t M = 0x00FF00FFu;
-#define ROWP(yy) (ref + (size_t)min(max((yy), 0), H - 1) * W)
 	if (cls == 0) {
-		// (every class: the words of the next reference row are fetched before the current row is worked on)
-		const bool fast = words_fast(x, NQ, W);
-		uint32_t nx[NQ];
-		load_words<NQ, false>(ROWP(y), W, x, fast, nx);
+		RowFetch<NQ, false> f(ref, W, H, x, ring);
+		f.start(y, h);
 		for (int r = 0; r < h; ++r) {
 			uint32_t pw[NQ];
-#pragma unroll
-			for (int q = 0; q < NQ; ++q) pw[q] = nx[q];
-			if (r + 1 < h) load_words<NQ, false>(ROWP(y + r + 1), W, x, fast, nx);
+			f.next(r, y, h, pw);
 			sink(r, pw);
 		}
 	} else if (cls == 1) {
-		const bool fast = words_fast(x - 2, NQ + 2, W);
-		uint32_t nx[NQ + 2];
-		load_words<NQ + 2, false>(ROWP(y), W, x - 2, fast, nx);
+		RowFetch<NQ + 2, false> f(ref, W, H, x - 2, ring);
+		f.start(y, h);
 		for (int r = 0; r < h; ++r) {
 			uint32_t w[NQ + 2], pw[NQ];
-#pragma unroll
-			for (int q = 0; q < NQ + 2; ++q) w[q] = nx[q];
-			if (r + 1 < h) load_words<NQ + 2, false>(ROWP(y + r + 1), W, x - 2, fast, nx);
+			f.next(r, y, h, w);
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
 				uint32_t b = hhalf4(&w[q]);
@@ -326,19 +377,16 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 			sink(r, pw);
 		}
 	} else if (cls == 2) {
-		const bool fast = words_fast(x, NQ, W);
+		RowFetch<NQ, false> f(ref, W, H, x, ring);
 		uint32_t E[NQ][6], O[NQ][6];
 #pragma unroll
 		for (int q = 0; q < NQ; ++q)
 #pragma unroll
 			for (int j = 0; j < 6; ++j) E[q][j] = O[q][j] = 0;
-		uint32_t nx[NQ];
-		load_words<NQ, false>(ROWP(y - 2), W, x, fast, nx);
+		f.start(y - 2, h + 5);
 		for (int k = 0; k < h + 5; ++k) {
 			uint32_t w[NQ], pw[NQ];
-#pragma unroll
-			for (int q = 0; q < NQ; ++q) w[q] = nx[q];
-			if (k + 1 < h + 5) load_words<NQ, false>(ROWP(y - 1 + k), W, x, fast, nx);
+			f.next(k, y - 2, h + 5, w);
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -349,14 +397,14 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 			if (k < 5) continue;
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
-				uint32_t hw = vhalf4(E[q], O[q]);
+				uint32_t hw = vhalf4(E[q], O[q], 5);
 				if (fy != 2) hw = __vavgu4(fy == 1 ? (E[q][2] | (O[q][2] << 8)) : (E[q][3] | (O[q][3] << 8)), hw);
 				pw[q] = hw;
 			}
 			sink(k - 5, pw);
 		}
 	} else if (cls == 3) {
-		const bool fast = words_fast(x - 2, NQ + 2, W);
+		RowFetch<NQ + 2, false> f(ref, W, H, x - 2, ring);
 		const bool xo = fx == 3, yo = fy == 3;
 		uint32_t E[NQ][6], O[NQ][6], bq[NQ][4];
 #pragma unroll
@@ -366,13 +414,10 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 #pragma unroll
 			for (int j = 0; j < 4; ++j) bq[q][j] = 0;
 		}
-		uint32_t nx[NQ + 2];
-		load_words<NQ + 2, false>(ROWP(y - 2), W, x - 2, fast, nx);
+		f.start(y - 2, h + 5);
 		for (int k = 0; k < h + 5; ++k) {
 			uint32_t w[NQ + 2], pw[NQ];
-#pragma unroll
-			for (int q = 0; q < NQ + 2; ++q) w[q] = nx[q];
-			if (k + 1 < h + 5) load_words<NQ + 2, false>(ROWP(y - 1 + k), W, x - 2, fast, nx);
+			f.next(k, y - 2, h + 5, w);
 #pragma unroll
 			for (int q = 0; q < NQ; ++q) {
 #pragma unroll
@@ -387,14 +432,14 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 			if (k < 5) continue;
 			// output row r = k - 5: vertical half sample over rows r .. r + 5, b of row r + 2 + yo = k - 3 + yo
 #pragma unroll
-			for (int q = 0; q < NQ; ++q) pw[q] = __vavgu4(yo ? bq[q][1] : bq[q][0], vhalf4(E[q], O[q]));
+			for (int q = 0; q < NQ; ++q) pw[q] = __vavgu4(yo ? bq[q][1] : bq[q][0], vhalf4(E[q], O[q], 5));
 			sink(k - 5, pw);
 		}
 	} else if (NQ == 1) {
 		// centre sample j from unrounded horizontal intermediates (biased to unsigned 16 bit, two vertically
 		// adjacent rows per register) with dp2a down the column; cls 4: alone or averaged with b / s,
 		// cls 5: averaged with the vertical half sample h / m
-		const bool fast = words_fast(x - 2, 3, W);
+		RowFetch<3, false> f(ref, W, H, x - 2, ring);
 		const bool xo = fx == 3, yo = fy == 3, with_b = cls == 4 && fy != 2, with_h = cls == 5;
 		uint32_t PW[5][4], prevb[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0}, E[6], O[6];
 #pragma unroll
@@ -404,13 +449,10 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 #pragma unroll
 		for (int j = 0; j < 6; ++j) E[j] = O[j] = 0;
 		const uint32_t T0 = (1u & 255u) | ((uint32_t)(-5 & 255) << 8), T1 = 20u | (20u << 8), T2 = (uint32_t)(-5 & 255) | (1u << 8);
-		uint32_t nx[3];
-		load_words<3, false>(ROWP(y - 2), W, x - 2, fast, nx);
+		f.start(y - 2, h + 5);
 		for (int k = 0; k < h + 5; ++k) {
 			uint32_t w[3];
-#pragma unroll
-			for (int q = 0; q < 3; ++q) w[q] = nx[q];
-			if (k + 1 < h + 5) load_words<3, false>(ROWP(y - 1 + k), W, x - 2, fast, nx);
+			f.next(k, y - 2, h + 5, w);
 			int hb[4];
 			hfilter4(w, hb);
 #pragma unroll
@@ -444,31 +486,27 @@ __device__ __forceinline__ void i5_luma(const uint8_t *__restrict__ ref, int W, 
 			}
 			uint32_t pw = pack4(jv[0], jv[1], jv[2], jv[3]);
 			if (with_b) pw = __vavgu4(yo ? bq[1] : bq[0], pw);
-			if (with_h) pw = __vavgu4(vhalf4(E, O), pw);
+			if (with_h) pw = __vavgu4(vhalf4(E, O, 5), pw);
 			sink(k - 5, &pw);
 		}
 	}
-#undef ROWP
 }
 
 // Chroma prediction (eighth-sample bilinear, 16-bit lanes): NQ words (Cb Cr Cb Cr) per row, `rows` rows, at
 // byte column xb (even) / chroma row cy of the picture
 template <int NQ, class Sink>
-__device__ __forceinline__ void i5_chroma(const uint8_t *__restrict__ refc, int W, int CH, int xb, int cy, int mvx, int mvy, int rows, Sink &&sink) {
+__device__ __forceinline__ void i5_chroma(const uint8_t *__restrict__ refc, int W, int CH, int xb, int cy, int mvx, int mvy, int rows, uint4 *ring, Sink &&sink) {
 	const uint32_t M = 0x00FF00FFu;
 	const uint32_t cfx = mvx & 7, cfy = mvy & 7;
 	const int x = xb + (mvx >> 3) * 2, y = cy + (mvy >> 3);
-	const bool fast = words_fast(x, NQ + 1, W);
+	RowFetch<NQ + 1, true> f(refc, W, CH, x, ring);
 	uint32_t pcb[NQ], pcr[NQ];
 #pragma unroll
 	for (int q = 0; q < NQ; ++q) pcb[q] = pcr[q] = 0;
-	uint32_t nx[NQ + 1];
-	load_words<NQ + 1, true>(refc + (size_t)min(max(y, 0), CH - 1) * W, W, x, fast, nx);
+	f.start(y, rows + 1);
 	for (int k = 0; k <= rows; ++k) {
 		uint32_t w[NQ + 1], pw[NQ];
-#pragma unroll
-		for (int q = 0; q < NQ + 1; ++q) w[q] = nx[q];
-		if (k < rows) load_words<NQ + 1, true>(refc + (size_t)min(max(y + k + 1, 0), CH - 1) * W, W, x, fast, nx);
+		f.next(k, y, rows + 1, w);
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) {
 			const uint32_t a = w[q], b = __funnelshift_r(w[q], w[q + 1], 16);
@@ -493,28 +531,28 @@ constexpr int I5_QUEUE = 256;         // queue entries per warp: 32 lanes x (up 
 
 template <int NQ>
 __device__ __forceinline__ void i5_first_list(const uint8_t *__restrict__ ref, uint8_t *dst_y, uint8_t *dst_c, int W, int H, int px0, int py0,
-                                              int cyp, int mvx, int mvy, int h) {
+                                              int cyp, int mvx, int mvy, int h, uint4 *ring) {
 	// first list of a bi-predicted strip: straight to the destination, the second list is combined with it
-	i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, [&](int r, const uint32_t *pw) {
+	i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, ring, [&](int r, const uint32_t *pw) {
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(dst_y + (size_t)(py0 + r) * W + px0 + 4 * q) = pw[q];
 	});
-	i5_chroma<NQ>(ref + (size_t)W * H, W, H >> 1, px0, cyp, mvx, mvy, h / 2, [&](int r, const uint32_t *pw) {
+	i5_chroma<NQ>(ref + (size_t)W * H, W, H >> 1, px0, cyp, mvx, mvy, h / 2, ring, [&](int r, const uint32_t *pw) {
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint32_t *>(dst_c + (size_t)(cyp + r) * W + px0 + 4 * q) = pw[q];
 	});
 }
 
 template <int NQ>
-__device__ __forceinline__ void i5_park_luma(const uint8_t *__restrict__ ref, int W, int H, int px0, int py0, int mvx, int mvy, int h, uint32_t *rows) {
-	i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, [&](int r, const uint32_t *pw) {
+__device__ __forceinline__ void i5_park_luma(const uint8_t *__restrict__ ref, int W, int H, int px0, int py0, int mvx, int mvy, int h, uint32_t *rows, uint4 *ring) {
+	i5_luma<NQ>(ref, W, H, px0 + (mvx >> 2), py0 + (mvy >> 2), mvx & 3, mvy & 3, h, ring, [&](int r, const uint32_t *pw) {
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) rows[(r * NQ + q) * I5_THREADS] = pw[q];
 	});
 }
 template <int NQ>
-__device__ __forceinline__ void i5_park_chroma(const uint8_t *__restrict__ refc, int W, int CH, int px0, int cyp, int mvx, int mvy, int rows_n, uint32_t *rows) {
-	i5_chroma<NQ>(refc, W, CH, px0, cyp, mvx, mvy, rows_n, [&](int r, const uint32_t *pw) {
+__device__ __forceinline__ void i5_park_chroma(const uint8_t *__restrict__ refc, int W, int CH, int px0, int cyp, int mvx, int mvy, int rows_n, uint32_t *rows, uint4 *ring) {
+	i5_chroma<NQ>(refc, W, CH, px0, cyp, mvx, mvy, rows_n, ring, [&](int r, const uint32_t *pw) {
 #pragma unroll
 		for (int q = 0; q < NQ; ++q) rows[(r * NQ + q) * I5_THREADS] = pw[q];
 	});
@@ -571,6 +609,10 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	                       mc.o[0][0] | mc.o[0][1] | mc.o[0][2] | mc.o[1][0] | mc.o[1][1] | mc.o[1][2]);      // default prediction for whatever lists are used
 	uint32_t *rows = &s_rows[0][tid];
 	int16_t *rs = s_rs[tid];
+	// the reference-row ring of the warp's lanes (RowFetch) lies over the warp's residual scratch: interpolation and the
+	// residual phases that use the scratch are separated by __syncwarp()
+	static_assert(sizeof(uint4) * 64 * I5_DEPTH <= sizeof(int16_t) * 66 * 32, "ring fits the warp's scratch");
+	uint4 *ring = reinterpret_cast<uint4 *>(s_rs[tid & ~31]) + lane;
 	uint16_t *queue = s_queue[warp];
 	const unsigned lt_mask = (1u << lane) - 1;
 	const uint8_t *refl = job.frames + job.frame_bytes * mc.ref_frame[lastl];
@@ -580,15 +622,15 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	if (MODE != 2) {
 		if (bi && h) {
 			const uint8_t *ref0 = job.frames + job.frame_bytes * mc.ref_frame[0];
-			if (wide) i5_first_list<2>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
-			else i5_first_list<1>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h);
+			if (wide) i5_first_list<2>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h, ring);
+			else i5_first_list<1>(ref0, dst_y, dst_c, W, H, px0, py0, cyp, mc.mv[0][0], mc.mv[0][1], h, ring);
 		}
 		if (first_pass) return;
 	}
 	// ---- luma: prediction of the (last) list, parked -------------------------------------------------------
 	if (h) {
-		if (wide) i5_park_luma<2>(refl, W, H, px0, py0, mvx, mvy, h, rows);
-		else i5_park_luma<1>(refl, W, H, px0, py0, mvx, mvy, h, rows);
+		if (wide) i5_park_luma<2>(refl, W, H, px0, py0, mvx, mvy, h, rows, ring);
+		else i5_park_luma<1>(refl, W, H, px0, py0, mvx, mvy, h, rows, ring);
 	}
 	if (bi || !plain_w) {
 		for (int r = 0; r < h; ++r)
@@ -676,8 +718,8 @@ h264_inter5_kernel(const H4Job *__restrict__ jobs) {
 	// ---- chroma: nq words (Cb Cr Cb Cr) per row, h / 2 rows ------------------------------------------------------
 	const int hc = h / 2;
 	if (h) {
-		if (wide) i5_park_chroma<2>(refl + luma_size, W, H >> 1, px0, cyp, mvx, mvy, hc, rows);
-		else i5_park_chroma<1>(refl + luma_size, W, H >> 1, px0, cyp, mvx, mvy, hc, rows);
+		if (wide) i5_park_chroma<2>(refl + luma_size, W, H >> 1, px0, cyp, mvx, mvy, hc, rows, ring);
+		else i5_park_chroma<1>(refl + luma_size, W, H >> 1, px0, cyp, mvx, mvy, hc, rows, ring);
 	}
 	if (bi || !plain_w) {
 		for (int r = 0; r < hc; ++r)
@@ -1525,11 +1567,6 @@ h264_wave_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h,
 // |difference| has the bit set exactly when the test holds) and applied by masking the clipping bounds, so the
 // filter has no branch except the bS 4 case.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t vneg2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
 __device__ __forceinline__ uint32_t bits_mask(uint32_t bits) { return bits - (bits >> 15); }     // 0x8000 per lane -> 0x7fff per lane

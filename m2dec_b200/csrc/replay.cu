@@ -65,7 +65,7 @@ extern "C" int b2_replay_create(int cuda_device, int codec, int width, int heigh
 	memset(&r->stats, 0, sizeof(r->stats));
 	r->lane_len.assign(lanes, 0);
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-	B2_CUDA_OK(cudaMalloc(&r->frames, r->frame_bytes * pool_frames * lanes));
+	B2_CUDA_OK(cudaMalloc(&r->frames, r->frame_bytes * pool_frames * lanes + H4_POOL_TAIL));
 	B2_CUDA_OK(cudaMemset(r->frames, 0, r->frame_bytes * pool_frames * lanes));
 	// default: one group.  Measured on B200 (64 and 128 lanes of 1080p): 2 / 4 / 8 groups took
 	// 1.04x / 1.15x / 1.19x and 0.99x / 1.09x / 1.26x the time of one group, and no better with the

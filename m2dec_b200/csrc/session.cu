@@ -171,7 +171,7 @@ static int session_build(b2_session *s) {
 		// waited for by host threads that have nothing else to do meanwhile: block, do not spin
 		B2_CUDA_OK(cudaEventCreateWithFlags(&s->copy_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
 	}
-	if (cache_get(s->dev, false, s->frame_bytes * s->nframes, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
+	if (cache_get(s->dev, false, s->frame_bytes * s->nframes + H4_POOL_TAIL, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
 	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * s->nframes, s->stream));
 	if (cache_get(s->dev, false, h264_sync_bytes(1, s->width / 16, s->height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
 	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming | cudaEventBlockingSync));

@@ -18,6 +18,7 @@ ap.add_argument("--lanes", type=int, default=16)
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--runs", type=int, default=2)
 ap.add_argument("--distinct", type=int, default=0, help="number of distinct streams (0 = one per lane); the others are repeats: shorter preparation for kernel A/B runs")
+ap.add_argument("--threads", type=int, default=os.cpu_count() or 1, help="host threads that write and load the streams (1 under ncu)")
 a = ap.parse_args()
 
 
@@ -35,7 +36,7 @@ def stream(seed):
 rp = m2dec_b200.Replay(a.codec, bench.MBW * 16, bench.MBH * 16, a.lanes, pool_frames=18 if a.codec == "h264" else 4)
 from concurrent.futures import ThreadPoolExecutor
 seeds = sorted({100 + (lane % a.distinct if a.distinct else lane) for lane in range(a.lanes)})
-with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+with ThreadPoolExecutor(a.threads) as ex:
     _cache = dict(zip(seeds, ex.map(stream, seeds)))
 
 
@@ -44,7 +45,7 @@ def _load(lane):
     assert n == a.frames, (n, a.frames)
 
 
-with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+with ThreadPoolExecutor(a.threads) as ex:
     list(ex.map(_load, range(a.lanes)))
 for _ in range(a.runs):
     rp.run(timed=True)
