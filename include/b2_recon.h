@@ -91,7 +91,7 @@ typedef struct {
 	uint32_t mc_idx;        /* first motion-compensation record of this MB                        */
 	uint8_t mc_cnt;
 	uint8_t intra_avail_c;  /* availability mask the chroma predictor received (differs from intra_avail only for a no-residual Intra4x4 MB under constrained_intra_pred, h264.cpp:3281 vs 3292) */
-	uint8_t reserved[2];
+	uint16_t nnz4x4;        /* bit 4 * y + x: luma 4x4 block (x, y) counts as "has coefficients" in the deblocking-strength derivation (the parse's total_coeff / coded_block_flag state as str_previous_coef sees it, h264.cpp:7119-7322); used when bs_on_device is set */
 	uint8_t i4_modes[8];    /* Intra4x4 (16 nibbles) / Intra8x8 (4 nibbles) prediction modes, block k in nibble k */
 } b2_h264_mb;               /* 32 bytes */
 
@@ -133,8 +133,10 @@ typedef struct {
 	int8_t qp_y, qp_cb, qp_cr;   /* as the reference stores them for the filter (I_PCM: 0 and qpc - qp, h264.cpp:4749-4751) */
 	uint8_t flags;
 	int8_t alpha_off, beta_off;  /* FilterOffsetA / FilterOffsetB (= 2 * slice_*_offset_div2)          */
-	uint8_t reserved[2];
+	uint8_t bs_mode;             /* bs_on_device: bit 3 = the macroblock belongs to a B slice; bits 0..2 = which of its edges (0 macroblock edges, 1 centre edges, 2 other inner edges) take the reference's reduced same-picture comparison (enum below) */
+	uint8_t reserved;
 } b2_h264_dbk;              /* 16 bytes */
+enum { B2_BS_REDUCED_MB_EDGE = 0x01, B2_BS_REDUCED_CENTRE = 0x02, B2_BS_REDUCED_INNER = 0x04, B2_BS_B_SLICE = 0x08 };
 
 typedef struct {
 	int32_t mb_w, mb_h;
@@ -159,6 +161,11 @@ typedef struct {
 	 * is one item per strip for its last (or only) list, class = that list's, which combines with the
 	 * first pass, adds the residual and stores.  Both parts are sorted by (class, height, edge).      */
 	uint32_t n_items_first;
+	/* SURVEY.md 8f rank 2.  != 0: bs_v / bs_h and the BS4 flags of the b2_h264_dbk records are NOT filled in; the
+	 * device derives them (h264_bs_kernel) from the motion records, b2_h264_mb.nnz4x4 and b2_h264_dbk.bs_mode, as
+	 * the reference's parse does (store_info_inter*, str_mv_calc*, str_previous_coef: h264.cpp:7119-7322, 7451-7604,
+	 * 8796-9400).  qp_*, alpha_off / beta_off and the flags B2_DBK_OFF / LEFT_EDGE / TOP_EDGE always come from the host. */
+	uint32_t bs_on_device;
 } b2_h264_picture;
 
 /* ------------------------------------------------------------------------------------ */
@@ -191,6 +198,10 @@ int b2_context_release(void *ctx);
 /* set_frames() a few frames more than get_info() asks for lets the application collect digests a few        */
 /* pictures late without ever waiting for a hash.                                           */
 int b2_context_set_md5(void *ctx, int on);
+/* H.264 deblocking strengths: by default the front end leaves them to the device        */
+/* (b2_h264_picture.bs_on_device) whenever nobody reads the records on the host; on != 0 makes it derive them   */
+/* itself, as it does for a picture tap.  Call after init(), before the first decode_picture().               */
+int b2_context_set_host_strengths(void *ctx, int on);
 int b2_context_frame_md5(void *ctx, const m2d_frame_t *frame, uint8_t digest[16]);
 
 /* ------------------------------------------------------------------------------------ */

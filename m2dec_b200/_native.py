@@ -69,6 +69,7 @@ lib.b2_context_set_tap.argtypes = [C.c_void_p, TAP_CB, C.c_void_p, C.c_int]
 lib.b2_context_set_device.argtypes = [C.c_void_p, C.c_int]
 lib.b2_context_release.argtypes = [C.c_void_p]
 lib.b2_context_set_md5.argtypes = [C.c_void_p, C.c_int]
+lib.b2_context_set_host_strengths.argtypes = [C.c_void_p, C.c_int]
 lib.b2_context_frame_md5.argtypes = [C.c_void_p, C.POINTER(FrameT), C.c_void_p]
 lib.b2_device_count.restype = C.c_int
 lib.b2_host_alloc.argtypes = [C.c_size_t, C.c_int]

@@ -40,6 +40,7 @@ struct H4Job {
 	int32_t dst, mb_w, mb_h, n_intra;
 	const uint32_t *items;      // b2_h264_picture.items
 	uint32_t n_items, n_first;  // b2_h264_picture.n_items / n_items_first
+	uint32_t derive_bs, pad_;   // b2_h264_picture.bs_on_device
 };
 // A picture with few intra macroblocks (P / B pictures) goes through the sparse intra kernel, which
 // orders macroblocks by per-macroblock flags; a mostly-intra picture through the row wavefront.
@@ -48,13 +49,13 @@ __host__ __device__ inline bool h264_intra_sparse(int n_intra, int n_mbs) { retu
 // pool's last row may be read 16 bytes past it (never used), so pools are allocated with this many spare bytes.
 constexpr size_t H4_POOL_TAIL = 256;
 // phase: 0 inter (MC + residual), 1 intra wavefront (dense pictures), 2 deblock wavefront,
-// 3 intra, sparse pictures
+// 3 intra, sparse pictures, 4 deblocking strengths (pictures with b2_h264_picture.bs_on_device: every job of the launch)
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h);
 // max_items: largest n_items among the jobs (phase 0 only)
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
                       uint32_t max_items = 0, uint32_t max_first = 0);
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense,
-                bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first = 0);
+                bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first = 0, bool derive_bs = false);
 
 // md5.cu: MD5 of a cropped window of n frames (one thread per frame); d_slots / d_out are device pointers
 int md5_pictures(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, const int *d_slots, int n, int stride, int rows, int left, int top, int w, int h,

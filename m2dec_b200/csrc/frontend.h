@@ -53,6 +53,10 @@ public:
 	int fetch(int idx, uint8_t *luma, uint8_t *chroma);
 	void release();
 	bool device_off() const { return device_off_; }
+	bool has_tap() const { return tap_ != nullptr; }
+	// b2_context_set_host_strengths: the H.264 front end derives the deblocking strengths itself
+	void set_host_bs(bool on) { host_bs_ = on; }
+	bool host_bs() const { return host_bs_; }
 	const b2_session *session() const { return sess_; }
 	// true once a CUDA session could not be created: the decoder then refuses to go on
 	bool dead() const { return dead_; }
@@ -66,6 +70,7 @@ private:
 	int codec_, width_, height_, nframes_;
 	int n_host_;
 	uint8_t *host_luma_[64], *host_chroma_[64];
+	bool host_bs_ = false;
 	bool md5_;
 	int md5_stride_, md5_left_, md5_top_, md5_w_, md5_h_;
 };

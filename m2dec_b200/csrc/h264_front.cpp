@@ -757,6 +757,11 @@ private:
 		coef_used_ = 0;
 		n_intra_ = 0;
 		any_deblock_ = false;
+		// Deblocking strengths: derived on the device from the motion records unless someone looks at
+		// the records on the host -- a picture tap (the CPU oracle of tests/, bench.py's capture for the kernel replay),
+		// parse-only runs -- or the application asked for it (b2_context_set_host_strengths; B2_HOST_BS=1 for A/B runs).
+		static const bool env_host_bs = getenv("B2_HOST_BS") != nullptr;
+		host_bs_ = env_host_bs || backend.host_bs() || backend.has_tap() || backend.device_off();
 		slice_num_ = -1;
 		mb_addr_ = 0;
 		pic_open_ = true;
@@ -785,6 +790,7 @@ private:
 		for (const auto &b : items_) items_all_.insert(items_all_.end(), b.begin(), b.end());
 		p.items = items_all_.data();
 		p.n_items = (uint32_t)items_all_.size();
+		p.bs_on_device = host_bs_ ? 0u : 1u;
 		backend.submit(B2_CODEC_H264, &p);
 		pic_open_ = false;
 		// reference marking (8.2.5) and DPB insertion (h264.cpp:10840-10873, 11036-11045)
@@ -1724,11 +1730,23 @@ private:
 		}
 		d.alpha_off = (int8_t)h.alpha_off;
 		d.beta_off = (int8_t)h.beta_off;
+		// what the device needs to derive the strengths itself (b2_h264_picture.bs_on_device)
+		const uint8_t *nnz = ctx_.nnz_of(mbx, mby);
+		{
+			unsigned nzm = 0;
+			for (int i = 0; i < 16; ++i) nzm |= (unsigned)(nnz[i] != 0) << i;
+			mbs_[(size_t)mby * mb_w_ + mbx].nnz4x4 = (uint16_t)nzm;
+			d.bs_mode = (uint8_t)((bs_reduced_ & 7) | (bslice_ ? B2_BS_B_SLICE : 0));
+		}
 		if (h.disable_deblock == 1) { d.flags = B2_DBK_OFF; return; }
 		any_deblock_ = true;
-		const uint8_t *nnz = ctx_.nnz_of(mbx, mby);
 		bool left_ok = mbx > 0 && (h.disable_deblock == 0 || ctx_.mb_avail(mbx - 1, mby, slice_num_));
 		bool top_ok = mby > 0 && (h.disable_deblock == 0 || ctx_.mb_avail(mbx, mby - 1, slice_num_));
+		if (!host_bs_) {
+			if (left_ok) d.flags |= B2_DBK_LEFT_EDGE;
+			if (top_ok) d.flags |= B2_DBK_TOP_EDGE;
+			return;
+		}
 		uint32_t bsv = 0, bsh = 0;
 		if (intra) {
 			// inner edges bS 3; MB edges bS 4 (flagged, stored as 3)
@@ -1922,6 +1940,7 @@ private:
 	bool bslice_ = false, direct_8x8_inference_ = true;
 	bool cabac_ = false;
 	int bs_reduced_ = 0;        // see set_shape
+	bool host_bs_ = true;       // this picture's deblocking strengths are derived here, not on the device (begin_picture)
 	int last_dqp_ = 0;          // mb_qp_delta of the previous macroblock in decoding order (CABAC ctxIdxInc)
 	CabacSyntax<CabacDec> cs_;
 	struct { int mode, denom[2]; int8_t w[2][32][3], o[2][32][3]; } wt_;   // mode 0 default, 1 explicit, 2 implicit

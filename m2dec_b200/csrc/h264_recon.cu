@@ -2104,6 +2104,140 @@ h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, i
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Deblocking strengths on the device (reference: store_info_inter*, str_mv_calc*,
+// str_previous_coef, h264.cpp:7119-7322, 7451-7604, 8796-9400, which run inside the parse).  One warp per
+// macroblock: the 4x4 motion field of the macroblock, of the column to its left and of the row above it is
+// rebuilt from the motion records (lanes 0..15 / 16..19 / 20..23 look their block up), then lane
+// (direction, edge, segment) = (l >> 4, (l >> 2) & 3, l & 3) compares the two blocks its segment separates:
+//   either block has coefficients                                          -> 2
+//   P slice: other picture, or a vector component differs by >= 4          -> 1
+//   B slice: other pictures or number of vectors -> 1; the vectors that point to the same pictures compared,
+//            where both lists of both blocks name ONE picture "straight" and "crosswise" -- except on the edges the
+//            reference compares only straight (b2_h264_dbk.bs_mode: a deviation from 8.7.2.1 that decides pixels)
+//   intra macroblock: 3 everywhere, macroblock edges flagged bS 4
+// and two ballots spread into the 2-bit fields of the record.  The host supplies what only the parse knows:
+// nnz4x4, bs_mode, QPs, offsets and which macroblock edges are filtered at all.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bs_far(uint32_t a, uint32_t b) {
+	const int dx = (int)(int16_t)(a & 0xffff) - (int)(int16_t)(b & 0xffff), dy = (int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16);
+	return (unsigned)(dx + 3) > 6u || (unsigned)(dy + 3) > 6u;
+}
+// Morton spread: bit i of the low 16 bits -> bit 2 i
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+	x &= 0xffffu;
+	x = (x | (x << 8)) & 0x00ff00ffu;
+	x = (x | (x << 4)) & 0x0f0f0f0fu;
+	x = (x | (x << 2)) & 0x33333333u;
+	x = (x | (x << 1)) & 0x55555555u;
+	return x;
+}
+constexpr int BS_WARPS = 8;
+struct BsField {            // blocks (x, y), x, y = -1 .. 3, at index (y + 1) * 5 + x + 1
+	uint32_t mv[2][25];
+	int16_t ref[25];        // list 0 picture in the low byte, list 1 in the high byte (frame-pool indices, -1 = unused)
+};
+
+__global__ void __launch_bounds__(32 * BS_WARPS)
+h264_bs_kernel(const H4Job *__restrict__ jobs, int mb_w, int n_mbs) {
+	__shared__ BsField s_f[BS_WARPS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int mb = blockIdx.x * BS_WARPS + warp;
+	if (mb >= n_mbs) return;
+	const H4Job job = jobs[blockIdx.y];
+	if (!job.derive_bs) return;
+	b2_h264_dbk *rec = const_cast<b2_h264_dbk *>(job.dbk) + mb;
+	const uint4 d = *reinterpret_cast<const uint4 *>(rec);
+	int flags = (d.z >> 24) & 255;
+	if (flags & B2_DBK_OFF) return;
+	const int mode = (d.w >> 16) & 255;
+	const bool left_ok = flags & B2_DBK_LEFT_EDGE, top_ok = flags & B2_DBK_TOP_EDGE;
+	const b2_h264_mb *cur = job.mbs + mb;
+	const bool t8 = cur->flags & B2_H4_T8x8;
+	uint32_t bsv, bsh;
+	if (cur->type != B2_H4_INTER) {
+		bsv = bsh = 0xffffff00u;
+		if (left_ok) { bsv |= 0xffu; flags |= B2_DBK_LEFT_BS4; }
+		if (top_ok) { bsh |= 0xffu; flags |= B2_DBK_TOP_BS4; }
+	} else {
+		const int mbx = mb % mb_w;
+		const b2_h264_mb *left = left_ok ? cur - 1 : nullptr, *top = top_ok ? cur - mb_w : nullptr;
+		const bool left_inter = left && left->type == B2_H4_INTER, top_inter = top && top->type == B2_H4_INTER;
+		(void)mbx;
+		BsField &f = s_f[warp];
+		// ---- the motion field: every lane looks up the record that covers its block --------------------------
+		{
+			const b2_h264_mb *src = nullptr;
+			int x = 0, y = 0, at = 0;
+			if (lane < 16) { src = cur; x = lane & 3; y = lane >> 2; at = (y + 1) * 5 + x + 1; }
+			else if (lane < 20) { if (left_inter) src = left; x = 3; y = lane - 16; at = (y + 1) * 5; }
+			else if (lane < 24) { if (top_inter) src = top; x = lane - 20; y = 3; at = x + 1; }
+			if (src) {
+				const b2_h264_mc *mc = job.mcs + src->mc_idx;
+				const int n = src->mc_cnt;
+				uint32_t m0 = 0, m1 = 0;
+				int r01 = -1;
+				for (int i = 0; i < n; ++i) {
+					const int pos = mc[i].pos, size = mc[i].size;
+					const int x4 = pos & 3, y4 = pos >> 2, w4 = size & 15, h4 = size >> 4;
+					if (x >= x4 && x < x4 + w4 && y >= y4 && y < y4 + h4) {
+						const uint2 v = *reinterpret_cast<const uint2 *>(mc[i].mv);
+						m0 = v.x; m1 = v.y;
+						r01 = (int)(uint8_t)mc[i].ref_frame[0] | ((int)(uint8_t)mc[i].ref_frame[1] << 8);
+						break;
+					}
+				}
+				f.mv[0][at] = m0; f.mv[1][at] = m1; f.ref[at] = (int16_t)r01;
+			}
+		}
+		__syncwarp();
+		// ---- one pair of blocks per lane ------------------------------------------------------------------------
+		const int dir = lane >> 4, e = (lane >> 2) & 3, sg = lane & 3;
+		const int bx = dir ? sg : e, by = dir ? e : sg;                      // the block on the right of / below the edge
+		const int ib = (by + 1) * 5 + bx + 1, ia = dir ? ib - 5 : ib - 1;
+		const unsigned nzc = cur->nnz4x4;
+		bool nzb = (nzc >> (by * 4 + bx)) & 1, nza;
+		int bs;
+		bool usable = true, other_intra = false;
+		if (e == 0) {
+			const b2_h264_mb *o = dir ? top : left;
+			usable = o != nullptr;
+			other_intra = usable && o->type != B2_H4_INTER;
+			nza = usable && !other_intra && ((o->nnz4x4 >> (dir ? 12 + sg : sg * 4 + 3)) & 1);
+		} else {
+			nza = (nzc >> (dir ? (by - 1) * 4 + bx : by * 4 + bx - 1)) & 1;
+		}
+		if (!usable) bs = 0;
+		else if (other_intra) bs = 3;
+		else if (nza | nzb) bs = 2;
+		else {
+			const int ra = f.ref[ia], rb = f.ref[ib];
+			const int a0 = (int8_t)(ra & 255), a1 = (int8_t)(ra >> 8), b0 = (int8_t)(rb & 255), b1 = (int8_t)(rb >> 8);
+			const uint32_t ma0 = f.mv[0][ia], ma1 = f.mv[1][ia], mb0 = f.mv[0][ib], mb1 = f.mv[1][ib];
+			if (!(mode & B2_BS_B_SLICE)) bs = (a0 != b0 || bs_far(ma0, mb0)) ? 1 : 0;
+			else if (!((a0 == b0 && a1 == b1) || (a0 == b1 && a1 == b0))) bs = 1;
+			else if (a0 != a1) {
+				if (a0 == b0) bs = ((a0 >= 0 && bs_far(ma0, mb0)) || (a1 >= 0 && bs_far(ma1, mb1))) ? 1 : 0;
+				else bs = ((a0 >= 0 && bs_far(ma0, mb1)) || (a1 >= 0 && bs_far(ma1, mb0))) ? 1 : 0;
+			} else {
+				const bool straight = bs_far(ma0, mb0) || bs_far(ma1, mb1), cross = bs_far(ma0, mb1) || bs_far(ma1, mb0);
+				const bool reduced = mode & (e == 0 ? B2_BS_REDUCED_MB_EDGE : (e == 2 ? B2_BS_REDUCED_CENTRE : B2_BS_REDUCED_INNER));
+				bs = reduced ? (straight ? 1 : 0) : ((straight && cross) ? 1 : 0);
+			}
+		}
+		const unsigned lo = __ballot_sync(0xffffffffu, bs & 1), hi = __ballot_sync(0xffffffffu, bs & 2);
+		bsv = spread16(lo) | (spread16(hi) << 1);
+		bsh = spread16(lo >> 16) | (spread16(hi >> 16) << 1);
+		if (left && !left_inter) flags |= B2_DBK_LEFT_BS4;
+		if (top && !top_inter) flags |= B2_DBK_TOP_BS4;
+	}
+	if (t8) {               // transform_size_8x8_flag: the 4x4 edges inside the 8x8 blocks are not filtered (8.7)
+		bsv &= 0x00ff00ffu;
+		bsh &= 0x00ff00ffu;
+	}
+	if (lane == 0) *reinterpret_cast<uint4 *>(rec) = make_uint4(bsv, bsh, (d.z & 0x00ffffffu) | ((uint32_t)flags << 24), d.w);
+}
+
 }  // namespace
 
 // ticket counters (32 ints) + row progress [n_jobs][mb_h] (wavefronts) or per-macroblock flags
@@ -2114,6 +2248,12 @@ size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h) { return (32 + (size_t)n_
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
                       uint32_t max_items, uint32_t max_first) {
 	if (n_jobs <= 0) return 0;
+	if (phase == 4) {
+		h264_bs_kernel<<<dim3((mb_w * mb_h + BS_WARPS - 1) / BS_WARPS, n_jobs), 32 * BS_WARPS, 0, stream>>>(d_jobs, mb_w, mb_w * mb_h);
+		if (launches) ++*launches;
+		B2_CUDA_OK(cudaGetLastError());
+		return 0;
+	}
 	if (phase == 0) {
 		dim3 grid5((max_items + I5_THREADS - 1) / I5_THREADS, n_jobs);
 		constexpr size_t smem5 = sizeof(uint32_t) * 32 * I5_THREADS + sizeof(int16_t) * 66 * I5_THREADS + sizeof(uint16_t) * I5_QUEUE * (I5_THREADS / 32);
@@ -2162,7 +2302,8 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 }
 
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense, bool intra_sparse,
-                bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first) {
+                bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first, bool derive_bs) {
+	if (derive_bs && deblock && launch_h264_phase(stream, 4, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (max_items && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches, max_items, max_first) < 0) return -1;
 	if (intra_dense && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (intra_sparse && launch_h264_phase(stream, 3, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;

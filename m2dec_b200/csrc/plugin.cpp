@@ -38,6 +38,13 @@ extern "C" int b2_context_set_md5(void *ctx, int on) {
 	return 0;
 }
 
+extern "C" int b2_context_set_host_strengths(void *ctx, int on) {
+	b2::Backend *be = b2::backend_of(ctx);
+	if (!be) return -1;
+	be->set_host_bs(on != 0);
+	return 0;
+}
+
 extern "C" int b2_context_frame_md5(void *ctx, const m2d_frame_t *frame, uint8_t digest[16]) {
 	b2::Backend *be = b2::backend_of(ctx);
 	if (!be) return -1;

@@ -22,7 +22,7 @@ struct Step {
 	std::vector<H4Job> h4;       // one job per lane (of the group) that has a picture at this step
 	std::vector<M2Job> m2;
 	void *d_jobs = nullptr;
-	bool intra_dense = false, intra_sparse = false, deblock = false;
+	bool intra_dense = false, intra_sparse = false, deblock = false, derive_bs = false;
 	uint32_t max_items = 0, max_first = 0;
 };
 struct Group {
@@ -145,6 +145,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	job.items = (const uint32_t *)(d + off[4]);
 	job.n_items = p->n_items;
 	job.n_first = p->n_items_first;
+	job.derive_bs = p->bs_on_device;
 	job.dst = p->dst; job.mb_w = p->mb_w; job.mb_h = p->mb_h; job.n_intra = (int32_t)p->n_intra;
 	int t = r->lane_len[lane]++;
 	std::vector<Step> &steps = r->groups[lane % r->groups.size()].steps;
@@ -155,6 +156,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	if (p->n_items_first > s.max_first) s.max_first = p->n_items_first;
 	if (p->n_intra > 0) (h264_intra_sparse((int)p->n_intra, (int)p->n_mbs) ? s.intra_sparse : s.intra_dense) = true;
 	s.deblock |= p->deblock != 0;
+	s.derive_bs |= p->bs_on_device != 0 && p->deblock != 0;
 	// algorithmic bytes: S(1 + 2 dbk) + R + C + M, split by kernel
 	uint64_t n_inter = 0, c_inter = 0, c_intra = 0, rbytes = 0;
 	for (uint32_t i = 0; i < p->n_mbs; ++i) {
@@ -256,6 +258,7 @@ extern "C" int b2_replay_run(b2_replay *r, int timed) {
 			if (s.intra_dense && launch_h264_phase(g.stream, 1, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (s.intra_sparse && launch_h264_phase(g.stream, 3, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 2], g.stream));
+			if (s.derive_bs && launch_h264_phase(g.stream, 4, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (s.deblock && launch_h264_phase(g.stream, 2, jobs, n, mb_w, mb_h, g.sync_area, &launches) < 0) return -1;
 			if (timed) B2_CUDA_OK(cudaEventRecord(g.ev[t * 4 + 3], g.stream));
 

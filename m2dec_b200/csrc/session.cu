@@ -451,6 +451,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	job.items = (const uint32_t *)(sl->dev + off_items);
 	job.n_items = p->n_items;
 	job.n_first = p->n_items_first;
+	job.derive_bs = p->bs_on_device;
 	memcpy(sl->host, &job, sizeof(job));
 	stream_copy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
 	stream_copy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
@@ -465,7 +466,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	s->trace.lap(T_H2D);
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_items,
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
-	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first) < 0) return -1;
+	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first, p->bs_on_device != 0) < 0) return -1;
 	s->trace.lap(T_LAUNCH);
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));

@@ -105,11 +105,13 @@ def frame_md5(frm):
 
 
 class M2Decoder:
-    def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None, chunk=0, device_md5=False):
+    def __init__(self, codec, data, dpb=-1, outbuf=0, tap=None, device_off=False, cuda_device=None, chunk=0, device_md5=False, host_strengths=False):
         """chunk > 0: the stream is handed over `chunk` bytes at a time through ONE reused buffer, as the
         reference application refills its input buffer (bytes of an earlier refill do not stay valid).
         device_md5: digest mode (b2_context_set_md5) -- frames are hashed on the device, `frame_digest(frm)`
-        returns what `frame_md5(frm)` would, the frame buffers themselves are not filled."""
+        returns what `frame_md5(frm)` would, the frame buffers themselves are not filled.
+        host_strengths: the H.264 front end derives the deblocking strengths itself instead of leaving them to the
+        device (b2_context_set_host_strengths)."""
         self.codec = codec
         self._chunk, self._pos = int(chunk), 0
         self._chunk_buf = np.empty(max(int(chunk), 1), np.uint8)
@@ -135,6 +137,8 @@ class M2Decoder:
             L.lib.b2_context_set_device(self.ctx, cuda_device)
         if device_md5:
             L.lib.b2_context_set_md5(self.ctx, 1)
+        if host_strengths:
+            L.lib.b2_context_set_host_strengths(self.ctx, 1)
         self.stream = self.func.stream_pos(self.ctx)
         L.lib.dec_bits_set_callback(self.stream, self._refill_cb, None)
 

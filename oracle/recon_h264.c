@@ -679,3 +679,89 @@ int oracle_h264_picture(const b2_h264_picture *p, uint8_t *const *luma, uint8_t 
 			for (int mbx = 0; mbx < p->mb_w; ++mbx) deblock_mb(p, mbx, mby, luma[p->dst], chroma[p->dst]);
 	return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Deblocking strengths from the records (test infrastructure like the rest of this file).
+ * Restates what the reference's parse stores into deblock_info_t (store_info_inter*, str_mv_calc*,
+ * str_previous_coef: h264.cpp:7119-7322, 7451-7604, 8796-9400; intra: 3 / bS 4 on macroblock edges, 8.7.2.1) from
+ * the inputs the device kernel gets (motion records, b2_h264_mb.nnz4x4, b2_h264_dbk.bs_mode, the edge flags) and
+ * compares the result with the strengths the host front end filled in.  Returns the number of macroblocks whose
+ * bs_v / bs_h / BS4 flags differ (0 = the two derivations agree), -1 if the picture carries no host strengths.
+ * tests/util.py runs it on every tapped picture, so every CPU test stream pins the derivation the CUDA kernel
+ * (h264_bs_kernel) implements.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { int8_t ref[2]; int16_t mv[2][2]; } bs_block;
+
+static int bs_far(const int16_t *a, const int16_t *b)
+{
+	return (unsigned)(a[0] - b[0] + 3) > 6u || (unsigned)(a[1] - b[1] + 3) > 6u;
+}
+
+static int bs_pair(const bs_block *a, const bs_block *b, int nza, int nzb, int bslice, int reduced)
+{
+	if (nza | nzb) return 2;
+	if (!bslice) return a->ref[0] != b->ref[0] || bs_far(a->mv[0], b->mv[0]);
+	if (!((a->ref[0] == b->ref[0] && a->ref[1] == b->ref[1]) || (a->ref[0] == b->ref[1] && a->ref[1] == b->ref[0]))) return 1;
+	if (a->ref[0] != a->ref[1]) {
+		if (a->ref[0] == b->ref[0]) return (a->ref[0] >= 0 && bs_far(a->mv[0], b->mv[0])) || (a->ref[1] >= 0 && bs_far(a->mv[1], b->mv[1]));
+		return (a->ref[0] >= 0 && bs_far(a->mv[0], b->mv[1])) || (a->ref[1] >= 0 && bs_far(a->mv[1], b->mv[0]));
+	}
+	int straight = bs_far(a->mv[0], b->mv[0]) || bs_far(a->mv[1], b->mv[1]), cross = bs_far(a->mv[0], b->mv[1]) || bs_far(a->mv[1], b->mv[0]);
+	return reduced ? straight : (straight && cross);
+}
+
+int oracle_h264_bs_check(const b2_h264_picture *p)
+{
+	if (p->bs_on_device) return -1;
+	const int w4 = p->mb_w * 4, n_mbs = p->mb_w * p->mb_h;
+	bs_block *f = (bs_block *)calloc((size_t)n_mbs * 16, sizeof(bs_block));
+	for (int mb = 0; mb < n_mbs; ++mb) {
+		const b2_h264_mb *m = &p->mbs[mb];
+		if (m->type != B2_H4_INTER) continue;
+		int mbx = mb % p->mb_w, mby = mb / p->mb_w;
+		for (int i = 0; i < m->mc_cnt; ++i) {
+			const b2_h264_mc *r = &p->mcs[m->mc_idx + i];
+			for (int y = r->pos >> 2; y < (r->pos >> 2) + (r->size >> 4); ++y)
+				for (int x = r->pos & 3; x < (r->pos & 3) + (r->size & 15); ++x) {
+					bs_block *b = &f[(size_t)(mby * 4 + y) * w4 + mbx * 4 + x];
+					for (int l = 0; l < 2; ++l) { b->ref[l] = r->ref_frame[l]; b->mv[l][0] = r->mv[l][0]; b->mv[l][1] = r->mv[l][1]; }
+				}
+		}
+	}
+	int bad = 0;
+	for (int mb = 0; mb < n_mbs; ++mb) {
+		const b2_h264_mb *m = &p->mbs[mb];
+		const b2_h264_dbk *d = &p->dbk[mb];
+		if (d->flags & B2_DBK_OFF) continue;
+		int mbx = mb % p->mb_w, mby = mb / p->mb_w;
+		uint32_t bs[2] = {0, 0};
+		int flags = d->flags & ~(B2_DBK_LEFT_BS4 | B2_DBK_TOP_BS4);
+		for (int dir = 0; dir < 2; ++dir) {
+			int edge_ok = d->flags & (dir ? B2_DBK_TOP_EDGE : B2_DBK_LEFT_EDGE);
+			const b2_h264_mb *o = edge_ok ? (dir ? m - p->mb_w : m - 1) : NULL;
+			for (int e = 0; e < 4; ++e)
+				for (int sg = 0; sg < 4; ++sg) {
+					int v;
+					if (m->type != B2_H4_INTER) v = (e > 0 || o) ? 3 : 0;
+					else if (e == 0 && !o) v = 0;
+					else if (e == 0 && o->type != B2_H4_INTER) v = 3;
+					else {
+						int bx = dir ? sg : e, by = dir ? e : sg;
+						int gx = mbx * 4 + bx, gy = mby * 4 + by;
+						const bs_block *b = &f[(size_t)gy * w4 + gx], *a = dir ? b - w4 : b - 1;
+						int nzb = (m->nnz4x4 >> (by * 4 + bx)) & 1, nza;
+						if (e == 0) nza = (o->nnz4x4 >> (dir ? 12 + sg : sg * 4 + 3)) & 1;
+						else nza = (m->nnz4x4 >> (dir ? (by - 1) * 4 + bx : by * 4 + bx - 1)) & 1;
+						int red = d->bs_mode & (e == 0 ? B2_BS_REDUCED_MB_EDGE : (e == 2 ? B2_BS_REDUCED_CENTRE : B2_BS_REDUCED_INNER));
+						v = bs_pair(a, b, nza, nzb, d->bs_mode & B2_BS_B_SLICE, red != 0);
+					}
+					bs[dir] |= (uint32_t)v << (e * 8 + sg * 2);
+				}
+			if (o && (m->type != B2_H4_INTER || o->type != B2_H4_INTER)) flags |= dir ? B2_DBK_TOP_BS4 : B2_DBK_LEFT_BS4;
+		}
+		if (m->flags & B2_H4_T8x8) { bs[0] &= 0x00ff00ffu; bs[1] &= 0x00ff00ffu; }
+		if (bs[0] != d->bs_v || bs[1] != d->bs_h || flags != d->flags) ++bad;
+	}
+	free(f);
+	return bad;
+}

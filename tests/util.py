@@ -56,6 +56,10 @@ def oracle_tap(dec, codec, pic):
     assert check(C.c_void_p(pic), n) == 0, (L.lib.b2_last_error() or b"").decode()
     if codec == 1:
         return o.oracle_mpeg2_picture(C.c_void_p(pic), luma, chroma)
+    # the deblocking strengths the device would derive from the same records (oracle restatement of h264_bs_kernel's
+    # rules) must be the ones the host front end filled in: every tapped picture of every test stream checks it
+    bad = o.oracle_h264_bs_check(C.c_void_p(pic))
+    assert bad == 0, "%d macroblocks: strengths derived from the records differ from the host's" % bad
     return o.oracle_h264_picture(C.c_void_p(pic), luma, chroma)
 
 
