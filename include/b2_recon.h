@@ -66,7 +66,10 @@ typedef struct {
 /* ------------------------------------------------------------------------------------ */
 
 enum { B2_H4_INTER = 0, B2_H4_I4x4 = 1, B2_H4_I8x8 = 2, B2_H4_I16x16 = 3, B2_H4_IPCM = 4 };
-enum { B2_H4_T8x8 = 0x01 };     /* b2_h264_mb.flags: transform_size_8x8_flag */
+/* b2_h264_mb.flags: transform_size_8x8_flag; with mv_on_device: P_Skip (the motion vector is inferred, 8.4.1.1) and,
+ * in bits 4..7, which neighbouring macroblocks (bit 4 left, 5 top, 6 top-right, 7 top-left) are available to the
+ * motion vector prediction (same slice, already decoded: 6.4.8)                                                   */
+enum { B2_H4_T8x8 = 0x01, B2_H4_PSKIP = 0x02, B2_H4_NB_SHIFT = 4 };
 
 /* b2_h264_mb.nz — which coefficient records exist, bit order == record order:
  *   bit 0        Intra16x16 luma DC (16 levels, raster 4x4 of the DC matrix)
@@ -112,6 +115,19 @@ typedef struct {
 	int8_t o[2][3];         /* [list][Y, Cb, Cr] offset                                           */
 	uint8_t reserved[4];
 } b2_h264_mc;               /* 32 bytes */
+
+/* mv_on_device (SURVEY.md 8f rank 3, P macroblocks of Baseline-profile streams): one partition of a P macroblock
+ * as the parse read it -- the motion vector DIFFERENCE, not the vector.  The device predicts the vectors
+ * (8.4.1.3; reference calc_mv*, h264.cpp:6669-6724, 7379-7604) in a macroblock wavefront, writes the
+ * b2_h264_mc record of every partition (default weights) and builds the inter kernel's work list.
+ * b2_h264_mb.mc_idx / mc_cnt index the partitions (and the motion records the device makes of them, 1:1). */
+typedef struct {
+	uint8_t pos;            /* (y4 << 2) | x4                                                        */
+	uint8_t size;           /* (h4 << 4) | w4                                                        */
+	int8_t ref_idx;         /* refIdxL0                                                              */
+	int8_t ref_frame;       /* frame-pool index of RefPicList0[ref_idx]                              */
+	int16_t mvd[2];         /* mvd_l0 (x, y), quarter samples; 0 for P_Skip                          */
+} b2_h264_part;             /* 8 bytes */
 
 /* b2_h264_dbk.flags */
 enum {
@@ -166,6 +182,13 @@ typedef struct {
 	 * the reference's parse does (store_info_inter*, str_mv_calc*, str_previous_coef: h264.cpp:7119-7322, 7451-7604,
 	 * 8796-9400).  qp_*, alpha_off / beta_off and the flags B2_DBK_OFF / LEFT_EDGE / TOP_EDGE always come from the host. */
 	uint32_t bs_on_device;
+	/* SURVEY.md 8f rank 3.  != 0: mcs and items are NULL (n_mcs = 0); `parts` holds n_parts partitions, the device
+	 * derives vectors, motion records and work list itself (h264_mv_kernel, h264_items_kernel).  n_items is then an
+	 * UPPER BOUND of the number of work items (one per 4 luma columns of every partition); requires bs_on_device.
+	 * Only pictures of P / I slices without weighted prediction qualify (the front end uses it for Baseline streams). */
+	uint32_t mv_on_device;
+	uint32_t n_parts;
+	const b2_h264_part *parts;
 } b2_h264_picture;
 
 /* ------------------------------------------------------------------------------------ */

@@ -40,8 +40,21 @@ struct H4Job {
 	int32_t dst, mb_w, mb_h, n_intra;
 	const uint32_t *items;      // b2_h264_picture.items
 	uint32_t n_items, n_first;  // b2_h264_picture.n_items / n_items_first
-	uint32_t derive_bs, pad_;   // b2_h264_picture.bs_on_device
+	uint32_t derive_bs;         // b2_h264_picture.bs_on_device
+	// b2_h264_picture.mv_on_device: the partitions as parsed; mcs / items / n_items above are then device scratch that
+	// h264_mv_kernel and h264_items_kernel fill before the inter kernel runs
+	uint32_t derive_mv;
+	const b2_h264_part *parts;
+	uint32_t n_parts, pad_;
+	int8_t *field_ref;          // [n_mbs][16] reference index of every 4x4 block (-1 intra), raster inside the macroblock
+	uint32_t *field_mv;         // [n_mbs][16] motion vector (x | y << 16)
+	uint32_t *owner;            // [n_parts] macroblock of a partition
 };
+// bytes of device scratch a picture with mv_on_device needs behind its records: motion records, work list (bound),
+// owner table, motion field
+inline size_t h264_mv_scratch_bytes(size_t n_mbs, size_t n_parts, size_t item_bound) {
+	return n_parts * 32 + (item_bound + 64) * 4 + n_parts * 4 + 256 + n_mbs * 16 + 256 + n_mbs * 64 + 1024;
+}
 // A picture with few intra macroblocks (P / B pictures) goes through the sparse intra kernel, which
 // orders macroblocks by per-macroblock flags; a mostly-intra picture through the row wavefront.
 __host__ __device__ inline bool h264_intra_sparse(int n_intra, int n_mbs) { return n_intra * 3 < n_mbs; }
@@ -49,13 +62,14 @@ __host__ __device__ inline bool h264_intra_sparse(int n_intra, int n_mbs) { retu
 // pool's last row may be read 16 bytes past it (never used), so pools are allocated with this many spare bytes.
 constexpr size_t H4_POOL_TAIL = 256;
 // phase: 0 inter (MC + residual), 1 intra wavefront (dense pictures), 2 deblock wavefront,
-// 3 intra, sparse pictures, 4 deblocking strengths (pictures with b2_h264_picture.bs_on_device: every job of the launch)
+// 3 intra, sparse pictures, 4 deblocking strengths (the jobs with b2_h264_picture.bs_on_device), 5 motion vectors,
+// motion records and work list (the jobs with mv_on_device; d_jobs is written: n_items)
 size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h);
 // max_items: largest n_items among the jobs (phase 0 only)
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
                       uint32_t max_items = 0, uint32_t max_first = 0);
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense,
-                bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first = 0, bool derive_bs = false);
+                bool intra_sparse, bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first = 0, bool derive_bs = false, bool derive_mv = false);
 
 // md5.cu: MD5 of a cropped window of n frames (one thread per frame); d_slots / d_out are device pointers
 int md5_pictures(cudaStream_t stream, const uint8_t *frames, size_t frame_bytes, const int *d_slots, int n, int stride, int rows, int left, int top, int w, int h,

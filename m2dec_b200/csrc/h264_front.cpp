@@ -586,6 +586,8 @@ private:
 		if (br_.overrun()) throw BitError();
 		slice_num_++;
 		bslice_ = st == SLICE_B;
+		// (tools the Baseline profile does not have: a stream that claims it and uses them is damaged)
+		if (dev_mv_ && (bslice_ || pps.cabac || wt_.mode != 0)) return -1;
 		direct_8x8_inference_ = sps.direct_8x8_inference != 0;
 		cabac_ = pps.cabac != 0;
 		ctx_.cabac = cabac_;
@@ -762,6 +764,14 @@ private:
 		// parse-only runs -- or the application asked for it (b2_context_set_host_strengths; B2_HOST_BS=1 for A/B runs).
 		static const bool env_host_bs = getenv("B2_HOST_BS") != nullptr;
 		host_bs_ = env_host_bs || backend.host_bs() || backend.has_tap() || backend.device_off();
+		// Motion vectors: Baseline-profile streams (P and I slices only, no weighted prediction, no
+		// co-located motion to keep for later direct prediction) hand the device motion vector DIFFERENCES; prediction,
+		// motion records and the inter kernel's work list are made there.  Needs the device-side strengths.
+		static const bool env_host_mv = getenv("B2_HOST_MV") != nullptr;
+		dev_mv_ = !host_bs_ && !env_host_mv && sps.profile_idc == 66;
+		keep_parts_ = !dev_mv_ && backend.has_tap() && sps.profile_idc == 66;
+		parts_.clear();
+		item_bound_ = 0;
 		slice_num_ = -1;
 		mb_addr_ = 0;
 		pic_open_ = true;
@@ -791,6 +801,20 @@ private:
 		p.items = items_all_.data();
 		p.n_items = (uint32_t)items_all_.size();
 		p.bs_on_device = host_bs_ ? 0u : 1u;
+		if (keep_parts_ && parts_.size() == mcs_.size()) {       // host derivation, partitions alongside (1:1 with the records)
+			p.n_parts = (uint32_t)parts_.size();
+			p.parts = parts_.data();
+		}
+		if (dev_mv_) {
+			p.mv_on_device = 1;
+			p.n_parts = (uint32_t)parts_.size();
+			p.parts = parts_.data();
+			p.mcs = nullptr;
+			p.items = nullptr;
+			p.n_mcs = 0;
+			p.n_items = item_bound_;
+			p.n_items_first = 0;
+		}
 		backend.submit(B2_CODEC_H264, &p);
 		pic_open_ = false;
 		// reference marking (8.2.5) and DPB insertion (h264.cpp:10840-10873, 11036-11045)
@@ -979,7 +1003,7 @@ private:
 		b2_h264_mb &m = mbs_[(size_t)mby * mb_w_ + mbx];
 		memset(&m, 0, sizeof(m));
 		m.coef_idx = (uint32_t)(coef_used_ / 16);
-		m.mc_idx = (uint32_t)mcs_.size();
+		m.mc_idx = (uint32_t)(dev_mv_ ? parts_.size() : mcs_.size());
 	}
 
 	int ref_frame_of(int lx, int refidx) const {
@@ -1072,9 +1096,22 @@ private:
 		} else {
 			int16_t mv[2];
 			set_shape(mbx, mby, SHAPE_16x16, false);
+			if (dev_mv_) {
+				const int f = ref_frame_of(0, 0);
+				m.flags |= (uint8_t)(B2_H4_PSKIP | (ctx_.mb_avail_mask(mbx, mby, slice_num_) << B2_H4_NB_SHIFT));
+				parts_.push_back(b2_h264_part{0, 0x44, 0, (int8_t)(f < 0 ? cur_frame_ : f), {0, 0}});
+				m.mc_cnt++;
+				item_bound_ += 4;
+			} else {
+			if (keep_parts_) {
+				const int f = ref_frame_of(0, 0);
+				m.flags |= (uint8_t)(B2_H4_PSKIP | (ctx_.mb_avail_mask(mbx, mby, slice_num_) << B2_H4_NB_SHIFT));
+				parts_.push_back(b2_h264_part{0, 0x44, 0, (int8_t)(f < 0 ? cur_frame_ : f), {0, 0}});
+			}
 			ctx_.pskip_mv(mbx, mby, slice_num_, mv);
 			ctx_.set_motion(0, mbx, mby, 0, 0, 4, 4, 0, ref_frame_of(0, 0), mv[0], mv[1]);
 			emit_mc_p(m, 0, 0, 4, 4, 0, mv[0], mv[1]);
+			}
 		}
 		MbInfo &info = ctx_.info(mbx, mby);
 		info.kind = MB_SKIP;
@@ -1507,11 +1544,25 @@ private:
 		info.kind = MB_INTER;
 		memset(ctx_.ipred_of(mbx, mby), 2, 16);
 		const int nref = h.num_ref_idx_active[0];
+		if (dev_mv_ || keep_parts_) m.flags |= (uint8_t)(ctx_.mb_avail_mask(mbx, mby, slice_num_) << B2_H4_NB_SHIFT);
 		auto do_part = [&](int x4, int y4, int pw, int ph, int ref, int shape, int part) {
 			int16_t pred[2];
 			int d[2];
+			if (dev_mv_) {
+				// the device predicts: hand over the difference as read
+				rd_mvd(0, x4, y4, pw, ph, d);
+				const int f = ref_frame_of(0, ref);
+				parts_.push_back(b2_h264_part{(uint8_t)((y4 << 2) | x4), (uint8_t)((ph << 4) | pw), (int8_t)ref, (int8_t)(f < 0 ? cur_frame_ : f), {(int16_t)d[0], (int16_t)d[1]}});
+				m.mc_cnt++;
+				item_bound_ += (uint32_t)pw;
+				return;
+			}
 			ctx_.predict_mv(0, mbx, mby, x4, y4, pw, ref, slice_num_, shape, part, pred);
 			rd_mvd(0, x4, y4, pw, ph, d);
+			if (keep_parts_) {           // (a picture tap sees both the partitions and the records made of them)
+				const int f = ref_frame_of(0, ref);
+				parts_.push_back(b2_h264_part{(uint8_t)((y4 << 2) | x4), (uint8_t)((ph << 4) | pw), (int8_t)ref, (int8_t)(f < 0 ? cur_frame_ : f), {(int16_t)d[0], (int16_t)d[1]}});
+			}
 			int mvx = pred[0] + d[0];
 			int mvy = pred[1] + d[1];
 			ctx_.set_motion(0, mbx, mby, x4, y4, pw, ph, ref, ref_frame_of(0, ref), mvx, mvy);
@@ -1941,6 +1992,10 @@ private:
 	bool cabac_ = false;
 	int bs_reduced_ = 0;        // see set_shape
 	bool host_bs_ = true;       // this picture's deblocking strengths are derived here, not on the device (begin_picture)
+	bool dev_mv_ = false;       // this picture's motion vectors are predicted on the device (begin_picture)
+	bool keep_parts_ = false;   // host derivation, but the partitions are recorded too (what a tap's owner checks against)
+	std::vector<b2_h264_part> parts_;
+	uint32_t item_bound_ = 0;
 	int last_dqp_ = 0;          // mb_qp_delta of the previous macroblock in decoding order (CABAC ctxIdxInc)
 	CabacSyntax<CabacDec> cs_;
 	struct { int mode, denom[2]; int8_t w[2][32][3], o[2][32][3]; } wt_;   // mode 0 default, 1 explicit, 2 implicit

@@ -2105,6 +2105,179 @@ h264_intra_sparse_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Motion vectors on the device (reference calc_mv* / P_Skip, h264.cpp:6669-6724, 7379-7604,
+// standard 8.4.1.1, 8.4.1.3).  The parse of a Baseline-profile P picture hands over, per partition, the reference
+// index and the motion vector DIFFERENCE; prediction needs the final vectors of the left, top, top-right and top-left
+// neighbours, so the macroblocks are a wavefront like intra prediction: one warp per macroblock row (tickets in
+// picture-major row order), a row waits until the row above is two macroblocks ahead.  The derivation itself is
+// serial inside a macroblock (a partition predicts from the ones before it) and runs on lane 0; it is a few
+// hundred instructions per macroblock and hidden behind the host's parse of the next picture.  Output: the
+// b2_h264_mc record of every partition (default weights), the picture's motion field (for the rows below) and the
+// macroblock each partition belongs to (for h264_items_kernel).
+// ------------------------------------------------------------------------------------------------
+struct MvNb { int ref; int mvx, mvy; };       // ref: -2 unavailable, -1 intra
+__device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+__global__ void __launch_bounds__(32)
+h264_mv_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, int *__restrict__ sync_area) {
+	// blocks (x, y), x = -1 .. 4, y = -1 .. 3 of the current macroblock's neighbourhood at [y + 1][x + 1]
+	__shared__ int8_t s_ref[5][6];
+	__shared__ uint32_t s_mv[5][6];
+	int *ticket = sync_area;
+	int *progress = sync_area + 32;           // [n_jobs][mb_h]: macroblocks of the row whose motion is final
+	const int lane = threadIdx.x;
+	for (;;) {
+		int t = 0;
+		if (lane == 0) t = atomicAdd(ticket, 1);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= n_jobs * mb_h) return;
+		const int j = t / mb_h, mby = t % mb_h;
+		const H4Job job = jobs[j];
+		if (!job.derive_mv || lane != 0) continue;
+		int *prog_above = progress + (size_t)j * mb_h + mby - 1, *prog_mine = progress + (size_t)j * mb_h + mby;
+		b2_h264_mc *mcs = const_cast<b2_h264_mc *>(job.mcs);
+		int seen = 0;
+		for (int mbx = 0; mbx < mb_w; ++mbx) {
+			const int mb = mby * mb_w + mbx;
+			const b2_h264_mb *m = job.mbs + mb;
+			const int type = m->type, flags = m->flags, avail = flags >> B2_H4_NB_SHIFT;
+			int8_t *fr = job.field_ref + (size_t)mb * 16;
+			uint32_t *fm = job.field_mv + (size_t)mb * 16;
+			if (type != B2_H4_INTER) {
+				for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t *>(fr)[i] = 0xffffffffu;     // -1: intra
+				for (int i = 0; i < 16; ++i) fm[i] = 0;
+				// the next macroblock's left column
+				for (int y = 0; y < 4; ++y) { s_ref[y + 1][4] = -1; s_mv[y + 1][4] = 0; }
+			} else {
+				if (mby > 0 && (avail & 14)) {
+					const int want = min(mbx + 2, mb_w);
+					if (seen < want) seen = spin_until(prog_above, want);
+				}
+				// neighbourhood: left column = the previous macroblock's right column (still in the tile), the row above from
+				// the motion field (written by another warp: through L2)
+				for (int y = 0; y < 4; ++y) {
+					if (avail & 1) { s_ref[y + 1][0] = s_ref[y + 1][4]; s_mv[y + 1][0] = s_mv[y + 1][4]; }
+					else s_ref[y + 1][0] = -2;
+					for (int x = 0; x < 5; ++x) s_ref[y + 1][x + 1] = -2;                          // not decoded yet / outside
+				}
+				for (int x = -1; x < 5; ++x) {
+					const bool ok = x < 0 ? (avail & 8) != 0 : (x < 4 ? (avail & 2) != 0 : (avail & 4) != 0);
+					int r = -2;
+					uint32_t v = 0;
+					if (ok) {
+						const int nmb = mb - mb_w + (x < 0 ? -1 : (x < 4 ? 0 : 1)), blk = 12 + (x & 3);
+						r = (int8_t)__ldcg(reinterpret_cast<const char *>(job.field_ref) + (size_t)nmb * 16 + blk);
+						v = __ldcg(job.field_mv + (size_t)nmb * 16 + blk);
+					}
+					s_ref[0][x + 1] = (int8_t)r;
+					s_mv[0][x + 1] = v;
+				}
+				auto nb = [&](int x, int y) {
+					MvNb n;
+					n.ref = s_ref[y + 1][x + 1];
+					const uint32_t v = n.ref >= 0 ? s_mv[y + 1][x + 1] : 0u;
+					n.mvx = (int16_t)(v & 0xffff);
+					n.mvy = (int16_t)(v >> 16);
+					return n;
+				};
+				const b2_h264_part *parts = job.parts + m->mc_idx;
+				const int cnt = m->mc_cnt;
+				for (int i = 0; i < cnt; ++i) {
+					const b2_h264_part pt = parts[i];
+					const int x4 = pt.pos & 3, y4 = pt.pos >> 2, pw = pt.size & 15, ph = pt.size >> 4, refidx = pt.ref_idx;
+					MvNb a = nb(x4 - 1, y4), b = nb(x4, y4 - 1), c = nb(x4 + pw, y4 - 1);
+					if (c.ref == -2) c = nb(x4 - 1, y4 - 1);
+					int px, py;
+					bool done = false;
+					if (flags & B2_H4_PSKIP) {
+						if (a.ref == -2 || b.ref == -2 || (a.ref == 0 && a.mvx == 0 && a.mvy == 0) || (b.ref == 0 && b.mvx == 0 && b.mvy == 0)) { px = py = 0; done = true; }
+					} else if (pw == 4 && ph == 2) {          // 16x8: the upper partition from above, the lower one from the left
+						if (i == 0 && b.ref == refidx) { px = b.mvx; py = b.mvy; done = true; }
+						if (i == 1 && a.ref == refidx) { px = a.mvx; py = a.mvy; done = true; }
+					} else if (pw == 2 && ph == 4) {          // 8x16: the left partition from the left, the right one from above-right
+						if (i == 0 && a.ref == refidx) { px = a.mvx; py = a.mvy; done = true; }
+						if (i == 1 && c.ref == refidx) { px = c.mvx; py = c.mvy; done = true; }
+					}
+					if (!done) {
+						if (b.ref == -2 && c.ref == -2 && a.ref != -2) { b = a; c = a; }
+						const bool ma = a.ref == refidx, mb_ = b.ref == refidx, mc = c.ref == refidx;
+						if ((int)ma + (int)mb_ + (int)mc == 1) {
+							const MvNb &s1 = ma ? a : (mb_ ? b : c);
+							px = s1.mvx; py = s1.mvy;
+						} else {
+							px = median3(a.mvx, b.mvx, c.mvx);
+							py = median3(a.mvy, b.mvy, c.mvy);
+						}
+					}
+					const int mvx = (int16_t)(px + pt.mvd[0]), mvy = (int16_t)(py + pt.mvd[1]);
+					const uint32_t packed = (uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+					for (int y = y4; y < y4 + ph; ++y)
+						for (int x = x4; x < x4 + pw; ++x) { s_ref[y + 1][x + 1] = (int8_t)refidx; s_mv[y + 1][x + 1] = packed; }
+					// the motion record: list 0 only, default weights (include/b2_recon.h b2_h264_mc)
+					uint4 *rec = reinterpret_cast<uint4 *>(mcs + m->mc_idx + i);
+					rec[0] = make_uint4((uint32_t)pt.pos | ((uint32_t)pt.size << 8) | ((uint32_t)(uint8_t)pt.ref_frame << 16) | 0xff000000u,
+					                    (uint32_t)(uint8_t)refidx | 0x0000ff00u, packed, 0u);
+					rec[1] = make_uint4(0x01010101u, 0x00000101u, 0u, 0u);
+					job.owner[m->mc_idx + i] = (uint32_t)mb;
+				}
+				for (int y = 0; y < 4; ++y)
+					for (int x = 0; x < 4; ++x) { fr[y * 4 + x] = s_ref[y + 1][x + 1]; fm[y * 4 + x] = s_mv[y + 1][x + 1]; }
+			}
+			// rows below read this macroblock's bottom row
+			if (mby + 1 < mb_h) st_release(prog_mine, mbx + 1);
+		}
+	}
+}
+
+// Work list of the inter kernel from the motion records (what the host front end's emit_mc does, h264_front.cpp):
+// one CTA per picture counts the strips of every record per bucket (touches-the-edge, class, height), turns the
+// counts into offsets and writes the items; the order inside a bucket is whatever the atomics give (every strip
+// writes its own pixels, the order decides nothing).  Writes the picture's n_items into its job.
+__global__ void __launch_bounds__(1024)
+h264_items_kernel(H4Job *__restrict__ jobs, int mb_w, int mb_h) {
+	__shared__ uint32_t s_cnt[72], s_at[72];
+	H4Job &job = jobs[blockIdx.x];
+	if (!job.derive_mv) return;
+	for (int i = threadIdx.x; i < 72; i += blockDim.x) s_cnt[i] = 0;
+	__syncthreads();
+	const int W = mb_w * 16, H = mb_h * 16;
+	const uint32_t n = job.n_parts;
+	uint32_t *items = const_cast<uint32_t *>(job.items);
+	for (int pass = 0; pass < 2; ++pass) {
+		for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) {
+			const b2_h264_mc *mc = job.mcs + r;
+			const uint32_t mb = job.owner[r];
+			const int pos = mc->pos, size = mc->size, mvx = mc->mv[0][0], mvy = mc->mv[0][1];
+			const int x4 = pos & 3, y4 = pos >> 2, pw = size & 15, ph = size >> 4;
+			const int fc = frac_class(mvx & 3, mvy & 3);
+			const int wide = pw >= 2 && fc < 4, cnt = wide ? pw >> 1 : pw, sw = wide ? 8 : 4;
+			const int cls = fc + 6 * wide, hidx = ph == 4 ? 2 : ph - 1;
+			const int mbx = mb % mb_w, mby = mb / mb_w;
+			const int y0 = mby * 16 + y4 * 4 + (mvy >> 2);
+			const bool yedge = y0 - 3 < 0 || y0 + ph * 4 + 4 > H;
+			const uint32_t word = mb | ((r - job.mbs[mb].mc_idx) << 20) | ((uint32_t)cls << 26);
+			for (int k = 0; k < cnt; ++k) {
+				const int x0 = mbx * 16 + x4 * 4 + k * sw + (mvx >> 2);
+				const bool edge = yedge || x0 - 6 < 0 || x0 + sw + 12 > W;
+				const int b = (edge ? 36 : 0) + cls * 3 + hidx;
+				if (pass == 0) atomicAdd(&s_cnt[b], 1u);
+				else items[atomicAdd(&s_at[b], 1u)] = word | ((uint32_t)k << 24);
+			}
+		}
+		__syncthreads();
+		if (pass == 0) {
+			if (threadIdx.x == 0) {
+				uint32_t at = 0;
+				for (int b = 0; b < 72; ++b) { s_at[b] = at; at += s_cnt[b]; }
+				job.n_items = at;
+				job.n_first = 0;
+			}
+			__syncthreads();
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // Deblocking strengths on the device (reference: store_info_inter*, str_mv_calc*,
 // str_previous_coef, h264.cpp:7119-7322, 7451-7604, 8796-9400, which run inside the parse).  One warp per
 // macroblock: the 4x4 motion field of the macroblock, of the column to its left and of the row above it is
@@ -2248,6 +2421,16 @@ size_t h264_sync_bytes(int n_jobs, int mb_w, int mb_h) { return (32 + (size_t)n_
 int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, int *sync_area, uint64_t *launches,
                       uint32_t max_items, uint32_t max_first) {
 	if (n_jobs <= 0) return 0;
+	if (phase == 5) {
+		B2_CUDA_OK(cudaMemsetAsync(sync_area, 0, (32 + (size_t)n_jobs * mb_h) * sizeof(int), stream));
+		int ctas = n_jobs * mb_h;
+		if (ctas > 148 * 16) ctas = 148 * 16;                       // persistent: every CTA resident
+		h264_mv_kernel<<<ctas, 32, 0, stream>>>(d_jobs, n_jobs, mb_w, mb_h, sync_area);
+		h264_items_kernel<<<n_jobs, 1024, 0, stream>>>(const_cast<H4Job *>(d_jobs), mb_w, mb_h);
+		if (launches) *launches += 2;
+		B2_CUDA_OK(cudaGetLastError());
+		return 0;
+	}
 	if (phase == 4) {
 		h264_bs_kernel<<<dim3((mb_w * mb_h + BS_WARPS - 1) / BS_WARPS, n_jobs), 32 * BS_WARPS, 0, stream>>>(d_jobs, mb_w, mb_w * mb_h);
 		if (launches) ++*launches;
@@ -2302,7 +2485,8 @@ int launch_h264_phase(cudaStream_t stream, int phase, const H4Job *d_jobs, int n
 }
 
 int launch_h264(cudaStream_t stream, const H4Job *d_jobs, int n_jobs, int mb_w, int mb_h, uint32_t max_items, bool intra_dense, bool intra_sparse,
-                bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first, bool derive_bs) {
+                bool deblock, int *sync_area, uint64_t *launches, uint32_t max_first, bool derive_bs, bool derive_mv) {
+	if (derive_mv && max_items && launch_h264_phase(stream, 5, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (derive_bs && deblock && launch_h264_phase(stream, 4, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;
 	if (max_items && launch_h264_phase(stream, 0, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches, max_items, max_first) < 0) return -1;
 	if (intra_dense && launch_h264_phase(stream, 1, d_jobs, n_jobs, mb_w, mb_h, sync_area, launches) < 0) return -1;

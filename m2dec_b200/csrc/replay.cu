@@ -129,6 +129,7 @@ extern "C" int b2_replay_add_h264(b2_replay *r, int lane, const b2_h264_picture 
 	if (!r || !p || r->codec != B2_CODEC_H264 || (unsigned)lane >= (unsigned)r->lanes) return -1;
 	if (p->mb_w * 16 != r->width || p->mb_h * 16 != r->height || (unsigned)p->dst >= (unsigned)r->pool) return -1;
 	if (b2_h264_picture_check(p, r->pool) < 0) return -1;
+	if (p->mv_on_device) { set_error("kernel replay takes pictures with motion records (mv_on_device pictures go through a session)"); return -1; }
 	B2_CUDA_OK(cudaSetDevice(r->dev));
 	std::vector<size_t> off;
 	uint8_t *d;

@@ -427,14 +427,25 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (s->check_records && b2_h264_picture_check(p, s->nframes) < 0) return -1;
 	s->trace.lap(T_CHECK);
 	B2_CUDA_OK(cudaSetDevice(s->dev));
+	const bool dev_mv = p->mv_on_device != 0;
+	if (dev_mv && (!p->bs_on_device || p->n_mcs || p->n_items_first)) { set_error("mv_on_device needs bs_on_device and carries no motion records"); return -1; }
+	// motion records: copied from the host, or (mv_on_device) the partitions are copied and the records are device scratch
+	const size_t n_recs = dev_mv ? p->n_parts : p->n_mcs, rec_bytes = dev_mv ? sizeof(b2_h264_part) * p->n_parts : sizeof(b2_h264_mc) * p->n_mcs;
 	size_t off_mbs = align_up(sizeof(H4Job), 256);
 	size_t off_dbk = align_up(off_mbs + sizeof(b2_h264_mb) * p->n_mbs, 256);
 	size_t off_mcs = align_up(off_dbk + sizeof(b2_h264_dbk) * p->n_mbs, 256);
-	size_t off_coef = align_up(off_mcs + sizeof(b2_h264_mc) * p->n_mcs, 256);
+	size_t off_coef = align_up(off_mcs + rec_bytes, 256);
 	size_t off_items = align_up(off_coef + (size_t)p->n_coef_recs * 32, 256);
-	size_t total = off_items + (size_t)p->n_items * 4;
+	size_t total = off_items + (dev_mv ? 0 : (size_t)p->n_items * 4);
+	// device only, behind what is copied (mv_on_device): motion records, work list, owner table, motion field
+	size_t off_x_mcs = align_up(total, 256);
+	size_t off_x_items = align_up(off_x_mcs + n_recs * sizeof(b2_h264_mc), 256);
+	size_t off_x_owner = align_up(off_x_items + ((size_t)p->n_items + 64) * 4, 256);
+	size_t off_x_fref = align_up(off_x_owner + n_recs * 4, 256);
+	size_t off_x_fmv = align_up(off_x_fref + (size_t)p->n_mbs * 16, 256);
+	size_t total_dev = dev_mv ? off_x_fmv + (size_t)p->n_mbs * 64 : total;
 	StageSlot *sl;
-	if (acquire_slot(s, total, &sl) < 0) return -1;
+	if (acquire_slot(s, total_dev, &sl) < 0) return -1;
 	s->trace.lap(T_SLOT);
 	H4Job job;
 	memset(&job, 0, sizeof(job));
@@ -442,22 +453,30 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	job.frame_bytes = s->frame_bytes;
 	job.mbs = (const b2_h264_mb *)(sl->dev + off_mbs);
 	job.dbk = (const b2_h264_dbk *)(sl->dev + off_dbk);
-	job.mcs = (const b2_h264_mc *)(sl->dev + off_mcs);
+	job.mcs = (const b2_h264_mc *)(sl->dev + (dev_mv ? off_x_mcs : off_mcs));
 	job.coefs = (const int16_t *)(sl->dev + off_coef);
 	job.dst = p->dst;
 	job.mb_w = p->mb_w;
 	job.mb_h = p->mb_h;
 	job.n_intra = (int32_t)p->n_intra;
-	job.items = (const uint32_t *)(sl->dev + off_items);
-	job.n_items = p->n_items;
+	job.items = (const uint32_t *)(sl->dev + (dev_mv ? off_x_items : off_items));
+	job.n_items = dev_mv ? 0 : p->n_items;        // (mv_on_device: h264_items_kernel writes it)
 	job.n_first = p->n_items_first;
 	job.derive_bs = p->bs_on_device;
+	job.derive_mv = p->mv_on_device;
+	if (dev_mv) {
+		job.parts = (const b2_h264_part *)(sl->dev + off_mcs);
+		job.n_parts = p->n_parts;
+		job.owner = (uint32_t *)(sl->dev + off_x_owner);
+		job.field_ref = (int8_t *)(sl->dev + off_x_fref);
+		job.field_mv = (uint32_t *)(sl->dev + off_x_fmv);
+	}
 	memcpy(sl->host, &job, sizeof(job));
 	stream_copy(sl->host + off_mbs, p->mbs, sizeof(b2_h264_mb) * p->n_mbs);
 	stream_copy(sl->host + off_dbk, p->dbk, sizeof(b2_h264_dbk) * p->n_mbs);
-	if (p->n_mcs) stream_copy(sl->host + off_mcs, p->mcs, sizeof(b2_h264_mc) * p->n_mcs);
+	if (rec_bytes) stream_copy(sl->host + off_mcs, dev_mv ? (const void *)p->parts : (const void *)p->mcs, rec_bytes);
 	if (p->n_coef_recs) stream_copy(sl->host + off_coef, p->coefs, (size_t)p->n_coef_recs * 32);
-	if (p->n_items) stream_copy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
+	if (!dev_mv && p->n_items) stream_copy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
 	_mm_sfence();                 // the streamed stores are globally visible before the copy engine is told to read
 	s->trace.lap(T_PACK);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
@@ -466,7 +485,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	s->trace.lap(T_H2D);
 	if (launch_h264(s->stream, (const H4Job *)sl->dev, 1, p->mb_w, p->mb_h, p->n_items,
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
-	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first, p->bs_on_device != 0) < 0) return -1;
+	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first, p->bs_on_device != 0, dev_mv) < 0) return -1;
 	s->trace.lap(T_LAUNCH);
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));

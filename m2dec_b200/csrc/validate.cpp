@@ -21,12 +21,17 @@ extern "C" int b2_h264_picture_check(const b2_h264_picture *p, int nframes) {
 		set_error("H.264 picture: missing arrays");
 		return -1;
 	}
+	if (p->mv_on_device && (!p->bs_on_device || p->n_mcs || p->n_items_first || (p->n_parts && !p->parts))) {
+		set_error("H.264 picture: mv_on_device needs bs_on_device, partitions and no motion records");
+		return -1;
+	}
+	const uint32_t n_recs = p->mv_on_device ? p->n_parts : p->n_mcs;
 	uint32_t n_intra = 0;
 	for (uint32_t i = 0; i < p->n_mbs; ++i) {
 		const b2_h264_mb &m = p->mbs[i];
 		const uint32_t nrec = (uint32_t)__builtin_popcount(m.nz);
 		bool ok = m.type <= B2_H4_IPCM && m.qp_y <= 51 && m.qp_cb <= 51 && m.qp_cr <= 51 && m.i16_mode <= 3 && m.chroma_mode <= 3 &&
-		          !(m.nz >> 26) && (uint64_t)m.coef_idx + nrec <= p->n_coef_recs && (uint64_t)m.mc_idx + m.mc_cnt <= p->n_mcs && m.mc_cnt <= 16;
+		          !(m.nz >> 26) && (uint64_t)m.coef_idx + nrec <= p->n_coef_recs && (uint64_t)m.mc_idx + m.mc_cnt <= n_recs && m.mc_cnt <= 16;
 		if (ok && m.type == B2_H4_IPCM) ok = m.nz == 0xfff;
 		if (ok && m.type != B2_H4_INTER) { ok = m.mc_cnt == 0; n_intra++; }
 		if (ok && (m.flags & B2_H4_T8x8))
@@ -41,6 +46,21 @@ extern "C" int b2_h264_picture_check(const b2_h264_picture *p, int nframes) {
 		}
 	}
 	if (n_intra != p->n_intra) { set_error("H.264 picture: n_intra does not match the macroblock types"); return -1; }
+	if (p->mv_on_device) {
+		uint64_t cols = 0;
+		for (uint32_t i = 0; i < p->n_parts; ++i) {
+			const b2_h264_part &c = p->parts[i];
+			const int x4 = c.pos & 3, y4 = c.pos >> 2, w4 = c.size & 15, h4 = c.size >> 4;
+			const bool size_ok = (w4 == 1 || w4 == 2 || w4 == 4) && (h4 == 1 || h4 == 2 || h4 == 4) && x4 + w4 <= 4 && y4 + h4 <= 4 && y4 <= 3;
+			if (!size_ok || c.ref_idx < 0 || c.ref_frame < 0 || c.ref_frame >= nframes) {
+				set_error("H.264 picture: partition %u out of range (frame %d of %d)", i, c.ref_frame, nframes);
+				return -1;
+			}
+			cols += (uint64_t)w4;
+		}
+		if (cols > p->n_items) { set_error("H.264 picture: n_items is not an upper bound of the work items"); return -1; }
+		return 0;
+	}
 	for (uint32_t i = 0; i < p->n_mcs; ++i) {
 		const b2_h264_mc &c = p->mcs[i];
 		const int x4 = c.pos & 3, y4 = c.pos >> 2, w4 = c.size & 15, h4 = c.size >> 4;

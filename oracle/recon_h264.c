@@ -765,3 +765,78 @@ int oracle_h264_bs_check(const b2_h264_picture *p)
 	free(f);
 	return bad;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Motion vectors from the partitions (test infrastructure).  Restates motion vector prediction
+ * for P macroblocks (standard 8.4.1.1 P_Skip, 8.4.1.3 median / directional prediction with the neighbour
+ * availability of 6.4.8 and 6.4.11.7; reference calc_mv*, h264.cpp:6669-6724, 7379-7604) from the inputs the device
+ * kernel (h264_mv_kernel) gets -- partitions with vector differences, b2_h264_mb.flags -- and compares vectors,
+ * reference frames and geometry with the motion records the host front end derived.  Returns the number of
+ * differing records (0 = the derivations agree), -1 if the picture carries no partitions next to its records.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { int ref, mvx, mvy; } mv_nb;       /* ref: -2 unavailable, -1 intra */
+
+static int med3(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : (c < mn ? mn : c); }
+
+int oracle_h264_mv_check(const b2_h264_picture *p)
+{
+	if (p->mv_on_device || !p->parts || p->n_parts != p->n_mcs) return -1;
+	const int w4 = p->mb_w * 4, n_mbs = p->mb_w * p->mb_h;
+	int8_t *fref = (int8_t *)malloc((size_t)n_mbs * 16);
+	int16_t *fmv = (int16_t *)calloc((size_t)n_mbs * 32, sizeof(int16_t));
+	memset(fref, -2, (size_t)n_mbs * 16);           /* nothing decoded yet */
+	int bad = 0;
+	for (int mb = 0; mb < n_mbs; ++mb) {
+		const b2_h264_mb *m = &p->mbs[mb];
+		const int mbx = mb % p->mb_w, mby = mb / p->mb_w, avail = m->flags >> B2_H4_NB_SHIFT;
+		if (m->type != B2_H4_INTER) {
+			for (int y = 0; y < 4; ++y) memset(&fref[(size_t)(mby * 4 + y) * w4 + mbx * 4], -1, 4);
+			continue;
+		}
+		for (int i = 0; i < m->mc_cnt; ++i) {
+			const b2_h264_part *pt = &p->parts[m->mc_idx + i];
+			const b2_h264_mc *want = &p->mcs[m->mc_idx + i];
+			const int x4 = pt->pos & 3, y4 = pt->pos >> 2, pw = pt->size & 15, ph = pt->size >> 4;
+			mv_nb nb[4];      /* A left, B above, C above-right, D above-left */
+			const int dx[4] = {-1, 0, pw, -1}, dy[4] = {0, -1, -1, -1};
+			for (int k = 0; k < 4; ++k) {
+				int x = x4 + dx[k], y = y4 + dy[k];
+				int rx = x < 0 ? -1 : (x > 3 ? 1 : 0), ry = y < 0 ? -1 : 0;
+				int ok = ry == 0 ? (rx == 0 || (rx < 0 && (avail & 1))) : (rx == 0 ? (avail & 2) : (rx < 0 ? (avail & 8) : (avail & 4)));
+				nb[k].ref = -2; nb[k].mvx = nb[k].mvy = 0;
+				if (!ok) continue;
+				size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x;
+				nb[k].ref = fref[g];
+				if (nb[k].ref >= 0) { nb[k].mvx = fmv[g * 2]; nb[k].mvy = fmv[g * 2 + 1]; }
+			}
+			mv_nb a = nb[0], b = nb[1], c = nb[2].ref != -2 ? nb[2] : nb[3];
+			int px = 0, py = 0, done = 0;
+			if (m->flags & B2_H4_PSKIP) {
+				if (a.ref == -2 || b.ref == -2 || (a.ref == 0 && !a.mvx && !a.mvy) || (b.ref == 0 && !b.mvx && !b.mvy)) done = 1;
+			} else if (pw == 4 && ph == 2) {
+				if (i == 0 && b.ref == pt->ref_idx) { px = b.mvx; py = b.mvy; done = 1; }
+				if (i == 1 && a.ref == pt->ref_idx) { px = a.mvx; py = a.mvy; done = 1; }
+			} else if (pw == 2 && ph == 4) {
+				if (i == 0 && a.ref == pt->ref_idx) { px = a.mvx; py = a.mvy; done = 1; }
+				if (i == 1 && c.ref == pt->ref_idx) { px = c.mvx; py = c.mvy; done = 1; }
+			}
+			if (!done) {
+				if (b.ref == -2 && c.ref == -2 && a.ref != -2) { b = a; c = a; }
+				int ma = a.ref == pt->ref_idx, mb_ = b.ref == pt->ref_idx, mc = c.ref == pt->ref_idx;
+				if (ma + mb_ + mc == 1) { const mv_nb *s = ma ? &a : (mb_ ? &b : &c); px = s->mvx; py = s->mvy; }
+				else { px = med3(a.mvx, b.mvx, c.mvx); py = med3(a.mvy, b.mvy, c.mvy); }
+			}
+			int mvx = (int16_t)(px + pt->mvd[0]), mvy = (int16_t)(py + pt->mvd[1]);
+			for (int y = y4; y < y4 + ph; ++y)
+				for (int x = x4; x < x4 + pw; ++x) {
+					size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4 + x;
+					fref[g] = pt->ref_idx; fmv[g * 2] = (int16_t)mvx; fmv[g * 2 + 1] = (int16_t)mvy;
+				}
+			if (want->pos != pt->pos || want->size != pt->size || want->ref_frame[0] != pt->ref_frame || want->ref_frame[1] != -1 ||
+			    want->mv[0][0] != mvx || want->mv[0][1] != mvy) ++bad;
+		}
+	}
+	free(fref);
+	free(fmv);
+	return bad;
+}

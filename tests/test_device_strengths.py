@@ -1,4 +1,4 @@
-"""Deblocking strengths derived on the device (include/b2_recon.h b2_h264_picture.bs_on_device,
+"""Deblocking strengths and motion vectors (rank 3, Baseline streams) derived on the device ( include/b2_recon.h b2_h264_picture.bs_on_device,
 h264_bs_kernel).  Through the plugin table the front end leaves the strengths to the device whenever nobody reads the
 records on the host, so every golden / reference comparison of tests/test_h264.py already runs on device-derived
 strengths; here the two derivations are set against each other on the stream families whose strengths are hardest
@@ -38,8 +38,8 @@ def test_device_strengths_equal_host_strengths(name):
     dev, dev_launches = _decode(data, False)
     host, host_launches = _decode(data, True)
     assert dev == golden and host == golden
-    # one h264_bs_kernel launch per deblocked picture, and only when the device derives the strengths
-    assert dev_launches > host_launches and dev_launches - host_launches <= len(golden)
+    # h264_bs_kernel per deblocked picture (and h264_mv_kernel + h264_items_kernel per P picture of a Baseline stream) only when the device derives them
+    assert host_launches < dev_launches <= host_launches + 3 * len(golden)
 
 
 @pytest.mark.gpu
@@ -54,3 +54,12 @@ def test_device_strengths_on_writer_streams(args):
     dev, _ = _decode(data, False)
     host, _ = _decode(data, True)
     assert dev == host and dev == util.oracle_md5("h264", data)
+
+
+def test_oracle_restatements_of_the_device_derivations_run_on_tapped_pictures():
+    """CPU side: tests/util.py's picture tap runs oracle_h264_bs_check on every H.264 picture and oracle_h264_mv_check
+    on every picture that carries partitions (Baseline streams) -- here it is shown that the latter really happens."""
+    data = streams.generate("h264", streams.H264_CASES["h264_refs3"])
+    before = util.MV_CHECKED
+    md5s = util.oracle_md5("h264", data)
+    assert len(md5s) == 12 and util.MV_CHECKED - before == 11      # the IDR picture has no partitions

@@ -43,6 +43,9 @@ def ref_md5(data, ext, args=()):
             return [l.strip().decode() for l in f.read().split(b"\r\n") if l.strip()]
 
 
+MV_CHECKED = 0          # pictures whose partitions were checked against their motion records (oracle_h264_mv_check)
+
+
 def oracle_tap(dec, codec, pic):
     """Picture tap that reconstructs on the CPU oracle into the decoder's host frames."""
     fr = dec.frames
@@ -60,6 +63,12 @@ def oracle_tap(dec, codec, pic):
     # rules) must be the ones the host front end filled in: every tapped picture of every test stream checks it
     bad = o.oracle_h264_bs_check(C.c_void_p(pic))
     assert bad == 0, "%d macroblocks: strengths derived from the records differ from the host's" % bad
+    # likewise the motion vectors the device would predict from the partitions (Baseline streams carry them next to the
+    # records when a tap looks on): -1 = no partitions in this picture
+    bad = o.oracle_h264_mv_check(C.c_void_p(pic))
+    assert bad <= 0, "%d motion records differ from the vectors predicted from the partitions" % bad
+    global MV_CHECKED
+    MV_CHECKED += bad == 0
     return o.oracle_h264_picture(C.c_void_p(pic), luma, chroma)
 
 
