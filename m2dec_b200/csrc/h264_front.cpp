@@ -763,7 +763,8 @@ private:
 		// the records on the host -- a picture tap (the CPU oracle of tests/, bench.py's capture for the kernel replay),
 		// parse-only runs -- or the application asked for it (b2_context_set_host_strengths; B2_HOST_BS=1 for A/B runs).
 		static const bool env_host_bs = getenv("B2_HOST_BS") != nullptr;
-		host_bs_ = env_host_bs || backend.host_bs() || backend.has_tap() || backend.device_off();
+		static const bool env_as_device = getenv("B2_PARSE_AS_DEVICE") != nullptr;      // (tools/parsebench: time the parse of the product path)
+		host_bs_ = env_host_bs || backend.host_bs() || ((backend.has_tap() || backend.device_off()) && !env_as_device);
 		// Motion vectors: Baseline-profile streams (P and I slices only, no weighted prediction, no
 		// co-located motion to keep for later direct prediction) hand the device motion vector DIFFERENCES; prediction,
 		// motion records and the inter kernel's work list are made there.  Needs the device-side strengths.
