@@ -106,6 +106,7 @@ public:
 	// CABAC only (9.3.3.1.1.6 / .7): per 4x4 block |mvd| (x, y; saturated) and "refIdx > 0 and not
 	// direct-predicted", both zero for everything that codes neither
 	bool cabac = false;
+	bool keep_motion = true;
 	std::vector<uint8_t> mvd[2];
 	std::vector<uint8_t> refgt0[2];
 
@@ -123,11 +124,14 @@ public:
 			refgt0[l].assign(n * 16, 0);
 		}
 	}
-	void begin_picture() {
+	// motion: the picture's 4x4 motion field is kept here (not when the device predicts the vectors: nothing on the
+	// host reads it then, and clearing it is 1.6 MB of stores per 1080p picture)
+	void begin_picture(bool motion = true) {
+		keep_motion = motion;
 		for (auto &m : mb) { m = MbInfo(); m.slice = 0xffff; }
 		std::fill(nnz.begin(), nnz.end(), 0);
 		std::fill(ipred.begin(), ipred.end(), 2);
-		for (int l = 0; l < 2; ++l) {
+		for (int l = 0; l < 2 && motion; ++l) {
 			std::fill(mv[l].begin(), mv[l].end(), 0);
 			std::fill(ref[l].begin(), ref[l].end(), -2);
 			std::fill(refpic[l].begin(), refpic[l].end(), -1);
@@ -158,7 +162,7 @@ public:
 	void open_mb(int mbx, int mby, int cur_slice) {
 		MbInfo &m = mb[(size_t)mby * mb_w + mbx];
 		m.slice = (uint16_t)cur_slice;
-		for (int y = 0; y < 4; ++y) {
+		for (int y = 0; y < 4 && keep_motion; ++y) {
 			size_t g = (size_t)(mby * 4 + y) * w4 + mbx * 4;
 			const uint32_t undecoded = 0xFEFEFEFEu;       // -2 in every block
 			memcpy(&ref[0][g], &undecoded, 4);

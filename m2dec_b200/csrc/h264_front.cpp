@@ -747,18 +747,6 @@ private:
 		f.height = (int16_t)sps.height;
 		for (int i = 0; i < 4; ++i) f.crop[i] = (int16_t)sps.crop[i];
 		backend.ensure(B2_CODEC_H264, sps.width, sps.height, num_frames_);
-		if (ctx_.mb_w != mb_w_ || ctx_.mb_h != mb_h_) ctx_.resize(mb_w_, mb_h_);
-		ctx_.begin_picture();
-		size_t n = (size_t)mb_w_ * mb_h_;
-		mbs_.assign(n, b2_h264_mb());
-		dbk_.assign(n, b2_h264_dbk());
-		mb_seen_.assign(n, 0);
-		mcs_.clear();
-		for (auto &b : items_) b.clear();
-		for (auto &b : items_first_) b.clear();
-		coef_used_ = 0;
-		n_intra_ = 0;
-		any_deblock_ = false;
 		// Deblocking strengths: derived on the device from the motion records unless someone looks at
 		// the records on the host -- a picture tap (the CPU oracle of tests/, bench.py's capture for the kernel replay),
 		// parse-only runs -- or the application asked for it (b2_context_set_host_strengths; B2_HOST_BS=1 for A/B runs).
@@ -773,6 +761,18 @@ private:
 		keep_parts_ = !dev_mv_ && backend.has_tap() && sps.profile_idc == 66;
 		parts_.clear();
 		item_bound_ = 0;
+		if (ctx_.mb_w != mb_w_ || ctx_.mb_h != mb_h_) ctx_.resize(mb_w_, mb_h_);
+		ctx_.begin_picture(!dev_mv_);
+		size_t n = (size_t)mb_w_ * mb_h_;
+		mbs_.assign(n, b2_h264_mb());
+		dbk_.assign(n, b2_h264_dbk());
+		mb_seen_.assign(n, 0);
+		mcs_.clear();
+		for (auto &b : items_) b.clear();
+		for (auto &b : items_first_) b.clear();
+		coef_used_ = 0;
+		n_intra_ = 0;
+		any_deblock_ = false;
 		slice_num_ = -1;
 		mb_addr_ = 0;
 		pic_open_ = true;
@@ -1415,7 +1415,7 @@ private:
 					if (!kind_is_intra(o.kind)) avail_intra &= ~(1 << b);
 				}
 		}
-		ctx_.set_intra_motion(mbx, mby);
+		if (ctx_.keep_motion) ctx_.set_intra_motion(mbx, mby);
 		n_intra_++;
 		uint8_t *nnz = ctx_.nnz_of(mbx, mby);
 		int8_t *ip = ctx_.ipred_of(mbx, mby);

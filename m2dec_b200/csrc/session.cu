@@ -30,8 +30,9 @@ enum { NSLOT = 4 };
 #include <chrono>
 namespace {
 const bool g_trace = getenv("B2_TRACE") != nullptr;
-enum { T_CHECK, T_SLOT, T_PACK, T_H2D, T_LAUNCH, T_EVENTS, T_D2H_QUEUE, T_FETCH_WAIT, T_CREATE, T_N };
-const char *const g_trace_names[T_N] = {"record check", "slot wait", "pack SoA", "H2D enqueue", "kernel launches", "event records", "D2H enqueue", "frame wait", "session create (per picture)"};
+enum { T_CHECK, T_SLOT, T_PACK, T_H2D, T_LAUNCH, T_EVENTS, T_D2H_QUEUE, T_FETCH_WAIT, T_CREATE, T_GPU, T_N };
+// ("device time" is not the calling thread's: copy + kernels of a picture on the session's stream, from CUDA events)
+const char *const g_trace_names[T_N] = {"record check", "slot wait", "pack SoA", "H2D enqueue", "kernel launches", "event records", "D2H enqueue", "frame wait", "session create (per picture)", "device time"};
 struct Trace {
 	double us[T_N] = {0};
 	uint64_t pictures = 0;
@@ -115,6 +116,7 @@ struct StageSlot {
 	uint8_t *dev;
 	size_t cap, cap_host, cap_dev;
 	cudaEvent_t done;      // recorded after the kernels that read the slot
+	cudaEvent_t t0, t1;    // B2_TRACE: before the picture's copy / after its kernels, with timing
 	bool pending;
 };
 
@@ -152,6 +154,17 @@ struct b2_session {
 };
 
 extern "C" const char *b2_last_error(void) { return b2::g_err; }
+
+// A server runs one session (two CUDA streams) per decoding thread.  CUDA maps streams onto 8 hardware queues by
+// default; streams that share a queue wait for each other's work in issue order, and with 16 sessions the pictures
+// of one stream sat behind another stream's kernels for milliseconds (16 host threads: 2.87 k -> 3.3 k frames/s
+// with 16 queues; 32 queues: 3.1 k).  The variable is read when the process creates its CUDA context, so it is
+// set when the library is loaded, unless the application chose a value itself.
+namespace {
+struct MoreQueues {
+	MoreQueues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0); }
+} g_more_queues;
+}  // namespace
 
 extern "C" int b2_device_count(void) {
 	int n = 0;
@@ -216,7 +229,7 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 extern "C" void b2_session_destroy(b2_session *s) {
 	if (!s) return;
 	if (g_trace && s->trace.pictures) {
-		char line[512];
+		char line[768];
 		int n = snprintf(line, sizeof(line), "m2dec_b200 trace: %llu pictures, us per picture:", (unsigned long long)s->trace.pictures);
 		for (int k = 0; k < T_N; ++k) n += snprintf(line + n, sizeof(line) - n, " %s %.1f,", g_trace_names[k], s->trace.us[k] / s->trace.pictures);
 		fprintf(stderr, "%s\n", line);
@@ -227,6 +240,7 @@ extern "C" void b2_session_destroy(b2_session *s) {
 		cache_put(s->dev, true, s->slots[i].cap_host, s->slots[i].host);
 		cache_put(s->dev, false, s->slots[i].cap_dev, s->slots[i].dev);
 		if (s->slots[i].done) cudaEventDestroy(s->slots[i].done);
+		if (s->slots[i].t0) { cudaEventDestroy(s->slots[i].t0); cudaEventDestroy(s->slots[i].t1); }
 	}
 	if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
 	for (int i = 0; i < 12; ++i)
@@ -255,7 +269,12 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 	if (sl->pending) {
 		B2_CUDA_OK(cudaEventSynchronize(sl->done));
 		sl->pending = false;
+		if (g_trace && sl->t0) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, sl->t0, sl->t1) == cudaSuccess) s->trace.us[T_GPU] += 1000.0 * ms;
+		}
 	}
+	if (g_trace && !sl->t0) { cudaEventCreate(&sl->t0); cudaEventCreate(&sl->t1); }
 	if (sl->cap < bytes) {
 		cache_put(s->dev, true, sl->cap_host, sl->host);
 		cache_put(s->dev, false, sl->cap_dev, sl->dev);
@@ -479,6 +498,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	if (!dev_mv && p->n_items) stream_copy(sl->host + off_items, p->items, (size_t)p->n_items * 4);
 	_mm_sfence();                 // the streamed stores are globally visible before the copy engine is told to read
 	s->trace.lap(T_PACK);
+	if (g_trace) cudaEventRecord(sl->t0, s->stream);
 	B2_CUDA_OK(cudaMemcpyAsync(sl->dev, sl->host, total, cudaMemcpyHostToDevice, s->stream));
 	s->h2d_bytes += total;
 	if (before_write(s, p->dst) < 0) return -1;
@@ -487,6 +507,7 @@ extern "C" int b2_session_submit_h264(b2_session *s, const b2_h264_picture *p) {
 	                p->n_intra > 0 && !h264_intra_sparse((int)p->n_intra, (int)p->n_mbs), p->n_intra > 0 && h264_intra_sparse((int)p->n_intra, (int)p->n_mbs),
 	                p->deblock != 0, s->sync_area, &s->launches, p->n_items_first, p->bs_on_device != 0, dev_mv) < 0) return -1;
 	s->trace.lap(T_LAUNCH);
+	if (g_trace) cudaEventRecord(sl->t1, s->stream);
 	B2_CUDA_OK(cudaEventRecord(sl->done, s->stream));
 	B2_CUDA_OK(cudaEventRecord(s->frame_done[p->dst], s->stream));
 	s->frame_written[p->dst] = true;
