@@ -28,6 +28,7 @@ enum { NSLOT = 4 };
 // B2_TRACE=1: where the calling (parsing) thread's time goes inside this file, per session, printed at destroy.
 // Development aid for the end-to-end path (every microsecond here is taken from the parse).
 #include <chrono>
+#include <unistd.h>
 namespace {
 const bool g_trace = getenv("B2_TRACE") != nullptr;
 enum { T_CHECK, T_SLOT, T_PACK, T_H2D, T_LAUNCH, T_EVENTS, T_D2H_QUEUE, T_FETCH_WAIT, T_CREATE, T_GPU, T_N };
@@ -162,7 +163,14 @@ extern "C" const char *b2_last_error(void) { return b2::g_err; }
 // set when the library is loaded, unless the application chose a value itself.
 namespace {
 struct MoreQueues {
-	MoreQueues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0); }
+	MoreQueues() {
+		// one queue per host core (a session per decoding thread is the expected use), within what CUDA accepts
+		long n = sysconf(_SC_NPROCESSORS_ONLN);
+		n = n < 8 ? 8 : (n > 32 ? 32 : n);
+		char v[8];
+		snprintf(v, sizeof(v), "%ld", n);
+		setenv("CUDA_DEVICE_MAX_CONNECTIONS", v, 0);
+	}
 } g_more_queues;
 }  // namespace
 
