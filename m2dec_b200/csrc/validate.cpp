@@ -17,7 +17,7 @@ extern "C" int b2_h264_picture_check(const b2_h264_picture *p, int nframes) {
 		return -1;
 	}
 	if ((unsigned)p->dst >= (unsigned)nframes) { set_error("H.264 picture: destination frame %d outside the pool", p->dst); return -1; }
-	if (!p->mbs || !p->dbk || (p->n_mcs && !p->mcs) || (p->n_coef_recs && !p->coefs) || (p->n_items && !p->items) || p->n_items_first > p->n_items) {
+	if (!p->mbs || !p->dbk || (p->n_mcs && !p->mcs) || (p->n_coef_recs && !p->coefs) || (!p->mv_on_device && p->n_items && !p->items) || p->n_items_first > p->n_items) {
 		set_error("H.264 picture: missing arrays");
 		return -1;
 	}

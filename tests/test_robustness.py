@@ -214,3 +214,57 @@ def test_damaged_fixtures_on_the_device(name):
     good = open(os.path.join(util.GOLDEN, "h264_basic.264"), "rb").read()
     want = open(os.path.join(util.GOLDEN, "h264_basic.md5")).read().split()
     assert m2dec_b200.decode_file("h264", good) == want
+
+
+# ---- the product path's records (strengths and, for Baseline streams, vectors left to the device) -------------------
+def test_h264_damaged_streams_in_device_mode_records_are_sound():
+    """With B2_PARSE_AS_DEVICE the front end emits what it sends to a device session when nobody looks on
+    (bs_on_device, and mv_on_device with partitions instead of motion records for Baseline streams): those records
+    must pass the structural check on damaged input as well.  The switch is read once per process: a child runs it."""
+    import subprocess
+    import sys
+    code = r'''
+import random, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import test_robustness as T
+for name in ("h264_basic", "h264_intra_ipcm", "h264_cabac_b_mixed"):
+    data = T._golden(name, ".264")
+    full = T._decode("h264", data)
+    assert full[1] > 0 and full[2] == 0, (name, full)
+    rng = random.Random(7)
+    for cut in sorted(rng.sample(range(1, len(data)), 25)):
+        assert T._decode("h264", data[:cut])[2] == 0, (name, cut)
+    for trial in range(40):
+        d = bytearray(data)
+        for _ in range(rng.choice([1, 1, 2, 8, 64])):
+            pos = rng.randrange(len(d))
+            d[pos] = rng.randrange(256) if rng.random() < 0.5 else d[pos] ^ (1 << rng.randrange(8))
+        assert T._decode("h264", bytes(d))[2] == 0, (name, trial)
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2_PARSE_AS_DEVICE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["h264_basic", "h264_intra_ipcm", "h264_cabac_b_mixed"])
+def test_h264_damaged_streams_through_the_device(name):
+    """Damaged streams through the product path (device-derived strengths and vectors): every decode ends, and the
+    device is still sound afterwards -- the clean stream decodes to its golden MD5s."""
+    data = _golden(name, ".264")
+    golden = open(os.path.join(util.GOLDEN, name + ".md5")).read().split()
+    rng = random.Random(11)
+    for trial in range(30):
+        d = bytearray(data)
+        if trial % 3 == 0:
+            d = d[:rng.randrange(1, len(d))]
+        else:
+            for _ in range(rng.choice([1, 2, 8, 64])):
+                pos = rng.randrange(len(d))
+                d[pos] = rng.randrange(256) if rng.random() < 0.5 else d[pos] ^ (1 << rng.randrange(8))
+        try:
+            m2dec_b200.decode_file("h264", bytes(d))
+        except RuntimeError:
+            pass
+    assert m2dec_b200.decode_file("h264", data) == golden
