@@ -565,7 +565,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "streams": ne, "repetitions": a.e2e_reps, "frames": e2e_frames, "md5_checked_frames": e2e_checked[0], "host_threads": threads_n, "seconds": e2e_s,
                 "host": e2e_host,
-                "path": "m2d_func_table_t (h264d_gpu_func): host ES -> parse -> H2D SoA -> kernels -> D2H every output frame"},
+                "path": "m2d_func_table_t (h264d_gpu_func): host ES -> entropy decode -> H2D SoA (partitions with vector differences, coefficient levels) -> kernels (motion vector prediction, work list, strengths, reconstruction) -> D2H every output frame"},
         "gpu_launches": int(st.launches) * a.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
