@@ -82,7 +82,10 @@ static int on_header(void *arg, void *) {
 	a->f->get_info(a->ctx, &info);
 	int w = (info.src_width + 15) & ~15, h = (info.src_height + 15) & ~15, n = info.frame_num + 16;
 	if (n > 16 && a->f == m2d_gpu_func) n = 16;
-	a->bufs.assign(n, std::vector<uint8_t>((size_t)w * h * 3 / 2 + 32));
+	// (allocated once: the sequence header comes back with every GOP / repetition, 50 MB of clearing and copying each
+	// time would be timed as parse)
+	const size_t fb = (size_t)w * h * 3 / 2 + 32;
+	if ((int)a->bufs.size() != n || a->bufs[0].size() != fb) a->bufs.assign(n, std::vector<uint8_t>(fb));
 	a->frames.assign(n, m2d_frame_t());
 	for (int i = 0; i < n; ++i) {
 		uint8_t *p = a->bufs[i].data();
