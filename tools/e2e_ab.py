@@ -12,7 +12,7 @@ nums = [int(x) for x in args[:cut]]
 n_streams = nums[0] if nums else 64
 reps = nums[1] if len(nums) > 1 else 5
 configs = args[cut + 1:] or ["default="]
-threads = os.cpu_count() or 1
+threads = int(os.environ.get("E2E_THREADS", os.cpu_count() or 1))
 with tempfile.TemporaryDirectory() as d:
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(threads) as ex:
