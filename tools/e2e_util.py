@@ -1,0 +1,7 @@
+import os, subprocess, sys, tempfile
+sys.path.insert(0, '/root/repo'); import bench
+from concurrent.futures import ThreadPoolExecutor
+with ThreadPoolExecutor(16) as ex: data = list(ex.map(lambda i: bench.make_stream(100 + i, 16), range(128)))
+d = tempfile.mkdtemp(); paths = bench.write_streams(data, d)
+r = subprocess.run([bench.E2EBENCH, 'h264', '16', '4', '0', '0'] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+print(r.stderr[-600:])

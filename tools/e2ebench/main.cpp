@@ -281,6 +281,7 @@ int main(int argc, char **argv) {
 		if (rep == 1) sample_start();       // (repetition 0 is the warm-up)
 		std::atomic<int> next(0);
 		auto t0 = std::chrono::steady_clock::now();
+		std::vector<double> busy(threads, 0.0);       // when each thread ran out of streams
 		std::vector<std::thread> ths;
 		for (int t = 0; t < threads; ++t)
 			ths.emplace_back([&, t]() {
@@ -298,9 +299,14 @@ int main(int argc, char **argv) {
 					if (!run_stream(&a, &streams[i], &streams[i])) ok = false;
 				}
 				frames += a.n_frames;
+				busy[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 			});
 		for (auto &th : ths) th.join();
 		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		double sum = 0;
+		for (double b : busy) sum += b;
+		// (second figure: how much of the repetition the average thread had work for -- the rest is the tail)
+		fprintf(stderr, "e2ebench threads busy %.0f %% of repetition %d\n", 100.0 * sum / (threads * dt), rep);
 		fprintf(stderr, "e2ebench repetition %d: %.3f s\n", rep, dt);
 		seconds += dt;
 	}
