@@ -39,6 +39,16 @@ extern "C" int b2_h264_picture_check(const b2_h264_picture *p, int nframes) {
 		if (ok && (m.type == B2_H4_I4x4 || m.type == B2_H4_I8x8))
 			for (int k = 0; k < 8; ++k) ok &= (m.i4_modes[k] & 15) <= 8 && (m.i4_modes[k] >> 4) <= 8;
 		if (!ok) { set_error("H.264 picture: macroblock %u has a field out of range", i); return -1; }
+		// the kernels take a macroblock's neighbours from these flags: none may point outside the picture
+		{
+			const uint32_t mbx = i % (uint32_t)p->mb_w, mby = i / (uint32_t)p->mb_w;
+			const int fl = p->dbk[i].flags, nb = p->mv_on_device ? m.flags >> B2_H4_NB_SHIFT : 0;
+			if (((fl & B2_DBK_LEFT_EDGE) && mbx == 0) || ((fl & B2_DBK_TOP_EDGE) && mby == 0) ||
+			    ((nb & 1) && mbx == 0) || ((nb & 2) && mby == 0) || ((nb & 4) && (mby == 0 || mbx + 1 >= (uint32_t)p->mb_w)) || ((nb & 8) && (mbx == 0 || mby == 0))) {
+				set_error("H.264 picture: macroblock %u names a neighbour outside the picture", i);
+				return -1;
+			}
+		}
 		const b2_h264_dbk &d = p->dbk[i];
 		if (d.qp_y < -51 || d.qp_y > 51 || d.qp_cb < -51 || d.qp_cb > 51 || d.qp_cr < -51 || d.qp_cr > 51 || d.alpha_off < -12 || d.alpha_off > 12 || d.beta_off < -12 || d.beta_off > 12) {
 			set_error("H.264 picture: deblocking record %u out of range", i);
