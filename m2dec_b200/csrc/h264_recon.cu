@@ -10,6 +10,10 @@
 //   h264_deblock3_kernel     K4     in-loop filter from the per-MB strength records: two pictures (packed 16x2 lanes)
 //   h264_wave_kernel<2>             and two macroblock rows per warp (batched launches) / one picture per launch
 //                                   (plugin path).
+//   h264_bs_kernel                  deblocking strengths from the motion records: pictures whose
+//                                   host left them out (b2_h264_picture.bs_on_device)
+//   h264_mv_kernel           \      motion vector prediction in a macroblock-row wavefront, motion records and the inter
+//   h264_items_kernel        /      kernel's work list: pictures with mv_on_device (Baseline streams)
 //
 // Arithmetic restated from the reference (src/lib/h264.cpp): dequant tables 964-1054 and
 // coeff_writeback 2005-2022; 4x4 transform 2145-2269; 8x8 transform 3942-4080; DC transforms
