@@ -1763,9 +1763,6 @@ private:
 	}
 
 	void finish_mb(int mbx, int mby, const Pps &pps, int dbk_qp) {
-#ifdef NO_FINISH
-		return;
-#endif
 		const SliceHeader &h = hdr_;
 		b2_h264_dbk &d = dbk_[(size_t)mby * mb_w_ + mbx];
 		memset(&d, 0, sizeof(d));

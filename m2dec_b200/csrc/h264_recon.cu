@@ -228,7 +228,7 @@ __device__ __forceinline__ uint32_t vfinish2(uint32_t t) {
 #define B2_I5_THREADS 128
 #endif
 #ifndef B2_I5_CTAS
-#define B2_I5_CTAS 5
+#define B2_I5_CTAS 4
 #endif
 constexpr int I5_THREADS = B2_I5_THREADS;
 
