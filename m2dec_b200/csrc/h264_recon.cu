@@ -1481,7 +1481,7 @@ constexpr int WAVE_WARPS = B2_WAVE_WARPS;
 #define B2_DBK_WARPS_PER_SM 24
 #endif
 #ifndef B2_INTRA_WARPS_PER_SM
-#define B2_INTRA_WARPS_PER_SM 32
+#define B2_INTRA_WARPS_PER_SM 40
 #endif
 constexpr int WAVE_CTAS_DBK = B2_DBK_WARPS_PER_SM / WAVE_WARPS, WAVE_CTAS_INTRA = B2_INTRA_WARPS_PER_SM / WAVE_WARPS;    // resident CTAs per SM (register budget)
 
