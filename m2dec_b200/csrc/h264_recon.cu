@@ -2127,6 +2127,9 @@ h264_mv_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, i
 	// blocks (x, y), x = -1 .. 4, y = -1 .. 3 of the current macroblock's neighbourhood at [y + 1][x + 1]
 	__shared__ int8_t s_ref[5][6];
 	__shared__ uint32_t s_mv[5][6];
+	// what the lanes fetch for lane 0 and store for it: the macroblock's partitions, the records made of them
+	__shared__ b2_h264_part s_part[16];
+	__shared__ uint4 s_rec[16][2];
 	int *ticket = sync_area;
 	int *progress = sync_area + 32;           // [n_jobs][mb_h]: macroblocks of the row whose motion is final
 	const int lane = threadIdx.x;
@@ -2137,45 +2140,68 @@ h264_mv_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, i
 		if (t >= n_jobs * mb_h) return;
 		const int j = t / mb_h, mby = t % mb_h;
 		const H4Job job = jobs[j];
-		if (!job.derive_mv || lane != 0) continue;
+		if (!job.derive_mv) continue;
 		int *prog_above = progress + (size_t)j * mb_h + mby - 1, *prog_mine = progress + (size_t)j * mb_h + mby;
 		b2_h264_mc *mcs = const_cast<b2_h264_mc *>(job.mcs);
 		int seen = 0;
+		// The derivation is serial (lane 0); the other lanes turn its memory round trips into one per macroblock: the
+		// header of the NEXT macroblock is fetched while this one is worked on, partitions and the row above come in
+		// with one load per lane, records / owners / motion field go out with one store per lane.
+		uint32_t hdr_next = 0, idx_next = 0, cnt_next = 0;
+		if (lane == 0) {
+			const b2_h264_mb *m0 = job.mbs + (size_t)mby * mb_w;
+			hdr_next = __ldg(reinterpret_cast<const uint32_t *>(m0));             // type, flags, ...
+			idx_next = __ldg(&m0->mc_idx);
+			cnt_next = __ldg(&m0->mc_cnt);
+		}
 		for (int mbx = 0; mbx < mb_w; ++mbx) {
 			const int mb = mby * mb_w + mbx;
-			const b2_h264_mb *m = job.mbs + mb;
-			const int type = m->type, flags = m->flags, avail = flags >> B2_H4_NB_SHIFT;
+			// header of this macroblock (lane 0 had asked for it), broadcast; then the request for the next one
+			const uint32_t h0 = __shfl_sync(0xffffffffu, hdr_next, 0), mc_idx = __shfl_sync(0xffffffffu, idx_next, 0);
+			const int cnt = min((int)__shfl_sync(0xffffffffu, cnt_next, 0), 16);
+			if (lane == 0 && mbx + 1 < mb_w) {
+				const b2_h264_mb *m1 = job.mbs + mb + 1;
+				hdr_next = __ldg(reinterpret_cast<const uint32_t *>(m1));
+				idx_next = __ldg(&m1->mc_idx);
+				cnt_next = __ldg(&m1->mc_cnt);
+			}
+			const int type = h0 & 255, flags = (h0 >> 8) & 255, avail = flags >> B2_H4_NB_SHIFT;
 			int8_t *fr = job.field_ref + (size_t)mb * 16;
 			uint32_t *fm = job.field_mv + (size_t)mb * 16;
-			if (type != B2_H4_INTER) {
-				for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t *>(fr)[i] = 0xffffffffu;     // -1: intra
-				for (int i = 0; i < 16; ++i) fm[i] = 0;
-				// the next macroblock's left column
-				for (int y = 0; y < 4; ++y) { s_ref[y + 1][4] = -1; s_mv[y + 1][4] = 0; }
-			} else {
-				if (mby > 0 && (avail & 14)) {
-					const int want = min(mbx + 2, mb_w);
-					if (seen < want) seen = spin_until(prog_above, want);
+			const bool inter = type == B2_H4_INTER;
+			// ---- fetch: partitions (lanes 0..15), the row above (lanes 16..21) ------------------------------------------
+			if (inter && lane < cnt) s_part[lane] = job.parts[mc_idx + lane];
+			if (inter && mby > 0 && (avail & 14)) {
+				const int want = min(mbx + 2, mb_w);
+				if (seen < want) {
+					if (lane == 0) seen = spin_until(prog_above, want);
+					seen = __shfl_sync(0xffffffffu, seen, 0);
 				}
-				// neighbourhood: left column = the previous macroblock's right column (still in the tile), the row above from
-				// the motion field (written by another warp: through L2)
+			}
+			if (lane == 0) {
+				// left column = the previous macroblock's right column (still in the tile); the rest is not decoded yet / outside
 				for (int y = 0; y < 4; ++y) {
-					if (avail & 1) { s_ref[y + 1][0] = s_ref[y + 1][4]; s_mv[y + 1][0] = s_mv[y + 1][4]; }
+					if (inter && (avail & 1)) { s_ref[y + 1][0] = s_ref[y + 1][4]; s_mv[y + 1][0] = s_mv[y + 1][4]; }
 					else s_ref[y + 1][0] = -2;
-					for (int x = 0; x < 5; ++x) s_ref[y + 1][x + 1] = -2;                          // not decoded yet / outside
+					for (int x = 0; x < 5; ++x) s_ref[y + 1][x + 1] = inter ? -2 : -1;
 				}
-				for (int x = -1; x < 5; ++x) {
-					const bool ok = x < 0 ? (avail & 8) != 0 : (x < 4 ? (avail & 2) != 0 : (avail & 4) != 0);
-					int r = -2;
-					uint32_t v = 0;
-					if (ok) {
-						const int nmb = mb - mb_w + (x < 0 ? -1 : (x < 4 ? 0 : 1)), blk = 12 + (x & 3);
-						r = (int8_t)__ldcg(reinterpret_cast<const char *>(job.field_ref) + (size_t)nmb * 16 + blk);
-						v = __ldcg(job.field_mv + (size_t)nmb * 16 + blk);
-					}
-					s_ref[0][x + 1] = (int8_t)r;
-					s_mv[0][x + 1] = v;
+			}
+			if (inter && lane >= 16 && lane < 22) {
+				const int x = lane - 17;                   // -1 .. 4
+				const bool ok = x < 0 ? (avail & 8) != 0 : (x < 4 ? (avail & 2) != 0 : (avail & 4) != 0);
+				int r = -2;
+				uint32_t v = 0;
+				if (ok) {
+					const int nmb = mb - mb_w + (x < 0 ? -1 : (x < 4 ? 0 : 1)), blk = 12 + (x & 3);
+					r = (int8_t)__ldcg(reinterpret_cast<const char *>(job.field_ref) + (size_t)nmb * 16 + blk);
+					v = __ldcg(job.field_mv + (size_t)nmb * 16 + blk);
 				}
+				s_ref[0][x + 1] = (int8_t)r;
+				s_mv[0][x + 1] = v;
+			}
+			__syncwarp();
+			// ---- derive (lane 0) -------------------------------------------------------------------------------------------
+			if (lane == 0 && inter) {
 				auto nb = [&](int x, int y) {
 					MvNb n;
 					n.ref = s_ref[y + 1][x + 1];
@@ -2184,10 +2210,8 @@ h264_mv_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, i
 					n.mvy = (int16_t)(v >> 16);
 					return n;
 				};
-				const b2_h264_part *parts = job.parts + m->mc_idx;
-				const int cnt = m->mc_cnt;
 				for (int i = 0; i < cnt; ++i) {
-					const b2_h264_part pt = parts[i];
+					const b2_h264_part pt = s_part[i];
 					const int x4 = pt.pos & 3, y4 = pt.pos >> 2, pw = pt.size & 15, ph = pt.size >> 4, refidx = pt.ref_idx;
 					MvNb a = nb(x4 - 1, y4), b = nb(x4, y4 - 1), c = nb(x4 + pw, y4 - 1);
 					if (c.ref == -2) c = nb(x4 - 1, y4 - 1);
@@ -2218,17 +2242,33 @@ h264_mv_kernel(const H4Job *__restrict__ jobs, int n_jobs, int mb_w, int mb_h, i
 					for (int y = y4; y < y4 + ph; ++y)
 						for (int x = x4; x < x4 + pw; ++x) { s_ref[y + 1][x + 1] = (int8_t)refidx; s_mv[y + 1][x + 1] = packed; }
 					// the motion record: list 0 only, default weights (include/b2_recon.h b2_h264_mc)
-					uint4 *rec = reinterpret_cast<uint4 *>(mcs + m->mc_idx + i);
-					rec[0] = make_uint4((uint32_t)pt.pos | ((uint32_t)pt.size << 8) | ((uint32_t)(uint8_t)pt.ref_frame << 16) | 0xff000000u,
-					                    (uint32_t)(uint8_t)refidx | 0x0000ff00u, packed, 0u);
-					rec[1] = make_uint4(0x01010101u, 0x00000101u, 0u, 0u);
-					job.owner[m->mc_idx + i] = (uint32_t)mb;
+					s_rec[i][0] = make_uint4((uint32_t)pt.pos | ((uint32_t)pt.size << 8) | ((uint32_t)(uint8_t)pt.ref_frame << 16) | 0xff000000u,
+					                         (uint32_t)(uint8_t)refidx | 0x0000ff00u, packed, 0u);
+					s_rec[i][1] = make_uint4(0x01010101u, 0x00000101u, 0u, 0u);
 				}
-				for (int y = 0; y < 4; ++y)
-					for (int x = 0; x < 4; ++x) { fr[y * 4 + x] = s_ref[y + 1][x + 1]; fm[y * 4 + x] = s_mv[y + 1][x + 1]; }
 			}
+			__syncwarp();
+			// ---- store: records and owners (one per lane), the macroblock's motion field (16 lanes) ------------------------
+			if (inter && lane < cnt) {
+				uint4 *rec = reinterpret_cast<uint4 *>(mcs + mc_idx + lane);
+				rec[0] = s_rec[lane][0];
+				rec[1] = s_rec[lane][1];
+				job.owner[mc_idx + lane] = (uint32_t)mb;
+			}
+			if (lane < 16) {
+				const int x = lane & 3, y = lane >> 2;
+				fr[lane] = s_ref[y + 1][x + 1];
+				fm[lane] = inter ? s_mv[y + 1][x + 1] : 0u;
+			}
+			__syncwarp();
+			if (!inter && lane == 0)
+				for (int y = 0; y < 4; ++y) s_mv[y + 1][4] = 0;          // (the next macroblock's left column: intra, no vector)
 			// rows below read this macroblock's bottom row
-			if (mby + 1 < mb_h) st_release(prog_mine, mbx + 1);
+			if (mby + 1 < mb_h) {
+				__threadfence();
+				__syncwarp();
+				if (lane == 0) st_release(prog_mine, mbx + 1);
+			}
 		}
 	}
 }

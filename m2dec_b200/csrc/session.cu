@@ -289,8 +289,11 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 		sl->host = sl->dev = nullptr;
 		sl->cap = 0;
 		// sized for a dense picture of this geometry so that it rarely has to grow
+		// and in 4 MiB steps: slots of one geometry then nearly always ask for the same size, which the buffer cache has
+		// (an odd size is a cudaMalloc + cudaMallocHost in the middle of decoding, and those stall every stream of the device)
 		size_t cap = bytes + bytes / 2 + 4096, typical = (size_t)s->width * s->height * 3 / 2, got_h = 0, got_d = 0;
 		if (cap < typical) cap = typical;
+		cap = (cap + (4u << 20) - 1) & ~(size_t)((4u << 20) - 1);
 		if (cache_get(s->dev, true, cap, (void **)&sl->host, &got_h) < 0) return -1;
 		if (cache_get(s->dev, false, cap, (void **)&sl->dev, &got_d) < 0) return -1;
 		sl->cap_host = got_h;

@@ -1,6 +1,6 @@
 """A/B of the end-to-end leg (tools/e2ebench) under different environments, same streams, on the GPU box:
     python tools/e2e_ab.py [streams] [reps] -- NAME=ENV1=1,ENV2=x NAME2= ...
-prints frames/s of the timed repetitions (the first is the warm-up) per configuration, two rounds."""
+prints frames/s of the timed repetitions (the first two are the warm-up) per configuration, two rounds."""
 import os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -26,9 +26,9 @@ with tempfile.TemporaryDirectory() as d:
                 if kv:
                     k, _, v = kv.partition("=")
                     env[k] = v or "1"
-            r = subprocess.run([bench.E2EBENCH, "h264", str(threads), str(reps + 1), "0", "0"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+            r = subprocess.run([bench.E2EBENCH, "h264", str(threads), str(reps + 2), "0", "0"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
             t = [float(l.split()[-2]) for l in r.stderr.splitlines() if l.startswith("e2ebench repetition")]
-            if r.returncode != 0 or len(t) != reps + 1:
+            if r.returncode != 0 or len(t) != reps + 2:
                 print(name, "FAILED", r.stderr[-300:])
                 continue
-            print("%-12s %8.1f frames/s  (threads %d, %d streams, repetitions %s)" % (name, n_streams * 16 * reps / sum(t[1:]), threads, n_streams, " ".join("%.3f" % x for x in t[1:])), flush=True)
+            print("%-12s %8.1f frames/s  (threads %d, %d streams, repetitions %s)" % (name, n_streams * 16 * reps / sum(t[2:]), threads, n_streams, " ".join("%.3f" % x for x in t[2:])), flush=True)

@@ -1,7 +1,9 @@
 // e2ebench — end-to-end decode through the plugin table (m2d_func_table_t) from a native multi-threaded host:
 // elementary streams in host memory -> parse -> H2D of the records -> kernels -> D2H of every output frame into
 // page-locked application frame buffers.  One decoder context per stream, T host threads, the decode loop of the
-// reference application (src/app/m2decoder.h:132-157, h264dec.cpp:251-257).  Links libm2dec_b200.so; the Python
+// reference application (src/app/m2decoder.h:132-157, h264dec.cpp:251-257); a thread keeps two contexts and collects the
+// last frames of a finished stream after the first pictures of its next one (start_stream / step_stream /
+// finish_stream below), as a server multiplexing streams would.  Links libm2dec_b200.so; the Python
 // bench drives it and checks its frame hashes against the frames the (MD5-verified) Python path produced.
 //   e2ebench <h264|mpeg2> <threads> <repetitions> <cuda device> <md5 0|1|2> file...
 // md5 = 2: digest mode (b2_context_set_md5): the frames are hashed ON THE DEVICE and only their 16-byte MD5s come
@@ -151,7 +153,7 @@ struct App {
 	bool digest = false;                 // md5 = 2
 	std::deque<m2d_frame_t> pending;     // frames whose digest has not been collected yet
 };
-enum { DIGEST_LAG = 10 };
+enum { DIGEST_LAG = 10, OVERLAP_PICTURES = 3 };
 
 static void collect_digest(App *a) {
 	uint8_t d[16];
@@ -214,25 +216,26 @@ static void post(App *a, const m2d_frame_t &fr) {
 	a->out->hashes.push_back(m.hex());
 }
 
-static int decode(App *a) {                       // reference m2decoder.h:132-157
+static int decode(App *a) {                       // reference m2decoder.h:132-157 (the flush at the end of data: finish_stream)
 	void *c = a->ctx.data();
 	m2d_frame_t fr;
 	while (a->f->peek_decoded_frame(c, &fr, 0) <= 0) {
 		int err = a->f->decode_picture(c);
-		if (err < 0) {
-			while (a->f->peek_decoded_frame(c, &fr, 1) > 0) { post(a, fr); a->f->get_decoded_frame(c, &fr, 1); }
-			return err;
-		}
+		if (err < 0) return err;
 	}
 	a->f->get_decoded_frame(c, &fr, 0);
 	post(a, fr);
 	return a->f->decode_picture(c);
 }
 
-static bool run_stream(App *a, const Stream *in, Stream *out) {
+// A stream in three parts, so that a thread can have the end of one stream and the start of the next in flight at
+// the same time: the frames still inside the decoder when the data ends (the last pictures' copies need the device
+// another ~2 ms) are collected after the next stream's first pictures have been parsed, not waited for.
+static bool start_stream(App *a, const Stream *in, Stream *out) {
 	a->in = in;
 	a->out = out;
 	a->fed = false;
+	a->failed = false;
 	a->frames_w = a->frames_h = 0;
 	a->frames.clear();
 	if (a->hash || a->digest) out->hashes.clear();
@@ -242,18 +245,23 @@ static bool run_stream(App *a, const Stream *in, Stream *out) {
 	b2_context_set_device(c, a->device);
 	if (a->digest) b2_context_set_md5(c, 1);
 	dec_bits_set_callback(a->f->stream_pos(c), on_refill, a);
-	for (;;) {
-		int err = decode(a);
-		if (a->failed || err == -4) { b2_context_release(c); return false; }
-		if (err < 0) break;
-	}
-	m2d_frame_t fr;
-	while (a->f->peek_decoded_frame(c, &fr, 1) > 0) { post(a, fr); a->f->get_decoded_frame(c, &fr, 1); }
-	while (!a->pending.empty()) collect_digest(a);
-	if (a->failed) { b2_context_release(c); return false; }
-	b2_context_stats(c, out->stats);
-	b2_context_release(c);
 	return true;
+}
+// one step of the decode loop; false once the data has ended (or the stream failed)
+static bool step_stream(App *a) {
+	int err = decode(a);
+	if (a->failed || err == -4) { a->failed = true; return false; }
+	return err >= 0;
+}
+static bool finish_stream(App *a) {
+	void *c = a->ctx.data();
+	m2d_frame_t fr;
+	if (!a->failed)
+		while (a->f->peek_decoded_frame(c, &fr, 1) > 0) { post(a, fr); a->f->get_decoded_frame(c, &fr, 1); }
+	while (!a->failed && !a->pending.empty()) collect_digest(a);
+	if (!a->failed) b2_context_stats(c, a->out->stats);
+	b2_context_release(c);
+	return !a->failed;
 }
 
 int main(int argc, char **argv) {
@@ -273,7 +281,7 @@ int main(int argc, char **argv) {
 	}
 	if (b2_device_count() <= 0) { fprintf(stderr, "e2ebench: no CUDA device: %s\n", b2_last_error()); return 3; }
 	const m2d_func_table_t *f = h264 ? h264d_gpu_func : m2d_gpu_func;
-	std::vector<FramePool> pools(threads);
+	std::vector<FramePool> pools(2 * threads);
 	std::atomic<long> frames(0);
 	std::atomic<bool> ok(true);
 	double seconds = 0;
@@ -285,20 +293,33 @@ int main(int argc, char **argv) {
 		std::vector<std::thread> ths;
 		for (int t = 0; t < threads; ++t)
 			ths.emplace_back([&, t]() {
-				App a;
-				a.f = f;
-				a.h264 = h264;
-				a.device = device;
-				a.hash = hash;
-				a.digest = digest;
-				a.ctx.resize(f->context_size);
-				a.pool = &pools[t];
+				App slot[2];
+				for (int k = 0; k < 2; ++k) {
+					App &a = slot[k];
+					a.f = f;
+					a.h264 = h264;
+					a.device = device;
+					a.hash = hash;
+					a.digest = digest;
+					a.ctx.resize(f->context_size);
+					a.pool = &pools[2 * t + k];
+				}
+				int cur = 0;
+				bool waiting = false;            // slot[1 - cur] has reached the end of its data and awaits finish_stream
 				for (;;) {
 					const int i = next.fetch_add(1);
 					if (i >= (int)streams.size()) break;
-					if (!run_stream(&a, &streams[i], &streams[i])) ok = false;
+					App &a = slot[cur];
+					if (!start_stream(&a, &streams[i], &streams[i])) { ok = false; continue; }
+					int steps = 0;
+					while (step_stream(&a))
+						if (waiting && ++steps == OVERLAP_PICTURES) { if (!finish_stream(&slot[1 - cur])) ok = false; waiting = false; }
+					if (waiting && !finish_stream(&slot[1 - cur])) ok = false;
+					waiting = true;
+					cur = 1 - cur;
 				}
-				frames += a.n_frames;
+				if (waiting && !finish_stream(&slot[1 - cur])) ok = false;
+				frames += slot[0].n_frames + slot[1].n_frames;
 				busy[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 			});
 		for (auto &th : ths) th.join();

@@ -77,6 +77,8 @@ def launch(path, out_txt):
         a[1] += float(r[14]) / 1e6
     def is_replay(k, g):       # batched launches: the strip kernel has one grid row per picture, the persistent kernels many CTAs
         x, y, _ = [int(t) for t in g.strip("()").split(",")]
+        if k.startswith(("h264_mv", "h264_items", "h264_bs")):       # derivation kernels: the plugin path's (one picture per launch)
+            return False
         return y > 1 or (not k.startswith("h264_inter5") and not k.startswith("mpeg2") and x > 64)
     big = sum(v[1] for (k, g), v in agg.items() if is_replay(k, g))
     lines = ["kernel                                 grid             launches     total ms     avg us    share of the replay launches"]
