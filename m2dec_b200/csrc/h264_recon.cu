@@ -28,6 +28,8 @@ namespace {
 
 __constant__ uint8_t c_blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
 __constant__ uint8_t c_blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+// Intra4x4 blocks a warp's two halves predict in the same step (-1: the half idles)
+__constant__ int8_t c_i4_pair[2][10] = {{0, 1, 2, 3, 6, 7, 10, 11, 14, 15}, {-1, -1, 4, 5, 8, 9, 12, 13, -1, -1}};
 __constant__ uint8_t c_r2b[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
 __constant__ uint8_t c_norm_adjust[6][3] = {{10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23}};
 __constant__ uint8_t c_norm_adjust8[6][6] = {{20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
@@ -994,10 +996,15 @@ __device__ void intra_mb(const H4Job &job, const b2_h264_mb &m, int mbx, int mby
 
 	// ---- luma -----------------------------------------------------------------------------------
 	if (m.type == B2_H4_I4x4) {
-		for (int k = 0; k < 16; ++k) {
-			const int bx = c_blk_x[k], by = c_blk_y[k];
-			if (lane < 16) {
-				int x = lane & 3, y = lane >> 2;
+		// Ten steps instead of sixteen: blocks 2 | 4, 3 | 5, 6 | 8, 7 | 9, 10 | 12, 11 | 13 of the decoding order depend on
+		// nothing of each other (a block's top-right neighbour counts only if it comes earlier in that order), so the two
+		// halves of the warp take one each.
+#pragma unroll 1
+		for (int s = 0; s < 10; ++s) {
+			const int k = c_i4_pair[lane >> 4][s];
+			if (k >= 0) {
+				const int bx = c_blk_x[k], by = c_blk_y[k];
+				int x = lane & 3, y = (lane >> 2) & 3;
 				int mode = (m.i4_modes[k >> 1] >> ((k & 1) * 4)) & 15;
 				int v = pred4x4_sample(tl, bx, by, mode, blk_avail(k, m.intra_avail), x, y);
 				if ((tl.has >> k) & 1) v = clip255(v + tl.res[k][y * 4 + x]);
