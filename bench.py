@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=512, help="independent 1080p streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream (IDR + P)")
     ap.add_argument("--prep-threads", type=int, default=16, help="host threads that write and parse the lanes' streams (untimed)")
-    ap.add_argument("--e2e-streams", type=int, default=32, help="streams per end-to-end repetition (at least; eight per host thread are used when that is more)")
+    ap.add_argument("--e2e-streams", type=int, default=32, help="streams per end-to-end repetition (at least; sixteen per host thread are used when that is more)")
     ap.add_argument("--e2e-reps", type=int, default=6, help="timed repetitions of the end-to-end pool run")
     ap.add_argument("--verify-lanes", type=int, default=32, help="lanes whose every frame is MD5-checked against the reference")
     a = ap.parse_args()
@@ -378,9 +378,9 @@ def main():
 
     # ---- end to end through the plugin table with host buffers --------------------------------
     threads_n = max(1, min(a.lanes, ncores // world))     # the ranks of a node share its host cores
-    # streams per repetition: at least eight per host thread, so that a repetition measures the pool's rate and not the
+    # streams per repetition: at least sixteen per host thread, so that a repetition measures the pool's rate and not the
     # start-up and drain of one short stream per thread (a 32-core box ran the former 32 streams one per thread)
-    ne = min(a.lanes, max(a.e2e_streams, 8 * threads_n))
+    ne = min(a.lanes, max(a.e2e_streams, 16 * threads_n))
     threads_n = min(threads_n, ne)
     counts = [None] * ne
     frames_out = [0] * ne
