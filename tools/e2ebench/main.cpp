@@ -13,6 +13,7 @@
 // times go to stderr), then with md5=1 one line per stream: "stream i n m0 m1 ..." = the MD5 of every output frame
 // as `h264dec -O` of the reference prints it (cropped luma rows, then cropped interleaved-CbCr rows;
 // src/app/filewrite.h:11-29, 99-124).
+#include <malloc.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -265,6 +266,11 @@ static bool finish_stream(App *a) {
 }
 
 int main(int argc, char **argv) {
+	// A decoder context allocates a few MB of tables per stream; above glibc's mmap threshold every stream start maps and
+	// every release unmaps them, and 16 threads then queue for the address-space lock and fault the pages in again
+	// (+2 % end to end with the heap kept).
+	mallopt(M_MMAP_THRESHOLD, 1 << 30);
+	mallopt(M_TRIM_THRESHOLD, 1 << 30);
 	if (argc < 7) { fprintf(stderr, "usage: e2ebench h264|mpeg2 threads repetitions device hash file...\n"); return 2; }
 	const bool h264 = !strcmp(argv[1], "h264");
 	const int threads = atoi(argv[2]), reps = atoi(argv[3]), device = atoi(argv[4]);
