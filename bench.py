@@ -453,9 +453,9 @@ def main():
                             raise SystemExit("bench.py: e2ebench MD5 mismatch on stream %d" % i)
                         e2e_checked[0] += len(goldens[i])
             barrier()
-            # repetitions 0 and 1 are the warm-up (CUDA context, page-locked frame buffers, the library's buffer cache: the
+            # the first three repetitions are the warm-up (CUDA context, page-locked frame buffers, the library's buffer cache: the
             # second pass still allocates where its threads meet the streams in another order)
-            WARM = 2
+            WARM = 3
             r = subprocess.run([E2EBENCH, "h264", str(threads_n), str(a.e2e_reps + WARM), str(local), "0"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
             if r.returncode != 0:
                 raise SystemExit("bench.py: e2ebench failed: " + r.stderr[-500:])

@@ -74,6 +74,7 @@ int cache_get(int dev, bool pinned, size_t bytes, void **out, size_t *actual = n
 			return 0;
 		}
 	}
+	if (g_trace) fprintf(stderr, "m2dec_b200 trace: buffer cache miss: %zu MiB %s\n", bytes >> 20, pinned ? "page-locked" : "device");
 	if (pinned) B2_CUDA_OK(cudaMallocHost(out, bytes));
 	else B2_CUDA_OK(cudaMalloc(out, bytes));
 	return 0;
@@ -291,7 +292,8 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 		// sized for a dense picture of this geometry so that it rarely has to grow
 		// and in 4 MiB steps: slots of one geometry then nearly always ask for the same size, which the buffer cache has
 		// (an odd size is a cudaMalloc + cudaMallocHost in the middle of decoding, and those stall every stream of the device)
-		size_t cap = bytes + bytes / 2 + 4096, typical = (size_t)s->width * s->height * 3 / 2, got_h = 0, got_d = 0;
+		// (2.5 frames' worth: what a dense 1080p picture's records plus the device-side scratch of mv_on_device come to)
+		size_t cap = bytes + bytes / 2 + 4096, typical = (size_t)s->width * s->height * 15 / 4, got_h = 0, got_d = 0;
 		if (cap < typical) cap = typical;
 		cap = (cap + (4u << 20) - 1) & ~(size_t)((4u << 20) - 1);
 		if (cache_get(s->dev, true, cap, (void **)&sl->host, &got_h) < 0) return -1;
