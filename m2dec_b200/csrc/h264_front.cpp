@@ -1782,8 +1782,8 @@ private:
 		// what the device needs to derive the strengths itself (b2_h264_picture.bs_on_device)
 		const uint8_t *nnz = ctx_.nnz_of(mbx, mby);
 		{
-			unsigned nzm = 0;
-			for (int i = 0; i < 16; ++i) nzm |= (unsigned)(nnz[i] != 0) << i;
+			// bit i = nnz[i] != 0: one compare of the sixteen counts with zero
+			const unsigned nzm = ~(unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(nnz)), _mm_setzero_si128())) & 0xffffu;
 			mbs_[(size_t)mby * mb_w_ + mbx].nnz4x4 = (uint16_t)nzm;
 			d.bs_mode = (uint8_t)((bs_reduced_ & 7) | (bslice_ ? B2_BS_B_SLICE : 0));
 		}
