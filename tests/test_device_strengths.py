@@ -48,6 +48,7 @@ def test_device_strengths_equal_host_strengths(name):
     "mbw=40 mbh=30 frames=7 seed=32 refs=3 bframes=2 profile=77 direct_spatial=0 slices=3 deblock=2 intra_pct=15 direct_pct=40 skip_pct=20",
     "mbw=20 mbh=12 frames=10 seed=34 refs=2 bframes=1 profile=77 direct_8x8_inference=0 cabac=1",
     "mbw=120 mbh=68 frames=3 seed=33 crop_bottom=8 intra_pct=10 skip_pct=15 coded_pct=25",
+    "mbw=120 mbh=68 frames=5 seed=35 crop_bottom=8 refs=3 slices=4 deblock=2 mv_range=300 mv_out=60 skip_pct=30",
 ])
 def test_device_strengths_on_writer_streams(args):
     data = streams.generate("h264", args)
