@@ -185,6 +185,27 @@ extern "C" int b2_device_count(void) {
 	return n;
 }
 
+// Gives a staging slot buffers for at least `bytes`.  Sized for a dense picture of this geometry (2.5 frames' worth: what
+// a dense 1080p picture's records plus the device-side scratch of mv_on_device come to) so that it rarely has to
+// grow, and in 4 MiB steps: slots of one geometry then nearly always ask for the same size, which the buffer cache
+// has (an odd size is a cudaMalloc + cudaMallocHost in the middle of decoding, and those stall every stream of
+// the device).
+static int slot_grow(b2_session *s, StageSlot *sl, size_t bytes) {
+	cache_put(s->dev, true, sl->cap_host, sl->host);
+	cache_put(s->dev, false, sl->cap_dev, sl->dev);
+	sl->host = sl->dev = nullptr;
+	sl->cap = 0;
+	size_t cap = bytes + bytes / 2 + 4096, typical = (size_t)s->width * s->height * 15 / 4, got_h = 0, got_d = 0;
+	if (cap < typical) cap = typical;
+	cap = (cap + (4u << 20) - 1) & ~(size_t)((4u << 20) - 1);
+	if (cache_get(s->dev, true, cap, (void **)&sl->host, &got_h) < 0) return -1;
+	if (cache_get(s->dev, false, cap, (void **)&sl->dev, &got_d) < 0) return -1;
+	sl->cap_host = got_h;
+	sl->cap_dev = got_d;
+	sl->cap = got_h < got_d ? got_h : got_d;
+	return 0;
+}
+
 static int session_build(b2_session *s) {
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
@@ -196,7 +217,12 @@ static int session_build(b2_session *s) {
 	if (cache_get(s->dev, false, s->frame_bytes * s->nframes + H4_POOL_TAIL, (void **)&s->frames, &s->frames_alloc) < 0) return -1;
 	B2_CUDA_OK(cudaMemsetAsync(s->frames, 0, s->frame_bytes * s->nframes, s->stream));
 	if (cache_get(s->dev, false, h264_sync_bytes(1, s->width / 16, s->height / 16), (void **)&s->sync_area, &s->sync_alloc) < 0) return -1;
-	for (int i = 0; i < NSLOT; ++i) B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
+	for (int i = 0; i < NSLOT; ++i) {
+		B2_CUDA_OK(cudaEventCreateWithFlags(&s->slots[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
+		// all slots at once: a process then reaches the number of buffers it will ever hold as soon as its threads have
+		// their sessions open, not a few passes over the streams later
+		if (slot_grow(s, &s->slots[i], 1) < 0) return -1;
+	}
 	return 0;
 }
 
@@ -284,24 +310,7 @@ static int acquire_slot(b2_session *s, size_t bytes, StageSlot **out) {
 		}
 	}
 	if (g_trace && !sl->t0) { cudaEventCreate(&sl->t0); cudaEventCreate(&sl->t1); }
-	if (sl->cap < bytes) {
-		cache_put(s->dev, true, sl->cap_host, sl->host);
-		cache_put(s->dev, false, sl->cap_dev, sl->dev);
-		sl->host = sl->dev = nullptr;
-		sl->cap = 0;
-		// sized for a dense picture of this geometry so that it rarely has to grow
-		// and in 4 MiB steps: slots of one geometry then nearly always ask for the same size, which the buffer cache has
-		// (an odd size is a cudaMalloc + cudaMallocHost in the middle of decoding, and those stall every stream of the device)
-		// (2.5 frames' worth: what a dense 1080p picture's records plus the device-side scratch of mv_on_device come to)
-		size_t cap = bytes + bytes / 2 + 4096, typical = (size_t)s->width * s->height * 15 / 4, got_h = 0, got_d = 0;
-		if (cap < typical) cap = typical;
-		cap = (cap + (4u << 20) - 1) & ~(size_t)((4u << 20) - 1);
-		if (cache_get(s->dev, true, cap, (void **)&sl->host, &got_h) < 0) return -1;
-		if (cache_get(s->dev, false, cap, (void **)&sl->dev, &got_d) < 0) return -1;
-		sl->cap_host = got_h;
-		sl->cap_dev = got_d;
-		sl->cap = got_h < got_d ? got_h : got_d;
-	}
+	if (sl->cap < bytes && slot_grow(s, sl, bytes) < 0) return -1;
 	*out = sl;
 	return 0;
 }

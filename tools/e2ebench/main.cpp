@@ -154,7 +154,10 @@ struct App {
 	bool digest = false;                 // md5 = 2
 	std::deque<m2d_frame_t> pending;     // frames whose digest has not been collected yet
 };
-enum { DIGEST_LAG = 10, OVERLAP_PICTURES = 3 };
+#ifndef B2_DIGEST_LAG
+#define B2_DIGEST_LAG 10
+#endif
+enum { DIGEST_LAG = B2_DIGEST_LAG, OVERLAP_PICTURES = 3 };
 
 static void collect_digest(App *a) {
 	uint8_t d[16];
