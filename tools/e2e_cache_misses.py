@@ -1,5 +1,8 @@
+"""Buffer-cache misses (cudaMalloc / cudaMallocHost inside a session) per repetition of tools/e2ebench, from the B2_TRACE
+lines of the library; run on the GPU box: python tools/e2e_cache_misses.py"""
 import os, subprocess, sys, tempfile
-sys.path.insert(0, '/root/repo'); import bench
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); import bench
 from concurrent.futures import ThreadPoolExecutor
 with ThreadPoolExecutor(16) as ex: data = list(ex.map(lambda i: bench.make_stream(100 + i, 16), range(128)))
 d = tempfile.mkdtemp(); paths = bench.write_streams(data, d)

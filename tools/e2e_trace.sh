@@ -1,7 +1,9 @@
-cd /root/repo
+# Where a host thread's time goes in the end-to-end leg (B2_TRACE=1 lines of the library, last repetition), at 16, 8 and 1
+# threads; run on the GPU box: bash tools/e2e_trace.sh
+cd "$(dirname "$0")/.."
 python - <<'PY'
 import sys, os, subprocess, tempfile, re, collections
-sys.path.insert(0, '/root/repo'); import bench
+sys.path.insert(0, os.getcwd()); import bench
 from concurrent.futures import ThreadPoolExecutor
 with ThreadPoolExecutor(16) as ex: data = list(ex.map(lambda i: bench.make_stream(100 + i, 16), range(64)))
 d = tempfile.mkdtemp(); paths = bench.write_streams(data, d)

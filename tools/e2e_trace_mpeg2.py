@@ -1,5 +1,8 @@
+"""MPEG-2 (BASELINE config 4) end to end: rate at 16 and 1 host threads, the parse alone, the reference CLI on one stream;
+run on the GPU box: python tools/e2e_trace_mpeg2.py"""
 import os, subprocess, sys, tempfile, re, collections
-sys.path.insert(0, '/root/repo'); import bench
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); import bench
 from concurrent.futures import ThreadPoolExecutor
 args = "mbw=120 mbh=68 frames=12 seed=%d bframes=2 gop=12 mv_range=64"
 with ThreadPoolExecutor(16) as ex: data = list(ex.map(lambda i: subprocess.run([bench.STREAMGEN, 'mpeg2', *(args % (100+i)).split()], stdout=subprocess.PIPE, check=True).stdout, range(64)))
