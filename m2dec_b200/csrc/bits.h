@@ -83,6 +83,7 @@ public:
 	// bits still unread; negative once the parse has consumed zeros fed past the end
 	inline long bits_left() const { return (long)(end_ - p_) * 8 + n_ - (long)fake_ * 8; }
 	inline bool overrun() const { return bits_left() < 0; }
+	const uint8_t *end_ptr() const { return end_; }
 	// byte pointer of the current position (call when byte aligned)
 	const uint8_t *byte_ptr() const {
 		long back = (n_ >> 3) - fake_;

@@ -15,6 +15,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include "bits.h"
 #include "h264_cabac_tables.h"
 #include "h264_common.h"
@@ -36,14 +37,23 @@ struct CabacModels {
 	}
 };
 
-// 9.3.3.2: arithmetic decoding engine on top of the front end's bit reader
+// 9.3.3.2: arithmetic decoding engine.  codIOffset is kept with `bits_` bits of the stream already behind it
+// (value_ = codIOffset << bits_ | the next bits_ bits of the stream): renormalisation and bypass bins then only move
+// bits_, and the stream is touched once per 32 bits instead of once per renormalisation.  The comparison
+// codIOffset >= codIRange becomes value_ >= codIRange << bits_.  The engine reads the slice data itself, from the
+// byte position the front end's bit reader stands at when start() is called; the bit reader is moved only for I_PCM.
 class CabacDec {
 public:
 	CabacModels m;
-	void start(BitReader *br) {
+	void start(BitReader *br) {          // (the reader is byte aligned: cabac_alignment_one_bit / after pcm samples)
 		br_ = br;
+		start_ = p_ = br->byte_ptr();
+		end_ = br->end_ptr();
 		range_ = 510;
-		offset_ = br->get(9);
+		value_ = 0;
+		bits_ = -9;                       // nine bits of the first fetch are codIOffset itself
+		fetched_ = 0;
+		refill();
 	}
 	inline int bin(int ctx, int /*unused*/) {
 		uint8_t &s = m.st[ctx];
@@ -51,10 +61,11 @@ public:
 		int mps = s & 1;
 		const uint32_t lps = h4t::range_tab_lps[p][(range_ >> 6) & 3];
 		range_ -= lps;
+		const uint64_t scaled = (uint64_t)range_ << bits_;
 		int b;
-		if (offset_ >= range_) {
+		if (value_ >= scaled) {
 			b = mps ^ 1;
-			offset_ -= range_;
+			value_ -= scaled;
 			range_ = lps;
 			if (p == 0) mps ^= 1;
 			s = (uint8_t)((h4t::trans_idx_lps[p] << 1) | mps);
@@ -62,33 +73,61 @@ public:
 			b = mps;
 			if (p < 62) s = (uint8_t)(s + 2);
 		}
-		if (range_ < 256) renorm();
+		if (range_ < 256) {
+			const int sh = __builtin_clz(range_) - 23;      // at most 6 (the smallest LPS range is 6)
+			range_ <<= sh;
+			bits_ -= sh;
+			if (bits_ < 8) refill();
+		}
 		return b;
 	}
 	inline int bypass(int /*unused*/) {
-		offset_ = (offset_ << 1) | br_->get1();
-		if (offset_ >= range_) { offset_ -= range_; return 1; }
-		return 0;
+		--bits_;
+		const uint64_t scaled = (uint64_t)range_ << bits_;
+		int b = 0;
+		if (value_ >= scaled) { value_ -= scaled; b = 1; }
+		if (bits_ < 8) refill();
+		return b;
 	}
 	inline int term(int /*unused*/) {
 		range_ -= 2;
-		if (offset_ >= range_) return 1;
-		if (range_ < 256) renorm();
+		if (value_ >= ((uint64_t)range_ << bits_)) return 1;
+		if (range_ < 256) {
+			range_ <<= 1;
+			if (--bits_ < 8) refill();
+		}
 		return 0;
 	}
 	// After term() == 1 for mb_type I_PCM.  The nine bits the offset register holds at that
 	// point are exactly what the encoder's flush (9.3.4.5) wrote, its first-ever output bit
-	// having been dropped (firstBitFlag), so the read position already sits after the flush and
-	// only pcm_alignment_zero_bit remains (the reference does the same, h264.cpp:4741).
-	void before_pcm() { br_->byte_align(); }
+	// having been dropped (firstBitFlag), so the position after the bits this engine has consumed already sits after the
+	// flush and only pcm_alignment_zero_bit remains (the reference does the same, h264.cpp:4741): the bit reader, which
+	// still stands where start() found it, is moved there.
+	void before_pcm() { br_->skip_bytes((size_t)((consumed() + 7) >> 3)); }
+	// true once the engine has consumed bits beyond the end of the data (what it fetched ahead does not count)
+	bool overrun() const { return consumed() > (long)(end_ - start_) * 8; }
 private:
-	inline void renorm() {
-		const int sh = __builtin_clz(range_) - 23;
-		range_ <<= sh;
-		offset_ = (offset_ << sh) | br_->get(sh);
+	long consumed() const { return fetched_ - bits_; }
+	inline void refill() {
+		uint32_t v;
+		if (end_ - p_ >= 4) {
+			memcpy(&v, p_, 4);
+			v = __builtin_bswap32(v);
+			p_ += 4;
+		} else {                          // past the end: zeros (overrun() tells)
+			v = 0;
+			for (int i = 0; i < 4; ++i) v = (v << 8) | (p_ < end_ ? *p_++ : 0u);
+		}
+		value_ = (value_ << 32) | v;
+		bits_ += 32;
+		fetched_ += 32;
 	}
 	BitReader *br_ = nullptr;
-	uint32_t range_ = 510, offset_ = 0;
+	const uint8_t *start_ = nullptr, *p_ = nullptr, *end_ = nullptr;
+	uint64_t value_ = 0;
+	uint32_t range_ = 510;
+	int bits_ = 0;
+	long fetched_ = 0;
 };
 
 // Table 9-34 ctxIdxOffset per ctxBlockCat for coded_block_flag / significant_coeff_flag /

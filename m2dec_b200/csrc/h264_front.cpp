@@ -940,7 +940,7 @@ private:
 			if (skipped) { skip_mb(pps); last_dqp_ = 0; }
 			else macroblock(pps);
 			mb_addr_++;
-			if (br_.overrun()) throw BitError();
+			if (cs_.e.overrun()) throw BitError();
 			if (cs_.end_of_slice(0)) break;
 		}
 	}
