@@ -10,6 +10,7 @@
 // interlaced frame pictures with field prediction / field DCT).  Field pictures and MPEG-1
 // streams are rejected (the reference handles field pictures only partially).
 #include <exception>
+#include <memory>
 #include <new>
 #include <stdio.h>
 #include <stdlib.h>
@@ -326,7 +327,11 @@ private:
 		pic_fwd_ = ref_idx_[0];
 		pic_bwd_ = ref_idx_[1];
 		mbs_.assign((size_t)mb_w_ * mb_h_, b2_m2_mb());   // flags = 0: macroblock left untouched
-		coefs_.clear();
+		if (cap_blocks_ < 6 * mbs_.size()) {
+			cap_blocks_ = 6 * mbs_.size();
+			coefs_.reset(new int16_t[64 * cap_blocks_]);
+		}
+		n_blocks_ = 0;
 		picture_open_ = true;
 		host_valid_[cur_idx_] = false;
 	}
@@ -343,9 +348,9 @@ private:
 		p.fwd = pic_fwd_;
 		p.bwd = pic_bwd_;
 		p.n_mbs = (uint32_t)mbs_.size();
-		p.n_blocks = (uint32_t)(coefs_.size() / 64);
+		p.n_blocks = (uint32_t)n_blocks_;
 		p.mbs = mbs_.data();
-		p.coefs = coefs_.data();
+		p.coefs = coefs_.get();
 		backend.submit(B2_CODEC_MPEG2, &p);
 	}
 
@@ -517,9 +522,13 @@ private:
 	// Coefficient records of a whole macroblock at once: a bitstream error in the middle of the macroblock
 	// then leaves zero blocks behind, never a cbp that claims records which do not exist.
 	int16_t *new_blocks(int count) {
-		size_t n = coefs_.size();
-		coefs_.resize(n + 64 * (size_t)count, 0);
-		return &coefs_[n];
+		// (one allocation per picture size, sized for every macroblock coding all six blocks: growing a vector block by
+		// block cost a fifth of the parse of a stream's first pictures in reallocation copies and element-wise fills)
+		if (n_blocks_ + (size_t)count > cap_blocks_) throw BitError();   // more blocks than the picture can hold: overlapping slices
+		int16_t *p = coefs_.get() + 64 * n_blocks_;
+		memset(p, 0, 128 * (size_t)count);
+		n_blocks_ += (size_t)count;
+		return p;
 	}
 
 	// run/level decode + inverse quantisation (mpeg2.cpp:1020-1097); idx = first scan position
@@ -528,20 +537,27 @@ private:
 		const uint8_t *qm = qmat_[inter ? 1 : 0];
 		const uint8_t *scan = m2t::scan[alternate_scan_];
 		int sum = idx ? blk[0] : 0;
+		// One look at the stream per coefficient: 32 bits hold the longest code (16 bits) with its sign, and the escape
+		// (6) with run (6) and level (12).  Past the end of the unit the reader feeds zeros, which are an undefined
+		// code in both tables, so the overrun is looked at once per block.
 		for (;; ++idx) {
-			int v = tab.decode(br_);
+			const uint32_t w = br_.peek(32);
+			int len;
+			int v = tab.lookup(w, &len);
 			if (v == Vlc::INVALID) throw BitError();
-			if (v == m2t::DCT_EOB) break;
+			if (v == m2t::DCT_EOB) { br_.skip(len); break; }
 			int level, neg;
 			if (v == m2t::DCT_ESC) {
-				idx += (int)br_.get(6);
-				int l = (int)br_.get(12);
+				idx += (int)((w >> 20) & 63);
+				int l = (int)((w >> 8) & 4095);
 				neg = l >> 11;
 				level = neg ? 4096 - l : l;
+				br_.skip(24);
 			} else {
 				idx += v >> 6;
 				level = v & 63;
-				neg = (int)br_.get1();
+				neg = (int)((w >> (31 - len)) & 1);
+				br_.skip(len + 1);
 			}
 			if (idx >= 64) break;
 			int pos = scan[idx];
@@ -552,8 +568,8 @@ private:
 			else if (val < -2048) val = -2048;
 			sum += val;
 			blk[pos] = (int16_t)val;
-			if (br_.overrun()) throw BitError();
 		}
+		if (br_.overrun()) throw BitError();
 		if (!(sum & 1)) blk[63] ^= 1;   // mismatch control (mpeg2.cpp:974-983)
 	}
 
@@ -606,10 +622,11 @@ private:
 				motion_vectors(0, mt, mv, sel);
 				br_.skip(1);
 			}
+			const uint32_t first = (uint32_t)n_blocks_;
+			int16_t *blocks = new_blocks(6);      // (may refuse: before the record claims any block)
 			m->flags = B2_M2_INTRA | (dct_type ? B2_M2_FIELD_DCT : 0);
 			m->cbp = 0x3f;
-			m->coef_idx = (uint32_t)(coefs_.size() / 64);
-			int16_t *blocks = new_blocks(6);
+			m->coef_idx = first;
 			for (int k = 0; k < 6; ++k) {
 				int comp = k < 4 ? 0 : k - 3;
 				int dc = intra_dc(comp);
@@ -646,9 +663,10 @@ private:
 		if (type & m2t::MT_PATTERN) {
 			int cbp = t.cbp.decode(br_);
 			if (cbp == Vlc::INVALID) throw BitError();
-			m->cbp = (uint8_t)cbp;
-			m->coef_idx = (uint32_t)(coefs_.size() / 64);
+			const uint32_t first = (uint32_t)n_blocks_;
 			int16_t *blk = new_blocks(__builtin_popcount((unsigned)cbp & 63u)) - 64;
+			m->cbp = (uint8_t)cbp;
+			m->coef_idx = first;
 			for (int k = 0; k < 6; ++k) {
 				if (!(cbp & (1 << (5 - k)))) continue;
 				blk += 64;
@@ -687,7 +705,8 @@ private:
 	bool picture_open_;
 	int frames_mb_w_ = 0, frames_mb_h_ = 0;   // geometry set_frames was called for
 	std::vector<b2_m2_mb> mbs_;
-	std::vector<int16_t> coefs_;
+	std::unique_ptr<int16_t[]> coefs_;        // 64 coefficients per coded block, in macroblock order
+	size_t n_blocks_ = 0, cap_blocks_ = 0;
 	b2_m2_mb scratch_mb_;
 };
 

@@ -72,6 +72,14 @@ public:
 		br.skip(e->len);
 		return e->value;
 	}
+	// The same lookup on 32 bits of the stream the caller holds (nothing is consumed): the value and its code length,
+	// or INVALID.
+	inline __attribute__((always_inline)) int32_t lookup(uint32_t look32, int *len) const {
+		const Entry *e = &tab_[look32 >> (32 - l1_)];
+		if (e->len == -1) e = &tab_[(uint32_t)e->value + ((look32 >> (32 - maxlen_)) & ((1u << (maxlen_ - l1_)) - 1))];
+		*len = e->len;
+		return e->len <= 0 ? (int32_t)INVALID : e->value;
+	}
 	int maxlen() const { return maxlen_; }
 private:
 	struct Entry { int32_t value; int8_t len; };
