@@ -37,6 +37,19 @@ struct CabacModels {
 	}
 };
 
+// 9.3.3.2.1.1 for both outcomes: t[s] after the most probable symbol, t[128 + s] after the least probable one
+struct CabacNext {
+	uint8_t t[256];
+	constexpr CabacNext() : t() {
+		for (int s = 0; s < 128; ++s) {
+			const int p = s >> 1, mps = s & 1;
+			t[s] = (uint8_t)(p < 62 ? s + 2 : s);
+			t[128 + s] = (uint8_t)((h4t::trans_idx_lps[p] << 1) | (p == 0 ? mps ^ 1 : mps));
+		}
+	}
+};
+static constexpr CabacNext cabac_next{};
+
 // 9.3.3.2: arithmetic decoding engine.  codIOffset is kept with `bits_` bits of the stream already behind it
 // (value_ = codIOffset << bits_ | the next bits_ bits of the stream): renormalisation and bypass bins then only move
 // bits_, and the stream is touched once per 32 bits instead of once per renormalisation.  The comparison
@@ -55,39 +68,31 @@ public:
 		fetched_ = 0;
 		refill();
 	}
+	// Straight-line: which of the two sub-intervals the offset falls into is a coin the branch predictor loses a
+	// quarter of the time, so the interval, the offset and the next state are selected with a mask (the state transition
+	// of both outcomes comes from one table, cabac_next.t[LPS ? 128 + s : s]).
 	inline int bin(int ctx, int /*unused*/) {
-		uint8_t &s = m.st[ctx];
-		const int p = s >> 1;
-		int mps = s & 1;
-		const uint32_t lps = h4t::range_tab_lps[p][(range_ >> 6) & 3];
-		range_ -= lps;
-		const uint64_t scaled = (uint64_t)range_ << bits_;
-		int b;
-		if (value_ >= scaled) {
-			b = mps ^ 1;
-			value_ -= scaled;
-			range_ = lps;
-			if (p == 0) mps ^= 1;
-			s = (uint8_t)((h4t::trans_idx_lps[p] << 1) | mps);
-		} else {
-			b = mps;
-			if (p < 62) s = (uint8_t)(s + 2);
-		}
-		if (range_ < 256) {
-			const int sh = __builtin_clz(range_) - 23;      // at most 6 (the smallest LPS range is 6)
-			range_ <<= sh;
-			bits_ -= sh;
-			if (bits_ < 8) refill();
-		}
-		return b;
+		const uint32_t s = m.st[ctx];
+		const uint32_t lps = h4t::range_tab_lps[s >> 1][(range_ >> 6) & 3];
+		const uint32_t rmps = range_ - lps;
+		const uint64_t scaled = (uint64_t)rmps << bits_;
+		const uint64_t is_lps = (uint64_t)0 - (uint64_t)(value_ >= scaled);      // all ones: least probable symbol
+		value_ -= scaled & is_lps;
+		uint32_t r = rmps ^ ((rmps ^ lps) & (uint32_t)is_lps);
+		m.st[ctx] = cabac_next.t[s + ((uint32_t)is_lps & 128u)];
+		const int sh = __builtin_clz(r) - 23;              // 0 when the range is still >= 256; at most 6
+		range_ = r << sh;
+		bits_ -= sh;
+		if (bits_ < 8) refill();
+		return (int)((s ^ (uint32_t)is_lps) & 1);
 	}
-	inline int bypass(int /*unused*/) {
+	inline int bypass(int /*unused*/) {          // (signs and escape suffixes: a fair coin, so no branch either)
 		--bits_;
 		const uint64_t scaled = (uint64_t)range_ << bits_;
-		int b = 0;
-		if (value_ >= scaled) { value_ -= scaled; b = 1; }
+		const uint64_t one = (uint64_t)0 - (uint64_t)(value_ >= scaled);
+		value_ -= scaled & one;
 		if (bits_ < 8) refill();
-		return b;
+		return (int)(one & 1);
 	}
 	inline int term(int /*unused*/) {
 		range_ -= 2;
