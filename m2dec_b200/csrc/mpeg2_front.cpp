@@ -80,6 +80,7 @@ public:
 		ref_idx_[0] = ref_idx_[1] = 0;
 		memset(lru_, 0, sizeof(lru_));
 		out_state_ = 0;
+		outq_n_ = 0;
 		mb_x_ = -1;
 		mb_y_ = 0;
 		prev_type_ = 0;
@@ -96,7 +97,7 @@ public:
 		info->src_height = (int16_t)((height_ + 15) & ~15);
 		info->disp_width = (int16_t)disp_w_;
 		info->disp_height = (int16_t)disp_h_;
-		info->frame_num = 3;
+		info->frame_num = 4;      // two references, the picture in flight and a B picture waiting to go out (peek_frame)
 		info->crop[0] = 0;
 		info->crop[1] = (int16_t)(info->src_width - width_);
 		info->crop[2] = 0;
@@ -115,6 +116,7 @@ public:
 		num_frames_ = num;
 		memcpy(frames_, frames, sizeof(frames_[0]) * num);
 		cur_idx_ = -1;
+		outq_n_ = 0;
 		memset(host_valid_, 0, sizeof(host_valid_));
 		frames_mb_w_ = mb_w_;    // the application sized its buffers for this geometry (get_info); slices of
 		frames_mb_h_ = mb_h_;    // any other are ignored, their pictures would overrun those buffers
@@ -153,44 +155,83 @@ public:
 				picture_open_ = false;
 				return -1;
 			}
-			if (r == 1) return 1;
+			if (r == 1) {
+				note_due();
+				return 1;
+			}
 		}
 	}
 
-	int peek_frame(m2d_frame_t *out, int is_end) {
-		if (!out) return -1;
-		int idx;
-		if (pic_type_ == B_PIC) idx = cur_idx_;
-		else if (is_end && out_state_ > 0 && out_state_ < 4) idx = ref_idx_[1];
-		else idx = ref_idx_[0];
-		if (idx < 0) idx = 0;
+	// Frame-out.  mpeg2.cpp:1543-1587 decides which frame is due after a picture; the order of frames is the reference's.
+	// One thing is different: a frame is due the moment its picture (a B picture) or the picture after it (an anchor) has
+	// been decoded, which here is the moment that picture's records were handed to the device, so returning it at once
+	// would make the host wait for the copy, the kernel and the frame's way back, picture after picture.  With a fourth
+	// frame buffer (get_info asks for it) every due frame goes out one decode_picture call later instead: the frames wait
+	// in a queue whose last entry is held back until the next picture is done or the stream ends.  The held frame is
+	// either a reference or the most recently written buffer, neither of which the next picture takes (pick_frame), and
+	// a frame that has been handed out stays untouched until the next decode_picture call, as in the reference.
+	int peek_frame(m2d_frame_t *out, int is_end) { return out_frame(out, is_end, false); }
+	int get_frame(m2d_frame_t *out, int is_end) { return out_frame(out, is_end, true); }
+
+private:
+	bool can_defer() const { return num_frames_ >= 4; }
+	// after a complete picture: what the reference's frame-out would report now joins the queue
+	void note_due() {
+		int idx = -1;
+		if (pic_type_ == B_PIC) {
+			if (out_state_ & 1) { idx = cur_idx_; out_state_ &= ~1; }
+		} else if ((out_state_ >> 1) >= 2) {
+			idx = ref_idx_[0];
+			out_state_ -= 2;
+		}
+		if (idx < 0) return;
+		if (outq_n_ == MAX_OUTQ) {            // an application that never collects: the oldest frame is dropped
+			memmove(outq_, outq_ + 1, sizeof(outq_[0]) * (MAX_OUTQ - 1));
+			outq_n_--;
+		}
+		outq_[outq_n_++] = idx;
+	}
+	int hand_out(m2d_frame_t *out, int idx, bool fetch) {
 		*out = frames_[idx];
 		out->width = (int16_t)width_;
 		out->height = (int16_t)height_;
-		int ret;
-		if (pic_type_ != B_PIC) {
-			int s = out_state_ >> 1;
-			ret = (s == 0) ? 0 : (s == 1 ? (is_end != 0) : 1);
-		} else {
-			ret = out_state_ & 1;
-		}
-		if (ret > 0 && !host_valid_[idx]) {
+		if (fetch && !host_valid_[idx]) {
 			if (backend.fetch(idx, frames_[idx].luma, frames_[idx].chroma) < 0) return -1;
 			host_valid_[idx] = true;
 		}
-		return ret;
+		return 0;
 	}
-
-	int get_frame(m2d_frame_t *out, int is_end) {
-		int ret = peek_frame(out, is_end);
-		if (ret > 0) {
+	int out_frame(m2d_frame_t *out, int is_end, bool consume) {
+		if (!out) return -1;
+		const int hold = (!is_end && can_defer()) ? 1 : 0;
+		if (outq_n_ > hold) {
+			const int idx = outq_[0];
+			if (hand_out(out, idx, true) < 0) return -1;
+			if (consume) {
+				outq_n_--;
+				memmove(outq_, outq_ + 1, sizeof(outq_[0]) * outq_n_);
+			}
+			return 1;
+		}
+		// nothing queued (or only the held frame): at the end of the stream the last anchor is still due
+		int idx, ret;
+		if (pic_type_ == B_PIC) {
+			idx = cur_idx_;
+			ret = out_state_ & 1;
+		} else {
+			idx = (is_end && out_state_ > 0 && out_state_ < 4) ? ref_idx_[1] : ref_idx_[0];
+			const int st = out_state_ >> 1;
+			ret = (st == 0) ? 0 : (st == 1 ? (is_end != 0) : 1);
+		}
+		if (idx < 0) idx = 0;
+		if (hand_out(out, idx, ret > 0) < 0) return -1;
+		if (ret > 0 && consume) {
 			if (pic_type_ == B_PIC) out_state_ &= ~1;
 			else out_state_ -= 2;
 		}
 		return ret;
 	}
 
-private:
 	// ---- start-code dispatch (mpeg2.cpp:662-697) ---------------------------------------
 	int dispatch(int code) {
 		if (code == 0x00) return picture_header();
@@ -699,6 +740,8 @@ private:
 	bool host_valid_[MAX_M2_FRAMES];
 	int num_frames_, cur_idx_, ref_idx_[2], lru_[MAX_M2_FRAMES], out_state_;
 	int pic_fwd_, pic_bwd_;
+	enum { MAX_OUTQ = 8 };
+	int outq_[MAX_OUTQ], outq_n_;             // frames due, in output order (peek_frame)
 	int mb_x_, mb_y_, prev_type_;
 	int16_t dc_pred_[3];
 	int16_t pmv_[2][2][2];

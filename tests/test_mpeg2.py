@@ -96,3 +96,24 @@ def test_cuda_1080p_mp_hl():
     gpu = m2dec_b200.decode_file("mpeg2", data)
     want = util.ref_md5(data, "m2v") if util.have_ref() else util.oracle_md5("mpeg2", data)
     assert len(gpu) == 7 and gpu == want
+
+
+# ---- frame-out: the held frame (four buffers or more) and the reference's own timing (three buffers) ----------------
+@pytest.mark.parametrize("name", streams.MPEG2_GOLDEN)
+@pytest.mark.parametrize("outbuf", [-1, 0, 3])
+def test_frame_out_order_does_not_depend_on_the_pool(name, outbuf):
+    """get_info asks for four frame buffers so that a due frame can wait one picture for the device; an application
+    that hands over three (the reference's number) gets every frame at once, one that hands over more gets the same
+    frames in the same order."""
+    data, golden = _golden(name)
+    assert util.oracle_md5("mpeg2", data, outbuf=outbuf) == golden
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mpeg2_ipb", "mpeg2_field"])
+@pytest.mark.parametrize("outbuf", [-1, 0, 3])
+def test_cuda_frame_out_order_does_not_depend_on_the_pool(name, outbuf):
+    import m2dec_b200
+    data, golden = _golden(name)
+    assert m2dec_b200.decode_file("mpeg2", data, outbuf=outbuf) == golden
+    assert m2dec_b200.decode_file("mpeg2", data, outbuf=outbuf, device_md5=True) == golden

@@ -13,12 +13,13 @@ for i, s in enumerate(data):
 for th in (16, 1):
     n = 64 if th > 1 else 8
     r = subprocess.run([bench.E2EBENCH, 'mpeg2', str(th), '3', '0', '0'] + paths[:n], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, B2_TRACE='1'))
-    tl = [l for l in r.stderr.splitlines() if l.startswith('m2dec_b200 trace')][-n:]
+    miss = collections.Counter(l for l in r.stderr.splitlines() if 'buffer cache miss' in l)
+    tl = [l for l in r.stderr.splitlines() if l.startswith('m2dec_b200 trace') and 'per picture:' in l][-n:]
     acc = collections.defaultdict(float)
     for l in tl:
         for name, v in re.findall(r' ([a-zA-Z0-9 ()]+?) ([0-9.]+),', l.split('per picture:')[1]): acc[name.strip()] += float(v)
     reps = [float(l.split()[-2]) for l in r.stderr.splitlines() if l.startswith('e2ebench repetition')]
-    print('threads', th, 'fps', n * 12 / reps[-1], 'ms/frame/thread', 1000 * reps[-1] * th / (n * 12), {k: round(v / max(1,len(tl)), 1) for k, v in acc.items()})
+    print('threads', th, 'fps', n * 12 / reps[-1], 'ms/frame/thread', 1000 * reps[-1] * th / (n * 12), {k: round(v / max(1,len(tl)), 1) for k, v in acc.items()}, 'buffer cache misses', dict(miss), 'repetitions', reps)
 # parse alone
 r = subprocess.run([os.path.join(bench.ROOT, 'tools/_bin/parsebench'), 'mpeg2', paths[0], '20'], stdout=subprocess.PIPE, text=True); print(r.stdout.strip())
 import time
