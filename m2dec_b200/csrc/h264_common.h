@@ -10,6 +10,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <memory>
 #include <vector>
 
 namespace b2 { namespace h4 {
@@ -84,7 +85,8 @@ struct ColBlk {
 	int32_t refpoc;    // POC of the picture that vector points to
 };
 struct ColPic {
-	std::vector<ColBlk> b;
+	std::unique_ptr<ColBlk[]> b;  // n blocks (4x4 raster); plain storage: store_col writes every field of every block
+	size_t n = 0;
 	std::vector<uint8_t> shape;   // per macroblock, SHAPE_*
 };
 // result of direct prediction for one macroblock, per 4x4 block in raster order
@@ -299,10 +301,13 @@ public:
 	// snapshot of this picture's motion, taken when it becomes a reference picture
 	template <class F>
 	void store_col(ColPic &c, F poc_of_frame) const {
-		c.b.resize((size_t)w4 * h4);
+		if (c.n != (size_t)w4 * h4) {
+			c.n = (size_t)w4 * h4;
+			c.b.reset(new ColBlk[c.n]);
+		}
 		c.shape.resize(mb.size());
 		for (size_t i = 0; i < mb.size(); ++i) c.shape[i] = (uint8_t)((mb[i].cflags >> MBF_SHAPE_SHIFT) & 3);
-		for (size_t g = 0; g < c.b.size(); ++g) {
+		for (size_t g = 0; g < c.n; ++g) {
 			ColBlk &o = c.b[g];
 			int l = ref[0][g] >= 0 ? 0 : (ref[1][g] >= 0 ? 1 : -1);
 			o.pad = 0;
@@ -344,7 +349,7 @@ public:
 				else if (col_shape == SHAPE_16x8) { cx = 0; cy = y & 2; }
 				else if (col_shape == SHAPE_8x16) { cx = x & 2; cy = 0; }
 				bool col_zero = false;
-				if (col && col_short_term && !col->b.empty()) {
+				if (col && col_short_term && col->n) {
 					const ColBlk &cb = col->b[(size_t)(gy + cy) * w4 + gx + cx];
 					col_zero = cb.ref == 0 && cb.mv[0] >= -1 && cb.mv[0] <= 1 && cb.mv[1] >= -1 && cb.mv[1] <= 1;
 				}
@@ -367,7 +372,7 @@ public:
 				int i = y * 4 + x;
 				out.ref[i][0] = 0; out.ref[i][1] = 0;
 				out.mv[i][0][0] = out.mv[i][0][1] = out.mv[i][1][0] = out.mv[i][1][1] = 0;
-				if (!col || col->b.empty()) continue;
+				if (!col || !col->n) continue;
 				const ColBlk &cb = col->b[(size_t)(gy + cy) * w4 + gx + cx];
 				if (cb.ref < 0) continue;
 				int r0 = 0;
