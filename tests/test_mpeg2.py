@@ -117,3 +117,19 @@ def test_cuda_frame_out_order_does_not_depend_on_the_pool(name, outbuf):
     data, golden = _golden(name)
     assert m2dec_b200.decode_file("mpeg2", data, outbuf=outbuf) == golden
     assert m2dec_b200.decode_file("mpeg2", data, outbuf=outbuf, device_md5=True) == golden
+
+
+@pytest.mark.parametrize("name", streams.MPEG2_GOLDEN)
+@pytest.mark.parametrize("outbuf", [-1, 0])
+def test_frame_out_order_in_emptify_mode(name, outbuf):
+    """The reference application's other loop (m2decoder.h:149-152: collect every frame that is due before decoding on)
+    sees the same frames in the same order."""
+    from m2dec_b200.decoder import M2Decoder, frame_md5
+    data, golden = _golden(name)
+    md5s = []
+    dec = M2Decoder("mpeg2", data, tap=util.oracle_tap, device_off=True, outbuf=outbuf)
+    try:
+        dec.run(lambda f: md5s.append(frame_md5(f)), emptify=True)
+    finally:
+        dec.close()
+    assert md5s == golden
