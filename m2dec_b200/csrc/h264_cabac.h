@@ -259,7 +259,9 @@ public:
 	// residual_block_cabac (7.3.5.3.3).  lv[0..maxc) holds the levels in scan order (written
 	// when decoding, read when encoding).  cbf_inc < 0: coded_block_flag is not coded (cat 5).
 	// Returns the number of non-zero levels.
-	int residual(int cat, int cbf_inc, int16_t *lv, int maxc) {
+	// scan (decoding only): level k of the scan goes to lv[scan[k]] instead of lv[k] -- the decoder hands over the
+	// zeroed coefficient record and the raster position of every scan index, so only the non-zero levels are stored.
+	int residual(int cat, int cbf_inc, int16_t *lv, int maxc, const uint8_t *scan = nullptr) {
 		int last_nz = -1;
 		for (int i = 0; i < maxc; ++i) if (lv[i]) last_nz = i;
 		if (cbf_inc >= 0 && !e.bin(cabac_cbf_base[cat] + cbf_inc, last_nz >= 0)) return 0;
@@ -276,7 +278,8 @@ public:
 		int eq1 = 0, gt1 = 0;
 		const int abs_base = cabac_abs_base[cat], gt1_max = cat == 3 ? 3 : 4;
 		for (int k = n - 1; k >= 0; --k) {
-			const int v = lv[idx[k]], a = v < 0 ? -v : v;
+			const int at = scan ? scan[idx[k]] : idx[k];
+			const int v = lv[at], a = v < 0 ? -v : v;
 			int m = 1;
 			if (e.bin(abs_base + (gt1 ? 0 : (eq1 < 3 ? 1 + eq1 : 4)), a > 1)) {
 				const int c = abs_base + 5 + (gt1 < gt1_max ? gt1 : gt1_max);
@@ -288,7 +291,7 @@ public:
 				eq1++;
 			}
 			if (m > 32767) m = 32767;
-			lv[idx[k]] = (int16_t)(e.bypass(v < 0) ? -m : m);
+			lv[at] = (int16_t)(e.bypass(v < 0) ? -m : m);
 		}
 		return n;
 	}

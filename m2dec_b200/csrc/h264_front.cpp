@@ -1299,13 +1299,9 @@ private:
 				const int x4 = (q & 1) * 2, y4 = (q >> 1) * 2;
 				int total = 0;
 				if (cbp & (1 << q)) {
-					int16_t lv[64];
-					memset(lv, 0, sizeof(lv));
-					total = cs_.residual(5, -1, lv, 64);
 					const size_t at = coef_used_;
 					for (int r = 0; r < 4; ++r) new_record();
-					int16_t *rec = &coefs_[at];      // 64 levels, raster 8x8
-					for (int i = 0; i < 64; ++i) rec[zigzag8x8[i]] = lv[i];
+					total = cs_.residual(5, -1, &coefs_[at], 64, zigzag8x8);      // 64 levels, raster 8x8
 					m.nz |= 0xfu << (1 + 4 * q);
 					if (total > 15) total = 15;
 				}
@@ -1344,13 +1340,9 @@ private:
 			if (!(cbp & (1 << (k >> 2)))) { nnz[y4 * 4 + x4] = 0; continue; }
 			int total;
 			if (cabac_) {
-				int16_t lv[16];
-				memset(lv, 0, sizeof(lv));
-				total = cs_.residual(i16 ? 1 : 2, ctx_.cabac_inc_cbf_luma(x4, y4, intra), lv, i16 ? 15 : 16);
-				if (total) {
-					int16_t *rec = new_record();
-					for (int i = 0; i < (i16 ? 15 : 16); ++i) rec[zigzag4x4[i + (i16 ? 1 : 0)]] = lv[i];
-				}
+				// (the levels go straight into a record, which is handed back when the block turns out empty)
+				total = cs_.residual(i16 ? 1 : 2, ctx_.cabac_inc_cbf_luma(x4, y4, intra), new_record(), i16 ? 15 : 16, zigzag4x4 + (i16 ? 1 : 0));
+				if (!total) coef_used_ -= 16;
 			} else {
 				int nc = ctx_.cavlc_nc(mbx, mby, 0, x4, y4, slice_num_);
 				auto rec = [this]() { return new_record(); };
@@ -1391,13 +1383,8 @@ private:
 					int x = b & 1, y = b >> 1;
 					int total;
 					if (cabac_) {
-						int16_t lv[16];
-						memset(lv, 0, sizeof(lv));
-						total = cs_.residual(4, ctx_.cabac_inc_cbf_chroma_ac(c, x, y, intra), lv, 15);
-						if (total) {
-							int16_t *rec = new_record();
-							for (int i = 0; i < 15; ++i) rec[zigzag4x4[i + 1]] = lv[i];
-						}
+						total = cs_.residual(4, ctx_.cabac_inc_cbf_chroma_ac(c, x, y, intra), new_record(), 15, zigzag4x4 + 1);
+						if (!total) coef_used_ -= 16;
 					} else {
 						int nc = ctx_.cavlc_nc(mbx, mby, 1 + c, x, y, slice_num_);
 						total = residual_block(nc, 15, [this]() { return new_record(); }, zigzag4x4, 1);
