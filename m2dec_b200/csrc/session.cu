@@ -111,7 +111,8 @@ void cache_trim(size_t keep) {
 }  // namespace
 
 // Release every buffer on the process-wide free lists (device and page-locked host memory of closed sessions).
-extern "C" void b2_cache_trim(void) { cache_trim(0); }
+static void pool_drain();
+extern "C" void b2_cache_trim(void) { pool_drain(); cache_trim(0); }
 
 struct StageSlot {
 	uint8_t *host;
@@ -142,6 +143,7 @@ struct b2_session {
 	uint64_t launches;
 	uint64_t h2d_bytes, d2h_bytes;
 	bool check_records;             // run b2_*_picture_check on every submitted picture (default)
+	bool built;                     // session_build went through (only such a session is parked for the next stream)
 	// Digest mode (b2_session_set_md5): every reconstructed picture is hashed on the device (md5.cu), on one of a
 	// few side streams, and only its 16-byte MD5 comes back; the pixels stay in HBM.
 	bool md5_on;
@@ -206,6 +208,17 @@ static int slot_grow(b2_session *s, StageSlot *sl, size_t bytes) {
 	return 0;
 }
 
+// Parked sessions.  A stream that ends leaves its session -- two streams, ~50 events, frame pool, staging slots -- to the
+// next stream of the same geometry instead of tearing it down: with closed GOPs or short clips as the unit of work a
+// session lives for a dozen pictures, and creating its streams and events cost 0.07-0.1 ms per picture with sixteen
+// threads doing the same (the driver serialises them).  b2_cache_trim() frees the parked sessions too.
+namespace {
+std::mutex g_pool_mu;
+std::vector<b2_session *> g_pool;
+constexpr size_t kPoolMax = 64;
+const bool g_pool_on = getenv("B2_NO_SESSION_POOL") == nullptr;
+}  // namespace
+
 static int session_build(b2_session *s) {
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	B2_CUDA_OK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
@@ -227,6 +240,7 @@ static int session_build(b2_session *s) {
 }
 
 extern "C" void b2_session_destroy(b2_session *s);
+static void session_free(b2_session *s);
 
 extern "C" int b2_session_create(int cuda_device, int codec, int width, int height, int nframes, b2_session **out) {
 	if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || nframes <= 0) {
@@ -240,6 +254,31 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 	}
 	B2_CUDA_OK(cudaSetDevice(cuda_device));
 	if (nframes > 64) { set_error("b2_session_create: at most 64 frames"); return -1; }
+	{
+		b2_session *parked = nullptr;
+		{
+			std::lock_guard<std::mutex> lk(g_pool_mu);
+			for (size_t i = 0; i < g_pool.size(); ++i) {
+				b2_session *c = g_pool[i];
+				if (c->dev == cuda_device && c->codec == codec && c->width == width && c->height == height && c->nframes == nframes) {
+					parked = c;
+					g_pool.erase(g_pool.begin() + i);
+					break;
+				}
+			}
+		}
+		if (parked) {
+			// (session_park left it idle and in its initial state; the frames start out black like a new session's)
+			parked->trace.begin();
+			if (cudaMemsetAsync(parked->frames, 0, parked->frame_bytes * parked->nframes, parked->stream) == cudaSuccess) {
+				parked->trace.lap(T_CREATE);
+				*out = parked;
+				return 0;
+			}
+			cudaGetLastError();
+			session_free(parked);
+		}
+	}
 	b2_session *s = new b2_session();
 	memset(s, 0, sizeof(*s));
 	s->dev = cuda_device;
@@ -256,30 +295,23 @@ extern "C" int b2_session_create(int cuda_device, int codec, int width, int heig
 		b2_session_destroy(s);
 		return -1;
 	}
+	s->built = true;
 	s->trace.lap(T_CREATE);
 	*out = s;
 	return 0;
 }
 
-extern "C" void b2_session_destroy(b2_session *s) {
-	if (!s) return;
-	if (g_trace && s->trace.pictures) {
-		char line[768];
-		int n = snprintf(line, sizeof(line), "m2dec_b200 trace: %llu pictures, us per picture:", (unsigned long long)s->trace.pictures);
-		for (int k = 0; k < T_N; ++k) n += snprintf(line + n, sizeof(line) - n, " %s %.1f,", g_trace_names[k], s->trace.us[k] / s->trace.pictures);
-		fprintf(stderr, "%s\n", line);
-	}
+// Releases everything a (possibly partly built) session holds; its streams have been drained or never used.
+static void session_free(b2_session *s) {
 	cudaSetDevice(s->dev);
-	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (int i = 0; i < NSLOT; ++i) {
 		cache_put(s->dev, true, s->slots[i].cap_host, s->slots[i].host);
 		cache_put(s->dev, false, s->slots[i].cap_dev, s->slots[i].dev);
 		if (s->slots[i].done) cudaEventDestroy(s->slots[i].done);
 		if (s->slots[i].t0) { cudaEventDestroy(s->slots[i].t0); cudaEventDestroy(s->slots[i].t1); }
 	}
-	if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
 	for (int i = 0; i < 12; ++i)
-		if (s->md5_streams[i]) { cudaStreamSynchronize(s->md5_streams[i]); cudaStreamDestroy(s->md5_streams[i]); }
+		if (s->md5_streams[i]) cudaStreamDestroy(s->md5_streams[i]);
 	// (through the free lists: cudaMalloc / cudaFree would wait for every hash in flight on the device)
 	cache_put(s->dev, false, s->md5_dev_alloc, s->md5_dev);
 	cache_put(s->dev, true, s->md5_host_alloc, s->md5_host);
@@ -294,7 +326,58 @@ extern "C" void b2_session_destroy(b2_session *s) {
 	if (s->stream) cudaStreamDestroy(s->stream);
 	cudaGetLastError();
 	delete s;
+}
+
+// Back to the state b2_session_create hands out (the session is idle: its streams were synchronised), then parked.
+static bool session_park(b2_session *s) {
+	if (!g_pool_on || !s->built) return false;
+	memset(s->frame_written, 0, sizeof(s->frame_written));
+	memset(s->host_luma, 0, sizeof(s->host_luma));
+	memset(s->host_chroma, 0, sizeof(s->host_chroma));
+	memset(s->host_state, 0, sizeof(s->host_state));
+	memset(s->eager, 0, sizeof(s->eager));
+	memset(s->md5_pending, 0, sizeof(s->md5_pending));
+	for (int i = 0; i < NSLOT; ++i) s->slots[i].pending = false;
+	s->next_slot = 0;
+	s->launches = s->h2d_bytes = s->d2h_bytes = 0;
+	s->check_records = true;
+	s->md5_on = false;
+	s->md5_next = 0;
+	s->md5_stride = s->md5_left = s->md5_top = s->md5_w = s->md5_h = 0;
+	s->trace = Trace();
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	if (g_pool.size() >= kPoolMax) return false;
+	g_pool.push_back(s);
+	return true;
+}
+
+extern "C" void b2_session_destroy(b2_session *s) {
+	if (!s) return;
+	if (g_trace && s->trace.pictures) {
+		char line[768];
+		int n = snprintf(line, sizeof(line), "m2dec_b200 trace: %llu pictures, us per picture:", (unsigned long long)s->trace.pictures);
+		for (int k = 0; k < T_N; ++k) n += snprintf(line + n, sizeof(line) - n, " %s %.1f,", g_trace_names[k], s->trace.us[k] / s->trace.pictures);
+		fprintf(stderr, "%s\n", line);
+	}
+	cudaSetDevice(s->dev);
+	bool idle = true;
+	if (s->stream) idle &= cudaStreamSynchronize(s->stream) == cudaSuccess;
+	if (s->copy_stream) idle &= cudaStreamSynchronize(s->copy_stream) == cudaSuccess;
+	for (int i = 0; i < 12; ++i)
+		if (s->md5_streams[i]) idle &= cudaStreamSynchronize(s->md5_streams[i]) == cudaSuccess;
+	cudaGetLastError();
+	if (idle && session_park(s)) return;       // (a session whose work ended in an error is not kept)
+	session_free(s);
 	cache_trim(kCacheKeepBytes);
+}
+
+static void pool_drain() {
+	std::vector<b2_session *> all;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		all.swap(g_pool);
+	}
+	for (b2_session *s : all) session_free(s);
 }
 
 // Obtain a staging slot of at least `bytes`, waiting for its previous use to drain.

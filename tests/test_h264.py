@@ -170,3 +170,21 @@ def test_oracle_1080p_high_cabac_b_slice():
     data = streams.generate("h264", "mbw=120 mbh=68 frames=4 seed=44 crop_bottom=8 refs=2 bframes=2 cabac=1 profile=100 "
                                     "transform8x8=1 weighted_pred=1 weighted_bipred=1 direct_spatial=0")
     assert util.oracle_md5("h264", data) == util.ref_md5(data, "264")
+
+
+@pytest.mark.gpu
+def test_cuda_parked_sessions_start_clean():
+    """A stream's device session is parked when the stream ends and handed to the next stream of the same geometry
+    (session.cu: session_park): streams of one geometry decoded back to back -- frames, then digests, then frames again,
+    with another geometry in between -- give the MD5s a first decode gives, and b2_cache_trim frees the parked sessions."""
+    import m2dec_b200
+    from m2dec_b200 import _native as L
+    names = ["h264_basic", "h264_refs3", "h264_b_spatial", "h264_cabac_ip"]
+    want = {n: _golden(n)[1] for n in names}
+    for rnd in range(3):
+        for n in names:
+            data = _golden(n)[0]
+            assert m2dec_b200.decode_file("h264", data, device_md5=(rnd == 1)) == want[n], (rnd, n)
+    L.lib.b2_cache_trim()
+    for n in names:
+        assert m2dec_b200.decode_file("h264", _golden(n)[0]) == want[n], n
