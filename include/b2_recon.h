@@ -237,8 +237,11 @@ int b2_device_count(void);                           /* <0: CUDA unavailable    
 const char *b2_last_error(void);
 int b2_session_create(int cuda_device, int codec, int width, int height, int nframes, b2_session **out);
 void b2_session_destroy(b2_session *s);
-/* Closed sessions leave their device / page-locked buffers on a process-wide free list (at most 4 GiB of each
- * kind is kept) so that the next session does not pay cudaMalloc; this frees all of them.                    */
+/* A destroyed session is parked whole (streams, events, frame pool, staging slots; at most 64 sessions) for the
+ * next b2_session_create with the same device, codec, size and frame count, which gets it back in its initial state
+ * with black frames; what is not parked leaves its device / page-locked buffers on a process-wide free list (at
+ * most 4 GiB of each kind is kept) so that the next session does not pay cudaMalloc.  This frees all of it.
+ * B2_NO_SESSION_POOL=1 in the environment switches the parking off.                                             */
 void b2_cache_trim(void);
 /* Asynchronous: copies the picture's SoA into pinned staging, enqueues H2D + kernels.     */
 int b2_session_submit_mpeg2(b2_session *s, const b2_m2_picture *pic);
