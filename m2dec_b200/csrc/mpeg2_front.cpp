@@ -533,7 +533,7 @@ private:
 		} else {
 			mv = *pred >> shift;
 		}
-		*pred = (int16_t)(mv << shift);
+		*pred = (int16_t)(mv * (1 << shift));   // (not mv << shift: mv may be negative)
 		return mv;
 	}
 
@@ -629,7 +629,7 @@ private:
 			if (dc < 0) dc = 0;
 			else if (dc > dc_max) dc = dc_max;
 		}
-		return dc << (3 - intra_dc_precision_);
+		return dc * (1 << (3 - intra_dc_precision_));   // (a damaged stream can drive the predictor negative: no shift)
 	}
 
 	void macroblock() {
